@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — one JSON line for the archive-analytics path on B200.
+
+READ THIS FIRST: BASELINE.json's metric is literally "N/A: no GPU hot path"; the
+reference is a web app whose largest possible archive is ~6.5k entries.  The metric below
+("archive entries analysed per second") is this repo's own, defined on the SURVEY §7 fallback
+scope, and the headline workload is ~1700x beyond what the reference can hold.  `config`
+carries a measurement at the reference-reachable maximum too (`reference_scale`), where the GPU
+end-to-end call is NOT faster than one CPU core.  vs_baseline is null: nothing is published.
+
+A step = one pass of the path over one batch: computeArchiveShowStats for every show, the daily
+groups and the 19 metric summaries per day (public/app.js:3401-3502, :3898-3953).
+  value : entries/s, table resident in HBM, kernels only (CUDA events on the launch stream)
+  e2e   : entries/s through pie_archive_analytics_host (HOST buffers in, HOST results out,
+          H2D + kernels + D2H inside the timed region)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+METRIC = "archive_entries_per_s"
+UNIT = "entries/s"
+DEFAULT_SHOWS = 1 << 20  # ~11 M entries; the columns one step reads are ~0.45 GB, well above the 126 MB L2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shows", type=int, default=DEFAULT_SHOWS, help="shows per GPU (weak scaling)")
+    ap.add_argument("--tz", type=int, default=-480, help="fixed local-zone offset in minutes east of UTC")
+    ap.add_argument("--cpu-sample-shows", type=int, default=1 << 18)
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.002):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.period = period_s
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # NVML missing: report it, do not invent clocks
+            self.nv = None
+            self.err = repr(e)
+
+    def sample(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            names = {
+                "hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+                "hw_power_brake_slowdown": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown,
+                "applications_clocks_setting": nv.nvmlClocksEventReasonApplicationsClocksSetting,
+            }
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample()
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": self.err}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def analytics_bytes(table, n_groups: int):
+    """Algorithmic bytes of one step: every input byte the path must read once + every output byte
+    it must write once.  Returns (show_stats_bytes, daily_bytes)."""
+    from sph_pie_b200 import _lib
+
+    S, E = table.n_shows, table.n_entries
+    cols = [table.entry_cols[c] for c in ("status", "launched", "primary_issue")]
+    stats_in = sum(c.nbytes() for c in cols) + 9 * E + 4 * (S + 1)
+    stats_out = (4 * _lib.PIE_SI_COUNT + 8 * _lib.PIE_SF_COUNT) * S
+    daily_in = 8 * S + (4 * 4 + 8 * 15) * S  # created_at + the 4 i32 / 15 f64 planes the 19 metrics read
+    daily_out = 12 * S + (8 + 4) * n_groups + (3 * 8 + 4) * _lib.PIE_N_METRICS * n_groups
+    return stats_in + stats_out, daily_in + daily_out
+
+
+def cpu_baseline_run(host_table, tz, nthreads, min_seconds=1.0, max_reps=8):
+    """Times the C oracle (oracle/pie_oracle.c) over `host_table`; returns (entries/s, reps, seconds)."""
+    import oracle_c
+    from sph_pie_b200.ops import HostOutputs
+
+    hout = HostOutputs(host_table.n_shows)
+    oracle_c.archive_analytics(host_table, tz, nthreads, hout)  # warm caches / page in
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        _, _, rc, _ = oracle_c.archive_analytics(host_table, tz, nthreads, hout)
+        assert rc == 0
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds or reps >= max_reps:
+            return host_table.n_entries * reps / dt, reps, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host CPU.  The reference itself is
+    JavaScript and cannot run here (no JS engine), so this is the C port (kind "port")."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import oracle_c
+    from sph_pie_b200.synth import synth_archive
+
+    oracle_c.build()
+    threads = oracle_c.max_threads()
+    shows = min(args.shows, args.cpu_sample_shows)
+    from sph_pie_b200.ops import HostOutputs
+
+    table = synth_archive(shows, seed=1234, device="cpu")
+    hout = HostOutputs(table.n_shows)
+    for _ in range(max(args.warmup, 1)):
+        oracle_c.archive_analytics(table, args.tz, threads, hout)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, rc, _ = oracle_c.archive_analytics(table, args.tz, threads, hout)
+        assert rc == 0
+    dt = time.perf_counter() - t0
+    value = table.n_entries * args.steps / dt
+    sample = f"{shows} shows / {table.n_entries} entries per step, C port of the path (oracle/pie_oracle.c), " \
+             f"show statistics on {threads} threads, daily grouping on 1"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32/f64", "data": "synthetic",
+        "config": workload_config(args, shows, table.n_entries),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, shows, entries):
+    return {
+        "workload": f"synthetic archive: {shows} shows x 0..21 entries ({entries} entries) per GPU, <=5 shows/day, "
+                    "show statistics + daily groups + 19 metric summaries",
+        "shows_per_gpu": shows, "entries_per_gpu": entries, "tz_offset_minutes": args.tz,
+        "l2_policy": "inputs larger than L2 (the columns a step reads are ~0.45 GB per GPU vs 126 MB L2)",
+        "baseline_metric": "N/A: no GPU hot path (BASELINE.json); metric defined by this repo, see DESIGN.md",
+    }
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: sph_pie_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from sph_pie_b200 import _lib, ops
+    from sph_pie_b200.synth import synth_archive
+
+    _lib.init(local)
+    lib = _lib.load()
+
+    # each rank owns a disjoint range of days (weak scaling, no data-path collective)
+    days_per_rank = (args.shows + 4) // 5
+    table = synth_archive(args.shows, seed=1234 + rank, device=dev, start_ms=1704067200000 + rank * days_per_rank * 86400000)
+    S, E = table.n_shows, table.n_entries
+    bufs = ops.DailyBuffers(S, E, dev)
+
+    def step():
+        ops.show_stats_dev(table, bufs)
+        ops.daily_summary_dev(table, bufs, args.tz)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    assert int(bufs.status[0]) == 0
+    n_groups = int(bufs.n_groups)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: resident inputs, CUDA events on torch's current stream (the launch stream)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = int(lib.pie_kernel_launch_count())
+    barrier()
+    with ClockSampler(local) as clocks:
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for k in range(args.steps):
+            ev[k][0].record()
+            ops.show_stats_dev(table, bufs)
+            ev[k][1].record()
+            ops.daily_summary_dev(table, bufs, args.tz)
+            ev[k][2].record()
+        t_end.record()
+        clocks.sample()
+        barrier()
+    launches = int(lib.pie_kernel_launch_count()) - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    stats_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    daily_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    host = table.to("cpu").pin()
+    hout = ops.HostOutputs(S, pinned=True)
+    for _ in range(3):
+        ops.archive_analytics(host, args.tz, hout)
+    h2d, d2h = _lib.last_transfer_bytes()
+    e2e_steps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ops.archive_analytics(host, args.tz, hout)  # returns after the D2H copies have completed
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([total_ms, e2e_s, float(E)], dtype=torch.float64, device=dev)
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, e2e_s, total_entries = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        total_entries = float(E)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    value = total_entries * args.steps / (total_ms * 1e-3)
+    e2e_value = total_entries * e2e_steps / e2e_s
+    stats_bytes, daily_bytes = analytics_bytes(table, n_groups)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = stats_bytes / (stats_ms * 1e-3) / 1e9
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32/f64", "data": "synthetic",
+        "config": workload_config(args, S, E),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "pie_archive_analytics_host (pinned host buffers in and out)"},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": {
+            "bound": "hbm", "kernel": "show statistics (classify_entries_kernel + reduce_shows_kernel)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": stats_bytes, "ms_per_launch": stats_ms,
+            "bytes_per_entry": stats_bytes / max(E, 1),
+            "daily": {"ms_per_step": daily_ms, "algorithmic_bytes": daily_bytes,
+                      "achieved_gbs": daily_bytes / (daily_ms * 1e-3) / 1e9},
+        },
+    }
+
+    # ---- CPU baseline (rank 0, N=1 only): the C port on one core, bounded sample of the same workload
+    if world == 1:
+        sample_shows = min(S, args.cpu_sample_shows)
+        sample = host.slice_shows(0, sample_shows)
+        v, reps, secs = cpu_baseline_run(sample, args.tz, 1, min_seconds=2.0)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"first {sample_shows} shows ({sample.n_entries} entries) of the workload, "
+                                         f"{reps} passes in {secs:.2f} s, oracle/pie_oracle.c single thread"}
+        out["config"]["reference_scale"] = reference_scale(args, dev)
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def reference_scale(args, dev):
+    """The same step at the largest archive the reference's own rules allow (310 shows x <=21
+    entries): GPU end-to-end vs one CPU core.  Reported so nobody reads the headline
+    as a speed-up of the reference."""
+    import torch
+
+    import oracle_c
+    from sph_pie_b200 import ops
+    from sph_pie_b200.synth import synth_archive
+
+    small = synth_archive(310, seed=99, device="cpu")
+    pinned = small.pin()
+    hout = ops.HostOutputs(small.n_shows, pinned=True)
+    for _ in range(5):
+        ops.archive_analytics(pinned, args.tz, hout)
+    n = 200
+    t0 = time.perf_counter()
+    for _ in range(n):
+        ops.archive_analytics(pinned, args.tz, hout)
+    gpu_us = (time.perf_counter() - t0) / n * 1e6
+    oracle_c.archive_analytics(small, args.tz, 1)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        oracle_c.archive_analytics(small, args.tz, 1)
+    cpu_us = (time.perf_counter() - t0) / n * 1e6
+    return {"shows": small.n_shows, "entries": small.n_entries, "gpu_e2e_us_per_call": gpu_us,
+            "cpu_port_1core_us_per_call": cpu_us,
+            "note": "at the reference's maximum size the GPU call is launch/copy-latency bound"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,184 @@
+/* sph_pie_b200.h — C ABI of the B200 (sm_100a) archive-analytics / export-row path.
+ *
+ * IMPORTANT CONTEXT.  The reference (sphereisaiahmin-dev/sph-pie) is a Node/Express web app with
+ * no FFI boundary and no data-parallel hot path (BASELINE.json).  This header is the
+ * boundary a maintainer WOULD bind if the reference's only bulk pure functions were moved off the
+ * JS heap: each entry point names the JavaScript function(s) it replaces.  INTEGRATION.md shows the
+ * N-API stub.  Nothing here accelerates the reference at the data sizes it can reach (<= ~6.5k
+ * entries); see DESIGN.md §0.
+ *
+ * Conventions
+ *  - plain C, no torch / CUDA types in signatures; `stream` is a cudaStream_t passed as void*
+ *    (NULL = the legacy default stream).
+ *  - every function returns PIE_OK (0) or a negative pie_status; pie_last_error() gives the text.
+ *  - "host" entry points take HOST pointers and do H2D + kernels + D2H themselves;
+ *    "dev" entry points take DEVICE pointers (inputs already resident in HBM) and only enqueue
+ *    kernels on `stream`.
+ *
+ * Data layout ("archive table", Arrow-style struct-of-arrays)
+ *  - a string column is (offsets int32[n+1], data uint8[]) holding UTF-8; value i is
+ *    data[offsets[i] .. offsets[i+1]).  JS null / undefined / '' are all the empty string, which is
+ *    what every function on this path does with them (`x || ''`).
+ *  - a string-list column (crew, actions) is list_offsets int32[n+1] into a string column.
+ *  - numbers are IEEE-754 binary64 (JS Number); "absent / null" is a separate validity byte for
+ *    delaySec (the path distinguishes null from NaN) and NaN for timestamps (the path only asks
+ *    Number.isFinite of them).
+ *  - entries of show s are rows entry_offsets[s] .. entry_offsets[s+1] of the entry columns.
+ *  The schema is the provider-normalised show (server/storage/sqlProvider.js:361-409): every text
+ *  field is a string, delaySec is number|null, actions/crew are string arrays.
+ */
+#ifndef SPH_PIE_B200_H
+#define SPH_PIE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIE_ABI_VERSION 1
+#define PIE_N_ISSUES 10   /* public/app.js:1-13 PRIMARY_ISSUES */
+#define PIE_N_METRICS 19  /* public/app.js:21-86 ARCHIVE_METRIC_DEFS (9) + issue:<name> (10), :3955-3994 */
+#define PIE_N_EXPORT_COLUMNS 24 /* server/webhookDispatcher.js:15-19 EXPORT_COLUMNS */
+
+typedef enum pie_status {
+  PIE_OK = 0,
+  PIE_ERR_CUDA = -1,             /* a CUDA call failed; text in pie_last_error() */
+  PIE_ERR_INVALID_ARG = -2,      /* NULL pointer / negative size / inconsistent offsets */
+  PIE_ERR_RANGE = -3,            /* JS RangeError "Invalid time value" (public/app.js:3415 toISOString) */
+  PIE_ERR_UNSUPPORTED_DATE = -4, /* show.date/time not in the ECMA-262 date-time format; V8's legacy
+                                    Date.parse fallback is implementation-defined and not provided */
+  PIE_ERR_CAPACITY = -5,         /* caller's output buffer too small; required size is reported */
+  PIE_ERR_NO_DEVICE = -6         /* no sm_100 device visible: there is NO CPU fallback */
+} pie_status;
+
+typedef struct pie_strcol {
+  const int32_t* offsets; /* [n + 1], offsets[0] may be non-zero (sliced columns) */
+  const uint8_t* data;    /* UTF-8 bytes */
+} pie_strcol;
+
+typedef struct pie_strlistcol {
+  const int32_t* list_offsets; /* [n + 1] into items */
+  pie_strcol items;
+} pie_strlistcol;
+
+/* One batch of shows with their entries.  All pointers are host pointers for *_host entry points
+ * and device pointers for *_dev entry points.  Columns an entry point does not read may be NULL;
+ * each entry point lists what it reads. */
+typedef struct pie_archive_view {
+  int64_t n_shows;
+  int64_t n_entries;
+  const int32_t* entry_offsets; /* [n_shows + 1] */
+
+  /* show-level columns, n_shows rows */
+  pie_strcol show_id, show_date, show_time, show_label, lead_pilot, monkey_lead, show_notes;
+  pie_strlistcol crew;
+  const double* created_at;  /* ms since epoch; NaN when absent / not a finite number */
+  const double* archived_at; /* same */
+
+  /* entry-level columns, n_entries rows */
+  pie_strcol entry_id, unit_id, planned, launched, status, primary_issue, sub_issue, other_detail,
+      severity, root_cause, operator_name, battery_id, command_rx, notes;
+  pie_strlistcol actions;
+  const double* delay_sec;    /* value (may be NaN/Inf when delay_valid) */
+  const uint8_t* delay_valid; /* 0 = null/undefined, 1 = a JS number */
+  const double* entry_ts;     /* ms since epoch; NaN when absent */
+} pie_archive_view;
+
+/* ---- planes of the per-show statistics table -------------------------------------------------
+ * stats_i32 is int32[PIE_SI_COUNT][stride], stats_f64 is double[PIE_SF_COUNT][stride], plane-major
+ * (plane p of show s at p*stride + s), stride >= n_shows.  Fields mirror the object returned by
+ * computeArchiveShowStats (public/app.js:3939-3952).  A JS null is encoded as NaN in the f64
+ * planes and is also derivable: avg/max are null iff DELAY_COUNT==0, rates iff TOTAL==0. */
+enum {
+  PIE_SI_TOTAL = 0,        /* totalEntries */
+  PIE_SI_COMPLETED = 1,    /* completedCount */
+  PIE_SI_NO_LAUNCH = 2,    /* noLaunchCount */
+  PIE_SI_ABORT = 3,        /* abortCount */
+  PIE_SI_LAUNCHED = 4,     /* launchedCount */
+  PIE_SI_DELAY_COUNT = 5,  /* delayValues.length */
+  PIE_SI_ISSUE_COUNT0 = 6, /* issueCounts[PRIMARY_ISSUES[k]], k = 0..9 (0 = key absent) */
+  PIE_SI_ISSUE_FIRST0 = 16,/* entry index (within the show) that first produced issue k, -1 if none:
+                              recovers issueCounts' property insertion order */
+  PIE_SI_COUNT = 26
+};
+enum {
+  PIE_SF_DELAY_SUM = 0,       /* delaySum (left-to-right, initial 0) */
+  PIE_SF_AVG_DELAY = 1,       /* avgDelaySec */
+  PIE_SF_MAX_DELAY = 2,       /* maxDelaySec */
+  PIE_SF_COMPLETION_RATE = 3, /* completionRate */
+  PIE_SF_LAUNCH_RATE = 4,     /* launchRate */
+  PIE_SF_ABORT_RATE = 5,      /* abortRate */
+  PIE_SF_ISSUE_RATE0 = 6,     /* issueRates[PRIMARY_ISSUES[k]] */
+  PIE_SF_COUNT = 16
+};
+
+/* ---- planes of the per-day summary table -----------------------------------------------------
+ * One row per local calendar day that has >= 1 show (a "daily group", public/app.js:3401-3443),
+ * ascending by day start.  summary_f64 is double[PIE_DF_COUNT][PIE_N_METRICS][stride],
+ * summary_count is int32[PIE_N_METRICS][stride]; metric m in the order of ALL metric keys
+ * (ARCHIVE_METRIC_DEFS order, then issue:<PRIMARY_ISSUES[k]>).  average/min/max are NaN (JS null)
+ * when count == 0 (public/app.js:3480-3484). */
+enum { PIE_DF_AVERAGE = 0, PIE_DF_MIN = 1, PIE_DF_MAX = 2, PIE_DF_COUNT = 3 };
+
+#define PIE_DAY_NONE INT64_MIN /* show has no usable timestamp: skipped by buildArchiveDailyGroups */
+
+typedef struct pie_daily_out {
+  int64_t stride;            /* capacity in rows of every array below (>= n_shows is always enough) */
+  int64_t* show_day_start;   /* [stride] local-midnight ms of each show, PIE_DAY_NONE if skipped */
+  int32_t* show_order;       /* [stride] show indices, stably ordered by day start, skipped ones last */
+  int64_t* group_day_start;  /* [stride] group.timestamp */
+  int32_t* group_offsets;    /* [stride + 1] group g = show_order[group_offsets[g] .. group_offsets[g+1]) */
+  double* summary_f64;       /* [PIE_DF_COUNT][PIE_N_METRICS][stride] */
+  int32_t* summary_count;    /* [PIE_N_METRICS][stride] */
+  int64_t* n_groups;         /* [1] number of groups written */
+  int32_t* status;           /* [2] {pie_status, offending show index}: PIE_ERR_RANGE /
+                                PIE_ERR_UNSUPPORTED_DATE raised by a show, else {0, -1} */
+} pie_daily_out;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int pie_abi_version(void);
+const char* pie_last_error(void);
+/* Select the CUDA device for the calling thread and verify it is sm_100.  PIE_ERR_NO_DEVICE if
+ * there is none — callers must fail, not fall back. */
+int pie_init(int device);
+int pie_device_sm_count(void);
+/* Pinned host memory for the *_host entry points (pageable pointers also work, slower). */
+void* pie_host_alloc(uint64_t bytes);
+void pie_host_free(void* p);
+/* Bytes the most recent *_host call copied host->device and device->host (e2e accounting). */
+void pie_last_transfer_bytes(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* Cumulative number of CUDA kernels this library has launched in this process. */
+uint64_t pie_kernel_launch_count(void);
+
+/* ---- archive statistics: replaces computeArchiveShowStats (public/app.js:3898-3953), called per
+ * show from buildArchiveDailyGroups (:3429-3432).  Reads: entry_offsets, status, launched,
+ * primary_issue, delay_sec, delay_valid.
+ * `scratch` (dev variant): device buffer of pie_show_stats_scratch_bytes(n_entries) bytes. */
+uint64_t pie_show_stats_scratch_bytes(int64_t n_entries);
+int pie_show_stats_dev(const pie_archive_view* dev_view, int32_t* stats_i32, double* stats_f64,
+                       int64_t stride, void* scratch, void* stream);
+int pie_show_stats_host(const pie_archive_view* host_view, int32_t* stats_i32, double* stats_f64,
+                        int64_t stride);
+
+/* ---- daily groups + metric summaries: replaces buildArchiveDailyGroups (public/app.js:3401-3443,
+ * with getShowTimestamp :4092-4116 and parseShowDateTime :4118-4126 for ISO strings) and the
+ * numeric part of getOrCreateGroupMetricSummary (:3445-3502) for all PIE_N_METRICS metrics.
+ * `tz_offset_minutes`: the zone is a fixed offset east of UTC (setHours(0,0,0,0) is local time).
+ * Reads: the stats planes produced above, created_at, archived_at, show_date, show_time,
+ * entry_offsets, entry_ts.
+ * `scratch` (dev variant): device buffer of pie_daily_scratch_bytes(n_shows) bytes. */
+uint64_t pie_daily_scratch_bytes(int64_t n_shows);
+int pie_daily_summary_dev(const pie_archive_view* dev_view, const int32_t* stats_i32,
+                          const double* stats_f64, int64_t stats_stride, int32_t tz_offset_minutes,
+                          const pie_daily_out* dev_out, void* scratch, void* stream);
+/* Host variant runs show statistics + daily summary in one call (the reference computes both in
+ * buildArchiveDailyGroups); stats_* may be NULL if the caller only wants the summaries. */
+int pie_archive_analytics_host(const pie_archive_view* host_view, int32_t tz_offset_minutes,
+                               int32_t* stats_i32, double* stats_f64, int64_t stats_stride,
+                               const pie_daily_out* host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_PIE_B200_H */

@@ -1,0 +1,72 @@
+"""ctypes loader for oracle/libpie_oracle.so (the C restatement).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs, never by the product.
+It reuses the product's ctypes struct definitions so both sides see one layout."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import torch
+
+from sph_pie_b200 import _lib
+from sph_pie_b200.columnar import ArchiveTable
+from sph_pie_b200.ops import DailySummary, HostOutputs, ShowStats
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libpie_oracle.so")
+_so = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "pie_oracle.c")
+    if force or not os.path.exists(SO_PATH) or os.path.getmtime(SO_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libpie_oracle.so"], stdout=subprocess.DEVNULL)
+    return SO_PATH
+
+
+def load():
+    global _so
+    if _so is None:
+        if not os.path.exists(SO_PATH):
+            build()
+        so = C.CDLL(SO_PATH)
+        so.oracle_show_stats.restype = C.c_int
+        so.oracle_show_stats.argtypes = [C.POINTER(_lib.ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        so.oracle_daily_summary.restype = C.c_int
+        so.oracle_daily_summary.argtypes = [C.POINTER(_lib.ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.c_int32, C.POINTER(_lib.DailyOutC)]
+        so.oracle_max_threads.restype = C.c_int
+        _so = so
+    return _so
+
+
+def max_threads() -> int:
+    return int(load().oracle_max_threads())
+
+
+def show_stats(table: ArchiveTable, nthreads: int = 1, out: HostOutputs = None) -> ShowStats:
+    assert not table.is_cuda
+    S = table.n_shows
+    h = out if out is not None else HostOutputs(S)
+    view = table.view()
+    rc = load().oracle_show_stats(C.byref(view), h.stats_i32.data_ptr(), h.stats_f64.data_ptr(), h.S, nthreads)
+    assert rc == 0
+    return ShowStats(h.stats_i32[:, :S], h.stats_f64[:, :S])
+
+
+def archive_analytics(table: ArchiveTable, tz_offset_minutes: int = 0, nthreads: int = 1, out: HostOutputs = None):
+    """Returns (ShowStats, DailySummary, status_code, status_show)."""
+    assert not table.is_cuda
+    S = table.n_shows
+    h = out if out is not None else HostOutputs(S)
+    st = show_stats(table, nthreads, h)
+    view = table.view()
+    out = h.daily_out()
+    rc = load().oracle_daily_summary(C.byref(view), h.stats_i32.data_ptr(), h.stats_f64.data_ptr(), h.S,
+                                     tz_offset_minutes, C.byref(out))
+    if rc != 0:
+        return st, None, rc, int(h.status[1])
+    G = int(h.n_groups[0])
+    return st, DailySummary(G, h.show_day_start[:S], h.show_order[:S], h.group_day_start[:G], h.group_offsets[:G + 1],
+                            h.summary_f64[:, :, :G], h.summary_count[:, :G]), 0, -1

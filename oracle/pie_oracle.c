@@ -1,0 +1,391 @@
+/* pie_oracle.c — plain-C restatement of the reference's archive analytics on the columnar
+ * "archive table" layout of include/sph_pie_b200.h.
+ *
+ * TEST INFRASTRUCTURE ONLY: the checker for the CUDA path and the timed CPU baseline of bench.py.
+ * Nothing under sph_pie_b200/ links or loads this file.
+ *
+ * PARITY STATUS: parity unpinned (see oracle/pie_oracle.py header): no JS engine exists in this
+ * image, so this restatement is validated against oracle/pie_oracle.py (a second, independent
+ * restatement that works on JSON-shaped objects) and the reference's single fixture, not against
+ * outputs of the reference itself.
+ *
+ * Deliberately structured differently from the CUDA kernels (no classification byte, no radix
+ * sort): per-show loops straight over the strings, grouping by a merge sort.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/sph_pie_b200.h"
+
+#include <pthread.h>
+#include <unistd.h>
+
+static const char* const kIssues[PIE_N_ISSUES] = { /* public/app.js:1-13 */
+    "Tracking lost", "Failed to launch", "Command delay", "RF link", "Battery",
+    "Motor or prop", "Sensor or IMU", "Software or show control", "Operator input", "Other"};
+
+static int lower_eq(const uint8_t* s, int n, const char* lit) {
+  int l = (int)strlen(lit);
+  if (n != l) return 0;
+  for (int i = 0; i < n; ++i) {
+    uint8_t c = s[i];
+    if (c >= 'A' && c <= 'Z') c = (uint8_t)(c + 32);
+    if (c != (uint8_t)lit[i]) return 0;
+  }
+  return 1;
+}
+
+/* decode one UTF-8 code point at s[i]; returns its length (>=1) and the code point */
+static int utf8_at(const uint8_t* s, int i, int n, uint32_t* cp) {
+  uint8_t c = s[i];
+  if (c < 0x80) { *cp = c; return 1; }
+  if ((c & 0xE0) == 0xC0 && i + 1 < n) { *cp = ((c & 0x1Fu) << 6) | (s[i + 1] & 0x3Fu); return 2; }
+  if ((c & 0xF0) == 0xE0 && i + 2 < n) {
+    *cp = ((c & 0x0Fu) << 12) | ((s[i + 1] & 0x3Fu) << 6) | (s[i + 2] & 0x3Fu);
+    return 3;
+  }
+  if ((c & 0xF8) == 0xF0 && i + 3 < n) {
+    *cp = ((c & 0x07u) << 18) | ((s[i + 1] & 0x3Fu) << 12) | ((s[i + 2] & 0x3Fu) << 6) | (s[i + 3] & 0x3Fu);
+    return 4;
+  }
+  *cp = 0xFFFD;
+  return 1;
+}
+
+static int is_js_space(uint32_t cp) { /* ECMAScript WhiteSpace + LineTerminator */
+  return cp == 9 || cp == 10 || cp == 11 || cp == 12 || cp == 13 || cp == 32 || cp == 0xA0 || cp == 0x1680 ||
+         (cp >= 0x2000 && cp <= 0x200A) || cp == 0x2028 || cp == 0x2029 || cp == 0x202F || cp == 0x205F ||
+         cp == 0x3000 || cp == 0xFEFF;
+}
+
+/* String.prototype.trim on UTF-8: [*b, *e) shrinks to the trimmed range */
+static void js_trim(const uint8_t* s, int* b, int* e) {
+  int i = *b, end = *e;
+  while (i < end) {
+    uint32_t cp;
+    int l = utf8_at(s, i, end, &cp);
+    if (!is_js_space(cp)) break;
+    i += l;
+  }
+  /* walk forward remembering the end of the last non-space code point */
+  int last = i, j = i;
+  while (j < end) {
+    uint32_t cp;
+    int l = utf8_at(s, j, end, &cp);
+    j += l;
+    if (!is_js_space(cp)) last = j;
+  }
+  *b = i;
+  *e = last;
+}
+
+static double js_max2(double a, double b) {
+  if (a > b) return a;
+  if (b > a) return b;
+  return signbit(a) ? b : a;
+}
+static double js_min2(double a, double b) {
+  if (a < b) return a;
+  if (b < a) return b;
+  return signbit(a) ? a : b;
+}
+
+/* computeArchiveShowStats, public/app.js:3898-3953, for show s */
+static void show_stats_one(const pie_archive_view* v, int64_t s, int32_t* si, double* sf, int64_t stride) {
+  int e0 = v->entry_offsets[s], e1 = v->entry_offsets[s + 1];
+  int completed = 0, no_launch = 0, abort_n = 0, launched = 0, delay_n = 0;
+  int issue_n[PIE_N_ISSUES], issue_first[PIE_N_ISSUES];
+  for (int k = 0; k < PIE_N_ISSUES; ++k) { issue_n[k] = 0; issue_first[k] = -1; }
+  double sum = 0.0, mx = 0.0;
+  for (int e = e0; e < e1; ++e) {
+    const uint8_t* st = v->status.data + v->status.offsets[e];
+    int stn = v->status.offsets[e + 1] - v->status.offsets[e];
+    if (lower_eq(st, stn, "completed")) completed++;
+    else if (lower_eq(st, stn, "no-launch")) no_launch++;
+    else if (lower_eq(st, stn, "abort")) abort_n++;
+    if (lower_eq(v->launched.data + v->launched.offsets[e], v->launched.offsets[e + 1] - v->launched.offsets[e], "yes"))
+      launched++;
+    if (v->delay_valid[e] && isfinite(v->delay_sec[e])) {
+      double d = v->delay_sec[e];
+      sum = sum + d;
+      mx = delay_n ? js_max2(mx, d) : d;
+      delay_n++;
+    }
+    int b = v->primary_issue.offsets[e], en = v->primary_issue.offsets[e + 1];
+    js_trim(v->primary_issue.data, &b, &en);
+    if (en > b) {
+      int k = PIE_N_ISSUES - 1; /* 'Other' */
+      for (int q = 0; q < PIE_N_ISSUES; ++q) {
+        if ((int)strlen(kIssues[q]) == en - b && memcmp(kIssues[q], v->primary_issue.data + b, (size_t)(en - b)) == 0) {
+          k = q;
+          break;
+        }
+      }
+      if (issue_n[k] == 0) issue_first[k] = e - e0;
+      issue_n[k]++;
+    }
+  }
+  int total = e1 - e0;
+  si[PIE_SI_TOTAL * stride + s] = total;
+  si[PIE_SI_COMPLETED * stride + s] = completed;
+  si[PIE_SI_NO_LAUNCH * stride + s] = no_launch;
+  si[PIE_SI_ABORT * stride + s] = abort_n;
+  si[PIE_SI_LAUNCHED * stride + s] = launched;
+  si[PIE_SI_DELAY_COUNT * stride + s] = delay_n;
+  sf[PIE_SF_DELAY_SUM * stride + s] = sum;
+  sf[PIE_SF_AVG_DELAY * stride + s] = delay_n ? sum / delay_n : NAN;
+  sf[PIE_SF_MAX_DELAY * stride + s] = delay_n ? mx : NAN;
+  sf[PIE_SF_COMPLETION_RATE * stride + s] = total ? ((double)completed / total) * 100 : NAN;
+  sf[PIE_SF_LAUNCH_RATE * stride + s] = total ? ((double)launched / total) * 100 : NAN;
+  sf[PIE_SF_ABORT_RATE * stride + s] = total ? ((double)abort_n / total) * 100 : NAN;
+  for (int k = 0; k < PIE_N_ISSUES; ++k) {
+    si[(PIE_SI_ISSUE_COUNT0 + k) * stride + s] = issue_n[k];
+    si[(PIE_SI_ISSUE_FIRST0 + k) * stride + s] = issue_first[k];
+    sf[(PIE_SF_ISSUE_RATE0 + k) * stride + s] = total ? ((double)issue_n[k] / total) * 100 : NAN;
+  }
+}
+
+typedef struct {
+  const pie_archive_view* v;
+  int32_t* si;
+  double* sf;
+  int64_t stride, s0, s1;
+} stats_job;
+
+static void* stats_worker(void* arg) {
+  stats_job* j = (stats_job*)arg;
+  for (int64_t s = j->s0; s < j->s1; ++s) show_stats_one(j->v, s, j->si, j->sf, j->stride);
+  return NULL;
+}
+
+/* nthreads <= 1: sequential.  Shows are independent; threads take contiguous, entry-balanced
+ * ranges of shows and run the same per-show code. */
+int oracle_show_stats(const pie_archive_view* v, int32_t* si, double* sf, int64_t stride, int nthreads) {
+  const int64_t S = v->n_shows;
+  if (nthreads <= 1 || S < 2 * (int64_t)nthreads) {
+    for (int64_t s = 0; s < S; ++s) show_stats_one(v, s, si, sf, stride);
+    return 0;
+  }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
+  stats_job* jobs = (stats_job*)malloc(sizeof(stats_job) * (size_t)nthreads);
+  const int64_t E = v->entry_offsets[S];
+  int64_t s0 = 0;
+  for (int t = 0; t < nthreads; ++t) {
+    int64_t s1 = s0;
+    const int64_t target = (int64_t)((double)E * (t + 1) / nthreads);
+    if (t == nthreads - 1) s1 = S;
+    else while (s1 < S && v->entry_offsets[s1] < target) s1++;
+    jobs[t] = (stats_job){v, si, sf, stride, s0, s1};
+    pthread_create(&th[t], NULL, stats_worker, &jobs[t]);
+    s0 = s1;
+  }
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+  free(th);
+  free(jobs);
+  return 0;
+}
+
+int oracle_max_threads(void) {
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+
+/* ---- getShowTimestamp / parseShowDateTime (public/app.js:4092-4126) --------------------------- */
+static int64_t days_from_civil(int64_t y, int m, int d) {
+  y -= m <= 2;
+  int64_t era = (y >= 0 ? y : y - 399) / 400;
+  int64_t yoe = y - era * 400;
+  int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return era * 146097 + doe - 719468;
+}
+
+static int digits(const uint8_t* s, int n, int* out) {
+  int v = 0;
+  for (int i = 0; i < n; ++i) {
+    if (s[i] < '0' || s[i] > '9') return 0;
+    v = v * 10 + (s[i] - '0');
+  }
+  *out = v;
+  return 1;
+}
+
+/* 1 = parsed, 0 = NaN (illegal element value), -1 = outside the ECMA-262 grammar */
+static int parse_iso(const uint8_t* ds, int dn, const uint8_t* ts, int tn, int64_t tz_ms, double* out) {
+  char buf[64];
+  if (tn == 0) { ts = (const uint8_t*)"00:00"; tn = 5; }
+  if (dn + 1 + tn >= (int)sizeof(buf)) return -1;
+  memcpy(buf, ds, (size_t)dn);
+  buf[dn] = 'T';
+  memcpy(buf + dn + 1, ts, (size_t)tn);
+  int n = dn + 1 + tn;
+  const uint8_t* p = (const uint8_t*)buf;
+  int Y, M, D, h, mi, sec = 0, ms = 0;
+  if (n < 16) return -1;
+  if (!digits(p, 4, &Y) || p[4] != '-' || !digits(p + 5, 2, &M) || p[7] != '-' || !digits(p + 8, 2, &D) ||
+      p[10] != 'T' || !digits(p + 11, 2, &h) || p[13] != ':' || !digits(p + 14, 2, &mi))
+    return -1;
+  int pos = 16;
+  if (pos < n && p[pos] == ':') {
+    if (pos + 3 > n || !digits(p + pos + 1, 2, &sec)) return -1;
+    pos += 3;
+    if (pos < n && p[pos] == '.') {
+      if (pos + 4 > n || !digits(p + pos + 1, 3, &ms)) return -1;
+      pos += 4;
+    }
+  }
+  int has_off = 0;
+  int64_t off = 0;
+  if (pos < n) {
+    if (p[pos] == 'Z' && pos + 1 == n) has_off = 1;
+    else if ((p[pos] == '+' || p[pos] == '-') && pos + 6 == n && p[pos + 3] == ':') {
+      int oh, om;
+      if (!digits(p + pos + 1, 2, &oh) || !digits(p + pos + 4, 2, &om)) return -1;
+      if (oh > 23 || om > 59) return 0;
+      off = (int64_t)(oh * 60 + om) * 60000 * (p[pos] == '-' ? -1 : 1);
+      has_off = 1;
+    } else return -1;
+  }
+  if (M < 1 || M > 12 || D < 1 || D > 31 || h > 24 || mi > 59 || sec > 59) return 0;
+  if (h == 24 && (mi || sec || ms)) return 0;
+  int leap = (Y % 4 == 0) && (Y % 100 != 0 || Y % 400 == 0);
+  int dim = M == 2 ? (leap ? 29 : 28) : ((M == 4 || M == 6 || M == 9 || M == 11) ? 30 : 31);
+  if (D > dim) return -1;
+  int64_t local = ((days_from_civil(Y, M, D) * 24 + h) * 60 + mi) * 60000 + sec * 1000 + ms;
+  *out = (double)(local - (has_off ? off : tz_ms));
+  return 1;
+}
+
+typedef struct { int64_t day; int32_t show; } day_item;
+
+static void merge_sort(day_item* a, day_item* tmp, int64_t n) { /* stable */
+  if (n < 2) return;
+  int64_t h = n / 2;
+  merge_sort(a, tmp, h);
+  merge_sort(a + h, tmp, n - h);
+  if (a[h - 1].day <= a[h].day) return; /* halves already in order (archives usually arrive sorted) */
+  int64_t i = 0, j = h, k = 0;
+  while (i < h && j < n) tmp[k++] = (a[j].day < a[i].day) ? a[j++] : a[i++];
+  while (i < h) tmp[k++] = a[i++];
+  while (j < n) tmp[k++] = a[j++];
+  memcpy(a, tmp, (size_t)n * sizeof(day_item));
+}
+
+static double metric_value(const int32_t* si, const double* sf, int64_t stride, int m, int64_t s) {
+  switch (m) {
+    case 0: return si[PIE_SI_TOTAL * stride + s];
+    case 1: return si[PIE_SI_COMPLETED * stride + s];
+    case 2: return si[PIE_SI_NO_LAUNCH * stride + s];
+    case 3: return si[PIE_SI_ABORT * stride + s];
+    case 4: return sf[PIE_SF_AVG_DELAY * stride + s];
+    case 5: return sf[PIE_SF_MAX_DELAY * stride + s];
+    case 6: return sf[PIE_SF_COMPLETION_RATE * stride + s];
+    case 7: return sf[PIE_SF_LAUNCH_RATE * stride + s];
+    case 8: return sf[PIE_SF_ABORT_RATE * stride + s];
+    default: return sf[(PIE_SF_ISSUE_RATE0 + (m - 9)) * stride + s];
+  }
+}
+
+/* buildArchiveDailyGroups + getOrCreateGroupMetricSummary (public/app.js:3401-3502).
+ * Returns a pie_status; out->status mirrors it. */
+int oracle_daily_summary(const pie_archive_view* v, const int32_t* si, const double* sf, int64_t stride,
+                         int32_t tz_offset_minutes, const pie_daily_out* out) {
+  const int64_t S = v->n_shows, tz = (int64_t)tz_offset_minutes * 60000, DAY = 86400000LL;
+  day_item* items = (day_item*)malloc((size_t)(S > 0 ? S : 1) * sizeof(day_item) * 2);
+  int64_t nvalid = 0, nskip = 0;
+  int32_t* skipped = (int32_t*)malloc((size_t)(S > 0 ? S : 1) * sizeof(int32_t));
+  out->status[0] = 0;
+  out->status[1] = -1;
+  for (int64_t s = 0; s < S; ++s) {
+    double ts = NAN;
+    if (isfinite(v->created_at[s])) {
+      ts = v->created_at[s];
+    } else {
+      int parsed = 0;
+      if (v->show_date.offsets && v->show_date.offsets[s + 1] > v->show_date.offsets[s]) {
+        int tb = 0, te = 0;
+        if (v->show_time.offsets) { tb = v->show_time.offsets[s]; te = v->show_time.offsets[s + 1]; }
+        parsed = parse_iso(v->show_date.data + v->show_date.offsets[s],
+                           v->show_date.offsets[s + 1] - v->show_date.offsets[s],
+                           v->show_time.offsets ? v->show_time.data + tb : NULL, te - tb, tz, &ts);
+        if (parsed < 0) {
+          out->status[0] = PIE_ERR_UNSUPPORTED_DATE; out->status[1] = (int32_t)s;
+          free(items); free(skipped);
+          return PIE_ERR_UNSUPPORTED_DATE;
+        }
+      }
+      if (parsed == 0) {
+        if (v->archived_at && isfinite(v->archived_at[s])) ts = v->archived_at[s];
+        else if (v->entry_ts) {
+          int any = 0;
+          double best = 0;
+          for (int e = v->entry_offsets[s]; e < v->entry_offsets[s + 1]; ++e)
+            if (isfinite(v->entry_ts[e]) && (!any || v->entry_ts[e] < best)) { best = v->entry_ts[e]; any = 1; }
+          if (any) ts = best;
+        }
+      }
+    }
+    if (!isfinite(ts)) {
+      out->show_day_start[s] = PIE_DAY_NONE;
+      skipped[nskip++] = (int32_t)s;
+      continue;
+    }
+    int bad = fabs(ts) > 8.64e15;
+    int64_t start = 0, day = 0;
+    if (!bad) {
+      int64_t t = (int64_t)ts, local = t + tz;
+      day = local / DAY;
+      if (local % DAY < 0) day--;
+      start = day * DAY - tz;
+      if (start > 8640000000000000LL || start < -8640000000000000LL) bad = 1;
+    }
+    if (bad) {
+      out->status[0] = PIE_ERR_RANGE; out->status[1] = (int32_t)s;
+      free(items); free(skipped);
+      return PIE_ERR_RANGE;
+    }
+    out->show_day_start[s] = start;
+    items[nvalid].day = day;
+    items[nvalid].show = (int32_t)s;
+    nvalid++;
+  }
+  merge_sort(items, items + (S > 0 ? S : 1), nvalid);
+  int64_t G = 0;
+  for (int64_t i = 0; i < nvalid; ++i) {
+    out->show_order[i] = items[i].show;
+    if (i == 0 || items[i].day != items[i - 1].day) {
+      out->group_offsets[G] = (int32_t)i;
+      out->group_day_start[G] = items[i].day * DAY - tz;
+      G++;
+    }
+  }
+  out->group_offsets[G] = (int32_t)nvalid;
+  for (int64_t i = 0; i < nskip; ++i) out->show_order[nvalid + i] = skipped[i];
+  *out->n_groups = G;
+  const int64_t plane = (int64_t)PIE_N_METRICS * out->stride;
+  for (int64_t g = 0; g < G; ++g) {
+    for (int m = 0; m < PIE_N_METRICS; ++m) {
+      double sum = 0, mn = 0, mx = 0;
+      int n = 0;
+      for (int i = out->group_offsets[g]; i < out->group_offsets[g + 1]; ++i) {
+        double x = metric_value(si, sf, stride, m, out->show_order[i]);
+        if (isfinite(x)) {
+          sum = sum + x;
+          mn = n ? js_min2(mn, x) : x;
+          mx = n ? js_max2(mx, x) : x;
+          n++;
+        }
+      }
+      int64_t o = (int64_t)m * out->stride + g;
+      out->summary_f64[PIE_DF_AVERAGE * plane + o] = n ? sum / n : NAN;
+      out->summary_f64[PIE_DF_MIN * plane + o] = n ? mn : NAN;
+      out->summary_f64[PIE_DF_MAX * plane + o] = n ? mx : NAN;
+      out->summary_count[o] = n;
+    }
+  }
+  free(items);
+  free(skipped);
+  return 0;
+}

@@ -1,0 +1,610 @@
+"""CPU restatement of the reference's archive-analytics and export-row functions.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``sph_pie_b200/`` may import this file;
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
+use it, and only as the checker.
+
+PARITY STATUS: **parity unpinned** for values.  The reference is JavaScript and no
+JS engine exists in this image (node, d8, quickjs, ... all probed absent), so the
+reference cannot be executed to produce golden vectors.  The reference's own test
+material for this path is one fixture (``scripts/simulate-webhook.js:42-65``) that
+is checked only against the *same module's* builders (``:75-95``), i.e. it pins
+column order and shape, not values.  ``tests/golden/`` holds that fixture plus the
+row this restatement derives from it by reading the source; it is a
+hand-derivation, not reference output.
+
+Every function cites the reference lines it restates.  Inputs are the Python
+images of ``JSON.parse`` output: dict / list / str / int / float / bool / None,
+plus ``UNDEFINED`` for a missing property where JS distinguishes it from null.
+"""
+from __future__ import annotations
+
+import math
+from decimal import Decimal
+
+# public/app.js:1-13  (ISSUE_MAP keys, in insertion order)
+PRIMARY_ISSUES = [
+    "Tracking lost",
+    "Failed to launch",
+    "Command delay",
+    "RF link",
+    "Battery",
+    "Motor or prop",
+    "Sensor or IMU",
+    "Software or show control",
+    "Operator input",
+    "Other",
+]
+
+# server/webhookDispatcher.js:15-19 == public/app.js:16-20
+EXPORT_COLUMNS = [
+    "showId", "showDate", "showTime", "showLabel", "crew", "leadPilot", "monkeyLead", "showNotes",
+    "entryId", "unitId", "planned", "launched", "status", "primaryIssue", "subIssue", "otherDetail",
+    "severity", "rootCause", "actions", "operator", "batteryId", "delaySec", "commandRx", "notes",
+]
+
+# public/app.js:21-86 (ARCHIVE_METRIC_DEFS keys, insertion order) + issue metrics (:98, :3955-3994)
+ARCHIVE_METRIC_KEYS = [
+    "entriesCount", "completedCount", "noLaunchCount", "abortCount", "avgDelaySec",
+    "maxDelaySec", "completionRate", "launchRate", "abortRate",
+]
+ISSUE_METRIC_PREFIX = "issue:"
+ALL_METRIC_KEYS = ARCHIVE_METRIC_KEYS + [ISSUE_METRIC_PREFIX + i for i in PRIMARY_ISSUES]
+
+_STAT_FIELD_FOR_METRIC = {
+    "entriesCount": "totalEntries",
+    "completedCount": "completedCount",
+    "noLaunchCount": "noLaunchCount",
+    "abortCount": "abortCount",
+    "avgDelaySec": "avgDelaySec",
+    "maxDelaySec": "maxDelaySec",
+    "completionRate": "completionRate",
+    "launchRate": "launchRate",
+    "abortRate": "abortRate",
+}
+
+
+class _Undefined:
+    _inst = None
+
+    def __new__(cls):
+        if cls._inst is None:
+            cls._inst = super().__new__(cls)
+        return cls._inst
+
+    def __repr__(self):
+        return "undefined"
+
+    def __bool__(self):
+        return False
+
+
+UNDEFINED = _Undefined()
+
+# ECMAScript WhiteSpace + LineTerminator code points (String.prototype.trim)
+JS_WHITESPACE = (
+    "\t\n\v\f\r \u00a0\u1680"
+    "\u2000\u2001\u2002\u2003\u2004\u2005\u2006\u2007\u2008\u2009\u200a"
+    "\u2028\u2029\u202f\u205f\u3000\ufeff"
+)
+
+
+# --------------------------------------------------------------------------- JS value semantics
+def js_get(obj, key):
+    """obj?.key for a JSON object: missing property -> undefined."""
+    if isinstance(obj, dict):
+        return obj.get(key, UNDEFINED)
+    return UNDEFINED
+
+
+def js_is_number(v) -> bool:
+    return isinstance(v, (int, float)) and not isinstance(v, bool)
+
+
+def js_truthy(v) -> bool:
+    if v is None or v is UNDEFINED:
+        return False
+    if isinstance(v, bool):
+        return v
+    if js_is_number(v):
+        return not (v == 0 or (isinstance(v, float) and math.isnan(v)))
+    if isinstance(v, str):
+        return len(v) > 0
+    return True  # objects / arrays
+
+
+def js_or(v, default):
+    """``v || default``"""
+    return v if js_truthy(v) else default
+
+
+def number_is_finite(v) -> bool:
+    """Number.isFinite: no coercion; only numbers qualify."""
+    return js_is_number(v) and math.isfinite(v)
+
+
+def js_number_to_string(x) -> str:
+    """Number::toString(x) radix 10 (ECMA-262 6.1.6.1.20): shortest round-trip digits,
+    fixed notation for 1e-7 < |x| < 1e21, exponent notation otherwise."""
+    x = float(x)
+    if math.isnan(x):
+        return "NaN"
+    if x == 0:
+        return "0"
+    if math.isinf(x):
+        return "Infinity" if x > 0 else "-Infinity"
+    sign = "-" if x < 0 else ""
+    d = Decimal(repr(abs(x)))  # repr() is the shortest round-trip decimal (David Gay)
+    _, digits, exp = d.as_tuple()
+    digits = list(digits)
+    while len(digits) > 1 and digits[-1] == 0:  # repr may keep a trailing ".0"
+        digits.pop()
+        exp += 1
+    k = len(digits)
+    n = k + exp  # value = 0.d1..dk * 10^n
+    s = "".join(str(c) for c in digits)
+    if k <= n <= 21:
+        body = s + "0" * (n - k)
+    elif 0 < n <= 21:
+        body = s[:n] + "." + s[n:]
+    elif -6 < n <= 0:
+        body = "0." + "0" * (-n) + s
+    else:
+        e = n - 1
+        es = ("+" if e >= 0 else "-") + str(abs(e))
+        body = (s if k == 1 else s[0] + "." + s[1:]) + "e" + es
+    return sign + body
+
+
+def js_string(v) -> str:
+    """String(v) for JSON-shaped values."""
+    if isinstance(v, str):
+        return v
+    if v is None:
+        return "null"
+    if v is UNDEFINED:
+        return "undefined"
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if js_is_number(v):
+        return js_number_to_string(v)
+    if isinstance(v, list):
+        return js_array_join(v, ",")
+    return "[object Object]"
+
+
+def js_array_join(arr, sep: str) -> str:
+    """Array.prototype.join: null/undefined elements become ''."""
+    return sep.join("" if (e is None or e is UNDEFINED) else js_string(e) for e in arr)
+
+
+def js_trim(s: str) -> str:
+    return s.strip(JS_WHITESPACE)
+
+
+def js_to_lower(s: str) -> str:
+    # For the ASCII targets compared on this path ('completed', 'no-launch', 'abort', 'yes', 'no')
+    # only code points whose lowercase is an ASCII letter matter; Python and ECMAScript agree there
+    # (both follow Unicode SpecialCasing; U+212A KELVIN SIGN -> 'k' in both).
+    return s.lower()
+
+
+# --------------------------------------------------------------------------- archive analytics
+def compute_archive_show_stats(show):
+    """public/app.js:3898-3953 computeArchiveShowStats(show)."""
+    entries = js_get(show, "entries")
+    entries = entries if isinstance(entries, list) else []
+    completed = no_launch = abort = launched = 0
+    delay_values = []
+    issue_counts = {}
+    for entry in entries:
+        status = js_to_lower(js_string(js_or(js_get(entry, "status"), "")))  # :3907
+        if status == "completed":
+            completed += 1
+        elif status == "no-launch":
+            no_launch += 1
+        elif status == "abort":
+            abort += 1
+        if js_to_lower(js_string(js_or(js_get(entry, "launched"), ""))) == "yes":  # :3915
+            launched += 1
+        d = js_get(entry, "delaySec")
+        if number_is_finite(d):  # :3918
+            delay_values.append(float(d))
+        pi = js_get(entry, "primaryIssue")
+        issue = js_trim(pi) if isinstance(pi, str) else ""  # :3921
+        if issue:
+            normalized = issue if issue in PRIMARY_ISSUES else "Other"  # :3923
+            issue_counts[normalized] = issue_counts.get(normalized, 0) + 1
+    total = len(entries)
+    delay_sum = 0.0
+    for v in delay_values:  # :3928 left-to-right reduce, initial 0
+        delay_sum = delay_sum + v
+    avg_delay = delay_sum / len(delay_values) if delay_values else None
+    max_delay = js_math_max(delay_values) if delay_values else None
+    completion_rate = (completed / total) * 100 if total else None
+    launch_rate = (launched / total) * 100 if total else None
+    abort_rate = (abort / total) * 100 if total else None
+    issue_rates = {}
+    for issue in PRIMARY_ISSUES:  # :3935-3938
+        count = issue_counts.get(issue, 0)
+        issue_rates[issue] = (count / total) * 100 if total else None
+    return {
+        "totalEntries": total,
+        "completedCount": completed,
+        "noLaunchCount": no_launch,
+        "abortCount": abort,
+        "launchedCount": launched,
+        "avgDelaySec": avg_delay,
+        "maxDelaySec": max_delay,
+        "completionRate": completion_rate,
+        "launchRate": launch_rate,
+        "abortRate": abort_rate,
+        "issueCounts": issue_counts,
+        "issueRates": issue_rates,
+    }
+
+
+def js_math_max(values):
+    """Math.max(...values): +0 > -0; values here are finite."""
+    best = values[0]
+    for v in values[1:]:
+        if v > best or (v == best and v == 0 and math.copysign(1.0, best) < 0 and math.copysign(1.0, v) > 0):
+            best = v
+    return best
+
+
+def js_math_min(values):
+    """Math.min(...values): -0 < +0."""
+    best = values[0]
+    for v in values[1:]:
+        if v < best or (v == best and v == 0 and math.copysign(1.0, v) < 0 and math.copysign(1.0, best) > 0):
+            best = v
+    return best
+
+
+def parse_show_date_time(date_str, time_str, tz_offset_minutes=0):
+    """public/app.js:4118-4126 parseShowDateTime.  ``Date.parse`` of ``${date}T${time}``: only the
+    ECMA-262 date-time string format is specified (21.4.1.32); a date-time form without an offset is
+    local time.  Anything else falls to V8's legacy parser, which is implementation-defined and is
+    NOT restated: such strings raise NotImplementedError here."""
+    if not isinstance(date_str, str) or not date_str:
+        return None
+    time = time_str if (isinstance(time_str, str) and time_str) else "00:00"
+    iso = f"{date_str}T{time}"
+    ms = _parse_iso_local(iso, tz_offset_minutes)
+    return ms
+
+
+def _parse_iso_local(iso: str, tz_offset_minutes: int):
+    import re
+
+    m = re.fullmatch(r"(\d{4})-(\d{2})-(\d{2})T(\d{2}):(\d{2})(?::(\d{2})(?:\.(\d{1,3}))?)?", iso)
+    if not m:
+        raise NotImplementedError(f"non-ISO date string {iso!r}: V8 legacy Date.parse is not restated")
+    y, mo, d, h, mi = (int(m.group(i)) for i in range(1, 6))
+    s = int(m.group(6)) if m.group(6) else 0
+    ms = int((m.group(7) or "0").ljust(3, "0"))
+    if not (1 <= mo <= 12 and 1 <= d <= days_in_month(y, mo) and h <= 24 and mi <= 59 and s <= 59):
+        return None
+    if h == 24 and (mi or s or ms):
+        return None
+    days = days_from_civil(y, mo, d)
+    local = ((days * 24 + h) * 60 + mi) * 60000 + s * 1000 + ms
+    return float(local - tz_offset_minutes * 60000)
+
+
+def days_in_month(y, m):
+    if m == 2:
+        return 29 if (y % 4 == 0 and (y % 100 != 0 or y % 400 == 0)) else 28
+    return 30 if m in (4, 6, 9, 11) else 31
+
+
+def days_from_civil(y, m, d):
+    """Days since 1970-01-01 (proleptic Gregorian)."""
+    y -= m <= 2
+    era = (y if y >= 0 else y - 399) // 400
+    yoe = y - era * 400
+    doy = (153 * (m + (-3 if m > 2 else 9)) + 2) // 5 + d - 1
+    doe = yoe * 365 + yoe // 4 - yoe // 100 + doy
+    return era * 146097 + doe - 719468
+
+
+def civil_from_days(z):
+    z += 719468
+    era = (z if z >= 0 else z - 146096) // 146097
+    doe = z - era * 146097
+    yoe = (doe - doe // 1460 + doe // 36524 - doe // 146096) // 365
+    y = yoe + era * 400
+    doy = doe - (365 * yoe + yoe // 4 - yoe // 100)
+    mp = (5 * doy + 2) // 153
+    d = doy - (153 * mp + 2) // 5 + 1
+    m = mp + (3 if mp < 10 else -9)
+    return (y + (m <= 2), m, d)
+
+
+def get_show_timestamp(show, tz_offset_minutes=0):
+    """public/app.js:4092-4116 getShowTimestamp(show)."""
+    if not js_truthy(show):
+        return None
+    created = js_get(show, "createdAt")
+    if number_is_finite(created):
+        return float(created)
+    parsed = parse_show_date_time(js_get(show, "date"), js_get(show, "time"), tz_offset_minutes)
+    if parsed is not None:
+        return parsed
+    archived = js_get(show, "archivedAt")
+    if number_is_finite(archived):
+        return float(archived)
+    entries = js_get(show, "entries")
+    if isinstance(entries, list) and entries:
+        ts = sorted(float(js_get(e, "ts")) for e in entries if number_is_finite(js_get(e, "ts")))
+        if ts:
+            return ts[0]
+    return None
+
+
+class JsRangeError(ValueError):
+    """RangeError: Invalid time value (Date.prototype.toISOString on an invalid Date)."""
+
+
+MAX_TIME_MS = 8.64e15
+
+
+def local_day_start(timestamp: float, tz_offset_minutes=0):
+    """``d = new Date(ts); d.setHours(0,0,0,0); d.getTime()`` (public/app.js:3412-3414) in a zone
+    that is a fixed ``tz_offset_minutes`` east of UTC.  Returns None for an invalid Date."""
+    if not math.isfinite(timestamp) or abs(timestamp) > MAX_TIME_MS:
+        return None  # TimeClip -> NaN
+    t = int(timestamp)  # TimeClip: ToIntegerOrInfinity truncates toward zero
+    off = tz_offset_minutes * 60000
+    local = t + off
+    start = (local // 86400000) * 86400000 - off
+    if abs(start) > MAX_TIME_MS:
+        return None
+    return start
+
+
+def iso_date_key(ms: int) -> str:
+    """``new Date(ms).toISOString().slice(0, 10)`` (public/app.js:3415)."""
+    y, m, d = civil_from_days(ms // 86400000)
+    if 0 <= y <= 9999:
+        full = f"{y:04d}-{m:02d}-{d:02d}"
+    else:
+        full = f"{'+' if y > 0 else '-'}{abs(y):06d}-{m:02d}-{d:02d}"
+    return full[:10]
+
+
+def metric_value(metric_key, stats):
+    """metricDef.getValue(stats, show): public/app.js:21-86 and :3978-3988."""
+    if metric_key in _STAT_FIELD_FOR_METRIC:
+        return stats[_STAT_FIELD_FOR_METRIC[metric_key]]
+    if metric_key.startswith(ISSUE_METRIC_PREFIX):
+        issue = metric_key[len(ISSUE_METRIC_PREFIX):]
+        rates = stats.get("issueRates")
+        if rates is not None and issue in rates:
+            v = rates[issue]
+            return v if number_is_finite(v) else (0 if v == 0 and v is not None else None)
+        return None
+    raise KeyError(metric_key)
+
+
+def is_valid_metric_value(v) -> bool:
+    """public/app.js:4128-4134 (for number-or-null inputs)."""
+    if v is None or v is UNDEFINED:
+        return False
+    return math.isfinite(float(v))
+
+
+def build_archive_daily_groups(shows, tz_offset_minutes=0):
+    """public/app.js:3401-3443 buildArchiveDailyGroups(shows), without the display label."""
+    groups = {}
+    lst = shows if isinstance(shows, list) else []
+    for show in lst:
+        if not js_truthy(show):
+            continue
+        ts = get_show_timestamp(show, tz_offset_minutes)
+        if ts is None or not math.isfinite(ts):
+            continue
+        start = local_day_start(ts, tz_offset_minutes)
+        if start is None:
+            raise JsRangeError("Invalid time value")  # :3415 toISOString throws
+        key = iso_date_key(start)
+        g = groups.get(key)
+        if g is None:
+            g = {"dateKey": key, "timestamp": start, "midpoint": start + 12 * 60 * 60 * 1000,
+                 "shows": [], "metrics": {}, "totalShows": 0}
+            groups[key] = g
+        g["shows"].append({"show": show, "stats": compute_archive_show_stats(show)})
+    out = sorted(groups.values(), key=lambda g: g["timestamp"])  # stable, :3435
+    for g in out:
+        g["totalShows"] = len(g["shows"])
+    return out
+
+
+def group_metric_summary(group, metric_key):
+    """public/app.js:3445-3502 getOrCreateGroupMetricSummary, numeric part
+    (average / min / max / count / totalShows and the per-show numeric values)."""
+    values = []
+    numeric = []
+    for item in group["shows"]:
+        v = metric_value(metric_key, item["stats"])
+        n = float(v) if is_valid_metric_value(v) else None
+        values.append(n)
+        if n is not None:
+            numeric.append(n)
+    total = 0.0
+    for v in numeric:  # :3481 left-to-right reduce, initial 0
+        total = total + v
+    return {
+        "average": total / len(numeric) if numeric else None,
+        "min": js_math_min(numeric) if numeric else None,
+        "max": js_math_max(numeric) if numeric else None,
+        "count": len(numeric),
+        "totalShows": len(group["shows"]),
+        "values": values,
+    }
+
+
+def compute_metrics(show):
+    """public/app.js:5024-5047 computeMetrics(show) (live show header)."""
+    entries = js_or(js_get(show, "entries"), [])
+    planned_yes = sum(1 for e in entries if js_get(e, "planned") == "Yes")
+    completed = sum(1 for e in entries if js_get(e, "status") == "Completed")
+    no_launch = sum(1 for e in entries if js_get(e, "status") == "No-launch")
+    abort = sum(1 for e in entries if js_get(e, "status") == "Abort")
+    delays = [float(js_get(e, "delaySec")) for e in entries if js_is_number(js_get(e, "delaySec"))]
+    if delays:
+        total = 0.0
+        for v in delays:
+            total = total + v
+        avg = js_to_fixed2(total / len(delays))
+    else:
+        avg = "0.00"
+    issues = {}
+    for e in entries:
+        pi = js_get(e, "primaryIssue")
+        if js_get(e, "status") != "Completed" and js_truthy(pi):
+            k = js_string(pi)
+            issues[k] = issues.get(k, 0) + 1
+    top = [k for k, _ in sorted(issues.items(), key=lambda kv: -kv[1])[:3]]  # stable
+    success = js_math_round((completed / planned_yes) * 100) if planned_yes else 0
+    return {"successRate": success, "countCompleted": completed, "countNoLaunch": no_launch,
+            "countAbort": abort, "avgDelay": avg, "topIssues": top}
+
+
+def js_math_round(x: float):
+    """Math.round: half toward +inf."""
+    return math.floor(x + 0.5) if math.isfinite(x) else x
+
+
+def js_to_fixed2(x: float) -> str:
+    """Number.prototype.toFixed(2): exact decimal expansion of the double, ties away from zero
+    on the exact value ("let n be an integer for which n/10^f - x is as close to zero as possible;
+    if there are two such n, pick the larger n")."""
+    if math.isnan(x):
+        return "NaN"
+    if abs(x) >= 1e21:
+        return js_number_to_string(x)
+    neg = x < 0 or (x == 0 and math.copysign(1, x) < 0)
+    d = Decimal(abs(x)) * 100
+    n = int(d.to_integral_value(rounding="ROUND_HALF_UP"))
+    s = f"{n // 100}.{n % 100:02d}"
+    return ("-" + s) if (neg and n != 0) else s
+
+
+# --------------------------------------------------------------------------- export rows
+def build_table_row(show=UNDEFINED, entry=UNDEFINED):
+    """server/webhookDispatcher.js:276-305 buildTableRow == public/app.js:5582-5612 buildWebhookRow."""
+    show = {} if show is UNDEFINED else show
+    entry = {} if entry is UNDEFINED else entry
+    crew = js_get(show, "crew")
+    crew = crew if isinstance(crew, list) else []
+    actions = js_get(entry, "actions")
+    actions = actions if isinstance(actions, list) else []
+    completed = js_get(entry, "status") == "Completed"  # strict ===, case-sensitive
+
+    def g(o, k):
+        return js_or(js_get(o, k), "")
+
+    d = js_get(entry, "delaySec")
+    return {
+        "showId": g(show, "id"),
+        "showDate": g(show, "date"),
+        "showTime": g(show, "time"),
+        "showLabel": g(show, "label"),
+        "crew": js_array_join(crew, "|"),
+        "leadPilot": g(show, "leadPilot"),
+        "monkeyLead": g(show, "monkeyLead"),
+        "showNotes": g(show, "notes"),
+        "entryId": g(entry, "id"),
+        "unitId": g(entry, "unitId"),
+        "planned": g(entry, "planned"),
+        "launched": g(entry, "launched"),
+        "status": g(entry, "status"),
+        "primaryIssue": "" if completed else g(entry, "primaryIssue"),
+        "subIssue": "" if completed else g(entry, "subIssue"),
+        "otherDetail": "" if completed else g(entry, "otherDetail"),
+        "severity": "" if completed else g(entry, "severity"),
+        "rootCause": "" if completed else g(entry, "rootCause"),
+        "actions": js_array_join(actions, "|"),
+        "operator": g(entry, "operator"),
+        "batteryId": g(entry, "batteryId"),
+        "delaySec": "" if (d is None or d is UNDEFINED) else d,
+        "commandRx": g(entry, "commandRx"),
+        "notes": g(entry, "notes"),
+    }
+
+
+def build_message_payload(row=UNDEFINED):
+    """server/webhookDispatcher.js:307-313 buildMessagePayload."""
+    row = {} if row is UNDEFINED else row
+    out = {}
+    for c in EXPORT_COLUMNS:
+        v = js_get(row, c)
+        out[c] = "" if (v is UNDEFINED or v is None) else v
+    return out
+
+
+def csv_escape(value) -> str:
+    """server/webhookDispatcher.js:332-338 csvEscape == public/app.js:6025-6034."""
+    s = "" if (value is None or value is UNDEFINED) else js_string(value)
+    if '"' in s or "," in s or "\n" in s or "\r" in s:
+        return '"' + s.replace('"', '""') + '"'
+    return s
+
+
+def build_csv_row(row) -> str:
+    """server/webhookDispatcher.js:340-342 buildCsvRow."""
+    cells = []
+    for c in EXPORT_COLUMNS:
+        v = js_get(row, c)
+        cells.append(csv_escape("" if (v is None or v is UNDEFINED) else v))  # ?? ''
+    return ",".join(cells)
+
+
+def export_show_as_csv(show) -> str:
+    """public/app.js:5558-5570 exportShowAsCsv: header line + one line per entry, '\\n'-joined."""
+    entries = js_or(js_get(show, "entries"), [])
+    lines = [",".join(csv_escape(c) for c in EXPORT_COLUMNS)]
+    for e in entries:
+        lines.append(build_csv_row(build_table_row(show, e)))
+    return "\n".join(lines)
+
+
+def to_yes_no_boolean(value) -> bool:
+    """server/webhookDispatcher.js:60-77 toYesNoBoolean."""
+    if isinstance(value, str):
+        n = js_to_lower(js_trim(value))
+        if n == "yes":
+            return True
+        if n == "no":
+            return False
+    if isinstance(value, bool):
+        return value
+    if js_is_number(value):
+        return (value != 0) if math.isfinite(value) else False
+    return False
+
+
+def build_archive_entry_payload(show=UNDEFINED, entry=UNDEFINED):
+    """server/webhookDispatcher.js:315-330 buildArchiveEntryPayload."""
+    show = {} if show is UNDEFINED else show
+    entry = {} if entry is UNDEFINED else entry
+
+    def g(o, k):
+        return js_or(js_get(o, k), "")
+
+    return {
+        "showDate": g(show, "date"),
+        "showTime": g(show, "time"),
+        "showNumber": g(show, "label"),
+        "leadPilot": g(show, "leadPilot"),
+        "monkeyLead": g(show, "monkeyLead"),
+        "operator": g(entry, "operator"),
+        "monkeyId": g(entry, "unitId"),
+        "planned": to_yes_no_boolean(js_get(entry, "planned")),
+        "launched": to_yes_no_boolean(js_get(entry, "launched")),
+        "commandReceived": to_yes_no_boolean(js_get(entry, "commandRx")),
+        "primaryIssue": g(entry, "primaryIssue"),
+        "subIssue": g(entry, "subIssue"),
+    }

@@ -1,0 +1,168 @@
+"""ctypes binding of libsphpie_b200.so (include/sph_pie_b200.h).
+
+The library is the product: if it is missing or no sm_100 GPU is present, every compute call
+raises.  There is no CPU fallback in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsphpie_b200.so")
+
+PIE_N_ISSUES = 10
+PIE_N_METRICS = 19
+PIE_SI_COUNT = 26
+PIE_SF_COUNT = 16
+PIE_DF_COUNT = 3
+PIE_DAY_NONE = -(2 ** 63)
+
+PIE_OK = 0
+PIE_ERR_CUDA = -1
+PIE_ERR_INVALID_ARG = -2
+PIE_ERR_RANGE = -3
+PIE_ERR_UNSUPPORTED_DATE = -4
+PIE_ERR_CAPACITY = -5
+PIE_ERR_NO_DEVICE = -6
+
+# plane indices (include/sph_pie_b200.h)
+SI_TOTAL, SI_COMPLETED, SI_NO_LAUNCH, SI_ABORT, SI_LAUNCHED, SI_DELAY_COUNT = range(6)
+SI_ISSUE_COUNT0 = 6
+SI_ISSUE_FIRST0 = 16
+SF_DELAY_SUM, SF_AVG_DELAY, SF_MAX_DELAY, SF_COMPLETION_RATE, SF_LAUNCH_RATE, SF_ABORT_RATE = range(6)
+SF_ISSUE_RATE0 = 6
+DF_AVERAGE, DF_MIN, DF_MAX = range(3)
+
+
+class StrColC(C.Structure):
+    _fields_ = [("offsets", C.c_void_p), ("data", C.c_void_p)]
+
+
+class StrListColC(C.Structure):
+    _fields_ = [("list_offsets", C.c_void_p), ("items", StrColC)]
+
+
+SHOW_STR_COLS = ["show_id", "show_date", "show_time", "show_label", "lead_pilot", "monkey_lead", "show_notes"]
+ENTRY_STR_COLS = ["entry_id", "unit_id", "planned", "launched", "status", "primary_issue", "sub_issue",
+                  "other_detail", "severity", "root_cause", "operator_name", "battery_id", "command_rx", "notes"]
+
+
+class ArchiveViewC(C.Structure):
+    _fields_ = (
+        [("n_shows", C.c_int64), ("n_entries", C.c_int64), ("entry_offsets", C.c_void_p)]
+        + [(n, StrColC) for n in SHOW_STR_COLS]
+        + [("crew", StrListColC), ("created_at", C.c_void_p), ("archived_at", C.c_void_p)]
+        + [(n, StrColC) for n in ENTRY_STR_COLS]
+        + [("actions", StrListColC), ("delay_sec", C.c_void_p), ("delay_valid", C.c_void_p),
+           ("entry_ts", C.c_void_p)]
+    )
+
+
+class DailyOutC(C.Structure):
+    _fields_ = [
+        ("stride", C.c_int64),
+        ("show_day_start", C.c_void_p),
+        ("show_order", C.c_void_p),
+        ("group_day_start", C.c_void_p),
+        ("group_offsets", C.c_void_p),
+        ("summary_f64", C.c_void_p),
+        ("summary_count", C.c_void_p),
+        ("n_groups", C.c_void_p),
+        ("status", C.c_void_p),
+    ]
+
+
+class PieError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[pie {code}] {message}")
+        self.code = code
+        self.message = message
+
+
+class JsRangeError(PieError, ValueError):
+    """RangeError: Invalid time value — what the reference throws from toISOString
+    (public/app.js:3415) for a show whose timestamp is outside the ECMAScript time range."""
+
+
+class UnsupportedDateError(PieError, NotImplementedError):
+    """show.date/time is outside the ECMA-262 date-time grammar (V8 legacy parsing not provided)."""
+
+
+_lib = None
+
+# every function include/sph_pie_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "pie_abi_version": (C.c_int, []),
+    "pie_last_error": (C.c_char_p, []),
+    "pie_init": (C.c_int, [C.c_int]),
+    "pie_device_sm_count": (C.c_int, []),
+    "pie_host_alloc": (C.c_void_p, [C.c_uint64]),
+    "pie_host_free": (None, [C.c_void_p]),
+    "pie_last_transfer_bytes": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "pie_kernel_launch_count": (C.c_uint64, []),
+    "pie_show_stats_scratch_bytes": (C.c_uint64, [C.c_int64]),
+    "pie_show_stats_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_void_p]),
+    "pie_show_stats_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64]),
+    "pie_daily_scratch_bytes": (C.c_uint64, [C.c_int64]),
+    "pie_daily_summary_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                        C.POINTER(DailyOutC), C.c_void_p, C.c_void_p]),
+    "pie_archive_analytics_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                             C.POINTER(DailyOutC)]),
+}
+
+
+def load():
+    """Load the shared library (no GPU needed to load; compute calls need one)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "sph_pie_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().pie_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc == PIE_OK:
+        return
+    msg = last_error()
+    if rc == PIE_ERR_RANGE:
+        raise JsRangeError(rc, msg)
+    if rc == PIE_ERR_UNSUPPORTED_DATE:
+        raise UnsupportedDateError(rc, msg)
+    raise PieError(rc, msg)
+
+
+_initialised = False
+
+
+def init(device: int = -1) -> None:
+    """pie_init: verifies an sm_100 device; raises PieError(PIE_ERR_NO_DEVICE) otherwise."""
+    global _initialised
+    check(load().pie_init(device))
+    _initialised = True
+
+
+def ensure_init() -> None:
+    if not _initialised:
+        init(-1)
+
+
+def last_transfer_bytes():
+    h, d = C.c_uint64(0), C.c_uint64(0)
+    load().pie_last_transfer_bytes(C.byref(h), C.byref(d))
+    return int(h.value), int(d.value)

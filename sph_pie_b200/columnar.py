@@ -1,0 +1,244 @@
+"""The columnar "archive table"  and the packer from provider-normalised show
+documents (reference server/storage/sqlProvider.js:361-409 `_normalizeShow` / `_normalizeEntry`).
+
+Columns are torch tensors (CPU, pinned CPU, or CUDA); torch is used for memory only.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# show document key -> column
+SHOW_KEY_TO_COL = {"id": "show_id", "date": "show_date", "time": "show_time", "label": "show_label",
+                   "leadPilot": "lead_pilot", "monkeyLead": "monkey_lead", "notes": "show_notes"}
+ENTRY_KEY_TO_COL = {"id": "entry_id", "unitId": "unit_id", "planned": "planned", "launched": "launched",
+                    "status": "status", "primaryIssue": "primary_issue", "subIssue": "sub_issue",
+                    "otherDetail": "other_detail", "severity": "severity", "rootCause": "root_cause",
+                    "operator": "operator_name", "batteryId": "battery_id", "commandRx": "command_rx",
+                    "notes": "notes"}
+
+
+@dataclass
+class StrCol:
+    offsets: torch.Tensor  # int32 [n + 1]
+    data: torch.Tensor     # uint8 [bytes]
+
+    def to(self, device, non_blocking=False):
+        return StrCol(self.offsets.to(device, non_blocking=non_blocking), self.data.to(device, non_blocking=non_blocking))
+
+    def pin(self):
+        return StrCol(self.offsets.pin_memory(), self.data.pin_memory())
+
+    def nbytes(self) -> int:
+        return self.offsets.numel() * 4 + self.data.numel()
+
+    def get(self, i: int) -> str:
+        o = self.offsets
+        return bytes(self.data[int(o[i]):int(o[i + 1])].cpu().numpy()).decode("utf-8")
+
+    def c(self) -> _lib.StrColC:
+        return _lib.StrColC(self.offsets.data_ptr(), self.data.data_ptr())
+
+
+@dataclass
+class StrListCol:
+    list_offsets: torch.Tensor  # int32 [n + 1]
+    items: StrCol
+
+    def to(self, device, non_blocking=False):
+        return StrListCol(self.list_offsets.to(device, non_blocking=non_blocking), self.items.to(device, non_blocking))
+
+    def pin(self):
+        return StrListCol(self.list_offsets.pin_memory(), self.items.pin())
+
+    def nbytes(self) -> int:
+        return self.list_offsets.numel() * 4 + self.items.nbytes()
+
+    def c(self) -> _lib.StrListColC:
+        return _lib.StrListColC(self.list_offsets.data_ptr(), self.items.c())
+
+
+def strcol_from_strings(values: List[str]) -> StrCol:
+    enc = []
+    for v in values:
+        try:
+            enc.append(v.encode("utf-8"))
+        except UnicodeEncodeError as e:  # lone surrogate: a JS string that is not well-formed UTF-16
+            raise TypeError(f"string {v!r} is not encodable as UTF-8 (lone surrogate)") from e
+    lens = np.fromiter((len(b) for b in enc), dtype=np.int64, count=len(enc))
+    offs = np.zeros(len(enc) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    if offs[-1] >= 2 ** 31:
+        raise ValueError("string column exceeds 2 GiB: split the batch")
+    data = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if enc else np.zeros(0, dtype=np.uint8)
+    return StrCol(torch.from_numpy(offs.astype(np.int32)), torch.from_numpy(data))
+
+
+def _norm_str(v, what: str) -> str:
+    """null / undefined / '' are one value for every function on the path (`x || ''`)."""
+    if v is None:
+        return ""
+    if isinstance(v, str):
+        return v
+    raise TypeError(
+        f"{what} is {type(v).__name__}, not a string: the archive table holds provider-normalised shows "
+        "(sqlProvider.js:361-409)"
+    )
+
+
+def _norm_time(v) -> float:
+    """Number.isFinite(v) ? v : NaN (no coercion: only JS numbers qualify)."""
+    if isinstance(v, bool) or not isinstance(v, (int, float)):
+        return math.nan
+    f = float(v)
+    return f if math.isfinite(f) else math.nan
+
+
+@dataclass
+class ArchiveTable:
+    n_shows: int
+    n_entries: int
+    entry_offsets: torch.Tensor
+    show_cols: Dict[str, StrCol]
+    crew: StrListCol
+    created_at: torch.Tensor
+    archived_at: torch.Tensor
+    entry_cols: Dict[str, StrCol]
+    actions: StrListCol
+    delay_sec: torch.Tensor
+    delay_valid: torch.Tensor
+    entry_ts: torch.Tensor
+    _keep: list = field(default_factory=list, repr=False)
+
+    @property
+    def device(self) -> torch.device:
+        return self.entry_offsets.device
+
+    @property
+    def is_cuda(self) -> bool:
+        return self.entry_offsets.is_cuda
+
+    def _map(self, f_tensor, f_col):
+        return ArchiveTable(
+            self.n_shows, self.n_entries, f_tensor(self.entry_offsets),
+            {k: f_col(c) for k, c in self.show_cols.items()}, f_col(self.crew),
+            f_tensor(self.created_at), f_tensor(self.archived_at),
+            {k: f_col(c) for k, c in self.entry_cols.items()}, f_col(self.actions),
+            f_tensor(self.delay_sec), f_tensor(self.delay_valid), f_tensor(self.entry_ts))
+
+    def to(self, device, non_blocking=False) -> "ArchiveTable":
+        return self._map(lambda t: t.to(device, non_blocking=non_blocking), lambda c: c.to(device, non_blocking))
+
+    def pin(self) -> "ArchiveTable":
+        return self._map(lambda t: t.pin_memory(), lambda c: c.pin())
+
+    def nbytes(self) -> int:
+        n = self.entry_offsets.numel() * 4 + (self.created_at.numel() + self.archived_at.numel()) * 8
+        n += self.delay_sec.numel() * 8 + self.delay_valid.numel() + self.entry_ts.numel() * 8
+        n += sum(c.nbytes() for c in self.show_cols.values()) + sum(c.nbytes() for c in self.entry_cols.values())
+        return n + self.crew.nbytes() + self.actions.nbytes()
+
+    def view(self) -> _lib.ArchiveViewC:
+        """pie_archive_view over this table's buffers (valid while the table is alive)."""
+        v = _lib.ArchiveViewC()
+        v.n_shows = self.n_shows
+        v.n_entries = self.n_entries
+        v.entry_offsets = self.entry_offsets.data_ptr()
+        for name in _lib.SHOW_STR_COLS:
+            setattr(v, name, self.show_cols[name].c())
+        v.crew = self.crew.c()
+        v.created_at = self.created_at.data_ptr()
+        v.archived_at = self.archived_at.data_ptr()
+        for name in _lib.ENTRY_STR_COLS:
+            setattr(v, name, self.entry_cols[name].c())
+        v.actions = self.actions.c()
+        v.delay_sec = self.delay_sec.data_ptr()
+        v.delay_valid = self.delay_valid.data_ptr()
+        v.entry_ts = self.entry_ts.data_ptr()
+        return v
+
+    def slice_shows(self, s0: int, s1: int) -> "ArchiveTable":
+        """Rows [s0, s1) of the show columns and their entries, sharing the byte heaps (string
+        offsets keep their absolute values, which the ABI allows).  Used to shard by show range."""
+        eo = self.entry_offsets
+        e0, e1 = int(eo[s0]), int(eo[s1])
+
+        def sl_col(c: StrCol, a, b):
+            return StrCol(c.offsets[a:b + 1], c.data)
+
+        def sl_list(c: StrListCol, a, b):
+            return StrListCol(c.list_offsets[a:b + 1], c.items)
+
+        return ArchiveTable(
+            s1 - s0, e1 - e0, (eo[s0:s1 + 1] - e0).contiguous(),
+            {k: sl_col(c, s0, s1) for k, c in self.show_cols.items()}, sl_list(self.crew, s0, s1),
+            self.created_at[s0:s1], self.archived_at[s0:s1],
+            {k: sl_col(c, e0, e1) for k, c in self.entry_cols.items()}, sl_list(self.actions, e0, e1),
+            self.delay_sec[e0:e1], self.delay_valid[e0:e1], self.entry_ts[e0:e1])
+
+
+def _list_col(lists: List[List[str]]) -> StrListCol:
+    lo = np.zeros(len(lists) + 1, dtype=np.int64)
+    np.cumsum(np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists)), out=lo[1:])
+    flat = [s for x in lists for s in x]
+    return StrListCol(torch.from_numpy(lo.astype(np.int32)), strcol_from_strings(flat))
+
+
+def pack_shows(shows: List[Optional[dict]]) -> ArchiveTable:
+    """Pack provider-normalised show documents into an archive table.
+
+    A falsy list element (null) becomes an empty show whose timestamp columns are NaN, so it is
+    skipped by the daily grouping exactly like `if(!show) return` (public/app.js:3405-3407).
+    """
+    show_vals = {c: [] for c in SHOW_KEY_TO_COL.values()}
+    entry_vals = {c: [] for c in ENTRY_KEY_TO_COL.values()}
+    crew, actions = [], []
+    created, archived, delay, delay_valid, ets = [], [], [], [], []
+    entry_offsets = [0]
+    for si, show in enumerate(shows):
+        show = show if isinstance(show, dict) else {}
+        for k, c in SHOW_KEY_TO_COL.items():
+            show_vals[c].append(_norm_str(show.get(k), f"shows[{si}].{k}"))
+        cr = show.get("crew")
+        crew.append([_norm_str(x, f"shows[{si}].crew[]") for x in cr] if isinstance(cr, list) else [])
+        created.append(_norm_time(show.get("createdAt")))
+        archived.append(_norm_time(show.get("archivedAt")))
+        entries = show.get("entries")
+        entries = entries if isinstance(entries, list) else []
+        for ei, e in enumerate(entries):
+            e = e if isinstance(e, dict) else {}
+            for k, c in ENTRY_KEY_TO_COL.items():
+                entry_vals[c].append(_norm_str(e.get(k), f"shows[{si}].entries[{ei}].{k}"))
+            ac = e.get("actions")
+            actions.append([_norm_str(x, f"shows[{si}].entries[{ei}].actions[]") for x in ac]
+                           if isinstance(ac, list) else [])
+            d = e.get("delaySec")
+            if d is None:
+                delay.append(0.0)
+                delay_valid.append(0)
+            elif isinstance(d, bool) or not isinstance(d, (int, float)):
+                raise TypeError(f"shows[{si}].entries[{ei}].delaySec is {type(d).__name__}; number or null expected")
+            else:
+                delay.append(float(d))
+                delay_valid.append(1)
+            ets.append(_norm_time(e.get("ts")))
+        entry_offsets.append(entry_offsets[-1] + len(entries))
+    return ArchiveTable(
+        n_shows=len(shows), n_entries=entry_offsets[-1],
+        entry_offsets=torch.tensor(entry_offsets, dtype=torch.int32),
+        show_cols={c: strcol_from_strings(v) for c, v in show_vals.items()},
+        crew=_list_col(crew),
+        created_at=torch.tensor(created, dtype=torch.float64),
+        archived_at=torch.tensor(archived, dtype=torch.float64),
+        entry_cols={c: strcol_from_strings(v) for c, v in entry_vals.items()},
+        actions=_list_col(actions),
+        delay_sec=torch.tensor(delay, dtype=torch.float64),
+        delay_valid=torch.tensor(delay_valid, dtype=torch.uint8),
+        entry_ts=torch.tensor(ets, dtype=torch.float64),
+    )

@@ -1,0 +1,485 @@
+// Daily groups and per-day metric summaries on sm_100a.
+// Replaces buildArchiveDailyGroups (reference public/app.js:3401-3443, with getShowTimestamp
+// :4092-4116 and parseShowDateTime :4118-4126) and the numeric part of
+// getOrCreateGroupMetricSummary (:3445-3502).
+//
+// Pipeline (all on one stream, no host synchronisation):
+//   show_day_kernel        timestamp chain -> local-midnight ms and a 32-bit day key per show
+//   radix passes           STABLE LSD radix sort of (day key, show index); 8-bit digits; passes whose
+//                          digit is identical in every key are skipped on the device
+//   group_* kernels        run heads of equal keys -> group ids / offsets / day starts
+//   daily_summary_kernel   one thread per (group, metric): left-to-right sum, min, max, count
+// The Map-insertion-then-sort of the reference (groups ordered by day, shows inside a group in
+// input order) is exactly a stable sort of the shows by day.
+#include "pie_device.cuh"
+#include "pie_kernels.h"
+
+namespace pie {
+
+constexpr int kTile = 2048;  // shows per CTA in the sort / group kernels (256 threads x 8)
+constexpr int kThreads = 256;
+constexpr int kItems = kTile / kThreads;
+constexpr uint32_t kKeyNone = 0xFFFFFFFFu;
+constexpr int64_t kMsPerDay = 86400000LL;
+constexpr double kMaxTimeMs = 8.64e15;  // ECMA-262 TimeClip
+
+struct DailyMeta {
+  unsigned long long err;  // (show index << 32) | -status, minimum wins; ~0 = no error
+  uint32_t or_bits, and_bits;
+  uint32_t n_valid;
+  uint32_t pad;
+};
+
+struct DailyScratch {
+  uint32_t *keys_a, *keys_b;
+  int32_t *vals_a, *vals_b;
+  uint32_t* hist;       // [256][nblk]
+  uint32_t* tile_heads; // [nblk]
+  DailyMeta* meta;
+};
+
+static inline int64_t n_tiles(int64_t n) { return (n + kTile - 1) / kTile; }
+static inline uint64_t align_up(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
+
+uint64_t daily_scratch_bytes(int64_t n_shows) {
+  const uint64_t s = (uint64_t)(n_shows > 0 ? n_shows : 1), nb = (uint64_t)n_tiles(s);
+  return 4 * align_up(4 * s) + align_up(4 * 256 * nb) + align_up(4 * nb) + align_up(sizeof(DailyMeta));
+}
+
+static DailyScratch carve(void* scratch, int64_t n_shows) {
+  const uint64_t s = (uint64_t)(n_shows > 0 ? n_shows : 1), nb = (uint64_t)n_tiles(s);
+  uint8_t* p = static_cast<uint8_t*>(scratch);
+  DailyScratch d;
+  d.keys_a = (uint32_t*)p; p += align_up(4 * s);
+  d.keys_b = (uint32_t*)p; p += align_up(4 * s);
+  d.vals_a = (int32_t*)p; p += align_up(4 * s);
+  d.vals_b = (int32_t*)p; p += align_up(4 * s);
+  d.hist = (uint32_t*)p; p += align_up(4 * 256 * nb);
+  d.tile_heads = (uint32_t*)p; p += align_up(4 * nb);
+  d.meta = (DailyMeta*)p;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ECMA-262 21.4.1.32 date-time string `${date}T${time}` (public/app.js:4122-4124).
+// returns 1 parsed (ms in *out), 0 -> NaN (illegal element values; the chain continues),
+// -1 unsupported (outside the specified grammar: V8's legacy parser would decide).
+__device__ __forceinline__ int two_digits(const uint8_t* s) {
+  uint32_t a = s[0] - '0', b = s[1] - '0';
+  return (a > 9 || b > 9) ? -1 : (int)(a * 10 + b);
+}
+
+__device__ __forceinline__ int64_t days_from_civil(int64_t y, int m, int d) {
+  y -= m <= 2;
+  const int64_t era = (y >= 0 ? y : y - 399) / 400;
+  const int64_t yoe = y - era * 400;
+  const int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  const int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return era * 146097 + doe - 719468;
+}
+
+__device__ int parse_show_date_time(const uint8_t* ds, int dn, const uint8_t* ts, int tn, int64_t tz_off_ms,
+                                    double* out) {
+  const uint8_t dflt[5] = {'0', '0', ':', '0', '0'};
+  if (tn == 0) { ts = dflt; tn = 5; }
+  if (dn != 10 || ds[4] != '-' || ds[7] != '-') return -1;
+  const int y1 = two_digits(ds), y2 = two_digits(ds + 2), mo = two_digits(ds + 5), d = two_digits(ds + 8);
+  if (y1 < 0 || y2 < 0 || mo < 0 || d < 0) return -1;
+  if (tn < 5 || ts[2] != ':') return -1;
+  const int h = two_digits(ts), mi = two_digits(ts + 3);
+  if (h < 0 || mi < 0) return -1;
+  int pos = 5, sec = 0, ms = 0;
+  if (pos < tn && ts[pos] == ':') {
+    if (pos + 3 > tn) return -1;
+    sec = two_digits(ts + pos + 1);
+    if (sec < 0) return -1;
+    pos += 3;
+    if (pos < tn && ts[pos] == '.') {
+      if (pos + 4 > tn) return -1;
+      const uint32_t a = ts[pos + 1] - '0', b = ts[pos + 2] - '0', c = ts[pos + 3] - '0';
+      if (a > 9 || b > 9 || c > 9) return -1;
+      ms = (int)(a * 100 + b * 10 + c);
+      pos += 4;
+    }
+  }
+  bool has_off = false;
+  int64_t off_ms = 0;
+  if (pos < tn) {
+    if (ts[pos] == 'Z' && pos + 1 == tn) {
+      has_off = true;
+    } else if ((ts[pos] == '+' || ts[pos] == '-') && pos + 6 == tn && ts[pos + 3] == ':') {
+      const int oh = two_digits(ts + pos + 1), om = two_digits(ts + pos + 4);
+      if (oh < 0 || om < 0) return -1;
+      if (oh > 23 || om > 59) return 0;
+      off_ms = (int64_t)(oh * 60 + om) * 60000 * (ts[pos] == '-' ? -1 : 1);
+      has_off = true;
+    } else {
+      return -1;
+    }
+  }
+  const int year = y1 * 100 + y2;
+  if (mo < 1 || mo > 12 || d < 1 || d > 31 || h > 24 || mi > 59 || sec > 59) return 0;
+  if (h == 24 && (mi || sec || ms)) return 0;
+  const bool leap = (year % 4 == 0) && (year % 100 != 0 || year % 400 == 0);
+  const int dim = (mo == 2) ? (leap ? 29 : 28) : ((mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30 : 31);
+  if (d > dim) return -1;  // e.g. Feb 30: engines disagree (V8 rolls over, others NaN)
+  const int64_t local = ((days_from_civil(year, mo, d) * 24 + h) * 60 + mi) * 60000 + sec * 1000 + ms;
+  *out = (double)(local - (has_off ? off_ms : tz_off_ms));
+  return 1;
+}
+
+__global__ void daily_init_kernel(DailyMeta* meta) {
+  meta->err = ~0ull;
+  meta->or_bits = 0;
+  meta->and_bits = 0xFFFFFFFFu;
+  meta->n_valid = 0;
+}
+
+__global__ void __launch_bounds__(kThreads) show_day_kernel(pie_archive_view v, int64_t tz_off_ms,
+                                                            int64_t* __restrict__ show_day_start,
+                                                            uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
+                                                            DailyMeta* meta) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t key = kKeyNone;
+  bool in_range = s < v.n_shows;
+  if (in_range) {
+    double ts = quiet_nan();
+    int err = 0;
+    const double created = v.created_at[s];
+    if (is_finite_f64(created)) {
+      ts = created;
+    } else {
+      int parsed = 0;
+      if (v.show_date.offsets) {
+        const int db = v.show_date.offsets[s], de = v.show_date.offsets[s + 1];
+        if (de > db) {
+          int tb = 0, te = 0;
+          if (v.show_time.offsets) { tb = v.show_time.offsets[s]; te = v.show_time.offsets[s + 1]; }
+          parsed = parse_show_date_time(v.show_date.data + db, de - db, v.show_time.data + tb, te - tb, tz_off_ms, &ts);
+          if (parsed < 0) err = -PIE_ERR_UNSUPPORTED_DATE;
+        }
+      }
+      if (parsed == 0) {
+        const double archived = v.archived_at ? v.archived_at[s] : quiet_nan();
+        if (is_finite_f64(archived)) {
+          ts = archived;
+        } else if (v.entry_ts) {  // smallest finite entry.ts (:4106-4113)
+          bool any = false;
+          double best = 0.0;
+          for (int e = v.entry_offsets[s]; e < v.entry_offsets[s + 1]; ++e) {
+            const double t = v.entry_ts[e];
+            if (is_finite_f64(t) && (!any || t < best)) { best = t; any = true; }
+          }
+          if (any) ts = best;
+        }
+      }
+    }
+    int64_t start = PIE_DAY_NONE;
+    if (!err && is_finite_f64(ts)) {
+      if (fabs(ts) > kMaxTimeMs) {
+        err = -PIE_ERR_RANGE;  // new Date(ts) is invalid -> toISOString throws (:3415)
+      } else {
+        const int64_t t = (int64_t)ts;  // TimeClip truncates toward zero
+        const int64_t local = t + tz_off_ms;
+        int64_t day = local / kMsPerDay;
+        if (local % kMsPerDay < 0) day -= 1;  // floor
+        start = day * kMsPerDay - tz_off_ms;
+        if (start > (int64_t)kMaxTimeMs || start < -(int64_t)kMaxTimeMs) {
+          err = -PIE_ERR_RANGE;
+          start = PIE_DAY_NONE;
+        } else {
+          key = (uint32_t)(day + 0x80000000LL);  // |day| <= 1.0e8 + 1
+        }
+      }
+    }
+    if (err) atomicMin(&meta->err, ((unsigned long long)s << 32) | (unsigned long long)err);
+    show_day_start[s] = start;
+    keys[s] = key;
+    vals[s] = (int32_t)s;
+  }
+  // digit-skip masks and the valid count, one atomic per warp
+  const uint32_t k_or = __reduce_or_sync(0xFFFFFFFFu, in_range ? key : 0u);
+  const uint32_t k_and = __reduce_and_sync(0xFFFFFFFFu, in_range ? key : 0xFFFFFFFFu);
+  const uint32_t nv = __popc(__ballot_sync(0xFFFFFFFFu, in_range && key != kKeyNone));
+  if ((threadIdx.x & 31) == 0) {
+    atomicOr(&meta->or_bits, k_or);
+    atomicAnd(&meta->and_bits, k_and);
+    if (nv) atomicAdd(&meta->n_valid, nv);
+  }
+}
+
+// ---- stable LSD radix sort, 8-bit digits ----------------------------------------------------
+__device__ __forceinline__ bool pass_skipped(const DailyMeta* meta, int pass) {
+  return (((meta->or_bits ^ meta->and_bits) >> (8 * pass)) & 0xFFu) == 0;
+}
+// number of executed passes before `pass`, i.e. which buffer currently holds the data
+__device__ __forceinline__ int parity_before(const DailyMeta* meta, int pass) {
+  int p = 0;
+  for (int q = 0; q < pass; ++q) p ^= pass_skipped(meta, q) ? 0 : 1;
+  return p;
+}
+
+__global__ void __launch_bounds__(kThreads) radix_hist_kernel(DailyScratch d, int64_t n, int pass, int nblk) {
+  if (pass_skipped(d.meta, pass)) return;
+  const uint32_t* keys = parity_before(d.meta, pass) ? d.keys_b : d.keys_a;
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kTile;
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const int64_t i = base + r * kThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> (8 * pass)) & 0xFF], 1u);
+  }
+  __syncthreads();
+  d.hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of `n` uint32 in place by ONE block of 1024 threads; returns the total via *total
+__device__ void block_exclusive_scan_inplace(uint32_t* a, int64_t n, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
+  const int64_t b = (int64_t)tid * per, e = (b + per < n) ? b + per : n;
+  uint32_t sum = 0;
+  for (int64_t i = b; i < e; ++i) sum += a[i];
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = warp_sums[lane];
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_sums[lane] = wi - w;
+    if (lane == 31) carry = wi;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[wid] + incl - sum;
+  for (int64_t i = b; i < e; ++i) {
+    const uint32_t x = a[i];
+    a[i] = run;
+    run += x;
+  }
+  if (total && tid == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(1024) radix_scan_kernel(DailyScratch d, int pass, int nblk) {
+  if (pass_skipped(d.meta, pass)) return;
+  block_exclusive_scan_inplace(d.hist, (int64_t)256 * nblk, nullptr);
+}
+
+__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(DailyScratch d, int64_t n, int pass, int nblk) {
+  if (pass_skipped(d.meta, pass)) return;
+  const int par = parity_before(d.meta, pass);
+  const uint32_t* kin = par ? d.keys_b : d.keys_a;
+  const int32_t* vin = par ? d.vals_b : d.vals_a;
+  uint32_t* kout = par ? d.keys_a : d.keys_b;
+  int32_t* vout = par ? d.vals_a : d.vals_b;
+
+  __shared__ uint32_t cnt[kThreads / 32][256];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < (kThreads / 32) * 256; i += kThreads) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+
+  // warp `wid` owns kItems*32 consecutive items of the tile; round r covers 32 consecutive items
+  const int64_t wbase = (int64_t)blockIdx.x * kTile + (int64_t)wid * (kItems * 32);
+  uint32_t key[kItems];
+  int32_t val[kItems];
+  uint32_t dig[kItems];
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const int64_t i = wbase + r * 32 + lane;
+    const bool ok = i < n;
+    key[r] = ok ? kin[i] : 0;
+    val[r] = ok ? vin[i] : 0;
+    dig[r] = ok ? ((key[r] >> (8 * pass)) & 0xFF) : 0x100u;
+  }
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dig[r]);
+    if (dig[r] < 256 && (__ffs(peers) - 1) == lane) cnt[wid][dig[r]] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // thread tid = digit: turn per-warp counts into global start positions, warps in order
+    uint32_t run = d.hist[(int64_t)tid * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      const uint32_t c = cnt[w][tid];
+      cnt[w][tid] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  const uint32_t lt = (1u << lane) - 1;
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dig[r]);
+    uint32_t pos = 0;
+    if (dig[r] < 256) pos = cnt[wid][dig[r]] + __popc(peers & lt);
+    __syncwarp();
+    if (dig[r] < 256 && (__ffs(peers) - 1) == lane) cnt[wid][dig[r]] += __popc(peers);
+    __syncwarp();
+    if (dig[r] < 256) {
+      kout[pos] = key[r];
+      vout[pos] = val[r];
+    }
+  }
+}
+
+// ---- groups ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_head(const uint32_t* __restrict__ keys, int64_t i) {
+  const uint32_t k = keys[i];
+  return k != kKeyNone && (i == 0 || keys[i - 1] != k);
+}
+
+__global__ void __launch_bounds__(kThreads) group_count_kernel(DailyScratch d, int64_t n) {
+  const uint32_t* keys = parity_before(d.meta, 4) ? d.keys_b : d.keys_a;
+  const int64_t base = (int64_t)blockIdx.x * kTile;
+  uint32_t c = 0;
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const int64_t i = base + r * kThreads + threadIdx.x;
+    if (i < n) c += is_head(keys, i);
+  }
+  __shared__ uint32_t ws[kThreads / 32];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += ws[w];
+    d.tile_heads[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) group_scan_kernel(DailyScratch d, int nblk, pie_daily_out out) {
+  __shared__ uint32_t total;
+  block_exclusive_scan_inplace(d.tile_heads, nblk, &total);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *out.n_groups = (int64_t)total;
+    out.group_offsets[total] = (int32_t)d.meta->n_valid;
+    const unsigned long long err = d.meta->err;
+    out.status[0] = (err == ~0ull) ? 0 : -(int32_t)(err & 0xFFFFFFFFull);
+    out.status[1] = (err == ~0ull) ? -1 : (int32_t)(err >> 32);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) group_write_kernel(DailyScratch d, int64_t n, pie_daily_out out) {
+  const int par = parity_before(d.meta, 4);
+  const uint32_t* keys = par ? d.keys_b : d.keys_a;
+  const int32_t* vals = par ? d.vals_b : d.vals_a;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t tbase = (int64_t)blockIdx.x * kTile + (int64_t)tid * kItems;  // kItems consecutive per thread
+  bool head[kItems];
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int64_t i = tbase + j;
+    head[j] = (i < n) && is_head(keys, i);
+    c += head[j];
+  }
+  uint32_t incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __shared__ uint32_t ws[kThreads / 32];
+  if (lane == 31) ws[wid] = incl;
+  __syncthreads();
+  uint32_t run = d.tile_heads[blockIdx.x] + incl - c;
+  for (int w = 0; w < wid; ++w) run += ws[w];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int64_t i = tbase + j;
+    if (i < n) {
+      const int32_t s = vals[i];
+      out.show_order[i] = s;
+      if (head[j]) {
+        out.group_offsets[run] = (int32_t)i;
+        out.group_day_start[run] = out.show_day_start[s];
+        run += 1;
+      }
+    }
+  }
+}
+
+// metric m of show s as a Number, NaN when the reference's getValue yields null
+// (public/app.js:21-86, :3978-3988); validity is then isValidMetricValue == isfinite (:4128-4134).
+__device__ __forceinline__ double metric_value(const int32_t* __restrict__ si, const double* __restrict__ sf,
+                                               int64_t stride, int m, int64_t s) {
+  if (m < 4) return (double)si[(int64_t)m * stride + s];  // TOTAL, COMPLETED, NO_LAUNCH, ABORT planes 0..3
+  return sf[(int64_t)(m - 3) * stride + s];  // 4->AVG(1) 5->MAX(2) 6..8->rates(3..5) 9..18->issue rates(6..15)
+}
+
+__global__ void __launch_bounds__(128) daily_summary_kernel(const int32_t* __restrict__ si, const double* __restrict__ sf,
+                                                            int64_t stats_stride, pie_daily_out out) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= *out.n_groups) return;
+  const int m = blockIdx.y;
+  const int b = out.group_offsets[g], e = out.group_offsets[g + 1];
+  double sum = 0.0, mn = 0.0, mx = 0.0;
+  int n = 0;
+  for (int i = b; i < e; ++i) {
+    const double v = metric_value(si, sf, stats_stride, m, out.show_order[i]);
+    if (is_finite_f64(v)) {
+      sum = sum + v;  // left to right, initial 0 (:3481)
+      mn = n ? js_min(mn, v) : v;
+      mx = n ? js_max(mx, v) : v;
+      n += 1;
+    }
+  }
+  const double nan = quiet_nan();
+  const int64_t o = (int64_t)m * out.stride + g;
+  const int64_t plane = (int64_t)PIE_N_METRICS * out.stride;
+  out.summary_f64[PIE_DF_AVERAGE * plane + o] = n ? sum / (double)n : nan;
+  out.summary_f64[PIE_DF_MIN * plane + o] = n ? mn : nan;
+  out.summary_f64[PIE_DF_MAX * plane + o] = n ? mx : nan;
+  out.summary_count[o] = n;
+}
+
+cudaError_t launch_daily_summary(const pie_archive_view& v, const int32_t* si, const double* sf, int64_t stats_stride,
+                                 int32_t tz_offset_minutes, const pie_daily_out& out, void* scratch, int sm_count,
+                                 cudaStream_t stream) {
+  (void)sm_count;
+  const int64_t n = v.n_shows;
+  DailyScratch d = carve(scratch, n);
+  const int nblk = (int)n_tiles(n > 0 ? n : 1);
+  daily_init_kernel<<<1, 1, 0, stream>>>(d.meta);
+  g_launches += 2 + (n > 0 ? 4 + 12 : 0);  // init, group_scan + (show_day, 12 radix, group_count/write, summary)
+  if (n > 0) {
+    show_day_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
+        v, (int64_t)tz_offset_minutes * 60000, out.show_day_start, d.keys_a, d.vals_a, d.meta);
+    for (int pass = 0; pass < 4; ++pass) {
+      radix_hist_kernel<<<nblk, kThreads, 0, stream>>>(d, n, pass, nblk);
+      radix_scan_kernel<<<1, 1024, 0, stream>>>(d, pass, nblk);
+      radix_scatter_kernel<<<nblk, kThreads, 0, stream>>>(d, n, pass, nblk);
+    }
+    group_count_kernel<<<nblk, kThreads, 0, stream>>>(d, n);
+  } else {
+    cudaMemsetAsync(d.tile_heads, 0, sizeof(uint32_t), stream);
+  }
+  group_scan_kernel<<<1, 1024, 0, stream>>>(d, n > 0 ? nblk : 1, out);
+  if (n > 0) {
+    group_write_kernel<<<nblk, kThreads, 0, stream>>>(d, n, out);
+    dim3 grid((unsigned)((n + 127) / 128), PIE_N_METRICS);
+    daily_summary_kernel<<<grid, 128, 0, stream>>>(si, sf, stats_stride, out);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace pie

@@ -1,0 +1,354 @@
+// C ABI of libsphpie_b200 (include/sph_pie_b200.h).  Host-buffer entry points stage the columns an
+// operation reads into a grow-only device arena, run the kernels and copy the results back;
+// device entry points only enqueue kernels.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "pie_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+int g_sm_count = 0;
+std::mutex g_host_mutex;  // host entry points share one arena + stream
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define PIE_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(PIE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+int ensure_init() {
+  if (g_sm_count > 0) return PIE_OK;
+  return pie_init(-1);
+}
+
+// Grow-only device arena with bump allocation, reset at the start of every host entry point.
+struct Arena {
+  uint8_t* base = nullptr;
+  uint64_t cap = 0, used = 0;
+  cudaStream_t stream = nullptr;
+
+  int reserve(uint64_t bytes) {
+    if (!stream) PIE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    used = 0;
+    if (bytes <= cap) return PIE_OK;
+    if (base) PIE_CUDA(cudaFree(base));
+    base = nullptr;
+    cap = 0;
+    PIE_CUDA(cudaMalloc(&base, bytes));
+    cap = bytes;
+    return PIE_OK;
+  }
+  void* take(uint64_t bytes) {
+    uint64_t off = (used + 255) & ~(uint64_t)255;
+    used = off + bytes;
+    return base + off;
+  }
+};
+Arena g_arena;
+
+inline uint64_t pad(uint64_t b) { return ((b + 255) & ~(uint64_t)255) + 256; }
+
+struct StrColPlan {
+  const pie_strcol* src;
+  pie_strcol* dst;
+  int64_t n;
+  int32_t first, last;
+};
+
+// bytes needed on the device for a string column of n rows
+int plan_strcol(StrColPlan& p, const pie_strcol* src, pie_strcol* dst, int64_t n, uint64_t* bytes, const char* name) {
+  p.src = src; p.dst = dst; p.n = n;
+  if (!src->offsets) return fail(PIE_ERR_INVALID_ARG, "column %s: offsets is NULL", name);
+  p.first = src->offsets[0];
+  p.last = src->offsets[n];
+  if (p.last < p.first) return fail(PIE_ERR_INVALID_ARG, "column %s: offsets decrease", name);
+  if (p.last > p.first && !src->data) return fail(PIE_ERR_INVALID_ARG, "column %s: data is NULL", name);
+  *bytes += pad(4 * (uint64_t)(n + 1)) + pad((uint64_t)(p.last - p.first));
+  return PIE_OK;
+}
+
+int upload_strcol(const StrColPlan& p, uint64_t* h2d) {
+  int32_t* d_off = (int32_t*)g_arena.take(4 * (uint64_t)(p.n + 1));
+  const uint64_t nbytes = (uint64_t)(p.last - p.first);
+  uint8_t* d_data = (uint8_t*)g_arena.take(nbytes ? nbytes : 1);
+  PIE_CUDA(cudaMemcpyAsync(d_off, p.src->offsets, 4 * (uint64_t)(p.n + 1), cudaMemcpyHostToDevice, g_arena.stream));
+  if (nbytes)
+    PIE_CUDA(cudaMemcpyAsync(d_data, p.src->data + p.first, nbytes, cudaMemcpyHostToDevice, g_arena.stream));
+  p.dst->offsets = d_off;
+  p.dst->data = d_data - p.first;  // offsets keep their host values
+  *h2d += 4 * (uint64_t)(p.n + 1) + nbytes;
+  return PIE_OK;
+}
+
+template <typename T>
+int upload_array(const T* src, int64_t n, const T** dst, uint64_t* h2d) {
+  T* d = (T*)g_arena.take(sizeof(T) * (uint64_t)(n > 0 ? n : 1));
+  if (n > 0) PIE_CUDA(cudaMemcpyAsync(d, src, sizeof(T) * (uint64_t)n, cudaMemcpyHostToDevice, g_arena.stream));
+  *dst = d;
+  *h2d += sizeof(T) * (uint64_t)n;
+  return PIE_OK;
+}
+
+int check_view_common(const pie_archive_view* v) {
+  if (!v) return fail(PIE_ERR_INVALID_ARG, "view is NULL");
+  if (v->n_shows < 0 || v->n_entries < 0) return fail(PIE_ERR_INVALID_ARG, "negative row count");
+  if (v->n_shows > 0x7FFFFFF0LL || v->n_entries > 0x7FFFFFF0LL)
+    return fail(PIE_ERR_INVALID_ARG, "batch too large: split into batches of < 2^31 rows");
+  if (!v->entry_offsets) return fail(PIE_ERR_INVALID_ARG, "entry_offsets is NULL");
+  return PIE_OK;
+}
+
+uint64_t g_last_h2d = 0, g_last_d2h = 0;
+
+}  // namespace
+
+extern "C" {
+
+int pie_abi_version(void) { return PIE_ABI_VERSION; }
+
+const char* pie_last_error(void) { return g_err; }
+
+int pie_init(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(PIE_ERR_NO_DEVICE, "no CUDA device visible (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device >= 0) PIE_CUDA(cudaSetDevice(device));
+  int dev = 0;
+  PIE_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  PIE_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(PIE_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major,
+                prop.minor);
+  g_sm_count = prop.multiProcessorCount;
+  return PIE_OK;
+}
+
+int pie_device_sm_count(void) { return g_sm_count; }
+
+void* pie_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    fail(PIE_ERR_CUDA, "cudaHostAlloc(%llu) failed", (unsigned long long)bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+void pie_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+/* bytes moved by the most recent *_host call on this process (for bench.py's e2e accounting) */
+void pie_last_transfer_bytes(uint64_t* h2d, uint64_t* d2h) {
+  if (h2d) *h2d = g_last_h2d;
+  if (d2h) *d2h = g_last_d2h;
+}
+
+uint64_t pie_kernel_launch_count(void) { return pie::g_launches; }
+
+uint64_t pie_show_stats_scratch_bytes(int64_t n_entries) { return (uint64_t)(n_entries > 0 ? n_entries : 1); }
+
+int pie_show_stats_dev(const pie_archive_view* v, int32_t* stats_i32, double* stats_f64, int64_t stride, void* scratch,
+                       void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_view_common(v))) return rc;
+  if (!stats_i32 || !stats_f64 || !scratch) return fail(PIE_ERR_INVALID_ARG, "output or scratch is NULL");
+  if (stride < v->n_shows) return fail(PIE_ERR_INVALID_ARG, "stride < n_shows");
+  if (v->n_entries > 0 && (!v->status.offsets || !v->launched.offsets || !v->primary_issue.offsets || !v->delay_sec ||
+                           !v->delay_valid))
+    return fail(PIE_ERR_INVALID_ARG, "show stats reads status, launched, primary_issue, delay_sec, delay_valid");
+  PIE_CUDA(pie::launch_show_stats(*v, stats_i32, stats_f64, stride, scratch, g_sm_count, (cudaStream_t)stream));
+  return PIE_OK;
+}
+
+uint64_t pie_daily_scratch_bytes(int64_t n_shows) { return pie::daily_scratch_bytes(n_shows); }
+
+int pie_daily_summary_dev(const pie_archive_view* v, const int32_t* stats_i32, const double* stats_f64,
+                          int64_t stats_stride, int32_t tz_offset_minutes, const pie_daily_out* out, void* scratch,
+                          void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_view_common(v))) return rc;
+  if (!stats_i32 || !stats_f64 || !out || !scratch) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  if (stats_stride < v->n_shows || out->stride < v->n_shows) return fail(PIE_ERR_INVALID_ARG, "stride < n_shows");
+  if (tz_offset_minutes < -24 * 60 || tz_offset_minutes > 24 * 60)
+    return fail(PIE_ERR_INVALID_ARG, "tz_offset_minutes out of range");
+  if (!out->show_day_start || !out->show_order || !out->group_day_start || !out->group_offsets || !out->summary_f64 ||
+      !out->summary_count || !out->n_groups || !out->status)
+    return fail(PIE_ERR_INVALID_ARG, "pie_daily_out has a NULL array");
+  if (v->n_shows > 0 && !v->created_at) return fail(PIE_ERR_INVALID_ARG, "created_at is NULL");
+  PIE_CUDA(pie::launch_daily_summary(*v, stats_i32, stats_f64, stats_stride, tz_offset_minutes, *out, scratch,
+                                     g_sm_count, (cudaStream_t)stream));
+  return PIE_OK;
+}
+
+static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_minutes, int32_t* stats_i32,
+                                 double* stats_f64, int64_t stats_stride, const pie_daily_out* hout) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_view_common(hv))) return rc;
+  const int64_t S = hv->n_shows, E = hv->n_entries;
+  const bool want_daily = hout != nullptr;
+  const bool want_stats = stats_i32 != nullptr || stats_f64 != nullptr;
+  if (want_stats && (!stats_i32 || !stats_f64)) return fail(PIE_ERR_INVALID_ARG, "stats_i32 and stats_f64 go together");
+  if (want_stats && stats_stride < S) return fail(PIE_ERR_INVALID_ARG, "stats_stride < n_shows");
+  if (S > 0 && hv->entry_offsets[S] - hv->entry_offsets[0] != E)
+    return fail(PIE_ERR_INVALID_ARG, "entry_offsets span %d rows but n_entries is %lld",
+                hv->entry_offsets[S] - hv->entry_offsets[0], (long long)E);
+  if (S > 0 && hv->entry_offsets[0] != 0) return fail(PIE_ERR_INVALID_ARG, "entry_offsets[0] must be 0");
+  if (E > 0 && (!hv->delay_sec || !hv->delay_valid)) return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
+  if (want_daily) {
+    if (hout->stride < S) return fail(PIE_ERR_INVALID_ARG, "pie_daily_out.stride < n_shows");
+    if (!hout->show_day_start || !hout->show_order || !hout->group_day_start || !hout->group_offsets ||
+        !hout->summary_f64 || !hout->summary_count || !hout->n_groups || !hout->status)
+      return fail(PIE_ERR_INVALID_ARG, "pie_daily_out has a NULL array");
+    if (S > 0 && !hv->created_at) return fail(PIE_ERR_INVALID_ARG, "created_at is NULL");
+  }
+
+  // ---- plan device memory
+  uint64_t bytes = 0;
+  StrColPlan p_status, p_launched, p_issue, p_date, p_time;
+  if ((rc = plan_strcol(p_status, &hv->status, nullptr, E, &bytes, "status"))) return rc;
+  if ((rc = plan_strcol(p_launched, &hv->launched, nullptr, E, &bytes, "launched"))) return rc;
+  if ((rc = plan_strcol(p_issue, &hv->primary_issue, nullptr, E, &bytes, "primary_issue"))) return rc;
+  const bool has_date = want_daily && hv->show_date.offsets;
+  const bool has_time = has_date && hv->show_time.offsets;
+  if (has_date && (rc = plan_strcol(p_date, &hv->show_date, nullptr, S, &bytes, "show_date"))) return rc;
+  if (has_time && (rc = plan_strcol(p_time, &hv->show_time, nullptr, S, &bytes, "show_time"))) return rc;
+  const int64_t Sc = S > 0 ? S : 1;
+  bytes += pad(4 * (uint64_t)(S + 1)) + pad(8 * (uint64_t)E) + pad((uint64_t)E);          // offsets, delay, valid
+  bytes += pad(pie_show_stats_scratch_bytes(E));                                           // codes
+  bytes += pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc);                  // stats planes
+  if (want_daily) {
+    bytes += 2 * pad(8 * (uint64_t)Sc) + pad(8 * (uint64_t)E);                             // created, archived, entry_ts
+    bytes += pad(pie::daily_scratch_bytes(S));
+    bytes += pad(8ull * Sc) * 2 + pad(4ull * Sc) + pad(4ull * (Sc + 1));                    // day_start, group_day, order, goffs
+    bytes += pad(8ull * PIE_DF_COUNT * PIE_N_METRICS * Sc) + pad(4ull * PIE_N_METRICS * Sc) + pad(64);
+  }
+  if ((rc = g_arena.reserve(bytes))) return rc;
+  cudaStream_t st = g_arena.stream;
+
+  // ---- H2D
+  uint64_t h2d = 0, d2h = 0;
+  pie_archive_view dv;
+  memset(&dv, 0, sizeof(dv));
+  dv.n_shows = S;
+  dv.n_entries = E;
+  if ((rc = upload_array(hv->entry_offsets, S + 1, &dv.entry_offsets, &h2d))) return rc;
+  p_status.dst = &dv.status; p_launched.dst = &dv.launched; p_issue.dst = &dv.primary_issue;
+  if ((rc = upload_strcol(p_status, &h2d))) return rc;
+  if ((rc = upload_strcol(p_launched, &h2d))) return rc;
+  if ((rc = upload_strcol(p_issue, &h2d))) return rc;
+  if ((rc = upload_array(hv->delay_sec, E, &dv.delay_sec, &h2d))) return rc;
+  if ((rc = upload_array(hv->delay_valid, E, &dv.delay_valid, &h2d))) return rc;
+  if (want_daily) {
+    if (S > 0 && (rc = upload_array(hv->created_at, S, &dv.created_at, &h2d))) return rc;
+    if (hv->archived_at && (rc = upload_array(hv->archived_at, S, &dv.archived_at, &h2d))) return rc;
+    if (hv->entry_ts && (rc = upload_array(hv->entry_ts, E, &dv.entry_ts, &h2d))) return rc;
+    if (has_date) { p_date.dst = &dv.show_date; if ((rc = upload_strcol(p_date, &h2d))) return rc; }
+    if (has_time) { p_time.dst = &dv.show_time; if ((rc = upload_strcol(p_time, &h2d))) return rc; }
+  }
+
+  // ---- kernels
+  void* codes = g_arena.take(pie_show_stats_scratch_bytes(E));
+  int32_t* d_si = (int32_t*)g_arena.take(4ull * PIE_SI_COUNT * Sc);
+  double* d_sf = (double*)g_arena.take(8ull * PIE_SF_COUNT * Sc);
+  PIE_CUDA(pie::launch_show_stats(dv, d_si, d_sf, Sc, codes, g_sm_count, st));
+
+  pie_daily_out dout;
+  memset(&dout, 0, sizeof(dout));
+  if (want_daily) {
+    dout.stride = Sc;
+    dout.show_day_start = (int64_t*)g_arena.take(8ull * Sc);
+    dout.group_day_start = (int64_t*)g_arena.take(8ull * Sc);
+    dout.show_order = (int32_t*)g_arena.take(4ull * Sc);
+    dout.group_offsets = (int32_t*)g_arena.take(4ull * (Sc + 1));
+    dout.summary_f64 = (double*)g_arena.take(8ull * PIE_DF_COUNT * PIE_N_METRICS * Sc);
+    dout.summary_count = (int32_t*)g_arena.take(4ull * PIE_N_METRICS * Sc);
+    dout.n_groups = (int64_t*)g_arena.take(16);
+    dout.status = (int32_t*)g_arena.take(16);
+    void* dscratch = g_arena.take(pie::daily_scratch_bytes(S));
+    PIE_CUDA(pie::launch_daily_summary(dv, d_si, d_sf, Sc, tz_offset_minutes, dout, dscratch, g_sm_count, st));
+  }
+
+  // ---- D2H
+  if (want_stats && S > 0) {
+    PIE_CUDA(cudaMemcpy2DAsync(stats_i32, 4 * (uint64_t)stats_stride, d_si, 4 * (uint64_t)Sc, 4 * (uint64_t)S,
+                               PIE_SI_COUNT, cudaMemcpyDeviceToHost, st));
+    PIE_CUDA(cudaMemcpy2DAsync(stats_f64, 8 * (uint64_t)stats_stride, d_sf, 8 * (uint64_t)Sc, 8 * (uint64_t)S,
+                               PIE_SF_COUNT, cudaMemcpyDeviceToHost, st));
+    d2h += (4ull * PIE_SI_COUNT + 8ull * PIE_SF_COUNT) * (uint64_t)S;
+  }
+  if (want_daily) {
+    PIE_CUDA(cudaMemcpyAsync(hout->n_groups, dout.n_groups, 8, cudaMemcpyDeviceToHost, st));
+    PIE_CUDA(cudaMemcpyAsync(hout->status, dout.status, 8, cudaMemcpyDeviceToHost, st));
+    PIE_CUDA(cudaStreamSynchronize(st));
+    d2h += 16;
+    if (hout->status[0] != 0) {
+      g_last_h2d = h2d; g_last_d2h = d2h;
+      const int code = hout->status[0];
+      return fail(code, code == PIE_ERR_RANGE ? "RangeError: Invalid time value (show %d)"
+                                              : "show %d: date/time is not an ECMA-262 date-time string",
+                  hout->status[1]);
+    }
+    const int64_t G = *hout->n_groups;
+    if (S > 0) {
+      PIE_CUDA(cudaMemcpyAsync(hout->show_day_start, dout.show_day_start, 8 * (uint64_t)S, cudaMemcpyDeviceToHost, st));
+      PIE_CUDA(cudaMemcpyAsync(hout->show_order, dout.show_order, 4 * (uint64_t)S, cudaMemcpyDeviceToHost, st));
+      d2h += 12 * (uint64_t)S;
+    }
+    PIE_CUDA(cudaMemcpyAsync(hout->group_offsets, dout.group_offsets, 4 * (uint64_t)(G + 1), cudaMemcpyDeviceToHost, st));
+    d2h += 4 * (uint64_t)(G + 1);
+    if (G > 0) {
+      PIE_CUDA(cudaMemcpyAsync(hout->group_day_start, dout.group_day_start, 8 * (uint64_t)G, cudaMemcpyDeviceToHost, st));
+      PIE_CUDA(cudaMemcpy2DAsync(hout->summary_f64, 8 * (uint64_t)hout->stride, dout.summary_f64, 8 * (uint64_t)Sc,
+                                 8 * (uint64_t)G, PIE_DF_COUNT * PIE_N_METRICS, cudaMemcpyDeviceToHost, st));
+      PIE_CUDA(cudaMemcpy2DAsync(hout->summary_count, 4 * (uint64_t)hout->stride, dout.summary_count, 4 * (uint64_t)Sc,
+                                 4 * (uint64_t)G, PIE_N_METRICS, cudaMemcpyDeviceToHost, st));
+      d2h += (8ull + 8ull * PIE_DF_COUNT * PIE_N_METRICS + 4ull * PIE_N_METRICS) * (uint64_t)G;
+    }
+  }
+  PIE_CUDA(cudaStreamSynchronize(st));
+  g_last_h2d = h2d;
+  g_last_d2h = d2h;
+  return PIE_OK;
+}
+
+int pie_archive_analytics_host(const pie_archive_view* hv, int32_t tz_offset_minutes, int32_t* stats_i32,
+                               double* stats_f64, int64_t stats_stride, const pie_daily_out* hout) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (tz_offset_minutes < -24 * 60 || tz_offset_minutes > 24 * 60)
+    return fail(PIE_ERR_INVALID_ARG, "tz_offset_minutes out of range");
+  if (!hout) return fail(PIE_ERR_INVALID_ARG, "pie_daily_out is NULL (use pie_show_stats_host for stats only)");
+  return analytics_host_locked(hv, tz_offset_minutes, stats_i32, stats_f64, stats_stride, hout);
+}
+
+int pie_show_stats_host(const pie_archive_view* hv, int32_t* stats_i32, double* stats_f64, int64_t stride) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (!stats_i32 || !stats_f64) return fail(PIE_ERR_INVALID_ARG, "output is NULL");
+  return analytics_host_locked(hv, 0, stats_i32, stats_f64, stride, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,23 @@
+// Internal launch API between the kernel translation units and the C ABI (pie_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sph_pie_b200.h"
+
+namespace pie {
+
+// cumulative number of kernels this library has launched (bench.py reports it as gpu_launches)
+extern unsigned long long g_launches;
+
+// archive_stats.cu
+cudaError_t launch_show_stats(const pie_archive_view& dev_view, int32_t* stats_i32, double* stats_f64,
+                              int64_t stride, void* scratch, int sm_count, cudaStream_t stream);
+
+// archive_daily.cu
+uint64_t daily_scratch_bytes(int64_t n_shows);
+cudaError_t launch_daily_summary(const pie_archive_view& dev_view, const int32_t* stats_i32,
+                                 const double* stats_f64, int64_t stats_stride, int32_t tz_offset_minutes,
+                                 const pie_daily_out& out, void* scratch, int sm_count, cudaStream_t stream);
+
+}  // namespace pie

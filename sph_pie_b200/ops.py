@@ -1,0 +1,161 @@
+"""Operators over an ArchiveTable: thin Python over the C ABI (include/sph_pie_b200.h).
+
+A CUDA-resident table goes through the `*_dev` entry points on torch's current stream (outputs are
+CUDA tensors); a host table goes through the `*_host` entry points, which copy host->device, run
+the kernels and copy the results back (outputs are CPU tensors).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .columnar import ArchiveTable
+
+
+@dataclass
+class ShowStats:
+    """Plane-major per-show statistics (computeArchiveShowStats, reference public/app.js:3939-3952)."""
+    i32: torch.Tensor  # int32 [PIE_SI_COUNT, n_shows]
+    f64: torch.Tensor  # float64 [PIE_SF_COUNT, n_shows]
+
+
+@dataclass
+class DailySummary:
+    """Daily groups and metric summaries (reference public/app.js:3401-3502)."""
+    n_groups: int
+    show_day_start: torch.Tensor   # int64 [n_shows]
+    show_order: torch.Tensor       # int32 [n_shows]
+    group_day_start: torch.Tensor  # int64 [n_groups]
+    group_offsets: torch.Tensor    # int32 [n_groups + 1]
+    summary_f64: torch.Tensor      # float64 [3, 19, n_groups]   (average, min, max)
+    summary_count: torch.Tensor    # int32 [19, n_groups]
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DailyBuffers:
+    """Pre-allocated outputs + scratch for the device entry points (reused across calls)."""
+
+    def __init__(self, n_shows: int, n_entries: int, device):
+        lib = _lib.load()
+        S = max(n_shows, 1)
+        self.S = S
+        self.stats_i32 = torch.empty((_lib.PIE_SI_COUNT, S), dtype=torch.int32, device=device)
+        self.stats_f64 = torch.empty((_lib.PIE_SF_COUNT, S), dtype=torch.float64, device=device)
+        self.stats_scratch = torch.empty(int(lib.pie_show_stats_scratch_bytes(n_entries)), dtype=torch.uint8,
+                                         device=device)
+        self.show_day_start = torch.empty(S, dtype=torch.int64, device=device)
+        self.show_order = torch.empty(S, dtype=torch.int32, device=device)
+        self.group_day_start = torch.empty(S, dtype=torch.int64, device=device)
+        self.group_offsets = torch.empty(S + 1, dtype=torch.int32, device=device)
+        self.summary_f64 = torch.empty((_lib.PIE_DF_COUNT, _lib.PIE_N_METRICS, S), dtype=torch.float64, device=device)
+        self.summary_count = torch.empty((_lib.PIE_N_METRICS, S), dtype=torch.int32, device=device)
+        self.n_groups = torch.zeros(1, dtype=torch.int64, device=device)
+        self.status = torch.zeros(2, dtype=torch.int32, device=device)
+        self.daily_scratch = torch.empty(int(lib.pie_daily_scratch_bytes(n_shows)), dtype=torch.uint8, device=device)
+
+    def daily_out(self) -> _lib.DailyOutC:
+        return _lib.DailyOutC(self.S, self.show_day_start.data_ptr(), self.show_order.data_ptr(),
+                              self.group_day_start.data_ptr(), self.group_offsets.data_ptr(),
+                              self.summary_f64.data_ptr(), self.summary_count.data_ptr(),
+                              self.n_groups.data_ptr(), self.status.data_ptr())
+
+
+def show_stats_dev(table: ArchiveTable, bufs: DailyBuffers) -> None:
+    """Enqueue the show-statistics kernels on torch's current stream (no sync)."""
+    _lib.ensure_init()
+    view = table.view()
+    _lib.check(_lib.load().pie_show_stats_dev(C.byref(view), bufs.stats_i32.data_ptr(), bufs.stats_f64.data_ptr(),
+                                              bufs.S, bufs.stats_scratch.data_ptr(), _stream_ptr()))
+
+
+def daily_summary_dev(table: ArchiveTable, bufs: DailyBuffers, tz_offset_minutes: int = 0) -> None:
+    """Enqueue the daily-group kernels (reads bufs.stats_*) on torch's current stream (no sync)."""
+    _lib.ensure_init()
+    view = table.view()
+    out = bufs.daily_out()
+    _lib.check(_lib.load().pie_daily_summary_dev(C.byref(view), bufs.stats_i32.data_ptr(), bufs.stats_f64.data_ptr(),
+                                                 bufs.S, tz_offset_minutes, C.byref(out),
+                                                 bufs.daily_scratch.data_ptr(), _stream_ptr()))
+
+
+def _raise_daily_status(code: int, show: int) -> None:
+    if code == _lib.PIE_ERR_RANGE:
+        raise _lib.JsRangeError(code, f"RangeError: Invalid time value (show {show})")
+    if code == _lib.PIE_ERR_UNSUPPORTED_DATE:
+        raise _lib.UnsupportedDateError(code, f"show {show}: date/time is not an ECMA-262 date-time string")
+    if code != 0:
+        raise _lib.PieError(code, f"daily summary failed at show {show}")
+
+
+def show_stats(table: ArchiveTable) -> ShowStats:
+    """computeArchiveShowStats for every show of the table."""
+    _lib.ensure_init()
+    S = table.n_shows
+    if table.is_cuda:
+        bufs = DailyBuffers(S, table.n_entries, table.device)
+        show_stats_dev(table, bufs)
+        return ShowStats(bufs.stats_i32[:, :S], bufs.stats_f64[:, :S])
+    Sc = max(S, 1)
+    i32 = torch.empty((_lib.PIE_SI_COUNT, Sc), dtype=torch.int32)
+    f64 = torch.empty((_lib.PIE_SF_COUNT, Sc), dtype=torch.float64)
+    view = table.view()
+    _lib.check(_lib.load().pie_show_stats_host(C.byref(view), i32.data_ptr(), f64.data_ptr(), Sc))
+    return ShowStats(i32[:, :S], f64[:, :S])
+
+
+class HostOutputs:
+    """Reusable (optionally pinned) host result buffers for archive_analytics on a host table."""
+
+    def __init__(self, n_shows: int, pinned: bool = False):
+        S = max(n_shows, 1)
+        self.S = S
+        kw = dict(pin_memory=pinned)
+        self.stats_i32 = torch.empty((_lib.PIE_SI_COUNT, S), dtype=torch.int32, **kw)
+        self.stats_f64 = torch.empty((_lib.PIE_SF_COUNT, S), dtype=torch.float64, **kw)
+        self.show_day_start = torch.empty(S, dtype=torch.int64, **kw)
+        self.show_order = torch.empty(S, dtype=torch.int32, **kw)
+        self.group_day_start = torch.empty(S, dtype=torch.int64, **kw)
+        self.group_offsets = torch.empty(S + 1, dtype=torch.int32, **kw)
+        self.summary_f64 = torch.empty((_lib.PIE_DF_COUNT, _lib.PIE_N_METRICS, S), dtype=torch.float64, **kw)
+        self.summary_count = torch.empty((_lib.PIE_N_METRICS, S), dtype=torch.int32, **kw)
+        self.n_groups = torch.zeros(1, dtype=torch.int64, **kw)
+        self.status = torch.zeros(2, dtype=torch.int32, **kw)
+
+    def daily_out(self) -> _lib.DailyOutC:
+        return _lib.DailyOutC(self.S, self.show_day_start.data_ptr(), self.show_order.data_ptr(),
+                              self.group_day_start.data_ptr(), self.group_offsets.data_ptr(),
+                              self.summary_f64.data_ptr(), self.summary_count.data_ptr(),
+                              self.n_groups.data_ptr(), self.status.data_ptr())
+
+
+def archive_analytics(table: ArchiveTable, tz_offset_minutes: int = 0, bufs=None):
+    """Show statistics + daily groups + metric summaries: what buildArchiveDailyGroups followed by
+    getOrCreateGroupMetricSummary for every metric computes.  Returns (ShowStats, DailySummary)."""
+    _lib.ensure_init()
+    S = table.n_shows
+    if table.is_cuda:
+        b = bufs if bufs is not None else DailyBuffers(S, table.n_entries, table.device)
+        show_stats_dev(table, b)
+        daily_summary_dev(table, b, tz_offset_minutes)
+        code, show = (int(x) for x in b.status.cpu())  # syncs the stream
+        _raise_daily_status(code, show)
+        G = int(b.n_groups.cpu())
+        return (ShowStats(b.stats_i32[:, :S], b.stats_f64[:, :S]),
+                DailySummary(G, b.show_day_start[:S], b.show_order[:S], b.group_day_start[:G],
+                             b.group_offsets[:G + 1], b.summary_f64[:, :, :G], b.summary_count[:, :G]))
+    h = bufs if bufs is not None else HostOutputs(S)
+    view = table.view()
+    out = h.daily_out()
+    _lib.check(_lib.load().pie_archive_analytics_host(C.byref(view), tz_offset_minutes, h.stats_i32.data_ptr(),
+                                                      h.stats_f64.data_ptr(), h.S, C.byref(out)))
+    G = int(h.n_groups[0])
+    return (ShowStats(h.stats_i32[:, :S], h.stats_f64[:, :S]),
+            DailySummary(G, h.show_day_start[:S], h.show_order[:S], h.group_day_start[:G], h.group_offsets[:G + 1],
+                         h.summary_f64[:, :, :G], h.summary_count[:, :G]))

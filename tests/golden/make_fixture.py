@@ -1,0 +1,42 @@
+"""Writes tests/golden/webhook_fixture.json.
+
+The `show` and `entry` objects are the reference's only test fixture
+(/root/reference/scripts/simulate-webhook.js:42-65).  The reference checks them only against its
+own builders (:75-95), so it pins column ORDER and shape; it holds no expected values.  The
+`expected_*` members below are therefore a hand derivation from reading
+server/webhookDispatcher.js:276-342, computed with oracle/pie_oracle.py and reviewed by eye; they
+are NOT output of the reference (no JS engine exists in the build image).
+Run from the repo root:  python tests/golden/make_fixture.py
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import pie_oracle as po  # noqa: E402
+
+show = {
+    "id": "simulation-show", "date": "2024-07-04", "time": "21:00", "label": "Independence Demo",
+    "crew": ["Alex", "Nazar"], "leadPilot": "Alex", "monkeyLead": "Nazar", "notes": "Verification run",
+}
+entry = {
+    "id": "entry-001", "unitId": "Drone-01", "planned": "Yes", "launched": "Yes", "status": "Completed",
+    "actions": ["Logged only"], "operator": "Alex", "batteryId": "B-12", "delaySec": 0, "commandRx": "Yes",
+    "notes": "Green across the board",
+}
+row = po.build_table_row(show, entry)
+doc = {
+    "source": "scripts/simulate-webhook.js:42-65 (show, entry); expected_* hand-derived, see make_fixture.py",
+    "export_columns": po.EXPORT_COLUMNS,
+    "show": show,
+    "entry": entry,
+    "expected_table_row": [row[c] for c in po.EXPORT_COLUMNS],
+    "expected_message": po.build_message_payload(row),
+    "expected_csv_row": po.build_csv_row(row),
+    "expected_archive_entry_payload": po.build_archive_entry_payload(show, entry),
+    "expected_show_stats": po.compute_archive_show_stats({**show, "entries": [entry]}),
+}
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "webhook_fixture.json"), "w") as f:
+    json.dump(doc, f, indent=1)
+print(json.dumps(doc, indent=1))

@@ -1,0 +1,98 @@
+"""Host-side logic that needs no GPU: packing, slicing, date keys, the ABI surface."""
+import os
+import re
+
+import pytest
+import torch
+
+from sph_pie_b200 import _lib
+from sph_pie_b200.archive import _iso_date_key
+from sph_pie_b200.columnar import pack_shows
+from sph_pie_b200.synth import synth_archive, table_to_shows
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    header = open(os.path.join(ROOT, "include", "sph_pie_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pie_[a-z0-9_]+)\s*\(", body))
+    assert declared, "no functions found in the header"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/sph_pie_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.pie_abi_version() == 1
+
+
+def test_struct_layouts_match_header(built):
+    import ctypes as C
+
+    assert C.sizeof(_lib.StrColC) == 16 and C.sizeof(_lib.StrListColC) == 24
+    # 3 scalars/pointers + 7 strcols + strlist + 2 ptr + 14 strcols + strlist + 3 ptr
+    assert C.sizeof(_lib.ArchiveViewC) == 8 * 3 + 16 * 7 + 24 + 16 + 16 * 14 + 24 + 24
+    assert C.sizeof(_lib.DailyOutC) == 8 * 9
+
+
+def test_no_gpu_means_loud_failure(built):
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.PieError) as e:
+        _lib.init(0)
+    assert e.value.code == _lib.PIE_ERR_NO_DEVICE
+    from sph_pie_b200 import computeArchiveShowStats
+
+    with pytest.raises(_lib.PieError):
+        computeArchiveShowStats({"entries": []})
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "sph_pie_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "pie_oracle" not in text and "oracle_c" not in text and "libpie_oracle" not in text, f
+
+
+def test_pack_shows_schema():
+    t = pack_shows([{"id": "s", "crew": ["a", None, "b"], "createdAt": 5, "entries": [
+        {"status": "Abort", "delaySec": 3, "actions": ["x", "y"], "ts": 7}, {"delaySec": None}]}, None])
+    assert (t.n_shows, t.n_entries) == (2, 2)
+    assert t.entry_offsets.tolist() == [0, 2, 2]
+    assert t.entry_cols["status"].get(0) == "Abort" and t.entry_cols["status"].get(1) == ""
+    assert t.delay_valid.tolist() == [1, 0] and t.delay_sec.tolist()[0] == 3.0
+    assert t.crew.list_offsets.tolist() == [0, 3, 3] and t.crew.items.get(1) == ""
+    assert t.created_at[0] == 5 and torch.isnan(t.created_at[1])
+    with pytest.raises(TypeError):
+        pack_shows([{"entries": [{"status": 5}]}])
+    with pytest.raises(TypeError):
+        pack_shows([{"entries": [{"delaySec": "5"}]}])
+    with pytest.raises(TypeError):
+        pack_shows([{"label": "\ud800"}])
+
+
+def test_slice_shows_keeps_absolute_string_offsets():
+    t = synth_archive(50, seed=3)
+    part = t.slice_shows(10, 30)
+    assert part.n_shows == 20 and part.entry_offsets[0] == 0
+    assert part.n_entries == int(t.entry_offsets[30] - t.entry_offsets[10])
+    whole, sl = table_to_shows(t), table_to_shows(part)
+    assert sl == whole[10:30]
+
+
+def test_iso_date_key():
+    assert _iso_date_key(0) == "1970-01-01" and _iso_date_key(-1) == "1969-12-31"
+    assert _iso_date_key(1719964800000) == "2024-07-03"
+    assert _iso_date_key(253402300800000) == "+010000-01"[:10]   # year 10000: toISOString is +010000-01-01T...
+    assert _iso_date_key(-62198755200000) == "-000001-01"[:10]
+
+
+def test_synth_is_deterministic_and_well_formed():
+    a, b = synth_archive(100, seed=11), synth_archive(100, seed=11)
+    assert torch.equal(a.entry_cols["status"].data, b.entry_cols["status"].data)
+    assert torch.equal(a.delay_sec.view(torch.int64), b.delay_sec.view(torch.int64))
+    for c in list(a.entry_cols.values()) + list(a.show_cols.values()):
+        o = c.offsets
+        assert o[0] == 0 and bool((o[1:] >= o[:-1]).all()) and int(o[-1]) == c.data.numel()
+    assert int(a.entry_offsets[-1]) == a.n_entries
