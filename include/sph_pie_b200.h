@@ -98,19 +98,18 @@ enum {
   PIE_SI_LAUNCHED = 4,     /* launchedCount */
   PIE_SI_DELAY_COUNT = 5,  /* delayValues.length */
   PIE_SI_ISSUE_COUNT0 = 6, /* issueCounts[PRIMARY_ISSUES[k]], k = 0..9 (0 = key absent) */
-  PIE_SI_ISSUE_FIRST0 = 16,/* entry index (within the show) that first produced issue k, -1 if none:
-                              recovers issueCounts' property insertion order */
-  PIE_SI_COUNT = 26
+  PIE_SI_ISSUE_ORDER_LO = 16, /* property insertion order of issueCounts: 4-bit nibbles, nibble j = */
+  PIE_SI_ISSUE_ORDER_HI = 17, /* (k+1) of the j-th distinct issue met, 0 ends; LO = bits 0-31, HI = 32-39 */
+  PIE_SI_COUNT = 18
 };
 enum {
-  PIE_SF_DELAY_SUM = 0,       /* delaySum (left-to-right, initial 0) */
-  PIE_SF_AVG_DELAY = 1,       /* avgDelaySec */
-  PIE_SF_MAX_DELAY = 2,       /* maxDelaySec */
-  PIE_SF_COMPLETION_RATE = 3, /* completionRate */
-  PIE_SF_LAUNCH_RATE = 4,     /* launchRate */
-  PIE_SF_ABORT_RATE = 5,      /* abortRate */
-  PIE_SF_ISSUE_RATE0 = 6,     /* issueRates[PRIMARY_ISSUES[k]] */
-  PIE_SF_COUNT = 16
+  PIE_SF_AVG_DELAY = 0,       /* avgDelaySec */
+  PIE_SF_MAX_DELAY = 1,       /* maxDelaySec */
+  PIE_SF_COMPLETION_RATE = 2, /* completionRate */
+  PIE_SF_LAUNCH_RATE = 3,     /* launchRate */
+  PIE_SF_ABORT_RATE = 4,      /* abortRate */
+  PIE_SF_ISSUE_RATE0 = 5,     /* issueRates[PRIMARY_ISSUES[k]] */
+  PIE_SF_COUNT = 15
 };
 
 /* ---- planes of the per-day summary table -----------------------------------------------------
@@ -153,11 +152,9 @@ uint64_t pie_kernel_launch_count(void);
 
 /* ---- archive statistics: replaces computeArchiveShowStats (public/app.js:3898-3953), called per
  * show from buildArchiveDailyGroups (:3429-3432).  Reads: entry_offsets, status, launched,
- * primary_issue, delay_sec, delay_valid.
- * `scratch` (dev variant): device buffer of pie_show_stats_scratch_bytes(n_entries) bytes. */
-uint64_t pie_show_stats_scratch_bytes(int64_t n_entries);
+ * primary_issue, delay_sec, delay_valid.  One kernel, no scratch. */
 int pie_show_stats_dev(const pie_archive_view* dev_view, int32_t* stats_i32, double* stats_f64,
-                       int64_t stride, void* scratch, void* stream);
+                       int64_t stride, void* stream);
 int pie_show_stats_host(const pie_archive_view* host_view, int32_t* stats_i32, double* stats_f64,
                         int64_t stride);
 
@@ -177,6 +174,12 @@ int pie_daily_summary_dev(const pie_archive_view* dev_view, const int32_t* stats
 int pie_archive_analytics_host(const pie_archive_view* host_view, int32_t tz_offset_minutes,
                                int32_t* stats_i32, double* stats_f64, int64_t stats_stride,
                                const pie_daily_out* host_out);
+
+/* ---- self tests (device code paths that replace an IEEE operation by a faster exact sequence) */
+/* Compares the shared-reciprocal quotient used for the rate columns with IEEE a/b for every
+ * 0 <= a <= b <= max_b (max_b <= 4096, the largest b the kernels use it for); writes the number of
+ * bit mismatches (must be 0). */
+int pie_selftest_fast_div(int32_t max_b, uint64_t* mismatches);
 
 #ifdef __cplusplus
 }

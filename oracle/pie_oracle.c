@@ -96,8 +96,10 @@ static double js_min2(double a, double b) {
 static void show_stats_one(const pie_archive_view* v, int64_t s, int32_t* si, double* sf, int64_t stride) {
   int e0 = v->entry_offsets[s], e1 = v->entry_offsets[s + 1];
   int completed = 0, no_launch = 0, abort_n = 0, launched = 0, delay_n = 0;
-  int issue_n[PIE_N_ISSUES], issue_first[PIE_N_ISSUES];
-  for (int k = 0; k < PIE_N_ISSUES; ++k) { issue_n[k] = 0; issue_first[k] = -1; }
+  int issue_n[PIE_N_ISSUES];
+  for (int k = 0; k < PIE_N_ISSUES; ++k) issue_n[k] = 0;
+  uint64_t order = 0; /* 4-bit nibbles: (k+1) of the j-th distinct issue met = property insertion order */
+  int n_distinct = 0;
   double sum = 0.0, mx = 0.0;
   for (int e = e0; e < e1; ++e) {
     const uint8_t* st = v->status.data + v->status.offsets[e];
@@ -123,7 +125,7 @@ static void show_stats_one(const pie_archive_view* v, int64_t s, int32_t* si, do
           break;
         }
       }
-      if (issue_n[k] == 0) issue_first[k] = e - e0;
+      if (issue_n[k] == 0) order |= (uint64_t)(k + 1) << (4 * n_distinct++);
       issue_n[k]++;
     }
   }
@@ -134,7 +136,8 @@ static void show_stats_one(const pie_archive_view* v, int64_t s, int32_t* si, do
   si[PIE_SI_ABORT * stride + s] = abort_n;
   si[PIE_SI_LAUNCHED * stride + s] = launched;
   si[PIE_SI_DELAY_COUNT * stride + s] = delay_n;
-  sf[PIE_SF_DELAY_SUM * stride + s] = sum;
+  si[PIE_SI_ISSUE_ORDER_LO * stride + s] = (int32_t)(uint32_t)(order & 0xFFFFFFFFu);
+  si[PIE_SI_ISSUE_ORDER_HI * stride + s] = (int32_t)(uint32_t)(order >> 32);
   sf[PIE_SF_AVG_DELAY * stride + s] = delay_n ? sum / delay_n : NAN;
   sf[PIE_SF_MAX_DELAY * stride + s] = delay_n ? mx : NAN;
   sf[PIE_SF_COMPLETION_RATE * stride + s] = total ? ((double)completed / total) * 100 : NAN;
@@ -142,7 +145,6 @@ static void show_stats_one(const pie_archive_view* v, int64_t s, int32_t* si, do
   sf[PIE_SF_ABORT_RATE * stride + s] = total ? ((double)abort_n / total) * 100 : NAN;
   for (int k = 0; k < PIE_N_ISSUES; ++k) {
     si[(PIE_SI_ISSUE_COUNT0 + k) * stride + s] = issue_n[k];
-    si[(PIE_SI_ISSUE_FIRST0 + k) * stride + s] = issue_first[k];
     sf[(PIE_SF_ISSUE_RATE0 + k) * stride + s] = total ? ((double)issue_n[k] / total) * 100 : NAN;
   }
 }

@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libsphpie_b200.so")
 
 PIE_N_ISSUES = 10
 PIE_N_METRICS = 19
-PIE_SI_COUNT = 26
-PIE_SF_COUNT = 16
+PIE_SI_COUNT = 18
+PIE_SF_COUNT = 15
 PIE_DF_COUNT = 3
 PIE_DAY_NONE = -(2 ** 63)
 
@@ -29,9 +29,10 @@ PIE_ERR_NO_DEVICE = -6
 # plane indices (include/sph_pie_b200.h)
 SI_TOTAL, SI_COMPLETED, SI_NO_LAUNCH, SI_ABORT, SI_LAUNCHED, SI_DELAY_COUNT = range(6)
 SI_ISSUE_COUNT0 = 6
-SI_ISSUE_FIRST0 = 16
-SF_DELAY_SUM, SF_AVG_DELAY, SF_MAX_DELAY, SF_COMPLETION_RATE, SF_LAUNCH_RATE, SF_ABORT_RATE = range(6)
-SF_ISSUE_RATE0 = 6
+SI_ISSUE_ORDER_LO = 16
+SI_ISSUE_ORDER_HI = 17
+SF_AVG_DELAY, SF_MAX_DELAY, SF_COMPLETION_RATE, SF_LAUNCH_RATE, SF_ABORT_RATE = range(5)
+SF_ISSUE_RATE0 = 5
 DF_AVERAGE, DF_MIN, DF_MAX = range(3)
 
 
@@ -101,13 +102,12 @@ SIGNATURES = {
     "pie_host_free": (None, [C.c_void_p]),
     "pie_last_transfer_bytes": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pie_kernel_launch_count": (C.c_uint64, []),
-    "pie_show_stats_scratch_bytes": (C.c_uint64, [C.c_int64]),
-    "pie_show_stats_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
-                                     C.c_void_p]),
+    "pie_show_stats_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pie_show_stats_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64]),
     "pie_daily_scratch_bytes": (C.c_uint64, [C.c_int64]),
     "pie_daily_summary_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                         C.POINTER(DailyOutC), C.c_void_p, C.c_void_p]),
+    "pie_selftest_fast_div": (C.c_int, [C.c_int32, C.POINTER(C.c_uint64)]),
     "pie_archive_analytics_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                              C.POINTER(DailyOutC)]),
 }

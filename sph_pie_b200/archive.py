@@ -33,9 +33,12 @@ def _stats_dict(i32, f64, s: int) -> dict:
     """Plane values of show s -> the object computeArchiveShowStats returns (:3939-3952)."""
     total = int(i32[_lib.SI_TOTAL][s])
     delay_n = int(i32[_lib.SI_DELAY_COUNT][s])
-    counts = [(int(i32[_lib.SI_ISSUE_FIRST0 + k][s]), k) for k in range(_lib.PIE_N_ISSUES)
-              if int(i32[_lib.SI_ISSUE_COUNT0 + k][s]) > 0]
-    counts.sort()  # property insertion order = order of first occurrence among the entries
+    # property insertion order of issueCounts = order of first occurrence: packed nibbles (k+1), 0 ends
+    code = (int(i32[_lib.SI_ISSUE_ORDER_LO][s]) & 0xFFFFFFFF) | ((int(i32[_lib.SI_ISSUE_ORDER_HI][s]) & 0xFF) << 32)
+    order = []
+    while code & 0xF:
+        order.append((code & 0xF) - 1)
+        code >>= 4
 
     def rate(plane):
         return float(f64[plane][s]) if total else None
@@ -51,7 +54,7 @@ def _stats_dict(i32, f64, s: int) -> dict:
         "completionRate": rate(_lib.SF_COMPLETION_RATE),
         "launchRate": rate(_lib.SF_LAUNCH_RATE),
         "abortRate": rate(_lib.SF_ABORT_RATE),
-        "issueCounts": {PRIMARY_ISSUES[k]: int(i32[_lib.SI_ISSUE_COUNT0 + k][s]) for _, k in counts},
+        "issueCounts": {PRIMARY_ISSUES[k]: int(i32[_lib.SI_ISSUE_COUNT0 + k][s]) for k in order},
         "issueRates": {PRIMARY_ISSUES[k]: rate(_lib.SF_ISSUE_RATE0 + k) for k in range(_lib.PIE_N_ISSUES)},
     }
 

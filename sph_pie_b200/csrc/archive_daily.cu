@@ -27,7 +27,7 @@ struct DailyMeta {
   unsigned long long err;  // (show index << 32) | -status, minimum wins; ~0 = no error
   uint32_t or_bits, and_bits;
   uint32_t n_valid;
-  uint32_t pad;
+  uint32_t unsorted;  // some key is smaller than its predecessor: the radix sort has to run
 };
 
 struct DailyScratch {
@@ -133,83 +133,139 @@ __global__ void daily_init_kernel(DailyMeta* meta) {
   meta->or_bits = 0;
   meta->and_bits = 0xFFFFFFFFu;
   meta->n_valid = 0;
+  meta->unsorted = 0;
+}
+
+// getShowTimestamp (:4092-4116) -> local midnight (:3412-3414) -> 32-bit day key.  err is 0 or -pie_status.
+__device__ __forceinline__ uint32_t show_day_key(const pie_archive_view& v, int64_t s, int64_t tz_off_ms,
+                                                 int64_t* start_out, int* err_out) {
+  uint32_t key = kKeyNone;
+  double ts = quiet_nan();
+  int err = 0;
+  const double created = v.created_at[s];
+  if (is_finite_f64(created)) {
+    ts = created;
+  } else {
+    int parsed = 0;
+    if (v.show_date.offsets) {
+      const int db = v.show_date.offsets[s], de = v.show_date.offsets[s + 1];
+      if (de > db) {
+        int tb = 0, te = 0;
+        if (v.show_time.offsets) { tb = v.show_time.offsets[s]; te = v.show_time.offsets[s + 1]; }
+        parsed = parse_show_date_time(v.show_date.data + db, de - db, v.show_time.data + tb, te - tb, tz_off_ms, &ts);
+        if (parsed < 0) err = -PIE_ERR_UNSUPPORTED_DATE;
+      }
+    }
+    if (parsed == 0) {
+      const double archived = v.archived_at ? v.archived_at[s] : quiet_nan();
+      if (is_finite_f64(archived)) {
+        ts = archived;
+      } else if (v.entry_ts) {  // smallest finite entry.ts (:4106-4113)
+        bool any = false;
+        double best = 0.0;
+        for (int e = v.entry_offsets[s]; e < v.entry_offsets[s + 1]; ++e) {
+          const double t = v.entry_ts[e];
+          if (is_finite_f64(t) && (!any || t < best)) { best = t; any = true; }
+        }
+        if (any) ts = best;
+      }
+    }
+  }
+  int64_t start = PIE_DAY_NONE;
+  if (!err && is_finite_f64(ts)) {
+    if (fabs(ts) > kMaxTimeMs) {
+      err = -PIE_ERR_RANGE;  // new Date(ts) is invalid -> toISOString throws (:3415)
+    } else {
+      const int64_t t = (int64_t)ts;  // TimeClip truncates toward zero
+      const int64_t local = t + tz_off_ms;
+      int64_t day = local / kMsPerDay;
+      if (local % kMsPerDay < 0) day -= 1;  // floor
+      start = day * kMsPerDay - tz_off_ms;
+      if (start > (int64_t)kMaxTimeMs || start < -(int64_t)kMaxTimeMs) {
+        err = -PIE_ERR_RANGE;
+        start = PIE_DAY_NONE;
+      } else {
+        key = (uint32_t)(day + 0x80000000LL);  // |day| <= 1.0e8 + 1
+      }
+    }
+  }
+  *start_out = start;
+  *err_out = err;
+  return key;
 }
 
 __global__ void __launch_bounds__(kThreads) show_day_kernel(pie_archive_view v, int64_t tz_off_ms,
                                                             int64_t* __restrict__ show_day_start,
                                                             uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
                                                             DailyMeta* meta) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t key = kKeyNone;
-  bool in_range = s < v.n_shows;
-  if (in_range) {
-    double ts = quiet_nan();
-    int err = 0;
-    const double created = v.created_at[s];
-    if (is_finite_f64(created)) {
-      ts = created;
-    } else {
-      int parsed = 0;
-      if (v.show_date.offsets) {
-        const int db = v.show_date.offsets[s], de = v.show_date.offsets[s + 1];
-        if (de > db) {
-          int tb = 0, te = 0;
-          if (v.show_time.offsets) { tb = v.show_time.offsets[s]; te = v.show_time.offsets[s + 1]; }
-          parsed = parse_show_date_time(v.show_date.data + db, de - db, v.show_time.data + tb, te - tb, tz_off_ms, &ts);
-          if (parsed < 0) err = -PIE_ERR_UNSUPPORTED_DATE;
-        }
+  __shared__ uint32_t s_key[kThreads];
+  __shared__ uint32_t s_red[4][kThreads / 32];
+  uint32_t k_or = 0, k_and = 0xFFFFFFFFu, n_valid = 0, unsorted = 0;
+  unsigned long long first_err = ~0ull;
+  const int tid = threadIdx.x;
+  for (int64_t base = (int64_t)blockIdx.x * kThreads; base < v.n_shows; base += (int64_t)gridDim.x * kThreads) {
+    const int64_t s = base + tid;
+    uint32_t key = kKeyNone;
+    if (s < v.n_shows) {
+      int64_t start;
+      int err;
+      key = show_day_key(v, s, tz_off_ms, &start, &err);
+      if (err) {
+        const unsigned long long e = ((unsigned long long)s << 32) | (unsigned long long)err;
+        first_err = e < first_err ? e : first_err;
       }
-      if (parsed == 0) {
-        const double archived = v.archived_at ? v.archived_at[s] : quiet_nan();
-        if (is_finite_f64(archived)) {
-          ts = archived;
-        } else if (v.entry_ts) {  // smallest finite entry.ts (:4106-4113)
-          bool any = false;
-          double best = 0.0;
-          for (int e = v.entry_offsets[s]; e < v.entry_offsets[s + 1]; ++e) {
-            const double t = v.entry_ts[e];
-            if (is_finite_f64(t) && (!any || t < best)) { best = t; any = true; }
-          }
-          if (any) ts = best;
-        }
-      }
+      show_day_start[s] = start;
+      keys[s] = key;
+      vals[s] = (int32_t)s;
+      k_or |= key;
+      k_and &= key;
+      n_valid += (key != kKeyNone);
     }
-    int64_t start = PIE_DAY_NONE;
-    if (!err && is_finite_f64(ts)) {
-      if (fabs(ts) > kMaxTimeMs) {
-        err = -PIE_ERR_RANGE;  // new Date(ts) is invalid -> toISOString throws (:3415)
-      } else {
-        const int64_t t = (int64_t)ts;  // TimeClip truncates toward zero
-        const int64_t local = t + tz_off_ms;
-        int64_t day = local / kMsPerDay;
-        if (local % kMsPerDay < 0) day -= 1;  // floor
-        start = day * kMsPerDay - tz_off_ms;
-        if (start > (int64_t)kMaxTimeMs || start < -(int64_t)kMaxTimeMs) {
-          err = -PIE_ERR_RANGE;
-          start = PIE_DAY_NONE;
-        } else {
-          key = (uint32_t)(day + 0x80000000LL);  // |day| <= 1.0e8 + 1
-        }
+    // is the archive already ordered by day?  compare with the predecessor's key
+    s_key[tid] = key;
+    __syncthreads();
+    if (s < v.n_shows && s > 0) {
+      uint32_t prev;
+      if (tid > 0) {
+        prev = s_key[tid - 1];
+      } else {  // predecessor belongs to another tile: recompute it (1 in 256 shows)
+        int64_t st;
+        int er;
+        prev = show_day_key(v, s - 1, tz_off_ms, &st, &er);
       }
+      unsorted |= (key < prev);
     }
-    if (err) atomicMin(&meta->err, ((unsigned long long)s << 32) | (unsigned long long)err);
-    show_day_start[s] = start;
-    keys[s] = key;
-    vals[s] = (int32_t)s;
+    __syncthreads();
   }
-  // digit-skip masks and the valid count, one atomic per warp
-  const uint32_t k_or = __reduce_or_sync(0xFFFFFFFFu, in_range ? key : 0u);
-  const uint32_t k_and = __reduce_and_sync(0xFFFFFFFFu, in_range ? key : 0xFFFFFFFFu);
-  const uint32_t nv = __popc(__ballot_sync(0xFFFFFFFFu, in_range && key != kKeyNone));
-  if ((threadIdx.x & 31) == 0) {
-    atomicOr(&meta->or_bits, k_or);
-    atomicAnd(&meta->and_bits, k_and);
-    if (nv) atomicAdd(&meta->n_valid, nv);
+  // one set of atomics per CTA
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    k_or |= __shfl_xor_sync(0xFFFFFFFFu, k_or, o);
+    k_and &= __shfl_xor_sync(0xFFFFFFFFu, k_and, o);
+    n_valid += __shfl_xor_sync(0xFFFFFFFFu, n_valid, o);
+    unsorted |= __shfl_xor_sync(0xFFFFFFFFu, unsorted, o);
+    const unsigned long long oe = __shfl_xor_sync(0xFFFFFFFFu, first_err, o);
+    first_err = oe < first_err ? oe : first_err;
+  }
+  if ((tid & 31) == 0) {
+    s_red[0][tid >> 5] = k_or; s_red[1][tid >> 5] = k_and; s_red[2][tid >> 5] = n_valid; s_red[3][tid >> 5] = unsorted;
+    if (first_err != ~0ull) atomicMin(&meta->err, first_err);  // rare
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t a = 0, b = 0xFFFFFFFFu, c = 0, d = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) { a |= s_red[0][w]; b &= s_red[1][w]; c += s_red[2][w]; d |= s_red[3][w]; }
+    atomicOr(&meta->or_bits, a);
+    atomicAnd(&meta->and_bits, b);
+    if (c) atomicAdd(&meta->n_valid, c);
+    if (d) atomicOr(&meta->unsorted, 1u);
   }
 }
 
 // ---- stable LSD radix sort, 8-bit digits ----------------------------------------------------
 __device__ __forceinline__ bool pass_skipped(const DailyMeta* meta, int pass) {
+  if (!meta->unsorted) return true;  // already ordered by day: identity permutation, nothing to do
   return (((meta->or_bits ^ meta->and_bits) >> (8 * pass)) & 0xFFu) == 0;
 }
 // number of executed passes before `pass`, i.e. which buffer currently holds the data
@@ -235,42 +291,50 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(DailyScratch d, in
   d.hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
-// exclusive scan of `n` uint32 in place by ONE block of 1024 threads; returns the total via *total
+// exclusive scan of `n` uint32 in place by ONE block of 1024 threads: tiles of 4096 elements, each
+// thread 4 consecutive words (coalesced 16-byte accesses when a is 16-byte aligned), running carry.
 __device__ void block_exclusive_scan_inplace(uint32_t* a, int64_t n, uint32_t* total) {
   __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
+  __shared__ uint32_t carry_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t per = (n + blockDim.x - 1) / blockDim.x;
-  const int64_t b = (int64_t)tid * per, e = (b + per < n) ? b + per : n;
-  uint32_t sum = 0;
-  for (int64_t i = b; i < e; ++i) sum += a[i];
-  uint32_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) warp_sums[wid] = incl;
+  if (tid == 0) carry_s = 0;
   __syncthreads();
-  if (wid == 0) {
-    uint32_t w = warp_sums[lane];
-    uint32_t wi = w;
+  for (int64_t base = 0; base < n; base += 4096) {
+    const int64_t i0 = base + 4 * tid;
+    uint32_t x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = (i0 + j < n) ? a[i0 + j] : 0u;
+    const uint32_t sum = x[0] + x[1] + x[2] + x[3];
+    uint32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-      if (lane >= o) wi += t;
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
     }
-    warp_sums[lane] = wi - w;
-    if (lane == 31) carry = wi;
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    if (wid == 0) {
+      const uint32_t w = warp_sums[lane];
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_sums[lane] = wi - w;
+      if (lane == 31) carry_s = carry + wi;
+    }
+    __syncthreads();
+    uint32_t run = carry + warp_sums[wid] + incl - sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < n) a[i0 + j] = run;
+      run += x[j];
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  uint32_t run = warp_sums[wid] + incl - sum;
-  for (int64_t i = b; i < e; ++i) {
-    const uint32_t x = a[i];
-    a[i] = run;
-    run += x;
-  }
-  if (total && tid == 0) *total = carry;
+  if (total && tid == 0) *total = carry_s;
 }
 
 __global__ void __launch_bounds__(1024) radix_scan_kernel(DailyScratch d, int pass, int nblk) {
@@ -420,49 +484,54 @@ __global__ void __launch_bounds__(kThreads) group_write_kernel(DailyScratch d, i
 
 // metric m of show s as a Number, NaN when the reference's getValue yields null
 // (public/app.js:21-86, :3978-3988); validity is then isValidMetricValue == isfinite (:4128-4134).
+// m 0..3 -> int planes TOTAL, COMPLETED, NO_LAUNCH, ABORT; m 4..18 -> f64 planes 0..14.
 __device__ __forceinline__ double metric_value(const int32_t* __restrict__ si, const double* __restrict__ sf,
                                                int64_t stride, int m, int64_t s) {
-  if (m < 4) return (double)si[(int64_t)m * stride + s];  // TOTAL, COMPLETED, NO_LAUNCH, ABORT planes 0..3
-  return sf[(int64_t)(m - 3) * stride + s];  // 4->AVG(1) 5->MAX(2) 6..8->rates(3..5) 9..18->issue rates(6..15)
+  if (m < 4) return (double)si[(int64_t)m * stride + s];
+  return sf[(int64_t)(m - 4) * stride + s];
 }
 
+// One thread per daily group, all 19 metrics: the group's member list is read once.
 __global__ void __launch_bounds__(128) daily_summary_kernel(const int32_t* __restrict__ si, const double* __restrict__ sf,
                                                             int64_t stats_stride, pie_daily_out out) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= *out.n_groups) return;
-  const int m = blockIdx.y;
   const int b = out.group_offsets[g], e = out.group_offsets[g + 1];
-  double sum = 0.0, mn = 0.0, mx = 0.0;
-  int n = 0;
-  for (int i = b; i < e; ++i) {
-    const double v = metric_value(si, sf, stats_stride, m, out.show_order[i]);
-    if (is_finite_f64(v)) {
-      sum = sum + v;  // left to right, initial 0 (:3481)
-      mn = n ? js_min(mn, v) : v;
-      mx = n ? js_max(mx, v) : v;
-      n += 1;
-    }
-  }
   const double nan = quiet_nan();
-  const int64_t o = (int64_t)m * out.stride + g;
   const int64_t plane = (int64_t)PIE_N_METRICS * out.stride;
-  out.summary_f64[PIE_DF_AVERAGE * plane + o] = n ? sum / (double)n : nan;
-  out.summary_f64[PIE_DF_MIN * plane + o] = n ? mn : nan;
-  out.summary_f64[PIE_DF_MAX * plane + o] = n ? mx : nan;
-  out.summary_count[o] = n;
+#pragma unroll 1
+  for (int m = 0; m < PIE_N_METRICS; ++m) {
+    double sum = 0.0, mn = 0.0, mx = 0.0;
+    int n = 0;
+    for (int i = b; i < e; ++i) {
+      const double x = metric_value(si, sf, stats_stride, m, out.show_order[i]);
+      if (is_finite_f64(x)) {
+        sum = sum + x;  // left to right, initial 0 (:3481)
+        mn = n ? js_min(mn, x) : x;
+        mx = n ? js_max(mx, x) : x;
+        n += 1;
+      }
+    }
+    const int64_t o = (int64_t)m * out.stride + g;
+    out.summary_f64[PIE_DF_AVERAGE * plane + o] = n ? sum / (double)n : nan;
+    out.summary_f64[PIE_DF_MIN * plane + o] = n ? mn : nan;
+    out.summary_f64[PIE_DF_MAX * plane + o] = n ? mx : nan;
+    out.summary_count[o] = n;
+  }
 }
 
 cudaError_t launch_daily_summary(const pie_archive_view& v, const int32_t* si, const double* sf, int64_t stats_stride,
                                  int32_t tz_offset_minutes, const pie_daily_out& out, void* scratch, int sm_count,
                                  cudaStream_t stream) {
-  (void)sm_count;
   const int64_t n = v.n_shows;
   DailyScratch d = carve(scratch, n);
   const int nblk = (int)n_tiles(n > 0 ? n : 1);
   daily_init_kernel<<<1, 1, 0, stream>>>(d.meta);
   g_launches += 2 + (n > 0 ? 4 + 12 : 0);  // init, group_scan + (show_day, 12 radix, group_count/write, summary)
   if (n > 0) {
-    show_day_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, stream>>>(
+    int64_t day_blocks = (n + kThreads - 1) / kThreads;
+    if (day_blocks > (int64_t)sm_count * 8) day_blocks = (int64_t)sm_count * 8;
+    show_day_kernel<<<(unsigned)day_blocks, kThreads, 0, stream>>>(
         v, (int64_t)tz_offset_minutes * 60000, out.show_day_start, d.keys_a, d.vals_a, d.meta);
     for (int pass = 0; pass < 4; ++pass) {
       radix_hist_kernel<<<nblk, kThreads, 0, stream>>>(d, n, pass, nblk);
@@ -476,8 +545,7 @@ cudaError_t launch_daily_summary(const pie_archive_view& v, const int32_t* si, c
   group_scan_kernel<<<1, 1024, 0, stream>>>(d, n > 0 ? nblk : 1, out);
   if (n > 0) {
     group_write_kernel<<<nblk, kThreads, 0, stream>>>(d, n, out);
-    dim3 grid((unsigned)((n + 127) / 128), PIE_N_METRICS);
-    daily_summary_kernel<<<grid, 128, 0, stream>>>(si, sf, stats_stride, out);
+    daily_summary_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(si, sf, stats_stride, out);
   }
   return cudaGetLastError();
 }

@@ -167,19 +167,17 @@ void pie_last_transfer_bytes(uint64_t* h2d, uint64_t* d2h) {
 
 uint64_t pie_kernel_launch_count(void) { return pie::g_launches; }
 
-uint64_t pie_show_stats_scratch_bytes(int64_t n_entries) { return (uint64_t)(n_entries > 0 ? n_entries : 1); }
-
-int pie_show_stats_dev(const pie_archive_view* v, int32_t* stats_i32, double* stats_f64, int64_t stride, void* scratch,
+int pie_show_stats_dev(const pie_archive_view* v, int32_t* stats_i32, double* stats_f64, int64_t stride,
                        void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
   if ((rc = check_view_common(v))) return rc;
-  if (!stats_i32 || !stats_f64 || !scratch) return fail(PIE_ERR_INVALID_ARG, "output or scratch is NULL");
+  if (!stats_i32 || !stats_f64) return fail(PIE_ERR_INVALID_ARG, "output is NULL");
   if (stride < v->n_shows) return fail(PIE_ERR_INVALID_ARG, "stride < n_shows");
   if (v->n_entries > 0 && (!v->status.offsets || !v->launched.offsets || !v->primary_issue.offsets || !v->delay_sec ||
                            !v->delay_valid))
     return fail(PIE_ERR_INVALID_ARG, "show stats reads status, launched, primary_issue, delay_sec, delay_valid");
-  PIE_CUDA(pie::launch_show_stats(*v, stats_i32, stats_f64, stride, scratch, g_sm_count, (cudaStream_t)stream));
+  PIE_CUDA(pie::launch_show_stats(*v, stats_i32, stats_f64, stride, g_sm_count, (cudaStream_t)stream));
   return PIE_OK;
 }
 
@@ -239,7 +237,6 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   if (has_time && (rc = plan_strcol(p_time, &hv->show_time, nullptr, S, &bytes, "show_time"))) return rc;
   const int64_t Sc = S > 0 ? S : 1;
   bytes += pad(4 * (uint64_t)(S + 1)) + pad(8 * (uint64_t)E) + pad((uint64_t)E);          // offsets, delay, valid
-  bytes += pad(pie_show_stats_scratch_bytes(E));                                           // codes
   bytes += pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc);                  // stats planes
   if (want_daily) {
     bytes += 2 * pad(8 * (uint64_t)Sc) + pad(8 * (uint64_t)E);                             // created, archived, entry_ts
@@ -272,10 +269,9 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   }
 
   // ---- kernels
-  void* codes = g_arena.take(pie_show_stats_scratch_bytes(E));
   int32_t* d_si = (int32_t*)g_arena.take(4ull * PIE_SI_COUNT * Sc);
   double* d_sf = (double*)g_arena.take(8ull * PIE_SF_COUNT * Sc);
-  PIE_CUDA(pie::launch_show_stats(dv, d_si, d_sf, Sc, codes, g_sm_count, st));
+  PIE_CUDA(pie::launch_show_stats(dv, d_si, d_sf, Sc, g_sm_count, st));
 
   pie_daily_out dout;
   memset(&dout, 0, sizeof(dout));
@@ -349,6 +345,21 @@ int pie_show_stats_host(const pie_archive_view* hv, int32_t* stats_i32, double* 
   std::lock_guard<std::mutex> lock(g_host_mutex);
   if (!stats_i32 || !stats_f64) return fail(PIE_ERR_INVALID_ARG, "output is NULL");
   return analytics_host_locked(hv, 0, stats_i32, stats_f64, stride, nullptr);
+}
+
+int pie_selftest_fast_div(int32_t max_b, uint64_t* mismatches) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!mismatches || max_b < 1 || max_b > 4096) return fail(PIE_ERR_INVALID_ARG, "max_b must be in 1..4096");
+  unsigned long long* d = nullptr;
+  PIE_CUDA(cudaMalloc(&d, 8));
+  PIE_CUDA(cudaMemset(d, 0, 8));
+  PIE_CUDA(pie::launch_selftest_fast_div(max_b, d, nullptr));
+  unsigned long long h = 0;
+  PIE_CUDA(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+  PIE_CUDA(cudaFree(d));
+  *mismatches = h;
+  return PIE_OK;
 }
 
 }  // extern "C"

@@ -46,6 +46,60 @@ __device__ __forceinline__ bool equals_exact(const uint8_t* __restrict__ s, int 
   return true;
 }
 
+// ---- word-at-a-time string access -----------------------------------------------------------
+// Strings are compared 4 bytes at a time: the NW aligned 32-bit words that contain bytes
+// [p, p+n) are loaded (never a word that holds no byte of the string, so no over-read beyond the
+// 4-byte-aligned end of the buffer), funnel-shifted to string alignment and zero-padded past n.
+// Requires n >= 1 and n <= 4*NW.  Buffers must start 4-byte aligned in memory (any cudaMalloc /
+// torch allocation does) — the aligned word containing the first / last byte is then in bounds.
+template <int NW>
+__device__ __forceinline__ void fetch_words(const uint8_t* __restrict__ p, int n, uint32_t (&x)[NW]) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+  const int last = static_cast<int>(((a & 3) + n - 1) >> 2);
+  uint32_t raw[NW + 1];
+#pragma unroll
+  for (int k = 0; k <= NW; ++k) raw[k] = (k <= last) ? __ldg(w + k) : 0u;
+#pragma unroll
+  for (int k = 0; k < NW; ++k) {
+    const uint32_t v = __funnelshift_r(raw[k], raw[k + 1], sh);
+    const int nb = n - 4 * k;
+    x[k] = nb >= 4 ? v : (nb <= 0 ? 0u : (v & ((1u << (8 * nb)) - 1u)));
+  }
+}
+
+// ASCII upper -> lower on 4 packed bytes, other bytes unchanged (no cross-byte carries).
+__device__ __forceinline__ uint32_t lower4(uint32_t w) {
+  const uint32_t hept = w & 0x7f7f7f7fu;
+  const uint32_t ge_a = hept + 0x3f3f3f3fu;  // bit 7 set iff (b & 0x7f) >= 'A'
+  const uint32_t gt_z = hept + 0x25252525u;  // bit 7 set iff (b & 0x7f) >  'Z'
+  const uint32_t upper = ge_a & ~gt_z & ~w & 0x80808080u;
+  return w | (upper >> 2);
+}
+
+// little-endian pack of literal bytes [4k, 4k+4), zero padded
+template <int L>
+__host__ __device__ constexpr uint32_t lit_word(const char (&s)[L], int k) {
+  uint32_t v = 0;
+  for (int j = 0; j < 4; ++j) {
+    const int i = 4 * k + j;
+    if (i < L - 1) v |= static_cast<uint32_t>(static_cast<unsigned char>(s[i])) << (8 * j);
+  }
+  return v;
+}
+
+// a / b for a, b small non-negative integers held in doubles, given y = RN(1/b):
+// q0 = RN(a*y); r = a - b*q0 (exact in one FMA); q = RN(q0 + r*y) is the correctly rounded
+// quotient (Markstein).  Used only for b <= kFastDivMax, where it is verified EXHAUSTIVELY against
+// IEEE division by pie_selftest_fast_div (tests/test_gpu_parity.py).
+constexpr int kFastDivMax = 4096;
+__device__ __forceinline__ double div_by_shared_reciprocal(double a, double b, double y) {
+  const double q0 = a * y;
+  const double r = fma(-b, q0, a);
+  return fma(r, y, q0);
+}
+
 // Length in bytes of an ECMAScript WhiteSpace/LineTerminator code point starting at s[i] (UTF-8),
 // 0 if s[i] does not start one.  Set: TAB LF VT FF CR SP, U+00A0, U+1680, U+2000-200A, U+2028,
 // U+2029, U+202F, U+205F, U+3000, U+FEFF  (String.prototype.trim).

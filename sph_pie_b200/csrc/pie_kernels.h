@@ -12,7 +12,8 @@ extern unsigned long long g_launches;
 
 // archive_stats.cu
 cudaError_t launch_show_stats(const pie_archive_view& dev_view, int32_t* stats_i32, double* stats_f64,
-                              int64_t stride, void* scratch, int sm_count, cudaStream_t stream);
+                              int64_t stride, int sm_count, cudaStream_t stream);
+cudaError_t launch_selftest_fast_div(int max_b, unsigned long long* d_mismatches, cudaStream_t stream);
 
 // archive_daily.cu
 uint64_t daily_scratch_bytes(int64_t n_shows);

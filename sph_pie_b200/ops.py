@@ -48,8 +48,6 @@ class DailyBuffers:
         self.S = S
         self.stats_i32 = torch.empty((_lib.PIE_SI_COUNT, S), dtype=torch.int32, device=device)
         self.stats_f64 = torch.empty((_lib.PIE_SF_COUNT, S), dtype=torch.float64, device=device)
-        self.stats_scratch = torch.empty(int(lib.pie_show_stats_scratch_bytes(n_entries)), dtype=torch.uint8,
-                                         device=device)
         self.show_day_start = torch.empty(S, dtype=torch.int64, device=device)
         self.show_order = torch.empty(S, dtype=torch.int32, device=device)
         self.group_day_start = torch.empty(S, dtype=torch.int64, device=device)
@@ -72,7 +70,7 @@ def show_stats_dev(table: ArchiveTable, bufs: DailyBuffers) -> None:
     _lib.ensure_init()
     view = table.view()
     _lib.check(_lib.load().pie_show_stats_dev(C.byref(view), bufs.stats_i32.data_ptr(), bufs.stats_f64.data_ptr(),
-                                              bufs.S, bufs.stats_scratch.data_ptr(), _stream_ptr()))
+                                              bufs.S, _stream_ptr()))
 
 
 def daily_summary_dev(table: ArchiveTable, bufs: DailyBuffers, tz_offset_minutes: int = 0) -> None:

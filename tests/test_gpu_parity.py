@@ -143,6 +143,30 @@ def test_error_behaviour_matches_reference(cuda):
         ops.archive_analytics(pack_shows([ok]), 99999)
 
 
+def test_shared_reciprocal_division_is_exact(cuda):
+    """The rate columns use one IEEE reciprocal + an exact correction instead of 13 divisions per
+    show.  Every (count, total) pair the kernels can feed it (total <= 4096) is compared bit-for-bit
+    with IEEE division on the device."""
+    import ctypes as C
+
+    bad = C.c_uint64(123)
+    _lib.check(_lib.load().pie_selftest_fast_div(4096, C.byref(bad)))
+    assert bad.value == 0
+
+
+def test_large_shows_use_true_division_and_counter_flush(cuda):
+    """Shows with > 4096 entries (true-division path) and > 255 entries (packed-counter flush)."""
+    rows = lambda n: [{"status": ["Completed", "Abort", "No-launch", "x"][i % 4], "launched": "Yes" if i % 3 else "",
+                       "primaryIssue": po.PRIMARY_ISSUES[i % 10] if i % 2 else "", "delaySec": (i % 13) * 0.25}
+                      for i in range(n)]
+    shows = [{"id": f"n{n}", "createdAt": 1.7e12 + k * 9e7, "entries": rows(n)}
+             for k, n in enumerate((254, 255, 256, 511, 4096, 4097, 9001))]
+    table = pack_shows(shows)
+    for t in (table, table.to(cuda)):
+        assert_analytics_equal(ops.archive_analytics(t, 0), oracle(table, 0))
+    assert_stats_match_py_oracle(shows[:4], ops.show_stats(pack_shows(shows[:4])))
+
+
 def test_sliced_table_equals_whole(cuda):
     host = synth_archive(4000, seed=13)
     whole = ops.show_stats(host)
