@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsphpie_b200.so")
+LIB_PATH = os.environ.get("PIE_LIB_PATH") or os.path.join(_HERE, "libsphpie_b200.so")  # env: tuning sweeps only
 
 PIE_N_ISSUES = 10
 PIE_N_METRICS = 19

@@ -501,21 +501,22 @@ __global__ void __launch_bounds__(128) daily_summary_kernel(const int32_t* __res
   const int64_t plane = (int64_t)PIE_N_METRICS * out.stride;
 #pragma unroll 1
   for (int m = 0; m < PIE_N_METRICS; ++m) {
-    double sum = 0.0, mn = 0.0, mx = 0.0;
+    double sum = 0.0;
+    long long kmin = kKeyHighest, kmax = kKeyLowest;  // Math.min / Math.max as integer min / max
     int n = 0;
     for (int i = b; i < e; ++i) {
       const double x = metric_value(si, sf, stats_stride, m, out.show_order[i]);
-      if (is_finite_f64(x)) {
-        sum = sum + x;  // left to right, initial 0 (:3481)
-        mn = n ? js_min(mn, x) : x;
-        mx = n ? js_max(mx, x) : x;
-        n += 1;
-      }
+      const bool ok = is_finite_f64(x);
+      sum = sum + (ok ? x : -0.0);  // left to right, initial 0 (:3481); -0.0 is an exact no-op here
+      const long long k = ordered_key(x);
+      kmin = (ok && k < kmin) ? k : kmin;
+      kmax = (ok && k > kmax) ? k : kmax;
+      n += ok;
     }
     const int64_t o = (int64_t)m * out.stride + g;
     out.summary_f64[PIE_DF_AVERAGE * plane + o] = n ? sum / (double)n : nan;
-    out.summary_f64[PIE_DF_MIN * plane + o] = n ? mn : nan;
-    out.summary_f64[PIE_DF_MAX * plane + o] = n ? mx : nan;
+    out.summary_f64[PIE_DF_MIN * plane + o] = n ? from_ordered_key(kmin) : nan;
+    out.summary_f64[PIE_DF_MAX * plane + o] = n ? from_ordered_key(kmax) : nan;
     out.summary_count[o] = n;
   }
 }

@@ -57,7 +57,7 @@ __device__ __forceinline__ void fetch_words(const uint8_t* __restrict__ p, int n
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
   const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
   const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
-  const int last = static_cast<int>(((a & 3) + n - 1) >> 2);
+  const int last = n > 0 ? static_cast<int>(((a & 3) + n - 1) >> 2) : -1;  // n <= 0: no load at all
   uint32_t raw[NW + 1];
 #pragma unroll
   for (int k = 0; k <= NW; ++k) raw[k] = (k <= last) ? __ldg(w + k) : 0u;
@@ -67,6 +67,51 @@ __device__ __forceinline__ void fetch_words(const uint8_t* __restrict__ p, int n
     const int nb = n - 4 * k;
     x[k] = nb >= 4 ? v : (nb <= 0 ? 0u : (v & ((1u << (8 * nb)) - 1u)));
   }
+}
+
+template <int L>
+__host__ __device__ constexpr uint32_t lit_word(const char (&s)[L], int k);  // defined below
+
+// Same fetch without the zero padding: bytes past n are whatever follows in the loaded words.
+// For comparisons against a literal of exactly n bytes through literal-specific masks.
+template <int NW>
+__device__ __forceinline__ void fetch_words_raw(const uint8_t* __restrict__ p, int n, uint32_t (&x)[NW]) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+  const int last = n > 0 ? static_cast<int>(((a & 3) + n - 1) >> 2) : -1;  // n <= 0: no load at all
+  uint32_t raw[NW + 1];
+#pragma unroll
+  for (int k = 0; k <= NW; ++k) raw[k] = (k <= last) ? __ldg(w + k) : 0u;
+#pragma unroll
+  for (int k = 0; k < NW; ++k) x[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
+}
+
+// Mask word k for comparing against literal s: 0xFF per literal byte (0xDF for a lower-case letter
+// when case_insensitive: the byte may differ from the literal in bit 5 only, i.e. be its upper
+// case), 0x00 past the literal's end.
+template <int L>
+__host__ __device__ constexpr uint32_t lit_mask(const char (&s)[L], int k, bool case_insensitive) {
+  uint32_t v = 0;
+  for (int j = 0; j < 4; ++j) {
+    const int i = 4 * k + j;
+    if (i < L - 1) {
+      const bool letter = s[i] >= 'a' && s[i] <= 'z';
+      v |= static_cast<uint32_t>((case_insensitive && letter) ? 0xDFu : 0xFFu) << (8 * j);
+    }
+  }
+  return v;
+}
+
+// x[0..NW) (raw words of a string of EXACTLY L-1 bytes) equals the lower-case literal `s` under
+// ASCII case folding.  One LOP3 per word: ((x ^ lit) & mask), OR-reduced.
+template <int NW, int L>
+__device__ __forceinline__ bool words_equal_ci(const uint32_t (&x)[NW], const char (&s)[L]) {
+  static_assert(4 * NW >= L - 1, "literal longer than the fetched words");
+  uint32_t diff = 0;
+#pragma unroll
+  for (int k = 0; k < NW; ++k) diff |= (x[k] ^ lit_word(s, k)) & lit_mask(s, k, true);
+  return diff == 0;
 }
 
 // ASCII upper -> lower on 4 packed bytes, other bytes unchanged (no cross-byte carries).
@@ -144,6 +189,19 @@ __device__ __forceinline__ double js_min(double a, double b) {
   if (a < b) return a;
   if (b < a) return b;
   return (__double2hiint(a) < 0) ? a : b;
+}
+
+// Order-preserving map from finite doubles to signed 64-bit integers: a < b  <=>  key(a) < key(b),
+// and key(-0.0) = -1 < key(+0.0) = 0 — exactly Math.max / Math.min's ordering — so max/min become
+// branch-free integer max/min.  The map is an involution on the low 63 bits.
+constexpr long long kKeyLowest = (long long)0x8000000000000000ull;   // below every key
+constexpr long long kKeyHighest = (long long)0x7FFFFFFFFFFFFFFFull;  // above every finite key
+__device__ __forceinline__ long long ordered_key(double x) {
+  const long long b = __double_as_longlong(x);
+  return b ^ ((b >> 63) & 0x7FFFFFFFFFFFFFFFLL);
+}
+__device__ __forceinline__ double from_ordered_key(long long k) {
+  return __longlong_as_double(k ^ ((k >> 63) & 0x7FFFFFFFFFFFFFFFLL));
 }
 
 __device__ __forceinline__ bool is_finite_f64(double x) {
