@@ -175,6 +175,24 @@ int pie_archive_analytics_host(const pie_archive_view* host_view, int32_t tz_off
                                int32_t* stats_i32, double* stats_f64, int64_t stats_stride,
                                const pie_daily_out* host_out);
 
+/* ---- export rows: replaces buildTableRow + csvEscape + buildCsvRow (server/webhookDispatcher.js:
+ * 276-342; browser twins public/app.js:5582-5612, :6025-6034) mapped over every entry of every show:
+ * the strings dispatchShowEvent puts in csv.rows (:571) and exportShowAsCsv joins with '\n'
+ * (public/app.js:5558-5570).  delaySec goes through Number::toString (ECMA-262 6.1.6.1.20).
+ * Output is one string column: row i = out_data[row_offsets[i] .. row_offsets[i+1]-1), every row is
+ * followed by one '\n' (a show's CSV body is one contiguous slice); row_offsets has n_entries+1
+ * elements.  Reads every string column, crew, actions, delay_sec, delay_valid, entry_offsets.
+ * dev variant: out_data == NULL computes row_offsets and the total only; if out_capacity is too
+ * small nothing past it is written and *total_bytes_dev still reports the size needed.
+ * Device string heaps must start 16-byte aligned (any cudaMalloc / torch allocation does). */
+uint64_t pie_csv_rows_scratch_bytes(int64_t n_entries);
+int pie_csv_rows_dev(const pie_archive_view* dev_view, int64_t* row_offsets, uint8_t* out_data,
+                     uint64_t out_capacity, uint64_t* total_bytes_dev, void* scratch, void* stream);
+/* host variant: out_data == NULL is a size query (fills row_offsets and *total_bytes);
+ * PIE_ERR_CAPACITY if out_capacity < *total_bytes (which is set either way). */
+int pie_csv_rows_host(const pie_archive_view* host_view, int64_t* row_offsets, uint8_t* out_data,
+                      uint64_t out_capacity, uint64_t* total_bytes);
+
 /* ---- self tests (device code paths that replace an IEEE operation by a faster exact sequence) */
 /* Compares the shared-reciprocal quotient used for the rate columns with IEEE a/b for every
  * 0 <= a <= b <= max_b (max_b <= 4096, the largest b the kernels use it for); writes the number of

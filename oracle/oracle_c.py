@@ -70,3 +70,33 @@ def archive_analytics(table: ArchiveTable, tz_offset_minutes: int = 0, nthreads:
     G = int(h.n_groups[0])
     return st, DailySummary(G, h.show_day_start[:S], h.show_order[:S], h.group_day_start[:G], h.group_offsets[:G + 1],
                             h.summary_f64[:, :, :G], h.summary_count[:, :G]), 0, -1
+
+
+def csv_rows(table: ArchiveTable):
+    """(row_offsets int64[E+1], data uint8[total]) from the C restatement of buildCsvRow."""
+    assert not table.is_cuda
+    so = load()
+    so.oracle_csv_rows.restype = C.c_int
+    so.oracle_csv_rows.argtypes = [C.POINTER(_lib.ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    view = table.view()
+    offsets = torch.empty(table.n_entries + 1, dtype=torch.int64)
+    total = C.c_uint64(0)
+    so.oracle_csv_rows(C.byref(view), offsets.data_ptr(), None, 0, C.byref(total))
+    data = torch.empty(max(int(total.value), 1), dtype=torch.uint8)
+    so.oracle_csv_rows(C.byref(view), offsets.data_ptr(), data.data_ptr(), int(total.value), C.byref(total))
+    return offsets, data[: int(total.value)]
+
+
+def number_to_string_batch(xs):
+    import numpy as np
+
+    so = load()
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    n = len(xs)
+    out = np.zeros(n * 32, dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.int32)
+    so.oracle_number_to_string_batch.restype = None
+    so.oracle_number_to_string_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    so.oracle_number_to_string_batch(xs.ctypes.data, n, out.ctypes.data, lens.ctypes.data)
+    b = out.tobytes()
+    return [b[i * 32:i * 32 + lens[i]].decode() for i in range(n)]

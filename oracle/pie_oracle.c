@@ -391,3 +391,145 @@ int oracle_daily_summary(const pie_archive_view* v, const int32_t* si, const dou
   free(skipped);
   return 0;
 }
+
+
+/* ---- export rows: buildTableRow + csvEscape + buildCsvRow (server/webhookDispatcher.js:276-342) -- */
+#include <stdio.h>
+
+/* Number::toString via printf/strtod (independent of the product's Ryu).  For p = 1..17 digits:
+ * m = the correctly rounded p-digit decimal of |x| (printf is exact), which is the p-digit decimal
+ * closest to |x|.  The decimals that read back as x form an interval, so at the first p where any
+ * p-digit decimal round-trips it is m itself, or else exactly one of its neighbours m+1 / m-1. */
+static int js_number_to_string(double x, char* out) {
+  if (isnan(x)) return sprintf(out, "NaN");
+  if (isinf(x)) return sprintf(out, x > 0 ? "Infinity" : "-Infinity");
+  if (x == 0) return sprintf(out, "0");
+  const double ax = fabs(x);
+  char buf[48], cand[48];
+  unsigned long long best = 0;
+  int best_q = 0, found = 0;
+  for (int p = 1; p <= 17 && !found; ++p) {
+    snprintf(buf, sizeof buf, "%.*e", p - 1, ax);
+    char* e = strchr(buf, 'e');
+    unsigned long long m = 0;
+    for (char* c = buf; c < e; ++c) if (*c != '.') m = m * 10 + (unsigned long long)(*c - '0');
+    const int q = atoi(e + 1) - (p - 1); /* |x| ~ m * 10^q */
+    const long long delta[3] = {0, 1, -1};
+    for (int t = 0; t < 3 && !found; ++t) {
+      if (m == 0 && delta[t] < 0) continue;
+      const unsigned long long c = m + (unsigned long long)delta[t];
+      snprintf(cand, sizeof cand, "%llue%d", c, q);
+      if (strtod(cand, NULL) == ax) { best = c; best_q = q; found = 1; }
+    }
+  }
+  while (best % 10 == 0) { best /= 10; best_q++; } /* 10^p from a carry, trailing zeros */
+  char digits[24];
+  int k = snprintf(digits, sizeof digits, "%llu", best);
+  int n = k + best_q; /* value = 0.d1..dk * 10^n */
+  char* o = out;
+  if (x < 0) *o++ = '-';
+  if (k <= n && n <= 21) {
+    memcpy(o, digits, (size_t)k); o += k;
+    for (int i = k; i < n; ++i) *o++ = '0';
+  } else if (0 < n && n <= 21) {
+    memcpy(o, digits, (size_t)n); o += n;
+    *o++ = '.';
+    memcpy(o, digits + n, (size_t)(k - n)); o += k - n;
+  } else if (-6 < n && n <= 0) {
+    *o++ = '0'; *o++ = '.';
+    for (int i = 0; i < -n; ++i) *o++ = '0';
+    memcpy(o, digits, (size_t)k); o += k;
+  } else {
+    *o++ = digits[0];
+    if (k > 1) { *o++ = '.'; memcpy(o, digits + 1, (size_t)(k - 1)); o += k - 1; }
+    o += sprintf(o, "e%c%d", n - 1 < 0 ? '-' : '+', abs(n - 1));
+  }
+  *o = 0;
+  return (int)(o - out);
+}
+
+typedef struct { uint8_t* p; uint64_t n; uint64_t cap; } csv_out; /* p may be NULL: count only */
+
+static void put_bytes(csv_out* o, const uint8_t* s, uint64_t n) {
+  if (o->p && o->n + n <= o->cap) memcpy(o->p + o->n, s, (size_t)n);
+  o->n += n;
+}
+static void put_char(csv_out* o, char c) { uint8_t b = (uint8_t)c; put_bytes(o, &b, 1); }
+
+/* csvEscape (:332-338) */
+static void put_cell(csv_out* o, const uint8_t* s, int n) {
+  int quote = 0;
+  for (int i = 0; i < n; ++i) if (s[i] == '"' || s[i] == ',' || s[i] == '\n' || s[i] == '\r') quote = 1;
+  if (!quote) { put_bytes(o, s, (uint64_t)n); return; }
+  put_char(o, '"');
+  for (int i = 0; i < n; ++i) { if (s[i] == '"') put_char(o, '"'); put_bytes(o, s + i, 1); }
+  put_char(o, '"');
+}
+static void put_col(csv_out* o, const pie_strcol* c, int64_t i) {
+  put_cell(o, c->data + c->offsets[i], c->offsets[i + 1] - c->offsets[i]);
+}
+/* list.join('|') then csvEscape */
+static void put_joined(csv_out* o, const pie_strlistcol* c, int64_t i) {
+  int l0 = c->list_offsets[i], l1 = c->list_offsets[i + 1];
+  uint64_t cap = 16;
+  for (int l = l0; l < l1; ++l) cap += (uint64_t)(c->items.offsets[l + 1] - c->items.offsets[l]) + 1;
+  uint8_t* tmp = (uint8_t*)malloc(cap);
+  int n = 0;
+  for (int l = l0; l < l1; ++l) {
+    if (l > l0) tmp[n++] = '|';
+    int len = c->items.offsets[l + 1] - c->items.offsets[l];
+    memcpy(tmp + n, c->items.data + c->items.offsets[l], (size_t)len);
+    n += len;
+  }
+  put_cell(o, tmp, n);
+  free(tmp);
+}
+
+/* Fills row_offsets[n_entries+1]; writes rows (each followed by '\n') into out_data when it is not
+ * NULL and large enough; *total receives the size needed. */
+int oracle_csv_rows(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
+                    uint64_t* total) {
+  csv_out o = {out_data, 0, capacity};
+  for (int64_t s = 0; s < v->n_shows; ++s) {
+    for (int e = v->entry_offsets[s]; e < v->entry_offsets[s + 1]; ++e) {
+      row_offsets[e] = (int64_t)o.n;
+      put_col(&o, &v->show_id, s); put_char(&o, ',');
+      put_col(&o, &v->show_date, s); put_char(&o, ',');
+      put_col(&o, &v->show_time, s); put_char(&o, ',');
+      put_col(&o, &v->show_label, s); put_char(&o, ',');
+      put_joined(&o, &v->crew, s); put_char(&o, ',');
+      put_col(&o, &v->lead_pilot, s); put_char(&o, ',');
+      put_col(&o, &v->monkey_lead, s); put_char(&o, ',');
+      put_col(&o, &v->show_notes, s); put_char(&o, ',');
+      put_col(&o, &v->entry_id, e); put_char(&o, ',');
+      put_col(&o, &v->unit_id, e); put_char(&o, ',');
+      put_col(&o, &v->planned, e); put_char(&o, ',');
+      put_col(&o, &v->launched, e); put_char(&o, ',');
+      put_col(&o, &v->status, e); put_char(&o, ',');
+      int sn = v->status.offsets[e + 1] - v->status.offsets[e];
+      int completed = sn == 9 && memcmp(v->status.data + v->status.offsets[e], "Completed", 9) == 0; /* === */
+      const pie_strcol* blanked[5] = {&v->primary_issue, &v->sub_issue, &v->other_detail, &v->severity, &v->root_cause};
+      for (int k = 0; k < 5; ++k) { if (!completed) put_col(&o, blanked[k], e); put_char(&o, ','); }
+      put_joined(&o, &v->actions, e); put_char(&o, ',');
+      put_col(&o, &v->operator_name, e); put_char(&o, ',');
+      put_col(&o, &v->battery_id, e); put_char(&o, ',');
+      if (v->delay_valid[e]) {
+        char num[40];
+        int n = js_number_to_string(v->delay_sec[e], num);
+        put_bytes(&o, (const uint8_t*)num, (uint64_t)n);
+      }
+      put_char(&o, ',');
+      put_col(&o, &v->command_rx, e); put_char(&o, ',');
+      put_col(&o, &v->notes, e);
+      put_char(&o, '\n');
+    }
+  }
+  row_offsets[v->n_entries] = (int64_t)o.n;
+  *total = o.n;
+  return 0;
+}
+
+/* Number::toString of an array (checker for the product's Ryu): out is n x 32 bytes */
+void oracle_number_to_string_batch(const double* x, int64_t n, char* out, int32_t* lens) {
+  for (int64_t i = 0; i < n; ++i) lens[i] = js_number_to_string(x[i], out + 32 * i);
+}

@@ -115,6 +115,103 @@ int check_view_common(const pie_archive_view* v) {
 
 uint64_t g_last_h2d = 0, g_last_d2h = 0;
 
+// A second grow-only buffer for outputs whose size is only known after a device pass (CSV bytes):
+// growing it must not move the inputs already staged in g_arena.
+struct OutBuffer {
+  uint8_t* base = nullptr;
+  uint64_t cap = 0;
+  int ensure(uint64_t bytes) {
+    if (bytes <= cap) return PIE_OK;
+    if (base) PIE_CUDA(cudaFree(base));
+    base = nullptr;
+    cap = 0;
+    PIE_CUDA(cudaMalloc(&base, bytes));
+    cap = bytes;
+    return PIE_OK;
+  }
+};
+OutBuffer g_out;
+
+struct ColumnRef {
+  const pie_strcol* src;
+  pie_strcol* dst;
+  int64_t n;
+  const char* name;
+};
+struct ListRef {
+  const pie_strlistcol* src;
+  pie_strlistcol* dst;
+  int64_t n;
+  const char* name;
+};
+
+// Stage every column the export rows read (all 21 string columns, 2 list columns, delaySec).
+int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_t extra_bytes, uint64_t* h2d) {
+  const int64_t S = hv->n_shows, E = hv->n_entries;
+  ColumnRef cols[] = {
+      {&hv->show_id, &dv->show_id, S, "show_id"},           {&hv->show_date, &dv->show_date, S, "show_date"},
+      {&hv->show_time, &dv->show_time, S, "show_time"},     {&hv->show_label, &dv->show_label, S, "show_label"},
+      {&hv->lead_pilot, &dv->lead_pilot, S, "lead_pilot"},  {&hv->monkey_lead, &dv->monkey_lead, S, "monkey_lead"},
+      {&hv->show_notes, &dv->show_notes, S, "show_notes"},  {&hv->entry_id, &dv->entry_id, E, "entry_id"},
+      {&hv->unit_id, &dv->unit_id, E, "unit_id"},           {&hv->planned, &dv->planned, E, "planned"},
+      {&hv->launched, &dv->launched, E, "launched"},        {&hv->status, &dv->status, E, "status"},
+      {&hv->primary_issue, &dv->primary_issue, E, "primary_issue"},
+      {&hv->sub_issue, &dv->sub_issue, E, "sub_issue"},     {&hv->other_detail, &dv->other_detail, E, "other_detail"},
+      {&hv->severity, &dv->severity, E, "severity"},        {&hv->root_cause, &dv->root_cause, E, "root_cause"},
+      {&hv->operator_name, &dv->operator_name, E, "operator_name"},
+      {&hv->battery_id, &dv->battery_id, E, "battery_id"},  {&hv->command_rx, &dv->command_rx, E, "command_rx"},
+      {&hv->notes, &dv->notes, E, "notes"}};
+  ListRef lists[] = {{&hv->crew, &dv->crew, S, "crew"}, {&hv->actions, &dv->actions, E, "actions"}};
+  constexpr int kCols = sizeof(cols) / sizeof(cols[0]);
+  StrColPlan plans[kCols], item_plans[2];
+  pie_strcol item_src[2];   // the item rows this batch's lists point at (lists may be slices)
+  int32_t item_first[2];
+  uint64_t bytes = extra_bytes + pad(4 * (uint64_t)(S + 1)) + pad(8 * (uint64_t)E) + pad((uint64_t)E);
+  int rc;
+  for (int i = 0; i < kCols; ++i)
+    if ((rc = plan_strcol(plans[i], cols[i].src, cols[i].dst, cols[i].n, &bytes, cols[i].name))) return rc;
+  for (int i = 0; i < 2; ++i) {
+    const pie_strlistcol* l = lists[i].src;
+    if (!l->list_offsets || !l->items.offsets)
+      return fail(PIE_ERR_INVALID_ARG, "column %s: list_offsets / items.offsets is NULL", lists[i].name);
+    item_first[i] = l->list_offsets[0];
+    const int64_t n_items = (int64_t)l->list_offsets[lists[i].n] - item_first[i];
+    if (n_items < 0) return fail(PIE_ERR_INVALID_ARG, "column %s: list_offsets decrease", lists[i].name);
+    item_src[i].offsets = l->items.offsets + item_first[i];
+    item_src[i].data = l->items.data;
+    bytes += pad(4 * (uint64_t)(lists[i].n + 1));
+    if ((rc = plan_strcol(item_plans[i], &item_src[i], &lists[i].dst->items, n_items, &bytes, lists[i].name))) return rc;
+  }
+  if (E > 0 && (!hv->delay_sec || !hv->delay_valid)) return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
+  if ((rc = g_arena.reserve(bytes))) return rc;
+  dv->n_shows = S;
+  dv->n_entries = E;
+  if ((rc = upload_array(hv->entry_offsets, S + 1, &dv->entry_offsets, h2d))) return rc;
+  for (int i = 0; i < kCols; ++i)
+    if ((rc = upload_strcol(plans[i], h2d))) return rc;
+  for (int i = 0; i < 2; ++i) {
+    if ((rc = upload_array(lists[i].src->list_offsets, lists[i].n + 1, &lists[i].dst->list_offsets, h2d))) return rc;
+    if ((rc = upload_strcol(item_plans[i], h2d))) return rc;
+    lists[i].dst->items.offsets -= item_first[i];  // list offsets keep their host (absolute) values
+  }
+  if ((rc = upload_array(hv->delay_sec, E, &dv->delay_sec, h2d))) return rc;
+  if ((rc = upload_array(hv->delay_valid, E, &dv->delay_valid, h2d))) return rc;
+  return PIE_OK;
+}
+
+int check_export_view_dev(const pie_archive_view* v) {
+  const pie_strcol* cols[] = {&v->show_id, &v->show_date, &v->show_time, &v->show_label, &v->lead_pilot, &v->monkey_lead,
+                              &v->show_notes, &v->entry_id, &v->unit_id, &v->planned, &v->launched, &v->status,
+                              &v->primary_issue, &v->sub_issue, &v->other_detail, &v->severity, &v->root_cause,
+                              &v->operator_name, &v->battery_id, &v->command_rx, &v->notes, &v->crew.items,
+                              &v->actions.items};
+  for (const pie_strcol* c : cols)
+    if (!c->offsets) return fail(PIE_ERR_INVALID_ARG, "export rows read every string column: one is NULL");
+  if (!v->crew.list_offsets || !v->actions.list_offsets) return fail(PIE_ERR_INVALID_ARG, "list_offsets is NULL");
+  if (v->n_entries > 0 && (!v->delay_sec || !v->delay_valid)) return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
+  return PIE_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -345,6 +442,67 @@ int pie_show_stats_host(const pie_archive_view* hv, int32_t* stats_i32, double* 
   std::lock_guard<std::mutex> lock(g_host_mutex);
   if (!stats_i32 || !stats_f64) return fail(PIE_ERR_INVALID_ARG, "output is NULL");
   return analytics_host_locked(hv, 0, stats_i32, stats_f64, stride, nullptr);
+}
+
+uint64_t pie_csv_rows_scratch_bytes(int64_t n_entries) { return pie::csv_scratch_bytes(n_entries); }
+
+int pie_csv_rows_dev(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,
+                     uint64_t* total_bytes_dev, void* scratch, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_view_common(v))) return rc;
+  if ((rc = check_export_view_dev(v))) return rc;
+  if (!row_offsets || !total_bytes_dev || !scratch) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  PIE_CUDA(pie::launch_csv_rows(*v, row_offsets, out_data, out_data ? out_capacity : 0,
+                                (unsigned long long*)total_bytes_dev, scratch, (cudaStream_t)stream));
+  return PIE_OK;
+}
+
+int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,
+                      uint64_t* total_bytes) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_view_common(hv))) return rc;
+  if (!row_offsets || !total_bytes) return fail(PIE_ERR_INVALID_ARG, "row_offsets / total_bytes is NULL");
+  const int64_t S = hv->n_shows, E = hv->n_entries;
+  if (S > 0 && (hv->entry_offsets[0] != 0 || hv->entry_offsets[S] != E))
+    return fail(PIE_ERR_INVALID_ARG, "entry_offsets must run from 0 to n_entries");
+  uint64_t h2d = 0, d2h = 0;
+  pie_archive_view dv;
+  memset(&dv, 0, sizeof(dv));
+  const uint64_t extra = pad(pie::csv_scratch_bytes(E)) + pad(8 * (uint64_t)(E + 1)) + pad(64);
+  if ((rc = upload_export_view(hv, &dv, extra, &h2d))) return rc;
+  cudaStream_t st = g_arena.stream;
+  void* scratch = g_arena.take(pie::csv_scratch_bytes(E));
+  int64_t* d_offsets = (int64_t*)g_arena.take(8 * (uint64_t)(E + 1));
+  unsigned long long* d_total = (unsigned long long*)g_arena.take(16);
+  // pass 1: sizes only (row offsets + total), so the output buffer can be sized exactly
+  PIE_CUDA(pie::launch_csv_rows(dv, d_offsets, nullptr, 0, d_total, scratch, st));
+  unsigned long long total = 0;
+  PIE_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+  PIE_CUDA(cudaStreamSynchronize(st));
+  d2h += 8;
+  *total_bytes = total;
+  g_last_h2d = h2d;
+  g_last_d2h = d2h;
+  if (!out_data) {  // size query
+    PIE_CUDA(cudaMemcpyAsync(row_offsets, d_offsets, 8 * (uint64_t)(E + 1), cudaMemcpyDeviceToHost, st));
+    PIE_CUDA(cudaStreamSynchronize(st));
+    g_last_d2h += 8 * (uint64_t)(E + 1);
+    return PIE_OK;
+  }
+  if (total > out_capacity)
+    return fail(PIE_ERR_CAPACITY, "CSV rows need %llu bytes, the caller's buffer holds %llu", total,
+                (unsigned long long)out_capacity);
+  if ((rc = g_out.ensure(total + 256))) return rc;
+  // pass 2: write (the inputs are still resident; most of them are now in L2)
+  PIE_CUDA(pie::launch_csv_rows(dv, d_offsets, g_out.base, total, d_total, scratch, st));
+  PIE_CUDA(cudaMemcpyAsync(row_offsets, d_offsets, 8 * (uint64_t)(E + 1), cudaMemcpyDeviceToHost, st));
+  if (total) PIE_CUDA(cudaMemcpyAsync(out_data, g_out.base, total, cudaMemcpyDeviceToHost, st));
+  PIE_CUDA(cudaStreamSynchronize(st));
+  g_last_d2h = d2h + 8 * (uint64_t)(E + 1) + total;
+  return PIE_OK;
 }
 
 int pie_selftest_fast_div(int32_t max_b, uint64_t* mismatches) {

@@ -15,6 +15,11 @@ cudaError_t launch_show_stats(const pie_archive_view& dev_view, int32_t* stats_i
                               int64_t stride, int sm_count, cudaStream_t stream);
 cudaError_t launch_selftest_fast_div(int max_b, unsigned long long* d_mismatches, cudaStream_t stream);
 
+// csv_rows.cu
+uint64_t csv_scratch_bytes(int64_t n_entries);
+cudaError_t launch_csv_rows(const pie_archive_view& dev_view, int64_t* row_offsets, uint8_t* out_data,
+                            uint64_t capacity, unsigned long long* total_out, void* scratch, cudaStream_t stream);
+
 // archive_daily.cu
 uint64_t daily_scratch_bytes(int64_t n_shows);
 cudaError_t launch_daily_summary(const pie_archive_view& dev_view, const int32_t* stats_i32,

@@ -157,3 +157,62 @@ def archive_analytics(table: ArchiveTable, tz_offset_minutes: int = 0, bufs=None
     return (ShowStats(h.stats_i32[:, :S], h.stats_f64[:, :S]),
             DailySummary(G, h.show_day_start[:S], h.show_order[:S], h.group_day_start[:G], h.group_offsets[:G + 1],
                          h.summary_f64[:, :, :G], h.summary_count[:, :G]))
+
+
+@dataclass
+class CsvRows:
+    """Export rows as one string column (buildCsvRow per entry, reference webhookDispatcher.js:340-342):
+    row i = data[row_offsets[i] : row_offsets[i+1] - 1]; every row is followed by '\\n'."""
+    row_offsets: torch.Tensor  # int64 [n_entries + 1]
+    data: torch.Tensor         # uint8 [total_bytes]
+
+    def row(self, i: int) -> str:
+        o = self.row_offsets
+        return bytes(self.data[int(o[i]):int(o[i + 1]) - 1].cpu().numpy()).decode("utf-8")
+
+    def rows(self):
+        o = self.row_offsets.cpu().tolist()
+        b = bytes(self.data.cpu().numpy())
+        return [b[o[i]:o[i + 1] - 1].decode("utf-8") for i in range(len(o) - 1)]
+
+
+class CsvBuffers:
+    """Pre-allocated device outputs + scratch for pie_csv_rows_dev."""
+
+    def __init__(self, n_entries: int, capacity_bytes: int, device):
+        lib = _lib.load()
+        self.row_offsets = torch.empty(n_entries + 1, dtype=torch.int64, device=device)
+        self.data = torch.empty(max(capacity_bytes, 1), dtype=torch.uint8, device=device)
+        self.capacity = capacity_bytes
+        self.total = torch.zeros(1, dtype=torch.int64, device=device)
+        self.scratch = torch.empty(int(lib.pie_csv_rows_scratch_bytes(n_entries)), dtype=torch.uint8, device=device)
+
+
+def csv_rows_dev(table: ArchiveTable, bufs: CsvBuffers, size_only: bool = False) -> None:
+    """Enqueue the export-row kernels on torch's current stream (no sync)."""
+    _lib.ensure_init()
+    view = table.view()
+    _lib.check(_lib.load().pie_csv_rows_dev(C.byref(view), bufs.row_offsets.data_ptr(),
+                                            None if size_only else bufs.data.data_ptr(), bufs.capacity,
+                                            bufs.total.data_ptr(), bufs.scratch.data_ptr(), _stream_ptr()))
+
+
+def csv_rows(table: ArchiveTable) -> CsvRows:
+    """buildCsvRow(buildTableRow(show, entry)) for every entry of every show."""
+    _lib.ensure_init()
+    E = table.n_entries
+    if table.is_cuda:
+        sizing = CsvBuffers(E, 0, table.device)
+        csv_rows_dev(table, sizing, size_only=True)
+        total = int(sizing.total.cpu())
+        bufs = CsvBuffers(E, total, table.device)
+        csv_rows_dev(table, bufs)
+        return CsvRows(bufs.row_offsets, bufs.data[:total])
+    view = table.view()
+    offsets = torch.empty(E + 1, dtype=torch.int64)
+    total = C.c_uint64(0)
+    lib = _lib.load()
+    _lib.check(lib.pie_csv_rows_host(C.byref(view), offsets.data_ptr(), None, 0, C.byref(total)))
+    data = torch.empty(max(int(total.value), 1), dtype=torch.uint8)
+    _lib.check(lib.pie_csv_rows_host(C.byref(view), offsets.data_ptr(), data.data_ptr(), int(total.value), C.byref(total)))
+    return CsvRows(offsets, data[:int(total.value)])

@@ -1,0 +1,44 @@
+"""Host-side mirror of the reference's export-row functions (server/webhookDispatcher.js), same
+names and argument meaning.  The per-entry CSV strings are produced on the GPU through the C ABI;
+the pure re-shaping functions (object <-> column order) are plain host code, as in the reference.
+
+    EXPORT_COLUMNS                       server/webhookDispatcher.js:15-19
+    buildCsvRows(show)                   tableRows.map(buildCsvRow) of dispatchShowEvent (:556, :571)
+    exportShowAsCsv(show)                public/app.js:5558-5570 (returns the CSV text)
+    buildMessagePayload(rowObject)       server/webhookDispatcher.js:307-313
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+from .columnar import pack_shows
+from .ops import csv_rows
+
+EXPORT_COLUMNS = [
+    "showId", "showDate", "showTime", "showLabel", "crew", "leadPilot", "monkeyLead", "showNotes",
+    "entryId", "unitId", "planned", "launched", "status", "primaryIssue", "subIssue", "otherDetail",
+    "severity", "rootCause", "actions", "operator", "batteryId", "delaySec", "commandRx", "notes",
+]
+
+
+def buildCsvRowsMany(shows: List[Optional[dict]]) -> List[List[str]]:
+    """csv.rows of every show in one launch: buildCsvRow(buildTableRow(show, entry)) per entry."""
+    table = pack_shows(shows)
+    rows = csv_rows(table).rows()
+    eo = table.entry_offsets.tolist()
+    return [rows[eo[s]:eo[s + 1]] for s in range(len(shows))]
+
+
+def buildCsvRows(show: Optional[dict]) -> List[str]:
+    return buildCsvRowsMany([show])[0]
+
+
+def exportShowAsCsv(show: dict) -> str:
+    """Header line + one line per entry, joined by '\\n' (public/app.js:5567).  The header cells
+    are EXPORT_COLUMNS through csvEscape, which leaves these identifiers unchanged."""
+    return "\n".join([",".join(EXPORT_COLUMNS)] + buildCsvRows(show))
+
+
+def buildMessagePayload(rowObject: Optional[dict] = None) -> dict:
+    row = rowObject if isinstance(rowObject, dict) else {}
+    return {c: ("" if row.get(c) is None else row[c]) for c in EXPORT_COLUMNS}

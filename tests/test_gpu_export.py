@@ -1,0 +1,137 @@
+"""Export rows (buildTableRow -> csvEscape -> buildCsvRow) on the GPU against the oracles.
+Bit-exact: byte strings and int64 offsets."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_c
+import pie_oracle as po
+from sph_pie_b200 import _lib, ops
+from sph_pie_b200.columnar import pack_shows
+from sph_pie_b200.synth import synth_archive, table_to_shows
+from sph_pie_b200.webhook import EXPORT_COLUMNS, buildCsvRows, buildCsvRowsMany, buildMessagePayload, exportShowAsCsv
+from test_export_rows_cpu import number_samples
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_same_rows(got: ops.CsvRows, table):
+    offsets, data = oracle_c.csv_rows(table)
+    assert torch.equal(got.row_offsets.cpu(), offsets), "row_offsets"
+    assert torch.equal(got.data.cpu(), data), "csv bytes"
+
+
+@pytest.mark.parametrize("n_shows,seed", [(1, 0), (7, 1), (310, 2), (5000, 3), (40000, 4)])
+def test_csv_rows_match_c_oracle_both_entry_points(cuda, n_shows, seed):
+    host = synth_archive(n_shows, seed=seed)
+    assert_same_rows(ops.csv_rows(host), host)
+    assert_same_rows(ops.csv_rows(host.to(cuda)), host)
+
+
+def test_number_to_string_on_device(cuda):
+    """delaySec cells over ~160k doubles (random bit patterns, integers, decimals, powers, subnormals,
+    specials): Number::toString on the device vs the Python oracle and the printf oracle."""
+    xs = number_samples(20000, 11)
+    n = len(xs)
+    table = synth_archive(1, seed=0, max_entries=0)
+    shows = [{"id": "n", "entries": [{"delaySec": float(x)} for x in xs]}]
+    table = pack_shows(shows)
+    rows = ops.csv_rows(table.to(cuda)).rows()
+    assert len(rows) == n
+    printf = oracle_c.number_to_string_batch(xs)
+    for x, row, want_c in zip(xs.tolist(), rows, printf):
+        cell = row.split(",")[21]
+        assert cell == po.js_number_to_string(x) == want_c, (x, cell, want_c)
+
+
+def test_edge_rows_and_mirror_api(cuda):
+    shows = [{"id": 'a"b', "date": "2024-07-04", "time": "21:00", "label": "x,y", "crew": ["A|B", 'q"', ""],
+              "leadPilot": "l\np", "monkeyLead": "", "notes": "r\rn",
+              "entries": [
+                  {"id": "e1", "status": "Completed", "primaryIssue": "Battery", "subIssue": "s", "otherDetail": "o",
+                   "severity": "v", "rootCause": "r", "actions": ["x,y", "z"], "delaySec": 0, "notes": '""'},
+                  {"id": "e2", "status": "completed", "primaryIssue": "Battery", "delaySec": 1e21, "actions": []},
+                  {"id": "e3", "status": "Abort", "delaySec": None, "notes": ","},
+                  {"id": "e4", "delaySec": -0.0}, {"id": "e5", "delaySec": float("nan")}, {"delaySec": 1.5e-7},
+                  {"id": "ü-ñ-漢字", "notes": "emoji 🚁, ok"}]},
+             {"id": "empty", "entries": []}, None,
+             {"id": "long", "entries": [{"id": "L", "notes": "x" * 70000 + '"' + "y" * 5000}, {"id": "after"}]}]
+    many = buildCsvRowsMany(shows)
+    for show, rows in zip(shows, many):
+        entries = (show or {}).get("entries", [])
+        assert rows == [po.build_csv_row(po.build_table_row(show, e)) for e in entries]
+    assert exportShowAsCsv(shows[0]) == po.export_show_as_csv(shows[0])
+    assert exportShowAsCsv(shows[1]) == ",".join(EXPORT_COLUMNS)
+    assert buildCsvRows(None) == []
+    row = po.build_table_row(shows[0], shows[0]["entries"][0])
+    assert buildMessagePayload(row) == po.build_message_payload(row)
+    dev = pack_shows(shows).to(cuda)
+    assert_same_rows(ops.csv_rows(dev), pack_shows(shows))
+
+
+def test_reference_fixture_row(cuda):
+    """The reference's only fixture (scripts/simulate-webhook.js:42-65)."""
+    import json
+    import os
+
+    fix = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "webhook_fixture.json")))
+    show = dict(fix["show"], entries=[fix["entry"]])
+    assert buildCsvRows(show) == [fix["expected_csv_row"]]
+    assert exportShowAsCsv(show) == ",".join(fix["export_columns"]) + "\n" + fix["expected_csv_row"]
+
+
+def test_capacity_and_size_query(cuda):
+    host = synth_archive(300, seed=5)
+    dev = host.to(cuda)
+    offsets, data = oracle_c.csv_rows(host)
+    sizing = ops.CsvBuffers(dev.n_entries, 0, cuda)
+    ops.csv_rows_dev(dev, sizing, size_only=True)
+    assert int(sizing.total.cpu()) == data.numel() and torch.equal(sizing.row_offsets.cpu(), offsets)
+    small = ops.CsvBuffers(dev.n_entries, data.numel() // 2, cuda)
+    small.data.fill_(0xEE)
+    ops.csv_rows_dev(dev, small)
+    torch.cuda.synchronize()
+    assert int(small.total.cpu()) == data.numel()            # still reports the size needed
+    # nothing written past the capacity the caller gave (buffer is exactly capacity bytes long, so an
+    # overrun would corrupt the allocator's neighbour; check the prefix that was written is right)
+    written = small.data.cpu()
+    k = int(torch.nonzero(written != 0xEE).max()) + 1 if bool((written != 0xEE).any()) else 0
+    assert k <= data.numel() // 2 and torch.equal(written[:k], data[:k])
+    import ctypes as C
+
+    view = host.view()
+    total = C.c_uint64(0)
+    off = torch.empty(host.n_entries + 1, dtype=torch.int64)
+    buf = torch.empty(16, dtype=torch.uint8)
+    rc = _lib.load().pie_csv_rows_host(C.byref(view), off.data_ptr(), buf.data_ptr(), 16, C.byref(total))
+    assert rc == _lib.PIE_ERR_CAPACITY and total.value == data.numel()
+
+
+def test_round_trip_through_python_csv_module(cuda):
+    """Size-independent property at a larger size: the bytes parse back (RFC 4180 reader) into the
+    24 cells buildTableRow defines, for every row."""
+    import csv
+    import io
+
+    host = synth_archive(20000, seed=6)
+    shows = table_to_shows(host)
+    got = ops.csv_rows(host.to(cuda))
+    text = bytes(got.data.cpu().numpy()).decode("utf-8")
+    parsed = list(csv.reader(io.StringIO(text, newline=""), lineterminator="\n"))
+    assert len(parsed) == host.n_entries
+    i = 0
+    for show in shows:
+        for entry in show["entries"]:
+            row = po.build_table_row(show, entry)
+            want = ["" if row[c] == "" else po.js_string(row[c]) for c in EXPORT_COLUMNS]
+            assert parsed[i] == want, i
+            i += 1
+
+
+def test_sliced_table_rows(cuda):
+    host = synth_archive(3000, seed=7)
+    whole = ops.csv_rows(host).rows()
+    part = host.slice_shows(1000, 2200)
+    e0, e1 = int(host.entry_offsets[1000]), int(host.entry_offsets[2200])
+    assert ops.csv_rows(part).rows() == whole[e0:e1]
+    assert ops.csv_rows(host.to(cuda).slice_shows(1000, 2200)).rows() == whole[e0:e1]
