@@ -8,11 +8,13 @@ scope, and the headline workload is ~1700x beyond what the reference can hold.  
 carries a measurement at the reference-reachable maximum too (`reference_scale`), where the GPU
 end-to-end call is NOT faster than one CPU core.  vs_baseline is null: nothing is published.
 
-A step = one pass of the path over one batch: computeArchiveShowStats for every show, the daily
-groups and the 19 metric summaries per day (public/app.js:3401-3502, :3898-3953).
+A step = one pass of the path over one batch:
+  analytics  computeArchiveShowStats for every show, the daily groups and the 19 metric summaries per
+             day (public/app.js:3401-3502, :3898-3953)
+  export     buildCsvRow(buildTableRow(show, entry)) for every entry (server/webhookDispatcher.js:276-342)
   value : entries/s, table resident in HBM, kernels only (CUDA events on the launch stream)
-  e2e   : entries/s through pie_archive_analytics_host (HOST buffers in, HOST results out,
-          H2D + kernels + D2H inside the timed region)
+  e2e   : entries/s through pie_archive_analytics_host + pie_csv_rows_host (HOST buffers in, HOST
+          results out, H2D + kernels + D2H inside the timed region)
 """
 from __future__ import annotations
 
@@ -129,17 +131,33 @@ def analytics_bytes(table, n_groups: int):
     return stats_in + stats_out, daily_in + daily_out
 
 
-def cpu_baseline_run(host_table, tz, nthreads, min_seconds=1.0, max_reps=8):
-    """Times the C oracle (oracle/pie_oracle.c) over `host_table`; returns (entries/s, reps, seconds)."""
-    import oracle_c
-    from sph_pie_b200.ops import HostOutputs
+class CpuStep:
+    """One step of the path on the host CPU with the C oracle (oracle/pie_oracle.c), output buffers
+    preallocated outside the timed region (like the GPU arm)."""
 
-    hout = HostOutputs(host_table.n_shows)
-    oracle_c.archive_analytics(host_table, tz, nthreads, hout)  # warm caches / page in
+    def __init__(self, host_table, tz, nthreads):
+        import torch
+
+        import oracle_c
+        from sph_pie_b200.ops import HostOutputs
+
+        self.o, self.t, self.tz, self.n = oracle_c, host_table, tz, nthreads
+        self.hout = HostOutputs(host_table.n_shows)
+        self.csv_off, data = oracle_c.csv_rows(host_table, nthreads)
+        self.csv_data = torch.empty(max(data.numel(), 1), dtype=torch.uint8)
+
+    def __call__(self):
+        _, _, rc, _ = self.o.archive_analytics(self.t, self.tz, self.n, self.hout)
+        assert rc == 0
+        self.o.csv_rows(self.t, self.n, self.csv_off, self.csv_data)
+
+
+def cpu_baseline_run(host_table, tz, nthreads, min_seconds=1.0, max_reps=8):
+    """Times the C oracle over `host_table`; returns (entries/s, reps, seconds)."""
+    step = CpuStep(host_table, tz, nthreads)  # construction = one warm pass
     reps, t0 = 0, time.perf_counter()
     while True:
-        _, _, rc, _ = oracle_c.archive_analytics(host_table, tz, nthreads, hout)
-        assert rc == 0
+        step()
         reps += 1
         dt = time.perf_counter() - t0
         if dt >= min_seconds or reps >= max_reps:
@@ -158,20 +176,17 @@ def run_reference(args):
     oracle_c.build()
     threads = oracle_c.max_threads()
     shows = min(args.shows, args.cpu_sample_shows)
-    from sph_pie_b200.ops import HostOutputs
-
     table = synth_archive(shows, seed=1234, device="cpu")
-    hout = HostOutputs(table.n_shows)
-    for _ in range(max(args.warmup, 1)):
-        oracle_c.archive_analytics(table, args.tz, threads, hout)
+    step = CpuStep(table, args.tz, threads)
+    for _ in range(max(args.warmup - 1, 0)):
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, _, rc, _ = oracle_c.archive_analytics(table, args.tz, threads, hout)
-        assert rc == 0
+        step()
     dt = time.perf_counter() - t0
     value = table.n_entries * args.steps / dt
     sample = f"{shows} shows / {table.n_entries} entries per step, C port of the path (oracle/pie_oracle.c), " \
-             f"show statistics on {threads} threads, daily grouping on 1"
+             f"show statistics and export rows on {threads} threads, daily grouping on 1"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -185,11 +200,20 @@ def run_reference(args):
 def workload_config(args, shows, entries):
     return {
         "workload": f"synthetic archive: {shows} shows x 0..21 entries ({entries} entries) per GPU, <=5 shows/day, "
-                    "show statistics + daily groups + 19 metric summaries",
+                    "show statistics + daily groups + 19 metric summaries + CSV export rows",
         "shows_per_gpu": shows, "entries_per_gpu": entries, "tz_offset_minutes": args.tz,
-        "l2_policy": "inputs larger than L2 (the columns a step reads are ~0.45 GB per GPU vs 126 MB L2)",
+        "l2_policy": "inputs larger than L2 (a step reads ~2.2 GB and writes ~3 GB per GPU vs 126 MB L2)",
         "baseline_metric": "N/A: no GPU hot path (BASELINE.json); metric defined by this repo, see DESIGN.md",
     }
+
+
+def csv_bytes(table, total_out: int) -> int:
+    """Algorithmic bytes of the export rows: every column byte once (show-level columns once per
+    SHOW), plus the output bytes and the int64 row offsets."""
+    E, S = table.n_entries, table.n_shows
+    n = sum(c.nbytes() for c in table.entry_cols.values()) + sum(c.nbytes() for c in table.show_cols.values())
+    n += table.crew.nbytes() + table.actions.nbytes() + 9 * E + 4 * (S + 1)
+    return n + total_out + 8 * (E + 1)
 
 
 def main():
@@ -219,15 +243,21 @@ def main():
     table = synth_archive(args.shows, seed=1234 + rank, device=dev, start_ms=1704067200000 + rank * days_per_rank * 86400000)
     S, E = table.n_shows, table.n_entries
     bufs = ops.DailyBuffers(S, E, dev)
+    sizing = ops.CsvBuffers(E, 0, dev)
+    ops.csv_rows_dev(table, sizing, size_only=True)
+    csv_total = int(sizing.total.cpu())
+    del sizing
+    cbufs = ops.CsvBuffers(E, csv_total, dev)
 
     def step():
         ops.show_stats_dev(table, bufs)
         ops.daily_summary_dev(table, bufs, args.tz)
+        ops.csv_rows_dev(table, cbufs)
 
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    assert int(bufs.status[0]) == 0
+    assert int(bufs.status[0]) == 0 and int(cbufs.total) == csv_total
     n_groups = int(bufs.n_groups)
 
     def barrier():
@@ -238,7 +268,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: resident inputs, CUDA events on torch's current stream (the launch stream)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     launches0 = int(lib.pie_kernel_launch_count())
     barrier()
     with ClockSampler(local) as clocks:
@@ -251,6 +281,8 @@ def main():
             ev[k][1].record()
             ops.daily_summary_dev(table, bufs, args.tz)
             ev[k][2].record()
+            ops.csv_rows_dev(table, cbufs)
+            ev[k][3].record()
         t_end.record()
         clocks.sample()
         barrier()
@@ -258,18 +290,32 @@ def main():
     total_ms = t_start.elapsed_time(t_end)
     stats_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     daily_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    csv_ms = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    import ctypes as C
+
     host = table.to("cpu").pin()
     hout = ops.HostOutputs(S, pinned=True)
-    for _ in range(3):
-        ops.archive_analytics(host, args.tz, hout)
-    h2d, d2h = _lib.last_transfer_bytes()
-    e2e_steps = max(3, min(args.steps, 20))
+    h_off = torch.empty(E + 1, dtype=torch.int64, pin_memory=True)
+    h_csv = torch.empty(max(csv_total, 1), dtype=torch.uint8, pin_memory=True)
+    hview = host.view()
+    h_total = C.c_uint64(0)
+
+    def e2e_step():
+        ops.archive_analytics(host, args.tz, hout)  # returns after its D2H copies have completed
+        a = _lib.last_transfer_bytes()
+        _lib.check(lib.pie_csv_rows_host(C.byref(hview), h_off.data_ptr(), h_csv.data_ptr(), csv_total, C.byref(h_total)))
+        b = _lib.last_transfer_bytes()
+        return a[0] + b[0], a[1] + b[1]
+
+    for _ in range(2):
+        h2d, d2h = e2e_step()
+    e2e_steps = max(3, min(args.steps, 10))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ops.archive_analytics(host, args.tz, hout)  # returns after the D2H copies have completed
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
@@ -293,12 +339,15 @@ def main():
     value = total_entries * args.steps / (total_ms * 1e-3)
     e2e_value = total_entries * e2e_steps / e2e_s
     stats_bytes, daily_bytes = analytics_bytes(table, n_groups)
+    export_bytes = csv_bytes(table, csv_total)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    achieved = stats_bytes / (stats_ms * 1e-3) / 1e9
+
+    def gbs(nbytes, ms):
+        return nbytes / (ms * 1e-3) / 1e9
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -306,16 +355,21 @@ def main():
         "dtype": "u8/int32/f64", "data": "synthetic",
         "config": workload_config(args, S, E),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "pie_archive_analytics_host (pinned host buffers in and out)"},
+                "steps": e2e_steps, "api": "pie_archive_analytics_host + pie_csv_rows_host (pinned host buffers in and out)"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
-        "roofline": {
-            "bound": "hbm", "kernel": "show statistics (classify_entries_kernel + reduce_shows_kernel)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": stats_bytes, "ms_per_launch": stats_ms,
-            "bytes_per_entry": stats_bytes / max(E, 1),
-            "daily": {"ms_per_step": daily_ms, "algorithmic_bytes": daily_bytes,
-                      "achieved_gbs": daily_bytes / (daily_ms * 1e-3) / 1e9},
+        "roofline": {  # the dominant kernel of the step: csv_rows_kernel
+            "bound": "hbm", "kernel": "csv_rows_kernel (export rows)",
+            "achieved": gbs(export_bytes, csv_ms), "peak": peak, "unit": "GB/s", "frac": gbs(export_bytes, csv_ms) / peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": export_bytes,
+            "ms_per_launch": csv_ms, "bytes_per_entry": export_bytes / max(E, 1), "csv_bytes_out": csv_total,
+            "other_kernels": {
+                "show_stats_kernel": {"ms_per_launch": stats_ms, "algorithmic_bytes": stats_bytes,
+                                      "achieved_gbs": gbs(stats_bytes, stats_ms), "frac": gbs(stats_bytes, stats_ms) / peak},
+                "daily pipeline (7 small kernels)": {"ms_per_step": daily_ms, "algorithmic_bytes": daily_bytes,
+                                                     "achieved_gbs": gbs(daily_bytes, daily_ms),
+                                                     "frac": gbs(daily_bytes, daily_ms) / peak},
+            },
         },
     }
 
@@ -343,20 +397,32 @@ def reference_scale(args, dev):
     from sph_pie_b200 import ops
     from sph_pie_b200.synth import synth_archive
 
+    import ctypes as C
+
+    from sph_pie_b200 import _lib
+
     small = synth_archive(310, seed=99, device="cpu")
     pinned = small.pin()
     hout = ops.HostOutputs(small.n_shows, pinned=True)
-    for _ in range(5):
+    cpu = CpuStep(small, args.tz, 1)
+    off = torch.empty(small.n_entries + 1, dtype=torch.int64, pin_memory=True)
+    data = torch.empty(cpu.csv_data.numel(), dtype=torch.uint8, pin_memory=True)
+    view, total, lib = pinned.view(), C.c_uint64(0), _lib.load()
+
+    def gpu_step():
         ops.archive_analytics(pinned, args.tz, hout)
+        _lib.check(lib.pie_csv_rows_host(C.byref(view), off.data_ptr(), data.data_ptr(), data.numel(), C.byref(total)))
+
+    for _ in range(5):
+        gpu_step()
     n = 200
     t0 = time.perf_counter()
     for _ in range(n):
-        ops.archive_analytics(pinned, args.tz, hout)
+        gpu_step()
     gpu_us = (time.perf_counter() - t0) / n * 1e6
-    oracle_c.archive_analytics(small, args.tz, 1)
     t0 = time.perf_counter()
     for _ in range(n):
-        oracle_c.archive_analytics(small, args.tz, 1)
+        cpu()
     cpu_us = (time.perf_counter() - t0) / n * 1e6
     return {"shows": small.n_shows, "entries": small.n_entries, "gpu_e2e_us_per_call": gpu_us,
             "cpu_port_1core_us_per_call": cpu_us,

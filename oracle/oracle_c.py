@@ -72,18 +72,22 @@ def archive_analytics(table: ArchiveTable, tz_offset_minutes: int = 0, nthreads:
                             h.summary_f64[:, :, :G], h.summary_count[:, :G]), 0, -1
 
 
-def csv_rows(table: ArchiveTable):
-    """(row_offsets int64[E+1], data uint8[total]) from the C restatement of buildCsvRow."""
+def csv_rows(table: ArchiveTable, nthreads: int = 1, offsets=None, data=None):
+    """(row_offsets int64[E+1], data uint8[total]) from the C restatement of buildCsvRow.
+    With preallocated `offsets`/`data` (timed baseline) one call does the whole job."""
     assert not table.is_cuda
     so = load()
-    so.oracle_csv_rows.restype = C.c_int
-    so.oracle_csv_rows.argtypes = [C.POINTER(_lib.ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    so.oracle_csv_rows_mt.restype = C.c_int
+    so.oracle_csv_rows_mt.argtypes = [C.POINTER(_lib.ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64,
+                                      C.POINTER(C.c_uint64), C.c_int]
     view = table.view()
-    offsets = torch.empty(table.n_entries + 1, dtype=torch.int64)
     total = C.c_uint64(0)
-    so.oracle_csv_rows(C.byref(view), offsets.data_ptr(), None, 0, C.byref(total))
-    data = torch.empty(max(int(total.value), 1), dtype=torch.uint8)
-    so.oracle_csv_rows(C.byref(view), offsets.data_ptr(), data.data_ptr(), int(total.value), C.byref(total))
+    if offsets is None:
+        offsets = torch.empty(table.n_entries + 1, dtype=torch.int64)
+    if data is None:
+        so.oracle_csv_rows_mt(C.byref(view), offsets.data_ptr(), None, 0, C.byref(total), nthreads)
+        data = torch.empty(max(int(total.value), 1), dtype=torch.uint8)
+    so.oracle_csv_rows_mt(C.byref(view), offsets.data_ptr(), data.data_ptr(), data.numel(), C.byref(total), nthreads)
     return offsets, data[: int(total.value)]
 
 

@@ -405,22 +405,44 @@ static int js_number_to_string(double x, char* out) {
   if (isinf(x)) return sprintf(out, x > 0 ? "Infinity" : "-Infinity");
   if (x == 0) return sprintf(out, "0");
   const double ax = fabs(x);
+  if (ax < 9007199254740992.0 && ax == floor(ax)) /* integers below 2^53 print exactly */
+    return sprintf(out, "%s%llu", x < 0 ? "-" : "", (unsigned long long)ax);
   char buf[48], cand[48];
   unsigned long long best = 0;
   int best_q = 0, found = 0;
-  for (int p = 1; p <= 17 && !found; ++p) {
+  /* short fixed-point decimals (12.5, 0.25, 3.1): the fewest fractional digits d with
+   * m = |x|*10^d integral and "m e-d" reading back as x.  m < 2^50 keeps neighbouring d-digit
+   * decimals more than an ulp apart, so the round-tripping one is unique (hence the closest). */
+  double scale = 1;
+  for (int d = 1; d <= 6 && !found; ++d) {
+    scale *= 10;
+    const double m = ax * scale;
+    if (m >= 1125899906842624.0) break;
+    if (m == floor(m)) {
+      snprintf(cand, sizeof cand, "%llue-%d", (unsigned long long)m, d);
+      if (strtod(cand, NULL) == ax) { best = (unsigned long long)m; best_q = -d; found = 1; }
+    }
+  }
+  /* general case: "p digits suffice" is monotone in p -> binary search for the smallest p */
+  int lo = 1, hi = 17;
+  while (!found) {
+    const int p = (lo == hi) ? lo : (lo + hi) / 2;
     snprintf(buf, sizeof buf, "%.*e", p - 1, ax);
     char* e = strchr(buf, 'e');
     unsigned long long m = 0;
     for (char* c = buf; c < e; ++c) if (*c != '.') m = m * 10 + (unsigned long long)(*c - '0');
     const int q = atoi(e + 1) - (p - 1); /* |x| ~ m * 10^q */
     const long long delta[3] = {0, 1, -1};
-    for (int t = 0; t < 3 && !found; ++t) {
+    int ok = 0;
+    unsigned long long okc = 0;
+    for (int t = 0; t < 3 && !ok; ++t) {
       if (m == 0 && delta[t] < 0) continue;
       const unsigned long long c = m + (unsigned long long)delta[t];
       snprintf(cand, sizeof cand, "%llue%d", c, q);
-      if (strtod(cand, NULL) == ax) { best = c; best_q = q; found = 1; }
+      if (strtod(cand, NULL) == ax) { ok = 1; okc = c; }
     }
+    if (lo == hi) { best = okc; best_q = q; found = 1; break; } /* p = 17 always round-trips */
+    if (ok) hi = p; else lo = p + 1;
   }
   while (best % 10 == 0) { best /= 10; best_q++; } /* 10^p from a carry, trailing zeros */
   char digits[24];
@@ -450,49 +472,55 @@ static int js_number_to_string(double x, char* out) {
 
 typedef struct { uint8_t* p; uint64_t n; uint64_t cap; } csv_out; /* p may be NULL: count only */
 
-static void put_bytes(csv_out* o, const uint8_t* s, uint64_t n) {
-  if (o->p && o->n + n <= o->cap) memcpy(o->p + o->n, s, (size_t)n);
+static inline void put_bytes(csv_out* o, const uint8_t* s, uint64_t n) {
+  if (o->p && o->n + n <= o->cap) {
+    uint8_t* d = o->p + o->n;
+    if (n <= 16) for (uint64_t i = 0; i < n; ++i) d[i] = s[i];
+    else memcpy(d, s, (size_t)n);
+  }
   o->n += n;
 }
-static void put_char(csv_out* o, char c) { uint8_t b = (uint8_t)c; put_bytes(o, &b, 1); }
+static inline void put_char(csv_out* o, char c) {
+  if (o->p && o->n < o->cap) o->p[o->n] = (uint8_t)c;
+  o->n += 1;
+}
+static inline int is_special(uint8_t c) { return c == '"' || c == ',' || c == '\n' || c == '\r'; }
 
 /* csvEscape (:332-338) */
-static void put_cell(csv_out* o, const uint8_t* s, int n) {
+static inline void put_cell(csv_out* o, const uint8_t* s, int n) {
   int quote = 0;
-  for (int i = 0; i < n; ++i) if (s[i] == '"' || s[i] == ',' || s[i] == '\n' || s[i] == '\r') quote = 1;
+  for (int i = 0; i < n; ++i) quote |= is_special(s[i]);
   if (!quote) { put_bytes(o, s, (uint64_t)n); return; }
   put_char(o, '"');
-  for (int i = 0; i < n; ++i) { if (s[i] == '"') put_char(o, '"'); put_bytes(o, s + i, 1); }
+  for (int i = 0; i < n; ++i) { if (s[i] == '"') put_char(o, '"'); put_char(o, (char)s[i]); }
   put_char(o, '"');
 }
-static void put_col(csv_out* o, const pie_strcol* c, int64_t i) {
+static inline void put_col(csv_out* o, const pie_strcol* c, int64_t i) {
   put_cell(o, c->data + c->offsets[i], c->offsets[i + 1] - c->offsets[i]);
 }
-/* list.join('|') then csvEscape */
-static void put_joined(csv_out* o, const pie_strlistcol* c, int64_t i) {
-  int l0 = c->list_offsets[i], l1 = c->list_offsets[i + 1];
-  uint64_t cap = 16;
-  for (int l = l0; l < l1; ++l) cap += (uint64_t)(c->items.offsets[l + 1] - c->items.offsets[l]) + 1;
-  uint8_t* tmp = (uint8_t*)malloc(cap);
-  int n = 0;
+/* list.join('|') then csvEscape of the joined string: '|' is not special, so the joined string
+ * needs quotes iff one of the items holds a special character */
+static inline void put_joined(csv_out* o, const pie_strlistcol* c, int64_t i) {
+  const int l0 = c->list_offsets[i], l1 = c->list_offsets[i + 1];
+  if (l1 <= l0) return;
+  const uint8_t* d = c->items.data;
+  int quote = 0;
+  for (int k = c->items.offsets[l0]; k < c->items.offsets[l1]; ++k) quote |= is_special(d[k]);
+  if (quote) put_char(o, '"');
   for (int l = l0; l < l1; ++l) {
-    if (l > l0) tmp[n++] = '|';
-    int len = c->items.offsets[l + 1] - c->items.offsets[l];
-    memcpy(tmp + n, c->items.data + c->items.offsets[l], (size_t)len);
-    n += len;
+    if (l > l0) put_char(o, '|');
+    const int b = c->items.offsets[l], e = c->items.offsets[l + 1];
+    if (!quote) put_bytes(o, d + b, (uint64_t)(e - b));
+    else for (int k = b; k < e; ++k) { if (d[k] == '"') put_char(o, '"'); put_char(o, (char)d[k]); }
   }
-  put_cell(o, tmp, n);
-  free(tmp);
+  if (quote) put_char(o, '"');
 }
 
-/* Fills row_offsets[n_entries+1]; writes rows (each followed by '\n') into out_data when it is not
- * NULL and large enough; *total receives the size needed. */
-int oracle_csv_rows(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
-                    uint64_t* total) {
-  csv_out o = {out_data, 0, capacity};
-  for (int64_t s = 0; s < v->n_shows; ++s) {
+static void csv_show_range(const pie_archive_view* v, int64_t s0, int64_t s1, int64_t* row_offsets, csv_out* op) {
+  csv_out o = *op;
+  for (int64_t s = s0; s < s1; ++s) {
     for (int e = v->entry_offsets[s]; e < v->entry_offsets[s + 1]; ++e) {
-      row_offsets[e] = (int64_t)o.n;
+      if (row_offsets) row_offsets[e] = (int64_t)o.n;
       put_col(&o, &v->show_id, s); put_char(&o, ',');
       put_col(&o, &v->show_date, s); put_char(&o, ',');
       put_col(&o, &v->show_time, s); put_char(&o, ',');
@@ -524,8 +552,66 @@ int oracle_csv_rows(const pie_archive_view* v, int64_t* row_offsets, uint8_t* ou
       put_char(&o, '\n');
     }
   }
+  *op = o;
+}
+
+/* Fills row_offsets[n_entries+1]; writes rows (each followed by '\n') into out_data when it is not
+ * NULL and large enough; *total receives the size needed. */
+int oracle_csv_rows(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
+                    uint64_t* total) {
+  csv_out o = {out_data, 0, capacity};
+  csv_show_range(v, 0, v->n_shows, row_offsets, &o);
   row_offsets[v->n_entries] = (int64_t)o.n;
   *total = o.n;
+  return 0;
+}
+
+typedef struct {
+  const pie_archive_view* v;
+  int64_t s0, s1;
+  int64_t* row_offsets;
+  csv_out out;
+} csv_job;
+
+static void* csv_worker(void* arg) {
+  csv_job* j = (csv_job*)arg;
+  csv_show_range(j->v, j->s0, j->s1, j->row_offsets, &j->out);
+  return NULL;
+}
+
+/* Threaded variant for the CPU baseline: a counting pass per show range, a prefix over the ranges,
+ * then the writing pass — the same per-row code as oracle_csv_rows. */
+int oracle_csv_rows_mt(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
+                       uint64_t* total, int nthreads) {
+  const int64_t S = v->n_shows;
+  if (nthreads <= 1 || S < 2 * (int64_t)nthreads) return oracle_csv_rows(v, row_offsets, out_data, capacity, total);
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
+  csv_job* jobs = (csv_job*)malloc(sizeof(csv_job) * (size_t)nthreads);
+  const int64_t E = v->entry_offsets[S];
+  int64_t s0 = 0;
+  for (int t = 0; t < nthreads; ++t) {
+    int64_t s1 = s0;
+    const int64_t target = (int64_t)((double)E * (t + 1) / nthreads);
+    if (t == nthreads - 1) s1 = S;
+    else while (s1 < S && v->entry_offsets[s1] < target) s1++;
+    jobs[t] = (csv_job){v, s0, s1, NULL, {NULL, 0, 0}};
+    s0 = s1;
+  }
+  for (int t = 0; t < nthreads; ++t) pthread_create(&th[t], NULL, csv_worker, &jobs[t]);
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+  uint64_t base = 0;
+  for (int t = 0; t < nthreads; ++t) {
+    const uint64_t n = jobs[t].out.n;
+    jobs[t].row_offsets = row_offsets;
+    jobs[t].out = (csv_out){out_data, base, capacity}; /* p + n addressing: n starts at the range's base */
+    base += n;
+  }
+  *total = base;
+  row_offsets[v->n_entries] = (int64_t)base;
+  for (int t = 0; t < nthreads; ++t) pthread_create(&th[t], NULL, csv_worker, &jobs[t]);
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+  free(th);
+  free(jobs);
   return 0;
 }
 

@@ -7,12 +7,14 @@
 // by one '\n', so a show's CSV body is a single contiguous slice.
 //
 // ONE pass over the inputs.  A CTA takes a tile of kRowsPerTile consecutive entries:
-//   1. every thread measures its row (escaped length of 24 cells; Number::toString for delaySec)
+//   1. every thread measures its row: escaped length of the 24 cells (word-wise scan for the four
+//      characters that force quoting), Number::toString(delaySec) formatted once
 //   2. block scan -> tile total; decoupled look-back over the tile totals -> the tile's byte offset
 //   3. every thread writes its row into SHARED memory at the same 16-byte phase as the global
-//      destination; the tile is flushed with 16-byte coalesced stores
-// Rows of the tile that do not fit the shared buffer (very long free text) are written straight
-// to global memory by the same code.
+//      destination (word-wise copy through a byte-stream writer); the tile is flushed with 16-byte
+//      coalesced stores
+// Tiles whose rows do not fit the shared buffer (very long free text) are written straight to
+// global memory by the same code.
 #include "pie_device.cuh"
 #include "pie_kernels.h"
 #include "pie_numfmt.cuh"
@@ -23,7 +25,7 @@ __device__ const uint64_t d_pow5_inv[PIE_RYU_POW5_INV_SPLIT_N][2] = PIE_RYU_POW5
 __device__ const uint64_t d_pow5[PIE_RYU_POW5_SPLIT_N][2] = PIE_RYU_POW5_SPLIT_INIT;
 
 constexpr int kRowsPerTile = 128;
-constexpr int kTileBytes = 40 * 1024;  // shared staging buffer (rows of ~190 B -> ~24 KB per tile)
+constexpr int kTileBytes = 40 * 1024;  // shared staging buffer (rows of ~280 B -> ~35 KB per tile)
 
 constexpr unsigned long long kStatusShift = 62;
 constexpr unsigned long long kValueMask = (1ull << kStatusShift) - 1;
@@ -37,7 +39,9 @@ struct CsvScratch {
 };
 
 static inline uint64_t align256(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
-__host__ __device__ static inline int64_t csv_tiles(int64_t n_entries) { return (n_entries + kRowsPerTile - 1) / kRowsPerTile; }
+__host__ __device__ static inline int64_t csv_tiles(int64_t n_entries) {
+  return (n_entries + kRowsPerTile - 1) / kRowsPerTile;
+}
 
 uint64_t csv_scratch_bytes(int64_t n_entries) {
   const uint64_t e = (uint64_t)(n_entries > 0 ? n_entries : 1);
@@ -64,130 +68,263 @@ __global__ void __launch_bounds__(256) expand_entry_show_kernel(pie_archive_view
   for (int e = v.entry_offsets[s]; e < v.entry_offsets[s + 1]; ++e) entry_show[e] = (int32_t)s;
 }
 
-// ---- sinks: the row builder is written once and instantiated for measuring and for writing ----
-struct SizeSink {
-  uint32_t n = 0;
-  __device__ __forceinline__ void put(uint8_t) { n += 1; }
-  __device__ __forceinline__ void skip(uint32_t k) { n += k; }
-  static constexpr bool kMeasureOnly = true;
-};
-struct ByteSink {  // shared or global memory, byte granular
-  uint8_t* p;
-  __device__ __forceinline__ void put(uint8_t c) { *p++ = c; }
-  static constexpr bool kMeasureOnly = false;
+// ---- word-wise scanning and copying -----------------------------------------------------------
+// A cell is measured by scanning the ALIGNED 32-bit words it touches for the four characters that
+// force quoting (SIMD-in-register zero-byte test), and written by re-aligning those words with a
+// funnel shift into a byte-stream writer that emits aligned 32-bit stores.  Per-byte loops remain
+// only for cells that do need quoting (rare) and for the 0..3 bytes at the two ends of a row.
+
+// != 0 iff some byte of v is zero (exact as a boolean)
+__device__ __forceinline__ uint32_t zero_byte_flags(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
+
+__device__ __forceinline__ uint32_t special_flags(uint32_t x) {  // " , \n \r   (csvEscape, :334)
+  return zero_byte_flags(x ^ 0x22222222u) | zero_byte_flags(x ^ 0x2C2C2C2Cu) | zero_byte_flags(x ^ 0x0A0A0A0Au) |
+         zero_byte_flags(x ^ 0x0D0D0D0Du);
+}
+
+__device__ __forceinline__ bool has_special(const uint8_t* __restrict__ p, int n) {
+  if (n <= 0) return false;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  const uint32_t lead = static_cast<uint32_t>(a & 3);
+  const int nw = static_cast<int>((lead + n + 3) >> 2);  // aligned words that hold bytes of the cell
+  const uint32_t tail = (lead + n) & 3u;
+  uint32_t flags = 0;
+  for (int k = 0; k < nw; ++k) {
+    uint32_t x = __ldg(w + k);
+    if (k == 0) x &= 0xFFFFFFFFu << (8 * lead);             // bytes before the cell -> 0 (not special)
+    if (k == nw - 1 && tail) x &= (1u << (8 * tail)) - 1u;  // bytes after the cell  -> 0
+    flags |= special_flags(x);
+  }
+  return flags != 0;
+}
+
+__device__ __forceinline__ uint32_t count_quotes(const uint8_t* __restrict__ p, int n) {
+  uint32_t c = 0;
+  for (int i = 0; i < n; ++i) c += (p[i] == '"');
+  return c;
+}
+
+// Byte-stream writer: bytes are collected in a 64-bit accumulator and leave as aligned 32-bit stores.
+// The first word of a row may start mid-word (its low `lead` bytes belong to the previous row, which
+// another thread writes): that word and the last partial word are stored byte by byte.
+struct StreamWriter {
+  uint8_t* p;  // aligned address of the next word to store
+  unsigned long long acc;
+  uint32_t fill;  // bytes pending in acc (including `lead` placeholders before the first flush)
+  uint32_t lead;  // placeholder bytes of the first word; 0 once the first word has been stored
+
+  __device__ __forceinline__ void init(uint8_t* start) {
+    lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(start) & 3);
+    p = start - lead;
+    acc = 0;
+    fill = lead;
+  }
+  __device__ __forceinline__ void flush_word() {
+    const uint32_t v = static_cast<uint32_t>(acc);
+    if (lead) {
+      for (uint32_t b = lead; b < 4; ++b) p[b] = static_cast<uint8_t>(v >> (8 * b));
+      lead = 0;
+    } else {
+      *reinterpret_cast<uint32_t*>(p) = v;
+    }
+    p += 4;
+    acc >>= 32;
+    fill -= 4;
+  }
+  // k (1..4) low bytes of w; the other bytes of w must be zero
+  __device__ __forceinline__ void append(uint32_t w, uint32_t k) {
+    acc |= static_cast<unsigned long long>(w) << (8 * fill);
+    fill += k;
+    if (fill >= 4) flush_word();
+  }
+  __device__ __forceinline__ void put(uint8_t c) { append(c, 1); }
+  __device__ __forceinline__ void finish() {
+    for (uint32_t b = lead; b < fill; ++b) p[b] = static_cast<uint8_t>(acc >> (8 * b));
+  }
 };
 
-__device__ __forceinline__ bool csv_special(uint8_t c) { return c == '"' || c == ',' || c == '\n' || c == '\r'; }
+// copy s[0..n) (no quoting needed) followed by the separator byte
+__device__ __forceinline__ void copy_plain(StreamWriter& out, const uint8_t* __restrict__ s, int n, uint8_t sep) {
+  if (n > 0) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+    const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+    const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+    const int last = static_cast<int>(((a & 3) + n - 1) >> 2);  // last aligned word holding cell bytes
+    uint32_t cur = __ldg(w);
+    int k = 0;
+    for (; n >= 4; n -= 4, ++k) {  // full words of the cell
+      const uint32_t nxt = (k + 1 <= last) ? __ldg(w + k + 1) : 0u;
+      out.append(__funnelshift_r(cur, nxt, sh), 4);
+      cur = nxt;
+    }
+    if (n > 0) {  // 1..3 trailing bytes; the separator rides in the same word
+      const uint32_t nxt = (k + 1 <= last) ? __ldg(w + k + 1) : 0u;
+      const uint32_t x = __funnelshift_r(cur, nxt, sh) & ((1u << (8 * n)) - 1u);
+      out.append(x | (static_cast<uint32_t>(sep) << (8 * n)), static_cast<uint32_t>(n) + 1);
+      return;
+    }
+  }
+  out.put(sep);
+}
 
-// csvEscape(str) (:332-338): quote iff the string contains " , \n or \r; double the quotes.
-template <typename Sink>
-__device__ __forceinline__ void emit_cell(Sink& out, const uint8_t* __restrict__ s, int n) {
-  bool quote = false;
-  uint32_t dq = 0;
+// csvEscape of a cell that needs quotes (rare): byte-wise
+__device__ __forceinline__ void copy_quoted_bytes(StreamWriter& out, const uint8_t* __restrict__ s, int n) {
   for (int i = 0; i < n; ++i) {
     const uint8_t c = s[i];
-    quote |= csv_special(c);
-    dq += (c == '"');
-  }
-  if constexpr (Sink::kMeasureOnly) {
-    out.skip((uint32_t)n + (quote ? 2u + dq : 0u));
-  } else {
-    if (quote) out.put('"');
-    for (int i = 0; i < n; ++i) {
-      const uint8_t c = s[i];
-      if (quote && c == '"') out.put('"');
-      out.put(c);
-    }
-    if (quote) out.put('"');
+    if (c == '"') out.put('"');
+    out.put(c);
   }
 }
 
-template <typename Sink>
-__device__ __forceinline__ void emit_strcol(Sink& out, const pie_strcol& c, int64_t i) {
-  const int b = c.offsets[i], e = c.offsets[i + 1];
-  emit_cell(out, c.data + b, e - b);
+struct RowPlan {
+  uint32_t len;    // bytes of the row including the trailing '\n'
+  uint32_t quote;  // bit c: cell c (EXPORT_COLUMNS index) is wrapped in quotes; bit 31: status === 'Completed'
+};
+
+__device__ __forceinline__ void measure_cell(RowPlan& r, int col, const uint8_t* __restrict__ s, int n) {
+  if (has_special(s, n)) {
+    r.quote |= 1u << col;
+    r.len += 2u + count_quotes(s, n);
+  }
+  r.len += static_cast<uint32_t>(n);
 }
 
-// Array.prototype.join('|') then csvEscape of the joined string (crew :284, actions :298)
-template <typename Sink>
-__device__ __forceinline__ void emit_joined(Sink& out, const pie_strlistcol& c, int64_t i) {
-  const int l0 = c.list_offsets[i], l1 = c.list_offsets[i + 1];
-  if (l1 <= l0) return;
-  const int b = c.items.offsets[l0], e = c.items.offsets[l1];
-  const uint8_t* __restrict__ s = c.items.data;
-  bool quote = false;
-  uint32_t dq = 0;
-  for (int k = b; k < e; ++k) {
-    const uint8_t ch = s[k];
-    quote |= csv_special(ch);
-    dq += (ch == '"');
-  }
-  if constexpr (Sink::kMeasureOnly) {
-    out.skip((uint32_t)(e - b) + (uint32_t)(l1 - l0 - 1) + (quote ? 2u + dq : 0u));
+__device__ __forceinline__ void write_cell(StreamWriter& out, bool quote, const uint8_t* __restrict__ s, int n,
+                                           uint8_t sep) {
+  if (!quote) {
+    copy_plain(out, s, n, sep);
   } else {
-    if (quote) out.put('"');
-    for (int l = l0; l < l1; ++l) {
-      if (l > l0) out.put('|');
-      for (int k = c.items.offsets[l]; k < c.items.offsets[l + 1]; ++k) {
-        const uint8_t ch = s[k];
-        if (quote && ch == '"') out.put('"');
-        out.put(ch);
+    out.put('"');
+    copy_quoted_bytes(out, s, n);
+    out.put('"');
+    out.put(sep);
+  }
+}
+
+// entry.status === 'Completed' (strict, case-sensitive, :293-297) blanks the five issue cells
+__device__ __forceinline__ bool status_is_completed(const pie_archive_view& v, int64_t e) {
+  const int b = v.status.offsets[e], n = v.status.offsets[e + 1] - b;
+  if (n != 9) return false;
+  uint32_t x[3];
+  fetch_words_raw<3>(v.status.data + b, 9, x);
+  return x[0] == lit_word("Completed", 0) && x[1] == lit_word("Completed", 1) &&
+         (x[2] & 0xFFu) == lit_word("Completed", 2);
+}
+
+// The 24 cells of a row, in EXPORT_COLUMNS order (:15-19), as a table the kernels LOOP over: calling
+// 24 inlined cell handlers twice made a 30 000-instruction kernel that thrashed the instruction cache.
+enum : uint8_t { kCellString = 0, kCellJoined = 1, kCellNumber = 2 };
+struct CellDesc {
+  const int32_t* offsets;       // string column / items of a list column
+  const uint8_t* data;
+  const int32_t* list_offsets;  // kCellJoined only
+  uint8_t kind;
+  uint8_t per_entry;            // row index is the entry (1) or its show (0)
+  uint8_t blank_if_completed;   // :293-297
+};
+struct RowTable {
+  CellDesc cell[PIE_N_EXPORT_COLUMNS];
+};
+
+static RowTable make_row_table(const pie_archive_view& v) {
+  RowTable t;
+  auto str = [](const pie_strcol& c, int per_entry, int blank = 0) {
+    return CellDesc{c.offsets, c.data, nullptr, kCellString, (uint8_t)per_entry, (uint8_t)blank};
+  };
+  auto lst = [](const pie_strlistcol& c, int per_entry) {
+    return CellDesc{c.items.offsets, c.items.data, c.list_offsets, kCellJoined, (uint8_t)per_entry, 0};
+  };
+  t.cell[0] = str(v.show_id, 0);      t.cell[1] = str(v.show_date, 0);     t.cell[2] = str(v.show_time, 0);
+  t.cell[3] = str(v.show_label, 0);   t.cell[4] = lst(v.crew, 0);          t.cell[5] = str(v.lead_pilot, 0);
+  t.cell[6] = str(v.monkey_lead, 0);  t.cell[7] = str(v.show_notes, 0);    t.cell[8] = str(v.entry_id, 1);
+  t.cell[9] = str(v.unit_id, 1);      t.cell[10] = str(v.planned, 1);      t.cell[11] = str(v.launched, 1);
+  t.cell[12] = str(v.status, 1);      t.cell[13] = str(v.primary_issue, 1, 1);
+  t.cell[14] = str(v.sub_issue, 1, 1);  t.cell[15] = str(v.other_detail, 1, 1);
+  t.cell[16] = str(v.severity, 1, 1);   t.cell[17] = str(v.root_cause, 1, 1);
+  t.cell[18] = lst(v.actions, 1);     t.cell[19] = str(v.operator_name, 1); t.cell[20] = str(v.battery_id, 1);
+  t.cell[21] = CellDesc{nullptr, nullptr, nullptr, kCellNumber, 1, 0};
+  t.cell[22] = str(v.command_rx, 1);  t.cell[23] = str(v.notes, 1);
+  return t;
+}
+
+// Row = cells joined by ',' (:341), then '\n'.
+// num / num_len: Number::toString(delaySec), produced once here and reused by write_row.
+__device__ __forceinline__ RowPlan measure_row(const pie_archive_view& v, const RowTable& tab, int64_t e, int64_t s,
+                                               char* num, int* num_len) {
+  RowPlan r{24u, 0u};  // 23 commas + '\n'
+  const bool completed = status_is_completed(v, e);
+  if (completed) r.quote |= 1u << 31;  // remembered for write_row
+  *num_len = 0;
+#pragma unroll 1
+  for (int col = 0; col < PIE_N_EXPORT_COLUMNS; ++col) {
+    const CellDesc& d = tab.cell[col];
+    const int64_t i = d.per_entry ? e : s;
+    if (d.blank_if_completed && completed) continue;
+    if (d.kind == kCellString) {
+      const int b = d.offsets[i];
+      measure_cell(r, col, d.data + b, d.offsets[i + 1] - b);
+    } else if (d.kind == kCellJoined) {
+      const int l0 = d.list_offsets[i], l1 = d.list_offsets[i + 1];
+      if (l1 > l0) {
+        const int b = d.offsets[l0], n = d.offsets[l1] - b;
+        measure_cell(r, col, d.data + b, n);  // '|' is not special: quotes iff some item needs them
+        r.len += static_cast<uint32_t>(l1 - l0 - 1);
       }
+    } else if (v.delay_valid[e]) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
+      const RyuTables t{d_pow5_inv, d_pow5};
+      const int nl = js_number_to_string(v.delay_sec[e], num, t);
+      *num_len = nl;
+      r.len += static_cast<uint32_t>(nl);
     }
-    if (quote) out.put('"');
   }
+  return r;
 }
 
-// One CSV row: EXPORT_COLUMNS order (:15-19), cells joined by ',' (:341), then '\n'.
-template <typename Sink>
-__device__ __forceinline__ void emit_row(Sink& out, const pie_archive_view& v, int64_t e, int64_t s) {
-  emit_strcol(out, v.show_id, s);      out.put(',');
-  emit_strcol(out, v.show_date, s);    out.put(',');
-  emit_strcol(out, v.show_time, s);    out.put(',');
-  emit_strcol(out, v.show_label, s);   out.put(',');
-  emit_joined(out, v.crew, s);         out.put(',');
-  emit_strcol(out, v.lead_pilot, s);   out.put(',');
-  emit_strcol(out, v.monkey_lead, s);  out.put(',');
-  emit_strcol(out, v.show_notes, s);   out.put(',');
-  emit_strcol(out, v.entry_id, e);     out.put(',');
-  emit_strcol(out, v.unit_id, e);      out.put(',');
-  emit_strcol(out, v.planned, e);      out.put(',');
-  emit_strcol(out, v.launched, e);     out.put(',');
-  emit_strcol(out, v.status, e);       out.put(',');
-  // entry.status === 'Completed' (strict, case-sensitive, :293-297) blanks the five issue cells
-  const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
-  const bool completed = equals_exact(v.status.data + sb, sn, "Completed");
-  if (!completed) emit_strcol(out, v.primary_issue, e);
-  out.put(',');
-  if (!completed) emit_strcol(out, v.sub_issue, e);
-  out.put(',');
-  if (!completed) emit_strcol(out, v.other_detail, e);
-  out.put(',');
-  if (!completed) emit_strcol(out, v.severity, e);
-  out.put(',');
-  if (!completed) emit_strcol(out, v.root_cause, e);
-  out.put(',');
-  emit_joined(out, v.actions, e);      out.put(',');
-  emit_strcol(out, v.operator_name, e); out.put(',');
-  emit_strcol(out, v.battery_id, e);   out.put(',');
-  if (v.delay_valid[e]) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
-    char buf[kMaxNumberChars];
-    const RyuTables t{d_pow5_inv, d_pow5};
-    const int n = js_number_to_string(v.delay_sec[e], buf, t);
-    if constexpr (Sink::kMeasureOnly) out.skip((uint32_t)n);
-    else for (int i = 0; i < n; ++i) out.put((uint8_t)buf[i]);
+__device__ __forceinline__ void write_row(StreamWriter& out, const RowTable& tab, int64_t e, int64_t s, uint32_t q,
+                                          const char* num, int num_len) {
+  const bool completed = (q >> 31) != 0;
+#pragma unroll 1
+  for (int col = 0; col < PIE_N_EXPORT_COLUMNS; ++col) {
+    const CellDesc& d = tab.cell[col];
+    const int64_t i = d.per_entry ? e : s;
+    const uint8_t sep = (col == PIE_N_EXPORT_COLUMNS - 1) ? (uint8_t)'\n' : (uint8_t)',';
+    const bool quote = (q >> col) & 1u;
+    if (d.blank_if_completed && completed) {
+      out.put(sep);
+    } else if (d.kind == kCellString) {
+      const int b = d.offsets[i];
+      write_cell(out, quote, d.data + b, d.offsets[i + 1] - b, sep);
+    } else if (d.kind == kCellJoined) {
+      const int l0 = d.list_offsets[i], l1 = d.list_offsets[i + 1];
+      if (quote) out.put('"');
+      for (int l = l0; l < l1; ++l) {
+        const int b = d.offsets[l], n = d.offsets[l + 1] - b;
+        const bool last_item = (l + 1 == l1);
+        if (quote) {
+          copy_quoted_bytes(out, d.data + b, n);
+          if (!last_item) out.put('|');
+        } else {
+          copy_plain(out, d.data + b, n, last_item ? sep : (uint8_t)'|');
+        }
+      }
+      if (quote) out.put('"');
+      if (quote || l1 <= l0) out.put(sep);
+    } else {
+      for (int k = 0; k < num_len; ++k) out.put(static_cast<uint8_t>(num[k]));
+      out.put(sep);
+    }
   }
-  out.put(',');
-  emit_strcol(out, v.command_rx, e);   out.put(',');
-  emit_strcol(out, v.notes, e);
-  out.put('\n');
+  out.finish();
 }
 
-__global__ void __launch_bounds__(kRowsPerTile) csv_rows_kernel(pie_archive_view v, CsvScratch sc,
+__global__ void __launch_bounds__(kRowsPerTile) csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab,
+                                                                CsvScratch sc,
                                                                 int64_t* __restrict__ row_offsets,
                                                                 uint8_t* __restrict__ out_data, uint64_t capacity,
                                                                 unsigned long long* __restrict__ total_out) {
   extern __shared__ __align__(16) uint8_t s_tile[];  // kTileBytes + 16
+  __shared__ char s_num[kRowsPerTile][kMaxNumberChars];
   __shared__ uint32_t s_warp[kRowsPerTile / 32];
   __shared__ unsigned int s_tile_id;
   __shared__ unsigned long long s_base;
@@ -200,12 +337,13 @@ __global__ void __launch_bounds__(kRowsPerTile) csv_rows_kernel(pie_archive_view
   const bool have = e < v.n_entries;
   const int64_t s = have ? sc.entry_show[e] : 0;
 
-  // 1. measure
-  uint32_t len = 0;
+  // 1. measure (and format delaySec once)
+  uint32_t len = 0, qmask = 0;
+  int num_len = 0;
   if (have) {
-    SizeSink sz;
-    emit_row(sz, v, e, s);
-    len = sz.n;
+    const RowPlan plan = measure_row(v, tab, e, s, s_num[tid], &num_len);
+    len = plan.len;
+    qmask = plan.quote;
   }
   // 2. block exclusive scan of the row lengths
   uint32_t incl = len;
@@ -270,8 +408,9 @@ __global__ void __launch_bounds__(kRowsPerTile) csv_rows_kernel(pie_archive_view
   const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(out_data) + base) & 15);
   const bool staged = (pad + tile_total) <= (uint32_t)kTileBytes + 16u;
   if (have) {
-    ByteSink w{staged ? (s_tile + pad + local) : (out_data + base + local)};
-    emit_row(w, v, e, s);
+    StreamWriter w;
+    w.init(staged ? (s_tile + pad + local) : (out_data + base + local));
+    write_row(w, tab, e, s, qmask, s_num[tid], num_len);
   }
   if (!staged) return;
   __syncthreads();
@@ -309,7 +448,7 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
   }
   expand_entry_show_kernel<<<(unsigned)((v.n_shows + 255) / 256), 256, 0, stream>>>(v, sc.entry_show);
   csv_rows_kernel<<<(unsigned)csv_tiles(v.n_entries), kRowsPerTile, kTileBytes + 16, stream>>>(
-      v, sc, row_offsets, out_data, capacity, total_out);
+      v, make_row_table(v), sc, row_offsets, out_data, capacity, total_out);
   g_launches += 2;
   return cudaGetLastError();
 }
