@@ -6,15 +6,21 @@
 // Output = one string column: row i is out_data[row_offsets[i] .. row_offsets[i+1]-1) and is followed
 // by one '\n', so a show's CSV body is a single contiguous slice.
 //
-// ONE pass over the inputs.  A CTA takes a tile of kRowsPerTile consecutive entries:
-//   1. every thread measures its row: escaped length of the 24 cells (word-wise scan for the four
-//      characters that force quoting), Number::toString(delaySec) formatted once
-//   2. block scan -> tile total; decoupled look-back over the tile totals -> the tile's byte offset
-//   3. every thread writes its row into SHARED memory at the same 16-byte phase as the global
-//      destination (word-wise copy through a byte-stream writer); the tile is flushed with 16-byte
-//      coalesced stores
-// Tiles whose rows do not fit the shared buffer (very long free text) are written straight to
-// global memory by the same code.
+// ONE pass over the inputs.  A CTA takes a tile of kRows consecutive entries = 24 x
+// kRows CELLS, and works cell-parallel, column-major: a warp handles ONE column for 32 consecutive
+// rows, so its offset loads are coalesced, its cell lengths are alike (no divergence), and every
+// thread has independent loads in flight (a thread per row walked 24 dependent cells serially).
+//   1. measure  every cell: escaped length (word-wise scan for the characters that force quotes);
+//               Number::toString(delaySec) is formatted once into shared memory
+//   2. scan     per row over its 24 cells (shared memory), block scan over the rows -> tile total;
+//               the tile's aggregate is published for the decoupled look-back
+//   3. write    every cell into the SHARED tile buffer through a byte-stream writer (aligned
+//               32-bit stores; only the 0..3 bytes at a cell's two ends are byte stores)
+//   4. look-back over the tile totals -> the tile's global byte offset (overlaps 3 in other CTAs)
+//   5. flush    16-byte coalesced stores; the shared buffer is re-aligned to the destination with a
+//               funnel shift, so step 3 does not have to wait for the offset
+// A tile that does not fit the shared buffer (very long free text) is written straight to global
+// memory by the same cell code, after its look-back.
 #include "pie_device.cuh"
 #include "pie_kernels.h"
 #include "pie_numfmt.cuh"
@@ -24,8 +30,21 @@ namespace pie {
 __device__ const uint64_t d_pow5_inv[PIE_RYU_POW5_INV_SPLIT_N][2] = PIE_RYU_POW5_INV_SPLIT_INIT;
 __device__ const uint64_t d_pow5[PIE_RYU_POW5_SPLIT_N][2] = PIE_RYU_POW5_SPLIT_INIT;
 
-constexpr int kRowsPerTile = 128;
-constexpr int kTileBytes = 40 * 1024;  // shared staging buffer (rows of ~280 B -> ~35 KB per tile)
+#ifndef PIE_CSV_ROWS
+#define PIE_CSV_ROWS 128
+#endif
+#ifndef PIE_CSV_THREADS
+#define PIE_CSV_THREADS 512
+#endif
+#ifndef PIE_CSV_TILE_KB
+#define PIE_CSV_TILE_KB 48
+#endif
+constexpr int kRows = PIE_CSV_ROWS;                 // rows (entries) per tile; multiple of 32
+constexpr int kThreads = PIE_CSV_THREADS;           // multiple of kRows
+constexpr int kCols = PIE_N_EXPORT_COLUMNS;         // 24
+constexpr int kCells = kRows * kCols;
+constexpr int kTileBytes = PIE_CSV_TILE_KB * 1024;  // shared tile buffer (rows of ~280 B -> ~36 KB per 128 rows)
+static_assert(kRows % 32 == 0 && kThreads % kRows == 0 && kCells % kThreads == 0, "tile shape");
 
 constexpr unsigned long long kStatusShift = 62;
 constexpr unsigned long long kValueMask = (1ull << kStatusShift) - 1;
@@ -39,9 +58,7 @@ struct CsvScratch {
 };
 
 static inline uint64_t align256(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
-__host__ __device__ static inline int64_t csv_tiles(int64_t n_entries) {
-  return (n_entries + kRowsPerTile - 1) / kRowsPerTile;
-}
+__host__ __device__ static inline int64_t csv_tiles(int64_t n_entries) { return (n_entries + kRows - 1) / kRows; }
 
 uint64_t csv_scratch_bytes(int64_t n_entries) {
   const uint64_t e = (uint64_t)(n_entries > 0 ? n_entries : 1);
@@ -69,11 +86,6 @@ __global__ void __launch_bounds__(256) expand_entry_show_kernel(pie_archive_view
 }
 
 // ---- word-wise scanning and copying -----------------------------------------------------------
-// A cell is measured by scanning the ALIGNED 32-bit words it touches for the four characters that
-// force quoting (SIMD-in-register zero-byte test), and written by re-aligning those words with a
-// funnel shift into a byte-stream writer that emits aligned 32-bit stores.  Per-byte loops remain
-// only for cells that do need quoting (rare) and for the 0..3 bytes at the two ends of a row.
-
 // != 0 iff some byte of v is zero (exact as a boolean)
 __device__ __forceinline__ uint32_t zero_byte_flags(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
 
@@ -82,6 +94,7 @@ __device__ __forceinline__ uint32_t special_flags(uint32_t x) {  // " , \n \r   
          zero_byte_flags(x ^ 0x0D0D0D0Du);
 }
 
+// does s[0..n) contain a character that forces quoting?  Scans the ALIGNED words the cell touches.
 __device__ __forceinline__ bool has_special(const uint8_t* __restrict__ p, int n) {
   if (n <= 0) return false;
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -99,15 +112,27 @@ __device__ __forceinline__ bool has_special(const uint8_t* __restrict__ p, int n
   return flags != 0;
 }
 
+// number of '"' in s[0..n), four bytes at a time over the aligned words the cell touches
 __device__ __forceinline__ uint32_t count_quotes(const uint8_t* __restrict__ p, int n) {
+  if (n <= 0) return 0;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  const uint32_t lead = static_cast<uint32_t>(a & 3);
+  const int nw = static_cast<int>((lead + n + 3) >> 2);
+  const uint32_t tail = (lead + n) & 3u;
   uint32_t c = 0;
-  for (int i = 0; i < n; ++i) c += (p[i] == '"');
+  for (int k = 0; k < nw; ++k) {
+    uint32_t x = __ldg(w + k);
+    if (k == 0) x &= 0xFFFFFFFFu << (8 * lead);
+    if (k == nw - 1 && tail) x &= (1u << (8 * tail)) - 1u;
+    c += __popc(__vcmpeq4(x, 0x22222222u)) >> 3;  // 0xFF per byte equal to '"'
+  }
   return c;
 }
 
 // Byte-stream writer: bytes are collected in a 64-bit accumulator and leave as aligned 32-bit stores.
-// The first word of a row may start mid-word (its low `lead` bytes belong to the previous row, which
-// another thread writes): that word and the last partial word are stored byte by byte.
+// A cell may start and end mid-word; the neighbouring bytes of those words belong to other cells,
+// which other threads write, so the first and the last partial word are stored byte by byte.
 struct StreamWriter {
   uint8_t* p;  // aligned address of the next word to store
   unsigned long long acc;
@@ -170,35 +195,27 @@ __device__ __forceinline__ void copy_plain(StreamWriter& out, const uint8_t* __r
 
 // csvEscape of a cell that needs quotes (rare): byte-wise
 __device__ __forceinline__ void copy_quoted_bytes(StreamWriter& out, const uint8_t* __restrict__ s, int n) {
-  for (int i = 0; i < n; ++i) {
-    const uint8_t c = s[i];
-    if (c == '"') out.put('"');
-    out.put(c);
-  }
-}
-
-struct RowPlan {
-  uint32_t len;    // bytes of the row including the trailing '\n'
-  uint32_t quote;  // bit c: cell c (EXPORT_COLUMNS index) is wrapped in quotes; bit 31: status === 'Completed'
-};
-
-__device__ __forceinline__ void measure_cell(RowPlan& r, int col, const uint8_t* __restrict__ s, int n) {
-  if (has_special(s, n)) {
-    r.quote |= 1u << col;
-    r.len += 2u + count_quotes(s, n);
-  }
-  r.len += static_cast<uint32_t>(n);
-}
-
-__device__ __forceinline__ void write_cell(StreamWriter& out, bool quote, const uint8_t* __restrict__ s, int n,
-                                           uint8_t sep) {
-  if (!quote) {
-    copy_plain(out, s, n, sep);
-  } else {
-    out.put('"');
-    copy_quoted_bytes(out, s, n);
-    out.put('"');
-    out.put(sep);
+  if (n <= 0) return;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
+  const int last = static_cast<int>(((a & 3) + n - 1) >> 2);
+  uint32_t cur = __ldg(w);
+  for (int k = 0; n > 0; n -= 4, ++k) {
+    const uint32_t nxt = (k + 1 <= last) ? __ldg(w + k + 1) : 0u;
+    const uint32_t m = n >= 4 ? 4u : static_cast<uint32_t>(n);
+    uint32_t x = __funnelshift_r(cur, nxt, sh);
+    if (m < 4) x &= (1u << (8 * m)) - 1u;
+    cur = nxt;
+    if (zero_byte_flags(x ^ 0x22222222u) == 0) {  // no '"' in these bytes: whole word at once
+      out.append(x, m);
+    } else {
+      for (uint32_t b = 0; b < m; ++b) {
+        const uint8_t c = static_cast<uint8_t>(x >> (8 * b));
+        if (c == '"') out.put('"');
+        out.put(c);
+      }
+    }
   }
 }
 
@@ -212,8 +229,7 @@ __device__ __forceinline__ bool status_is_completed(const pie_archive_view& v, i
          (x[2] & 0xFFu) == lit_word("Completed", 2);
 }
 
-// The 24 cells of a row, in EXPORT_COLUMNS order (:15-19), as a table the kernels LOOP over: calling
-// 24 inlined cell handlers twice made a 30 000-instruction kernel that thrashed the instruction cache.
+// The 24 cells of a row, in EXPORT_COLUMNS order (:15-19)
 enum : uint8_t { kCellString = 0, kCellJoined = 1, kCellNumber = 2 };
 struct CellDesc {
   const int32_t* offsets;       // string column / items of a list column
@@ -224,7 +240,7 @@ struct CellDesc {
   uint8_t blank_if_completed;   // :293-297
 };
 struct RowTable {
-  CellDesc cell[PIE_N_EXPORT_COLUMNS];
+  CellDesc cell[kCols];
 };
 
 static RowTable make_row_table(const pie_archive_view& v) {
@@ -248,184 +264,255 @@ static RowTable make_row_table(const pie_archive_view& v) {
   return t;
 }
 
-// Row = cells joined by ',' (:341), then '\n'.
-// num / num_len: Number::toString(delaySec), produced once here and reused by write_row.
-__device__ __forceinline__ RowPlan measure_row(const pie_archive_view& v, const RowTable& tab, int64_t e, int64_t s,
-                                               char* num, int* num_len) {
-  RowPlan r{24u, 0u};  // 23 commas + '\n'
-  const bool completed = status_is_completed(v, e);
-  if (completed) r.quote |= 1u << 31;  // remembered for write_row
-  *num_len = 0;
-#pragma unroll 1
-  for (int col = 0; col < PIE_N_EXPORT_COLUMNS; ++col) {
-    const CellDesc& d = tab.cell[col];
-    const int64_t i = d.per_entry ? e : s;
-    if (d.blank_if_completed && completed) continue;
-    if (d.kind == kCellString) {
-      const int b = d.offsets[i];
-      measure_cell(r, col, d.data + b, d.offsets[i + 1] - b);
-    } else if (d.kind == kCellJoined) {
-      const int l0 = d.list_offsets[i], l1 = d.list_offsets[i + 1];
-      if (l1 > l0) {
-        const int b = d.offsets[l0], n = d.offsets[l1] - b;
-        measure_cell(r, col, d.data + b, n);  // '|' is not special: quotes iff some item needs them
-        r.len += static_cast<uint32_t>(l1 - l0 - 1);
-      }
-    } else if (v.delay_valid[e]) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
-      const RyuTables t{d_pow5_inv, d_pow5};
-      const int nl = js_number_to_string(v.delay_sec[e], num, t);
-      *num_len = nl;
-      r.len += static_cast<uint32_t>(nl);
+// Source bytes of one cell: [data + b, data + b + n); for a joined list the items are contiguous in
+// the item heap and `items` = l1 - l0.  blank = the reference writes '' for this cell.
+struct CellSrc {
+  int b, n, l0, l1;
+  bool blank;
+};
+
+__device__ __forceinline__ CellSrc locate_cell(const pie_archive_view& v, const CellDesc& d, int64_t e, int64_t s) {
+  CellSrc c{0, 0, 0, 0, false};
+  const int64_t i = d.per_entry ? e : s;
+  if (d.blank_if_completed && status_is_completed(v, e)) {
+    c.blank = true;
+  } else if (d.kind == kCellString) {
+    c.b = d.offsets[i];
+    c.n = d.offsets[i + 1] - c.b;
+  } else if (d.kind == kCellJoined) {
+    c.l0 = d.list_offsets[i];
+    c.l1 = d.list_offsets[i + 1];
+    if (c.l1 > c.l0) {
+      c.b = d.offsets[c.l0];
+      c.n = d.offsets[c.l1] - c.b;
     }
   }
-  return r;
+  return c;
 }
 
-__device__ __forceinline__ void write_row(StreamWriter& out, const RowTable& tab, int64_t e, int64_t s, uint32_t q,
-                                          const char* num, int num_len) {
-  const bool completed = (q >> 31) != 0;
-#pragma unroll 1
-  for (int col = 0; col < PIE_N_EXPORT_COLUMNS; ++col) {
-    const CellDesc& d = tab.cell[col];
-    const int64_t i = d.per_entry ? e : s;
-    const uint8_t sep = (col == PIE_N_EXPORT_COLUMNS - 1) ? (uint8_t)'\n' : (uint8_t)',';
-    const bool quote = (q >> col) & 1u;
-    if (d.blank_if_completed && completed) {
-      out.put(sep);
-    } else if (d.kind == kCellString) {
-      const int b = d.offsets[i];
-      write_cell(out, quote, d.data + b, d.offsets[i + 1] - b, sep);
-    } else if (d.kind == kCellJoined) {
-      const int l0 = d.list_offsets[i], l1 = d.list_offsets[i + 1];
-      if (quote) out.put('"');
-      for (int l = l0; l < l1; ++l) {
-        const int b = d.offsets[l], n = d.offsets[l + 1] - b;
-        const bool last_item = (l + 1 == l1);
-        if (quote) {
-          copy_quoted_bytes(out, d.data + b, n);
-          if (!last_item) out.put('|');
-        } else {
-          copy_plain(out, d.data + b, n, last_item ? sep : (uint8_t)'|');
-        }
-      }
-      if (quote) out.put('"');
-      if (quote || l1 <= l0) out.put(sep);
-    } else {
-      for (int k = 0; k < num_len; ++k) out.put(static_cast<uint8_t>(num[k]));
-      out.put(sep);
-    }
-  }
-  out.finish();
-}
+constexpr uint32_t kQuoteBit = 0x80000000u;
 
-__global__ void __launch_bounds__(kRowsPerTile) csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab,
-                                                                CsvScratch sc,
-                                                                int64_t* __restrict__ row_offsets,
-                                                                uint8_t* __restrict__ out_data, uint64_t capacity,
-                                                                unsigned long long* __restrict__ total_out) {
-  extern __shared__ __align__(16) uint8_t s_tile[];  // kTileBytes + 16
-  __shared__ char s_num[kRowsPerTile][kMaxNumberChars];
-  __shared__ uint32_t s_warp[kRowsPerTile / 32];
-  __shared__ unsigned int s_tile_id;
-  __shared__ unsigned long long s_base;
+struct CsvSmem {
+  uint32_t cell[kCols][kRows];  // step 1: escaped length | kQuoteBit; step 2: start offset in the row | kQuoteBit
+  uint32_t row_start[kRows];    // byte offset of the row inside the tile
+  char num[kRows][kMaxNumberChars];
+  uint8_t num_len[kRows];
+  uint32_t warp_sum[kRows / 32];
+  uint32_t tile_total;
+  unsigned int tile_id;
+  unsigned long long base;
+};
+
+__global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab,
+                                                            CsvScratch sc, int64_t* __restrict__ row_offsets,
+                                                            uint8_t* __restrict__ out_data, uint64_t capacity,
+                                                            unsigned long long* __restrict__ total_out) {
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  uint8_t* s_tile = s_dyn;                                               // kTileBytes + 32
+  CsvSmem& sm = *reinterpret_cast<CsvSmem*>(s_dyn + kTileBytes + 32);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-  if (tid == 0) s_tile_id = atomicAdd(sc.tile_counter, 1u);  // tiles start in id order: look-back cannot deadlock
+  if (tid == 0) sm.tile_id = atomicAdd(sc.tile_counter, 1u);  // tiles start in id order: look-back cannot deadlock
   __syncthreads();
-  const int64_t tile = s_tile_id;
-  const int64_t e = tile * kRowsPerTile + tid;
-  const bool have = e < v.n_entries;
-  const int64_t s = have ? sc.entry_show[e] : 0;
+  const int64_t tile = sm.tile_id;
+  const int64_t e0 = tile * kRows;
+  const int rows = (v.n_entries - e0 < kRows) ? (int)(v.n_entries - e0) : kRows;
 
-  // 1. measure (and format delaySec once)
-  uint32_t len = 0, qmask = 0;
-  int num_len = 0;
-  if (have) {
-    const RowPlan plan = measure_row(v, tab, e, s, s_num[tid], &num_len);
-    len = plan.len;
-    qmask = plan.quote;
+  // ---- 1. measure every cell (cell q: column q / kRows, row q % kRows -> a warp = one column)
+#pragma unroll 1  // one generic body: unrolled, the compiler specialises it per column (15k instructions)
+  for (int q = tid; q < kCells; q += kThreads) {
+    const int col = q / kRows, r = q % kRows;
+    uint32_t len = 0;
+    if (r < rows) {
+      const int64_t e = e0 + r;
+      const CellDesc& d = tab.cell[col];
+      if (d.kind == kCellNumber) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
+        int nl = 0;
+        if (v.delay_valid[e]) {
+          const RyuTables t{d_pow5_inv, d_pow5};
+          nl = js_number_to_string(v.delay_sec[e], sm.num[r], t);
+        }
+        sm.num_len[r] = (uint8_t)nl;
+        len = (uint32_t)nl;
+      } else {
+        const CellSrc c = locate_cell(v, d, e, d.per_entry ? 0 : sc.entry_show[e]);
+        if (c.n > 0) {
+          len = (uint32_t)c.n;
+          if (has_special(d.data + c.b, c.n)) len = (len + 2u + count_quotes(d.data + c.b, c.n)) | kQuoteBit;
+        }
+        if (c.l1 > c.l0) len += (uint32_t)(c.l1 - c.l0 - 1);  // '|' between items (not special)
+      }
+    }
+    sm.cell[col][r] = len;
   }
-  // 2. block exclusive scan of the row lengths
-  uint32_t incl = len;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_warp[wid] = incl;
   __syncthreads();
-  uint32_t warp_base = 0, tile_total = 0;
-#pragma unroll
-  for (int w = 0; w < kRowsPerTile / 32; ++w) {
-    if (w < wid) warp_base += s_warp[w];
-    tile_total += s_warp[w];
-  }
-  const uint32_t local = warp_base + incl - len;  // byte offset of this row inside the tile
 
-  // decoupled look-back over the tile totals (warp 0)
-  if (wid == 0) {
-    volatile unsigned long long* state = sc.tile_state;
-    if (lane == 0) {
+  // ---- 2. per-row scan over the 24 cells, then block scan over the rows
+  uint32_t row_len = 0;
+  if (tid < kRows) {
+    if (tid < rows) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int col = 0; col < kCols; ++col) {
+        const uint32_t x = sm.cell[col][tid];
+        sm.cell[col][tid] = run | (x & kQuoteBit);
+        run += (x & ~kQuoteBit) + 1u;  // + ',' (or the final '\n')
+      }
+      row_len = run;
+    }
+    uint32_t incl = row_len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm.warp_sum[wid] = incl;
+    sm.row_start[tid] = incl - row_len;  // completed below with the preceding warps' sums
+  }
+  __syncthreads();
+  if (tid < kRows) {
+    uint32_t before = 0;
+    for (int w = 0; w < wid; ++w) before += sm.warp_sum[w];
+    sm.row_start[tid] += before;
+    if (tid == kRows - 1) {
+      const uint32_t total = sm.row_start[tid] + row_len;
+      sm.tile_total = total;
       __threadfence();
-      state[tile] = (tile == 0 ? kPrefix : kAggregate) | (unsigned long long)tile_total;
-    }
-    unsigned long long exclusive = 0;
-    int64_t idx = tile - 1;
-    while (idx >= 0) {
-      const int64_t j = idx - lane;
-      unsigned long long st;
-      do {
-        st = 2ull << kStatusShift;  // before tile 0: an empty prefix
-        if (j >= 0) st = state[j];
-      } while (__any_sync(0xFFFFFFFFu, (st >> kStatusShift) == 0));
-      const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (st >> kStatusShift) == 2);
-      const int stop = is_prefix ? (__ffs(is_prefix) - 1) : 32;  // nearest tile that already knows its prefix
-      unsigned long long part = (lane <= stop) ? (st & kValueMask) : 0ull;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-      exclusive += part;
-      if (is_prefix) break;
-      idx -= 32;
-    }
-    if (lane == 0) {
-      if (tile > 0) {
-        __threadfence();
-        state[tile] = kPrefix | (exclusive + tile_total);
-      }
-      s_base = exclusive;
-      if (tile == csv_tiles(v.n_entries) - 1) {
-        *total_out = exclusive + tile_total;
-        row_offsets[v.n_entries] = (int64_t)(exclusive + tile_total);
-      }
+      reinterpret_cast<volatile unsigned long long*>(sc.tile_state)[tile] =
+          (tile == 0 ? kPrefix : kAggregate) | (unsigned long long)total;  // published for later tiles
     }
   }
   __syncthreads();
-  const unsigned long long base = s_base;
-  if (have) row_offsets[e] = (int64_t)(base + local);
-  if (out_data == nullptr || base + tile_total > capacity) return;  // size-only call, or caller's buffer too small
+  const uint32_t tile_total = sm.tile_total;
+  const bool write = out_data != nullptr;
+  const bool staged = tile_total <= (uint32_t)kTileBytes;
 
-  // 3. write the rows
-  const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(out_data) + base) & 15);
-  const bool staged = (pad + tile_total) <= (uint32_t)kTileBytes + 16u;
-  if (have) {
-    StreamWriter w;
-    w.init(staged ? (s_tile + pad + local) : (out_data + base + local));
-    write_row(w, tab, e, s, qmask, s_num[tid], num_len);
+  // ---- 4. decoupled look-back, by warp 0 — WHILE warps 1.. write the cells of a staged tile (step 3
+  // does not need the offset); before step 3 when the tile must be written to global memory directly.
+  auto look_back_warp0 = [&]() {
+    {
+      volatile unsigned long long* state = sc.tile_state;
+      unsigned long long exclusive = 0;
+      int64_t idx = tile - 1;
+      while (idx >= 0) {
+        const int64_t j = idx - lane;
+        unsigned long long st;
+        do {
+          st = 2ull << kStatusShift;  // before tile 0: an empty prefix
+          if (j >= 0) st = state[j];
+        } while (__any_sync(0xFFFFFFFFu, (st >> kStatusShift) == 0));
+        const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (st >> kStatusShift) == 2);
+        const int stop = is_prefix ? (__ffs(is_prefix) - 1) : 32;  // nearest tile that already knows its prefix
+        unsigned long long part = (lane <= stop) ? (st & kValueMask) : 0ull;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+        exclusive += part;
+        if (is_prefix) break;
+        idx -= 32;
+      }
+      if (lane == 0) {
+        if (tile > 0) {
+          __threadfence();
+          state[tile] = kPrefix | (exclusive + tile_total);
+        }
+        sm.base = exclusive;
+        if (tile == csv_tiles(v.n_entries) - 1) {
+          *total_out = exclusive + tile_total;
+          row_offsets[v.n_entries] = (int64_t)(exclusive + tile_total);
+        }
+      }
+    }
+  };
+  const bool overlap = write && staged;  // warp 0 looks back while the other warps write
+  if (!overlap) {
+    if (wid == 0) look_back_warp0();
+    __syncthreads();
   }
-  if (!staged) return;
-  __syncthreads();
-  // flush s_tile[pad .. pad+tile_total) -> out_data[base ..): smem and global share the 16-byte phase
-  uint8_t* __restrict__ dst = out_data + base - pad;  // dst + k <-> s_tile + k
-  const uint32_t end = pad + tile_total;
-  const uint32_t body_begin = pad ? 16u : 0u, body_end = end & ~15u;
-  if (body_end > body_begin) {
-    for (uint32_t k = body_begin + 16u * tid; k < body_end; k += 16u * kRowsPerTile)
-      *reinterpret_cast<uint4*>(dst + k) = *reinterpret_cast<const uint4*>(s_tile + k);
-    for (uint32_t k = pad + tid; k < body_begin && k < end; k += kRowsPerTile) dst[k] = s_tile[k];
-    for (uint32_t k = body_end + tid; k < end; k += kRowsPerTile) dst[k] = s_tile[k];
-  } else {
-    for (uint32_t k = pad + tid; k < end; k += kRowsPerTile) dst[k] = s_tile[k];
+  if (!write) {
+    if (tid < rows) row_offsets[e0 + tid] = (int64_t)(sm.base + sm.row_start[tid]);
+    return;
   }
+  const bool fits = staged || (sm.base + tile_total <= capacity);  // direct writes must respect the caller's capacity
+
+  // ---- 3. write every cell
+  if (overlap && wid == 0) {
+    look_back_warp0();
+  } else if (fits) {
+    uint8_t* const dst0 = staged ? s_tile : (out_data + sm.base);
+    const int q0 = overlap ? tid - 32 : tid, qstride = overlap ? kThreads - 32 : kThreads;
+#pragma unroll 1
+    for (int q = q0; q < kCells; q += qstride) {
+      const int col = q / kRows, r = q % kRows;
+      if (r >= rows) continue;
+      const int64_t e = e0 + r;
+      const CellDesc& d = tab.cell[col];
+      const uint32_t x = sm.cell[col][r];
+      const bool quote = (x & kQuoteBit) != 0;
+      const uint8_t sep = (col == kCols - 1) ? (uint8_t)'\n' : (uint8_t)',';
+      StreamWriter out;
+      out.init(dst0 + sm.row_start[r] + (x & ~kQuoteBit));
+      if (d.kind == kCellNumber) {
+        const int nl = sm.num_len[r];
+        for (int k = 0; k < nl; ++k) out.put((uint8_t)sm.num[r][k]);
+        out.put(sep);
+      } else {
+        const CellSrc c = locate_cell(v, d, e, d.per_entry ? 0 : sc.entry_show[e]);
+        if (d.kind == kCellString || c.l1 <= c.l0) {
+          if (!quote) {
+            copy_plain(out, d.data + c.b, c.n, sep);
+          } else {
+            out.put('"');
+            copy_quoted_bytes(out, d.data + c.b, c.n);
+            out.put('"');
+            out.put(sep);
+          }
+        } else {  // Array.prototype.join('|') then csvEscape of the joined string (crew :284, actions :298)
+          if (quote) out.put('"');
+          for (int l = c.l0; l < c.l1; ++l) {
+            const int b = d.offsets[l], n = d.offsets[l + 1] - b;
+            const bool last_item = (l + 1 == c.l1);
+            if (quote) {
+              copy_quoted_bytes(out, d.data + b, n);
+              if (!last_item) out.put('|');
+            } else {
+              copy_plain(out, d.data + b, n, last_item ? sep : (uint8_t)'|');
+            }
+          }
+          if (quote) {
+            out.put('"');
+            out.put(sep);
+          }
+        }
+      }
+      out.finish();
+    }
+  }
+  if (staged) __syncthreads();  // the tile is complete in shared memory and its offset is known
+  const unsigned long long base = sm.base;
+  if (tid < rows) row_offsets[e0 + tid] = (int64_t)(base + sm.row_start[tid]);
+  if (!staged || base + tile_total > capacity) return;
+
+  // ---- 5. flush s_tile[0 .. tile_total) -> out_data[base ..) with 16-byte stores.  Global chunk k
+  // starts at the first 16-byte boundary >= out_data+base, i.e. at tile offset head + 16k, which has
+  // an arbitrary phase in shared memory: read 5 aligned words and funnel-shift.
+  uint8_t* __restrict__ dst = out_data + base;
+  const uint32_t head_raw = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
+  const uint32_t head = head_raw < tile_total ? head_raw : tile_total;
+  for (uint32_t k = tid; k < head; k += kThreads) dst[k] = s_tile[k];
+  const uint32_t n_chunks = (tile_total - head) >> 4;
+  const uint32_t sh = (head & 3u) * 8u;
+  const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(s_tile) + (head >> 2);
+  for (uint32_t k = tid; k < n_chunks; k += kThreads) {
+    const uint32_t* w = sw + 4 * k;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];  // w[4] stays inside the +32 slack
+    uint4 o;
+    o.x = __funnelshift_r(w0, w1, sh);
+    o.y = __funnelshift_r(w1, w2, sh);
+    o.z = __funnelshift_r(w2, w3, sh);
+    o.w = __funnelshift_r(w3, w4, sh);
+    *reinterpret_cast<uint4*>(dst + head + 16u * k) = o;
+  }
+  for (uint32_t k = head + 16u * n_chunks + tid; k < tile_total; k += kThreads) dst[k] = s_tile[k];
 }
 
 cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
@@ -438,17 +525,18 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
     if (err != cudaSuccess) return err;
     return cudaMemsetAsync(row_offsets, 0, 8, stream);
   }
+  const int smem = kTileBytes + 32 + (int)sizeof(CsvSmem);
   static int configured_device = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_device != dev) {
-    err = cudaFuncSetAttribute(csv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileBytes + 16);
+    err = cudaFuncSetAttribute(csv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
     configured_device = dev;
   }
   expand_entry_show_kernel<<<(unsigned)((v.n_shows + 255) / 256), 256, 0, stream>>>(v, sc.entry_show);
-  csv_rows_kernel<<<(unsigned)csv_tiles(v.n_entries), kRowsPerTile, kTileBytes + 16, stream>>>(
-      v, make_row_table(v), sc, row_offsets, out_data, capacity, total_out);
+  csv_rows_kernel<<<(unsigned)csv_tiles(v.n_entries), kThreads, smem, stream>>>(v, make_row_table(v), sc, row_offsets,
+                                                                                out_data, capacity, total_out);
   g_launches += 2;
   return cudaGetLastError();
 }
