@@ -192,6 +192,10 @@ int pie_csv_rows_dev(const pie_archive_view* dev_view, int64_t* row_offsets, uin
  * PIE_ERR_CAPACITY if out_capacity < *total_bytes (which is set either way). */
 int pie_csv_rows_host(const pie_archive_view* host_view, int64_t* row_offsets, uint8_t* out_data,
                       uint64_t out_capacity, uint64_t* total_bytes);
+/* The host variant streams the batch in chunks of about this many rows (cut at show boundaries):
+ * the upload of chunk c+1 and the download of chunk c-1 overlap the kernels of chunk c.  Returns the
+ * previous value; rows <= 0 only queries.  Default 2^20. */
+int64_t pie_set_csv_chunk_rows(int64_t rows);
 
 /* ---- self tests (device code paths that replace an IEEE operation by a faster exact sequence) */
 /* Compares the shared-reciprocal quotient used for the rate columns with IEEE a/b for every

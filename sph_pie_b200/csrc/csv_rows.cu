@@ -306,6 +306,7 @@ struct CsvSmem {
 __global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab,
                                                             CsvScratch sc, int64_t* __restrict__ row_offsets,
                                                             uint8_t* __restrict__ out_data, uint64_t capacity,
+                                                            unsigned long long bias,
                                                             unsigned long long* __restrict__ total_out) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   uint8_t* s_tile = s_dyn;                                               // kTileBytes + 32
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view 
         sm.base = exclusive;
         if (tile == csv_tiles(v.n_entries) - 1) {
           *total_out = exclusive + tile_total;
-          row_offsets[v.n_entries] = (int64_t)(exclusive + tile_total);
+          row_offsets[v.n_entries] = (int64_t)(bias + exclusive + tile_total);
         }
       }
     }
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view 
     __syncthreads();
   }
   if (!write) {
-    if (tid < rows) row_offsets[e0 + tid] = (int64_t)(sm.base + sm.row_start[tid]);
+    if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + sm.base + sm.row_start[tid]);
     return;
   }
   const bool fits = staged || (sm.base + tile_total <= capacity);  // direct writes must respect the caller's capacity
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view 
   }
   if (staged) __syncthreads();  // the tile is complete in shared memory and its offset is known
   const unsigned long long base = sm.base;
-  if (tid < rows) row_offsets[e0 + tid] = (int64_t)(base + sm.row_start[tid]);
+  if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + base + sm.row_start[tid]);
   if (!staged || base + tile_total > capacity) return;
 
   // ---- 5. flush s_tile[0 .. tile_total) -> out_data[base ..) with 16-byte stores.  Global chunk k
@@ -516,14 +517,15 @@ __global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view 
 }
 
 cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
-                            unsigned long long* total_out, void* scratch, cudaStream_t stream) {
+                            unsigned long long bias, unsigned long long* total_out, void* scratch,
+                            cudaStream_t stream) {
   CsvScratch sc = carve_csv(scratch, v.n_entries);
   cudaError_t err = cudaMemsetAsync(scratch, 0, csv_scratch_zero_bytes(v.n_entries), stream);
   if (err != cudaSuccess) return err;
   if (v.n_entries == 0) {
     err = cudaMemsetAsync(total_out, 0, 8, stream);
     if (err != cudaSuccess) return err;
-    return cudaMemsetAsync(row_offsets, 0, 8, stream);
+    return cudaMemcpyAsync(row_offsets, total_out, 8, cudaMemcpyDeviceToDevice, stream);  // 0; the caller adds its bias
   }
   const int smem = kTileBytes + 32 + (int)sizeof(CsvSmem);
   static int configured_device = -1;
@@ -536,7 +538,7 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
   }
   expand_entry_show_kernel<<<(unsigned)((v.n_shows + 255) / 256), 256, 0, stream>>>(v, sc.entry_show);
   csv_rows_kernel<<<(unsigned)csv_tiles(v.n_entries), kThreads, smem, stream>>>(v, make_row_table(v), sc, row_offsets,
-                                                                                out_data, capacity, total_out);
+                                                                                out_data, capacity, bias, total_out);
   g_launches += 2;
   return cudaGetLastError();
 }

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "pie_kernels.h"
 
@@ -60,6 +61,11 @@ struct Arena {
   }
 };
 Arena g_arena;
+// The upload helpers below stage into *g_cur on g_cur_stream: the analytics path uses g_arena; the
+// pipelined export path flips between two input arenas (all under g_host_mutex).
+Arena g_pipe_in[2];
+Arena* g_cur = &g_arena;
+cudaStream_t g_cur_stream = nullptr;
 
 inline uint64_t pad(uint64_t b) { return ((b + 255) & ~(uint64_t)255) + 256; }
 
@@ -83,12 +89,12 @@ int plan_strcol(StrColPlan& p, const pie_strcol* src, pie_strcol* dst, int64_t n
 }
 
 int upload_strcol(const StrColPlan& p, uint64_t* h2d) {
-  int32_t* d_off = (int32_t*)g_arena.take(4 * (uint64_t)(p.n + 1));
+  int32_t* d_off = (int32_t*)g_cur->take(4 * (uint64_t)(p.n + 1));
   const uint64_t nbytes = (uint64_t)(p.last - p.first);
-  uint8_t* d_data = (uint8_t*)g_arena.take(nbytes ? nbytes : 1);
-  PIE_CUDA(cudaMemcpyAsync(d_off, p.src->offsets, 4 * (uint64_t)(p.n + 1), cudaMemcpyHostToDevice, g_arena.stream));
+  uint8_t* d_data = (uint8_t*)g_cur->take(nbytes ? nbytes : 1);
+  PIE_CUDA(cudaMemcpyAsync(d_off, p.src->offsets, 4 * (uint64_t)(p.n + 1), cudaMemcpyHostToDevice, g_cur_stream));
   if (nbytes)
-    PIE_CUDA(cudaMemcpyAsync(d_data, p.src->data + p.first, nbytes, cudaMemcpyHostToDevice, g_arena.stream));
+    PIE_CUDA(cudaMemcpyAsync(d_data, p.src->data + p.first, nbytes, cudaMemcpyHostToDevice, g_cur_stream));
   p.dst->offsets = d_off;
   p.dst->data = d_data - p.first;  // offsets keep their host values
   *h2d += 4 * (uint64_t)(p.n + 1) + nbytes;
@@ -97,8 +103,8 @@ int upload_strcol(const StrColPlan& p, uint64_t* h2d) {
 
 template <typename T>
 int upload_array(const T* src, int64_t n, const T** dst, uint64_t* h2d) {
-  T* d = (T*)g_arena.take(sizeof(T) * (uint64_t)(n > 0 ? n : 1));
-  if (n > 0) PIE_CUDA(cudaMemcpyAsync(d, src, sizeof(T) * (uint64_t)n, cudaMemcpyHostToDevice, g_arena.stream));
+  T* d = (T*)g_cur->take(sizeof(T) * (uint64_t)(n > 0 ? n : 1));
+  if (n > 0) PIE_CUDA(cudaMemcpyAsync(d, src, sizeof(T) * (uint64_t)n, cudaMemcpyHostToDevice, g_cur_stream));
   *dst = d;
   *h2d += sizeof(T) * (uint64_t)n;
   return PIE_OK;
@@ -115,8 +121,8 @@ int check_view_common(const pie_archive_view* v) {
 
 uint64_t g_last_h2d = 0, g_last_d2h = 0;
 
-// A second grow-only buffer for outputs whose size is only known after a device pass (CSV bytes):
-// growing it must not move the inputs already staged in g_arena.
+// Grow-only device buffer for outputs whose size is only known after a device pass (CSV bytes):
+// growing it must not move the inputs already staged in an arena.
 struct OutBuffer {
   uint8_t* base = nullptr;
   uint64_t cap = 0;
@@ -130,7 +136,6 @@ struct OutBuffer {
     return PIE_OK;
   }
 };
-OutBuffer g_out;
 
 struct ColumnRef {
   const pie_strcol* src;
@@ -183,7 +188,8 @@ int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_
     if ((rc = plan_strcol(item_plans[i], &item_src[i], &lists[i].dst->items, n_items, &bytes, lists[i].name))) return rc;
   }
   if (E > 0 && (!hv->delay_sec || !hv->delay_valid)) return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
-  if ((rc = g_arena.reserve(bytes))) return rc;
+  if ((rc = g_cur->reserve(bytes))) return rc;
+  if (!g_cur_stream) g_cur_stream = g_cur->stream;
   dv->n_shows = S;
   dv->n_entries = E;
   if ((rc = upload_array(hv->entry_offsets, S + 1, &dv->entry_offsets, h2d))) return rc;
@@ -343,6 +349,8 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   }
   if ((rc = g_arena.reserve(bytes))) return rc;
   cudaStream_t st = g_arena.stream;
+  g_cur = &g_arena;
+  g_cur_stream = st;
 
   // ---- H2D
   uint64_t h2d = 0, d2h = 0;
@@ -453,9 +461,89 @@ int pie_csv_rows_dev(const pie_archive_view* v, int64_t* row_offsets, uint8_t* o
   if ((rc = check_view_common(v))) return rc;
   if ((rc = check_export_view_dev(v))) return rc;
   if (!row_offsets || !total_bytes_dev || !scratch) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
-  PIE_CUDA(pie::launch_csv_rows(*v, row_offsets, out_data, out_data ? out_capacity : 0,
+  PIE_CUDA(pie::launch_csv_rows(*v, row_offsets, out_data, out_data ? out_capacity : 0, 0ull,
                                 (unsigned long long*)total_bytes_dev, scratch, (cudaStream_t)stream));
   return PIE_OK;
+}
+
+// Rows per pipeline chunk of the host export path (H2D of chunk c+1 and D2H of chunk c-1 overlap the
+// kernels of chunk c; PCIe is full duplex).
+static int64_t kCsvChunkRows = 1 << 20;  // pie_set_csv_chunk_rows (tests exercise the multi-chunk path)
+
+struct CsvPipeline {
+  cudaStream_t h2d = nullptr, cmp = nullptr, d2h = nullptr;
+  cudaEvent_t h2d_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+  OutBuffer out[2];
+  unsigned long long* h_total = nullptr;  // pinned
+  int init() {
+    if (h2d) return PIE_OK;
+    PIE_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+    PIE_CUDA(cudaStreamCreateWithFlags(&cmp, cudaStreamNonBlocking));
+    PIE_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      PIE_CUDA(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
+      PIE_CUDA(cudaEventCreateWithFlags(&kernel_done[i], cudaEventDisableTiming));
+      PIE_CUDA(cudaEventCreateWithFlags(&d2h_done[i], cudaEventDisableTiming));
+    }
+    PIE_CUDA(cudaHostAlloc(&h_total, 64, cudaHostAllocDefault));
+    return PIE_OK;
+  }
+};
+static CsvPipeline g_pipe;
+
+struct CsvChunk {
+  int64_t s0, s1, e0, e1;
+  std::vector<int32_t> entry_offsets;  // rebased to the chunk
+  pie_archive_view host;                // sliced host view
+  pie_archive_view dev;
+  void* scratch;
+  int64_t* d_offsets;
+  unsigned long long* d_total;
+};
+
+static void slice_col(pie_strcol* c, int64_t first) { if (c->offsets) c->offsets += first; }
+
+static void make_chunk_view(const pie_archive_view* hv, CsvChunk* c) {
+  c->entry_offsets.resize((size_t)(c->s1 - c->s0 + 1));
+  for (int64_t s = c->s0; s <= c->s1; ++s) c->entry_offsets[(size_t)(s - c->s0)] = hv->entry_offsets[s] - (int32_t)c->e0;
+  pie_archive_view v = *hv;
+  v.n_shows = c->s1 - c->s0;
+  v.n_entries = c->e1 - c->e0;
+  v.entry_offsets = c->entry_offsets.data();
+  pie_strcol* show_cols[] = {&v.show_id, &v.show_date, &v.show_time, &v.show_label, &v.lead_pilot, &v.monkey_lead, &v.show_notes};
+  for (pie_strcol* x : show_cols) slice_col(x, c->s0);
+  pie_strcol* entry_cols[] = {&v.entry_id, &v.unit_id, &v.planned, &v.launched, &v.status, &v.primary_issue, &v.sub_issue,
+                              &v.other_detail, &v.severity, &v.root_cause, &v.operator_name, &v.battery_id, &v.command_rx,
+                              &v.notes};
+  for (pie_strcol* x : entry_cols) slice_col(x, c->e0);
+  if (v.crew.list_offsets) v.crew.list_offsets += c->s0;
+  if (v.actions.list_offsets) v.actions.list_offsets += c->e0;
+  if (v.delay_sec) v.delay_sec += c->e0;
+  if (v.delay_valid) v.delay_valid += c->e0;
+  c->host = v;
+}
+
+// stage chunk c into input arena `slot` on the H2D stream
+static int upload_chunk(CsvChunk* c, int slot, uint64_t* h2d) {
+  g_cur = &g_pipe_in[slot];
+  g_cur_stream = g_pipe.h2d;
+  if (!g_cur->stream) g_cur->stream = g_pipe.h2d;  // reserve() only creates a stream when there is none
+  const int64_t E = c->e1 - c->e0;
+  memset(&c->dev, 0, sizeof(c->dev));
+  const uint64_t extra = pad(pie::csv_scratch_bytes(E)) + pad(8 * (uint64_t)(E + 1)) + pad(64);
+  int rc = upload_export_view(&c->host, &c->dev, extra + (extra >> 2), h2d);  // +25 %: later chunks rarely regrow
+  if (rc) return rc;
+  c->scratch = g_cur->take(pie::csv_scratch_bytes(E));
+  c->d_offsets = (int64_t*)g_cur->take(8 * (uint64_t)(E + 1));
+  c->d_total = (unsigned long long*)g_cur->take(16);
+  return PIE_OK;
+}
+
+int64_t pie_set_csv_chunk_rows(int64_t rows) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  const int64_t old = kCsvChunkRows;
+  if (rows > 0) kCsvChunkRows = rows;
+  return old;
 }
 
 int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,
@@ -468,40 +556,87 @@ int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t*
   const int64_t S = hv->n_shows, E = hv->n_entries;
   if (S > 0 && (hv->entry_offsets[0] != 0 || hv->entry_offsets[S] != E))
     return fail(PIE_ERR_INVALID_ARG, "entry_offsets must run from 0 to n_entries");
-  uint64_t h2d = 0, d2h = 0;
-  pie_archive_view dv;
-  memset(&dv, 0, sizeof(dv));
-  const uint64_t extra = pad(pie::csv_scratch_bytes(E)) + pad(8 * (uint64_t)(E + 1)) + pad(64);
-  if ((rc = upload_export_view(hv, &dv, extra, &h2d))) return rc;
-  cudaStream_t st = g_arena.stream;
-  void* scratch = g_arena.take(pie::csv_scratch_bytes(E));
-  int64_t* d_offsets = (int64_t*)g_arena.take(8 * (uint64_t)(E + 1));
-  unsigned long long* d_total = (unsigned long long*)g_arena.take(16);
-  // pass 1: sizes only (row offsets + total), so the output buffer can be sized exactly
-  PIE_CUDA(pie::launch_csv_rows(dv, d_offsets, nullptr, 0, d_total, scratch, st));
-  unsigned long long total = 0;
-  PIE_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
-  PIE_CUDA(cudaStreamSynchronize(st));
-  d2h += 8;
-  *total_bytes = total;
-  g_last_h2d = h2d;
-  g_last_d2h = d2h;
-  if (!out_data) {  // size query
-    PIE_CUDA(cudaMemcpyAsync(row_offsets, d_offsets, 8 * (uint64_t)(E + 1), cudaMemcpyDeviceToHost, st));
-    PIE_CUDA(cudaStreamSynchronize(st));
-    g_last_d2h += 8 * (uint64_t)(E + 1);
-    return PIE_OK;
+  if ((rc = g_pipe.init())) return rc;
+
+  // chunks of ~kCsvChunkRows rows, cut at show boundaries
+  std::vector<CsvChunk> chunks;
+  for (int64_t s0 = 0; s0 < S || chunks.empty();) {
+    CsvChunk c;
+    c.s0 = s0;
+    c.e0 = S > 0 ? hv->entry_offsets[s0] : 0;
+    int64_t s1 = s0;
+    while (s1 < S && hv->entry_offsets[s1] - c.e0 < kCsvChunkRows) {
+      const int64_t step = (S - s1 > 4096 && hv->entry_offsets[s1 + 4096] - c.e0 < kCsvChunkRows) ? 4096 : 1;
+      s1 += step;
+    }
+    c.s1 = s1;
+    c.e1 = S > 0 ? hv->entry_offsets[s1] : 0;
+    chunks.push_back(std::move(c));
+    s0 = s1;
+    if (S == 0) break;
   }
-  if (total > out_capacity)
-    return fail(PIE_ERR_CAPACITY, "CSV rows need %llu bytes, the caller's buffer holds %llu", total,
+  const int K = (int)chunks.size();
+  for (CsvChunk& c : chunks) make_chunk_view(hv, &c);
+
+  uint64_t h2d = 0, d2h = 0;
+  unsigned long long bias = 0;
+  bool overflow = false;
+  if ((rc = upload_chunk(&chunks[0], 0, &h2d))) return rc;
+  PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[0], g_pipe.h2d));
+  for (int k = 0; k < K; ++k) {
+    const int slot = k & 1;
+    CsvChunk& c = chunks[(size_t)k];
+    const int64_t Ec = c.e1 - c.e0;
+    if (k + 1 < K) {  // prefetch the next chunk into the other input arena once chunk k-1's kernels have left it
+      if (k >= 1) {  // ... and its row offsets (which live in that arena) have been copied out
+        PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.kernel_done[slot ^ 1], 0));
+        PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.d2h_done[slot ^ 1], 0));
+      }
+      if ((rc = upload_chunk(&chunks[(size_t)k + 1], slot ^ 1, &h2d))) return rc;
+      PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[slot ^ 1], g_pipe.h2d));
+    }
+    PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.h2d_done[slot], 0));
+    // pass 1: sizes only (row offsets + total), so the output can be placed and sized exactly
+    PIE_CUDA(pie::launch_csv_rows(c.dev, c.d_offsets, nullptr, 0, bias, c.d_total, c.scratch, g_pipe.cmp));
+    PIE_CUDA(cudaMemcpyAsync(g_pipe.h_total, c.d_total, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
+    PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
+    const unsigned long long total = *g_pipe.h_total;
+    d2h += 8;
+    const bool want_data = out_data != nullptr && !overflow && bias + total <= out_capacity;
+    if (out_data && !want_data) overflow = true;
+    if (want_data) {
+      if (k >= 2) PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.d2h_done[slot], 0));  // output slot drained
+      if (g_pipe.out[slot].cap < total + 256) {
+        if (k >= 2) PIE_CUDA(cudaEventSynchronize(g_pipe.d2h_done[slot]));
+        if ((rc = g_pipe.out[slot].ensure(total + (total >> 2) + 256))) return rc;
+      }
+      // pass 2: write (the chunk's inputs are resident; most of them still in L2)
+      PIE_CUDA(pie::launch_csv_rows(c.dev, c.d_offsets, g_pipe.out[slot].base, total, bias, c.d_total, c.scratch,
+                                    g_pipe.cmp));
+    }
+    PIE_CUDA(cudaEventRecord(g_pipe.kernel_done[slot], g_pipe.cmp));
+    PIE_CUDA(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.kernel_done[slot], 0));
+    if (Ec > 0)
+      PIE_CUDA(cudaMemcpyAsync(row_offsets + c.e0, c.d_offsets, 8 * (uint64_t)Ec, cudaMemcpyDeviceToHost, g_pipe.d2h));
+    d2h += 8 * (uint64_t)Ec;
+    if (want_data && total) {
+      PIE_CUDA(cudaMemcpyAsync(out_data + bias, g_pipe.out[slot].base, total, cudaMemcpyDeviceToHost, g_pipe.d2h));
+      d2h += total;
+    }
+    PIE_CUDA(cudaEventRecord(g_pipe.d2h_done[slot], g_pipe.d2h));
+    bias += total;
+  }
+  PIE_CUDA(cudaStreamSynchronize(g_pipe.d2h));
+  PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
+  row_offsets[E] = (int64_t)bias;
+  *total_bytes = bias;
+  g_last_h2d = h2d;
+  g_last_d2h = d2h + 8;
+  g_cur = &g_arena;
+  g_cur_stream = g_arena.stream;
+  if (overflow)
+    return fail(PIE_ERR_CAPACITY, "CSV rows need %llu bytes, the caller's buffer holds %llu", bias,
                 (unsigned long long)out_capacity);
-  if ((rc = g_out.ensure(total + 256))) return rc;
-  // pass 2: write (the inputs are still resident; most of them are now in L2)
-  PIE_CUDA(pie::launch_csv_rows(dv, d_offsets, g_out.base, total, d_total, scratch, st));
-  PIE_CUDA(cudaMemcpyAsync(row_offsets, d_offsets, 8 * (uint64_t)(E + 1), cudaMemcpyDeviceToHost, st));
-  if (total) PIE_CUDA(cudaMemcpyAsync(out_data, g_out.base, total, cudaMemcpyDeviceToHost, st));
-  PIE_CUDA(cudaStreamSynchronize(st));
-  g_last_d2h = d2h + 8 * (uint64_t)(E + 1) + total;
   return PIE_OK;
 }
 

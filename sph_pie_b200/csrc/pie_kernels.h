@@ -17,8 +17,10 @@ cudaError_t launch_selftest_fast_div(int max_b, unsigned long long* d_mismatches
 
 // csv_rows.cu
 uint64_t csv_scratch_bytes(int64_t n_entries);
+// row_offsets receive offset_bias + the offset inside out_data (chunked callers place chunks back to back)
 cudaError_t launch_csv_rows(const pie_archive_view& dev_view, int64_t* row_offsets, uint8_t* out_data,
-                            uint64_t capacity, unsigned long long* total_out, void* scratch, cudaStream_t stream);
+                            uint64_t capacity, unsigned long long offset_bias, unsigned long long* total_out,
+                            void* scratch, cudaStream_t stream);
 
 // archive_daily.cu
 uint64_t daily_scratch_bytes(int64_t n_shows);

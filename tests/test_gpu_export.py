@@ -135,3 +135,31 @@ def test_sliced_table_rows(cuda):
     e0, e1 = int(host.entry_offsets[1000]), int(host.entry_offsets[2200])
     assert ops.csv_rows(part).rows() == whole[e0:e1]
     assert ops.csv_rows(host.to(cuda).slice_shows(1000, 2200)).rows() == whole[e0:e1]
+
+
+def test_host_pipeline_many_chunks(cuda):
+    """The host entry point streams the batch in chunks (upload / kernels / download overlapped on three
+    streams, two staging slots).  Force many small chunks and compare with the oracle."""
+    lib = _lib.load()
+    host = synth_archive(6000, seed=8).pin()
+    old = lib.pie_set_csv_chunk_rows(3000)
+    try:
+        assert lib.pie_set_csv_chunk_rows(0) == 3000
+        for _ in range(2):  # second pass reuses the staging arenas
+            assert_same_rows(ops.csv_rows(host), host)
+        # a show larger than a chunk, empty shows around it, and a capacity overflow in a late chunk
+        lib.pie_set_csv_chunk_rows(64)
+        shows = ([{"id": "e", "entries": []}] * 3 + [{"id": "big", "entries": [{"id": str(i), "delaySec": i / 8} for i in range(700)]}]
+                 + [{"id": "t", "entries": [{"id": "x"}]}] * 150 + [{"id": "e2", "entries": []}])
+        table = pack_shows(shows)
+        assert_same_rows(ops.csv_rows(table), table)
+        import ctypes as C
+
+        offsets, data = oracle_c.csv_rows(table)
+        view, total = table.view(), C.c_uint64(0)
+        off = torch.empty(table.n_entries + 1, dtype=torch.int64)
+        buf = torch.full((data.numel() - 10,), 0xEE, dtype=torch.uint8)
+        rc = lib.pie_csv_rows_host(C.byref(view), off.data_ptr(), buf.data_ptr(), buf.numel(), C.byref(total))
+        assert rc == _lib.PIE_ERR_CAPACITY and total.value == data.numel() and torch.equal(off, offsets)
+    finally:
+        lib.pie_set_csv_chunk_rows(old)
