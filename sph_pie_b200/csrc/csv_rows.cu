@@ -36,6 +36,9 @@ __device__ const uint64_t d_pow5[PIE_RYU_POW5_SPLIT_N][2] = PIE_RYU_POW5_SPLIT_I
 #ifndef PIE_CSV_THREADS
 #define PIE_CSV_THREADS 512
 #endif
+#ifndef PIE_CSV_MIN_BLOCKS
+#define PIE_CSV_MIN_BLOCKS 3
+#endif
 #ifndef PIE_CSV_TILE_KB
 #define PIE_CSV_TILE_KB 48
 #endif
@@ -54,6 +57,7 @@ constexpr unsigned long long kPrefix = 2ull << kStatusShift;
 struct CsvScratch {
   unsigned long long* tile_state;  // [n_tiles] packed (status, value); zeroed before launch
   unsigned int* tile_counter;      // [1] dynamic tile ids; zeroed before launch
+  unsigned int* col_dirty;         // [24] column c holds at least one " , \n \r somewhere; zeroed before launch
   int32_t* entry_show;             // [n_entries]
 };
 
@@ -73,7 +77,9 @@ static CsvScratch carve_csv(void* scratch, int64_t n_entries) {
   uint8_t* p = static_cast<uint8_t*>(scratch);
   CsvScratch s;
   s.tile_state = (unsigned long long*)p; p += align256(8 * (uint64_t)csv_tiles(e));
-  s.tile_counter = (unsigned int*)p; p += 256;
+  s.tile_counter = (unsigned int*)p;
+  s.col_dirty = (unsigned int*)(p + 64);
+  p += 256;
   s.entry_show = (int32_t*)p;
   return s;
 }
@@ -264,69 +270,145 @@ static RowTable make_row_table(const pie_archive_view& v) {
   return t;
 }
 
-// Source bytes of one cell: [data + b, data + b + n); for a joined list the items are contiguous in
-// the item heap and `items` = l1 - l0.  blank = the reference writes '' for this cell.
-struct CellSrc {
-  int b, n, l0, l1;
-  bool blank;
-};
-
-__device__ __forceinline__ CellSrc locate_cell(const pie_archive_view& v, const CellDesc& d, int64_t e, int64_t s) {
-  CellSrc c{0, 0, 0, 0, false};
-  const int64_t i = d.per_entry ? e : s;
-  if (d.blank_if_completed && status_is_completed(v, e)) {
-    c.blank = true;
-  } else if (d.kind == kCellString) {
-    c.b = d.offsets[i];
-    c.n = d.offsets[i + 1] - c.b;
-  } else if (d.kind == kCellJoined) {
-    c.l0 = d.list_offsets[i];
-    c.l1 = d.list_offsets[i + 1];
-    if (c.l1 > c.l0) {
-      c.b = d.offsets[c.l0];
-      c.n = d.offsets[c.l1] - c.b;
-    }
+// ---- pre-pass: which columns can need quoting at all? -----------------------------------------------
+// Most columns of an archive (ids, dates, enumerations, names) never contain " , \n or \r.  One
+// streaming pass over every column's byte heap (16 bytes per thread and step, HBM speed) sets a
+// per-column flag; the row kernel then skips the per-cell scan for clean columns altogether.
+__global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant__ RowTable tab, int64_t n_shows,
+                                                           int64_t n_entries, unsigned int* __restrict__ col_dirty) {
+  const int col = blockIdx.y;
+  const CellDesc& d = tab.cell[col];
+  if (d.kind == kCellNumber) return;
+  const int64_t n = d.per_entry ? n_entries : n_shows;
+  int64_t first = 0, last = n;  // rows of the string column that hold this cell's bytes
+  if (d.kind == kCellJoined) {
+    first = d.list_offsets[0];
+    last = d.list_offsets[n];
   }
-  return c;
+  const int64_t b0 = d.offsets[first], b1 = d.offsets[last];
+  if (b1 <= b0) return;
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(d.data + b0), a1 = reinterpret_cast<uintptr_t>(d.data + b1);
+  const uintptr_t w0 = a0 & ~static_cast<uintptr_t>(15), w1 = (a1 + 15) & ~static_cast<uintptr_t>(15);
+  const int64_t chunks = static_cast<int64_t>((w1 - w0) >> 4);
+  uint32_t flags = 0;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (int64_t)gridDim.x * blockDim.x) {
+    const uintptr_t a = w0 + 16 * (uintptr_t)c;
+    // Only words that hold heap bytes are loaded; the edge words are masked to the heap's bytes.
+    uint32_t x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uintptr_t wa = a + 4 * k;
+      uint32_t v = 0;
+      if (wa + 4 > a0 && wa < a1) {
+        v = __ldg(reinterpret_cast<const uint32_t*>(wa));
+        if (wa < a0) v &= 0xFFFFFFFFu << (8 * (uint32_t)(a0 - wa));
+        if (wa + 4 > a1) v &= (1u << (8 * (uint32_t)(a1 - wa))) - 1u;
+      }
+      x[k] = v;
+    }
+    flags |= special_flags(x[0]) | special_flags(x[1]) | special_flags(x[2]) | special_flags(x[3]);
+  }
+  if (__any_sync(0xFFFFFFFFu, flags != 0) && (threadIdx.x & 31) == 0) atomicOr(&col_dirty[col], 1u);
 }
 
-constexpr uint32_t kQuoteBit = 0x80000000u;
+// ---- the kernel ---------------------------------------------------------------------------------
+// Work item = (row, group of kGroupCols consecutive columns); thread tid owns row tid % kRows, group
+// tid / kRows, in BOTH the measuring and the writing phase, so the quote flags stay in registers and
+// one byte-stream writer emits the whole group (byte stores only at the group's two ends).  A warp =
+// one group x 32 consecutive rows: it walks the same column at the same time.
+constexpr int kGroups = 4;
+constexpr int kGroupCols = kCols / kGroups;   // 6
+constexpr int kWorkers = kRows * kGroups;     // 512 worker threads ...
+constexpr int kCtaThreads = kWorkers + 32;    // ... + one warp that runs the decoupled look-back
+static_assert(kGroups * kGroupCols == kCols && kThreads == kWorkers, "tile shape");
+constexpr uint32_t kCompletedBit = 1u << 31;
 
 struct CsvSmem {
-  uint32_t cell[kCols][kRows];  // step 1: escaped length | kQuoteBit; step 2: start offset in the row | kQuoteBit
-  uint32_t row_start[kRows];    // byte offset of the row inside the tile
+  uint32_t group[kGroups][kRows];  // phase 1: bytes of the group (with its separators); phase 2: start in the row
+  uint32_t row_start[kRows];       // byte offset of the row inside the tile
   char num[kRows][kMaxNumberChars];
   uint8_t num_len[kRows];
   uint32_t warp_sum[kRows / 32];
+  uint32_t col_dirty[kCols];
   uint32_t tile_total;
   unsigned int tile_id;
   unsigned long long base;
 };
 
-__global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab,
-                                                            CsvScratch sc, int64_t* __restrict__ row_offsets,
-                                                            uint8_t* __restrict__ out_data, uint64_t capacity,
-                                                            unsigned long long bias,
-                                                            unsigned long long* __restrict__ total_out) {
+__global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS) csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab,
+                                                                  CsvScratch sc, int64_t* __restrict__ row_offsets,
+                                                                  uint8_t* __restrict__ out_data, uint64_t capacity,
+                                                                  unsigned long long bias,
+                                                                  unsigned long long* __restrict__ total_out) {
   extern __shared__ __align__(16) uint8_t s_dyn[];
   uint8_t* s_tile = s_dyn;                                               // kTileBytes + 32
   CsvSmem& sm = *reinterpret_cast<CsvSmem*>(s_dyn + kTileBytes + 32);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool worker = tid < kWorkers;
 
   if (tid == 0) sm.tile_id = atomicAdd(sc.tile_counter, 1u);  // tiles start in id order: look-back cannot deadlock
+  if (tid < kCols) sm.col_dirty[tid] = sc.col_dirty[tid];
   __syncthreads();
   const int64_t tile = sm.tile_id;
   const int64_t e0 = tile * kRows;
   const int rows = (v.n_entries - e0 < kRows) ? (int)(v.n_entries - e0) : kRows;
+  const int g = tid / kRows, r = tid % kRows;
+  const bool have = worker && r < rows;
+  const int64_t e = e0 + r;
+  const int64_t show = (have && g < 2) ? sc.entry_show[e] : 0;  // groups 0-1 hold the show-level columns 0..7
 
-  // ---- 1. measure every cell (cell q: column q / kRows, row q % kRows -> a warp = one column)
-#pragma unroll 1  // one generic body: unrolled, the compiler specialises it per column (15k instructions)
-  for (int q = tid; q < kCells; q += kThreads) {
-    const int col = q / kRows, r = q % kRows;
-    uint32_t len = 0;
-    if (r < rows) {
-      const int64_t e = e0 + r;
+  // ---- 1a. locate the group's cells: every offset load is issued before any is consumed (a tile is
+  // latency-bound: per column a dependent chain offsets -> bytes; walking 6 columns one after the
+  // other cost 6 such chains per phase)
+  int cb[kGroupCols], cn[kGroupCols], citems[kGroupCols];
+  {
+    int a0[kGroupCols], a1[kGroupCols];
+#pragma unroll
+    for (int k = 0; k < kGroupCols; ++k) {
+      const CellDesc& d = tab.cell[g * kGroupCols + k];
+      const int64_t i = d.per_entry ? e : show;
+      const int32_t* __restrict__ p = (d.kind == kCellJoined) ? d.list_offsets : d.offsets;
+      a0[k] = 0;
+      a1[k] = 0;
+      if (have && d.kind != kCellNumber) {
+        a0[k] = p[i];
+        a1[k] = p[i + 1];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kGroupCols; ++k) {
+      const CellDesc& d = tab.cell[g * kGroupCols + k];
+      cb[k] = a0[k];
+      cn[k] = a1[k] - a0[k];
+      citems[k] = 1;
+      if (d.kind == kCellJoined) {  // Array.prototype.join('|') (crew :284, actions :298): items are contiguous
+        citems[k] = cn[k];
+        cb[k] = 0;
+        cn[k] = 0;
+        if (have && citems[k] > 0) {
+          cb[k] = d.offsets[a0[k]];
+          cn[k] = d.offsets[a1[k]] - cb[k];
+        }
+      }
+    }
+  }
+
+  // ---- 1b. measure the group
+  uint32_t glen = 0, qmask = 0;
+  if (have) {
+    bool completed = false;  // entry.status === 'Completed' (:293-297); status is column 12 = group 2, k = 0
+    if (g == 2 && cn[0] == 9) {
+      uint32_t x[3];
+      fetch_words_raw<3>(tab.cell[12].data + cb[0], 9, x);
+      completed = x[0] == lit_word("Completed", 0) && x[1] == lit_word("Completed", 1) &&
+                  (x[2] & 0xFFu) == lit_word("Completed", 2);
+    }
+    if (completed) qmask |= kCompletedBit;
+#pragma unroll 1  // generic body (unrolled it is specialised per column: 28k instructions, icache-bound)
+    for (int k = 0; k < kGroupCols; ++k) {
+      const int col = g * kGroupCols + k;
       const CellDesc& d = tab.cell[col];
+      uint32_t len = 0;
       if (d.kind == kCellNumber) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
         int nl = 0;
         if (v.delay_valid[e]) {
@@ -335,29 +417,29 @@ __global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view 
         }
         sm.num_len[r] = (uint8_t)nl;
         len = (uint32_t)nl;
-      } else {
-        const CellSrc c = locate_cell(v, d, e, d.per_entry ? 0 : sc.entry_show[e]);
-        if (c.n > 0) {
-          len = (uint32_t)c.n;
-          if (has_special(d.data + c.b, c.n)) len = (len + 2u + count_quotes(d.data + c.b, c.n)) | kQuoteBit;
+      } else if (!(d.blank_if_completed && completed)) {
+        len = (uint32_t)cn[k] + (citems[k] > 1 ? (uint32_t)(citems[k] - 1) : 0u);  // '|' between items: not special
+        if (sm.col_dirty[col] && has_special(d.data + cb[k], cn[k])) {  // csvEscape (:332-338)
+          qmask |= 1u << k;
+          len += 2u + count_quotes(d.data + cb[k], cn[k]);
         }
-        if (c.l1 > c.l0) len += (uint32_t)(c.l1 - c.l0 - 1);  // '|' between items (not special)
       }
+      glen += len + 1u;  // + ',' (or the final '\n')
     }
-    sm.cell[col][r] = len;
   }
+  if (worker) sm.group[g][r] = glen;
   __syncthreads();
 
-  // ---- 2. per-row scan over the 24 cells, then block scan over the rows
+  // ---- 2. per-row scan over the groups, then block scan over the rows
   uint32_t row_len = 0;
   if (tid < kRows) {
     if (tid < rows) {
       uint32_t run = 0;
 #pragma unroll
-      for (int col = 0; col < kCols; ++col) {
-        const uint32_t x = sm.cell[col][tid];
-        sm.cell[col][tid] = run | (x & kQuoteBit);
-        run += (x & ~kQuoteBit) + 1u;  // + ',' (or the final '\n')
+      for (int k = 0; k < kGroups; ++k) {
+        const uint32_t x = sm.group[k][tid];
+        sm.group[k][tid] = run;
+        run += x;
       }
       row_len = run;
     }
@@ -388,105 +470,102 @@ __global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view 
   const bool write = out_data != nullptr;
   const bool staged = tile_total <= (uint32_t)kTileBytes;
 
-  // ---- 4. decoupled look-back, by warp 0 — WHILE warps 1.. write the cells of a staged tile (step 3
-  // does not need the offset); before step 3 when the tile must be written to global memory directly.
-  auto look_back_warp0 = [&]() {
-    {
-      volatile unsigned long long* state = sc.tile_state;
-      unsigned long long exclusive = 0;
-      int64_t idx = tile - 1;
-      while (idx >= 0) {
-        const int64_t j = idx - lane;
-        unsigned long long st;
-        do {
-          st = 2ull << kStatusShift;  // before tile 0: an empty prefix
-          if (j >= 0) st = state[j];
-        } while (__any_sync(0xFFFFFFFFu, (st >> kStatusShift) == 0));
-        const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (st >> kStatusShift) == 2);
-        const int stop = is_prefix ? (__ffs(is_prefix) - 1) : 32;  // nearest tile that already knows its prefix
-        unsigned long long part = (lane <= stop) ? (st & kValueMask) : 0ull;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-        exclusive += part;
-        if (is_prefix) break;
-        idx -= 32;
+  // ---- 4. decoupled look-back, by the extra warp — WHILE the workers write the cells of a staged
+  // tile (step 3 does not need the offset); before step 3 when the tile goes straight to global memory.
+  auto look_back = [&]() {
+    volatile unsigned long long* state = sc.tile_state;
+    unsigned long long exclusive = 0;
+    int64_t idx = tile - 1;
+    while (idx >= 0) {
+      const int64_t j = idx - lane;
+      unsigned long long st;
+      unsigned ns = 32;
+      for (;;) {
+        st = 2ull << kStatusShift;  // before tile 0: an empty prefix
+        if (j >= 0) st = state[j];
+        if (!__any_sync(0xFFFFFFFFu, (st >> kStatusShift) == 0)) break;
+        __nanosleep(ns);  // the tiles we wait for are still measuring: do not hammer L2 / the issue slots
+        if (ns < 1024) ns <<= 1;
       }
-      if (lane == 0) {
-        if (tile > 0) {
-          __threadfence();
-          state[tile] = kPrefix | (exclusive + tile_total);
-        }
-        sm.base = exclusive;
-        if (tile == csv_tiles(v.n_entries) - 1) {
-          *total_out = exclusive + tile_total;
-          row_offsets[v.n_entries] = (int64_t)(bias + exclusive + tile_total);
-        }
+      const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (st >> kStatusShift) == 2);
+      const int stop = is_prefix ? (__ffs(is_prefix) - 1) : 32;  // nearest tile that already knows its prefix
+      unsigned long long part = (lane <= stop) ? (st & kValueMask) : 0ull;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+      exclusive += part;
+      if (is_prefix) break;
+      idx -= 32;
+    }
+    if (lane == 0) {
+      if (tile > 0) {
+        __threadfence();
+        state[tile] = kPrefix | (exclusive + tile_total);
+      }
+      sm.base = exclusive;
+      if (tile == csv_tiles(v.n_entries) - 1) {
+        *total_out = exclusive + tile_total;
+        row_offsets[v.n_entries] = (int64_t)(bias + exclusive + tile_total);
       }
     }
   };
-  const bool overlap = write && staged;  // warp 0 looks back while the other warps write
+  const bool overlap = write && staged;
   if (!overlap) {
-    if (wid == 0) look_back_warp0();
+    if (!worker) look_back();
     __syncthreads();
   }
   if (!write) {
     if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + sm.base + sm.row_start[tid]);
     return;
   }
-  const bool fits = staged || (sm.base + tile_total <= capacity);  // direct writes must respect the caller's capacity
+  const bool fits = staged || (sm.base + tile_total <= capacity);  // direct writes respect the caller's capacity
 
-  // ---- 3. write every cell
-  if (overlap && wid == 0) {
-    look_back_warp0();
-  } else if (fits) {
-    uint8_t* const dst0 = staged ? s_tile : (out_data + sm.base);
-    const int q0 = overlap ? tid - 32 : tid, qstride = overlap ? kThreads - 32 : kThreads;
+  // ---- 3. write the group
+  if (!worker) {
+    if (overlap) look_back();
+  } else if (have && fits) {
+    StreamWriter out;
+    out.init((staged ? s_tile : (out_data + sm.base)) + sm.row_start[r] + sm.group[g][r]);
+    const bool completed = (qmask & kCompletedBit) != 0;
 #pragma unroll 1
-    for (int q = q0; q < kCells; q += qstride) {
-      const int col = q / kRows, r = q % kRows;
-      if (r >= rows) continue;
-      const int64_t e = e0 + r;
+    for (int k = 0; k < kGroupCols; ++k) {
+      const int col = g * kGroupCols + k;
       const CellDesc& d = tab.cell[col];
-      const uint32_t x = sm.cell[col][r];
-      const bool quote = (x & kQuoteBit) != 0;
       const uint8_t sep = (col == kCols - 1) ? (uint8_t)'\n' : (uint8_t)',';
-      StreamWriter out;
-      out.init(dst0 + sm.row_start[r] + (x & ~kQuoteBit));
+      const bool quote = (qmask >> k) & 1u;
       if (d.kind == kCellNumber) {
         const int nl = sm.num_len[r];
-        for (int k = 0; k < nl; ++k) out.put((uint8_t)sm.num[r][k]);
+        for (int j = 0; j < nl; ++j) out.put((uint8_t)sm.num[r][j]);
         out.put(sep);
+      } else if (d.blank_if_completed && completed) {
+        out.put(sep);
+      } else if (d.kind == kCellString) {
+        if (!quote) {
+          copy_plain(out, d.data + cb[k], cn[k], sep);
+        } else {
+          out.put('"');
+          copy_quoted_bytes(out, d.data + cb[k], cn[k]);
+          out.put('"');
+          out.put(sep);
+        }
       } else {
-        const CellSrc c = locate_cell(v, d, e, d.per_entry ? 0 : sc.entry_show[e]);
-        if (d.kind == kCellString || c.l1 <= c.l0) {
-          if (!quote) {
-            copy_plain(out, d.data + c.b, c.n, sep);
-          } else {
-            out.put('"');
-            copy_quoted_bytes(out, d.data + c.b, c.n);
-            out.put('"');
-            out.put(sep);
-          }
-        } else {  // Array.prototype.join('|') then csvEscape of the joined string (crew :284, actions :298)
-          if (quote) out.put('"');
-          for (int l = c.l0; l < c.l1; ++l) {
-            const int b = d.offsets[l], n = d.offsets[l + 1] - b;
-            const bool last_item = (l + 1 == c.l1);
-            if (quote) {
-              copy_quoted_bytes(out, d.data + b, n);
-              if (!last_item) out.put('|');
-            } else {
-              copy_plain(out, d.data + b, n, last_item ? sep : (uint8_t)'|');
-            }
-          }
+        const int64_t i = d.per_entry ? e : show;
+        const int l0 = citems[k] > 0 ? d.list_offsets[i] : 0, l1 = l0 + citems[k];
+        if (quote) out.put('"');
+        for (int l = l0; l < l1; ++l) {
+          const int b = d.offsets[l], n = d.offsets[l + 1] - b;
+          const bool last_item = (l + 1 == l1);
           if (quote) {
-            out.put('"');
-            out.put(sep);
+            copy_quoted_bytes(out, d.data + b, n);
+            if (!last_item) out.put('|');
+          } else {
+            copy_plain(out, d.data + b, n, last_item ? sep : (uint8_t)'|');
           }
         }
+        if (quote) out.put('"');
+        if (quote || l1 <= l0) out.put(sep);
       }
-      out.finish();
     }
+    out.finish();
   }
   if (staged) __syncthreads();  // the tile is complete in shared memory and its offset is known
   const unsigned long long base = sm.base;
@@ -499,11 +578,11 @@ __global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view 
   uint8_t* __restrict__ dst = out_data + base;
   const uint32_t head_raw = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
   const uint32_t head = head_raw < tile_total ? head_raw : tile_total;
-  for (uint32_t k = tid; k < head; k += kThreads) dst[k] = s_tile[k];
+  for (uint32_t k = tid; k < head; k += kCtaThreads) dst[k] = s_tile[k];
   const uint32_t n_chunks = (tile_total - head) >> 4;
   const uint32_t sh = (head & 3u) * 8u;
   const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(s_tile) + (head >> 2);
-  for (uint32_t k = tid; k < n_chunks; k += kThreads) {
+  for (uint32_t k = tid; k < n_chunks; k += kCtaThreads) {
     const uint32_t* w = sw + 4 * k;
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];  // w[4] stays inside the +32 slack
     uint4 o;
@@ -513,7 +592,7 @@ __global__ void __launch_bounds__(kThreads, 3) csv_rows_kernel(pie_archive_view 
     o.w = __funnelshift_r(w3, w4, sh);
     *reinterpret_cast<uint4*>(dst + head + 16u * k) = o;
   }
-  for (uint32_t k = head + 16u * n_chunks + tid; k < tile_total; k += kThreads) dst[k] = s_tile[k];
+  for (uint32_t k = head + 16u * n_chunks + tid; k < tile_total; k += kCtaThreads) dst[k] = s_tile[k];
 }
 
 cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
@@ -537,9 +616,16 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
     configured_device = dev;
   }
   expand_entry_show_kernel<<<(unsigned)((v.n_shows + 255) / 256), 256, 0, stream>>>(v, sc.entry_show);
-  csv_rows_kernel<<<(unsigned)csv_tiles(v.n_entries), kThreads, smem, stream>>>(v, make_row_table(v), sc, row_offsets,
+  const RowTable tab = make_row_table(v);
+  {
+    int64_t blocks = (v.n_entries * 3 + 255) / 256;  // ~ a 16-byte chunk per thread for the widest heaps
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    column_dirty_kernel<<<dim3((unsigned)blocks, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries, sc.col_dirty);
+  }
+  csv_rows_kernel<<<(unsigned)csv_tiles(v.n_entries), kCtaThreads, smem, stream>>>(v, tab, sc, row_offsets,
                                                                                 out_data, capacity, bias, total_out);
-  g_launches += 2;
+  g_launches += 3;
   return cudaGetLastError();
 }
 
