@@ -6,21 +6,27 @@
 // Output = one string column: row i is out_data[row_offsets[i] .. row_offsets[i+1]-1) and is followed
 // by one '\n', so a show's CSV body is a single contiguous slice.
 //
-// ONE pass over the inputs.  A CTA takes a tile of kRows consecutive entries = 24 x
-// kRows CELLS, and works cell-parallel, column-major: a warp handles ONE column for 32 consecutive
-// rows, so its offset loads are coalesced, its cell lengths are alike (no divergence), and every
-// thread has independent loads in flight (a thread per row walked 24 dependent cells serially).
-//   1. measure  every cell: escaped length (word-wise scan for the characters that force quotes);
-//               Number::toString(delaySec) is formatted once into shared memory
-//   2. scan     per row over its 24 cells (shared memory), block scan over the rows -> tile total;
-//               the tile's aggregate is published for the decoupled look-back
-//   3. write    every cell into the SHARED tile buffer through a byte-stream writer (aligned
-//               32-bit stores; only the 0..3 bytes at a cell's two ends are byte stores)
-//   4. look-back over the tile totals -> the tile's global byte offset (overlaps 3 in other CTAs)
-//   5. flush    16-byte coalesced stores; the shared buffer is re-aligned to the destination with a
-//               funnel shift, so step 3 does not have to wait for the offset
-// A tile that does not fit the shared buffer (very long free text) is written straight to global
-// memory by the same cell code, after its look-back.
+// ONE pass over the inputs.  A CTA takes a tile of kRows consecutive entries:
+//   A. stage    the tile's bytes of every column are ONE contiguous range of that column's heap (rows
+//               are consecutive), so a single warp issues <= 23 TMA bulk copies (cp.async.bulk,
+//               completion on an mbarrier) into shared memory; the < 16 bytes past the last full
+//               16-byte chunk of a range are copied as words so nothing is read past a heap's end.
+//               Meanwhile the other warps gather their offsets and format delaySec (Ryu).
+//   B. cells    every cell becomes a plain (src, len) pair in the staging buffer: show-level cells
+//               are normalised once per show of the tile, not once per row; cells that need csvEscape
+//               or Array.join('|') are materialised in a bump area behind the staged bytes;
+//               Number::toString output lives next to it; cells blanked by status === 'Completed'
+//               get len 0.
+//   C. scan     per-row and per-tile sizes; the tile's aggregate is published for the decoupled
+//               look-back, which the extra warp runs WHILE the others write (D needs no offset).
+//   D. write    the OUTPUT is partitioned: the tile's bytes are cut into equal 16-byte-multiple
+//               chunks, one per thread.  The cell that contains a chunk's first byte registers itself
+//               in a table, so a thread starts there and streams cells into its own aligned words —
+//               no byte stores, no races, and the work per thread is the same whatever the row
+//               lengths are.
+//   E. flush    16-byte coalesced stores; the tile is re-aligned to the destination with a funnel shift.
+// A tile that does not fit (very long free text, more than kMaxTileShows shows) takes a slow path:
+// a warp per row, lanes striding over the bytes of a cell, straight from / to global memory.
 #include "pie_device.cuh"
 #include "pie_kernels.h"
 #include "pie_numfmt.cuh"
@@ -33,21 +39,31 @@ __device__ const uint64_t d_pow5[PIE_RYU_POW5_SPLIT_N][2] = PIE_RYU_POW5_SPLIT_I
 #ifndef PIE_CSV_ROWS
 #define PIE_CSV_ROWS 128
 #endif
-#ifndef PIE_CSV_THREADS
-#define PIE_CSV_THREADS 512
-#endif
 #ifndef PIE_CSV_MIN_BLOCKS
-#define PIE_CSV_MIN_BLOCKS 3
+#define PIE_CSV_MIN_BLOCKS 2
 #endif
-#ifndef PIE_CSV_TILE_KB
-#define PIE_CSV_TILE_KB 48
+#ifndef PIE_CSV_OUT_KB
+#define PIE_CSV_OUT_KB 42
 #endif
-constexpr int kRows = PIE_CSV_ROWS;                 // rows (entries) per tile; multiple of 32
-constexpr int kThreads = PIE_CSV_THREADS;           // multiple of kRows
-constexpr int kCols = PIE_N_EXPORT_COLUMNS;         // 24
-constexpr int kCells = kRows * kCols;
-constexpr int kTileBytes = PIE_CSV_TILE_KB * 1024;  // shared tile buffer (rows of ~280 B -> ~36 KB per 128 rows)
-static_assert(kRows % 32 == 0 && kThreads % kRows == 0 && kCells % kThreads == 0, "tile shape");
+#ifndef PIE_CSV_IN_KB
+#define PIE_CSV_IN_KB 40
+#endif
+constexpr int kRows = PIE_CSV_ROWS;            // rows (entries) per tile; multiple of 32
+constexpr int kCols = PIE_N_EXPORT_COLUMNS;    // 24
+constexpr int kGroups = 4;
+constexpr int kGroupCols = kCols / kGroups;    // 6
+constexpr int kWorkers = kRows * kGroups;      // worker threads: (row, group of 6 columns) ...
+constexpr int kCtaThreads = kWorkers + 32;     // ... + one warp: TMA producer, then decoupled look-back
+constexpr int kCtaWarps = kCtaThreads / 32;
+constexpr int kOutBytes = PIE_CSV_OUT_KB * 1024;  // shared output tile (rows of ~280 B -> ~36 KB per 128 rows)
+constexpr int kInBytes = PIE_CSV_IN_KB * 1024;    // staged column bytes + bump area
+constexpr int kNumBytes = kRows * kMaxNumberChars;
+constexpr int kShowCols = 8;                   // columns 0..7 are show-level
+constexpr int kMaxTileShows = kRows;           // shows a tile may span on the fast path
+constexpr int kCellStride = kCols + 1;         // padded: lanes = consecutive rows hit distinct banks
+static_assert(kRows % 32 == 0 && kGroups * kGroupCols == kCols, "tile shape");
+static_assert(kInBytes + kNumBytes <= 65536, "cell sources are 16-bit offsets into the staging buffer");
+static_assert(kOutBytes <= 65536 - 256 && kRows * kCellStride < 4096, "chunk table packs (cell:12, skip:16)");
 
 constexpr unsigned long long kStatusShift = 62;
 constexpr unsigned long long kValueMask = (1ull << kStatusShift) - 1;
@@ -57,6 +73,7 @@ constexpr unsigned long long kPrefix = 2ull << kStatusShift;
 struct CsvScratch {
   unsigned long long* tile_state;  // [n_tiles] packed (status, value); zeroed before launch
   unsigned int* tile_counter;      // [1] dynamic tile ids; zeroed before launch
+  unsigned int* slow_tiles;        // [1] tiles that took the slow path (diagnostics); zeroed before launch
   unsigned int* col_dirty;         // [24] column c holds at least one " , \n \r somewhere; zeroed before launch
   int32_t* entry_show;             // [n_entries]
 };
@@ -78,10 +95,24 @@ static CsvScratch carve_csv(void* scratch, int64_t n_entries) {
   CsvScratch s;
   s.tile_state = (unsigned long long*)p; p += align256(8 * (uint64_t)csv_tiles(e));
   s.tile_counter = (unsigned int*)p;
+  s.slow_tiles = (unsigned int*)(p + 16);
   s.col_dirty = (unsigned int*)(p + 64);
   p += 256;
   s.entry_show = (int32_t*)p;
   return s;
+}
+
+static int g_force_slow = 0;  // tests: every tile through the slow path
+int csv_set_force_slow(int on) {
+  const int old = g_force_slow;
+  if (on >= 0) g_force_slow = on ? 1 : 0;
+  return old;
+}
+cudaError_t csv_read_slow_tiles(const void* scratch, int64_t n_entries, unsigned int* out, cudaStream_t stream) {
+  CsvScratch sc = carve_csv(const_cast<void*>(scratch), n_entries);
+  cudaError_t err = cudaMemcpyAsync(out, sc.slow_tiles, 4, cudaMemcpyDeviceToHost, stream);
+  if (err != cudaSuccess) return err;
+  return cudaStreamSynchronize(stream);
 }
 
 // show index of every entry (rows of show s are entry_offsets[s] .. entry_offsets[s+1])
@@ -91,7 +122,7 @@ __global__ void __launch_bounds__(256) expand_entry_show_kernel(pie_archive_view
   for (int e = v.entry_offsets[s]; e < v.entry_offsets[s + 1]; ++e) entry_show[e] = (int32_t)s;
 }
 
-// ---- word-wise scanning and copying -----------------------------------------------------------
+// ---- word-wise scanning ---------------------------------------------------------------------------
 // != 0 iff some byte of v is zero (exact as a boolean)
 __device__ __forceinline__ uint32_t zero_byte_flags(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
 
@@ -99,141 +130,7 @@ __device__ __forceinline__ uint32_t special_flags(uint32_t x) {  // " , \n \r   
   return zero_byte_flags(x ^ 0x22222222u) | zero_byte_flags(x ^ 0x2C2C2C2Cu) | zero_byte_flags(x ^ 0x0A0A0A0Au) |
          zero_byte_flags(x ^ 0x0D0D0D0Du);
 }
-
-// does s[0..n) contain a character that forces quoting?  Scans the ALIGNED words the cell touches.
-__device__ __forceinline__ bool has_special(const uint8_t* __restrict__ p, int n) {
-  if (n <= 0) return false;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
-  const uint32_t lead = static_cast<uint32_t>(a & 3);
-  const int nw = static_cast<int>((lead + n + 3) >> 2);  // aligned words that hold bytes of the cell
-  const uint32_t tail = (lead + n) & 3u;
-  uint32_t flags = 0;
-  for (int k = 0; k < nw; ++k) {
-    uint32_t x = __ldg(w + k);
-    if (k == 0) x &= 0xFFFFFFFFu << (8 * lead);             // bytes before the cell -> 0 (not special)
-    if (k == nw - 1 && tail) x &= (1u << (8 * tail)) - 1u;  // bytes after the cell  -> 0
-    flags |= special_flags(x);
-  }
-  return flags != 0;
-}
-
-// number of '"' in s[0..n), four bytes at a time over the aligned words the cell touches
-__device__ __forceinline__ uint32_t count_quotes(const uint8_t* __restrict__ p, int n) {
-  if (n <= 0) return 0;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
-  const uint32_t lead = static_cast<uint32_t>(a & 3);
-  const int nw = static_cast<int>((lead + n + 3) >> 2);
-  const uint32_t tail = (lead + n) & 3u;
-  uint32_t c = 0;
-  for (int k = 0; k < nw; ++k) {
-    uint32_t x = __ldg(w + k);
-    if (k == 0) x &= 0xFFFFFFFFu << (8 * lead);
-    if (k == nw - 1 && tail) x &= (1u << (8 * tail)) - 1u;
-    c += __popc(__vcmpeq4(x, 0x22222222u)) >> 3;  // 0xFF per byte equal to '"'
-  }
-  return c;
-}
-
-// Byte-stream writer: bytes are collected in a 64-bit accumulator and leave as aligned 32-bit stores.
-// A cell may start and end mid-word; the neighbouring bytes of those words belong to other cells,
-// which other threads write, so the first and the last partial word are stored byte by byte.
-struct StreamWriter {
-  uint8_t* p;  // aligned address of the next word to store
-  unsigned long long acc;
-  uint32_t fill;  // bytes pending in acc (including `lead` placeholders before the first flush)
-  uint32_t lead;  // placeholder bytes of the first word; 0 once the first word has been stored
-
-  __device__ __forceinline__ void init(uint8_t* start) {
-    lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(start) & 3);
-    p = start - lead;
-    acc = 0;
-    fill = lead;
-  }
-  __device__ __forceinline__ void flush_word() {
-    const uint32_t v = static_cast<uint32_t>(acc);
-    if (lead) {
-      for (uint32_t b = lead; b < 4; ++b) p[b] = static_cast<uint8_t>(v >> (8 * b));
-      lead = 0;
-    } else {
-      *reinterpret_cast<uint32_t*>(p) = v;
-    }
-    p += 4;
-    acc >>= 32;
-    fill -= 4;
-  }
-  // k (1..4) low bytes of w; the other bytes of w must be zero
-  __device__ __forceinline__ void append(uint32_t w, uint32_t k) {
-    acc |= static_cast<unsigned long long>(w) << (8 * fill);
-    fill += k;
-    if (fill >= 4) flush_word();
-  }
-  __device__ __forceinline__ void put(uint8_t c) { append(c, 1); }
-  __device__ __forceinline__ void finish() {
-    for (uint32_t b = lead; b < fill; ++b) p[b] = static_cast<uint8_t>(acc >> (8 * b));
-  }
-};
-
-// copy s[0..n) (no quoting needed) followed by the separator byte
-__device__ __forceinline__ void copy_plain(StreamWriter& out, const uint8_t* __restrict__ s, int n, uint8_t sep) {
-  if (n > 0) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-    const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
-    const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
-    const int last = static_cast<int>(((a & 3) + n - 1) >> 2);  // last aligned word holding cell bytes
-    uint32_t cur = __ldg(w);
-    int k = 0;
-    for (; n >= 4; n -= 4, ++k) {  // full words of the cell
-      const uint32_t nxt = (k + 1 <= last) ? __ldg(w + k + 1) : 0u;
-      out.append(__funnelshift_r(cur, nxt, sh), 4);
-      cur = nxt;
-    }
-    if (n > 0) {  // 1..3 trailing bytes; the separator rides in the same word
-      const uint32_t nxt = (k + 1 <= last) ? __ldg(w + k + 1) : 0u;
-      const uint32_t x = __funnelshift_r(cur, nxt, sh) & ((1u << (8 * n)) - 1u);
-      out.append(x | (static_cast<uint32_t>(sep) << (8 * n)), static_cast<uint32_t>(n) + 1);
-      return;
-    }
-  }
-  out.put(sep);
-}
-
-// csvEscape of a cell that needs quotes (rare): byte-wise
-__device__ __forceinline__ void copy_quoted_bytes(StreamWriter& out, const uint8_t* __restrict__ s, int n) {
-  if (n <= 0) return;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
-  const uint32_t sh = static_cast<uint32_t>(a & 3) * 8;
-  const int last = static_cast<int>(((a & 3) + n - 1) >> 2);
-  uint32_t cur = __ldg(w);
-  for (int k = 0; n > 0; n -= 4, ++k) {
-    const uint32_t nxt = (k + 1 <= last) ? __ldg(w + k + 1) : 0u;
-    const uint32_t m = n >= 4 ? 4u : static_cast<uint32_t>(n);
-    uint32_t x = __funnelshift_r(cur, nxt, sh);
-    if (m < 4) x &= (1u << (8 * m)) - 1u;
-    cur = nxt;
-    if (zero_byte_flags(x ^ 0x22222222u) == 0) {  // no '"' in these bytes: whole word at once
-      out.append(x, m);
-    } else {
-      for (uint32_t b = 0; b < m; ++b) {
-        const uint8_t c = static_cast<uint8_t>(x >> (8 * b));
-        if (c == '"') out.put('"');
-        out.put(c);
-      }
-    }
-  }
-}
-
-// entry.status === 'Completed' (strict, case-sensitive, :293-297) blanks the five issue cells
-__device__ __forceinline__ bool status_is_completed(const pie_archive_view& v, int64_t e) {
-  const int b = v.status.offsets[e], n = v.status.offsets[e + 1] - b;
-  if (n != 9) return false;
-  uint32_t x[3];
-  fetch_words_raw<3>(v.status.data + b, 9, x);
-  return x[0] == lit_word("Completed", 0) && x[1] == lit_word("Completed", 1) &&
-         (x[2] & 0xFFu) == lit_word("Completed", 2);
-}
+__device__ __forceinline__ bool is_special_byte(uint8_t c) { return c == '"' || c == ',' || c == '\n' || c == '\r'; }
 
 // The 24 cells of a row, in EXPORT_COLUMNS order (:15-19)
 enum : uint8_t { kCellString = 0, kCellJoined = 1, kCellNumber = 2 };
@@ -269,10 +166,11 @@ static RowTable make_row_table(const pie_archive_view& v) {
   t.cell[22] = str(v.command_rx, 1);  t.cell[23] = str(v.notes, 1);
   return t;
 }
+constexpr int kStatusCol = 12, kActionsCol = 18;
 
 // ---- pre-pass: which columns can need quoting at all? -----------------------------------------------
 // Most columns of an archive (ids, dates, enumerations, names) never contain " , \n or \r.  One
-// streaming pass over every column's byte heap (16 bytes per thread and step, HBM speed) sets a
+// streaming pass over every column's byte heap (a 128-bit load per thread and step) sets a
 // per-column flag; the row kernel then skips the per-cell scan for clean columns altogether.
 __global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant__ RowTable tab, int64_t n_shows,
                                                            int64_t n_entries, unsigned int* __restrict__ col_dirty) {
@@ -288,65 +186,289 @@ __global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant
   const int64_t b0 = d.offsets[first], b1 = d.offsets[last];
   if (b1 <= b0) return;
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(d.data + b0), a1 = reinterpret_cast<uintptr_t>(d.data + b1);
-  const uintptr_t w0 = a0 & ~static_cast<uintptr_t>(15), w1 = (a1 + 15) & ~static_cast<uintptr_t>(15);
-  const int64_t chunks = static_cast<int64_t>((w1 - w0) >> 4);
+  const uintptr_t w0 = (a0 + 15) & ~static_cast<uintptr_t>(15), w1 = a1 & ~static_cast<uintptr_t>(15);
   uint32_t flags = 0;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (int64_t)gridDim.x * blockDim.x) {
-    const uintptr_t a = w0 + 16 * (uintptr_t)c;
-    // Only words that hold heap bytes are loaded; the edge words are masked to the heap's bytes.
-    uint32_t x[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uintptr_t wa = a + 4 * k;
-      uint32_t v = 0;
-      if (wa + 4 > a0 && wa < a1) {
-        v = __ldg(reinterpret_cast<const uint32_t*>(wa));
-        if (wa < a0) v &= 0xFFFFFFFFu << (8 * (uint32_t)(a0 - wa));
-        if (wa + 4 > a1) v &= (1u << (8 * (uint32_t)(a1 - wa))) - 1u;
-      }
-      x[k] = v;
+  if (w1 > w0) {  // full 16-byte chunks inside the heap
+    const int64_t chunks = static_cast<int64_t>((w1 - w0) >> 4);
+    const uint4* __restrict__ p = reinterpret_cast<const uint4*>(w0);
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (int64_t)gridDim.x * blockDim.x) {
+      const uint4 x = __ldg(p + c);
+      flags |= special_flags(x.x) | special_flags(x.y) | special_flags(x.z) | special_flags(x.w);
     }
-    flags |= special_flags(x[0]) | special_flags(x[1]) | special_flags(x[2]) | special_flags(x[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {  // the < 16 bytes at either end (or a heap shorter than a chunk)
+    const uintptr_t head_end = (w1 > w0) ? w0 : a1, tail_begin = (w1 > w0) ? w1 : a1;
+    for (uintptr_t a = a0 + threadIdx.x; a < head_end; a += 32) flags |= is_special_byte(*reinterpret_cast<const uint8_t*>(a));
+    for (uintptr_t a = tail_begin + threadIdx.x; a < a1; a += 32) flags |= is_special_byte(*reinterpret_cast<const uint8_t*>(a));
   }
   if (__any_sync(0xFFFFFFFFu, flags != 0) && (threadIdx.x & 31) == 0) atomicOr(&col_dirty[col], 1u);
 }
 
-// ---- the kernel ---------------------------------------------------------------------------------
-// Work item = (row, group of kGroupCols consecutive columns); thread tid owns row tid % kRows, group
-// tid / kRows, in BOTH the measuring and the writing phase, so the quote flags stay in registers and
-// one byte-stream writer emits the whole group (byte stores only at the group's two ends).  A warp =
-// one group x 32 consecutive rows: it walks the same column at the same time.
-constexpr int kGroups = 4;
-constexpr int kGroupCols = kCols / kGroups;   // 6
-constexpr int kWorkers = kRows * kGroups;     // 512 worker threads ...
-constexpr int kCtaThreads = kWorkers + 32;    // ... + one warp that runs the decoupled look-back
-static_assert(kGroups * kGroupCols == kCols && kThreads == kWorkers, "tile shape");
-constexpr uint32_t kCompletedBit = 1u << 31;
+// ---- PTX: mbarrier + 1-D TMA bulk copy ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PIE_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PIE_DONE;\n"
+      "bra PIE_WAIT;\n"
+      "PIE_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared, 16-byte aligned on both sides, bytes a multiple of 16; completion on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
+// ---- shared-memory state of a tile ----------------------------------------------------------------
 struct CsvSmem {
-  uint32_t group[kGroups][kRows];  // phase 1: bytes of the group (with its separators); phase 2: start in the row
-  uint32_t row_start[kRows];       // byte offset of the row inside the tile
-  char num[kRows][kMaxNumberChars];
-  uint8_t num_len[kRows];
-  uint32_t warp_sum[kRows / 32];
+  unsigned long long mbar;
+  unsigned long long base;                      // global byte offset of the tile (look-back result)
+  uint32_t cell[kRows * kCellStride];           // (src:16 | len:16 << 16) of cell (r, c) at r*kCellStride + c
+  uint32_t shcell[kShowCols][kMaxTileShows];    // the same for the show-level cells of the tile's shows
+  uint32_t first[kWorkers];                     // chunk k starts inside cell (idx:12) at byte (skip << 12)
+  uint32_t group[kGroups][kRows];               // bytes of a row's group, then its start inside the row
+  uint32_t row_start[kRows];                    // byte offset of the row inside the tile
+  uint32_t delta[kCols];                        // staged address of heap byte b of column c = delta[c] + b
   uint32_t col_dirty[kCols];
+  uint32_t warp_sum[kRows / 32];
   uint32_t tile_total;
+  uint32_t bump;                                // next free byte of the bump area
+  uint32_t slow;                                // != 0: the tile does not fit the fast path
+  int32_t show0;                                // first show of the tile
+  uint32_t n_tile_shows;
   unsigned int tile_id;
-  unsigned long long base;
+  uint8_t num_len[kRows];
 };
+constexpr int kSmemOffIn = kOutBytes + 32;
+constexpr int kSmemOffState = kSmemOffIn + kInBytes + kNumBytes + 16;
+constexpr int kSmemBytes = kSmemOffState + (int)sizeof(CsvSmem);
+static_assert(kSmemOffIn % 16 == 0 && kSmemOffState % 8 == 0, "smem carve-up");
 
-__global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS) csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab,
-                                                                  CsvScratch sc, int64_t* __restrict__ row_offsets,
-                                                                  uint8_t* __restrict__ out_data, uint64_t capacity,
-                                                                  unsigned long long bias,
-                                                                  unsigned long long* __restrict__ total_out) {
-  extern __shared__ __align__(16) uint8_t s_dyn[];
-  uint8_t* s_tile = s_dyn;                                               // kTileBytes + 32
-  CsvSmem& sm = *reinterpret_cast<CsvSmem*>(s_dyn + kTileBytes + 32);
+__device__ __forceinline__ uint32_t pack_cell(uint32_t src, uint32_t len) { return (src & 0xFFFFu) | (len << 16); }
+
+// does s_in[src .. src+n) contain a character that forces quoting?  Aligned words, ends masked.
+__device__ __forceinline__ bool smem_has_special(const uint8_t* s_in, uint32_t src, uint32_t n) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + (src & ~3u));
+  const uint32_t lead = src & 3u;
+  const int nw = static_cast<int>((lead + n + 3) >> 2);
+  const uint32_t tail = (lead + n) & 3u;
+  uint32_t flags = 0;
+  for (int k = 0; k < nw; ++k) {
+    uint32_t x = w[k];
+    if (k == 0) x &= 0xFFFFFFFFu << (8 * lead);
+    if (k == nw - 1 && tail) x &= (1u << (8 * tail)) - 1u;
+    flags |= special_flags(x);
+  }
+  return flags != 0;
+}
+
+// Rare path: a cell that needs csvEscape (:332-338) and / or Array.prototype.join('|') (:284, :298) is
+// written out in the bump area.  s_in[src .. src+n) = the cell's staged bytes (for a list: all its
+// items, which are contiguous in the heap); items > 1 inserts '|' at the item boundaries, which are
+// item_offsets[l0+1 ..] in heap coordinates (+ delta = staged).
+__device__ __noinline__ uint32_t materialise_cell(CsvSmem& sm, uint8_t* s_in, const int32_t* __restrict__ item_offsets,
+                                                  uint32_t delta, bool dirty, uint32_t src, uint32_t n, int l0, int items) {
+  const bool special = dirty && n > 0 && smem_has_special(s_in, src, n);
+  if (!special && items <= 1) return pack_cell(src, n);
+  uint32_t nq = 0;
+  if (special)
+    for (uint32_t j = 0; j < n; ++j) nq += (s_in[src + j] == '"');
+  const uint32_t out_len = n + (items > 1 ? (uint32_t)(items - 1) : 0u) + (special ? 2u + nq : 0u);
+  const uint32_t p = atomicAdd(&sm.bump, out_len);
+  if (p + out_len > (uint32_t)kInBytes) {
+    sm.slow = 1;  // benign race: every writer stores 1
+    return 0;
+  }
+  uint32_t q = p;
+  if (special) s_in[q++] = '"';
+  uint32_t ib = src;
+  for (int it = 0; it < items; ++it) {
+    const uint32_t ie = (it + 1 < items) ? delta + (uint32_t)item_offsets[l0 + it + 1] : src + n;
+    for (uint32_t j = ib; j < ie; ++j) {
+      const uint8_t c = s_in[j];
+      if (special && c == '"') s_in[q++] = '"';
+      s_in[q++] = c;
+    }
+    if (it + 1 < items) s_in[q++] = '|';
+    ib = ie;
+  }
+  if (special) s_in[q++] = '"';
+  return pack_cell(p, out_len);
+}
+
+// ---- slow path: a warp per row, lanes stride over the bytes of a cell, global -> global ------------
+struct SlowCell {
+  const uint8_t* p;  // cell bytes in the heap (for a list: all items, contiguous)
+  int n;
+  int l0, items;     // list items (items == 1 for strings)
+};
+__device__ __forceinline__ SlowCell slow_locate(const CellDesc& d, int64_t i) {
+  SlowCell c{nullptr, 0, 0, 1};
+  if (d.kind == kCellString) {
+    const int b = d.offsets[i];
+    c.p = d.data + b;
+    c.n = d.offsets[i + 1] - b;
+  } else if (d.kind == kCellJoined) {
+    c.l0 = d.list_offsets[i];
+    c.items = d.list_offsets[i + 1] - c.l0;
+    if (c.items > 0) {
+      const int b = d.offsets[c.l0];
+      c.p = d.data + b;
+      c.n = d.offsets[c.l0 + c.items] - b;
+    }
+  }
+  return c;
+}
+
+// Row lengths (sm.group[0][r]) and per-row quote masks (bit c: cell c is quoted; bit 31: Completed).
+__device__ __noinline__ void slow_measure(const pie_archive_view& v, const RowTable& tab, const CsvScratch& sc,
+                                          CsvSmem& sm, char* s_num, uint32_t* qmask, int64_t e0, int rows) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int r = wid; r < rows; r += kCtaWarps) {
+    const int64_t e = e0 + r;
+    const int64_t show = sc.entry_show[e];
+    bool completed = false;
+    {
+      const SlowCell st = slow_locate(tab.cell[kStatusCol], e);
+      completed = equals_exact(st.p, st.n, "Completed");
+    }
+    uint32_t len = 0, qm = 0;
+    for (int col = 0; col < kCols; ++col) {
+      const CellDesc& d = tab.cell[col];
+      uint32_t cl = 0;
+      if (d.kind == kCellNumber) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
+        int nl = 0;
+        if (lane == 0 && v.delay_valid[e]) {
+          const RyuTables t{d_pow5_inv, d_pow5};
+          nl = js_number_to_string(v.delay_sec[e], s_num + r * kMaxNumberChars, t);
+        }
+        nl = __shfl_sync(0xFFFFFFFFu, nl, 0);
+        if (lane == 0) sm.num_len[r] = (uint8_t)nl;
+        cl = (uint32_t)nl;
+      } else if (!(d.blank_if_completed && completed)) {
+        const SlowCell c = slow_locate(d, d.per_entry ? e : show);
+        uint32_t sp = 0, nq = 0;
+        for (int j = lane; j < c.n; j += 32) {
+          const uint8_t ch = c.p[j];
+          sp |= is_special_byte(ch);
+          nq += (ch == '"');
+        }
+        cl = (uint32_t)c.n + (c.items > 1 ? (uint32_t)(c.items - 1) : 0u);
+        if (__any_sync(0xFFFFFFFFu, sp)) {
+          cl += 2u + __reduce_add_sync(0xFFFFFFFFu, nq);
+          qm |= 1u << col;
+        }
+      }
+      len += cl + 1u;
+    }
+    if (lane == 0) {
+      sm.group[0][r] = len;
+      qmask[r] = qm | (completed ? 1u << 31 : 0u);
+    }
+  }
+}
+
+__device__ __forceinline__ void slow_copy(uint8_t* __restrict__ dst, uint32_t& pos, const uint8_t* __restrict__ s, int n,
+                                          bool quote, int lane) {
+  if (!quote) {
+    for (int j = lane; j < n; j += 32) dst[pos + j] = s[j];
+    pos += (uint32_t)n;
+    return;
+  }
+  for (int j0 = 0; j0 < n; j0 += 32) {  // '"' doubled: positions from a ballot prefix
+    const int j = j0 + lane;
+    const uint8_t ch = j < n ? s[j] : 0;
+    const bool isq = j < n && ch == '"';
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, isq);
+    const uint32_t at = pos + (uint32_t)lane + __popc(m & ((1u << lane) - 1u));
+    if (j < n) {
+      dst[at] = ch;
+      if (isq) dst[at + 1] = '"';
+    }
+    pos += (uint32_t)min(32, n - j0) + __popc(m);
+  }
+}
+
+__device__ __noinline__ void slow_write(const RowTable& tab, const CsvScratch& sc, CsvSmem& sm, const char* s_num,
+                                        const uint32_t* qmask, int64_t e0, int rows, uint8_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int r = wid; r < rows; r += kCtaWarps) {
+    const int64_t e = e0 + r;
+    const int64_t show = sc.entry_show[e];
+    const uint32_t qm = qmask[r];
+    const bool completed = (qm >> 31) != 0;
+    uint8_t* dst = out + sm.row_start[r];
+    uint32_t pos = 0;
+    for (int col = 0; col < kCols; ++col) {
+      const CellDesc& d = tab.cell[col];
+      const uint8_t sep = (col == kCols - 1) ? (uint8_t)'\n' : (uint8_t)',';
+      if (d.kind == kCellNumber) {
+        const int nl = sm.num_len[r];
+        if (lane < nl) dst[pos + lane] = (uint8_t)s_num[r * kMaxNumberChars + lane];
+        pos += (uint32_t)nl;
+      } else if (!(d.blank_if_completed && completed)) {
+        const SlowCell c = slow_locate(d, d.per_entry ? e : show);
+        const bool quote = (qm >> col) & 1u;
+        if (quote) {
+          if (lane == 0) dst[pos] = '"';
+          ++pos;
+        }
+        if (c.items <= 1) {
+          slow_copy(dst, pos, c.p, c.n, quote, lane);
+        } else {
+          for (int it = 0; it < c.items; ++it) {
+            const int b = d.offsets[c.l0 + it], n = d.offsets[c.l0 + it + 1] - b;
+            slow_copy(dst, pos, d.data + b, n, quote, lane);
+            if (it + 1 < c.items) {
+              if (lane == 0) dst[pos] = '|';
+              ++pos;
+            }
+          }
+        }
+        if (quote) {
+          if (lane == 0) dst[pos] = '"';
+          ++pos;
+        }
+      }
+      if (lane == 0) dst[pos] = sep;
+      ++pos;
+    }
+  }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
+    csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab, CsvScratch sc,
+                    int64_t* __restrict__ row_offsets, uint8_t* __restrict__ out_data, uint64_t capacity,
+                    unsigned long long bias, unsigned long long* __restrict__ total_out, int force_slow) {
+  extern __shared__ __align__(128) uint8_t s_dyn[];
+  uint8_t* s_out = s_dyn;                                  // kOutBytes + 32
+  uint8_t* s_in = s_dyn + kSmemOffIn;                      // kInBytes: staged bytes, then the bump area ...
+  char* s_num = reinterpret_cast<char*>(s_in + kInBytes);  // ... then Number::toString output, kNumBytes (+16 slack)
+  CsvSmem& sm = *reinterpret_cast<CsvSmem*>(s_dyn + kSmemOffState);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool worker = tid < kWorkers;
+  const uint32_t bar = smem_u32(&sm.mbar);
 
-  if (tid == 0) sm.tile_id = atomicAdd(sc.tile_counter, 1u);  // tiles start in id order: look-back cannot deadlock
+  if (tid == 0) {
+    sm.tile_id = atomicAdd(sc.tile_counter, 1u);  // tiles start in id order: look-back cannot deadlock
+    sm.slow = (uint32_t)force_slow;
+    mbar_init(bar, 1);
+  }
   if (tid < kCols) sm.col_dirty[tid] = sc.col_dirty[tid];
   __syncthreads();
   const int64_t tile = sm.tile_id;
@@ -355,24 +477,78 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS) csv_rows_kern
   const int g = tid / kRows, r = tid % kRows;
   const bool have = worker && r < rows;
   const int64_t e = e0 + r;
-  const int64_t show = (have && g < 2) ? sc.entry_show[e] : 0;  // groups 0-1 hold the show-level columns 0..7
 
-  // ---- 1a. locate the group's cells: every offset load is issued before any is consumed (a tile is
-  // latency-bound: per column a dependent chain offsets -> bytes; walking 6 columns one after the
-  // other cost 6 such chains per phase)
-  int cb[kGroupCols], cn[kGroupCols], citems[kGroupCols];
-  {
+  // ---- A. stage.  Producer warp: column ranges -> smem layout -> TMA; workers: offsets + numbers.
+  int cb[kGroupCols], cn[kGroupCols];  // workers: heap range of the group's entry-level cells
+  int jl0 = 0, jitems = 1;             // actions (the one entry-level list column): first item, item count
+  int show = 0;
+  if (!worker) {
+    const int32_t s0 = sc.entry_show[e0], s1 = sc.entry_show[e0 + rows - 1];
+    uint32_t b0 = 0, b1 = 0;
+    const uint8_t* data = nullptr;
+    if (lane < kCols && tab.cell[lane].kind != kCellNumber) {
+      const CellDesc& d = tab.cell[lane];
+      int64_t i0 = d.per_entry ? e0 : (int64_t)s0, i1 = d.per_entry ? e0 + rows : (int64_t)s1 + 1;
+      if (d.kind == kCellJoined) {
+        i0 = d.list_offsets[i0];
+        i1 = d.list_offsets[i1];
+      }
+      b0 = (uint32_t)d.offsets[i0];
+      b1 = (uint32_t)d.offsets[i1];
+      data = d.data;
+    }
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(data) + b0, a1 = reinterpret_cast<uintptr_t>(data) + b1;
+    const uintptr_t lo = a0 & ~static_cast<uintptr_t>(15);  // >= heap start: heaps are 16-byte aligned
+    const uintptr_t hi = a1 & ~static_cast<uintptr_t>(15);  // full chunks only; the tail goes by hand
+    const uint32_t bulk = (b1 > b0 && hi > lo) ? (uint32_t)(hi - lo) : 0u;
+    const uint32_t span = (b1 > b0) ? (uint32_t)(((a1 + 15) & ~static_cast<uintptr_t>(15)) - lo) : 0u;
+    uint32_t incl = span;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t region = incl - span;
+    const uint32_t in_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t bulk_total = bulk;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) bulk_total += __shfl_xor_sync(0xFFFFFFFFu, bulk_total, o);
+    const bool fits = in_total <= (uint32_t)kInBytes && (s1 - s0) < kMaxTileShows && !force_slow;
+    if (lane == 0) {
+      sm.bump = in_total;
+      sm.show0 = s0;
+      sm.n_tile_shows = (uint32_t)(s1 - s0 + 1);
+      if (!fits) sm.slow = 1;
+      mbar_arrive_expect_tx(bar, fits ? bulk_total : 0u);
+    }
+    __syncwarp();
+    if (lane < kCols) sm.delta[lane] = region + (uint32_t)(a0 - lo) - b0;
+    if (fits && span) {
+      if (bulk) tma_bulk_g2s(smem_u32(s_in + region), reinterpret_cast<const void*>(lo), bulk, bar);
+      // The range's last, partial chunk (or a range inside one chunk): the <= 4 aligned words that
+      // hold bytes of it — never a word past the heap's last byte.
+      const uintptr_t t0 = bulk ? hi : (a0 & ~static_cast<uintptr_t>(3));
+      uint32_t x[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = (t0 + 4 * k < a1) ? __ldg(reinterpret_cast<const uint32_t*>(t0) + k) : 0u;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(s_in + region + (uint32_t)(t0 - lo));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t0 + 4 * k < a1) dst[k] = x[k];
+    }
+  } else if (have) {
+    if (g < 2) show = sc.entry_show[e];
+    // every offset load of the group is issued before any is consumed
     int a0[kGroupCols], a1[kGroupCols];
 #pragma unroll
     for (int k = 0; k < kGroupCols; ++k) {
       const CellDesc& d = tab.cell[g * kGroupCols + k];
-      const int64_t i = d.per_entry ? e : show;
-      const int32_t* __restrict__ p = (d.kind == kCellJoined) ? d.list_offsets : d.offsets;
       a0[k] = 0;
       a1[k] = 0;
-      if (have && d.kind != kCellNumber) {
-        a0[k] = p[i];
-        a1[k] = p[i + 1];
+      if (d.per_entry && d.kind != kCellNumber) {
+        const int32_t* __restrict__ p = (d.kind == kCellJoined) ? d.list_offsets : d.offsets;
+        a0[k] = p[e];
+        a1[k] = p[e + 1];
       }
     }
 #pragma unroll
@@ -380,99 +556,34 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS) csv_rows_kern
       const CellDesc& d = tab.cell[g * kGroupCols + k];
       cb[k] = a0[k];
       cn[k] = a1[k] - a0[k];
-      citems[k] = 1;
-      if (d.kind == kCellJoined) {  // Array.prototype.join('|') (crew :284, actions :298): items are contiguous
-        citems[k] = cn[k];
+      if (d.per_entry && d.kind == kCellJoined) {  // items are contiguous in the heap
+        jl0 = a0[k];
+        jitems = a1[k] - a0[k];
         cb[k] = 0;
         cn[k] = 0;
-        if (have && citems[k] > 0) {
+        if (jitems > 0) {
           cb[k] = d.offsets[a0[k]];
           cn[k] = d.offsets[a1[k]] - cb[k];
         }
       }
     }
-  }
-
-  // ---- 1b. measure the group
-  uint32_t glen = 0, qmask = 0;
-  if (have) {
-    bool completed = false;  // entry.status === 'Completed' (:293-297); status is column 12 = group 2, k = 0
-    if (g == 2 && cn[0] == 9) {
-      uint32_t x[3];
-      fetch_words_raw<3>(tab.cell[12].data + cb[0], 9, x);
-      completed = x[0] == lit_word("Completed", 0) && x[1] == lit_word("Completed", 1) &&
-                  (x[2] & 0xFFu) == lit_word("Completed", 2);
-    }
-    if (completed) qmask |= kCompletedBit;
-#pragma unroll 1  // generic body (unrolled it is specialised per column: 28k instructions, icache-bound)
-    for (int k = 0; k < kGroupCols; ++k) {
-      const int col = g * kGroupCols + k;
-      const CellDesc& d = tab.cell[col];
-      uint32_t len = 0;
-      if (d.kind == kCellNumber) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
-        int nl = 0;
-        if (v.delay_valid[e]) {
-          const RyuTables t{d_pow5_inv, d_pow5};
-          nl = js_number_to_string(v.delay_sec[e], sm.num[r], t);
-        }
-        sm.num_len[r] = (uint8_t)nl;
-        len = (uint32_t)nl;
-      } else if (!(d.blank_if_completed && completed)) {
-        len = (uint32_t)cn[k] + (citems[k] > 1 ? (uint32_t)(citems[k] - 1) : 0u);  // '|' between items: not special
-        if (sm.col_dirty[col] && has_special(d.data + cb[k], cn[k])) {  // csvEscape (:332-338)
-          qmask |= 1u << k;
-          len += 2u + count_quotes(d.data + cb[k], cn[k]);
-        }
+    if (g == 3) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
+      int nl = 0;
+      if (v.delay_valid[e]) {
+        const RyuTables t{d_pow5_inv, d_pow5};
+        nl = js_number_to_string(v.delay_sec[e], s_num + r * kMaxNumberChars, t);
       }
-      glen += len + 1u;  // + ',' (or the final '\n')
+      sm.num_len[r] = (uint8_t)nl;
     }
   }
-  if (worker) sm.group[g][r] = glen;
   __syncthreads();
 
-  // ---- 2. per-row scan over the groups, then block scan over the rows
-  uint32_t row_len = 0;
-  if (tid < kRows) {
-    if (tid < rows) {
-      uint32_t run = 0;
-#pragma unroll
-      for (int k = 0; k < kGroups; ++k) {
-        const uint32_t x = sm.group[k][tid];
-        sm.group[k][tid] = run;
-        run += x;
-      }
-      row_len = run;
-    }
-    uint32_t incl = row_len;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) sm.warp_sum[wid] = incl;
-    sm.row_start[tid] = incl - row_len;  // completed below with the preceding warps' sums
-  }
-  __syncthreads();
-  if (tid < kRows) {
-    uint32_t before = 0;
-    for (int w = 0; w < wid; ++w) before += sm.warp_sum[w];
-    sm.row_start[tid] += before;
-    if (tid == kRows - 1) {
-      const uint32_t total = sm.row_start[tid] + row_len;
-      sm.tile_total = total;
-      __threadfence();
-      reinterpret_cast<volatile unsigned long long*>(sc.tile_state)[tile] =
-          (tile == 0 ? kPrefix : kAggregate) | (unsigned long long)total;  // published for later tiles
-    }
-  }
-  __syncthreads();
-  const uint32_t tile_total = sm.tile_total;
   const bool write = out_data != nullptr;
-  const bool staged = tile_total <= (uint32_t)kTileBytes;
+  uint32_t* qmask = sm.first;  // slow path: per-row quote masks live in the chunk table
+  bool slow = sm.slow != 0;    // uniform
 
-  // ---- 4. decoupled look-back, by the extra warp — WHILE the workers write the cells of a staged
-  // tile (step 3 does not need the offset); before step 3 when the tile goes straight to global memory.
-  auto look_back = [&]() {
+  // Decoupled look-back over the tile totals, by the producer warp.
+  auto look_back = [&](uint32_t tile_total) {
     volatile unsigned long long* state = sc.tile_state;
     unsigned long long exclusive = 0;
     int64_t idx = tile - 1;
@@ -508,80 +619,244 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS) csv_rows_kern
       }
     }
   };
-  const bool overlap = write && staged;
-  if (!overlap) {
-    if (!worker) look_back();
+  // rows' lengths in sm.group[0][*] -> sm.row_start, sm.tile_total; the aggregate is published
+  auto scan_rows_and_publish = [&]() {
+    uint32_t row_len = 0;
+    if (tid < kRows) {
+      if (tid < rows) row_len = sm.group[0][tid];
+      uint32_t incl = row_len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) sm.warp_sum[wid] = incl;
+      sm.row_start[tid] = incl - row_len;  // completed below with the preceding warps' sums
+    }
     __syncthreads();
+    if (tid < kRows) {
+      uint32_t before = 0;
+      for (int w = 0; w < wid; ++w) before += sm.warp_sum[w];
+      sm.row_start[tid] += before;
+      if (tid == kRows - 1) {
+        const uint32_t total = sm.row_start[tid] + row_len;
+        sm.tile_total = total;
+        __threadfence();
+        reinterpret_cast<volatile unsigned long long*>(sc.tile_state)[tile] =
+            (tile == 0 ? kPrefix : kAggregate) | (unsigned long long)total;  // published for later tiles
+      }
+    }
+    __syncthreads();
+  };
+
+  bool published = false;
+  if (!slow) {
+    mbar_wait(bar, 0);  // the staged bytes have landed
+
+    // ---- B1. show-level cells, once per show of the tile
+    {
+      const uint32_t ns = sm.n_tile_shows;
+      for (uint32_t idx = tid; idx < ns * kShowCols; idx += kCtaThreads) {
+        const uint32_t col = idx / ns, i = idx - col * ns;
+        const CellDesc& d = tab.cell[col];
+        const int64_t s = (int64_t)sm.show0 + i;
+        int l0 = 0, items = 1;
+        uint32_t b = 0, n = 0;
+        if (d.kind == kCellJoined) {  // crew
+          l0 = d.list_offsets[s];
+          items = d.list_offsets[s + 1] - l0;
+          if (items > 0) {
+            b = (uint32_t)d.offsets[l0];
+            n = (uint32_t)d.offsets[l0 + items] - b;
+          }
+        } else {
+          b = (uint32_t)d.offsets[s];
+          n = (uint32_t)d.offsets[s + 1] - b;
+        }
+        const uint32_t src = (sm.delta[col] + b) & 0xFFFFu;
+        uint32_t c = pack_cell(src, n);
+        if ((sm.col_dirty[col] && n) || items > 1)
+          c = materialise_cell(sm, s_in, d.offsets, sm.delta[col], sm.col_dirty[col] != 0, src, n, l0, items);
+        sm.shcell[col][i] = c;
+      }
+    }
+    __syncthreads();
+
+    // ---- B2. the group's cells
+    if (have) {
+      bool completed = false;  // entry.status === 'Completed' (:293-297); status = first cell of group 2
+      if (g == 2 && cn[0] == 9) {
+        const uint32_t src = (sm.delta[kStatusCol] + (uint32_t)cb[0]) & 0xFFFFu;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + (src & ~3u));
+        const uint32_t sh = (src & 3u) * 8u;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];  // the 9 bytes lie inside these three words
+        completed = __funnelshift_r(w0, w1, sh) == lit_word("Completed", 0) &&
+                    __funnelshift_r(w1, w2, sh) == lit_word("Completed", 1) &&
+                    (__funnelshift_r(w2, 0u, sh) & 0xFFu) == lit_word("Completed", 2);
+      }
+      uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
+      const int show_i = show - sm.show0;
+#pragma unroll
+      for (int k = 0; k < kGroupCols; ++k) {
+        const int col = g * kGroupCols + k;
+        const CellDesc& d = tab.cell[col];
+        uint32_t c;
+        if (!d.per_entry) c = sm.shcell[col][show_i];
+        else if (d.kind == kCellNumber) c = pack_cell((uint32_t)kInBytes + (uint32_t)(r * kMaxNumberChars), sm.num_len[r]);
+        else if (d.blank_if_completed && completed) c = 0;
+        else c = pack_cell(sm.delta[col] + (uint32_t)cb[k], (uint32_t)cn[k]);
+        row_cells[k] = c;
+      }
+      uint32_t glen = 0;
+#pragma unroll 1
+      for (int k = 0; k < kGroupCols; ++k) {
+        const int col = g * kGroupCols + k;
+        const CellDesc& d = tab.cell[col];
+        uint32_t c = row_cells[k];
+        const int items = (col == kActionsCol) ? jitems : 1;
+        if (d.per_entry && d.kind != kCellNumber && ((sm.col_dirty[col] && (c >> 16)) || items > 1)) {
+          c = materialise_cell(sm, s_in, d.offsets, sm.delta[col], sm.col_dirty[col] != 0, c & 0xFFFFu, c >> 16, jl0,
+                               items);
+          row_cells[k] = c;
+        }
+        glen += (c >> 16) + 1u;  // + ',' (or the final '\n')
+      }
+      sm.group[g][r] = glen;
+    }
+    __syncthreads();
+    slow = sm.slow != 0;  // the bump area overflowed
+    if (!slow) {
+      // ---- C. per-row scan over the groups, then block scan over the rows
+      if (tid < rows) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < kGroups; ++k) {
+          const uint32_t x = sm.group[k][tid];
+          sm.group[k][tid] = run;
+          run += x;
+        }
+        sm.group[0][tid] = run;  // group 0 starts at 0: the slot carries the row length into the scan
+      }
+      __syncthreads();
+      scan_rows_and_publish();
+      published = true;
+      if (write && sm.tile_total > (uint32_t)kOutBytes) slow = true;  // uniform
+    }
   }
+
+  if (slow) {
+    // ---- slow path (uniform for the CTA).  If the fast path already published this tile's total, the
+    // measure below recomputes the same row lengths; only the quote masks are new.
+    if (tid == 0) atomicAdd(sc.slow_tiles, 1u);
+    slow_measure(v, tab, sc, sm, s_num, qmask, e0, rows);
+    __syncthreads();
+    if (!published) scan_rows_and_publish();
+    if (!worker) look_back(sm.tile_total);
+    __syncthreads();
+    const unsigned long long base = sm.base;
+    if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + base + sm.row_start[tid]);
+    if (!write || base + sm.tile_total > capacity) return;
+    slow_write(tab, sc, sm, s_num, qmask, e0, rows, out_data + base);
+    return;
+  }
+
+  const uint32_t tile_total = sm.tile_total;
   if (!write) {
+    if (!worker) look_back(tile_total);
+    __syncthreads();
     if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + sm.base + sm.row_start[tid]);
     return;
   }
-  const bool fits = staged || (sm.base + tile_total <= capacity);  // direct writes respect the caller's capacity
 
-  // ---- 3. write the group
+  // ---- D. write.  chunk = bytes per thread (multiple of 16); x / chunk by multiplication.
   if (!worker) {
-    if (overlap) look_back();
-  } else if (have && fits) {
-    StreamWriter out;
-    out.init((staged ? s_tile : (out_data + sm.base)) + sm.row_start[r] + sm.group[g][r]);
-    const bool completed = (qmask & kCompletedBit) != 0;
-#pragma unroll 1
-    for (int k = 0; k < kGroupCols; ++k) {
-      const int col = g * kGroupCols + k;
-      const CellDesc& d = tab.cell[col];
-      const uint8_t sep = (col == kCols - 1) ? (uint8_t)'\n' : (uint8_t)',';
-      const bool quote = (qmask >> k) & 1u;
-      if (d.kind == kCellNumber) {
-        const int nl = sm.num_len[r];
-        for (int j = 0; j < nl; ++j) out.put((uint8_t)sm.num[r][j]);
-        out.put(sep);
-      } else if (d.blank_if_completed && completed) {
-        out.put(sep);
-      } else if (d.kind == kCellString) {
-        if (!quote) {
-          copy_plain(out, d.data + cb[k], cn[k], sep);
-        } else {
-          out.put('"');
-          copy_quoted_bytes(out, d.data + cb[k], cn[k]);
-          out.put('"');
-          out.put(sep);
-        }
-      } else {
-        const int64_t i = d.per_entry ? e : show;
-        const int l0 = citems[k] > 0 ? d.list_offsets[i] : 0, l1 = l0 + citems[k];
-        if (quote) out.put('"');
-        for (int l = l0; l < l1; ++l) {
-          const int b = d.offsets[l], n = d.offsets[l + 1] - b;
-          const bool last_item = (l + 1 == l1);
-          if (quote) {
-            copy_quoted_bytes(out, d.data + b, n);
-            if (!last_item) out.put('|');
-          } else {
-            copy_plain(out, d.data + b, n, last_item ? sep : (uint8_t)'|');
-          }
-        }
-        if (quote) out.put('"');
-        if (quote || l1 <= l0) out.put(sep);
+    look_back(tile_total);
+  } else {
+    const uint32_t chunk = 16u * ((tile_total + 16u * kWorkers - 1u) / (16u * kWorkers));
+    const uint32_t magic = (uint32_t)((0x100000000ull + chunk - 1u) / chunk);  // exact for x < 2^16
+    if (have) {
+      uint32_t o = sm.row_start[r] + (g ? sm.group[g][r] : 0u);
+      const uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
+#pragma unroll
+      for (int k = 0; k < kGroupCols; ++k) {
+        const uint32_t len = row_cells[k] >> 16;
+        const uint32_t k_lo = __umulhi(o + chunk - 1u, magic), k_hi = __umulhi(o + len, magic);
+        for (uint32_t kk = k_lo; kk <= k_hi; ++kk)  // chunk kk starts inside this cell (or on its separator)
+          sm.first[kk] = (uint32_t)(r * kCellStride + g * kGroupCols + k) | ((kk * chunk - o) << 12);
+        o += len + 1u;
       }
     }
-    out.finish();
+    asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");  // workers only; the producer warp is looking back
+    const uint32_t begin = (uint32_t)tid * chunk;
+    if (begin < tile_total) {
+      uint32_t rem = min(chunk, tile_total - begin);  // bytes this thread produces
+      uint32_t* op = reinterpret_cast<uint32_t*>(s_out + begin);
+      const uint32_t f = sm.first[tid];
+      uint32_t idx = f & 0xFFFu, skip = f >> 12;
+      uint32_t c = idx % kCellStride;
+      unsigned long long acc = 0;
+      uint32_t fill = 0;  // bytes pending in acc: 0..3
+      for (;;) {
+        const uint32_t cell = sm.cell[idx];
+        const uint32_t src = (cell & 0xFFFFu) + skip;
+        uint32_t n = (cell >> 16) - skip;
+        skip = 0;
+        const uint32_t sep = (c == kCols - 1) ? (uint32_t)'\n' : (uint32_t)',';
+        const bool cut = n >= rem;  // the chunk ends inside this cell (its separator opens the next chunk)
+        if (cut) n = rem;
+        rem -= n;
+        if (n > 0) {
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + (src & ~3u));
+          const uint32_t sh = (src & 3u) * 8u;
+          uint32_t cur = *w;
+          for (; n >= 4; n -= 4) {
+            const uint32_t nxt = *++w;
+            acc |= static_cast<unsigned long long>(__funnelshift_r(cur, nxt, sh)) << (8 * fill);
+            *op++ = static_cast<uint32_t>(acc);
+            acc >>= 32;
+            cur = nxt;
+          }
+          if (n > 0) {
+            const uint32_t x = __funnelshift_r(cur, w[1], sh) & ((1u << (8 * n)) - 1u);
+            acc |= static_cast<unsigned long long>(x) << (8 * fill);
+            fill += n;
+          }
+        }
+        if (!cut) {  // the separator
+          acc |= static_cast<unsigned long long>(sep) << (8 * fill);
+          ++fill;
+          --rem;
+        }
+        if (fill >= 4) {
+          *op++ = static_cast<uint32_t>(acc);
+          acc >>= 32;
+          fill -= 4;
+        }
+        if (rem == 0) break;
+        ++idx;
+        if (++c == kCols) {
+          c = 0;
+          ++idx;  // the pad slot
+        }
+      }
+      if (fill) *op = static_cast<uint32_t>(acc);  // last chunk of the tile: the word is ours (+32 slack)
+    }
   }
-  if (staged) __syncthreads();  // the tile is complete in shared memory and its offset is known
+  __syncthreads();  // the tile is complete in shared memory and its offset is known
   const unsigned long long base = sm.base;
   if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + base + sm.row_start[tid]);
-  if (!staged || base + tile_total > capacity) return;
+  if (base + tile_total > capacity) return;
 
-  // ---- 5. flush s_tile[0 .. tile_total) -> out_data[base ..) with 16-byte stores.  Global chunk k
+  // ---- E. flush s_out[0 .. tile_total) -> out_data[base ..) with 16-byte stores.  Global chunk k
   // starts at the first 16-byte boundary >= out_data+base, i.e. at tile offset head + 16k, which has
   // an arbitrary phase in shared memory: read 5 aligned words and funnel-shift.
   uint8_t* __restrict__ dst = out_data + base;
   const uint32_t head_raw = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
   const uint32_t head = head_raw < tile_total ? head_raw : tile_total;
-  for (uint32_t k = tid; k < head; k += kCtaThreads) dst[k] = s_tile[k];
+  for (uint32_t k = tid; k < head; k += kCtaThreads) dst[k] = s_out[k];
   const uint32_t n_chunks = (tile_total - head) >> 4;
   const uint32_t sh = (head & 3u) * 8u;
-  const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(s_tile) + (head >> 2);
+  const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(s_out) + (head >> 2);
   for (uint32_t k = tid; k < n_chunks; k += kCtaThreads) {
     const uint32_t* w = sw + 4 * k;
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];  // w[4] stays inside the +32 slack
@@ -592,7 +867,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS) csv_rows_kern
     o.w = __funnelshift_r(w3, w4, sh);
     *reinterpret_cast<uint4*>(dst + head + 16u * k) = o;
   }
-  for (uint32_t k = head + 16u * n_chunks + tid; k < tile_total; k += kCtaThreads) dst[k] = s_tile[k];
+  for (uint32_t k = head + 16u * n_chunks + tid; k < tile_total; k += kCtaThreads) dst[k] = s_out[k];
 }
 
 cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
@@ -606,12 +881,11 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
     if (err != cudaSuccess) return err;
     return cudaMemcpyAsync(row_offsets, total_out, 8, cudaMemcpyDeviceToDevice, stream);  // 0; the caller adds its bias
   }
-  const int smem = kTileBytes + 32 + (int)sizeof(CsvSmem);
   static int configured_device = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_device != dev) {
-    err = cudaFuncSetAttribute(csv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    err = cudaFuncSetAttribute(csv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return err;
     configured_device = dev;
   }
@@ -623,8 +897,8 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
     if (blocks < 1) blocks = 1;
     column_dirty_kernel<<<dim3((unsigned)blocks, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries, sc.col_dirty);
   }
-  csv_rows_kernel<<<(unsigned)csv_tiles(v.n_entries), kCtaThreads, smem, stream>>>(v, tab, sc, row_offsets,
-                                                                                out_data, capacity, bias, total_out);
+  csv_rows_kernel<<<(unsigned)csv_tiles(v.n_entries), kCtaThreads, kSmemBytes, stream>>>(
+      v, tab, sc, row_offsets, out_data, capacity, bias, total_out, g_force_slow);
   g_launches += 3;
   return cudaGetLastError();
 }

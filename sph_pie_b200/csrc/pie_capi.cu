@@ -466,6 +466,18 @@ int pie_csv_rows_dev(const pie_archive_view* v, int64_t* row_offsets, uint8_t* o
   return PIE_OK;
 }
 
+int pie_debug_csv_force_slow_path(int on) { return pie::csv_set_force_slow(on); }
+
+int pie_debug_csv_slow_tiles(const void* scratch, int64_t n_entries, uint32_t* slow_tiles, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!scratch || !slow_tiles || n_entries < 0) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  unsigned int n = 0;
+  PIE_CUDA(pie::csv_read_slow_tiles(scratch, n_entries, &n, (cudaStream_t)stream));
+  *slow_tiles = n;
+  return PIE_OK;
+}
+
 // Rows per pipeline chunk of the host export path (H2D of chunk c+1 and D2H of chunk c-1 overlap the
 // kernels of chunk c; PCIe is full duplex).
 static int64_t kCsvChunkRows = 1 << 20;  // pie_set_csv_chunk_rows (tests exercise the multi-chunk path)

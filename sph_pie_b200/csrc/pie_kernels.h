@@ -22,6 +22,11 @@ cudaError_t launch_csv_rows(const pie_archive_view& dev_view, int64_t* row_offse
                             uint64_t capacity, unsigned long long offset_bias, unsigned long long* total_out,
                             void* scratch, cudaStream_t stream);
 
+// debug knobs of the export-row kernel (tests): force every tile through the slow path (on < 0 only
+// queries; returns the previous value); number of tiles of the last launch on `scratch` that took it
+int csv_set_force_slow(int on);
+cudaError_t csv_read_slow_tiles(const void* scratch, int64_t n_entries, unsigned int* out, cudaStream_t stream);
+
 // archive_daily.cu
 uint64_t daily_scratch_bytes(int64_t n_shows);
 cudaError_t launch_daily_summary(const pie_archive_view& dev_view, const int32_t* stats_i32,

@@ -163,3 +163,62 @@ def test_host_pipeline_many_chunks(cuda):
         assert rc == _lib.PIE_ERR_CAPACITY and total.value == data.numel() and torch.equal(off, offsets)
     finally:
         lib.pie_set_csv_chunk_rows(old)
+
+
+def test_slow_path_forced_matches_oracle(cuda):
+    """Tiles that do not fit the shared-memory staging go warp-per-row from / to global memory.  Force
+    every tile through that path and compare with the oracle (synthetic + the edge-case shows)."""
+    lib = _lib.load()
+    old = lib.pie_debug_csv_force_slow_path(1)
+    try:
+        assert lib.pie_debug_csv_force_slow_path(-1) == 1
+        for n_shows, seed in [(1, 0), (310, 2), (3000, 9)]:
+            host = synth_archive(n_shows, seed=seed)
+            dev = host.to(cuda)
+            assert_same_rows(ops.csv_rows(dev), host)
+        shows = [{"id": 'a"b', "label": "x,y", "crew": ["A|B", 'q"', ""], "notes": "r\rn",
+                  "entries": [{"id": "e1", "status": "Completed", "primaryIssue": "Battery", "actions": ["x,y", "z"],
+                               "delaySec": 0, "notes": '""' * 40},
+                              {"id": "e2", "delaySec": 1e21, "actions": [], "notes": 'q"' * 33 + "tail"}]}]
+        table = pack_shows(shows)
+        assert_same_rows(ops.csv_rows(table.to(cuda)), table)
+    finally:
+        lib.pie_debug_csv_force_slow_path(old)
+    assert lib.pie_debug_csv_force_slow_path(-1) == old
+
+
+def test_fast_path_is_the_one_that_runs(cuda):
+    """The synthetic archive fits the staging buffers: no tile may fall back to the slow path (the bench
+    measures the fast path), while an archive with one oversized cell sends exactly that tile there."""
+    host = synth_archive(5000, seed=3)
+    dev = host.to(cuda)
+    sizing = ops.CsvBuffers(dev.n_entries, 0, cuda)
+    ops.csv_rows_dev(dev, sizing, size_only=True)
+    total = int(sizing.total.cpu())
+    assert ops.csv_slow_tiles(dev, sizing) == 0
+    bufs = ops.CsvBuffers(dev.n_entries, total, cuda)
+    ops.csv_rows_dev(dev, bufs)
+    assert ops.csv_slow_tiles(dev, bufs) == 0
+    shows = [{"id": f"s{i}", "entries": [{"id": f"e{i}-{j}", "notes": "n" * (60000 if (i, j) == (40, 3) else 7)}
+                                          for j in range(10)]} for i in range(100)]
+    table = pack_shows(shows)
+    dev = table.to(cuda)
+    sizing = ops.CsvBuffers(dev.n_entries, 0, cuda)
+    ops.csv_rows_dev(dev, sizing, size_only=True)
+    assert ops.csv_slow_tiles(dev, sizing) == 1
+    assert_same_rows(ops.csv_rows(dev), table)
+
+
+def test_many_tiny_shows_and_empty_shows(cuda):
+    """More shows than rows in a tile (empty shows between entries) and single-entry shows with dirty
+    show-level cells: the show-level cell table of a tile is exercised at and beyond its capacity."""
+    shows = []
+    for i in range(700):
+        shows.append({"id": f"s,{i}" if i % 3 == 0 else f"s{i}", "label": 'The "Late" show' if i % 5 == 0 else "L",
+                      "crew": [f"c{i}", "x|y", 'q"z'][: i % 4], "notes": "a\nb" if i % 7 == 0 else "",
+                      "entries": [{"id": f"e{i}", "delaySec": i * 0.25, "actions": ["A", "B,C", "D"][: i % 4]}]
+                      if i % 2 == 0 or i > 600 else []})
+    shows += [{"id": "gap", "entries": []}] * 300 + [{"id": "last", "entries": [{"id": "z"}] * 5}]
+    table = pack_shows(shows)
+    assert_same_rows(ops.csv_rows(table.to(cuda)), table)
+    assert_same_rows(ops.csv_rows(table), table)
