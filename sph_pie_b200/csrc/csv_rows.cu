@@ -6,25 +6,28 @@
 // Output = one string column: row i is out_data[row_offsets[i] .. row_offsets[i+1]-1) and is followed
 // by one '\n', so a show's CSV body is a single contiguous slice.
 //
-// ONE pass over the inputs.  A CTA takes a tile of kRows consecutive entries:
-//   A. stage    the tile's bytes of every column are ONE contiguous range of that column's heap (rows
-//               are consecutive), so a single warp issues <= 23 TMA bulk copies (cp.async.bulk,
-//               completion on an mbarrier) into shared memory; the < 16 bytes past the last full
-//               16-byte chunk of a range are copied as words so nothing is read past a heap's end.
-//               Meanwhile the other warps gather their offsets and format delaySec (Ryu).
-//   B. cells    every cell becomes a plain (src, len) pair in the staging buffer: show-level cells
-//               are normalised once per show of the tile, not once per row; cells that need csvEscape
-//               or Array.join('|') are materialised in a bump area behind the staged bytes;
-//               Number::toString output lives next to it; cells blanked by status === 'Completed'
-//               get len 0.
-//   C. scan     per-row and per-tile sizes; the tile's aggregate is published for the decoupled
-//               look-back, which the extra warp runs WHILE the others write (D needs no offset).
-//   D. write    the OUTPUT is partitioned: the tile's bytes are cut into equal 16-byte-multiple
-//               chunks, one per thread.  The cell that contains a chunk's first byte registers itself
-//               in a table, so a thread starts there and streams cells into its own aligned words —
-//               no byte stores, no races, and the work per thread is the same whatever the row
-//               lengths are.
-//   E. flush    16-byte coalesced stores; the tile is re-aligned to the destination with a funnel shift.
+// ONE pass over the inputs, by a PERSISTENT, warp-specialised kernel.  A CTA loops over
+// tiles of kRows consecutive entries (claimed from a counter, so tile ids start in order):
+//   producer warp   one tile AHEAD of the workers.  Everything a tile reads is a handful of contiguous
+//                   ranges — per column the bytes of its heap and the slice of its offsets array, plus
+//                   delaySec / validity / the rows' show indices — so the warp resolves the ~50 range
+//                   ends (the only dependent global loads of the kernel) and issues one TMA bulk copy
+//                   (cp.async.bulk, completion on an mbarrier) per range into a two-stage shared-memory
+//                   pool; the < 16 bytes past a range's last full 16-byte chunk are copied as words so
+//                   nothing is read past an array's end.
+//   16 worker warps never touch global memory for input:
+//     cells  every cell becomes a plain (src, len) pair in the stage: show-level cells are normalised
+//            once per show of the tile, not once per row; cells that need csvEscape or
+//            Array.join('|') are materialised in a bump area behind the staged bytes;
+//            Number::toString (Ryu) output lives next to it; cells blanked by status === 'Completed'
+//            get len 0.
+//     scan   per-row and per-tile sizes; the tile's aggregate is published.
+//     write  the OUTPUT is partitioned: the tile's bytes are cut into equal 16-byte-multiple chunks,
+//            one per thread.  The cell that contains a chunk's first byte registers itself in a table,
+//            so a thread starts there and streams cells into its own aligned words of the shared
+//            output tile — no byte stores, no races, the same work per thread whatever the row lengths.
+//     flush  16-byte coalesced stores; the tile is re-aligned to the destination with a funnel shift.
+//   look-back warp  decoupled look-back over the published tile totals while the workers write.
 // A tile that does not fit (very long free text, more than kMaxTileShows shows) takes a slow path:
 // a warp per row, lanes striding over the bytes of a cell, straight from / to global memory.
 #include "pie_device.cuh"
@@ -40,30 +43,34 @@ __device__ const uint64_t d_pow5[PIE_RYU_POW5_SPLIT_N][2] = PIE_RYU_POW5_SPLIT_I
 #define PIE_CSV_ROWS 128
 #endif
 #ifndef PIE_CSV_MIN_BLOCKS
-#define PIE_CSV_MIN_BLOCKS 2
+#define PIE_CSV_MIN_BLOCKS 1
 #endif
 #ifndef PIE_CSV_OUT_KB
 #define PIE_CSV_OUT_KB 42
 #endif
-#ifndef PIE_CSV_IN_KB
-#define PIE_CSV_IN_KB 40
+#ifndef PIE_CSV_STAGE_KB
+#define PIE_CSV_STAGE_KB 50
 #endif
 constexpr int kRows = PIE_CSV_ROWS;            // rows (entries) per tile; multiple of 32
 constexpr int kCols = PIE_N_EXPORT_COLUMNS;    // 24
 constexpr int kGroups = 4;
 constexpr int kGroupCols = kCols / kGroups;    // 6
-constexpr int kWorkers = kRows * kGroups;      // worker threads: (row, group of 6 columns) ...
-constexpr int kCtaThreads = kWorkers + 32;     // ... + one warp: TMA producer, then decoupled look-back
-constexpr int kCtaWarps = kCtaThreads / 32;
-constexpr int kOutBytes = PIE_CSV_OUT_KB * 1024;  // shared output tile (rows of ~280 B -> ~36 KB per 128 rows)
-constexpr int kInBytes = PIE_CSV_IN_KB * 1024;    // staged column bytes + bump area
-constexpr int kNumBytes = kRows * kMaxNumberChars;
+constexpr int kWorkers = kRows * kGroups;      // worker threads: (row, group of 6 columns)
+constexpr int kWorkerWarps = kWorkers / 32;
+constexpr int kProducerWarp = kWorkerWarps;    // stages the next tile
+constexpr int kLookbackWarp = kWorkerWarps + 1;
+constexpr int kCtaThreads = kWorkers + 64;
+constexpr int kOutBytes = PIE_CSV_OUT_KB * 1024;      // shared output tile (rows of ~280 B -> ~36 KB per 128 rows)
+constexpr int kStageBytes = PIE_CSV_STAGE_KB * 1024;  // one stage: column bytes + offset arrays + bump area
+constexpr int kNumBytes = kRows * kMaxNumberChars;    // Number::toString output, behind the stage
+constexpr int kStageStride = kStageBytes + kNumBytes + 16;
 constexpr int kShowCols = 8;                   // columns 0..7 are show-level
 constexpr int kMaxTileShows = kRows;           // shows a tile may span on the fast path
 constexpr int kCellStride = kCols + 1;         // padded: lanes = consecutive rows hit distinct banks
 static_assert(kRows % 32 == 0 && kGroups * kGroupCols == kCols, "tile shape");
-static_assert(kInBytes + kNumBytes <= 65536, "cell sources are 16-bit offsets into the staging buffer");
+static_assert(kStageBytes + kNumBytes <= 65536, "cell sources are 16-bit offsets into a stage");
 static_assert(kOutBytes <= 65536 - 256 && kRows * kCellStride < 4096, "chunk table packs (cell:12, skip:16)");
+static_assert(kStageStride % 16 == 0, "stages are 16-byte aligned");
 
 constexpr unsigned long long kStatusShift = 62;
 constexpr unsigned long long kValueMask = (1ull << kStatusShift) - 1;
@@ -166,7 +173,12 @@ static RowTable make_row_table(const pie_archive_view& v) {
   t.cell[22] = str(v.command_rx, 1);  t.cell[23] = str(v.notes, 1);
   return t;
 }
-constexpr int kStatusCol = 12, kActionsCol = 18;
+constexpr int kStatusCol = 12;
+// Entry-level columns whose cells worker group g prepares.  The heavy ones sit on different groups:
+// delaySec (Ryu) on 0, actions (Array.join) on 1, the issue block on 2, notes (free text) on 3; status (12)
+// comes before the columns it blanks (13..17).
+__constant__ signed char c_owned[4][6] = {
+    {21, -1, -1, -1, -1, -1}, {8, 9, 10, 11, 18, -1}, {12, 13, 14, 15, 16, 17}, {19, 20, 22, 23, -1, -1}};
 
 // ---- pre-pass: which columns can need quoting at all? -----------------------------------------------
 // Most columns of an archive (ids, dates, enumerations, names) never contain " , \n or \r.  One
@@ -204,14 +216,17 @@ __global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant
   if (__any_sync(0xFFFFFFFFu, flags != 0) && (threadIdx.x & 31) == 0) atomicOr(&col_dirty[col], 1u);
 }
 
-// ---- PTX: mbarrier + 1-D TMA bulk copy ------------------------------------------------------------
+// ---- PTX: mbarrier, 1-D TMA bulk copy, named barriers ----------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -232,81 +247,140 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+constexpr int kBarWorkers = 1, kBarTotalReady = 2, kBarBaseReady = 3;  // named barriers (0 = __syncthreads)
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kBarWorkers), "n"(kWorkers) : "memory"); }
+template <int kBar>
+__device__ __forceinline__ void bar_arrive_workers_and_lookback() {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"n"(kBar), "n"(kWorkers + 32) : "memory");
+}
+template <int kBar>
+__device__ __forceinline__ void bar_sync_workers_and_lookback() {
+  asm volatile("bar.sync %0, %1;" ::"n"(kBar), "n"(kWorkers + 32) : "memory");
+}
 
-// ---- shared-memory state of a tile ----------------------------------------------------------------
+// ---- shared-memory state ----------------------------------------------------------------------------
+// What the producer tells the workers about a staged tile.  "staged address" = byte offset in the stage.
+struct StageInfo {
+  long long tile;             // < 0: no more tiles
+  int32_t rows;
+  int32_t show0;              // first show of the tile
+  uint32_t n_tile_shows;
+  uint32_t slow;              // the tile does not fit the stage: slow path
+  uint32_t bump0;             // first free byte behind the staged ranges
+  uint32_t delta[kCols];      // staged address of heap byte b of column c = delta[c] + b
+  uint32_t off_base[kCols];   // staged address of the column's first offset word (offsets[e0] / offsets[show0] /
+                              // list_offsets[...] for the two list columns)
+  uint32_t item_base[kCols];  // list columns: staged address of items.offsets[item_first[c]]
+  int32_t item_first[kCols];
+  uint32_t show_idx_base;     // entry_show[e0 ..]
+  uint32_t delay_base;        // delay_sec[e0 ..]
+  uint32_t valid_base;        // delay_valid[e0 ..]
+};
 struct CsvSmem {
-  unsigned long long mbar;
-  unsigned long long base;                      // global byte offset of the tile (look-back result)
+  unsigned long long full[2];                   // producer -> workers: stage s holds a tile
+  unsigned long long empty[2];                  // workers -> producer: stage s may be overwritten
+  unsigned long long base[2];                   // global byte offset of the tile (look-back result), by tile parity
+  StageInfo info[2];
   uint32_t cell[kRows * kCellStride];           // (src:16 | len:16 << 16) of cell (r, c) at r*kCellStride + c
   uint32_t shcell[kShowCols][kMaxTileShows];    // the same for the show-level cells of the tile's shows
   uint32_t first[kWorkers];                     // chunk k starts inside cell (idx:12) at byte (skip << 12)
-  uint32_t group[kGroups][kRows];               // bytes of a row's group, then its start inside the row
-  uint32_t row_start[kRows];                    // byte offset of the row inside the tile
-  uint32_t delta[kCols];                        // staged address of heap byte b of column c = delta[c] + b
+  uint32_t group[kGroups][kRows];               // bytes of a row's group
+  uint32_t row_start[2][kRows];                 // byte offset of the row inside the tile, by tile parity
   uint32_t col_dirty[kCols];
   uint32_t warp_sum[kRows / 32];
-  uint32_t tile_total;
-  uint32_t bump;                                // next free byte of the bump area
-  uint32_t slow;                                // != 0: the tile does not fit the fast path
-  int32_t show0;                                // first show of the tile
-  uint32_t n_tile_shows;
-  unsigned int tile_id;
+  uint32_t tile_total[2];                       // by tile parity (the flush of a tile is deferred by one tile)
+  long long cur_tile[2];                        // workers -> look-back warp
+  uint32_t bump;                                // next free byte of the current stage's bump area
+  uint32_t overflow;                            // the bump area ran out
+  uint32_t done;
   uint8_t num_len[kRows];
 };
-constexpr int kSmemOffIn = kOutBytes + 32;
-constexpr int kSmemOffState = kSmemOffIn + kInBytes + kNumBytes + 16;
+constexpr int kSmemOffStage = kOutBytes + 32;
+constexpr int kSmemOffState = kSmemOffStage + 2 * kStageStride;
 constexpr int kSmemBytes = kSmemOffState + (int)sizeof(CsvSmem);
-static_assert(kSmemOffIn % 16 == 0 && kSmemOffState % 8 == 0, "smem carve-up");
+static_assert(kSmemOffStage % 16 == 0 && kSmemOffState % 8 == 0, "smem carve-up");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
 
 __device__ __forceinline__ uint32_t pack_cell(uint32_t src, uint32_t len) { return (src & 0xFFFFu) | (len << 16); }
+__device__ __forceinline__ const int32_t* stage_i32(const uint8_t* stage, uint32_t addr) {
+  return reinterpret_cast<const int32_t*>(stage + addr);
+}
 
-// does s_in[src .. src+n) contain a character that forces quoting?  Aligned words, ends masked.
-__device__ __forceinline__ bool smem_has_special(const uint8_t* s_in, uint32_t src, uint32_t n) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + (src & ~3u));
+// does stage[src .. src+n) contain a character that forces quoting?  Aligned words, ends masked.
+__device__ __forceinline__ uint32_t smem_special_and_quotes(const uint8_t* stage, uint32_t src, uint32_t n, uint32_t& nq) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
   const uint32_t lead = src & 3u;
   const int nw = static_cast<int>((lead + n + 3) >> 2);
   const uint32_t tail = (lead + n) & 3u;
-  uint32_t flags = 0;
+  uint32_t flags = 0, q = 0;
   for (int k = 0; k < nw; ++k) {
     uint32_t x = w[k];
     if (k == 0) x &= 0xFFFFFFFFu << (8 * lead);
     if (k == nw - 1 && tail) x &= (1u << (8 * tail)) - 1u;
-    flags |= special_flags(x);
+    const uint32_t zq = zero_byte_flags(x ^ 0x22222222u);  // exact per byte when no borrow crosses: count below is
+    flags |= zq | zero_byte_flags(x ^ 0x2C2C2C2Cu) | zero_byte_flags(x ^ 0x0A0A0A0Au) | zero_byte_flags(x ^ 0x0D0D0D0Du);
+    q |= zq;
   }
-  return flags != 0;
+  nq = q;  // != 0 iff the cell holds a '"' (then the caller counts them byte-wise)
+  return flags;
 }
 
 // Rare path: a cell that needs csvEscape (:332-338) and / or Array.prototype.join('|') (:284, :298) is
-// written out in the bump area.  s_in[src .. src+n) = the cell's staged bytes (for a list: all its
+// written out in the bump area.  stage[src .. src+n) = the cell's staged bytes (for a list: all its
 // items, which are contiguous in the heap); items > 1 inserts '|' at the item boundaries, which are
-// item_offsets[l0+1 ..] in heap coordinates (+ delta = staged).
-__device__ __noinline__ uint32_t materialise_cell(CsvSmem& sm, uint8_t* s_in, const int32_t* __restrict__ item_offsets,
-                                                  uint32_t delta, bool dirty, uint32_t src, uint32_t n, int l0, int items) {
-  const bool special = dirty && n > 0 && smem_has_special(s_in, src, n);
+// item_offsets[1 ..] in heap coordinates (+ delta = staged).
+__device__ __noinline__ uint32_t materialise_cell(CsvSmem& sm, uint8_t* stage, const int32_t* item_offsets, uint32_t delta,
+                                                  bool dirty, uint32_t src, uint32_t n, int items) {
+  uint32_t has_quote = 0;
+  const bool special = dirty && n > 0 && smem_special_and_quotes(stage, src, n, has_quote) != 0;
   if (!special && items <= 1) return pack_cell(src, n);
+  if (items <= 1 && !has_quote) {
+    // '"' + the bytes + '"', nothing to double: word-wise copy into a 4-byte aligned allocation whose
+    // content starts on a word boundary (the opening quote is the byte before it)
+    const uint32_t words = (n + 3) >> 2;
+    const uint32_t p = atomicAdd(&sm.bump, 4u * words + 8u);  // bump stays 4-byte aligned
+    if (p + 4u * words + 8u > (uint32_t)kStageBytes) {
+      sm.overflow = 1;  // benign race: every writer stores 1
+      return 0;
+    }
+    stage[p + 3] = '"';
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
+    const uint32_t sh = (src & 3u) * 8u;
+    uint32_t* o = reinterpret_cast<uint32_t*>(stage + p + 4);
+    uint32_t cur = w[0];
+    for (uint32_t k = 0; k < words; ++k) {
+      const uint32_t nxt = w[k + 1];
+      o[k] = __funnelshift_r(cur, nxt, sh);
+      cur = nxt;
+    }
+    stage[p + 4 + n] = '"';  // after the word stores: the last word may have spilled past the content
+    return pack_cell(p + 3, n + 2);
+  }
   uint32_t nq = 0;
-  if (special)
-    for (uint32_t j = 0; j < n; ++j) nq += (s_in[src + j] == '"');
+  if (has_quote)
+    for (uint32_t j = 0; j < n; ++j) nq += (stage[src + j] == '"');
   const uint32_t out_len = n + (items > 1 ? (uint32_t)(items - 1) : 0u) + (special ? 2u + nq : 0u);
-  const uint32_t p = atomicAdd(&sm.bump, out_len);
-  if (p + out_len > (uint32_t)kInBytes) {
-    sm.slow = 1;  // benign race: every writer stores 1
+  const uint32_t alloc = (out_len + 3u) & ~3u;
+  const uint32_t p = atomicAdd(&sm.bump, alloc);
+  if (p + alloc > (uint32_t)kStageBytes) {
+    sm.overflow = 1;
     return 0;
   }
   uint32_t q = p;
-  if (special) s_in[q++] = '"';
+  if (special) stage[q++] = '"';
   uint32_t ib = src;
   for (int it = 0; it < items; ++it) {
-    const uint32_t ie = (it + 1 < items) ? delta + (uint32_t)item_offsets[l0 + it + 1] : src + n;
+    const uint32_t ie = (it + 1 < items) ? delta + (uint32_t)item_offsets[it + 1] : src + n;
     for (uint32_t j = ib; j < ie; ++j) {
-      const uint8_t c = s_in[j];
-      if (special && c == '"') s_in[q++] = '"';
-      s_in[q++] = c;
+      const uint8_t c = stage[j];
+      if (c == '"' && special) stage[q++] = '"';
+      stage[q++] = c;
     }
-    if (it + 1 < items) s_in[q++] = '|';
+    if (it + 1 < items) stage[q++] = '|';
     ib = ie;
   }
-  if (special) s_in[q++] = '"';
+  if (special) stage[q++] = '"';
   return pack_cell(p, out_len);
 }
 
@@ -338,7 +412,7 @@ __device__ __forceinline__ SlowCell slow_locate(const CellDesc& d, int64_t i) {
 __device__ __noinline__ void slow_measure(const pie_archive_view& v, const RowTable& tab, const CsvScratch& sc,
                                           CsvSmem& sm, char* s_num, uint32_t* qmask, int64_t e0, int rows) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int r = wid; r < rows; r += kCtaWarps) {
+  for (int r = wid; r < rows; r += kWorkerWarps) {
     const int64_t e = e0 + r;
     const int64_t show = sc.entry_show[e];
     bool completed = false;
@@ -404,14 +478,15 @@ __device__ __forceinline__ void slow_copy(uint8_t* __restrict__ dst, uint32_t& p
 }
 
 __device__ __noinline__ void slow_write(const RowTable& tab, const CsvScratch& sc, CsvSmem& sm, const char* s_num,
-                                        const uint32_t* qmask, int64_t e0, int rows, uint8_t* __restrict__ out) {
+                                        const uint32_t* qmask, uint32_t par, int64_t e0, int rows,
+                                        uint8_t* __restrict__ out) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int r = wid; r < rows; r += kCtaWarps) {
+  for (int r = wid; r < rows; r += kWorkerWarps) {
     const int64_t e = e0 + r;
     const int64_t show = sc.entry_show[e];
     const uint32_t qm = qmask[r];
     const bool completed = (qm >> 31) != 0;
-    uint8_t* dst = out + sm.row_start[r];
+    uint8_t* dst = out + sm.row_start[par][r];
     uint32_t pos = 0;
     for (int col = 0; col < kCols; ++col) {
       const CellDesc& d = tab.cell[col];
@@ -450,177 +525,223 @@ __device__ __noinline__ void slow_write(const RowTable& tab, const CsvScratch& s
   }
 }
 
+// ---- producer: plan and issue the ranges of one tile -------------------------------------------------
+struct Range {
+  uintptr_t begin, end;  // byte addresses in global memory
+};
+struct RangePlan {
+  uintptr_t lo, hi;  // [lo, hi): whole 16-byte chunks, by TMA
+  uint32_t span;     // bytes of the stage the range occupies (a multiple of 16)
+  uint32_t bulk;
+};
+__device__ __forceinline__ RangePlan plan_range(const Range& r) {
+  RangePlan p;
+  p.lo = r.begin & ~static_cast<uintptr_t>(15);  // not before the allocation: an address that is not 16-byte
+                                                 // aligned cannot be the first byte of one
+  p.hi = r.end & ~static_cast<uintptr_t>(15);    // full chunks only: nothing is read past the range's last word
+  const bool any = r.end > r.begin;
+  p.bulk = (any && p.hi > p.lo) ? (uint32_t)(p.hi - p.lo) : 0u;
+  p.span = any ? (uint32_t)(((r.end + 15) & ~static_cast<uintptr_t>(15)) - p.lo) : 0u;
+  return p;
+}
+__device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t x, uint32_t& total, int lane) {
+  uint32_t incl = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  return incl - x;
+}
+// copies the range into stage + region; returns nothing: the staged address of r.begin is region + (begin - lo)
+__device__ __forceinline__ void issue_range(const Range& r, const RangePlan& p, uint8_t* stage, uint32_t region, uint32_t bar) {
+  if (!p.span) return;
+  if (p.bulk) tma_bulk_g2s(smem_u32(stage + region), reinterpret_cast<const void*>(p.lo), p.bulk, bar);
+  // The range's last, partial chunk (or a range inside one chunk): the <= 4 aligned words that hold
+  // bytes of it — never a word past the one that holds the range's last byte.
+  const uintptr_t t0 = p.bulk ? p.hi : (r.begin & ~static_cast<uintptr_t>(3));
+  uint32_t x[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) x[k] = (t0 + 4 * k < r.end) ? __ldg(reinterpret_cast<const uint32_t*>(t0) + k) : 0u;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(stage + region + (uint32_t)(t0 - p.lo));
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (t0 + 4 * k < r.end) dst[k] = x[k];
+}
+
+__device__ __forceinline__ void produce_tile(const pie_archive_view& v, const RowTable& tab, const CsvScratch& sc,
+                                             StageInfo& info, uint8_t* stage, uint32_t bar, int64_t tile, int force_slow,
+                                             int lane) {
+  const int64_t e0 = tile * kRows;
+  const int rows = (v.n_entries - e0 < kRows) ? (int)(v.n_entries - e0) : kRows;
+  const int32_t s0 = sc.entry_show[e0], s1 = sc.entry_show[e0 + rows - 1];
+  Range rb{0, 0}, ro{0, 0}, ri{0, 0};  // heap bytes, offsets slice, item offsets slice
+  uint32_t b0 = 0;
+  int32_t l0 = 0;
+  if (lane < kCols && tab.cell[lane].kind != kCellNumber) {
+    const CellDesc& d = tab.cell[lane];
+    const int64_t i0 = d.per_entry ? e0 : (int64_t)s0, i1 = d.per_entry ? e0 + rows : (int64_t)s1 + 1;
+    const int32_t* oarr = (d.kind == kCellJoined) ? d.list_offsets : d.offsets;
+    ro = Range{reinterpret_cast<uintptr_t>(oarr + i0), reinterpret_cast<uintptr_t>(oarr + i1 + 1)};
+    int32_t f0 = oarr[i0], f1 = oarr[i1];
+    if (d.kind == kCellJoined) {
+      l0 = f0;
+      ri = Range{reinterpret_cast<uintptr_t>(d.offsets + f0), reinterpret_cast<uintptr_t>(d.offsets + f1 + 1)};
+      f0 = d.offsets[f0];
+      f1 = d.offsets[f1];
+    }
+    b0 = (uint32_t)f0;
+    rb = Range{reinterpret_cast<uintptr_t>(d.data) + (uint32_t)f0, reinterpret_cast<uintptr_t>(d.data) + (uint32_t)f1};
+  } else if (lane == kCols) {
+    ro = Range{reinterpret_cast<uintptr_t>(sc.entry_show + e0), reinterpret_cast<uintptr_t>(sc.entry_show + e0 + rows)};
+  } else if (lane == kCols + 1) {
+    ro = Range{reinterpret_cast<uintptr_t>(v.delay_sec + e0), reinterpret_cast<uintptr_t>(v.delay_sec + e0 + rows)};
+  } else if (lane == kCols + 2) {
+    ro = Range{reinterpret_cast<uintptr_t>(v.delay_valid + e0), reinterpret_cast<uintptr_t>(v.delay_valid + e0 + rows)};
+  }
+  const RangePlan pb = plan_range(rb), po = plan_range(ro), pi = plan_range(ri);
+  uint32_t tb, to, ti;
+  const uint32_t region_b = warp_exclusive_scan(pb.span, tb, lane);
+  const uint32_t region_o = tb + warp_exclusive_scan(po.span, to, lane);
+  const uint32_t region_i = tb + to + warp_exclusive_scan(pi.span, ti, lane);
+  const uint32_t used = tb + to + ti;
+  uint32_t bulk_total = pb.bulk + po.bulk + pi.bulk;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) bulk_total += __shfl_xor_sync(0xFFFFFFFFu, bulk_total, o);
+  const bool fits = used <= (uint32_t)kStageBytes && (s1 - s0) < kMaxTileShows && !force_slow;
+
+  if (lane < kCols) {
+    info.delta[lane] = region_b + (uint32_t)(rb.begin - pb.lo) - b0;
+    info.off_base[lane] = region_o + (uint32_t)(ro.begin - po.lo);
+    info.item_base[lane] = region_i + (uint32_t)(ri.begin - pi.lo);
+    info.item_first[lane] = l0;
+  } else if (lane == kCols) {
+    info.show_idx_base = region_o + (uint32_t)(ro.begin - po.lo);
+  } else if (lane == kCols + 1) {
+    info.delay_base = region_o + (uint32_t)(ro.begin - po.lo);
+  } else if (lane == kCols + 2) {
+    info.valid_base = region_o + (uint32_t)(ro.begin - po.lo);
+  }
+  if (lane == 0) {
+    info.tile = tile;
+    info.rows = rows;
+    info.show0 = s0;
+    info.n_tile_shows = (uint32_t)(s1 - s0 + 1);
+    info.slow = fits ? 0u : 1u;
+    info.bump0 = (used + 3u) & ~3u;
+    if (fits) mbar_expect_tx(bar, bulk_total);
+  }
+  __syncwarp();
+  if (fits) {
+    issue_range(rb, pb, stage, region_b, bar);
+    issue_range(ro, po, stage, region_o, bar);
+    issue_range(ri, pi, stage, region_i, bar);
+  }
+  __syncwarp();  // every lane's info fields and word copies are ordered before lane 0's release-arrive
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// ---- look-back warp ------------------------------------------------------------------------------------
+__device__ __forceinline__ void look_back(const CsvScratch& sc, CsvSmem& sm, uint32_t par, int64_t n_tiles,
+                                          int64_t n_entries, int64_t* __restrict__ row_offsets, unsigned long long bias,
+                                          unsigned long long* __restrict__ total_out, int lane) {
+  const int64_t tile = sm.cur_tile[par];
+  const uint32_t tile_total = sm.tile_total[par];
+  volatile unsigned long long* state = sc.tile_state;
+  unsigned long long exclusive = 0;
+  int64_t idx = tile - 1;
+  while (idx >= 0) {
+    const int64_t j = idx - lane;
+    unsigned long long st;
+    unsigned ns = 32;
+    for (;;) {
+      st = 2ull << kStatusShift;  // before tile 0: an empty prefix
+      if (j >= 0) st = state[j];
+      if (!__any_sync(0xFFFFFFFFu, (st >> kStatusShift) == 0)) break;
+      __nanosleep(ns);  // the tiles we wait for are still measuring: do not hammer L2 / the issue slots
+      if (ns < 512) ns <<= 1;
+    }
+    const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (st >> kStatusShift) == 2);
+    const int stop = is_prefix ? (__ffs(is_prefix) - 1) : 32;  // nearest tile that already knows its prefix
+    unsigned long long part = (lane <= stop) ? (st & kValueMask) : 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    exclusive += part;
+    if (is_prefix) break;
+    idx -= 32;
+  }
+  if (lane == 0) {
+    // (status, value) travel in one 64-bit word and nothing else is read through it: no fence needed
+    if (tile > 0) state[tile] = kPrefix | (exclusive + tile_total);
+    sm.base[par] = exclusive;
+    if (tile == n_tiles - 1) {
+      *total_out = exclusive + tile_total;
+      row_offsets[n_entries] = (int64_t)(bias + exclusive + tile_total);
+    }
+  }
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab, CsvScratch sc,
                     int64_t* __restrict__ row_offsets, uint8_t* __restrict__ out_data, uint64_t capacity,
                     unsigned long long bias, unsigned long long* __restrict__ total_out, int force_slow) {
   extern __shared__ __align__(128) uint8_t s_dyn[];
-  uint8_t* s_out = s_dyn;                                  // kOutBytes + 32
-  uint8_t* s_in = s_dyn + kSmemOffIn;                      // kInBytes: staged bytes, then the bump area ...
-  char* s_num = reinterpret_cast<char*>(s_in + kInBytes);  // ... then Number::toString output, kNumBytes (+16 slack)
+  uint8_t* s_out = s_dyn;  // kOutBytes + 32
   CsvSmem& sm = *reinterpret_cast<CsvSmem*>(s_dyn + kSmemOffState);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const bool worker = tid < kWorkers;
-  const uint32_t bar = smem_u32(&sm.mbar);
+  const int64_t n_tiles = csv_tiles(v.n_entries);
 
   if (tid == 0) {
-    sm.tile_id = atomicAdd(sc.tile_counter, 1u);  // tiles start in id order: look-back cannot deadlock
-    sm.slow = (uint32_t)force_slow;
-    mbar_init(bar, 1);
+    mbar_init(smem_u32(&sm.full[0]), 1);
+    mbar_init(smem_u32(&sm.full[1]), 1);
+    mbar_init(smem_u32(&sm.empty[0]), kWorkerWarps);
+    mbar_init(smem_u32(&sm.empty[1]), kWorkerWarps);
+    mbar_fence_init();
+    sm.done = 0;
   }
   if (tid < kCols) sm.col_dirty[tid] = sc.col_dirty[tid];
   __syncthreads();
-  const int64_t tile = sm.tile_id;
-  const int64_t e0 = tile * kRows;
-  const int rows = (v.n_entries - e0 < kRows) ? (int)(v.n_entries - e0) : kRows;
-  const int g = tid / kRows, r = tid % kRows;
-  const bool have = worker && r < rows;
-  const int64_t e = e0 + r;
 
-  // ---- A. stage.  Producer warp: column ranges -> smem layout -> TMA; workers: offsets + numbers.
-  int cb[kGroupCols], cn[kGroupCols];  // workers: heap range of the group's entry-level cells
-  int jl0 = 0, jitems = 1;             // actions (the one entry-level list column): first item, item count
-  int show = 0;
-  if (!worker) {
-    const int32_t s0 = sc.entry_show[e0], s1 = sc.entry_show[e0 + rows - 1];
-    uint32_t b0 = 0, b1 = 0;
-    const uint8_t* data = nullptr;
-    if (lane < kCols && tab.cell[lane].kind != kCellNumber) {
-      const CellDesc& d = tab.cell[lane];
-      int64_t i0 = d.per_entry ? e0 : (int64_t)s0, i1 = d.per_entry ? e0 + rows : (int64_t)s1 + 1;
-      if (d.kind == kCellJoined) {
-        i0 = d.list_offsets[i0];
-        i1 = d.list_offsets[i1];
-      }
-      b0 = (uint32_t)d.offsets[i0];
-      b1 = (uint32_t)d.offsets[i1];
-      data = d.data;
-    }
-    const uintptr_t a0 = reinterpret_cast<uintptr_t>(data) + b0, a1 = reinterpret_cast<uintptr_t>(data) + b1;
-    const uintptr_t lo = a0 & ~static_cast<uintptr_t>(15);  // >= heap start: heaps are 16-byte aligned
-    const uintptr_t hi = a1 & ~static_cast<uintptr_t>(15);  // full chunks only; the tail goes by hand
-    const uint32_t bulk = (b1 > b0 && hi > lo) ? (uint32_t)(hi - lo) : 0u;
-    const uint32_t span = (b1 > b0) ? (uint32_t)(((a1 + 15) & ~static_cast<uintptr_t>(15)) - lo) : 0u;
-    uint32_t incl = span;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const uint32_t region = incl - span;
-    const uint32_t in_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    uint32_t bulk_total = bulk;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) bulk_total += __shfl_xor_sync(0xFFFFFFFFu, bulk_total, o);
-    const bool fits = in_total <= (uint32_t)kInBytes && (s1 - s0) < kMaxTileShows && !force_slow;
-    if (lane == 0) {
-      sm.bump = in_total;
-      sm.show0 = s0;
-      sm.n_tile_shows = (uint32_t)(s1 - s0 + 1);
-      if (!fits) sm.slow = 1;
-      mbar_arrive_expect_tx(bar, fits ? bulk_total : 0u);
-    }
-    __syncwarp();
-    if (lane < kCols) sm.delta[lane] = region + (uint32_t)(a0 - lo) - b0;
-    if (fits && span) {
-      if (bulk) tma_bulk_g2s(smem_u32(s_in + region), reinterpret_cast<const void*>(lo), bulk, bar);
-      // The range's last, partial chunk (or a range inside one chunk): the <= 4 aligned words that
-      // hold bytes of it — never a word past the heap's last byte.
-      const uintptr_t t0 = bulk ? hi : (a0 & ~static_cast<uintptr_t>(3));
-      uint32_t x[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) x[k] = (t0 + 4 * k < a1) ? __ldg(reinterpret_cast<const uint32_t*>(t0) + k) : 0u;
-      uint32_t* dst = reinterpret_cast<uint32_t*>(s_in + region + (uint32_t)(t0 - lo));
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (t0 + 4 * k < a1) dst[k] = x[k];
-    }
-  } else if (have) {
-    if (g < 2) show = sc.entry_show[e];
-    // every offset load of the group is issued before any is consumed
-    int a0[kGroupCols], a1[kGroupCols];
-#pragma unroll
-    for (int k = 0; k < kGroupCols; ++k) {
-      const CellDesc& d = tab.cell[g * kGroupCols + k];
-      a0[k] = 0;
-      a1[k] = 0;
-      if (d.per_entry && d.kind != kCellNumber) {
-        const int32_t* __restrict__ p = (d.kind == kCellJoined) ? d.list_offsets : d.offsets;
-        a0[k] = p[e];
-        a1[k] = p[e + 1];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kGroupCols; ++k) {
-      const CellDesc& d = tab.cell[g * kGroupCols + k];
-      cb[k] = a0[k];
-      cn[k] = a1[k] - a0[k];
-      if (d.per_entry && d.kind == kCellJoined) {  // items are contiguous in the heap
-        jl0 = a0[k];
-        jitems = a1[k] - a0[k];
-        cb[k] = 0;
-        cn[k] = 0;
-        if (jitems > 0) {
-          cb[k] = d.offsets[a0[k]];
-          cn[k] = d.offsets[a1[k]] - cb[k];
+  // ================= producer warp =================
+  if (wid == kProducerWarp) {
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+      long long tile = 0;
+      if (lane == 0) tile = (long long)atomicAdd(sc.tile_counter, 1u);  // tiles start in id order: look-back cannot deadlock
+      tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+      mbar_wait(smem_u32(&sm.empty[s]), ph ^ 1u);  // the workers are done with what the stage held
+      if (tile >= n_tiles) {
+        if (lane == 0) {
+          sm.info[s].tile = -1;
+          mbar_arrive(smem_u32(&sm.full[s]));
         }
+        return;
       }
-    }
-    if (g == 3) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
-      int nl = 0;
-      if (v.delay_valid[e]) {
-        const RyuTables t{d_pow5_inv, d_pow5};
-        nl = js_number_to_string(v.delay_sec[e], s_num + r * kMaxNumberChars, t);
-      }
-      sm.num_len[r] = (uint8_t)nl;
+      produce_tile(v, tab, sc, sm.info[s], s_dyn + kSmemOffStage + s * kStageStride, smem_u32(&sm.full[s]), tile,
+                   force_slow, lane);
     }
   }
-  __syncthreads();
 
+  // ================= look-back warp =================
+  if (wid == kLookbackWarp) {
+    for (uint32_t it = 0;; ++it) {
+      bar_sync_workers_and_lookback<kBarTotalReady>();
+      if (sm.done) return;
+      const uint32_t par = it & 1u;
+      look_back(sc, sm, par, n_tiles, v.n_entries, row_offsets, bias, total_out, lane);
+      bar_arrive_workers_and_lookback<kBarBaseReady>();
+    }
+  }
+
+  // ================= workers =================
   const bool write = out_data != nullptr;
+  const int g = tid / kRows, r = tid % kRows;
   uint32_t* qmask = sm.first;  // slow path: per-row quote masks live in the chunk table
-  bool slow = sm.slow != 0;    // uniform
 
-  // Decoupled look-back over the tile totals, by the producer warp.
-  auto look_back = [&](uint32_t tile_total) {
-    volatile unsigned long long* state = sc.tile_state;
-    unsigned long long exclusive = 0;
-    int64_t idx = tile - 1;
-    while (idx >= 0) {
-      const int64_t j = idx - lane;
-      unsigned long long st;
-      unsigned ns = 32;
-      for (;;) {
-        st = 2ull << kStatusShift;  // before tile 0: an empty prefix
-        if (j >= 0) st = state[j];
-        if (!__any_sync(0xFFFFFFFFu, (st >> kStatusShift) == 0)) break;
-        __nanosleep(ns);  // the tiles we wait for are still measuring: do not hammer L2 / the issue slots
-        if (ns < 1024) ns <<= 1;
-      }
-      const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (st >> kStatusShift) == 2);
-      const int stop = is_prefix ? (__ffs(is_prefix) - 1) : 32;  // nearest tile that already knows its prefix
-      unsigned long long part = (lane <= stop) ? (st & kValueMask) : 0ull;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-      exclusive += part;
-      if (is_prefix) break;
-      idx -= 32;
-    }
-    if (lane == 0) {
-      if (tile > 0) {
-        __threadfence();
-        state[tile] = kPrefix | (exclusive + tile_total);
-      }
-      sm.base = exclusive;
-      if (tile == csv_tiles(v.n_entries) - 1) {
-        *total_out = exclusive + tile_total;
-        row_offsets[v.n_entries] = (int64_t)(bias + exclusive + tile_total);
-      }
-    }
-  };
-  // rows' lengths in sm.group[0][*] -> sm.row_start, sm.tile_total; the aggregate is published
-  auto scan_rows_and_publish = [&]() {
+  // rows' lengths in sm.group[0][*] -> sm.row_start[par], sm.tile_total[par]; the aggregate is published
+  auto scan_rows_and_publish = [&](int64_t tile, int rows, uint32_t par) {
     uint32_t row_len = 0;
     if (tid < kRows) {
       if (tid < rows) row_len = sm.group[0][tid];
@@ -631,243 +752,309 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
         if (lane >= o) incl += t;
       }
       if (lane == 31) sm.warp_sum[wid] = incl;
-      sm.row_start[tid] = incl - row_len;  // completed below with the preceding warps' sums
+      sm.row_start[par][tid] = incl - row_len;  // completed below with the preceding warps' sums
     }
-    __syncthreads();
+    workers_sync();
     if (tid < kRows) {
       uint32_t before = 0;
       for (int w = 0; w < wid; ++w) before += sm.warp_sum[w];
-      sm.row_start[tid] += before;
+      sm.row_start[par][tid] += before;
       if (tid == kRows - 1) {
-        const uint32_t total = sm.row_start[tid] + row_len;
-        sm.tile_total = total;
-        __threadfence();
+        const uint32_t total = sm.row_start[par][tid] + row_len;
+        sm.tile_total[par] = total;
+        sm.cur_tile[par] = tile;
+        // (status, value) travel in one 64-bit word and nothing else is read through it: no fence needed
         reinterpret_cast<volatile unsigned long long*>(sc.tile_state)[tile] =
-            (tile == 0 ? kPrefix : kAggregate) | (unsigned long long)total;  // published for later tiles
+            (tile == 0 ? kPrefix : kAggregate) | (unsigned long long)total;
       }
     }
-    __syncthreads();
+    workers_sync();
   };
 
-  bool published = false;
-  if (!slow) {
-    mbar_wait(bar, 0);  // the staged bytes have landed
-
-    // ---- B1. show-level cells, once per show of the tile
-    {
-      const uint32_t ns = sm.n_tile_shows;
-      for (uint32_t idx = tid; idx < ns * kShowCols; idx += kCtaThreads) {
-        const uint32_t col = idx / ns, i = idx - col * ns;
-        const CellDesc& d = tab.cell[col];
-        const int64_t s = (int64_t)sm.show0 + i;
-        int l0 = 0, items = 1;
-        uint32_t b = 0, n = 0;
-        if (d.kind == kCellJoined) {  // crew
-          l0 = d.list_offsets[s];
-          items = d.list_offsets[s + 1] - l0;
-          if (items > 0) {
-            b = (uint32_t)d.offsets[l0];
-            n = (uint32_t)d.offsets[l0 + items] - b;
-          }
-        } else {
-          b = (uint32_t)d.offsets[s];
-          n = (uint32_t)d.offsets[s + 1] - b;
-        }
-        const uint32_t src = (sm.delta[col] + b) & 0xFFFFu;
-        uint32_t c = pack_cell(src, n);
-        if ((sm.col_dirty[col] && n) || items > 1)
-          c = materialise_cell(sm, s_in, d.offsets, sm.delta[col], sm.col_dirty[col] != 0, src, n, l0, items);
-        sm.shcell[col][i] = c;
-      }
+  // The flush of a tile is deferred until the next tile has been measured: its look-back (a walk over
+  // the totals of the ~150 tiles in flight on the other SMs) then has a whole tile of slack.
+  bool pending = false;
+  int64_t p_e0 = 0;
+  int p_rows = 0;
+  uint32_t p_total = 0, p_par = 0;
+  auto finish_pending = [&]() {
+    if (!pending) return;
+    pending = false;
+    bar_sync_workers_and_lookback<kBarBaseReady>();  // every chunk is written and the tile's offset is known
+    const unsigned long long base = sm.base[p_par];
+    if (tid < p_rows) row_offsets[p_e0 + tid] = (int64_t)(bias + base + sm.row_start[p_par][tid]);
+    if (!write || base + p_total > capacity) return;
+    // s_out[0 .. p_total) -> out_data[base ..) with 16-byte stores.  Global chunk k starts at the first
+    // 16-byte boundary >= out_data+base, i.e. at tile offset head + 16k, which has an arbitrary phase in
+    // shared memory: read 5 aligned words and funnel-shift.
+    uint8_t* __restrict__ dst = out_data + base;
+    const uint32_t head_raw = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
+    const uint32_t head = head_raw < p_total ? head_raw : p_total;
+    for (uint32_t k = tid; k < head; k += kWorkers) dst[k] = s_out[k];
+    const uint32_t n_chunks = (p_total - head) >> 4;
+    const uint32_t sh = (head & 3u) * 8u;
+    const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(s_out) + (head >> 2);
+    for (uint32_t k = tid; k < n_chunks; k += kWorkers) {
+      const uint32_t* w = sw + 4 * k;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];  // w[4] stays inside the +32 slack
+      uint4 o;
+      o.x = __funnelshift_r(w0, w1, sh);
+      o.y = __funnelshift_r(w1, w2, sh);
+      o.z = __funnelshift_r(w2, w3, sh);
+      o.w = __funnelshift_r(w3, w4, sh);
+      *reinterpret_cast<uint4*>(dst + head + 16u * k) = o;
     }
-    __syncthreads();
+    for (uint32_t k = head + 16u * n_chunks + tid; k < p_total; k += kWorkers) dst[k] = s_out[k];
+  };
 
-    // ---- B2. the group's cells
-    if (have) {
-      bool completed = false;  // entry.status === 'Completed' (:293-297); status = first cell of group 2
-      if (g == 2 && cn[0] == 9) {
-        const uint32_t src = (sm.delta[kStatusCol] + (uint32_t)cb[0]) & 0xFFFFu;
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + (src & ~3u));
-        const uint32_t sh = (src & 3u) * 8u;
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];  // the 9 bytes lie inside these three words
-        completed = __funnelshift_r(w0, w1, sh) == lit_word("Completed", 0) &&
-                    __funnelshift_r(w1, w2, sh) == lit_word("Completed", 1) &&
-                    (__funnelshift_r(w2, 0u, sh) & 0xFFu) == lit_word("Completed", 2);
-      }
-      uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
-      const int show_i = show - sm.show0;
-#pragma unroll
-      for (int k = 0; k < kGroupCols; ++k) {
-        const int col = g * kGroupCols + k;
-        const CellDesc& d = tab.cell[col];
-        uint32_t c;
-        if (!d.per_entry) c = sm.shcell[col][show_i];
-        else if (d.kind == kCellNumber) c = pack_cell((uint32_t)kInBytes + (uint32_t)(r * kMaxNumberChars), sm.num_len[r]);
-        else if (d.blank_if_completed && completed) c = 0;
-        else c = pack_cell(sm.delta[col] + (uint32_t)cb[k], (uint32_t)cn[k]);
-        row_cells[k] = c;
-      }
-      uint32_t glen = 0;
-#pragma unroll 1
-      for (int k = 0; k < kGroupCols; ++k) {
-        const int col = g * kGroupCols + k;
-        const CellDesc& d = tab.cell[col];
-        uint32_t c = row_cells[k];
-        const int items = (col == kActionsCol) ? jitems : 1;
-        if (d.per_entry && d.kind != kCellNumber && ((sm.col_dirty[col] && (c >> 16)) || items > 1)) {
-          c = materialise_cell(sm, s_in, d.offsets, sm.delta[col], sm.col_dirty[col] != 0, c & 0xFFFFu, c >> 16, jl0,
-                               items);
-          row_cells[k] = c;
-        }
-        glen += (c >> 16) + 1u;  // + ',' (or the final '\n')
-      }
-      sm.group[g][r] = glen;
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t s = it & 1u, ph = (it >> 1) & 1u, par = it & 1u;
+    uint8_t* stage = s_dyn + kSmemOffStage + s * kStageStride;
+    char* s_num = reinterpret_cast<char*>(stage + kStageBytes);
+    const StageInfo& info = sm.info[s];
+    mbar_wait(smem_u32(&sm.full[s]), ph);  // the staged ranges have landed, info is visible
+    const int64_t tile = info.tile;
+    if (tile < 0) {
+      finish_pending();
+      if (tid == 0) sm.done = 1;
+      bar_arrive_workers_and_lookback<kBarTotalReady>();
+      return;
     }
-    __syncthreads();
-    slow = sm.slow != 0;  // the bump area overflowed
+    const int64_t e0 = tile * kRows;
+    const int rows = info.rows;
+    const bool have = r < rows;
+    bool slow = info.slow != 0;  // uniform
+    bool published = false;
+
     if (!slow) {
-      // ---- C. per-row scan over the groups, then block scan over the rows
-      if (tid < rows) {
-        uint32_t run = 0;
-#pragma unroll
-        for (int k = 0; k < kGroups; ++k) {
-          const uint32_t x = sm.group[k][tid];
-          sm.group[k][tid] = run;
-          run += x;
+      if (tid == 0) {
+        sm.bump = info.bump0;
+        sm.overflow = 0;
+      }
+      workers_sync();  // also: every worker has left the previous tile's write phase (cell / chunk tables)
+      // ---- cells 1. show-level cells once per show of the tile; entry-level cells: thread (r, g) takes
+      // the columns c_owned[g] (the expensive ones — Ryu, Array.join, free text — on different groups)
+      {
+        const uint32_t ns = info.n_tile_shows;
+        for (uint32_t idx = tid; idx < ns * kShowCols; idx += kWorkers) {
+          const uint32_t col = idx / ns, i = idx - col * ns;
+          const int32_t* o = stage_i32(stage, info.off_base[col]);
+          const int32_t f0 = o[i], f1 = o[i + 1];
+          int items = 1;
+          uint32_t b = (uint32_t)f0, n = (uint32_t)(f1 - f0);
+          const int32_t* io = nullptr;
+          if (tab.cell[col].kind == kCellJoined) {  // crew
+            items = f1 - f0;
+            b = 0;
+            n = 0;
+            io = stage_i32(stage, info.item_base[col]) + (f0 - info.item_first[col]);
+            if (items > 0) {
+              b = (uint32_t)io[0];
+              n = (uint32_t)io[items] - b;
+            }
+          }
+          const uint32_t src = (info.delta[col] + b) & 0xFFFFu;
+          uint32_t c = pack_cell(src, n);
+          if ((sm.col_dirty[col] && n) || items > 1)
+            c = materialise_cell(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
+          sm.shcell[col][i] = c;
         }
-        sm.group[0][tid] = run;  // group 0 starts at 0: the slot carries the row length into the scan
       }
-      __syncthreads();
-      scan_rows_and_publish();
-      published = true;
-      if (write && sm.tile_total > (uint32_t)kOutBytes) slow = true;  // uniform
-    }
-  }
-
-  if (slow) {
-    // ---- slow path (uniform for the CTA).  If the fast path already published this tile's total, the
-    // measure below recomputes the same row lengths; only the quote masks are new.
-    if (tid == 0) atomicAdd(sc.slow_tiles, 1u);
-    slow_measure(v, tab, sc, sm, s_num, qmask, e0, rows);
-    __syncthreads();
-    if (!published) scan_rows_and_publish();
-    if (!worker) look_back(sm.tile_total);
-    __syncthreads();
-    const unsigned long long base = sm.base;
-    if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + base + sm.row_start[tid]);
-    if (!write || base + sm.tile_total > capacity) return;
-    slow_write(tab, sc, sm, s_num, qmask, e0, rows, out_data + base);
-    return;
-  }
-
-  const uint32_t tile_total = sm.tile_total;
-  if (!write) {
-    if (!worker) look_back(tile_total);
-    __syncthreads();
-    if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + sm.base + sm.row_start[tid]);
-    return;
-  }
-
-  // ---- D. write.  chunk = bytes per thread (multiple of 16); x / chunk by multiplication.
-  if (!worker) {
-    look_back(tile_total);
-  } else {
-    const uint32_t chunk = 16u * ((tile_total + 16u * kWorkers - 1u) / (16u * kWorkers));
-    const uint32_t magic = (uint32_t)((0x100000000ull + chunk - 1u) / chunk);  // exact for x < 2^16
-    if (have) {
-      uint32_t o = sm.row_start[r] + (g ? sm.group[g][r] : 0u);
-      const uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
+      if (have) {
+        bool completed = false;  // entry.status === 'Completed' (:293-297); status precedes the cells it blanks
+        uint32_t* row_cells = sm.cell + r * kCellStride;
+#pragma unroll 1
+        for (int k = 0; k < kGroupCols; ++k) {
+          const int col = c_owned[g][k];
+          if (col < 0) break;
+          const CellDesc& d = tab.cell[col];
+          uint32_t c = 0;
+          if (d.kind == kCellNumber) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
+            int nl = 0;
+            if (stage[info.valid_base + r]) {
+              const RyuTables t{d_pow5_inv, d_pow5};
+              nl = js_number_to_string(*reinterpret_cast<const double*>(stage + info.delay_base + 8 * r),
+                                       s_num + r * kMaxNumberChars, t);
+            }
+            c = pack_cell((uint32_t)kStageBytes + (uint32_t)(r * kMaxNumberChars), (uint32_t)nl);
+          } else {
+            const int32_t* o = stage_i32(stage, info.off_base[col]);
+            const int32_t f0 = o[r], f1 = o[r + 1];
+            int items = 1;
+            uint32_t b = (uint32_t)f0, n = (uint32_t)(f1 - f0);
+            const int32_t* io = nullptr;
+            if (d.kind == kCellJoined) {  // actions
+              items = f1 - f0;
+              b = 0;
+              n = 0;
+              io = stage_i32(stage, info.item_base[col]) + (f0 - info.item_first[col]);
+              if (items > 0) {
+                b = (uint32_t)io[0];
+                n = (uint32_t)io[items] - b;
+              }
+            }
+            const uint32_t src = (info.delta[col] + b) & 0xFFFFu;
+            if (col == kStatusCol && n == 9) {
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
+              const uint32_t sh = (src & 3u) * 8u;
+              const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];  // the 9 bytes lie inside these three words
+              completed = __funnelshift_r(w0, w1, sh) == lit_word("Completed", 0) &&
+                          __funnelshift_r(w1, w2, sh) == lit_word("Completed", 1) &&
+                          (__funnelshift_r(w2, 0u, sh) & 0xFFu) == lit_word("Completed", 2);
+            }
+            if (!(d.blank_if_completed && completed)) {
+              c = pack_cell(src, n);
+              if ((sm.col_dirty[col] && n) || items > 1)
+                c = materialise_cell(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
+            }
+          }
+          row_cells[col] = c;
+        }
+      }
+      workers_sync();
+      // ---- cells 2. rows pick up their show's cells; bytes per group of 6 consecutive columns
+      if (have) {
+        uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
+        const int show_i = (g < 2) ? stage_i32(stage, info.show_idx_base)[r] - info.show0 : 0;
+        uint32_t glen = 0;
 #pragma unroll
-      for (int k = 0; k < kGroupCols; ++k) {
-        const uint32_t len = row_cells[k] >> 16;
-        const uint32_t k_lo = __umulhi(o + chunk - 1u, magic), k_hi = __umulhi(o + len, magic);
-        for (uint32_t kk = k_lo; kk <= k_hi; ++kk)  // chunk kk starts inside this cell (or on its separator)
-          sm.first[kk] = (uint32_t)(r * kCellStride + g * kGroupCols + k) | ((kk * chunk - o) << 12);
-        o += len + 1u;
+        for (int k = 0; k < kGroupCols; ++k) {
+          const int col = g * kGroupCols + k;
+          uint32_t c;
+          if (col < kShowCols) {
+            c = sm.shcell[col][show_i];
+            row_cells[k] = c;
+          } else {
+            c = row_cells[k];
+          }
+          glen += (c >> 16) + 1u;  // + ',' (or the final '\n')
+        }
+        sm.group[g][r] = glen;
+      }
+      workers_sync();
+      slow = sm.overflow != 0;  // the bump area ran out
+      if (!slow) {
+        // ---- scan: groups -> starts inside the row; rows -> starts inside the tile
+        if (tid < rows) {
+          uint32_t row_len = 0;
+#pragma unroll
+          for (int k = 0; k < kGroups; ++k) {
+            const uint32_t x = sm.group[k][tid];
+            sm.group[k][tid] = row_len;
+            row_len += x;
+          }
+          sm.group[0][tid] = row_len;  // group 0 starts at 0: the slot carries the row length into the scan
+        }
+        scan_rows_and_publish(tile, rows, par);
+        published = true;
+        if (write && sm.tile_total[par] > (uint32_t)kOutBytes) slow = true;  // uniform
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");  // workers only; the producer warp is looking back
-    const uint32_t begin = (uint32_t)tid * chunk;
-    if (begin < tile_total) {
-      uint32_t rem = min(chunk, tile_total - begin);  // bytes this thread produces
-      uint32_t* op = reinterpret_cast<uint32_t*>(s_out + begin);
-      const uint32_t f = sm.first[tid];
-      uint32_t idx = f & 0xFFFu, skip = f >> 12;
-      uint32_t c = idx % kCellStride;
-      unsigned long long acc = 0;
-      uint32_t fill = 0;  // bytes pending in acc: 0..3
-      for (;;) {
-        const uint32_t cell = sm.cell[idx];
-        const uint32_t src = (cell & 0xFFFFu) + skip;
-        uint32_t n = (cell >> 16) - skip;
-        skip = 0;
-        const uint32_t sep = (c == kCols - 1) ? (uint32_t)'\n' : (uint32_t)',';
-        const bool cut = n >= rem;  // the chunk ends inside this cell (its separator opens the next chunk)
-        if (cut) n = rem;
-        rem -= n;
-        if (n > 0) {
-          const uint32_t* w = reinterpret_cast<const uint32_t*>(s_in + (src & ~3u));
-          const uint32_t sh = (src & 3u) * 8u;
-          uint32_t cur = *w;
-          for (; n >= 4; n -= 4) {
-            const uint32_t nxt = *++w;
-            acc |= static_cast<unsigned long long>(__funnelshift_r(cur, nxt, sh)) << (8 * fill);
+
+    if (slow) {
+      // ---- slow path (uniform for the CTA).  If the fast path already published this tile's total, the
+      // measure below recomputes the same row lengths; only the quote masks are new.
+      finish_pending();
+      if (tid == 0) atomicAdd(sc.slow_tiles, 1u);
+      workers_sync();
+      slow_measure(v, tab, sc, sm, s_num, qmask, e0, rows);
+      workers_sync();
+      if (!published) scan_rows_and_publish(tile, rows, par);
+      const uint32_t tile_total = sm.tile_total[par];
+      bar_arrive_workers_and_lookback<kBarTotalReady>();
+      if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));  // nothing of the stage's staged ranges is read any more
+      bar_sync_workers_and_lookback<kBarBaseReady>();
+      const unsigned long long base = sm.base[par];
+      if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + base + sm.row_start[par][tid]);
+      if (write && base + tile_total <= capacity)
+        slow_write(tab, sc, sm, s_num, qmask, par, e0, rows, out_data + base);
+      workers_sync();  // qmask (= the chunk table) is free again
+      continue;
+    }
+
+    const uint32_t tile_total = sm.tile_total[par];
+    bar_arrive_workers_and_lookback<kBarTotalReady>();  // this tile's look-back starts now ...
+    finish_pending();                                   // ... while the previous tile leaves s_out
+    if (write) {
+      // ---- write.  chunk = bytes per thread (multiple of 16); x / chunk by multiplication.
+      const uint32_t chunk = 16u * ((tile_total + 16u * kWorkers - 1u) / (16u * kWorkers));
+      const uint32_t magic = (uint32_t)((0x100000000ull + chunk - 1u) / chunk);  // exact for x < 2^16
+      if (have) {
+        uint32_t o = sm.row_start[par][r] + (g ? sm.group[g][r] : 0u);
+        const uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
+#pragma unroll
+        for (int k = 0; k < kGroupCols; ++k) {
+          const uint32_t len = row_cells[k] >> 16;
+          const uint32_t k_lo = __umulhi(o + chunk - 1u, magic), k_hi = __umulhi(o + len, magic);
+          for (uint32_t kk = k_lo; kk <= k_hi; ++kk)  // chunk kk starts inside this cell (or on its separator)
+            sm.first[kk] = (uint32_t)(r * kCellStride + g * kGroupCols + k) | ((kk * chunk - o) << 12);
+          o += len + 1u;
+        }
+      }
+      workers_sync();  // the chunk table is complete; the previous tile has left s_out
+      const uint32_t begin = (uint32_t)tid * chunk;
+      if (begin < tile_total) {
+        uint32_t rem = min(chunk, tile_total - begin);  // bytes this thread produces
+        uint32_t* op = reinterpret_cast<uint32_t*>(s_out + begin);
+        const uint32_t f = sm.first[tid];
+        uint32_t idx = f & 0xFFFu, skip = f >> 12;
+        uint32_t c = idx % kCellStride;
+        unsigned long long acc = 0;
+        uint32_t fill = 0;  // bytes pending in acc: 0..3
+        for (;;) {
+          const uint32_t cell = sm.cell[idx];
+          const uint32_t src = (cell & 0xFFFFu) + skip;
+          uint32_t n = (cell >> 16) - skip;
+          skip = 0;
+          const uint32_t sep = (c == kCols - 1) ? (uint32_t)'\n' : (uint32_t)',';
+          const bool cut = n >= rem;  // the chunk ends inside this cell (its separator opens the next chunk)
+          if (cut) n = rem;
+          rem -= n;
+          if (n > 0) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
+            const uint32_t sh = (src & 3u) * 8u;
+            uint32_t cur = *w;
+            for (; n >= 4; n -= 4) {
+              const uint32_t nxt = *++w;
+              acc |= static_cast<unsigned long long>(__funnelshift_r(cur, nxt, sh)) << (8 * fill);
+              *op++ = static_cast<uint32_t>(acc);
+              acc >>= 32;
+              cur = nxt;
+            }
+            if (n > 0) {
+              const uint32_t x = __funnelshift_r(cur, w[1], sh) & ((1u << (8 * n)) - 1u);
+              acc |= static_cast<unsigned long long>(x) << (8 * fill);
+              fill += n;
+            }
+          }
+          if (!cut) {  // the separator
+            acc |= static_cast<unsigned long long>(sep) << (8 * fill);
+            ++fill;
+            --rem;
+          }
+          if (fill >= 4) {
             *op++ = static_cast<uint32_t>(acc);
             acc >>= 32;
-            cur = nxt;
+            fill -= 4;
           }
-          if (n > 0) {
-            const uint32_t x = __funnelshift_r(cur, w[1], sh) & ((1u << (8 * n)) - 1u);
-            acc |= static_cast<unsigned long long>(x) << (8 * fill);
-            fill += n;
+          if (rem == 0) break;
+          ++idx;
+          if (++c == kCols) {
+            c = 0;
+            ++idx;  // the pad slot
           }
         }
-        if (!cut) {  // the separator
-          acc |= static_cast<unsigned long long>(sep) << (8 * fill);
-          ++fill;
-          --rem;
-        }
-        if (fill >= 4) {
-          *op++ = static_cast<uint32_t>(acc);
-          acc >>= 32;
-          fill -= 4;
-        }
-        if (rem == 0) break;
-        ++idx;
-        if (++c == kCols) {
-          c = 0;
-          ++idx;  // the pad slot
-        }
+        if (fill) *op = static_cast<uint32_t>(acc);  // last chunk of the tile: the word is ours (+32 slack)
       }
-      if (fill) *op = static_cast<uint32_t>(acc);  // last chunk of the tile: the word is ours (+32 slack)
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));  // the stage may be refilled (two tiles ahead)
+    pending = true;
+    p_e0 = e0;
+    p_rows = rows;
+    p_total = tile_total;
+    p_par = par;
   }
-  __syncthreads();  // the tile is complete in shared memory and its offset is known
-  const unsigned long long base = sm.base;
-  if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + base + sm.row_start[tid]);
-  if (base + tile_total > capacity) return;
-
-  // ---- E. flush s_out[0 .. tile_total) -> out_data[base ..) with 16-byte stores.  Global chunk k
-  // starts at the first 16-byte boundary >= out_data+base, i.e. at tile offset head + 16k, which has
-  // an arbitrary phase in shared memory: read 5 aligned words and funnel-shift.
-  uint8_t* __restrict__ dst = out_data + base;
-  const uint32_t head_raw = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
-  const uint32_t head = head_raw < tile_total ? head_raw : tile_total;
-  for (uint32_t k = tid; k < head; k += kCtaThreads) dst[k] = s_out[k];
-  const uint32_t n_chunks = (tile_total - head) >> 4;
-  const uint32_t sh = (head & 3u) * 8u;
-  const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(s_out) + (head >> 2);
-  for (uint32_t k = tid; k < n_chunks; k += kCtaThreads) {
-    const uint32_t* w = sw + 4 * k;
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];  // w[4] stays inside the +32 slack
-    uint4 o;
-    o.x = __funnelshift_r(w0, w1, sh);
-    o.y = __funnelshift_r(w1, w2, sh);
-    o.z = __funnelshift_r(w2, w3, sh);
-    o.w = __funnelshift_r(w3, w4, sh);
-    *reinterpret_cast<uint4*>(dst + head + 16u * k) = o;
-  }
-  for (uint32_t k = head + 16u * n_chunks + tid; k < tile_total; k += kCtaThreads) dst[k] = s_out[k];
 }
 
 cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
@@ -881,12 +1068,18 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
     if (err != cudaSuccess) return err;
     return cudaMemcpyAsync(row_offsets, total_out, 8, cudaMemcpyDeviceToDevice, stream);  // 0; the caller adds its bias
   }
-  static int configured_device = -1;
+  static int configured_device = -1, resident_ctas = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_device != dev) {
     err = cudaFuncSetAttribute(csv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return err;
+    int per_sm = 0, sms = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csv_rows_kernel, kCtaThreads, kSmemBytes);
+    if (err != cudaSuccess) return err;
+    err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (err != cudaSuccess) return err;
+    resident_ctas = (per_sm > 0 ? per_sm : 1) * sms;  // persistent: one wave of CTAs loops over the tiles
     configured_device = dev;
   }
   expand_entry_show_kernel<<<(unsigned)((v.n_shows + 255) / 256), 256, 0, stream>>>(v, sc.entry_show);
@@ -897,8 +1090,10 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
     if (blocks < 1) blocks = 1;
     column_dirty_kernel<<<dim3((unsigned)blocks, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries, sc.col_dirty);
   }
-  csv_rows_kernel<<<(unsigned)csv_tiles(v.n_entries), kCtaThreads, kSmemBytes, stream>>>(
-      v, tab, sc, row_offsets, out_data, capacity, bias, total_out, g_force_slow);
+  const int64_t tiles = csv_tiles(v.n_entries);
+  const unsigned grid = (unsigned)(tiles < resident_ctas ? tiles : resident_ctas);
+  csv_rows_kernel<<<grid, kCtaThreads, kSmemBytes, stream>>>(v, tab, sc, row_offsets, out_data, capacity, bias,
+                                                            total_out, g_force_slow);
   g_launches += 3;
   return cudaGetLastError();
 }

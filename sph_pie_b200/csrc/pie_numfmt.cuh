@@ -93,6 +93,33 @@ PIE_HD void shortest_decimal(uint64_t ieee_mantissa, uint32_t ieee_exponent, con
       }
     }
   }
+  // short exact decimals (halves, quarters, eighths ... of moderate size): x = odd * 2^-f is exactly the
+  // decimal (odd * 5^f) * 10^-f.  With at most 15 significant digits that decimal is THE shortest
+  // round-trip string: two different decimals of <= 15 digits never round to the same double
+  // (DBL_DIG), so no shorter one can sit in x's rounding interval; and it ends in no zero (odd * 5^f
+  // is odd).  Skips the general path's digit-by-digit removal of ~15 trailing zeros.
+  if (ieee_exponent != 0) {
+    const int32_t e2i = (int32_t)ieee_exponent - 1023 - 52;
+    if (e2i < 0 && e2i >= -62) {
+      const uint64_t m2i = (1ull << 52) | ieee_mantissa;
+#if defined(__CUDA_ARCH__)
+      const int32_t tz = __ffsll((long long)m2i) - 1;
+#else
+      const int32_t tz = __builtin_ctzll(m2i);
+#endif
+      const int32_t f = -e2i - tz;  // fractional bits of x (> 0: integers were handled above)
+      if (f > 0 && f <= 10) {
+        uint64_t p5 = 1;
+        for (int32_t i = 0; i < f; ++i) p5 *= 5;
+        const uint64_t odd = m2i >> tz;
+        if (odd <= 999999999999999ull / p5) {
+          *out_mantissa = odd * p5;
+          *out_exponent = -f;
+          return;
+        }
+      }
+    }
+  }
   int32_t e2;
   uint64_t m2;
   if (ieee_exponent == 0) {

@@ -19,7 +19,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def numfmt_host():
     src = os.path.join(HERE, "native", "numfmt_host.cpp")
     so = os.path.join(HERE, "native", "libnumfmt_host.so")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    csrc = os.path.join(HERE, "..", "sph_pie_b200", "csrc")
+    deps = [src, os.path.join(csrc, "pie_numfmt.cuh"), os.path.join(csrc, "ryu_tables.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
     lib = C.CDLL(so)
 
@@ -48,7 +50,11 @@ def number_samples(n, seed):
         np.array(SPECIAL), rng.integers(0, 2 ** 64, n, dtype=np.uint64).view(np.float64),
         rng.integers(-10 ** 6, 10 ** 6, n).astype(np.float64), np.round(rng.random(n) * 1000, 2),
         rng.random(n) * rng.choice([1e-9, 1e-3, 1, 1e3, 1e15, 1e25], n), 2.0 ** rng.integers(-1074, 1024, n),
-        10.0 ** rng.integers(-320, 309, n), rng.integers(1, 2 ** 52, n, dtype=np.uint64).view(np.float64)])
+        10.0 ** rng.integers(-320, 309, n), rng.integers(1, 2 ** 52, n, dtype=np.uint64).view(np.float64),
+        # short exact binary fractions k / 2^f at every size (the exact-decimal shortcut and its 15-digit limit)
+        rng.integers(1, 2 ** 20, n).astype(np.float64) / 2.0 ** rng.integers(1, 14, n),
+        rng.integers(1, 2 ** 53, n).astype(np.float64) / 2.0 ** rng.integers(1, 64, n),
+        (10.0 ** rng.integers(9, 16, n) + rng.integers(0, 1000, n)) / 2.0 ** rng.integers(0, 12, n)])
 
 
 def test_number_to_string_three_ways(built, numfmt_host):
