@@ -22,10 +22,10 @@
 //            Number::toString (Ryu) output lives next to it; cells blanked by status === 'Completed'
 //            get len 0.
 //     scan   per-row and per-tile sizes; the tile's aggregate is published.
-//     write  the OUTPUT is partitioned: the tile's bytes are cut into equal 16-byte-multiple chunks,
-//            one per thread.  The cell that contains a chunk's first byte registers itself in a table,
-//            so a thread starts there and streams cells into its own aligned words of the shared
-//            output tile — no byte stores, no races, the same work per thread whatever the row lengths.
+//     write  thread (row, group of 6 consecutive columns) streams its cells into the shared output tile
+//            through a byte accumulator (aligned 32-bit stores; byte stores only for the group's first
+//            and last word).  A warp = 32 consecutive rows on the same column at every step, so the
+//            cells it handles together are alike in length.
 //     flush  16-byte coalesced stores; the tile is re-aligned to the destination with a funnel shift.
 //   look-back warp  decoupled look-back over the published tile totals while the workers write.
 // A tile that does not fit (very long free text, more than kMaxTileShows shows) takes a slow path:
@@ -69,7 +69,6 @@ constexpr int kMaxTileShows = kRows;           // shows a tile may span on the f
 constexpr int kCellStride = kCols + 1;         // padded: lanes = consecutive rows hit distinct banks
 static_assert(kRows % 32 == 0 && kGroups * kGroupCols == kCols, "tile shape");
 static_assert(kStageBytes + kNumBytes <= 65536, "cell sources are 16-bit offsets into a stage");
-static_assert(kOutBytes <= 65536 - 256 && kRows * kCellStride < 4096, "chunk table packs (cell:12, skip:16)");
 static_assert(kStageStride % 16 == 0, "stages are 16-byte aligned");
 
 constexpr unsigned long long kStatusShift = 62;
@@ -284,7 +283,7 @@ struct CsvSmem {
   StageInfo info[2];
   uint32_t cell[kRows * kCellStride];           // (src:16 | len:16 << 16) of cell (r, c) at r*kCellStride + c
   uint32_t shcell[kShowCols][kMaxTileShows];    // the same for the show-level cells of the tile's shows
-  uint32_t first[kWorkers];                     // chunk k starts inside cell (idx:12) at byte (skip << 12)
+  uint32_t qmask[kRows];                        // slow path: per-row quote masks
   uint32_t group[kGroups][kRows];               // bytes of a row's group
   uint32_t row_start[2][kRows];                 // byte offset of the row inside the tile, by tile parity
   uint32_t col_dirty[kCols];
@@ -357,11 +356,9 @@ __device__ __noinline__ uint32_t materialise_cell(CsvSmem& sm, uint8_t* stage, c
     stage[p + 4 + n] = '"';  // after the word stores: the last word may have spilled past the content
     return pack_cell(p + 3, n + 2);
   }
-  uint32_t nq = 0;
-  if (has_quote)
-    for (uint32_t j = 0; j < n; ++j) nq += (stage[src + j] == '"');
-  const uint32_t out_len = n + (items > 1 ? (uint32_t)(items - 1) : 0u) + (special ? 2u + nq : 0u);
-  const uint32_t alloc = (out_len + 3u) & ~3u;
+  // '"' to double and / or items to join: byte-wise, in one pass, into a worst-case sized allocation
+  const uint32_t worst = (has_quote ? 2u * n : n) + (items > 1 ? (uint32_t)(items - 1) : 0u) + 2u;
+  const uint32_t alloc = (worst + 3u) & ~3u;
   const uint32_t p = atomicAdd(&sm.bump, alloc);
   if (p + alloc > (uint32_t)kStageBytes) {
     sm.overflow = 1;
@@ -381,6 +378,7 @@ __device__ __noinline__ uint32_t materialise_cell(CsvSmem& sm, uint8_t* stage, c
     ib = ie;
   }
   if (special) stage[q++] = '"';
+  const uint32_t out_len = q - p;
   return pack_cell(p, out_len);
 }
 
@@ -738,7 +736,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
   // ================= workers =================
   const bool write = out_data != nullptr;
   const int g = tid / kRows, r = tid % kRows;
-  uint32_t* qmask = sm.first;  // slow path: per-row quote masks live in the chunk table
+  uint32_t* qmask = sm.qmask;
 
   // rows' lengths in sm.group[0][*] -> sm.row_start[par], sm.tile_total[par]; the aggregate is published
   auto scan_rows_and_publish = [&](int64_t tile, int rows, uint32_t par) {
@@ -831,7 +829,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
         sm.bump = info.bump0;
         sm.overflow = 0;
       }
-      workers_sync();  // also: every worker has left the previous tile's write phase (cell / chunk tables)
+      workers_sync();  // also: every worker has left the previous tile's write phase (cell table)
       // ---- cells 1. show-level cells once per show of the tile; entry-level cells: thread (r, g) takes
       // the columns c_owned[g] (the expensive ones — Ryu, Array.join, free text — on different groups)
       {
@@ -968,7 +966,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + base + sm.row_start[par][tid]);
       if (write && base + tile_total <= capacity)
         slow_write(tab, sc, sm, s_num, qmask, par, e0, rows, out_data + base);
-      workers_sync();  // qmask (= the chunk table) is free again
+      workers_sync();  // qmask / row lengths are free again
       continue;
     }
 
@@ -976,75 +974,58 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     bar_arrive_workers_and_lookback<kBarTotalReady>();  // this tile's look-back starts now ...
     finish_pending();                                   // ... while the previous tile leaves s_out
     if (write) {
-      // ---- write.  chunk = bytes per thread (multiple of 16); x / chunk by multiplication.
-      const uint32_t chunk = 16u * ((tile_total + 16u * kWorkers - 1u) / (16u * kWorkers));
-      const uint32_t magic = (uint32_t)((0x100000000ull + chunk - 1u) / chunk);  // exact for x < 2^16
+      // ---- write.  Thread (r, g) streams its 6 consecutive cells into the shared output tile.  Lanes of
+      // a warp = 32 consecutive rows on the SAME column at every step, so cell lengths (and with them the
+      // trip counts of the word loop) are alike.  Bytes collect in a (lo, hi) accumulator and leave as
+      // aligned 32-bit stores; only the group's first and last word, which it shares with its neighbours,
+      // are stored byte by byte.
+      workers_sync();  // the previous tile has left s_out
       if (have) {
-        uint32_t o = sm.row_start[par][r] + (g ? sm.group[g][r] : 0u);
+        const uint32_t o = sm.row_start[par][r] + (g ? sm.group[g][r] : 0u);
         const uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
+        const uint32_t lead = o & 3u;
+        uint8_t* op = s_out + (o & ~3u);  // aligned address of the word being filled
+        uint32_t lo = 0, fill = lead;     // `lead` placeholder bytes stand for the neighbour's bytes
+        bool shared_word = lead != 0;
+        auto store_word = [&](uint32_t v) {
+          if (shared_word) {
+            for (uint32_t b = lead; b < 4; ++b) op[b] = static_cast<uint8_t>(v >> (8 * b));
+            shared_word = false;
+          } else {
+            *reinterpret_cast<uint32_t*>(op) = v;
+          }
+          op += 4;
+        };
 #pragma unroll
         for (int k = 0; k < kGroupCols; ++k) {
-          const uint32_t len = row_cells[k] >> 16;
-          const uint32_t k_lo = __umulhi(o + chunk - 1u, magic), k_hi = __umulhi(o + len, magic);
-          for (uint32_t kk = k_lo; kk <= k_hi; ++kk)  // chunk kk starts inside this cell (or on its separator)
-            sm.first[kk] = (uint32_t)(r * kCellStride + g * kGroupCols + k) | ((kk * chunk - o) << 12);
-          o += len + 1u;
-        }
-      }
-      workers_sync();  // the chunk table is complete; the previous tile has left s_out
-      const uint32_t begin = (uint32_t)tid * chunk;
-      if (begin < tile_total) {
-        uint32_t rem = min(chunk, tile_total - begin);  // bytes this thread produces
-        uint32_t* op = reinterpret_cast<uint32_t*>(s_out + begin);
-        const uint32_t f = sm.first[tid];
-        uint32_t idx = f & 0xFFFu, skip = f >> 12;
-        uint32_t c = idx % kCellStride;
-        unsigned long long acc = 0;
-        uint32_t fill = 0;  // bytes pending in acc: 0..3
-        for (;;) {
-          const uint32_t cell = sm.cell[idx];
-          const uint32_t src = (cell & 0xFFFFu) + skip;
-          uint32_t n = (cell >> 16) - skip;
-          skip = 0;
-          const uint32_t sep = (c == kCols - 1) ? (uint32_t)'\n' : (uint32_t)',';
-          const bool cut = n >= rem;  // the chunk ends inside this cell (its separator opens the next chunk)
-          if (cut) n = rem;
-          rem -= n;
-          if (n > 0) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
-            const uint32_t sh = (src & 3u) * 8u;
-            uint32_t cur = *w;
-            for (; n >= 4; n -= 4) {
-              const uint32_t nxt = *++w;
-              acc |= static_cast<unsigned long long>(__funnelshift_r(cur, nxt, sh)) << (8 * fill);
-              *op++ = static_cast<uint32_t>(acc);
-              acc >>= 32;
-              cur = nxt;
-            }
-            if (n > 0) {
-              const uint32_t x = __funnelshift_r(cur, w[1], sh) & ((1u << (8 * n)) - 1u);
-              acc |= static_cast<unsigned long long>(x) << (8 * fill);
-              fill += n;
-            }
+          const uint32_t cell = row_cells[k];
+          const uint32_t src = cell & 0xFFFFu;
+          uint32_t n = cell >> 16;
+          const uint32_t sep = (g == kGroups - 1 && k == kGroupCols - 1) ? (uint32_t)'\n' : (uint32_t)',';
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
+          const uint32_t sh = (src & 3u) * 8u;
+          const uint32_t osh = 8u * fill, csh = 32u - osh;  // appending 4 bytes leaves `fill` unchanged
+          uint32_t cur = n ? *w : 0u;
+          for (; n >= 4; n -= 4) {
+            const uint32_t nxt = *++w;
+            const uint32_t x = __funnelshift_r(cur, nxt, sh);
+            cur = nxt;
+            store_word(lo | (x << osh));
+            lo = __funnelshift_rc(x, 0u, csh);  // clamped: fill == 0 gives 0
           }
-          if (!cut) {  // the separator
-            acc |= static_cast<unsigned long long>(sep) << (8 * fill);
-            ++fill;
-            --rem;
-          }
+          // the 0..3 last bytes and the separator ride in one piece of 1..4 bytes
+          uint32_t x = sep << (8 * n);
+          if (n) x |= __funnelshift_r(cur, w[1], sh) & ((1u << (8 * n)) - 1u);
+          const uint32_t hi = __funnelshift_rc(x, 0u, csh);
+          lo |= x << osh;
+          fill += n + 1u;
           if (fill >= 4) {
-            *op++ = static_cast<uint32_t>(acc);
-            acc >>= 32;
+            store_word(lo);
+            lo = hi;
             fill -= 4;
           }
-          if (rem == 0) break;
-          ++idx;
-          if (++c == kCols) {
-            c = 0;
-            ++idx;  // the pad slot
-          }
         }
-        if (fill) *op = static_cast<uint32_t>(acc);  // last chunk of the tile: the word is ours (+32 slack)
+        for (uint32_t b = shared_word ? lead : 0u; b < fill; ++b) op[b] = static_cast<uint8_t>(lo >> (8 * b));
       }
     }
     __syncwarp();
