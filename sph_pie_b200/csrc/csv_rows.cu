@@ -33,6 +33,9 @@
 #include "pie_device.cuh"
 #include "pie_kernels.h"
 #include "pie_numfmt.cuh"
+#ifdef PIE_CSV_PROFILE
+#include <cstdio>
+#endif
 
 namespace pie {
 
@@ -59,7 +62,9 @@ constexpr int kWorkers = kRows * kGroups;      // worker threads: (row, group of
 constexpr int kWorkerWarps = kWorkers / 32;
 constexpr int kProducerWarp = kWorkerWarps;    // stages the next tile
 constexpr int kLookbackWarp = kWorkerWarps + 1;
-constexpr int kCtaThreads = kWorkers + 64;
+constexpr int kNumberWarp0 = kWorkerWarps + 2;  // Number::toString for the NEXT tile: a row per lane
+constexpr int kNumberWarps = kRows / 32;
+constexpr int kCtaThreads = kWorkers + 64 + 32 * kNumberWarps;
 constexpr int kOutBytes = PIE_CSV_OUT_KB * 1024;      // shared output tile (rows of ~280 B -> ~36 KB per 128 rows)
 constexpr int kStageBytes = PIE_CSV_STAGE_KB * 1024;  // one stage: column bytes + offset arrays + bump area
 constexpr int kNumBytes = kRows * kMaxNumberChars;    // Number::toString output, behind the stage
@@ -85,15 +90,16 @@ struct CsvScratch {
 };
 
 static inline uint64_t align256(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
+constexpr uint64_t kCtlBytes = 2048;  // tile counter, slow-tile counter, column flags; developer counters from byte 256
 __host__ __device__ static inline int64_t csv_tiles(int64_t n_entries) { return (n_entries + kRows - 1) / kRows; }
 
 uint64_t csv_scratch_bytes(int64_t n_entries) {
   const uint64_t e = (uint64_t)(n_entries > 0 ? n_entries : 1);
-  return align256(8 * (uint64_t)csv_tiles(e)) + 256 + align256(4 * e);
+  return align256(8 * (uint64_t)csv_tiles(e)) + kCtlBytes + align256(4 * e);
 }
 uint64_t csv_scratch_zero_bytes(int64_t n_entries) {  // leading part that must be zero at launch
   const uint64_t e = (uint64_t)(n_entries > 0 ? n_entries : 1);
-  return align256(8 * (uint64_t)csv_tiles(e)) + 256;
+  return align256(8 * (uint64_t)csv_tiles(e)) + kCtlBytes;
 }
 static CsvScratch carve_csv(void* scratch, int64_t n_entries) {
   const uint64_t e = (uint64_t)(n_entries > 0 ? n_entries : 1);
@@ -103,7 +109,7 @@ static CsvScratch carve_csv(void* scratch, int64_t n_entries) {
   s.tile_counter = (unsigned int*)p;
   s.slow_tiles = (unsigned int*)(p + 16);
   s.col_dirty = (unsigned int*)(p + 64);
-  p += 256;
+  p += kCtlBytes;
   s.entry_show = (int32_t*)p;
   return s;
 }
@@ -116,6 +122,16 @@ int csv_set_force_slow(int on) {
 }
 cudaError_t csv_read_slow_tiles(const void* scratch, int64_t n_entries, unsigned int* out, cudaStream_t stream) {
   CsvScratch sc = carve_csv(const_cast<void*>(scratch), n_entries);
+#ifdef PIE_CSV_PROFILE
+  {
+    unsigned long long ph[64];
+    cudaMemcpy(ph, sc.tile_counter + 64, sizeof(ph), cudaMemcpyDeviceToHost);
+    const long long tiles = csv_tiles(n_entries);
+    for (int i = 0; i < 12; ++i)
+      fprintf(stderr, "phase %2d: cycles per tile, first thread of group 0..3: %7llu %7llu %7llu %7llu\n", i,
+              ph[i] / tiles, ph[16 + i] / tiles, ph[32 + i] / tiles, ph[48 + i] / tiles);
+  }
+#endif
   cudaError_t err = cudaMemcpyAsync(out, sc.slow_tiles, 4, cudaMemcpyDeviceToHost, stream);
   if (err != cudaSuccess) return err;
   return cudaStreamSynchronize(stream);
@@ -174,10 +190,10 @@ static RowTable make_row_table(const pie_archive_view& v) {
 }
 constexpr int kStatusCol = 12;
 // Entry-level columns whose cells worker group g prepares.  The heavy ones sit on different groups:
-// delaySec (Ryu) on 0, actions (Array.join) on 1, the issue block on 2, notes (free text) on 3; status (12)
-// comes before the columns it blanks (13..17).
+// actions (Array.join) on 1, the issue block on 2, notes (free text) on 3; status (12) comes before the columns
+// it blanks (13..17); delaySec (21, formatted by the number warps) last on its group.
 __constant__ signed char c_owned[4][6] = {
-    {21, -1, -1, -1, -1, -1}, {8, 9, 10, 11, 18, -1}, {12, 13, 14, 15, 16, 17}, {19, 20, 22, 23, -1, -1}};
+    {8, 9, 10, 21, -1, -1}, {11, 18, 19, 20, -1, -1}, {12, 13, 14, 15, 16, 17}, {22, 23, -1, -1, -1, -1}};
 
 // ---- pre-pass: which columns can need quoting at all? -----------------------------------------------
 // Most columns of an archive (ids, dates, enumerations, names) never contain " , \n or \r.  One
@@ -278,7 +294,8 @@ struct StageInfo {
 };
 struct CsvSmem {
   unsigned long long full[2];                   // producer -> workers: stage s holds a tile
-  unsigned long long empty[2];                  // workers -> producer: stage s may be overwritten
+  unsigned long long empty[2];                  // workers + number warps -> producer: stage s may be overwritten
+  unsigned long long nums[2];                   // number warps -> workers: the stage's delaySec strings are ready
   unsigned long long base[2];                   // global byte offset of the tile (look-back result), by tile parity
   StageInfo info[2];
   uint32_t cell[kRows * kCellStride];           // (src:16 | len:16 << 16) of cell (r, c) at r*kCellStride + c
@@ -293,7 +310,7 @@ struct CsvSmem {
   uint32_t bump;                                // next free byte of the current stage's bump area
   uint32_t overflow;                            // the bump area ran out
   uint32_t done;
-  uint8_t num_len[kRows];
+  uint8_t num_len[2][kRows];                    // by stage
 };
 constexpr int kSmemOffStage = kOutBytes + 32;
 constexpr int kSmemOffState = kSmemOffStage + 2 * kStageStride;
@@ -325,6 +342,68 @@ __device__ __forceinline__ uint32_t smem_special_and_quotes(const uint8_t* stage
   return flags;
 }
 
+// Byte stream into shared memory: bytes collect in an accumulator and leave as aligned 32-bit stores.
+// kSharedEdges: the first and the last word are shared with other threads' streams and are stored byte by
+// byte; otherwise the stream owns whole words (a 4-byte aligned, padded allocation).
+template <bool kSharedEdges>
+struct ByteStream {
+  uint8_t* op;    // aligned address of the word being filled
+  uint32_t lo;    // its bytes so far
+  uint32_t fill;  // how many (including `lead` placeholders before the first store)
+  uint32_t lead;
+  bool shared_word;
+
+  __device__ __forceinline__ void init(uint8_t* start) {
+    lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(start) & 3u);
+    op = start - lead;
+    lo = 0;
+    fill = lead;
+    shared_word = kSharedEdges && lead != 0;
+  }
+  __device__ __forceinline__ void store_word(uint32_t v) {
+    if (kSharedEdges && shared_word) {
+      for (uint32_t b = lead; b < 4; ++b) op[b] = static_cast<uint8_t>(v >> (8 * b));
+      shared_word = false;
+    } else {
+      *reinterpret_cast<uint32_t*>(op) = v;
+    }
+    op += 4;
+  }
+  // stage[src .. src+n) followed by `nsep` (0 or 1) separator byte(s) `sep`
+  __device__ __forceinline__ void append(const uint8_t* stage, uint32_t src, uint32_t n, uint32_t sep, uint32_t nsep) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
+    const uint32_t sh = (src & 3u) * 8u;
+    const uint32_t osh = 8u * fill, csh = 32u - osh;  // appending 4 bytes leaves `fill` unchanged
+    uint32_t cur = n ? *w : 0u;
+    for (; n >= 4; n -= 4) {
+      const uint32_t nxt = *++w;
+      const uint32_t x = __funnelshift_r(cur, nxt, sh);
+      cur = nxt;
+      store_word(lo | (x << osh));
+      lo = __funnelshift_rc(x, 0u, csh);  // clamped: fill == 0 gives 0
+    }
+    // the 0..3 last bytes and the separator ride in one piece of 0..4 bytes
+    uint32_t x = nsep ? sep << (8 * n) : 0u;
+    if (n) x |= __funnelshift_r(cur, w[1], sh) & ((1u << (8 * n)) - 1u);
+    const uint32_t hi = __funnelshift_rc(x, 0u, csh);
+    lo |= x << osh;
+    fill += n + nsep;
+    if (fill >= 4) {
+      store_word(lo);
+      lo = hi;
+      fill -= 4;
+    }
+  }
+  __device__ __forceinline__ void put(uint32_t byte) { append(nullptr, 0, 0, byte, 1); }
+  __device__ __forceinline__ void finish() {
+    if (kSharedEdges) {
+      for (uint32_t b = shared_word ? lead : 0u; b < fill; ++b) op[b] = static_cast<uint8_t>(lo >> (8 * b));
+    } else if (fill) {
+      *reinterpret_cast<uint32_t*>(op) = lo;
+    }
+  }
+};
+
 // Rare path: a cell that needs csvEscape (:332-338) and / or Array.prototype.join('|') (:284, :298) is
 // written out in the bump area.  stage[src .. src+n) = the cell's staged bytes (for a list: all its
 // items, which are contiguous in the heap); items > 1 inserts '|' at the item boundaries, which are
@@ -334,30 +413,31 @@ __device__ __noinline__ uint32_t materialise_cell(CsvSmem& sm, uint8_t* stage, c
   uint32_t has_quote = 0;
   const bool special = dirty && n > 0 && smem_special_and_quotes(stage, src, n, has_quote) != 0;
   if (!special && items <= 1) return pack_cell(src, n);
-  if (items <= 1 && !has_quote) {
-    // '"' + the bytes + '"', nothing to double: word-wise copy into a 4-byte aligned allocation whose
-    // content starts on a word boundary (the opening quote is the byte before it)
-    const uint32_t words = (n + 3) >> 2;
-    const uint32_t p = atomicAdd(&sm.bump, 4u * words + 8u);  // bump stays 4-byte aligned
-    if (p + 4u * words + 8u > (uint32_t)kStageBytes) {
+  if (!has_quote) {
+    // nothing to double: ['"'] item ['|' item]... ['"'] through the word-wise stream, into a 4-byte aligned
+    // allocation (the stream may fill its last word past the content)
+    const uint32_t out_len = n + (items > 1 ? (uint32_t)(items - 1) : 0u) + (special ? 2u : 0u);
+    const uint32_t alloc = (out_len + 3u) & ~3u;
+    const uint32_t p = atomicAdd(&sm.bump, alloc);  // bump stays 4-byte aligned
+    if (p + alloc > (uint32_t)kStageBytes) {
       sm.overflow = 1;  // benign race: every writer stores 1
       return 0;
     }
-    stage[p + 3] = '"';
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
-    const uint32_t sh = (src & 3u) * 8u;
-    uint32_t* o = reinterpret_cast<uint32_t*>(stage + p + 4);
-    uint32_t cur = w[0];
-    for (uint32_t k = 0; k < words; ++k) {
-      const uint32_t nxt = w[k + 1];
-      o[k] = __funnelshift_r(cur, nxt, sh);
-      cur = nxt;
+    ByteStream<false> out;
+    out.init(stage + p);
+    if (special) out.put('"');
+    uint32_t ib = src;
+    for (int it = 0; it < items; ++it) {
+      const bool last = it + 1 >= items;
+      const uint32_t ie = last ? src + n : delta + (uint32_t)item_offsets[it + 1];
+      out.append(stage, ib, ie - ib, last ? (uint32_t)'"' : (uint32_t)'|', (last && !special) ? 0u : 1u);
+      ib = ie;
     }
-    stage[p + 4 + n] = '"';  // after the word stores: the last word may have spilled past the content
-    return pack_cell(p + 3, n + 2);
+    out.finish();
+    return pack_cell(p, out_len);
   }
   // '"' to double and / or items to join: byte-wise, in one pass, into a worst-case sized allocation
-  const uint32_t worst = (has_quote ? 2u * n : n) + (items > 1 ? (uint32_t)(items - 1) : 0u) + 2u;
+  const uint32_t worst = 2u * n + (items > 1 ? (uint32_t)(items - 1) : 0u) + 2u;
   const uint32_t alloc = (worst + 3u) & ~3u;
   const uint32_t p = atomicAdd(&sm.bump, alloc);
   if (p + alloc > (uint32_t)kStageBytes) {
@@ -408,7 +488,7 @@ __device__ __forceinline__ SlowCell slow_locate(const CellDesc& d, int64_t i) {
 
 // Row lengths (sm.group[0][r]) and per-row quote masks (bit c: cell c is quoted; bit 31: Completed).
 __device__ __noinline__ void slow_measure(const pie_archive_view& v, const RowTable& tab, const CsvScratch& sc,
-                                          CsvSmem& sm, char* s_num, uint32_t* qmask, int64_t e0, int rows) {
+                                          CsvSmem& sm, char* s_num, uint32_t* qmask, uint32_t s, int64_t e0, int rows) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int r = wid; r < rows; r += kWorkerWarps) {
     const int64_t e = e0 + r;
@@ -429,7 +509,7 @@ __device__ __noinline__ void slow_measure(const pie_archive_view& v, const RowTa
           nl = js_number_to_string(v.delay_sec[e], s_num + r * kMaxNumberChars, t);
         }
         nl = __shfl_sync(0xFFFFFFFFu, nl, 0);
-        if (lane == 0) sm.num_len[r] = (uint8_t)nl;
+        if (lane == 0) sm.num_len[s][r] = (uint8_t)nl;
         cl = (uint32_t)nl;
       } else if (!(d.blank_if_completed && completed)) {
         const SlowCell c = slow_locate(d, d.per_entry ? e : show);
@@ -476,7 +556,7 @@ __device__ __forceinline__ void slow_copy(uint8_t* __restrict__ dst, uint32_t& p
 }
 
 __device__ __noinline__ void slow_write(const RowTable& tab, const CsvScratch& sc, CsvSmem& sm, const char* s_num,
-                                        const uint32_t* qmask, uint32_t par, int64_t e0, int rows,
+                                        const uint32_t* qmask, uint32_t s, uint32_t par, int64_t e0, int rows,
                                         uint8_t* __restrict__ out) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int r = wid; r < rows; r += kWorkerWarps) {
@@ -490,7 +570,7 @@ __device__ __noinline__ void slow_write(const RowTable& tab, const CsvScratch& s
       const CellDesc& d = tab.cell[col];
       const uint8_t sep = (col == kCols - 1) ? (uint8_t)'\n' : (uint8_t)',';
       if (d.kind == kCellNumber) {
-        const int nl = sm.num_len[r];
+        const int nl = sm.num_len[s][r];
         if (lane < nl) dst[pos + lane] = (uint8_t)s_num[r * kMaxNumberChars + lane];
         pos += (uint32_t)nl;
       } else if (!(d.blank_if_completed && completed)) {
@@ -680,6 +760,22 @@ __device__ __forceinline__ void look_back(const CsvScratch& sc, CsvSmem& sm, uin
   }
 }
 
+// Developer instrumentation (-DPIE_CSV_PROFILE): cycles worker thread 0 spends between phase boundaries,
+// summed over tiles into 64-bit counters from byte 256 of the scratch control block, [group][phase].  Compiled out by default.
+#ifdef PIE_CSV_PROFILE
+#define PIE_PHASE(i)                                                                                   \
+  do {                                                                                                 \
+    if (r == 0) {                                                                                      \
+      const long long now_ = clock64();                                                                \
+      atomicAdd(reinterpret_cast<unsigned long long*>(sc.tile_counter + 64) + g * 16 + (i),            \
+                (unsigned long long)(now_ - t_phase));                                                 \
+      t_phase = now_;                                                                                  \
+    }                                                                                                  \
+  } while (0)
+#else
+#define PIE_PHASE(i) do { } while (0)
+#endif
+
 // ---- the kernel ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab, CsvScratch sc,
@@ -694,8 +790,10 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
   if (tid == 0) {
     mbar_init(smem_u32(&sm.full[0]), 1);
     mbar_init(smem_u32(&sm.full[1]), 1);
-    mbar_init(smem_u32(&sm.empty[0]), kWorkerWarps);
-    mbar_init(smem_u32(&sm.empty[1]), kWorkerWarps);
+    mbar_init(smem_u32(&sm.empty[0]), kWorkerWarps + kNumberWarps);
+    mbar_init(smem_u32(&sm.empty[1]), kWorkerWarps + kNumberWarps);
+    mbar_init(smem_u32(&sm.nums[0]), kNumberWarps);
+    mbar_init(smem_u32(&sm.nums[1]), kNumberWarps);
     mbar_fence_init();
     sm.done = 0;
   }
@@ -730,6 +828,38 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       const uint32_t par = it & 1u;
       look_back(sc, sm, par, n_tiles, v.n_entries, row_offsets, bias, total_out, lane);
       bar_arrive_workers_and_lookback<kBarBaseReady>();
+    }
+  }
+
+  // ================= number warps =================
+  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333).  Number::toString is a
+  // long chain of dependent 64-bit operations for the values that need the general algorithm, and a warp
+  // takes as long as its slowest lane: done here, a tile ahead of the workers, it is off their path.
+  if (wid >= kNumberWarp0) {
+    const int row = tid - kNumberWarp0 * 32;
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
+      uint8_t* stage = s_dyn + kSmemOffStage + s * kStageStride;
+      const StageInfo& info = sm.info[s];
+      mbar_wait(smem_u32(&sm.full[s]), ph);
+      if (info.tile < 0) return;
+      double value = 0.0;
+      bool valid = false;
+      const bool staged = info.slow == 0;  // read before the stage is released: info is rewritten two tiles on
+      if (staged && row < info.rows) {
+        valid = stage[info.valid_base + row] != 0;
+        value = *reinterpret_cast<const double*>(stage + info.delay_base + 8 * row);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));  // the staged ranges are not read again
+      int nl = 0;
+      if (valid) {
+        const RyuTables t{d_pow5_inv, d_pow5};
+        nl = js_number_to_string(value, reinterpret_cast<char*>(stage + kStageBytes) + row * kMaxNumberChars, t);
+      }
+      if (staged) sm.num_len[s][row] = (uint8_t)nl;  // a slow tile formats its numbers itself
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm.nums[s]));
     }
   }
 
@@ -805,12 +935,16 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     for (uint32_t k = head + 16u * n_chunks + tid; k < p_total; k += kWorkers) dst[k] = s_out[k];
   };
 
+#ifdef PIE_CSV_PROFILE
+  long long t_phase = clock64();
+#endif
   for (uint32_t it = 0;; ++it) {
     const uint32_t s = it & 1u, ph = (it >> 1) & 1u, par = it & 1u;
     uint8_t* stage = s_dyn + kSmemOffStage + s * kStageStride;
     char* s_num = reinterpret_cast<char*>(stage + kStageBytes);
     const StageInfo& info = sm.info[s];
     mbar_wait(smem_u32(&sm.full[s]), ph);  // the staged ranges have landed, info is visible
+    PIE_PHASE(0);  // waiting for the producer
     const int64_t tile = info.tile;
     if (tile < 0) {
       finish_pending();
@@ -830,6 +964,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
         sm.overflow = 0;
       }
       workers_sync();  // also: every worker has left the previous tile's write phase (cell table)
+      PIE_PHASE(1);
       // ---- cells 1. show-level cells once per show of the tile; entry-level cells: thread (r, g) takes
       // the columns c_owned[g] (the expensive ones — Ryu, Array.join, free text — on different groups)
       {
@@ -858,6 +993,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
           sm.shcell[col][i] = c;
         }
       }
+      PIE_PHASE(2);  // show-level cells
       if (have) {
         bool completed = false;  // entry.status === 'Completed' (:293-297); status precedes the cells it blanks
         uint32_t* row_cells = sm.cell + r * kCellStride;
@@ -867,14 +1003,9 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
           if (col < 0) break;
           const CellDesc& d = tab.cell[col];
           uint32_t c = 0;
-          if (d.kind == kCellNumber) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
-            int nl = 0;
-            if (stage[info.valid_base + r]) {
-              const RyuTables t{d_pow5_inv, d_pow5};
-              nl = js_number_to_string(*reinterpret_cast<const double*>(stage + info.delay_base + 8 * r),
-                                       s_num + r * kMaxNumberChars, t);
-            }
-            c = pack_cell((uint32_t)kStageBytes + (uint32_t)(r * kMaxNumberChars), (uint32_t)nl);
+          if (d.kind == kCellNumber) {  // formatted by the number warps
+            mbar_wait(smem_u32(&sm.nums[s]), ph);
+            c = pack_cell((uint32_t)kStageBytes + (uint32_t)(r * kMaxNumberChars), (uint32_t)sm.num_len[s][r]);
           } else {
             const int32_t* o = stage_i32(stage, info.off_base[col]);
             const int32_t f0 = o[r], f1 = o[r + 1];
@@ -909,7 +1040,9 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
           row_cells[col] = c;
         }
       }
+      PIE_PHASE(3);  // this thread's entry-level cells
       workers_sync();
+      PIE_PHASE(4);  // waiting for the other warps' cells
       // ---- cells 2. rows pick up their show's cells; bytes per group of 6 consecutive columns
       if (have) {
         uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
@@ -944,6 +1077,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
           sm.group[0][tid] = row_len;  // group 0 starts at 0: the slot carries the row length into the scan
         }
         scan_rows_and_publish(tile, rows, par);
+        PIE_PHASE(5);  // cells 2 + scans
         published = true;
         if (write && sm.tile_total[par] > (uint32_t)kOutBytes) slow = true;  // uniform
       }
@@ -955,7 +1089,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       finish_pending();
       if (tid == 0) atomicAdd(sc.slow_tiles, 1u);
       workers_sync();
-      slow_measure(v, tab, sc, sm, s_num, qmask, e0, rows);
+      slow_measure(v, tab, sc, sm, s_num, qmask, s, e0, rows);
       workers_sync();
       if (!published) scan_rows_and_publish(tile, rows, par);
       const uint32_t tile_total = sm.tile_total[par];
@@ -965,7 +1099,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       const unsigned long long base = sm.base[par];
       if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + base + sm.row_start[par][tid]);
       if (write && base + tile_total <= capacity)
-        slow_write(tab, sc, sm, s_num, qmask, par, e0, rows, out_data + base);
+        slow_write(tab, sc, sm, s_num, qmask, s, par, e0, rows, out_data + base);
       workers_sync();  // qmask / row lengths are free again
       continue;
     }
@@ -973,6 +1107,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     const uint32_t tile_total = sm.tile_total[par];
     bar_arrive_workers_and_lookback<kBarTotalReady>();  // this tile's look-back starts now ...
     finish_pending();                                   // ... while the previous tile leaves s_out
+    PIE_PHASE(6);  // wait for the previous tile's offset + its flush
     if (write) {
       // ---- write.  Thread (r, g) streams its 6 consecutive cells into the shared output tile.  Lanes of
       // a warp = 32 consecutive rows on the SAME column at every step, so cell lengths (and with them the
@@ -980,54 +1115,24 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       // aligned 32-bit stores; only the group's first and last word, which it shares with its neighbours,
       // are stored byte by byte.
       workers_sync();  // the previous tile has left s_out
+      PIE_PHASE(8);    // ... waiting for that
       if (have) {
         const uint32_t o = sm.row_start[par][r] + (g ? sm.group[g][r] : 0u);
         const uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
-        const uint32_t lead = o & 3u;
-        uint8_t* op = s_out + (o & ~3u);  // aligned address of the word being filled
-        uint32_t lo = 0, fill = lead;     // `lead` placeholder bytes stand for the neighbour's bytes
-        bool shared_word = lead != 0;
-        auto store_word = [&](uint32_t v) {
-          if (shared_word) {
-            for (uint32_t b = lead; b < 4; ++b) op[b] = static_cast<uint8_t>(v >> (8 * b));
-            shared_word = false;
-          } else {
-            *reinterpret_cast<uint32_t*>(op) = v;
-          }
-          op += 4;
-        };
+        uint32_t cells[kGroupCols];
+#pragma unroll
+        for (int k = 0; k < kGroupCols; ++k) cells[k] = row_cells[k];
+        ByteStream<true> out;
+        out.init(s_out + o);
 #pragma unroll
         for (int k = 0; k < kGroupCols; ++k) {
-          const uint32_t cell = row_cells[k];
-          const uint32_t src = cell & 0xFFFFu;
-          uint32_t n = cell >> 16;
           const uint32_t sep = (g == kGroups - 1 && k == kGroupCols - 1) ? (uint32_t)'\n' : (uint32_t)',';
-          const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
-          const uint32_t sh = (src & 3u) * 8u;
-          const uint32_t osh = 8u * fill, csh = 32u - osh;  // appending 4 bytes leaves `fill` unchanged
-          uint32_t cur = n ? *w : 0u;
-          for (; n >= 4; n -= 4) {
-            const uint32_t nxt = *++w;
-            const uint32_t x = __funnelshift_r(cur, nxt, sh);
-            cur = nxt;
-            store_word(lo | (x << osh));
-            lo = __funnelshift_rc(x, 0u, csh);  // clamped: fill == 0 gives 0
-          }
-          // the 0..3 last bytes and the separator ride in one piece of 1..4 bytes
-          uint32_t x = sep << (8 * n);
-          if (n) x |= __funnelshift_r(cur, w[1], sh) & ((1u << (8 * n)) - 1u);
-          const uint32_t hi = __funnelshift_rc(x, 0u, csh);
-          lo |= x << osh;
-          fill += n + 1u;
-          if (fill >= 4) {
-            store_word(lo);
-            lo = hi;
-            fill -= 4;
-          }
+          out.append(stage, cells[k] & 0xFFFFu, cells[k] >> 16, sep, 1u);
         }
-        for (uint32_t b = shared_word ? lead : 0u; b < fill; ++b) op[b] = static_cast<uint8_t>(lo >> (8 * b));
+        out.finish();
       }
     }
+    PIE_PHASE(7);  // write
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));  // the stage may be refilled (two tiles ahead)
     pending = true;

@@ -12,6 +12,7 @@
 // export kernels.  This is used for entry.delaySec in buildTableRow -> csvEscape(String(value))
 // (reference server/webhookDispatcher.js:301, :333).
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #include "ryu_tables.h"
@@ -65,6 +66,13 @@ PIE_HD bool multiple_of_pow2(uint64_t v, uint32_t p) { return (v & ((1ull << p) 
 PIE_HD int32_t pow5bits(int32_t e) { return (int32_t)(((uint32_t)e * 1217359u) >> 19) + 1; }   // bit length of 5^e
 PIE_HD int32_t log10_pow2(int32_t e) { return (int32_t)(((uint32_t)e * 78913u) >> 18); }       // floor(log10(2^e))
 PIE_HD int32_t log10_pow5(int32_t e) { return (int32_t)(((uint32_t)e * 732923u) >> 20); }      // floor(log10(5^e))
+
+PIE_HD uint32_t decimal_length9(uint32_t v) {  // v < 10^9
+  uint32_t n = 1;
+  uint32_t p = 10;
+  while (n < 9 && v >= p) { p *= 10; ++n; }
+  return n;
+}
 
 PIE_HD uint32_t decimal_length17(uint64_t v) {  // v < 10^17
   uint32_t n = 1;
@@ -231,12 +239,50 @@ PIE_HD int js_number_to_string(double x, char* buf, const RyuTables& t) {
     return n;
   }
   if (expo == 0 && mant == 0) { buf[0] = '0'; return 1; }  // +0 and -0 are both "0"
-  uint64_t m;
-  int32_t e;
-  shortest_decimal(mant, expo, t, &m, &e);
+  uint64_t m = 0;
+  int32_t e = 0;
+  // Numbers people type — integers and decimals with a few fractional digits (12, 3.5, 0.25, 3.7, 12.34):
+  // the smallest d <= 6 with fl(n / 10^d) == |x| for n = rint(|x| * 10^d).  IEEE division is correctly
+  // rounded, so the equality says the decimal n * 10^-d reads back as x.  With n < 10^15 it is the ONLY
+  // decimal of <= 15 significant digits that does (two such decimals never share a double: DBL_DIG),
+  // so it is the shortest round-trip string and the closest — exactly what the general algorithm below
+  // would find after stripping up to 16 digits one 64-bit division at a time.  (A true candidate n* is
+  // never missed: |x| * 10^d then lies within an ulp of the integer n*, so rint returns it.)
+  bool found = false;
+  {
+    const double ax = neg ? -x : x;
+    if (ax < 1e15) {
+      double p = 1.0;
+      for (int d = 0; d <= 6; ++d) {
+        const double scaled = ax * p;
+        if (!(scaled < 1e15)) break;
+        const double cand = rint(scaled);
+        if (cand / p == ax) {
+          m = (uint64_t)cand;
+          e = -d;
+          found = m != 0;
+          break;
+        }
+        p *= 10.0;
+      }
+    }
+  }
+  if (!found) shortest_decimal(mant, expo, t, &m, &e);
+  // digits of m (< 10^17) through two 32-bit halves: no 64-bit division per digit
   char digits[17];
-  const int k = (int)decimal_length17(m);
-  for (int i = k - 1; i >= 0; --i) { digits[i] = (char)('0' + (m % 10)); m /= 10; }
+  const uint32_t hi9 = (uint32_t)(m / 100000000ull);                    // < 10^9
+  uint32_t lo8 = (uint32_t)(m - (uint64_t)hi9 * 100000000ull);          // < 10^8
+  int k;
+  if (hi9 == 0) {
+    k = (int)decimal_length9(lo8);
+    for (int i = k - 1; i >= 0; --i) { digits[i] = (char)('0' + (lo8 % 10u)); lo8 /= 10u; }
+  } else {
+    const int kh = (int)decimal_length9(hi9);
+    k = kh + 8;
+    uint32_t h = hi9;
+    for (int i = kh - 1; i >= 0; --i) { digits[i] = (char)('0' + (h % 10u)); h /= 10u; }
+    for (int i = k - 1; i >= kh; --i) { digits[i] = (char)('0' + (lo8 % 10u)); lo8 /= 10u; }
+  }
   const int pt = k + e;  // value = 0.d1..dk * 10^pt
   if (neg) buf[n++] = '-';
   if (k <= pt && pt <= 21) {  // integer: digits then zeros

@@ -54,7 +54,13 @@ def number_samples(n, seed):
         # short exact binary fractions k / 2^f at every size (the exact-decimal shortcut and its 15-digit limit)
         rng.integers(1, 2 ** 20, n).astype(np.float64) / 2.0 ** rng.integers(1, 14, n),
         rng.integers(1, 2 ** 53, n).astype(np.float64) / 2.0 ** rng.integers(1, 64, n),
-        (10.0 ** rng.integers(9, 16, n) + rng.integers(0, 1000, n)) / 2.0 ** rng.integers(0, 12, n)])
+        (10.0 ** rng.integers(9, 16, n) + rng.integers(0, 1000, n)) / 2.0 ** rng.integers(0, 12, n),
+        # typed decimals: integers of every size over 10^d, d = 0..8 (the divide-and-compare shortcut, its d <= 6
+        # and 15-digit limits), and their neighbours one ulp away (which must NOT take the same string)
+        rng.integers(0, 10 ** rng.integers(1, 17, n)).astype(np.float64) / 10.0 ** rng.integers(0, 9, n),
+        np.nextafter(rng.integers(1, 10 ** 6, n).astype(np.float64) / 10.0 ** rng.integers(0, 7, n), np.inf),
+        np.nextafter(rng.integers(1, 10 ** 6, n).astype(np.float64) / 10.0 ** rng.integers(0, 7, n), -np.inf),
+        -rng.integers(1, 10 ** 9, n).astype(np.float64) / 10.0 ** rng.integers(0, 7, n)])
 
 
 def test_number_to_string_three_ways(built, numfmt_host):
