@@ -189,11 +189,11 @@ static RowTable make_row_table(const pie_archive_view& v) {
   return t;
 }
 constexpr int kStatusCol = 12;
-// Entry-level columns whose cells worker group g prepares.  The heavy ones sit on different groups:
-// actions (Array.join) on 1, the issue block on 2, notes (free text) on 3; status (12) comes before the columns
-// it blanks (13..17); delaySec (21, formatted by the number warps) last on its group.
+// Entry-level columns whose cells worker group g prepares: four each, the ones that usually need a scan
+// or more (primary issue, actions, other detail, notes) on different groups; delaySec (21, formatted by the
+// number warps, possibly still in flight) last on its group.
 __constant__ signed char c_owned[4][6] = {
-    {8, 9, 10, 21, -1, -1}, {11, 18, 19, 20, -1, -1}, {12, 13, 14, 15, 16, 17}, {22, 23, -1, -1, -1, -1}};
+    {8, 13, 16, 21, -1, -1}, {9, 14, 17, 18, -1, -1}, {10, 11, 12, 15, -1, -1}, {19, 20, 22, 23, -1, -1}};
 
 // ---- pre-pass: which columns can need quoting at all? -----------------------------------------------
 // Most columns of an archive (ids, dates, enumerations, names) never contain " , \n or \r.  One
@@ -256,6 +256,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Same for the warps that run AHEAD of the workers (producer, number warps): their waits are long and not
+// on the critical path, so the try_wait carries a suspend-time hint instead of spinning on the issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PIE_WAITR:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra PIE_DONER;\n"
+      "bra PIE_WAITR;\n"
+      "PIE_DONER:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(20000u)
+      : "memory");
+}
 // global -> shared, 16-byte aligned on both sides, bytes a multiple of 16; completion on the mbarrier
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -292,6 +307,13 @@ struct StageInfo {
   uint32_t delay_base;        // delay_sec[e0 ..]
   uint32_t valid_base;        // delay_valid[e0 ..]
 };
+constexpr int kMaxFillItems = 2 * kRows;  // per kind and tile; more sends the tile down the slow path
+// a cell whose bytes have to be produced in the bump area (see plan_cell / fill_item)
+struct FillItem {
+  uint32_t src_n;      // src:16 | n:16
+  uint32_t dst_items;  // dst:16 | items:15 | special:1
+  uint32_t io_delta;   // staged byte address of item_offsets[0] : 16 | low 16 bits of delta
+};
 struct CsvSmem {
   unsigned long long full[2];                   // producer -> workers: stage s holds a tile
   unsigned long long empty[2];                  // workers + number warps -> producer: stage s may be overwritten
@@ -301,6 +323,9 @@ struct CsvSmem {
   uint32_t cell[kRows * kCellStride];           // (src:16 | len:16 << 16) of cell (r, c) at r*kCellStride + c
   uint32_t shcell[kShowCols][kMaxTileShows];    // the same for the show-level cells of the tile's shows
   uint32_t qmask[kRows];                        // slow path: per-row quote masks
+  FillItem word_items[kMaxFillItems];           // cells to materialise through the word-wise stream ...
+  FillItem quote_items[kMaxFillItems];          // ... and byte by byte ('"' to double)
+  uint32_t n_word_items, n_quote_items;
   uint32_t group[kGroups][kRows];               // bytes of a row's group
   uint32_t row_start[2][kRows];                 // byte offset of the row inside the tile, by tile parity
   uint32_t col_dirty[kCols];
@@ -324,6 +349,11 @@ __device__ __forceinline__ const int32_t* stage_i32(const uint8_t* stage, uint32
 }
 
 // does stage[src .. src+n) contain a character that forces quoting?  Aligned words, ends masked.
+// 0x80 in every byte of v that is zero — exact per byte (no borrow crosses bytes), so it can be counted
+__device__ __forceinline__ uint32_t zero_bytes_exact(uint32_t v) {
+  return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+// does stage[src .. src+n) contain a character that forces quoting, and how many '"'?  Aligned words, ends masked.
 __device__ __forceinline__ uint32_t smem_special_and_quotes(const uint8_t* stage, uint32_t src, uint32_t n, uint32_t& nq) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
   const uint32_t lead = src & 3u;
@@ -334,11 +364,11 @@ __device__ __forceinline__ uint32_t smem_special_and_quotes(const uint8_t* stage
     uint32_t x = w[k];
     if (k == 0) x &= 0xFFFFFFFFu << (8 * lead);
     if (k == nw - 1 && tail) x &= (1u << (8 * tail)) - 1u;
-    const uint32_t zq = zero_byte_flags(x ^ 0x22222222u);  // exact per byte when no borrow crosses: count below is
+    const uint32_t zq = zero_bytes_exact(x ^ 0x22222222u);
     flags |= zq | zero_byte_flags(x ^ 0x2C2C2C2Cu) | zero_byte_flags(x ^ 0x0A0A0A0Au) | zero_byte_flags(x ^ 0x0D0D0D0Du);
-    q |= zq;
+    q += __popc(zq);
   }
-  nq = q;  // != 0 iff the cell holds a '"' (then the caller counts them byte-wise)
+  nq = q;
   return flags;
 }
 
@@ -405,61 +435,70 @@ struct ByteStream {
 };
 
 // Rare path: a cell that needs csvEscape (:332-338) and / or Array.prototype.join('|') (:284, :298) is
-// written out in the bump area.  stage[src .. src+n) = the cell's staged bytes (for a list: all its
-// items, which are contiguous in the heap); items > 1 inserts '|' at the item boundaries, which are
-// item_offsets[1 ..] in heap coordinates (+ delta = staged).
-__device__ __noinline__ uint32_t materialise_cell(CsvSmem& sm, uint8_t* stage, const int32_t* item_offsets, uint32_t delta,
-                                                  bool dirty, uint32_t src, uint32_t n, int items) {
-  uint32_t has_quote = 0;
-  const bool special = dirty && n > 0 && smem_special_and_quotes(stage, src, n, has_quote) != 0;
+// written out in the bump area.  It is done in two steps so that no warp pays for its slowest lane:
+//   plan_cell  (by the thread that owns the cell) scans the bytes, computes the FINAL length, reserves the
+//              bytes and queues the work — the cell table is final right away;
+//   fill_*     (one queued item per thread, after a barrier) produces the bytes.  Cells with '"' to double
+//              go byte by byte, everything else through the word-wise stream; the two kinds sit in
+//              separate queues, taken from opposite ends of the CTA, so a warp runs one kind only.
+// stage[src .. src+n) = the cell's staged bytes (for a list: all its items, which are contiguous in the
+// heap); items > 1 inserts '|' at the item boundaries, item_offsets[1 ..] in heap coordinates (+ delta =
+// staged).
+__device__ __forceinline__ uint32_t plan_cell(CsvSmem& sm, uint8_t* stage, const int32_t* item_offsets, uint32_t delta,
+                                              bool dirty, uint32_t src, uint32_t n, int items) {
+  uint32_t nq = 0;
+  const bool special = dirty && n > 0 && smem_special_and_quotes(stage, src, n, nq) != 0;
   if (!special && items <= 1) return pack_cell(src, n);
-  if (!has_quote) {
-    // nothing to double: ['"'] item ['|' item]... ['"'] through the word-wise stream, into a 4-byte aligned
-    // allocation (the stream may fill its last word past the content)
-    const uint32_t out_len = n + (items > 1 ? (uint32_t)(items - 1) : 0u) + (special ? 2u : 0u);
-    const uint32_t alloc = (out_len + 3u) & ~3u;
-    const uint32_t p = atomicAdd(&sm.bump, alloc);  // bump stays 4-byte aligned
-    if (p + alloc > (uint32_t)kStageBytes) {
-      sm.overflow = 1;  // benign race: every writer stores 1
-      return 0;
-    }
+  const uint32_t out_len = n + (items > 1 ? (uint32_t)(items - 1) : 0u) + (special ? 2u + nq : 0u);
+  const uint32_t alloc = (out_len + 3u) & ~3u;      // the word-wise stream may fill its last word
+  const uint32_t p = atomicAdd(&sm.bump, alloc);    // stays 4-byte aligned
+  const bool quotes = nq != 0;
+  const uint32_t slot = atomicAdd(quotes ? &sm.n_quote_items : &sm.n_word_items, 1u);
+  if (p + alloc > (uint32_t)kStageBytes || slot >= (uint32_t)kMaxFillItems || items > 0x7FFF) {
+    sm.overflow = 1;  // benign race: every writer stores 1
+    return 0;
+  }
+  FillItem& f = (quotes ? sm.quote_items : sm.word_items)[slot];
+  f.src_n = src | (n << 16);
+  f.dst_items = p | ((uint32_t)items << 16) | (special ? 0x80000000u : 0u);
+  f.io_delta = ((uint32_t)(reinterpret_cast<const uint8_t*>(item_offsets) - stage) & 0xFFFFu) | (delta << 16);
+  return pack_cell(p, out_len);
+}
+__device__ __forceinline__ void fill_item(uint8_t* stage, const FillItem& f, bool quotes) {
+  const uint32_t src = f.src_n & 0xFFFFu, n = f.src_n >> 16;
+  const uint32_t p = f.dst_items & 0xFFFFu;
+  const int items = (int)((f.dst_items >> 16) & 0x7FFFu);
+  const bool special = (f.dst_items >> 31) != 0;
+  const int32_t* item_offsets = reinterpret_cast<const int32_t*>(stage + (f.io_delta & 0xFFFFu));
+  const uint32_t delta16 = f.io_delta >> 16;  // staged addresses are < 2^16: the low half of delta is enough
+  if (!quotes) {  // ['"'] item ['|' item]... ['"'] through the word-wise stream
     ByteStream<false> out;
     out.init(stage + p);
     if (special) out.put('"');
     uint32_t ib = src;
     for (int it = 0; it < items; ++it) {
       const bool last = it + 1 >= items;
-      const uint32_t ie = last ? src + n : delta + (uint32_t)item_offsets[it + 1];
+      const uint32_t ie = last ? src + n : ((delta16 + (uint32_t)item_offsets[it + 1]) & 0xFFFFu);
       out.append(stage, ib, ie - ib, last ? (uint32_t)'"' : (uint32_t)'|', (last && !special) ? 0u : 1u);
       ib = ie;
     }
     out.finish();
-    return pack_cell(p, out_len);
+    return;
   }
-  // '"' to double and / or items to join: byte-wise, in one pass, into a worst-case sized allocation
-  const uint32_t worst = 2u * n + (items > 1 ? (uint32_t)(items - 1) : 0u) + 2u;
-  const uint32_t alloc = (worst + 3u) & ~3u;
-  const uint32_t p = atomicAdd(&sm.bump, alloc);
-  if (p + alloc > (uint32_t)kStageBytes) {
-    sm.overflow = 1;
-    return 0;
-  }
-  uint32_t q = p;
-  if (special) stage[q++] = '"';
+  uint32_t q = p;  // '"' to double: byte by byte
+  stage[q++] = '"';
   uint32_t ib = src;
   for (int it = 0; it < items; ++it) {
-    const uint32_t ie = (it + 1 < items) ? delta + (uint32_t)item_offsets[it + 1] : src + n;
+    const uint32_t ie = (it + 1 < items) ? ((delta16 + (uint32_t)item_offsets[it + 1]) & 0xFFFFu) : src + n;
     for (uint32_t j = ib; j < ie; ++j) {
       const uint8_t c = stage[j];
-      if (c == '"' && special) stage[q++] = '"';
+      if (c == '"') stage[q++] = '"';
       stage[q++] = c;
     }
     if (it + 1 < items) stage[q++] = '|';
     ib = ie;
   }
-  if (special) stage[q++] = '"';
-  const uint32_t out_len = q - p;
-  return pack_cell(p, out_len);
+  stage[q++] = '"';
 }
 
 // ---- slow path: a warp per row, lanes stride over the bytes of a cell, global -> global ------------
@@ -807,7 +846,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       long long tile = 0;
       if (lane == 0) tile = (long long)atomicAdd(sc.tile_counter, 1u);  // tiles start in id order: look-back cannot deadlock
       tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
-      mbar_wait(smem_u32(&sm.empty[s]), ph ^ 1u);  // the workers are done with what the stage held
+      mbar_wait_relaxed(smem_u32(&sm.empty[s]), ph ^ 1u);  // the workers are done with what the stage held
       if (tile >= n_tiles) {
         if (lane == 0) {
           sm.info[s].tile = -1;
@@ -841,7 +880,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
       uint8_t* stage = s_dyn + kSmemOffStage + s * kStageStride;
       const StageInfo& info = sm.info[s];
-      mbar_wait(smem_u32(&sm.full[s]), ph);
+      mbar_wait_relaxed(smem_u32(&sm.full[s]), ph);
       if (info.tile < 0) return;
       double value = 0.0;
       bool valid = false;
@@ -868,27 +907,29 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
   const int g = tid / kRows, r = tid % kRows;
   uint32_t* qmask = sm.qmask;
 
-  // rows' lengths in sm.group[0][*] -> sm.row_start[par], sm.tile_total[par]; the aggregate is published
-  auto scan_rows_and_publish = [&](int64_t tile, int rows, uint32_t par) {
-    uint32_t row_len = 0;
-    if (tid < kRows) {
-      if (tid < rows) row_len = sm.group[0][tid];
+  // Row threads: worker threads kRows .. 2*kRows-1 (warps that hold no word-stream fill items) own a row each
+  // for the length bookkeeping.
+  const int rt = tid - kRows;
+  const bool row_thread = rt >= 0 && rt < kRows;
+  // row_len of every row thread -> sm.row_start[par], sm.tile_total[par]; the aggregate is published
+  auto scan_rows_and_publish = [&](int64_t tile, uint32_t row_len, uint32_t par) {
+    if (row_thread) {
       uint32_t incl = row_len;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= o) incl += t;
       }
-      if (lane == 31) sm.warp_sum[wid] = incl;
-      sm.row_start[par][tid] = incl - row_len;  // completed below with the preceding warps' sums
+      if (lane == 31) sm.warp_sum[rt >> 5] = incl;
+      sm.row_start[par][rt] = incl - row_len;  // completed below with the preceding warps' sums
     }
     workers_sync();
-    if (tid < kRows) {
+    if (row_thread) {
       uint32_t before = 0;
-      for (int w = 0; w < wid; ++w) before += sm.warp_sum[w];
-      sm.row_start[par][tid] += before;
-      if (tid == kRows - 1) {
-        const uint32_t total = sm.row_start[par][tid] + row_len;
+      for (int w = 0; w < (rt >> 5); ++w) before += sm.warp_sum[w];
+      sm.row_start[par][rt] += before;
+      if (rt == kRows - 1) {
+        const uint32_t total = sm.row_start[par][rt] + row_len;
         sm.tile_total[par] = total;
         sm.cur_tile[par] = tile;
         // (status, value) travel in one 64-bit word and nothing else is read through it: no fence needed
@@ -962,6 +1003,8 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       if (tid == 0) {
         sm.bump = info.bump0;
         sm.overflow = 0;
+        sm.n_word_items = 0;
+        sm.n_quote_items = 0;
       }
       workers_sync();  // also: every worker has left the previous tile's write phase (cell table)
       PIE_PHASE(1);
@@ -989,13 +1032,28 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
           const uint32_t src = (info.delta[col] + b) & 0xFFFFu;
           uint32_t c = pack_cell(src, n);
           if ((sm.col_dirty[col] && n) || items > 1)
-            c = materialise_cell(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
+            c = plan_cell(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
           sm.shcell[col][i] = c;
         }
       }
       PIE_PHASE(2);  // show-level cells
       if (have) {
-        bool completed = false;  // entry.status === 'Completed' (:293-297); status precedes the cells it blanks
+        // entry.status === 'Completed' (:293-297) blanks the five issue cells, which sit on several groups:
+        // every thread reads the row's status itself (three shared-memory words)
+        bool completed = false;
+        {
+          const int32_t* o = stage_i32(stage, info.off_base[kStatusCol]);
+          const int32_t f0 = o[r];
+          if (o[r + 1] - f0 == 9) {
+            const uint32_t src = (info.delta[kStatusCol] + (uint32_t)f0) & 0xFFFFu;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
+            const uint32_t sh = (src & 3u) * 8u;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];  // the 9 bytes lie inside these three words
+            completed = __funnelshift_r(w0, w1, sh) == lit_word("Completed", 0) &&
+                        __funnelshift_r(w1, w2, sh) == lit_word("Completed", 1) &&
+                        (__funnelshift_r(w2, 0u, sh) & 0xFFu) == lit_word("Completed", 2);
+          }
+        }
         uint32_t* row_cells = sm.cell + r * kCellStride;
 #pragma unroll 1
         for (int k = 0; k < kGroupCols; ++k) {
@@ -1023,18 +1081,10 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
               }
             }
             const uint32_t src = (info.delta[col] + b) & 0xFFFFu;
-            if (col == kStatusCol && n == 9) {
-              const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
-              const uint32_t sh = (src & 3u) * 8u;
-              const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];  // the 9 bytes lie inside these three words
-              completed = __funnelshift_r(w0, w1, sh) == lit_word("Completed", 0) &&
-                          __funnelshift_r(w1, w2, sh) == lit_word("Completed", 1) &&
-                          (__funnelshift_r(w2, 0u, sh) & 0xFFu) == lit_word("Completed", 2);
-            }
             if (!(d.blank_if_completed && completed)) {
               c = pack_cell(src, n);
               if ((sm.col_dirty[col] && n) || items > 1)
-                c = materialise_cell(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
+                c = plan_cell(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
             }
           }
           row_cells[col] = c;
@@ -1043,40 +1093,35 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       PIE_PHASE(3);  // this thread's entry-level cells
       workers_sync();
       PIE_PHASE(4);  // waiting for the other warps' cells
-      // ---- cells 2. rows pick up their show's cells; bytes per group of 6 consecutive columns
-      if (have) {
-        uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
-        const int show_i = (g < 2) ? stage_i32(stage, info.show_idx_base)[r] - info.show0 : 0;
-        uint32_t glen = 0;
-#pragma unroll
-        for (int k = 0; k < kGroupCols; ++k) {
-          const int col = g * kGroupCols + k;
-          uint32_t c;
-          if (col < kShowCols) {
-            c = sm.shcell[col][show_i];
-            row_cells[k] = c;
-          } else {
-            c = row_cells[k];
-          }
-          glen += (c >> 16) + 1u;  // + ',' (or the final '\n')
-        }
-        sm.group[g][r] = glen;
+      // ---- cells 2. the queued cells get their bytes (one item per thread; the two kinds from opposite
+      // ends of the CTA); rows pick up their show's cells; bytes per group of 6 consecutive columns
+      if (!sm.overflow) {
+        const uint32_t n_word = sm.n_word_items, n_quote = sm.n_quote_items;
+        for (uint32_t i = tid; i < n_word; i += kWorkers) fill_item(stage, sm.word_items[i], false);
+        for (uint32_t i = kWorkers - 1 - tid; i < n_quote; i += kWorkers) fill_item(stage, sm.quote_items[i], true);
       }
-      workers_sync();
-      slow = sm.overflow != 0;  // the bump area ran out
+      PIE_PHASE(9);
+      slow = sm.overflow != 0;  // the bump area or a fill queue ran out (uniform: written before the barrier)
       if (!slow) {
-        // ---- scan: groups -> starts inside the row; rows -> starts inside the tile
-        if (tid < rows) {
-          uint32_t row_len = 0;
+        // ---- lengths: a row thread picks up its show's cells, adds up the row and its four groups
+        uint32_t row_len = 0;
+        if (row_thread && rt < rows) {
+          uint32_t* row_cells = sm.cell + rt * kCellStride;
+          const int show_i = stage_i32(stage, info.show_idx_base)[rt] - info.show0;
 #pragma unroll
-          for (int k = 0; k < kGroups; ++k) {
-            const uint32_t x = sm.group[k][tid];
-            sm.group[k][tid] = row_len;
-            row_len += x;
+          for (int col = 0; col < kCols; ++col) {
+            if (col % kGroupCols == 0) sm.group[col / kGroupCols][rt] = row_len;  // where the group starts in the row
+            uint32_t c;
+            if (col < kShowCols) {
+              c = sm.shcell[col][show_i];
+              row_cells[col] = c;
+            } else {
+              c = row_cells[col];
+            }
+            row_len += (c >> 16) + 1u;  // + ',' (or the final '\n')
           }
-          sm.group[0][tid] = row_len;  // group 0 starts at 0: the slot carries the row length into the scan
         }
-        scan_rows_and_publish(tile, rows, par);
+        scan_rows_and_publish(tile, row_len, par);
         PIE_PHASE(5);  // cells 2 + scans
         published = true;
         if (write && sm.tile_total[par] > (uint32_t)kOutBytes) slow = true;  // uniform
@@ -1091,7 +1136,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       workers_sync();
       slow_measure(v, tab, sc, sm, s_num, qmask, s, e0, rows);
       workers_sync();
-      if (!published) scan_rows_and_publish(tile, rows, par);
+      if (!published) scan_rows_and_publish(tile, (row_thread && rt < rows) ? sm.group[0][rt] : 0u, par);
       const uint32_t tile_total = sm.tile_total[par];
       bar_arrive_workers_and_lookback<kBarTotalReady>();
       if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));  // nothing of the stage's staged ranges is read any more
@@ -1159,6 +1204,9 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
   cudaGetDevice(&dev);
   if (configured_device != dev) {
     err = cudaFuncSetAttribute(csv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (err != cudaSuccess) return err;
+    err = cudaFuncSetAttribute(csv_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
     if (err != cudaSuccess) return err;
     int per_sm = 0, sms = 0;
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csv_rows_kernel, kCtaThreads, kSmemBytes);
