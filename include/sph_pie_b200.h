@@ -197,7 +197,7 @@ int pie_csv_rows_host(const pie_archive_view* host_view, int64_t* row_offsets, u
  * previous value; rows <= 0 only queries.  Default 2^20. */
 int64_t pie_set_csv_chunk_rows(int64_t rows);
 
-/* Test hooks of the export-row kernel.  A tile (128 consecutive rows) whose column bytes or CSV do not
+/* Test hooks of the export-row kernel.  A tile (160 consecutive rows) whose column bytes or CSV do not
  * fit the kernel's shared-memory staging takes a slower warp-per-row path; `on` = 1 forces every tile
  * through it, 0 restores the default, < 0 only queries; returns the previous value.
  * pie_debug_csv_slow_tiles reads how many tiles of the most recent pie_csv_rows_dev launch that used

@@ -19,7 +19,7 @@ bufs = ops.CsvBuffers(E, total, "cuda:0")
 for _ in range(3):
     ops.csv_rows_dev(table, bufs)
 torch.cuda.synchronize()
-print("rows", E, "tiles", (E + 127) // 128, "full pass: phase cycles summed over all tiles (worker thread 0):", flush=True)
+print("rows", E, "full pass: phase cycles summed over all tiles (worker thread 0):", flush=True)
 ops.csv_slow_tiles(table, bufs)
 print("size-only pass:", flush=True)
 ops.csv_rows_dev(table, sizing, size_only=True)

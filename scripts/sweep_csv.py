@@ -12,7 +12,7 @@ OUT = os.path.join(ROOT, "scripts", "_variants")
 
 # rows per tile, output tile KB, stage KB, min CTAs per SM
 VARIANTS = [dict(R=r, O=o, S=s, B=b) for r, o, s, b in [
-    (128, 42, 50, 1), (64, 22, 27, 2), (64, 24, 30, 2), (96, 32, 40, 1),
+    (128, 42, 50, 1), (64, 22, 27, 2), (32, 11, 14, 4), (160, 52, 58, 1),
 ]]
 
 

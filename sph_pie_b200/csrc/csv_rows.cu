@@ -43,16 +43,16 @@ __device__ const uint64_t d_pow5_inv[PIE_RYU_POW5_INV_SPLIT_N][2] = PIE_RYU_POW5
 __device__ const uint64_t d_pow5[PIE_RYU_POW5_SPLIT_N][2] = PIE_RYU_POW5_SPLIT_INIT;
 
 #ifndef PIE_CSV_ROWS
-#define PIE_CSV_ROWS 128
+#define PIE_CSV_ROWS 160
 #endif
 #ifndef PIE_CSV_MIN_BLOCKS
 #define PIE_CSV_MIN_BLOCKS 1
 #endif
 #ifndef PIE_CSV_OUT_KB
-#define PIE_CSV_OUT_KB 42
+#define PIE_CSV_OUT_KB 52
 #endif
 #ifndef PIE_CSV_STAGE_KB
-#define PIE_CSV_STAGE_KB 50
+#define PIE_CSV_STAGE_KB 58
 #endif
 constexpr int kRows = PIE_CSV_ROWS;            // rows (entries) per tile; multiple of 32
 constexpr int kCols = PIE_N_EXPORT_COLUMNS;    // 24
@@ -65,7 +65,7 @@ constexpr int kLookbackWarp = kWorkerWarps + 1;
 constexpr int kNumberWarp0 = kWorkerWarps + 2;  // Number::toString for the NEXT tile: a row per lane
 constexpr int kNumberWarps = kRows / 32;
 constexpr int kCtaThreads = kWorkers + 64 + 32 * kNumberWarps;
-constexpr int kOutBytes = PIE_CSV_OUT_KB * 1024;      // shared output tile (rows of ~280 B -> ~36 KB per 128 rows)
+constexpr int kOutBytes = PIE_CSV_OUT_KB * 1024;      // shared output tile (rows of ~280 B -> ~45 KB per 160 rows)
 constexpr int kStageBytes = PIE_CSV_STAGE_KB * 1024;  // one stage: column bytes + offset arrays + bump area
 constexpr int kNumBytes = kRows * kMaxNumberChars;    // Number::toString output, behind the stage
 constexpr int kStageStride = kStageBytes + kNumBytes + 16;
