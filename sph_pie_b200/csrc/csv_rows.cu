@@ -404,17 +404,25 @@ struct ByteStream {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
     const uint32_t sh = (src & 3u) * 8u;
     const uint32_t osh = 8u * fill, csh = 32u - osh;  // appending 4 bytes leaves `fill` unchanged
-    uint32_t cur = n ? *w : 0u;
+    // two source words are kept in flight ahead of the stores (a load is never moved above a store by
+    // the compiler: both are shared memory); reads run up to 8 bytes past the cell, inside the stage
+    uint32_t cur = 0, nxt = 0;
+    if (n) {
+      cur = w[0];
+      nxt = w[1];
+    }
     for (; n >= 4; n -= 4) {
-      const uint32_t nxt = *++w;
+      const uint32_t ahead = w[2];
+      ++w;
       const uint32_t x = __funnelshift_r(cur, nxt, sh);
       cur = nxt;
+      nxt = ahead;
       store_word(lo | (x << osh));
       lo = __funnelshift_rc(x, 0u, csh);  // clamped: fill == 0 gives 0
     }
     // the 0..3 last bytes and the separator ride in one piece of 0..4 bytes
     uint32_t x = nsep ? sep << (8 * n) : 0u;
-    if (n) x |= __funnelshift_r(cur, w[1], sh) & ((1u << (8 * n)) - 1u);
+    if (n) x |= __funnelshift_r(cur, nxt, sh) & ((1u << (8 * n)) - 1u);
     const uint32_t hi = __funnelshift_rc(x, 0u, csh);
     lo |= x << osh;
     fill += n + nsep;
@@ -962,10 +970,17 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     for (uint32_t k = tid; k < head; k += kWorkers) dst[k] = s_out[k];
     const uint32_t n_chunks = (p_total - head) >> 4;
     const uint32_t sh = (head & 3u) * 8u;
-    const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(s_out) + (head >> 2);
+    // The 5 words a chunk needs start at word (head >> 2) + 4k: two aligned 128-bit loads (conflict-free:
+    // consecutive lanes read consecutive 16-byte units) cover them; which 5 of the 8 words is uniform.
+    const uint32_t m = (head >> 2) & 3u;
+    const uint4* __restrict__ sq = reinterpret_cast<const uint4*>(s_out) + (head >> 4);
     for (uint32_t k = tid; k < n_chunks; k += kWorkers) {
-      const uint32_t* w = sw + 4 * k;
-      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];  // w[4] stays inside the +32 slack
+      const uint4 a = sq[k], b = sq[k + 1];  // b of the last chunk stays inside the +32 slack
+      uint32_t w0, w1, w2, w3, w4;
+      if (m == 0) { w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; }
+      else if (m == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }
+      else if (m == 2) { w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; }
+      else { w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; }
       uint4 o;
       o.x = __funnelshift_r(w0, w1, sh);
       o.y = __funnelshift_r(w1, w2, sh);
