@@ -257,19 +257,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 // Same for the warps that run AHEAD of the workers (producer, number warps): their waits are long and not
-// on the critical path, so the try_wait carries a suspend-time hint instead of spinning on the issue slots.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+// on the critical path, so they sleep between polls instead of spinning on the issue slots.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "PIE_WAITR:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra PIE_DONER;\n"
-      "bra PIE_WAITR;\n"
-      "PIE_DONER:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity), "r"(20000u)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(400);
 }
 // global -> shared, 16-byte aligned on both sides, bytes a multiple of 16; completion on the mbarrier
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
