@@ -197,6 +197,24 @@ int pie_csv_rows_host(const pie_archive_view* host_view, int64_t* row_offsets, u
  * previous value; rows <= 0 only queries.  Default 2^20. */
 int64_t pie_set_csv_chunk_rows(int64_t rows);
 
+/* ---- archive entry payloads: replaces JSON.stringify(buildArchiveEntryPayload(show, entry))
+ * (server/webhookDispatcher.js:315-330, with toYesNoBoolean :60-77) mapped over every entry of every show — the
+ * request bodies dispatchShowEvent('show.archived') posts one by one (:520-540; axios serialises the object with
+ * JSON.stringify).  Row i of the output string column is the body of entry i:
+ *   {"showDate":"..","showTime":"..","showNumber":"..","leadPilot":"..","monkeyLead":"..","operator":"..",
+ *    "monkeyId":"..","planned":true|false,"launched":..,"commandReceived":..,"primaryIssue":"..","subIssue":".."}
+ * followed by '\n' (the whole output is JSON Lines).  Strings are escaped as QuoteJSONString does (ECMA-262
+ * 25.5.2.3: \" \\ \b \t \n \f \r, other code units below U+0020 as \u00xx; everything else verbatim) — the
+ * columns hold well-formed UTF-8, so the lone-surrogate case of JSON.stringify cannot arise.  A boolean is
+ * value.trim().toLowerCase() === 'yes' (the columns are strings: sqlProvider.js:361-409).
+ * Same calling convention, scratch size (pie_csv_rows_scratch_bytes) and capacity rules as pie_csv_rows_*.
+ * Reads: entry_offsets, show_date, show_time, show_label, lead_pilot, monkey_lead, operator_name, unit_id, planned,
+ * launched, command_rx, primary_issue, sub_issue; every other column may be NULL. */
+int pie_archive_payloads_dev(const pie_archive_view* dev_view, int64_t* row_offsets, uint8_t* out_data,
+                             uint64_t out_capacity, uint64_t* total_bytes_dev, void* scratch, void* stream);
+int pie_archive_payloads_host(const pie_archive_view* host_view, int64_t* row_offsets, uint8_t* out_data,
+                              uint64_t out_capacity, uint64_t* total_bytes);
+
 /* Test hooks of the export-row kernel.  A tile (160 consecutive rows) whose column bytes or CSV do not
  * fit the kernel's shared-memory staging takes a slower warp-per-row path; `on` = 1 forces every tile
  * through it, 0 restores the default, < 0 only queries; returns the previous value.

@@ -72,23 +72,31 @@ def archive_analytics(table: ArchiveTable, tz_offset_minutes: int = 0, nthreads:
                             h.summary_f64[:, :, :G], h.summary_count[:, :G]), 0, -1
 
 
-def csv_rows(table: ArchiveTable, nthreads: int = 1, offsets=None, data=None):
-    """(row_offsets int64[E+1], data uint8[total]) from the C restatement of buildCsvRow.
-    With preallocated `offsets`/`data` (timed baseline) one call does the whole job."""
+def _rows(entry: str, table: ArchiveTable, nthreads: int, offsets, data):
     assert not table.is_cuda
-    so = load()
-    so.oracle_csv_rows_mt.restype = C.c_int
-    so.oracle_csv_rows_mt.argtypes = [C.POINTER(_lib.ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64,
-                                      C.POINTER(C.c_uint64), C.c_int]
+    fn = getattr(load(), entry)
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(_lib.ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
     view = table.view()
     total = C.c_uint64(0)
     if offsets is None:
         offsets = torch.empty(table.n_entries + 1, dtype=torch.int64)
     if data is None:
-        so.oracle_csv_rows_mt(C.byref(view), offsets.data_ptr(), None, 0, C.byref(total), nthreads)
+        fn(C.byref(view), offsets.data_ptr(), None, 0, C.byref(total), nthreads)
         data = torch.empty(max(int(total.value), 1), dtype=torch.uint8)
-    so.oracle_csv_rows_mt(C.byref(view), offsets.data_ptr(), data.data_ptr(), data.numel(), C.byref(total), nthreads)
+    fn(C.byref(view), offsets.data_ptr(), data.data_ptr(), data.numel(), C.byref(total), nthreads)
     return offsets, data[: int(total.value)]
+
+
+def csv_rows(table: ArchiveTable, nthreads: int = 1, offsets=None, data=None):
+    """(row_offsets int64[E+1], data uint8[total]) from the C restatement of buildCsvRow.
+    With preallocated `offsets`/`data` (timed baseline) one call does the whole job."""
+    return _rows("oracle_csv_rows_mt", table, nthreads, offsets, data)
+
+
+def payload_rows(table: ArchiveTable, nthreads: int = 1, offsets=None, data=None):
+    """Same for JSON.stringify(buildArchiveEntryPayload(show, entry)) + '\\n' per entry."""
+    return _rows("oracle_payload_rows_mt", table, nthreads, offsets, data)
 
 
 def number_to_string_batch(xs):

@@ -555,18 +555,85 @@ static void csv_show_range(const pie_archive_view* v, int64_t s0, int64_t s1, in
   *op = o;
 }
 
+/* ---- archive entry payloads: JSON.stringify(buildArchiveEntryPayload(show, entry)) --------------------
+ * server/webhookDispatcher.js:315-330 (the object literal's property order is the serialisation order),
+ * toYesNoBoolean :60-77, QuoteJSONString ECMA-262 25.5.2.3. */
+static void put_json_string(csv_out* o, const pie_strcol* c, int64_t i) {
+  static const char hex[] = "0123456789abcdef";
+  const uint8_t* s = c->data + c->offsets[i];
+  const int n = c->offsets[i + 1] - c->offsets[i];
+  put_char(o, '"');
+  for (int k = 0; k < n; ++k) {
+    const uint8_t ch = s[k];
+    switch (ch) {
+      case '"': put_char(o, '\\'); put_char(o, '"'); break;
+      case '\\': put_char(o, '\\'); put_char(o, '\\'); break;
+      case '\b': put_char(o, '\\'); put_char(o, 'b'); break;
+      case '\t': put_char(o, '\\'); put_char(o, 't'); break;
+      case '\n': put_char(o, '\\'); put_char(o, 'n'); break;
+      case '\f': put_char(o, '\\'); put_char(o, 'f'); break;
+      case '\r': put_char(o, '\\'); put_char(o, 'r'); break;
+      default:
+        if (ch < 0x20) {
+          put_char(o, '\\'); put_char(o, 'u'); put_char(o, '0'); put_char(o, '0');
+          put_char(o, hex[ch >> 4]); put_char(o, hex[ch & 15]);
+        } else {
+          put_char(o, (char)ch);
+        }
+    }
+  }
+  put_char(o, '"');
+}
+static void put_lit(csv_out* o, const char* s) { put_bytes(o, (const uint8_t*)s, strlen(s)); }
+static void put_yes_no(csv_out* o, const pie_strcol* c, int64_t i) { /* value.trim().toLowerCase() === 'yes' */
+  const uint8_t* s = c->data + c->offsets[i];
+  int b = 0, e = c->offsets[i + 1] - c->offsets[i];
+  js_trim(s, &b, &e);
+  put_lit(o, lower_eq(s + b, e - b, "yes") ? "true" : "false");
+}
+
+static void payload_show_range(const pie_archive_view* v, int64_t s0, int64_t s1, int64_t* row_offsets, csv_out* op) {
+  csv_out o = *op;
+  for (int64_t s = s0; s < s1; ++s) {
+    for (int e = v->entry_offsets[s]; e < v->entry_offsets[s + 1]; ++e) {
+      if (row_offsets) row_offsets[e] = (int64_t)o.n;
+      put_lit(&o, "{\"showDate\":"); put_json_string(&o, &v->show_date, s);
+      put_lit(&o, ",\"showTime\":"); put_json_string(&o, &v->show_time, s);
+      put_lit(&o, ",\"showNumber\":"); put_json_string(&o, &v->show_label, s);
+      put_lit(&o, ",\"leadPilot\":"); put_json_string(&o, &v->lead_pilot, s);
+      put_lit(&o, ",\"monkeyLead\":"); put_json_string(&o, &v->monkey_lead, s);
+      put_lit(&o, ",\"operator\":"); put_json_string(&o, &v->operator_name, e);
+      put_lit(&o, ",\"monkeyId\":"); put_json_string(&o, &v->unit_id, e);
+      put_lit(&o, ",\"planned\":"); put_yes_no(&o, &v->planned, e);
+      put_lit(&o, ",\"launched\":"); put_yes_no(&o, &v->launched, e);
+      put_lit(&o, ",\"commandReceived\":"); put_yes_no(&o, &v->command_rx, e);
+      put_lit(&o, ",\"primaryIssue\":"); put_json_string(&o, &v->primary_issue, e);
+      put_lit(&o, ",\"subIssue\":"); put_json_string(&o, &v->sub_issue, e);
+      put_lit(&o, "}\n");
+    }
+  }
+  *op = o;
+}
+
+typedef void (*row_range_fn)(const pie_archive_view*, int64_t, int64_t, int64_t*, csv_out*);
+
 /* Fills row_offsets[n_entries+1]; writes rows (each followed by '\n') into out_data when it is not
  * NULL and large enough; *total receives the size needed. */
-int oracle_csv_rows(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
-                    uint64_t* total) {
+static int rows_single(row_range_fn fn, const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data,
+                       uint64_t capacity, uint64_t* total) {
   csv_out o = {out_data, 0, capacity};
-  csv_show_range(v, 0, v->n_shows, row_offsets, &o);
+  fn(v, 0, v->n_shows, row_offsets, &o);
   row_offsets[v->n_entries] = (int64_t)o.n;
   *total = o.n;
   return 0;
 }
+int oracle_csv_rows(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
+                    uint64_t* total) {
+  return rows_single(csv_show_range, v, row_offsets, out_data, capacity, total);
+}
 
 typedef struct {
+  row_range_fn fn;
   const pie_archive_view* v;
   int64_t s0, s1;
   int64_t* row_offsets;
@@ -575,16 +642,16 @@ typedef struct {
 
 static void* csv_worker(void* arg) {
   csv_job* j = (csv_job*)arg;
-  csv_show_range(j->v, j->s0, j->s1, j->row_offsets, &j->out);
+  j->fn(j->v, j->s0, j->s1, j->row_offsets, &j->out);
   return NULL;
 }
 
 /* Threaded variant for the CPU baseline: a counting pass per show range, a prefix over the ranges,
- * then the writing pass — the same per-row code as oracle_csv_rows. */
-int oracle_csv_rows_mt(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
-                       uint64_t* total, int nthreads) {
+ * then the writing pass — the same per-row code as the single-threaded entry point. */
+static int rows_mt(row_range_fn fn, const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data,
+                   uint64_t capacity, uint64_t* total, int nthreads) {
   const int64_t S = v->n_shows;
-  if (nthreads <= 1 || S < 2 * (int64_t)nthreads) return oracle_csv_rows(v, row_offsets, out_data, capacity, total);
+  if (nthreads <= 1 || S < 2 * (int64_t)nthreads) return rows_single(fn, v, row_offsets, out_data, capacity, total);
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
   csv_job* jobs = (csv_job*)malloc(sizeof(csv_job) * (size_t)nthreads);
   const int64_t E = v->entry_offsets[S];
@@ -594,7 +661,7 @@ int oracle_csv_rows_mt(const pie_archive_view* v, int64_t* row_offsets, uint8_t*
     const int64_t target = (int64_t)((double)E * (t + 1) / nthreads);
     if (t == nthreads - 1) s1 = S;
     else while (s1 < S && v->entry_offsets[s1] < target) s1++;
-    jobs[t] = (csv_job){v, s0, s1, NULL, {NULL, 0, 0}};
+    jobs[t] = (csv_job){fn, v, s0, s1, NULL, {NULL, 0, 0}};
     s0 = s1;
   }
   for (int t = 0; t < nthreads; ++t) pthread_create(&th[t], NULL, csv_worker, &jobs[t]);
@@ -613,6 +680,15 @@ int oracle_csv_rows_mt(const pie_archive_view* v, int64_t* row_offsets, uint8_t*
   free(th);
   free(jobs);
   return 0;
+}
+int oracle_csv_rows_mt(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
+                       uint64_t* total, int nthreads) {
+  return rows_mt(csv_show_range, v, row_offsets, out_data, capacity, total, nthreads);
+}
+/* JSON.stringify(buildArchiveEntryPayload(show, entry)) + '\n' per entry */
+int oracle_payload_rows_mt(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
+                           uint64_t* total, int nthreads) {
+  return rows_mt(payload_show_range, v, row_offsets, out_data, capacity, total, nthreads);
 }
 
 /* Number::toString of an array (checker for the product's Ryu): out is n x 32 bytes */

@@ -608,3 +608,37 @@ def build_archive_entry_payload(show=UNDEFINED, entry=UNDEFINED):
         "primaryIssue": g(entry, "primaryIssue"),
         "subIssue": g(entry, "subIssue"),
     }
+
+
+def json_quote(s: str) -> str:
+    """QuoteJSONString (ECMA-262 25.5.2.3) for a string of well-formed code points: \" \\ and the
+    five short escapes, other code units below U+0020 as \\u00xx (lower-case hex), the rest verbatim.
+    (Lone surrogates, which JSON.stringify writes as \\udxxx, cannot occur in UTF-8 columns.)"""
+    short = {8: "\\b", 9: "\\t", 10: "\\n", 12: "\\f", 13: "\\r", 0x22: '\\"', 0x5C: "\\\\"}
+    out = ['"']
+    for ch in s:
+        cp = ord(ch)
+        if cp in short:
+            out.append(short[cp])
+        elif cp < 0x20:
+            out.append("\\u%04x" % cp)
+        else:
+            out.append(ch)
+    out.append('"')
+    return "".join(out)
+
+
+def archive_entry_payload_json(show=UNDEFINED, entry=UNDEFINED) -> str:
+    """JSON.stringify(buildArchiveEntryPayload(show, entry)) — the request body sendWebhookPayload hands to
+    axios for every entry of an archived show (server/webhookDispatcher.js:527-540).  SerializeJSONObject
+    walks the object's own string keys in insertion order, i.e. the order of the literal at :316-329; the
+    values are strings and booleans only."""
+    payload = build_archive_entry_payload(show, entry)
+    parts = []
+    for key, value in payload.items():
+        if isinstance(value, bool):
+            text = "true" if value else "false"
+        else:
+            text = json_quote(js_string(value))
+        parts.append(json_quote(key) + ":" + text)
+    return "{" + ",".join(parts) + "}"

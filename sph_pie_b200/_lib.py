@@ -112,6 +112,10 @@ SIGNATURES = {
     "pie_csv_rows_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     "pie_set_csv_chunk_rows": (C.c_int64, [C.c_int64]),
+    "pie_archive_payloads_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
+    "pie_archive_payloads_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64,
+                                            C.POINTER(C.c_uint64)]),
     "pie_debug_csv_force_slow_path": (C.c_int, [C.c_int]),
     "pie_debug_csv_slow_tiles": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32), C.c_void_p]),
     "pie_csv_rows_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64,

@@ -69,7 +69,6 @@ constexpr int kOutBytes = PIE_CSV_OUT_KB * 1024;      // shared output tile (row
 constexpr int kStageBytes = PIE_CSV_STAGE_KB * 1024;  // one stage: column bytes + offset arrays + bump area
 constexpr int kNumBytes = kRows * kMaxNumberChars;    // Number::toString output, behind the stage
 constexpr int kStageStride = kStageBytes + kNumBytes + 16;
-constexpr int kShowCols = 8;                   // columns 0..7 are show-level
 constexpr int kMaxTileShows = kRows;           // shows a tile may span on the fast path
 constexpr int kCellStride = kCols + 1;         // padded: lanes = consecutive rows hit distinct banks
 static_assert(kRows % 32 == 0 && kGroups * kGroupCols == kCols, "tile shape");
@@ -148,14 +147,78 @@ __global__ void __launch_bounds__(256) expand_entry_show_kernel(pie_archive_view
 // != 0 iff some byte of v is zero (exact as a boolean)
 __device__ __forceinline__ uint32_t zero_byte_flags(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
 
-__device__ __forceinline__ uint32_t special_flags(uint32_t x) {  // " , \n \r   (csvEscape, :334)
+// != 0 iff some byte of x is below 0x20 (exact as a boolean)
+__device__ __forceinline__ uint32_t control_byte_flags(uint32_t x) { return (x - 0x20202020u) & ~x & 0x80808080u; }
+
+// Which bytes make a cell "special"?
+//   kEscapeCsv   " , \n \r  force quotes, '"' is doubled            (csvEscape, webhookDispatcher.js:332-338)
+//   kEscapeJson  " \ and U+0000..U+001F are escaped                  (JSON.stringify, ECMA-262 QuoteJSONString)
+enum : uint8_t { kEscapeCsv = 0, kEscapeJson = 1 };
+template <bool kJson>
+__device__ __forceinline__ uint32_t special_flags(uint32_t x) {
+  if (kJson) return zero_byte_flags(x ^ 0x22222222u) | zero_byte_flags(x ^ 0x5C5C5C5Cu) | control_byte_flags(x);
   return zero_byte_flags(x ^ 0x22222222u) | zero_byte_flags(x ^ 0x2C2C2C2Cu) | zero_byte_flags(x ^ 0x0A0A0A0Au) |
          zero_byte_flags(x ^ 0x0D0D0D0Du);
 }
-__device__ __forceinline__ bool is_special_byte(uint8_t c) { return c == '"' || c == ',' || c == '\n' || c == '\r'; }
+template <bool kJson>
+__device__ __forceinline__ bool is_special_byte(uint8_t c) {
+  if (kJson) return c == '"' || c == '\\' || c < 0x20;
+  return c == '"' || c == ',' || c == '\n' || c == '\r';
+}
+// bytes a special byte ADDS to the output: CSV doubles '"' (the two enclosing quotes are counted per cell);
+// JSON: \" \\ \b \t \n \f \r take 2, the other control characters \u00XX take 6
+template <bool kJson>
+__device__ __forceinline__ uint32_t extra_bytes(uint8_t c) {
+  if (!kJson) return c == '"';
+  if (c == '"' || c == '\\') return 1;
+  if (c >= 0x20) return 0;
+  return (c == 8 || c == 9 || c == 10 || c == 12 || c == 13) ? 1u : 5u;
+}
+// writes the escaped form of c at dst, returns its length (1, 2 or 6)
+template <bool kJson>
+__device__ __forceinline__ uint32_t put_escaped(uint8_t* dst, uint8_t c) {
+  if (!kJson) {
+    if (c == '"') {
+      dst[0] = '"';
+      dst[1] = '"';
+      return 2;
+    }
+    dst[0] = c;
+    return 1;
+  }
+  if (c == '"' || c == '\\') {
+    dst[0] = '\\';
+    dst[1] = c;
+    return 2;
+  }
+  if (c >= 0x20) {
+    dst[0] = c;
+    return 1;
+  }
+  const char short_form = c == 8 ? 'b' : c == 9 ? 't' : c == 10 ? 'n' : c == 12 ? 'f' : c == 13 ? 'r' : 0;
+  dst[0] = '\\';
+  if (short_form) {
+    dst[1] = (uint8_t)short_form;
+    return 2;
+  }
+  dst[1] = 'u';
+  dst[2] = '0';
+  dst[3] = '0';
+  dst[4] = (uint8_t)('0' + (c >> 4));
+  dst[5] = (uint8_t)((c & 15) < 10 ? '0' + (c & 15) : 'a' + (c & 15) - 10);
+  return 6;
+}
 
-// The 24 cells of a row, in EXPORT_COLUMNS order (:15-19)
-enum : uint8_t { kCellString = 0, kCellJoined = 1, kCellNumber = 2 };
+// A row is kCols cells, each followed by ONE separator byte.  The two row formats of the path:
+//   CSV      buildCsvRow(buildTableRow(show, entry)): the 24 EXPORT_COLUMNS (webhookDispatcher.js:15-19), ',' between
+//            them, '\n' after the last.
+//   payload  JSON.stringify(buildArchiveEntryPayload(show, entry)) (webhookDispatcher.js:315-330, the body
+//            dispatchShowEvent posts per entry of an archived show, :527-540): 12 values between literal key text;
+//            a literal's last byte rides as its separator, and the three booleans select between two literals
+//            that also carry the next key.
+enum : uint8_t { kCellString = 0, kCellJoined = 1, kCellNumber = 2, kCellLiteral = 3, kCellYesNo = 4 };
+constexpr int kLiteralBytes = 256;  // literal text of a row format; staged at the start of every stage
+constexpr int kMaxShowSlots = 8;    // show-level value cells of a row format
 struct CellDesc {
   const int32_t* offsets;       // string column / items of a list column
   const uint8_t* data;
@@ -163,18 +226,49 @@ struct CellDesc {
   uint8_t kind;
   uint8_t per_entry;            // row index is the entry (1) or its show (0)
   uint8_t blank_if_completed;   // :293-297
+  uint8_t sep;                  // the byte that follows the cell
+  int8_t show_slot;             // show-level value cell: its row in the per-tile show-cell table; else -1
+  uint8_t pad_[3];
+  uint16_t lit, lit_len;        // kCellLiteral: its text in RowTable::literals; kCellYesNo: the text for true
+  uint16_t lit_no, lit_no_len;  // kCellYesNo: the text for false
 };
 struct RowTable {
   CellDesc cell[kCols];
+  signed char owned[4][6];          // value cells of the ENTRY level that worker group g prepares (-1 ends)
+  uint8_t show_col[kMaxShowSlots];  // column of show slot i
+  uint8_t n_show_slots;
+  int8_t status_col;                // the column `blank_if_completed` looks at, -1 if the format has none
+  uint8_t json;                     // escape mode of the value cells
+  uint8_t has_number;               // the format has a delaySec cell (number warps, delay ranges)
+  uint8_t literals[kLiteralBytes];
 };
 
-static RowTable make_row_table(const pie_archive_view& v) {
-  RowTable t;
+static void finish_row_table(RowTable& t) {
+  t.n_show_slots = 0;
+  t.has_number = 0;
+  for (int c = 0; c < kCols; ++c) {
+    if (t.cell[c].kind == kCellNumber) t.has_number = 1;
+    t.cell[c].show_slot = -1;
+    if (!t.cell[c].per_entry && (t.cell[c].kind == kCellString || t.cell[c].kind == kCellJoined)) {
+      t.cell[c].show_slot = (int8_t)t.n_show_slots;
+      t.show_col[t.n_show_slots++] = (uint8_t)c;
+    }
+  }
+}
+
+static RowTable make_csv_table(const pie_archive_view& v) {
+  RowTable t{};
   auto str = [](const pie_strcol& c, int per_entry, int blank = 0) {
-    return CellDesc{c.offsets, c.data, nullptr, kCellString, (uint8_t)per_entry, (uint8_t)blank};
+    CellDesc d{};
+    d.offsets = c.offsets; d.data = c.data; d.kind = kCellString; d.per_entry = (uint8_t)per_entry;
+    d.blank_if_completed = (uint8_t)blank;
+    return d;
   };
   auto lst = [](const pie_strlistcol& c, int per_entry) {
-    return CellDesc{c.items.offsets, c.items.data, c.list_offsets, kCellJoined, (uint8_t)per_entry, 0};
+    CellDesc d{};
+    d.offsets = c.items.offsets; d.data = c.items.data; d.list_offsets = c.list_offsets; d.kind = kCellJoined;
+    d.per_entry = (uint8_t)per_entry;
+    return d;
   };
   t.cell[0] = str(v.show_id, 0);      t.cell[1] = str(v.show_date, 0);     t.cell[2] = str(v.show_time, 0);
   t.cell[3] = str(v.show_label, 0);   t.cell[4] = lst(v.crew, 0);          t.cell[5] = str(v.lead_pilot, 0);
@@ -184,26 +278,95 @@ static RowTable make_row_table(const pie_archive_view& v) {
   t.cell[14] = str(v.sub_issue, 1, 1);  t.cell[15] = str(v.other_detail, 1, 1);
   t.cell[16] = str(v.severity, 1, 1);   t.cell[17] = str(v.root_cause, 1, 1);
   t.cell[18] = lst(v.actions, 1);     t.cell[19] = str(v.operator_name, 1); t.cell[20] = str(v.battery_id, 1);
-  t.cell[21] = CellDesc{nullptr, nullptr, nullptr, kCellNumber, 1, 0};
+  t.cell[21] = CellDesc{};
+  t.cell[21].kind = kCellNumber;
+  t.cell[21].per_entry = 1;
   t.cell[22] = str(v.command_rx, 1);  t.cell[23] = str(v.notes, 1);
+  for (int c = 0; c < kCols; ++c) t.cell[c].sep = (c == kCols - 1) ? (uint8_t)'\n' : (uint8_t)',';
+  // four value cells per worker group, the ones that usually need a scan or more (primary issue, actions, other
+  // detail, notes) on different groups; delaySec (21, formatted by the number warps, possibly still in flight)
+  // last on its group
+  const signed char owned[4][6] = {
+      {8, 13, 16, 21, -1, -1}, {9, 14, 17, 18, -1, -1}, {10, 11, 12, 15, -1, -1}, {19, 20, 22, 23, -1, -1}};
+  for (int g = 0; g < 4; ++g)
+    for (int k = 0; k < 6; ++k) t.owned[g][k] = owned[g][k];
+  t.status_col = 12;
+  t.json = 0;
+  finish_row_table(t);
   return t;
 }
-constexpr int kStatusCol = 12;
-// Entry-level columns whose cells worker group g prepares: four each, the ones that usually need a scan
-// or more (primary issue, actions, other detail, notes) on different groups; delaySec (21, formatted by the
-// number warps, possibly still in flight) last on its group.
-__constant__ signed char c_owned[4][6] = {
-    {8, 13, 16, 21, -1, -1}, {9, 14, 17, 18, -1, -1}, {10, 11, 12, 15, -1, -1}, {19, 20, 22, 23, -1, -1}};
+
+// {"showDate":"..","showTime":"..","showNumber":"..","leadPilot":"..","monkeyLead":"..","operator":"..",
+//  "monkeyId":"..","planned":b,"launched":b,"commandReceived":b,"primaryIssue":"..","subIssue":".."}\n
+// — the property order of the object literal at webhookDispatcher.js:316-329, as JSON.stringify emits it.
+static RowTable make_payload_table(const pie_archive_view& v) {
+  RowTable t{};
+  int used = 0;
+  auto lit_at = [&](const char* text, uint16_t& off, uint16_t& len) {  // text without its last byte; returns that byte
+    int n = 0;
+    while (text[n]) ++n;
+    off = (uint16_t)used;
+    len = (uint16_t)(n - 1);
+    for (int i = 0; i < n - 1; ++i) t.literals[used++] = (uint8_t)text[i];
+    return (uint8_t)text[n - 1];
+  };
+  int c = 0;
+  auto literal = [&](const char* text) {
+    CellDesc d{};
+    d.kind = kCellLiteral;
+    d.per_entry = 1;
+    d.sep = lit_at(text, d.lit, d.lit_len);
+    t.cell[c++] = d;
+  };
+  auto value = [&](const pie_strcol& col, int per_entry, char sep) {
+    CellDesc d{};
+    d.offsets = col.offsets; d.data = col.data; d.kind = kCellString; d.per_entry = (uint8_t)per_entry;
+    d.sep = (uint8_t)sep;
+    t.cell[c++] = d;
+  };
+  auto yes_no = [&](const pie_strcol& col, const char* if_true, const char* if_false) {  // both end in the same byte
+    CellDesc d{};
+    d.offsets = col.offsets; d.data = col.data; d.kind = kCellYesNo; d.per_entry = 1;
+    d.sep = lit_at(if_true, d.lit, d.lit_len);
+    lit_at(if_false, d.lit_no, d.lit_no_len);
+    t.cell[c++] = d;
+  };
+  literal("{\"showDate\":\"");        value(v.show_date, 0, '"');
+  literal(",\"showTime\":\"");        value(v.show_time, 0, '"');
+  literal(",\"showNumber\":\"");      value(v.show_label, 0, '"');
+  literal(",\"leadPilot\":\"");       value(v.lead_pilot, 0, '"');
+  literal(",\"monkeyLead\":\"");      value(v.monkey_lead, 0, '"');
+  literal(",\"operator\":\"");        value(v.operator_name, 1, '"');
+  literal(",\"monkeyId\":\"");        value(v.unit_id, 1, '"');
+  literal(",\"planned\"");            literal(":");
+  yes_no(v.planned, "true,\"launched\":", "false,\"launched\":");
+  yes_no(v.launched, "true,\"commandReceived\":", "false,\"commandReceived\":");
+  yes_no(v.command_rx, "true,\"primaryIssue\":\"", "false,\"primaryIssue\":\"");
+  value(v.primary_issue, 1, '"');
+  literal(",\"subIssue\":\"");        value(v.sub_issue, 1, '"');
+  literal("}");                        literal("\n");
+  // c == 24 by construction; value cells of the entry level: 11, 13 | 16, 17 | 18, 19 | 21
+  const signed char owned[4][6] = {
+      {11, 13, -1, -1, -1, -1}, {16, 17, -1, -1, -1, -1}, {18, 19, -1, -1, -1, -1}, {21, -1, -1, -1, -1, -1}};
+  for (int g = 0; g < 4; ++g)
+    for (int k = 0; k < 6; ++k) t.owned[g][k] = owned[g][k];
+  t.status_col = -1;
+  t.json = 1;
+  finish_row_table(t);
+  return t;
+}
+static_assert(kCols == 24, "the row formats above are laid out for 24 cells");
 
 // ---- pre-pass: which columns can need quoting at all? -----------------------------------------------
-// Most columns of an archive (ids, dates, enumerations, names) never contain " , \n or \r.  One
+// Most columns of an archive (ids, dates, enumerations, names) never contain a byte that needs escaping.  One
 // streaming pass over every column's byte heap (a 128-bit load per thread and step) sets a
 // per-column flag; the row kernel then skips the per-cell scan for clean columns altogether.
+template <bool kJson>
 __global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant__ RowTable tab, int64_t n_shows,
                                                            int64_t n_entries, unsigned int* __restrict__ col_dirty) {
   const int col = blockIdx.y;
   const CellDesc& d = tab.cell[col];
-  if (d.kind == kCellNumber) return;
+  if (d.kind != kCellString && d.kind != kCellJoined) return;
   const int64_t n = d.per_entry ? n_entries : n_shows;
   int64_t first = 0, last = n;  // rows of the string column that hold this cell's bytes
   if (d.kind == kCellJoined) {
@@ -220,13 +383,13 @@ __global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant
     const uint4* __restrict__ p = reinterpret_cast<const uint4*>(w0);
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (int64_t)gridDim.x * blockDim.x) {
       const uint4 x = __ldg(p + c);
-      flags |= special_flags(x.x) | special_flags(x.y) | special_flags(x.z) | special_flags(x.w);
+      flags |= special_flags<kJson>(x.x) | special_flags<kJson>(x.y) | special_flags<kJson>(x.z) | special_flags<kJson>(x.w);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {  // the < 16 bytes at either end (or a heap shorter than a chunk)
     const uintptr_t head_end = (w1 > w0) ? w0 : a1, tail_begin = (w1 > w0) ? w1 : a1;
-    for (uintptr_t a = a0 + threadIdx.x; a < head_end; a += 32) flags |= is_special_byte(*reinterpret_cast<const uint8_t*>(a));
-    for (uintptr_t a = tail_begin + threadIdx.x; a < a1; a += 32) flags |= is_special_byte(*reinterpret_cast<const uint8_t*>(a));
+    for (uintptr_t a = a0 + threadIdx.x; a < head_end; a += 32) flags |= is_special_byte<kJson>(*reinterpret_cast<const uint8_t*>(a));
+    for (uintptr_t a = tail_begin + threadIdx.x; a < a1; a += 32) flags |= is_special_byte<kJson>(*reinterpret_cast<const uint8_t*>(a));
   }
   if (__any_sync(0xFFFFFFFFu, flags != 0) && (threadIdx.x & 31) == 0) atomicOr(&col_dirty[col], 1u);
 }
@@ -324,7 +487,7 @@ struct CsvSmem {
   unsigned long long base[2];                   // global byte offset of the tile (look-back result), by tile parity
   StageInfo info[2];
   uint32_t cell[kRows * kCellStride];           // (src:16 | len:16 << 16) of cell (r, c) at r*kCellStride + c
-  uint32_t shcell[kShowCols][kMaxTileShows];    // the same for the show-level cells of the tile's shows
+  uint32_t shcell[kMaxShowSlots][kMaxTileShows];  // the same for the show-level cells of the tile's shows
   uint32_t qmask[kRows];                        // slow path: per-row quote masks
   FillItem word_items[kMaxFillItems];           // cells to materialise through the word-wise stream ...
   FillItem quote_items[kMaxFillItems];          // ... and byte by byte ('"' to double)
@@ -356,8 +519,10 @@ __device__ __forceinline__ const int32_t* stage_i32(const uint8_t* stage, uint32
 __device__ __forceinline__ uint32_t zero_bytes_exact(uint32_t v) {
   return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
 }
-// does stage[src .. src+n) contain a character that forces quoting, and how many '"'?  Aligned words, ends masked.
-__device__ __forceinline__ uint32_t smem_special_and_quotes(const uint8_t* stage, uint32_t src, uint32_t n, uint32_t& nq) {
+// Does stage[src .. src+n) contain a byte that needs escaping, and how many bytes does escaping add?
+// Aligned words; the bytes of the two end words that lie outside the cell are replaced by spaces.
+template <bool kJson>
+__device__ __forceinline__ bool smem_scan_special(const uint8_t* stage, uint32_t src, uint32_t n, uint32_t& extra) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
   const uint32_t lead = src & 3u;
   const int nw = static_cast<int>((lead + n + 3) >> 2);
@@ -365,14 +530,22 @@ __device__ __forceinline__ uint32_t smem_special_and_quotes(const uint8_t* stage
   uint32_t flags = 0, q = 0;
   for (int k = 0; k < nw; ++k) {
     uint32_t x = w[k];
-    if (k == 0) x &= 0xFFFFFFFFu << (8 * lead);
-    if (k == nw - 1 && tail) x &= (1u << (8 * tail)) - 1u;
-    const uint32_t zq = zero_bytes_exact(x ^ 0x22222222u);
-    flags |= zq | zero_byte_flags(x ^ 0x2C2C2C2Cu) | zero_byte_flags(x ^ 0x0A0A0A0Au) | zero_byte_flags(x ^ 0x0D0D0D0Du);
-    q += __popc(zq);
+    uint32_t keep = 0xFFFFFFFFu;
+    if (k == 0) keep &= 0xFFFFFFFFu << (8 * lead);
+    if (k == nw - 1 && tail) keep &= (1u << (8 * tail)) - 1u;
+    x = (x & keep) | (0x20202020u & ~keep);
+    if (kJson) {
+      flags |= special_flags<true>(x);
+    } else {
+      const uint32_t zq = zero_bytes_exact(x ^ 0x22222222u);
+      flags |= zq | zero_byte_flags(x ^ 0x2C2C2C2Cu) | zero_byte_flags(x ^ 0x0A0A0A0Au) | zero_byte_flags(x ^ 0x0D0D0D0Du);
+      q += __popc(zq);
+    }
   }
-  nq = q;
-  return flags;
+  if (kJson && flags)  // rare: count byte by byte
+    for (uint32_t j = 0; j < n; ++j) q += extra_bytes<true>(stage[src + j]);
+  extra = q;
+  return flags != 0;
 }
 
 // Byte stream into shared memory: bytes collect in an accumulator and leave as aligned 32-bit stores.
@@ -455,61 +628,78 @@ struct ByteStream {
 // stage[src .. src+n) = the cell's staged bytes (for a list: all its items, which are contiguous in the
 // heap); items > 1 inserts '|' at the item boundaries, item_offsets[1 ..] in heap coordinates (+ delta =
 // staged).
+// CSV: a special cell is wrapped in '"' and its '"' are doubled.  JSON: the specials are escaped in place
+// (the enclosing quotes belong to the row format).  `extra` = bytes the escaping adds inside the cell.
+template <bool kJson>
 __device__ __forceinline__ uint32_t plan_cell(CsvSmem& sm, uint8_t* stage, const int32_t* item_offsets, uint32_t delta,
                                               bool dirty, uint32_t src, uint32_t n, int items) {
-  uint32_t nq = 0;
-  const bool special = dirty && n > 0 && smem_special_and_quotes(stage, src, n, nq) != 0;
+  uint32_t extra = 0;
+  const bool special = dirty && n > 0 && smem_scan_special<kJson>(stage, src, n, extra);
   if (!special && items <= 1) return pack_cell(src, n);
-  const uint32_t out_len = n + (items > 1 ? (uint32_t)(items - 1) : 0u) + (special ? 2u + nq : 0u);
+  const uint32_t out_len = n + (items > 1 ? (uint32_t)(items - 1) : 0u) + extra + ((special && !kJson) ? 2u : 0u);
   const uint32_t alloc = (out_len + 3u) & ~3u;      // the word-wise stream may fill its last word
   const uint32_t p = atomicAdd(&sm.bump, alloc);    // stays 4-byte aligned
-  const bool quotes = nq != 0;
-  const uint32_t slot = atomicAdd(quotes ? &sm.n_quote_items : &sm.n_word_items, 1u);
+  const bool bytewise = extra != 0;
+  const uint32_t slot = atomicAdd(bytewise ? &sm.n_quote_items : &sm.n_word_items, 1u);
   if (p + alloc > (uint32_t)kStageBytes || slot >= (uint32_t)kMaxFillItems || items > 0x7FFF) {
     sm.overflow = 1;  // benign race: every writer stores 1
     return 0;
   }
-  FillItem& f = (quotes ? sm.quote_items : sm.word_items)[slot];
+  FillItem& f = (bytewise ? sm.quote_items : sm.word_items)[slot];
   f.src_n = src | (n << 16);
-  f.dst_items = p | ((uint32_t)items << 16) | (special ? 0x80000000u : 0u);
+  f.dst_items = p | ((uint32_t)items << 16) | ((special && !kJson) ? 0x80000000u : 0u);  // bit 31: wrap in quotes
   f.io_delta = ((uint32_t)(reinterpret_cast<const uint8_t*>(item_offsets) - stage) & 0xFFFFu) | (delta << 16);
   return pack_cell(p, out_len);
 }
-__device__ __forceinline__ void fill_item(uint8_t* stage, const FillItem& f, bool quotes) {
+template <bool kJson>
+__device__ __forceinline__ void fill_item(uint8_t* stage, const FillItem& f, bool bytewise) {
   const uint32_t src = f.src_n & 0xFFFFu, n = f.src_n >> 16;
   const uint32_t p = f.dst_items & 0xFFFFu;
   const int items = (int)((f.dst_items >> 16) & 0x7FFFu);
-  const bool special = (f.dst_items >> 31) != 0;
+  const bool wrap = (f.dst_items >> 31) != 0;
   const int32_t* item_offsets = reinterpret_cast<const int32_t*>(stage + (f.io_delta & 0xFFFFu));
   const uint32_t delta16 = f.io_delta >> 16;  // staged addresses are < 2^16: the low half of delta is enough
-  if (!quotes) {  // ['"'] item ['|' item]... ['"'] through the word-wise stream
+  if (!bytewise) {  // ['"'] item ['|' item]... ['"'] through the word-wise stream
     ByteStream<false> out;
     out.init(stage + p);
-    if (special) out.put('"');
+    if (wrap) out.put('"');
     uint32_t ib = src;
     for (int it = 0; it < items; ++it) {
       const bool last = it + 1 >= items;
       const uint32_t ie = last ? src + n : ((delta16 + (uint32_t)item_offsets[it + 1]) & 0xFFFFu);
-      out.append(stage, ib, ie - ib, last ? (uint32_t)'"' : (uint32_t)'|', (last && !special) ? 0u : 1u);
+      out.append(stage, ib, ie - ib, last ? (uint32_t)'"' : (uint32_t)'|', (last && !wrap) ? 0u : 1u);
       ib = ie;
     }
     out.finish();
     return;
   }
-  uint32_t q = p;  // '"' to double: byte by byte
-  stage[q++] = '"';
+  uint32_t q = p;  // bytes to escape: one by one
+  if (wrap) stage[q++] = '"';
   uint32_t ib = src;
   for (int it = 0; it < items; ++it) {
     const uint32_t ie = (it + 1 < items) ? ((delta16 + (uint32_t)item_offsets[it + 1]) & 0xFFFFu) : src + n;
-    for (uint32_t j = ib; j < ie; ++j) {
-      const uint8_t c = stage[j];
-      if (c == '"') stage[q++] = '"';
-      stage[q++] = c;
-    }
+    for (uint32_t j = ib; j < ie; ++j) q += put_escaped<kJson>(stage + q, stage[j]);
     if (it + 1 < items) stage[q++] = '|';
     ib = ie;
   }
-  stage[q++] = '"';
+  if (wrap) stage[q++] = '"';
+}
+
+// toYesNoBoolean of a string (webhookDispatcher.js:60-77): value.trim().toLowerCase() === 'yes'.  ASCII folding
+// is exact here: no non-ASCII code point lower-cases to 'y', 'e' or 's'.  Works on any address space.
+__device__ __forceinline__ bool is_yes(const uint8_t* s, int n) {
+  int b = 0, e = n;
+  while (b < e) {
+    const int l = js_ws_len_at(s, b, e);
+    if (!l) break;
+    b += l;
+  }
+  while (e > b) {
+    const int l = js_ws_len_before(s, b, e);
+    if (!l) break;
+    e -= l;
+  }
+  return e - b == 3 && ascii_lower(s[b]) == 'y' && ascii_lower(s[b + 1]) == 'e' && ascii_lower(s[b + 2]) == 's';
 }
 
 // ---- slow path: a warp per row, lanes stride over the bytes of a cell, global -> global ------------
@@ -520,7 +710,7 @@ struct SlowCell {
 };
 __device__ __forceinline__ SlowCell slow_locate(const CellDesc& d, int64_t i) {
   SlowCell c{nullptr, 0, 0, 1};
-  if (d.kind == kCellString) {
+  if (d.kind == kCellString || d.kind == kCellYesNo) {
     const int b = d.offsets[i];
     c.p = d.data + b;
     c.n = d.offsets[i + 1] - b;
@@ -536,7 +726,9 @@ __device__ __forceinline__ SlowCell slow_locate(const CellDesc& d, int64_t i) {
   return c;
 }
 
-// Row lengths (sm.group[0][r]) and per-row quote masks (bit c: cell c is quoted; bit 31: Completed).
+// Row lengths (sm.group[0][r]) and per-row cell masks (bit c: cell c needs escaping, or — for a yes/no cell — is
+// `true`; bit 31: Completed).
+template <bool kJson>
 __device__ __noinline__ void slow_measure(const pie_archive_view& v, const RowTable& tab, const CsvScratch& sc,
                                           CsvSmem& sm, char* s_num, uint32_t* qmask, uint32_t s, int64_t e0, int rows) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -544,15 +736,22 @@ __device__ __noinline__ void slow_measure(const pie_archive_view& v, const RowTa
     const int64_t e = e0 + r;
     const int64_t show = sc.entry_show[e];
     bool completed = false;
-    {
-      const SlowCell st = slow_locate(tab.cell[kStatusCol], e);
+    if (tab.status_col >= 0) {
+      const SlowCell st = slow_locate(tab.cell[tab.status_col], e);
       completed = equals_exact(st.p, st.n, "Completed");
     }
     uint32_t len = 0, qm = 0;
     for (int col = 0; col < kCols; ++col) {
       const CellDesc& d = tab.cell[col];
       uint32_t cl = 0;
-      if (d.kind == kCellNumber) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
+      if (d.kind == kCellLiteral) {
+        cl = d.lit_len;
+      } else if (d.kind == kCellYesNo) {
+        const SlowCell c = slow_locate(d, e);
+        const bool yes = is_yes(c.p, c.n);  // every lane reads the same few bytes
+        cl = yes ? d.lit_len : d.lit_no_len;
+        if (yes) qm |= 1u << col;
+      } else if (d.kind == kCellNumber) {  // delaySec === null || undefined ? '' : delaySec, then String() (:301, :333)
         int nl = 0;
         if (lane == 0 && v.delay_valid[e]) {
           const RyuTables t{d_pow5_inv, d_pow5};
@@ -563,15 +762,15 @@ __device__ __noinline__ void slow_measure(const pie_archive_view& v, const RowTa
         cl = (uint32_t)nl;
       } else if (!(d.blank_if_completed && completed)) {
         const SlowCell c = slow_locate(d, d.per_entry ? e : show);
-        uint32_t sp = 0, nq = 0;
+        uint32_t sp = 0, extra = 0;
         for (int j = lane; j < c.n; j += 32) {
           const uint8_t ch = c.p[j];
-          sp |= is_special_byte(ch);
-          nq += (ch == '"');
+          sp |= is_special_byte<kJson>(ch);
+          extra += extra_bytes<kJson>(ch);
         }
         cl = (uint32_t)c.n + (c.items > 1 ? (uint32_t)(c.items - 1) : 0u);
         if (__any_sync(0xFFFFFFFFu, sp)) {
-          cl += 2u + __reduce_add_sync(0xFFFFFFFFu, nq);
+          cl += (kJson ? 0u : 2u) + __reduce_add_sync(0xFFFFFFFFu, extra);
           qm |= 1u << col;
         }
       }
@@ -584,27 +783,30 @@ __device__ __noinline__ void slow_measure(const pie_archive_view& v, const RowTa
   }
 }
 
+template <bool kJson>
 __device__ __forceinline__ void slow_copy(uint8_t* __restrict__ dst, uint32_t& pos, const uint8_t* __restrict__ s, int n,
-                                          bool quote, int lane) {
-  if (!quote) {
+                                          bool escape, int lane) {
+  if (!escape) {
     for (int j = lane; j < n; j += 32) dst[pos + j] = s[j];
     pos += (uint32_t)n;
     return;
   }
-  for (int j0 = 0; j0 < n; j0 += 32) {  // '"' doubled: positions from a ballot prefix
+  for (int j0 = 0; j0 < n; j0 += 32) {  // a lane's byte lands after the escaped bytes of the lanes before it
     const int j = j0 + lane;
     const uint8_t ch = j < n ? s[j] : 0;
-    const bool isq = j < n && ch == '"';
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, isq);
-    const uint32_t at = pos + (uint32_t)lane + __popc(m & ((1u << lane) - 1u));
-    if (j < n) {
-      dst[at] = ch;
-      if (isq) dst[at + 1] = '"';
+    const uint32_t mine = j < n ? 1u + extra_bytes<kJson>(ch) : 0u;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
     }
-    pos += (uint32_t)min(32, n - j0) + __popc(m);
+    if (j < n) put_escaped<kJson>(dst + pos + incl - mine, ch);
+    pos += __shfl_sync(0xFFFFFFFFu, incl, 31);
   }
 }
 
+template <bool kJson>
 __device__ __noinline__ void slow_write(const RowTable& tab, const CsvScratch& sc, CsvSmem& sm, const char* s_num,
                                         const uint32_t* qmask, uint32_t s, uint32_t par, int64_t e0, int rows,
                                         uint8_t* __restrict__ out) {
@@ -618,36 +820,41 @@ __device__ __noinline__ void slow_write(const RowTable& tab, const CsvScratch& s
     uint32_t pos = 0;
     for (int col = 0; col < kCols; ++col) {
       const CellDesc& d = tab.cell[col];
-      const uint8_t sep = (col == kCols - 1) ? (uint8_t)'\n' : (uint8_t)',';
-      if (d.kind == kCellNumber) {
+      if (d.kind == kCellLiteral || d.kind == kCellYesNo) {
+        const bool yes = d.kind == kCellLiteral || ((qm >> col) & 1u);
+        const uint32_t off = yes ? d.lit : d.lit_no, n = yes ? d.lit_len : d.lit_no_len;
+        for (uint32_t j = lane; j < n; j += 32) dst[pos + j] = tab.literals[off + j];
+        pos += n;
+      } else if (d.kind == kCellNumber) {
         const int nl = sm.num_len[s][r];
         if (lane < nl) dst[pos + lane] = (uint8_t)s_num[r * kMaxNumberChars + lane];
         pos += (uint32_t)nl;
       } else if (!(d.blank_if_completed && completed)) {
         const SlowCell c = slow_locate(d, d.per_entry ? e : show);
-        const bool quote = (qm >> col) & 1u;
-        if (quote) {
+        const bool escape = (qm >> col) & 1u;
+        const bool wrap = escape && !kJson;
+        if (wrap) {
           if (lane == 0) dst[pos] = '"';
           ++pos;
         }
         if (c.items <= 1) {
-          slow_copy(dst, pos, c.p, c.n, quote, lane);
+          slow_copy<kJson>(dst, pos, c.p, c.n, escape, lane);
         } else {
           for (int it = 0; it < c.items; ++it) {
             const int b = d.offsets[c.l0 + it], n = d.offsets[c.l0 + it + 1] - b;
-            slow_copy(dst, pos, d.data + b, n, quote, lane);
+            slow_copy<kJson>(dst, pos, d.data + b, n, escape, lane);
             if (it + 1 < c.items) {
               if (lane == 0) dst[pos] = '|';
               ++pos;
             }
           }
         }
-        if (quote) {
+        if (wrap) {
           if (lane == 0) dst[pos] = '"';
           ++pos;
         }
       }
-      if (lane == 0) dst[pos] = sep;
+      if (lane == 0) dst[pos] = d.sep;
       ++pos;
     }
   }
@@ -707,7 +914,10 @@ __device__ __forceinline__ void produce_tile(const pie_archive_view& v, const Ro
   Range rb{0, 0}, ro{0, 0}, ri{0, 0};  // heap bytes, offsets slice, item offsets slice
   uint32_t b0 = 0;
   int32_t l0 = 0;
-  if (lane < kCols && tab.cell[lane].kind != kCellNumber) {
+  const bool has_bytes = lane < kCols && (tab.cell[lane < kCols ? lane : 0].kind == kCellString ||
+                                         tab.cell[lane < kCols ? lane : 0].kind == kCellJoined ||
+                                         tab.cell[lane < kCols ? lane : 0].kind == kCellYesNo);
+  if (has_bytes) {
     const CellDesc& d = tab.cell[lane];
     const int64_t i0 = d.per_entry ? e0 : (int64_t)s0, i1 = d.per_entry ? e0 + rows : (int64_t)s1 + 1;
     const int32_t* oarr = (d.kind == kCellJoined) ? d.list_offsets : d.offsets;
@@ -723,17 +933,18 @@ __device__ __forceinline__ void produce_tile(const pie_archive_view& v, const Ro
     rb = Range{reinterpret_cast<uintptr_t>(d.data) + (uint32_t)f0, reinterpret_cast<uintptr_t>(d.data) + (uint32_t)f1};
   } else if (lane == kCols) {
     ro = Range{reinterpret_cast<uintptr_t>(sc.entry_show + e0), reinterpret_cast<uintptr_t>(sc.entry_show + e0 + rows)};
-  } else if (lane == kCols + 1) {
+  } else if (lane == kCols + 1 && tab.has_number) {
     ro = Range{reinterpret_cast<uintptr_t>(v.delay_sec + e0), reinterpret_cast<uintptr_t>(v.delay_sec + e0 + rows)};
-  } else if (lane == kCols + 2) {
+  } else if (lane == kCols + 2 && tab.has_number) {
     ro = Range{reinterpret_cast<uintptr_t>(v.delay_valid + e0), reinterpret_cast<uintptr_t>(v.delay_valid + e0 + rows)};
   }
   const RangePlan pb = plan_range(rb), po = plan_range(ro), pi = plan_range(ri);
   uint32_t tb, to, ti;
-  const uint32_t region_b = warp_exclusive_scan(pb.span, tb, lane);
-  const uint32_t region_o = tb + warp_exclusive_scan(po.span, to, lane);
-  const uint32_t region_i = tb + to + warp_exclusive_scan(pi.span, ti, lane);
-  const uint32_t used = tb + to + ti;
+  // the first kLiteralBytes of a stage hold the row format's literal text (copied once, at kernel start)
+  const uint32_t region_b = (uint32_t)kLiteralBytes + warp_exclusive_scan(pb.span, tb, lane);
+  const uint32_t region_o = (uint32_t)kLiteralBytes + tb + warp_exclusive_scan(po.span, to, lane);
+  const uint32_t region_i = (uint32_t)kLiteralBytes + tb + to + warp_exclusive_scan(pi.span, ti, lane);
+  const uint32_t used = (uint32_t)kLiteralBytes + tb + to + ti;
   uint32_t bulk_total = pb.bulk + po.bulk + pi.bulk;
 #pragma unroll
   for (int o = 16; o; o >>= 1) bulk_total += __shfl_xor_sync(0xFFFFFFFFu, bulk_total, o);
@@ -827,10 +1038,12 @@ __device__ __forceinline__ void look_back(const CsvScratch& sc, CsvSmem& sm, uin
 #endif
 
 // ---- the kernel ---------------------------------------------------------------------------------
+// kJson: escape mode of the value cells (the row format itself is the run-time RowTable)
+template <bool kJson>
 __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
-    csv_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab, CsvScratch sc,
-                    int64_t* __restrict__ row_offsets, uint8_t* __restrict__ out_data, uint64_t capacity,
-                    unsigned long long bias, unsigned long long* __restrict__ total_out, int force_slow) {
+    export_rows_kernel(pie_archive_view v, const __grid_constant__ RowTable tab, CsvScratch sc,
+                       int64_t* __restrict__ row_offsets, uint8_t* __restrict__ out_data, uint64_t capacity,
+                       unsigned long long bias, unsigned long long* __restrict__ total_out, int force_slow) {
   extern __shared__ __align__(128) uint8_t s_dyn[];
   uint8_t* s_out = s_dyn;  // kOutBytes + 32
   CsvSmem& sm = *reinterpret_cast<CsvSmem*>(s_dyn + kSmemOffState);
@@ -848,6 +1061,14 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     sm.done = 0;
   }
   if (tid < kCols) sm.col_dirty[tid] = sc.col_dirty[tid];
+  // the row format's literal text goes to the head of both stages; the cells that are always the same
+  // literal are entered in the cell table once
+  for (int i = tid; i < 2 * kLiteralBytes; i += kCtaThreads)
+    s_dyn[kSmemOffStage + (i / kLiteralBytes) * kStageStride + (i % kLiteralBytes)] = tab.literals[i % kLiteralBytes];
+  for (int i = tid; i < kRows * kCols; i += kCtaThreads) {
+    const CellDesc& d = tab.cell[i % kCols];
+    if (d.kind == kCellLiteral) sm.cell[(i / kCols) * kCellStride + (i % kCols)] = pack_cell(d.lit, d.lit_len);
+  }
   __syncthreads();
 
   // ================= producer warp =================
@@ -896,7 +1117,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       double value = 0.0;
       bool valid = false;
       const bool staged = info.slow == 0;  // read before the stage is released: info is rewritten two tiles on
-      if (staged && row < info.rows) {
+      if (staged && tab.has_number && row < info.rows) {
         valid = stage[info.valid_base + row] != 0;
         value = *reinterpret_cast<const double*>(stage + info.delay_base + 8 * row);
       }
@@ -1027,11 +1248,12 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       workers_sync();  // also: every worker has left the previous tile's write phase (cell table)
       PIE_PHASE(1);
       // ---- cells 1. show-level cells once per show of the tile; entry-level cells: thread (r, g) takes
-      // the columns c_owned[g] (the expensive ones — Ryu, Array.join, free text — on different groups)
+      // the value cells tab.owned[g] (the expensive ones — Array.join, free text — on different groups)
       {
         const uint32_t ns = info.n_tile_shows;
-        for (uint32_t idx = tid; idx < ns * kShowCols; idx += kWorkers) {
-          const uint32_t col = idx / ns, i = idx - col * ns;
+        for (uint32_t idx = tid; idx < ns * tab.n_show_slots; idx += kWorkers) {
+          const uint32_t slot = idx / ns, i = idx - slot * ns;
+          const uint32_t col = tab.show_col[slot];
           const int32_t* o = stage_i32(stage, info.off_base[col]);
           const int32_t f0 = o[i], f1 = o[i + 1];
           int items = 1;
@@ -1050,8 +1272,8 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
           const uint32_t src = (info.delta[col] + b) & 0xFFFFu;
           uint32_t c = pack_cell(src, n);
           if ((sm.col_dirty[col] && n) || items > 1)
-            c = plan_cell(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
-          sm.shcell[col][i] = c;
+            c = plan_cell<kJson>(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
+          sm.shcell[slot][i] = c;
         }
       }
       PIE_PHASE(2);  // show-level cells
@@ -1059,11 +1281,11 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
         // entry.status === 'Completed' (:293-297) blanks the five issue cells, which sit on several groups:
         // every thread reads the row's status itself (three shared-memory words)
         bool completed = false;
-        {
-          const int32_t* o = stage_i32(stage, info.off_base[kStatusCol]);
+        if (tab.status_col >= 0) {
+          const int32_t* o = stage_i32(stage, info.off_base[tab.status_col]);
           const int32_t f0 = o[r];
           if (o[r + 1] - f0 == 9) {
-            const uint32_t src = (info.delta[kStatusCol] + (uint32_t)f0) & 0xFFFFu;
+            const uint32_t src = (info.delta[tab.status_col] + (uint32_t)f0) & 0xFFFFu;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(stage + (src & ~3u));
             const uint32_t sh = (src & 3u) * 8u;
             const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];  // the 9 bytes lie inside these three words
@@ -1075,7 +1297,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
         uint32_t* row_cells = sm.cell + r * kCellStride;
 #pragma unroll 1
         for (int k = 0; k < kGroupCols; ++k) {
-          const int col = c_owned[g][k];
+          const int col = tab.owned[g][k];
           if (col < 0) break;
           const CellDesc& d = tab.cell[col];
           uint32_t c = 0;
@@ -1099,10 +1321,12 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
               }
             }
             const uint32_t src = (info.delta[col] + b) & 0xFFFFu;
-            if (!(d.blank_if_completed && completed)) {
+            if (d.kind == kCellYesNo) {  // toYesNoBoolean picks one of two literals
+              c = is_yes(stage + src, (int)n) ? pack_cell(d.lit, d.lit_len) : pack_cell(d.lit_no, d.lit_no_len);
+            } else if (!(d.blank_if_completed && completed)) {
               c = pack_cell(src, n);
               if ((sm.col_dirty[col] && n) || items > 1)
-                c = plan_cell(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
+                c = plan_cell<kJson>(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
             }
           }
           row_cells[col] = c;
@@ -1115,8 +1339,8 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       // ends of the CTA); rows pick up their show's cells; bytes per group of 6 consecutive columns
       if (!sm.overflow) {
         const uint32_t n_word = sm.n_word_items, n_quote = sm.n_quote_items;
-        for (uint32_t i = tid; i < n_word; i += kWorkers) fill_item(stage, sm.word_items[i], false);
-        for (uint32_t i = kWorkers - 1 - tid; i < n_quote; i += kWorkers) fill_item(stage, sm.quote_items[i], true);
+        for (uint32_t i = tid; i < n_word; i += kWorkers) fill_item<kJson>(stage, sm.word_items[i], false);
+        for (uint32_t i = kWorkers - 1 - tid; i < n_quote; i += kWorkers) fill_item<kJson>(stage, sm.quote_items[i], true);
       }
       PIE_PHASE(9);
       slow = sm.overflow != 0;  // the bump area or a fill queue ran out (uniform: written before the barrier)
@@ -1130,13 +1354,14 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
           for (int col = 0; col < kCols; ++col) {
             if (col % kGroupCols == 0) sm.group[col / kGroupCols][rt] = row_len;  // where the group starts in the row
             uint32_t c;
-            if (col < kShowCols) {
-              c = sm.shcell[col][show_i];
+            const int slot = tab.cell[col].show_slot;
+            if (slot >= 0) {
+              c = sm.shcell[slot][show_i];
               row_cells[col] = c;
             } else {
               c = row_cells[col];
             }
-            row_len += (c >> 16) + 1u;  // + ',' (or the final '\n')
+            row_len += (c >> 16) + 1u;  // + the cell's separator byte
           }
         }
         scan_rows_and_publish(tile, row_len, par);
@@ -1152,7 +1377,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       finish_pending();
       if (tid == 0) atomicAdd(sc.slow_tiles, 1u);
       workers_sync();
-      slow_measure(v, tab, sc, sm, s_num, qmask, s, e0, rows);
+      slow_measure<kJson>(v, tab, sc, sm, s_num, qmask, s, e0, rows);
       workers_sync();
       if (!published) scan_rows_and_publish(tile, (row_thread && rt < rows) ? sm.group[0][rt] : 0u, par);
       const uint32_t tile_total = sm.tile_total[par];
@@ -1162,7 +1387,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       const unsigned long long base = sm.base[par];
       if (tid < rows) row_offsets[e0 + tid] = (int64_t)(bias + base + sm.row_start[par][tid]);
       if (write && base + tile_total <= capacity)
-        slow_write(tab, sc, sm, s_num, qmask, s, par, e0, rows, out_data + base);
+        slow_write<kJson>(tab, sc, sm, s_num, qmask, s, par, e0, rows, out_data + base);
       workers_sync();  // qmask / row lengths are free again
       continue;
     }
@@ -1189,8 +1414,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
         out.init(s_out + o);
 #pragma unroll
         for (int k = 0; k < kGroupCols; ++k) {
-          const uint32_t sep = (g == kGroups - 1 && k == kGroupCols - 1) ? (uint32_t)'\n' : (uint32_t)',';
-          out.append(stage, cells[k] & 0xFFFFu, cells[k] >> 16, sep, 1u);
+          out.append(stage, cells[k] & 0xFFFFu, cells[k] >> 16, tab.cell[g * kGroupCols + k].sep, 1u);
         }
         out.finish();
       }
@@ -1206,9 +1430,10 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
   }
 }
 
-cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
-                            unsigned long long bias, unsigned long long* total_out, void* scratch,
-                            cudaStream_t stream) {
+template <bool kJson>
+static cudaError_t launch_rows(const pie_archive_view& v, const RowTable& tab, int64_t* row_offsets, uint8_t* out_data,
+                               uint64_t capacity, unsigned long long bias, unsigned long long* total_out, void* scratch,
+                               cudaStream_t stream) {
   CsvScratch sc = carve_csv(scratch, v.n_entries);
   cudaError_t err = cudaMemsetAsync(scratch, 0, csv_scratch_zero_bytes(v.n_entries), stream);
   if (err != cudaSuccess) return err;
@@ -1217,17 +1442,17 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
     if (err != cudaSuccess) return err;
     return cudaMemcpyAsync(row_offsets, total_out, 8, cudaMemcpyDeviceToDevice, stream);  // 0; the caller adds its bias
   }
-  static int configured_device = -1, resident_ctas = 0;
+  static int configured_device = -1, resident_ctas = 0;  // per instantiation
   int dev = 0;
   cudaGetDevice(&dev);
   if (configured_device != dev) {
-    err = cudaFuncSetAttribute(csv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    err = cudaFuncSetAttribute(export_rows_kernel<kJson>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return err;
-    err = cudaFuncSetAttribute(csv_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    err = cudaFuncSetAttribute(export_rows_kernel<kJson>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                cudaSharedmemCarveoutMaxShared);
     if (err != cudaSuccess) return err;
     int per_sm = 0, sms = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csv_rows_kernel, kCtaThreads, kSmemBytes);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, export_rows_kernel<kJson>, kCtaThreads, kSmemBytes);
     if (err != cudaSuccess) return err;
     err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (err != cudaSuccess) return err;
@@ -1235,19 +1460,31 @@ cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uin
     configured_device = dev;
   }
   expand_entry_show_kernel<<<(unsigned)((v.n_shows + 255) / 256), 256, 0, stream>>>(v, sc.entry_show);
-  const RowTable tab = make_row_table(v);
   {
     int64_t blocks = (v.n_entries * 3 + 255) / 256;  // ~ a 16-byte chunk per thread for the widest heaps
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    column_dirty_kernel<<<dim3((unsigned)blocks, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries, sc.col_dirty);
+    column_dirty_kernel<kJson><<<dim3((unsigned)blocks, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries,
+                                                                                 sc.col_dirty);
   }
   const int64_t tiles = csv_tiles(v.n_entries);
   const unsigned grid = (unsigned)(tiles < resident_ctas ? tiles : resident_ctas);
-  csv_rows_kernel<<<grid, kCtaThreads, kSmemBytes, stream>>>(v, tab, sc, row_offsets, out_data, capacity, bias,
-                                                            total_out, g_force_slow);
+  export_rows_kernel<kJson><<<grid, kCtaThreads, kSmemBytes, stream>>>(v, tab, sc, row_offsets, out_data, capacity, bias,
+                                                                      total_out, g_force_slow);
   g_launches += 3;
   return cudaGetLastError();
+}
+
+cudaError_t launch_csv_rows(const pie_archive_view& v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
+                            unsigned long long bias, unsigned long long* total_out, void* scratch,
+                            cudaStream_t stream) {
+  return launch_rows<false>(v, make_csv_table(v), row_offsets, out_data, capacity, bias, total_out, scratch, stream);
+}
+
+cudaError_t launch_payload_rows(const pie_archive_view& v, int64_t* row_offsets, uint8_t* out_data, uint64_t capacity,
+                                unsigned long long bias, unsigned long long* total_out, void* scratch,
+                                cudaStream_t stream) {
+  return launch_rows<true>(v, make_payload_table(v), row_offsets, out_data, capacity, bias, total_out, scratch, stream);
 }
 
 }  // namespace pie

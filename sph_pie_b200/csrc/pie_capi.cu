@@ -150,9 +150,23 @@ struct ListRef {
   const char* name;
 };
 
-// Stage every column the export rows read (all 21 string columns, 2 list columns, delaySec).
-int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_t extra_bytes, uint64_t* h2d) {
+// Row formats of the export path (pie_kernels.h launchers)
+enum RowFormat { kFormatCsv = 0, kFormatPayload = 1 };
+// does the format read string column i of the table below?  (CSV: all of them)
+static bool format_reads(RowFormat f, int i) {
+  if (f == kFormatCsv) return true;
+  // payload: show_date, show_time, show_label, lead_pilot, monkey_lead | unit_id, planned, launched, primary_issue,
+  // sub_issue, operator_name, command_rx
+  static const bool payload[21] = {false, true, true, true, true, true, false, false, true, true, true,
+                                   false, true, true, false, false, false, true, false, true, false};
+  return payload[i];
+}
+
+// Stage every column the format reads (CSV: all 21 string columns, 2 list columns, delaySec).
+int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_t extra_bytes, uint64_t* h2d,
+                       RowFormat format) {
   const int64_t S = hv->n_shows, E = hv->n_entries;
+  const bool csv = format == kFormatCsv;
   ColumnRef cols[] = {
       {&hv->show_id, &dv->show_id, S, "show_id"},           {&hv->show_date, &dv->show_date, S, "show_date"},
       {&hv->show_time, &dv->show_time, S, "show_time"},     {&hv->show_label, &dv->show_label, S, "show_label"},
@@ -174,8 +188,10 @@ int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_
   uint64_t bytes = extra_bytes + pad(4 * (uint64_t)(S + 1)) + pad(8 * (uint64_t)E) + pad((uint64_t)E);
   int rc;
   for (int i = 0; i < kCols; ++i)
-    if ((rc = plan_strcol(plans[i], cols[i].src, cols[i].dst, cols[i].n, &bytes, cols[i].name))) return rc;
-  for (int i = 0; i < 2; ++i) {
+    if (format_reads(format, i) &&
+        (rc = plan_strcol(plans[i], cols[i].src, cols[i].dst, cols[i].n, &bytes, cols[i].name)))
+      return rc;
+  for (int i = 0; csv && i < 2; ++i) {
     const pie_strlistcol* l = lists[i].src;
     if (!l->list_offsets || !l->items.offsets)
       return fail(PIE_ERR_INVALID_ARG, "column %s: list_offsets / items.offsets is NULL", lists[i].name);
@@ -187,14 +203,16 @@ int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_
     bytes += pad(4 * (uint64_t)(lists[i].n + 1));
     if ((rc = plan_strcol(item_plans[i], &item_src[i], &lists[i].dst->items, n_items, &bytes, lists[i].name))) return rc;
   }
-  if (E > 0 && (!hv->delay_sec || !hv->delay_valid)) return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
+  if (csv && E > 0 && (!hv->delay_sec || !hv->delay_valid))
+    return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
   if ((rc = g_cur->reserve(bytes))) return rc;
   if (!g_cur_stream) g_cur_stream = g_cur->stream;
   dv->n_shows = S;
   dv->n_entries = E;
   if ((rc = upload_array(hv->entry_offsets, S + 1, &dv->entry_offsets, h2d))) return rc;
   for (int i = 0; i < kCols; ++i)
-    if ((rc = upload_strcol(plans[i], h2d))) return rc;
+    if (format_reads(format, i) && (rc = upload_strcol(plans[i], h2d))) return rc;
+  if (!csv) return PIE_OK;
   for (int i = 0; i < 2; ++i) {
     if ((rc = upload_array(lists[i].src->list_offsets, lists[i].n + 1, &lists[i].dst->list_offsets, h2d))) return rc;
     if ((rc = upload_strcol(item_plans[i], h2d))) return rc;
@@ -205,17 +223,27 @@ int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_
   return PIE_OK;
 }
 
-int check_export_view_dev(const pie_archive_view* v) {
+int check_export_view_dev(const pie_archive_view* v, RowFormat format) {
   const pie_strcol* cols[] = {&v->show_id, &v->show_date, &v->show_time, &v->show_label, &v->lead_pilot, &v->monkey_lead,
                               &v->show_notes, &v->entry_id, &v->unit_id, &v->planned, &v->launched, &v->status,
                               &v->primary_issue, &v->sub_issue, &v->other_detail, &v->severity, &v->root_cause,
-                              &v->operator_name, &v->battery_id, &v->command_rx, &v->notes, &v->crew.items,
-                              &v->actions.items};
-  for (const pie_strcol* c : cols)
-    if (!c->offsets) return fail(PIE_ERR_INVALID_ARG, "export rows read every string column: one is NULL");
-  if (!v->crew.list_offsets || !v->actions.list_offsets) return fail(PIE_ERR_INVALID_ARG, "list_offsets is NULL");
+                              &v->operator_name, &v->battery_id, &v->command_rx, &v->notes};
+  for (int i = 0; i < 21; ++i)
+    if (format_reads(format, i) && !cols[i]->offsets)  // data may be NULL for a column of empty strings
+      return fail(PIE_ERR_INVALID_ARG, "a string column this row format reads is NULL");
+  if (format != kFormatCsv) return PIE_OK;
+  if (!v->crew.items.offsets || !v->actions.items.offsets || !v->crew.list_offsets || !v->actions.list_offsets)
+    return fail(PIE_ERR_INVALID_ARG, "list_offsets / items of crew or actions is NULL");
   if (v->n_entries > 0 && (!v->delay_sec || !v->delay_valid)) return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
   return PIE_OK;
+}
+
+static cudaError_t launch_rows(RowFormat format, const pie_archive_view& v, int64_t* row_offsets, uint8_t* out_data,
+                               uint64_t capacity, unsigned long long bias, unsigned long long* total_out, void* scratch,
+                               cudaStream_t stream) {
+  return format == kFormatCsv
+             ? pie::launch_csv_rows(v, row_offsets, out_data, capacity, bias, total_out, scratch, stream)
+             : pie::launch_payload_rows(v, row_offsets, out_data, capacity, bias, total_out, scratch, stream);
 }
 
 }  // namespace
@@ -454,16 +482,26 @@ int pie_show_stats_host(const pie_archive_view* hv, int32_t* stats_i32, double* 
 
 uint64_t pie_csv_rows_scratch_bytes(int64_t n_entries) { return pie::csv_scratch_bytes(n_entries); }
 
-int pie_csv_rows_dev(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,
-                     uint64_t* total_bytes_dev, void* scratch, void* stream) {
+static int export_rows_dev(RowFormat format, const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data,
+                           uint64_t out_capacity, uint64_t* total_bytes_dev, void* scratch, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
   if ((rc = check_view_common(v))) return rc;
-  if ((rc = check_export_view_dev(v))) return rc;
+  if ((rc = check_export_view_dev(v, format))) return rc;
   if (!row_offsets || !total_bytes_dev || !scratch) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
-  PIE_CUDA(pie::launch_csv_rows(*v, row_offsets, out_data, out_data ? out_capacity : 0, 0ull,
-                                (unsigned long long*)total_bytes_dev, scratch, (cudaStream_t)stream));
+  PIE_CUDA(launch_rows(format, *v, row_offsets, out_data, out_data ? out_capacity : 0, 0ull,
+                       (unsigned long long*)total_bytes_dev, scratch, (cudaStream_t)stream));
   return PIE_OK;
+}
+
+int pie_csv_rows_dev(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,
+                     uint64_t* total_bytes_dev, void* scratch, void* stream) {
+  return export_rows_dev(kFormatCsv, v, row_offsets, out_data, out_capacity, total_bytes_dev, scratch, stream);
+}
+
+int pie_archive_payloads_dev(const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,
+                             uint64_t* total_bytes_dev, void* scratch, void* stream) {
+  return export_rows_dev(kFormatPayload, v, row_offsets, out_data, out_capacity, total_bytes_dev, scratch, stream);
 }
 
 int pie_debug_csv_force_slow_path(int on) { return pie::csv_set_force_slow(on); }
@@ -536,14 +574,14 @@ static void make_chunk_view(const pie_archive_view* hv, CsvChunk* c) {
 }
 
 // stage chunk c into input arena `slot` on the H2D stream
-static int upload_chunk(CsvChunk* c, int slot, uint64_t* h2d) {
+static int upload_chunk(CsvChunk* c, int slot, uint64_t* h2d, RowFormat format) {
   g_cur = &g_pipe_in[slot];
   g_cur_stream = g_pipe.h2d;
   if (!g_cur->stream) g_cur->stream = g_pipe.h2d;  // reserve() only creates a stream when there is none
   const int64_t E = c->e1 - c->e0;
   memset(&c->dev, 0, sizeof(c->dev));
   const uint64_t extra = pad(pie::csv_scratch_bytes(E)) + pad(8 * (uint64_t)(E + 1)) + pad(64);
-  int rc = upload_export_view(&c->host, &c->dev, extra + (extra >> 2), h2d);  // +25 %: later chunks rarely regrow
+  int rc = upload_export_view(&c->host, &c->dev, extra + (extra >> 2), h2d, format);  // +25 %: later chunks rarely regrow
   if (rc) return rc;
   c->scratch = g_cur->take(pie::csv_scratch_bytes(E));
   c->d_offsets = (int64_t*)g_cur->take(8 * (uint64_t)(E + 1));
@@ -558,8 +596,8 @@ int64_t pie_set_csv_chunk_rows(int64_t rows) {
   return old;
 }
 
-int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,
-                      uint64_t* total_bytes) {
+static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_t* row_offsets, uint8_t* out_data,
+                            uint64_t out_capacity, uint64_t* total_bytes) {
   std::lock_guard<std::mutex> lock(g_host_mutex);
   int rc = ensure_init();
   if (rc) return rc;
@@ -593,7 +631,7 @@ int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t*
   uint64_t h2d = 0, d2h = 0;
   unsigned long long bias = 0;
   bool overflow = false;
-  if ((rc = upload_chunk(&chunks[0], 0, &h2d))) return rc;
+  if ((rc = upload_chunk(&chunks[0], 0, &h2d, format))) return rc;
   PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[0], g_pipe.h2d));
   for (int k = 0; k < K; ++k) {
     const int slot = k & 1;
@@ -604,12 +642,12 @@ int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t*
         PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.kernel_done[slot ^ 1], 0));
         PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.d2h_done[slot ^ 1], 0));
       }
-      if ((rc = upload_chunk(&chunks[(size_t)k + 1], slot ^ 1, &h2d))) return rc;
+      if ((rc = upload_chunk(&chunks[(size_t)k + 1], slot ^ 1, &h2d, format))) return rc;
       PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[slot ^ 1], g_pipe.h2d));
     }
     PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.h2d_done[slot], 0));
     // pass 1: sizes only (row offsets + total), so the output can be placed and sized exactly
-    PIE_CUDA(pie::launch_csv_rows(c.dev, c.d_offsets, nullptr, 0, bias, c.d_total, c.scratch, g_pipe.cmp));
+    PIE_CUDA(launch_rows(format, c.dev, c.d_offsets, nullptr, 0, bias, c.d_total, c.scratch, g_pipe.cmp));
     PIE_CUDA(cudaMemcpyAsync(g_pipe.h_total, c.d_total, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
     PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
     const unsigned long long total = *g_pipe.h_total;
@@ -623,8 +661,8 @@ int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t*
         if ((rc = g_pipe.out[slot].ensure(total + (total >> 2) + 256))) return rc;
       }
       // pass 2: write (the chunk's inputs are resident; most of them still in L2)
-      PIE_CUDA(pie::launch_csv_rows(c.dev, c.d_offsets, g_pipe.out[slot].base, total, bias, c.d_total, c.scratch,
-                                    g_pipe.cmp));
+      PIE_CUDA(launch_rows(format, c.dev, c.d_offsets, g_pipe.out[slot].base, total, bias, c.d_total, c.scratch,
+                           g_pipe.cmp));
     }
     PIE_CUDA(cudaEventRecord(g_pipe.kernel_done[slot], g_pipe.cmp));
     PIE_CUDA(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.kernel_done[slot], 0));
@@ -647,9 +685,19 @@ int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t*
   g_cur = &g_arena;
   g_cur_stream = g_arena.stream;
   if (overflow)
-    return fail(PIE_ERR_CAPACITY, "CSV rows need %llu bytes, the caller's buffer holds %llu", bias,
+    return fail(PIE_ERR_CAPACITY, "the rows need %llu bytes, the caller's buffer holds %llu", bias,
                 (unsigned long long)out_capacity);
   return PIE_OK;
+}
+
+int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,
+                      uint64_t* total_bytes) {
+  return export_rows_host(kFormatCsv, hv, row_offsets, out_data, out_capacity, total_bytes);
+}
+
+int pie_archive_payloads_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,
+                              uint64_t* total_bytes) {
+  return export_rows_host(kFormatPayload, hv, row_offsets, out_data, out_capacity, total_bytes);
 }
 
 int pie_selftest_fast_div(int32_t max_b, uint64_t* mismatches) {

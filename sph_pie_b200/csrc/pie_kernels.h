@@ -22,6 +22,11 @@ cudaError_t launch_csv_rows(const pie_archive_view& dev_view, int64_t* row_offse
                             uint64_t capacity, unsigned long long offset_bias, unsigned long long* total_out,
                             void* scratch, cudaStream_t stream);
 
+// JSON.stringify(buildArchiveEntryPayload(show, entry)) + '\n' per entry: same kernel, another row format
+cudaError_t launch_payload_rows(const pie_archive_view& dev_view, int64_t* row_offsets, uint8_t* out_data,
+                                uint64_t capacity, unsigned long long offset_bias, unsigned long long* total_out,
+                                void* scratch, cudaStream_t stream);
+
 // debug knobs of the export-row kernel (tests): force every tile through the slow path (on < 0 only
 // queries; returns the previous value); number of tiles of the last launch on `scratch` that took it
 int csv_set_force_slow(int on);

@@ -188,13 +188,22 @@ class CsvBuffers:
         self.scratch = torch.empty(int(lib.pie_csv_rows_scratch_bytes(n_entries)), dtype=torch.uint8, device=device)
 
 
-def csv_rows_dev(table: ArchiveTable, bufs: CsvBuffers, size_only: bool = False) -> None:
-    """Enqueue the export-row kernels on torch's current stream (no sync)."""
+def _rows_dev(entry: str, table: ArchiveTable, bufs: CsvBuffers, size_only: bool) -> None:
     _lib.ensure_init()
     view = table.view()
-    _lib.check(_lib.load().pie_csv_rows_dev(C.byref(view), bufs.row_offsets.data_ptr(),
-                                            None if size_only else bufs.data.data_ptr(), bufs.capacity,
-                                            bufs.total.data_ptr(), bufs.scratch.data_ptr(), _stream_ptr()))
+    fn = getattr(_lib.load(), entry)
+    _lib.check(fn(C.byref(view), bufs.row_offsets.data_ptr(), None if size_only else bufs.data.data_ptr(),
+                  bufs.capacity, bufs.total.data_ptr(), bufs.scratch.data_ptr(), _stream_ptr()))
+
+
+def csv_rows_dev(table: ArchiveTable, bufs: CsvBuffers, size_only: bool = False) -> None:
+    """Enqueue the export-row kernels on torch's current stream (no sync)."""
+    _rows_dev("pie_csv_rows_dev", table, bufs, size_only)
+
+
+def archive_payloads_dev(table: ArchiveTable, bufs: CsvBuffers, size_only: bool = False) -> None:
+    """Enqueue the archive-entry-payload kernels (JSON Lines) on torch's current stream (no sync)."""
+    _rows_dev("pie_archive_payloads_dev", table, bufs, size_only)
 
 
 def csv_slow_tiles(table: ArchiveTable, bufs: CsvBuffers) -> int:
@@ -205,22 +214,32 @@ def csv_slow_tiles(table: ArchiveTable, bufs: CsvBuffers) -> int:
     return int(n.value)
 
 
-def csv_rows(table: ArchiveTable) -> CsvRows:
-    """buildCsvRow(buildTableRow(show, entry)) for every entry of every show."""
+def _rows(table: ArchiveTable, dev_fn, host_entry: str) -> CsvRows:
     _lib.ensure_init()
     E = table.n_entries
     if table.is_cuda:
         sizing = CsvBuffers(E, 0, table.device)
-        csv_rows_dev(table, sizing, size_only=True)
+        dev_fn(table, sizing, size_only=True)
         total = int(sizing.total.cpu())
         bufs = CsvBuffers(E, total, table.device)
-        csv_rows_dev(table, bufs)
+        dev_fn(table, bufs)
         return CsvRows(bufs.row_offsets, bufs.data[:total])
     view = table.view()
     offsets = torch.empty(E + 1, dtype=torch.int64)
     total = C.c_uint64(0)
-    lib = _lib.load()
-    _lib.check(lib.pie_csv_rows_host(C.byref(view), offsets.data_ptr(), None, 0, C.byref(total)))
+    fn = getattr(_lib.load(), host_entry)
+    _lib.check(fn(C.byref(view), offsets.data_ptr(), None, 0, C.byref(total)))
     data = torch.empty(max(int(total.value), 1), dtype=torch.uint8)
-    _lib.check(lib.pie_csv_rows_host(C.byref(view), offsets.data_ptr(), data.data_ptr(), int(total.value), C.byref(total)))
+    _lib.check(fn(C.byref(view), offsets.data_ptr(), data.data_ptr(), int(total.value), C.byref(total)))
     return CsvRows(offsets, data[:int(total.value)])
+
+
+def csv_rows(table: ArchiveTable) -> CsvRows:
+    """buildCsvRow(buildTableRow(show, entry)) for every entry of every show."""
+    return _rows(table, csv_rows_dev, "pie_csv_rows_host")
+
+
+def archive_payloads(table: ArchiveTable) -> CsvRows:
+    """JSON.stringify(buildArchiveEntryPayload(show, entry)) for every entry of every show (one row each,
+    reference webhookDispatcher.js:315-330 and :527-540)."""
+    return _rows(table, archive_payloads_dev, "pie_archive_payloads_host")

@@ -6,13 +6,16 @@ the pure re-shaping functions (object <-> column order) are plain host code, as 
     buildCsvRows(show)                   tableRows.map(buildCsvRow) of dispatchShowEvent (:556, :571)
     exportShowAsCsv(show)                public/app.js:5558-5570 (returns the CSV text)
     buildMessagePayload(rowObject)       server/webhookDispatcher.js:307-313
+    archiveEntryPayloadBodies(show)      JSON.stringify(buildArchiveEntryPayload(show, entry)) for every entry: the
+                                         bodies dispatchShowEvent('show.archived') posts one by one (:520-540)
+    buildArchiveEntryPayload(show, entry)  :315-330, as an object (parsed back from the GPU's JSON text)
 """
 from __future__ import annotations
 
 from typing import List, Optional
 
 from .columnar import pack_shows
-from .ops import csv_rows
+from .ops import archive_payloads, csv_rows
 
 EXPORT_COLUMNS = [
     "showId", "showDate", "showTime", "showLabel", "crew", "leadPilot", "monkeyLead", "showNotes",
@@ -42,3 +45,25 @@ def exportShowAsCsv(show: dict) -> str:
 def buildMessagePayload(rowObject: Optional[dict] = None) -> dict:
     row = rowObject if isinstance(rowObject, dict) else {}
     return {c: ("" if row.get(c) is None else row[c]) for c in EXPORT_COLUMNS}
+
+
+def archiveEntryPayloadBodiesMany(shows: List[Optional[dict]]) -> List[List[str]]:
+    """Request bodies of every entry of every show in one launch."""
+    table = pack_shows(shows)
+    rows = archive_payloads(table).rows()
+    eo = table.entry_offsets.tolist()
+    return [rows[eo[s]:eo[s + 1]] for s in range(len(shows))]
+
+
+def archiveEntryPayloadBodies(show: Optional[dict]) -> List[str]:
+    return archiveEntryPayloadBodiesMany([show])[0]
+
+
+def buildArchiveEntryPayload(show: Optional[dict] = None, entry: Optional[dict] = None) -> dict:
+    """The payload object of ONE entry (reference :315-330).  Computed on the GPU like the bulk call and
+    parsed back, so the mirror has no second implementation of toYesNoBoolean / the `|| ''` defaults."""
+    import json
+
+    s = dict(show) if isinstance(show, dict) else {}
+    s["entries"] = [entry if isinstance(entry, dict) else {}]
+    return json.loads(archiveEntryPayloadBodies(s)[0])

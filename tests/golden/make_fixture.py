@@ -26,6 +26,11 @@ entry = {
     "notes": "Green across the board",
 }
 row = po.build_table_row(show, entry)
+# written out by hand from the object literal at server/webhookDispatcher.js:316-329 (not computed):
+PAYLOAD_JSON = ('{"showDate":"2024-07-04","showTime":"21:00","showNumber":"Independence Demo","leadPilot":"Alex",'
+                '"monkeyLead":"Nazar","operator":"Alex","monkeyId":"Drone-01","planned":true,"launched":true,'
+                '"commandReceived":true,"primaryIssue":"","subIssue":""}')
+assert po.archive_entry_payload_json(show, entry) == PAYLOAD_JSON
 doc = {
     "source": "scripts/simulate-webhook.js:42-65 (show, entry); expected_* hand-derived, see make_fixture.py",
     "export_columns": po.EXPORT_COLUMNS,
@@ -35,6 +40,7 @@ doc = {
     "expected_message": po.build_message_payload(row),
     "expected_csv_row": po.build_csv_row(row),
     "expected_archive_entry_payload": po.build_archive_entry_payload(show, entry),
+    "expected_archive_payload_json": PAYLOAD_JSON,
     "expected_show_stats": po.compute_archive_show_stats({**show, "entries": [entry]}),
 }
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "webhook_fixture.json"), "w") as f:
