@@ -292,6 +292,29 @@ def main():
     daily_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
     csv_ms = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
 
+    # ---- outside the step: archive entry payloads (JSON Lines) on the same resident table — the next row of
+    # the scope table (DESIGN.md §0 f), timed alone with CUDA events on the launch stream
+    psizing = ops.CsvBuffers(E, 0, dev)
+    ops.archive_payloads_dev(table, psizing, size_only=True)
+    payload_total = int(psizing.total.cpu())
+    pbufs = ops.CsvBuffers(E, payload_total, dev)
+    for _ in range(3):
+        ops.archive_payloads_dev(table, pbufs)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_payload_runs = max(3, min(args.steps, 10))
+    torch.cuda.synchronize()
+    p0.record()
+    for _ in range(n_payload_runs):
+        ops.archive_payloads_dev(table, pbufs)
+    p1.record()
+    torch.cuda.synchronize()
+    payload_ms = p0.elapsed_time(p1) / n_payload_runs
+    payload_cols = ([table.show_cols[k] for k in ("show_date", "show_time", "show_label", "lead_pilot", "monkey_lead")]
+                    + [table.entry_cols[k] for k in ("operator_name", "unit_id", "planned", "launched", "command_rx",
+                                                      "primary_issue", "sub_issue")])
+    payload_bytes = sum(c.nbytes() for c in payload_cols) + 4 * (S + 1) + payload_total + 8 * (E + 1)
+    del pbufs, psizing
+
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     import ctypes as C
 
@@ -355,7 +378,7 @@ def main():
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("shows") == S:
-            k = tj["kernels"]["csv_rows_kernel"]
+            k = tj["kernels"].get("export_rows_kernel") or tj["kernels"]["csv_rows_kernel"]
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
 
     out = {
@@ -367,8 +390,8 @@ def main():
                 "steps": e2e_steps, "api": "pie_archive_analytics_host + pie_csv_rows_host (pinned host buffers in and out)"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
-        "roofline": {  # the dominant kernel of the step: csv_rows_kernel
-            "bound": "hbm", "kernel": "export rows (csv_rows_kernel 94 % + column_dirty_kernel + expand_entry_show_kernel)",
+        "roofline": {  # the dominant kernel of the step: export_rows_kernel<csv>
+            "bound": "hbm", "kernel": "export rows (export_rows_kernel<csv> 93 % + column_dirty_kernel + expand_entry_show_kernel)",
             "achieved": gbs(export_bytes, csv_ms), "peak": peak, "unit": "GB/s", "frac": gbs(export_bytes, csv_ms) / peak,
             "traffic": traffic, "traffic_source": "profiles/traffic_r01.json (ncu dram__bytes_read+write per launch)",
             "peak_source": peak_src, "algorithmic_bytes_per_launch": export_bytes,
@@ -379,6 +402,10 @@ def main():
                 "daily pipeline (7 small kernels)": {"ms_per_step": daily_ms, "algorithmic_bytes": daily_bytes,
                                                      "achieved_gbs": gbs(daily_bytes, daily_ms),
                                                      "frac": gbs(daily_bytes, daily_ms) / peak},
+                "archive entry payloads (export_rows_kernel<json>, not part of the step)": {
+                    "ms_per_launch": payload_ms, "algorithmic_bytes": payload_bytes, "json_bytes_out": payload_total,
+                    "achieved_gbs": gbs(payload_bytes, payload_ms), "frac": gbs(payload_bytes, payload_ms) / peak,
+                    "entries_per_s": E / (payload_ms * 1e-3)},
             },
         },
     }

@@ -12,7 +12,7 @@ hdr = rows[0]
 col = {h: i for i, h in enumerate(hdr)}
 agg = collections.defaultdict(lambda: collections.defaultdict(list))
 for r in rows[1:]:
-    name = r[col["Kernel Name"]].split("(")[0].replace("pie::", "")
+    name = r[col["Kernel Name"]].split("(")[0].replace("pie::", "").replace("void ", "").split("<")[0]
     agg[name][r[col["Metric Name"]]].append(float(r[col["Metric Value"]].replace(",", "")))
 out = {}
 for k, m in agg.items():

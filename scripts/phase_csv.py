@@ -1,4 +1,4 @@
-"""Developer tool: per-phase cycle counts of csv_rows_kernel (library built with -DPIE_CSV_PROFILE)."""
+"""Developer tool: per-phase cycle counts of export_rows_kernel (library built with -DPIE_CSV_PROFILE)."""
 import os
 import sys
 

@@ -1,4 +1,4 @@
-"""Developer tool: build csv_rows_kernel variants (-D tunables) and time each on the bench table.
+"""Developer tool: build export_rows_kernel variants (-D tunables) and time each on the bench table.
 Usage:  python scripts/sweep_csv.py build   (CPU box: cross-compiles the variants into scripts/_variants)
         python scripts/sweep_csv.py run     (GPU box: times each variant in its own process)"""
 import glob
@@ -32,7 +32,7 @@ def build():
             f"-DPIE_CSV_MIN_BLOCKS={v['B']}", "-Xptxas", "-v", "-o", so] + srcs
         r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
         lines = r.stderr.splitlines()
-        k = [i for i, l in enumerate(lines) if "Compiling entry function" in l and "csv_rows_kernel" in l]
+        k = [i for i, l in enumerate(lines) if "Compiling entry function" in l and "export_rows_kernel" in l]
         info = lines[k[0] + 2: k[0] + 4] if k else lines[-5:]
         print(name(v), r.returncode, " | ".join(x.strip() for x in info))
 
