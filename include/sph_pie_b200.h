@@ -197,6 +197,37 @@ int pie_csv_rows_host(const pie_archive_view* host_view, int64_t* row_offsets, u
  * previous value; rows <= 0 only queries.  Default 2^20. */
 int64_t pie_set_csv_chunk_rows(int64_t rows);
 
+/* ---- live show metrics: replaces computeMetrics(show) (public/app.js:5024-5047), the header strip of a show
+ * (success rate, status counts, average delay, top issues), for every show of the batch.
+ * metrics_i32 is int32[PIE_CM_COUNT][stride], plane-major like the statistics tables:
+ *   SUCCESS_RATE  Math.round(completed / plannedYes * 100), 0 when no entry has planned === 'Yes'
+ *   COMPLETED / NO_LAUNCH / ABORT  entries whose status === 'Completed' / 'No-launch' / 'Abort' (strict)
+ *   TOP0..TOP2    topIssues as ENTRY ROW INDICES: the first entry (in the batch's entry numbering) that carries
+ *                 the issue string, -1 past the end of the list; the string is primary_issue[that row].  Order =
+ *                 Object.entries(issues) (array-index keys first, ascending; then insertion order) stably sorted by
+ *                 count, descending — what .sort((a,b)=>b[1]-a[1]).slice(0,3) leaves.  Work is O(k^2) in the number
+ *                 k of a show's entries that carry an issue.
+ *   AVG_LEN       length of avgDelay, whose characters are avg_delay_text[show * PIE_CM_TEXT .. +AVG_LEN):
+ *                 (sum / count).toFixed(2) over the entries whose delaySec is a number (typeof: NaN and +-Infinity
+ *                 count), '0.00' when there is none.  toFixed rounds the EXACT binary value, ties up in magnitude.
+ * Reads: entry_offsets, planned, status, primary_issue, delay_sec, delay_valid. */
+enum {
+  PIE_CM_SUCCESS_RATE = 0,
+  PIE_CM_COMPLETED = 1,
+  PIE_CM_NO_LAUNCH = 2,
+  PIE_CM_ABORT = 3,
+  PIE_CM_TOP0 = 4,
+  PIE_CM_TOP1 = 5,
+  PIE_CM_TOP2 = 6,
+  PIE_CM_AVG_LEN = 7,
+  PIE_CM_COUNT = 8
+};
+#define PIE_CM_TEXT 32 /* bytes reserved per show for avgDelay (the longest is 25) */
+int pie_compute_metrics_dev(const pie_archive_view* dev_view, int32_t* metrics_i32, uint8_t* avg_delay_text,
+                            int64_t stride, void* stream);
+int pie_compute_metrics_host(const pie_archive_view* host_view, int32_t* metrics_i32, uint8_t* avg_delay_text,
+                             int64_t stride);
+
 /* ---- archive entry payloads: replaces JSON.stringify(buildArchiveEntryPayload(show, entry))
  * (server/webhookDispatcher.js:315-330, with toYesNoBoolean :60-77) mapped over every entry of every show — the
  * request bodies dispatchShowEvent('show.archived') posts one by one (:520-540; axios serialises the object with

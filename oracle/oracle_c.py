@@ -99,6 +99,20 @@ def payload_rows(table: ArchiveTable, nthreads: int = 1, offsets=None, data=None
     return _rows("oracle_payload_rows_mt", table, nthreads, offsets, data)
 
 
+def compute_metrics(table: ArchiveTable):
+    """(int32[PIE_CM_COUNT][S], uint8[S][32]) from the C restatement of computeMetrics."""
+    assert not table.is_cuda
+    so = load()
+    so.oracle_compute_metrics.restype = C.c_int
+    so.oracle_compute_metrics.argtypes = [C.POINTER(_lib.ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64]
+    S = max(table.n_shows, 1)
+    i32 = torch.zeros((_lib.PIE_CM_COUNT, S), dtype=torch.int32)
+    text = torch.zeros((S, _lib.PIE_CM_TEXT), dtype=torch.uint8)
+    view = table.view()
+    so.oracle_compute_metrics(C.byref(view), i32.data_ptr(), text.data_ptr(), S)
+    return i32[:, : table.n_shows], text[: table.n_shows]
+
+
 def number_to_string_batch(xs):
     import numpy as np
 

@@ -691,6 +691,120 @@ int oracle_payload_rows_mt(const pie_archive_view* v, int64_t* row_offsets, uint
   return rows_mt(payload_show_range, v, row_offsets, out_data, capacity, total, nthreads);
 }
 
+/* ---- computeMetrics(show) (public/app.js:5024-5047) ------------------------------------------------------- */
+/* Number.prototype.toFixed(2): the exact value of |x| * 100, rounded to an integer with ties up, by integer
+ * arithmetic on the mantissa (ECMA-262 21.1.3.3: "n / 10^f - x as close to zero as possible; two such n: the
+ * larger"); "-" iff x < 0; |x| >= 1e21 and non-finite values go through Number::toString. */
+static int js_to_fixed2(double x, char* out) {
+  if (x != x) { memcpy(out, "NaN", 3); return 3; }
+  if (fabs(x) >= 1e21) return js_number_to_string(x, out);
+  char* o = out;
+  if (x < 0) *o++ = '-';
+  int e2;
+  const double fr = frexp(fabs(x), &e2);                   /* |x| = fr * 2^e2, fr in [0.5, 1) */
+  const unsigned __int128 m = (unsigned __int128)(uint64_t)ldexp(fr, 53); /* 53-bit integer mantissa */
+  const int e = e2 - 53;                                   /* |x| = m * 2^e */
+  unsigned __int128 n;                                     /* round(|x| * 100) */
+  if (e >= 0) n = (m * 100) << e;                          /* < 1e23 < 2^77 */
+  else if (-e >= 120) n = 0;
+  else n = (m * 100 + ((unsigned __int128)1 << (-e - 1))) >> -e;
+  char digits[48];
+  int k = 0;
+  unsigned __int128 ip = n / 100;
+  const int frac = (int)(n % 100);
+  do { digits[k++] = (char)('0' + (int)(ip % 10)); ip /= 10; } while (ip);
+  while (k) *o++ = digits[--k];
+  *o++ = '.';
+  *o++ = (char)('0' + frac / 10);
+  *o++ = (char)('0' + frac % 10);
+  return (int)(o - out);
+}
+
+static int str_eq_lit(const pie_strcol* c, int64_t i, const char* lit) {
+  const int n = c->offsets[i + 1] - c->offsets[i];
+  return n == (int)strlen(lit) && memcmp(c->data + c->offsets[i], lit, (size_t)n) == 0;
+}
+/* array index key (ECMA-262 6.1.7): canonical decimal string of an integer in 0 .. 2^32-2 */
+static int array_index_key(const uint8_t* s, int n, uint64_t* value) {
+  if (n < 1 || n > 10 || (n > 1 && s[0] == '0')) return 0;
+  uint64_t v = 0;
+  for (int i = 0; i < n; ++i) { if (s[i] < '0' || s[i] > '9') return 0; v = v * 10 + (uint64_t)(s[i] - '0'); }
+  if (v > 4294967294ull) return 0;
+  *value = v;
+  return 1;
+}
+typedef struct { int first; int count; int is_index; uint64_t index; int order; } issue_slot;
+
+int oracle_compute_metrics(const pie_archive_view* v, int32_t* out, uint8_t* text, int64_t stride) {
+  for (int64_t s = 0; s < v->n_shows; ++s) {
+    const int e0 = v->entry_offsets[s], e1 = v->entry_offsets[s + 1];
+    int planned = 0, completed = 0, no_launch = 0, abort_ = 0, dn = 0;
+    double sum = 0.0;
+    issue_slot* slots = (issue_slot*)malloc(sizeof(issue_slot) * (size_t)(e1 - e0 + 1));
+    int ns = 0;
+    for (int e = e0; e < e1; ++e) {
+      planned += str_eq_lit(&v->planned, e, "Yes");
+      const int comp = str_eq_lit(&v->status, e, "Completed");
+      completed += comp;
+      no_launch += str_eq_lit(&v->status, e, "No-launch");
+      abort_ += str_eq_lit(&v->status, e, "Abort");
+      if (v->delay_valid[e]) { sum = sum + v->delay_sec[e]; dn++; }
+      const uint8_t* p = v->primary_issue.data + v->primary_issue.offsets[e];
+      const int n = v->primary_issue.offsets[e + 1] - v->primary_issue.offsets[e];
+      if (comp || n == 0) continue;
+      int k = 0;
+      for (; k < ns; ++k) {
+        const int f = slots[k].first;
+        const int fn = v->primary_issue.offsets[f + 1] - v->primary_issue.offsets[f];
+        if (fn == n && memcmp(v->primary_issue.data + v->primary_issue.offsets[f], p, (size_t)n) == 0) break;
+      }
+      if (k == ns) {
+        slots[ns].first = e; slots[ns].count = 0; slots[ns].order = ns;
+        slots[ns].is_index = array_index_key(p, n, &slots[ns].index);
+        ns++;
+      }
+      slots[k].count++;
+    }
+    /* Object.entries order: array-index keys ascending, then creation order; then a stable sort by count desc:
+     * insertion sort on the combined key keeps it simple and stable */
+    for (int i = 1; i < ns; ++i) {
+      issue_slot x = slots[i];
+      int j = i - 1;
+      for (; j >= 0; --j) {
+        const issue_slot* y = &slots[j];
+        int before; /* does x come before y? */
+        if (x.count != y->count) before = x.count > y->count;
+        else if (x.is_index != y->is_index) before = x.is_index;
+        else if (x.is_index) before = x.index < y->index;
+        else before = x.order < y->order;
+        if (!before) break;
+        slots[j + 1] = slots[j];
+      }
+      slots[j + 1] = x;
+    }
+    double rate = 0;
+    if (planned) {
+      const double q = ((double)completed / (double)planned) * 100.0;
+      const double r = floor(q);
+      rate = (q - r >= 0.5) ? r + 1 : r; /* Math.round: ties toward +inf */
+    }
+    out[0 * stride + s] = (int32_t)rate;
+    out[1 * stride + s] = completed;
+    out[2 * stride + s] = no_launch;
+    out[3 * stride + s] = abort_;
+    for (int k = 0; k < 3; ++k) out[(4 + k) * stride + s] = k < ns ? slots[k].first : -1;
+    char buf[64];
+    int len;
+    if (dn) len = js_to_fixed2(sum / (double)dn, buf);
+    else { memcpy(buf, "0.00", 4); len = 4; }
+    out[7 * stride + s] = len;
+    memset(text + 32 * s, 0, 32);
+    memcpy(text + 32 * s, buf, (size_t)len);
+    free(slots);
+  }
+  return 0;
+}
+
 /* Number::toString of an array (checker for the product's Ryu): out is n x 32 bytes */
 void oracle_number_to_string_batch(const double* x, int64_t n, char* out, int32_t* lens) {
   for (int64_t i = 0; i < n; ++i) lens[i] = js_number_to_string(x[i], out + 32 * i);

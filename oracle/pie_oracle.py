@@ -445,6 +445,19 @@ def group_metric_summary(group, metric_key):
     }
 
 
+def js_is_array_index(key: str) -> bool:
+    """A property key that is an array index (ECMA-262 6.1.7): the canonical decimal string of an integer in
+    0 .. 2^32 - 2.  OrdinaryOwnPropertyKeys lists such keys first, in ascending numeric order, before the string
+    keys in insertion order — which is the order Object.entries walks."""
+    return key.isascii() and key.isdigit() and (key == "0" or key[0] != "0") and len(key) <= 10 and int(key) <= 2 ** 32 - 2
+
+
+def js_object_entries(d: dict):
+    """Object.entries of an object whose properties were created in the dict's insertion order."""
+    idx = sorted((k for k in d if js_is_array_index(k)), key=int)
+    return [(k, d[k]) for k in idx] + [(k, v) for k, v in d.items() if not js_is_array_index(k)]
+
+
 def compute_metrics(show):
     """public/app.js:5024-5047 computeMetrics(show) (live show header)."""
     entries = js_or(js_get(show, "entries"), [])
@@ -466,15 +479,19 @@ def compute_metrics(show):
         if js_get(e, "status") != "Completed" and js_truthy(pi):
             k = js_string(pi)
             issues[k] = issues.get(k, 0) + 1
-    top = [k for k, _ in sorted(issues.items(), key=lambda kv: -kv[1])[:3]]  # stable
+    top = [k for k, _ in sorted(js_object_entries(issues), key=lambda kv: -kv[1])[:3]]  # Array.prototype.sort is stable
     success = js_math_round((completed / planned_yes) * 100) if planned_yes else 0
     return {"successRate": success, "countCompleted": completed, "countNoLaunch": no_launch,
             "countAbort": abort, "avgDelay": avg, "topIssues": top}
 
 
 def js_math_round(x: float):
-    """Math.round: half toward +inf."""
-    return math.floor(x + 0.5) if math.isfinite(x) else x
+    """Math.round: the integer closest to x, ties toward +inf (floor(x + 0.5) would round the double just
+    below 0.5 up, because the sum is not exact)."""
+    if not math.isfinite(x):
+        return x
+    r = math.floor(x)
+    return r + 1 if x - r >= 0.5 else r
 
 
 def js_to_fixed2(x: float) -> str:
@@ -485,11 +502,10 @@ def js_to_fixed2(x: float) -> str:
         return "NaN"
     if abs(x) >= 1e21:
         return js_number_to_string(x)
-    neg = x < 0 or (x == 0 and math.copysign(1, x) < 0)
     d = Decimal(abs(x)) * 100
     n = int(d.to_integral_value(rounding="ROUND_HALF_UP"))
     s = f"{n // 100}.{n % 100:02d}"
-    return ("-" + s) if (neg and n != 0) else s
+    return ("-" + s) if x < 0 else s  # step 6: "if x < 0, set s to '-' and x to -x": (-0.001).toFixed(2) is "-0.00", (-0).toFixed(2) "0.00"
 
 
 # --------------------------------------------------------------------------- export rows

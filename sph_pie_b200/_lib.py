@@ -16,6 +16,8 @@ PIE_N_METRICS = 19
 PIE_SI_COUNT = 18
 PIE_SF_COUNT = 15
 PIE_DF_COUNT = 3
+PIE_CM_COUNT = 8
+PIE_CM_TEXT = 32
 PIE_DAY_NONE = -(2 ** 63)
 
 PIE_OK = 0
@@ -34,6 +36,7 @@ SI_ISSUE_ORDER_HI = 17
 SF_AVG_DELAY, SF_MAX_DELAY, SF_COMPLETION_RATE, SF_LAUNCH_RATE, SF_ABORT_RATE = range(5)
 SF_ISSUE_RATE0 = 5
 DF_AVERAGE, DF_MIN, DF_MAX = range(3)
+(CM_SUCCESS_RATE, CM_COMPLETED, CM_NO_LAUNCH, CM_ABORT, CM_TOP0, CM_TOP1, CM_TOP2, CM_AVG_LEN) = range(8)
 
 
 class StrColC(C.Structure):
@@ -112,6 +115,8 @@ SIGNATURES = {
     "pie_csv_rows_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     "pie_set_csv_chunk_rows": (C.c_int64, [C.c_int64]),
+    "pie_compute_metrics_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pie_compute_metrics_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64]),
     "pie_archive_payloads_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                            C.c_void_p, C.c_void_p]),
     "pie_archive_payloads_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64,

@@ -4,6 +4,7 @@ argument meaning, computed on the GPU through the C ABI.
     computeArchiveShowStats(show)                     public/app.js:3898-3953
     buildArchiveDailyGroups(shows)                    public/app.js:3401-3443
     getOrCreateGroupMetricSummary(group, metricKey)   public/app.js:3445-3502 (numeric part)
+    computeMetrics(show)                              public/app.js:5024-5047 (live show header)
 
 Shows are provider-normalised documents (dicts as `json.loads` returns them).  JS `null` is None.
 Display-only members of the reference objects (`displayDate`, `label`, `shortLabel`, `formatted`:
@@ -15,7 +16,7 @@ from typing import List, Optional
 
 from . import _lib
 from .columnar import pack_shows
-from .ops import archive_analytics, show_stats
+from .ops import archive_analytics, compute_metrics, show_stats
 
 PRIMARY_ISSUES = [  # public/app.js:1-13
     "Tracking lost", "Failed to launch", "Command delay", "RF link", "Battery", "Motor or prop",
@@ -161,3 +162,29 @@ def getOrCreateGroupMetricSummary(group: Optional[dict], metricKey: str) -> Opti
     summary["valueMap"] = {e["showId"]: e for e in show_values if e["showId"]}
     group["metrics"][metricKey] = summary
     return summary
+
+
+def computeMetricsMany(shows: List[Optional[dict]]) -> List[dict]:
+    """computeMetrics for every show in one launch."""
+    table = pack_shows(shows)
+    m = compute_metrics(table)
+    i32 = m.i32.cpu().tolist()
+    text = m.text.cpu().numpy()
+    issue = table.entry_cols["primary_issue"]
+    offs, data = issue.offsets.tolist(), bytes(issue.data.cpu().numpy())
+    out = []
+    for s in range(table.n_shows):
+        rows = [i32[_lib.CM_TOP0 + k][s] for k in range(3)]
+        out.append({
+            "successRate": i32[_lib.CM_SUCCESS_RATE][s],
+            "countCompleted": i32[_lib.CM_COMPLETED][s],
+            "countNoLaunch": i32[_lib.CM_NO_LAUNCH][s],
+            "countAbort": i32[_lib.CM_ABORT][s],
+            "avgDelay": bytes(text[s, : i32[_lib.CM_AVG_LEN][s]]).decode("ascii"),
+            "topIssues": [data[offs[e]:offs[e + 1]].decode("utf-8") for e in rows if e >= 0],
+        })
+    return out
+
+
+def computeMetrics(show: Optional[dict]) -> dict:
+    return computeMetricsMany([show])[0]

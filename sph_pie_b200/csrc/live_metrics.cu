@@ -1,0 +1,230 @@
+// Live show metrics on sm_100a.
+// Replaces computeMetrics(show) (reference public/app.js:5024-5047) for every show of a batch: the counts
+// of planned / completed / no-launch / abort entries, Math.round(completed / plannedYes * 100), the average
+// delay as (sum / n).toFixed(2), and the three most frequent primary issues of the entries that did not
+// complete.
+//
+// A thread per show.  The entries of a show are a run of consecutive rows, so the threads of a warp read
+// nearby rows of the same columns (the rows of ~32 consecutive shows: a few KB per column).  The issue
+// ranking needs no per-show table of distinct strings: an entry that is the FIRST carrier of its issue
+// counts the later carriers and enters a three-slot ranking; "first" and "later" are decided by comparing
+// strings — O(k^2) in the k entries of the show that carry an issue, k <= 21 by the reference's own rules
+// (one entry per operator, sqlProvider.js:434-457).
+#include "pie_device.cuh"
+#include "pie_kernels.h"
+#include "pie_numfmt.cuh"
+
+namespace pie {
+
+// Number::toString tables for the |x| >= 1e21 branch of toFixed (this translation unit's own copy: the
+// library is built without relocatable device code)
+static __device__ const uint64_t d_pow5_inv[PIE_RYU_POW5_INV_SPLIT_N][2] = PIE_RYU_POW5_INV_SPLIT_INIT;
+static __device__ const uint64_t d_pow5[PIE_RYU_POW5_SPLIT_N][2] = PIE_RYU_POW5_SPLIT_INIT;
+
+// Number.prototype.toFixed(2) (ECMA-262 21.1.3.3): n = the integer closest to |x| * 100 computed on the EXACT
+// binary value (ties: the larger n), printed as n/100 with two decimals; "-" iff x < 0 (so (-0.001).toFixed(2)
+// is "-0.00"); NaN, and |x| >= 1e21 (incl. +-Infinity) through Number::toString.
+__device__ int js_to_fixed2(double x, char* out) {
+  if (x != x) {
+    out[0] = 'N'; out[1] = 'a'; out[2] = 'N';
+    return 3;
+  }
+  const double ax = fabs(x);
+  if (ax >= 1e21) {
+    const RyuTables t{d_pow5_inv, d_pow5};
+    return js_number_to_string(x, out, t);
+  }
+  int o = 0;
+  if (x < 0) out[o++] = '-';
+  const uint64_t bits = (uint64_t)__double_as_longlong(ax);
+  const uint32_t expo = (uint32_t)(bits >> 52);
+  uint64_t m = bits & ((1ull << 52) - 1);
+  int e;  // ax = m * 2^e
+  if (expo == 0) {
+    e = -1074;
+  } else {
+    m |= 1ull << 52;
+    e = (int)expo - 1075;
+  }
+  // integer part as up to three 9-digit chunks (most significant first), two fraction digits
+  uint32_t chunk[3] = {0, 0, 0};
+  uint32_t frac;
+  if (e >= 0) {  // an integer below 1e21 < 2^70: m << e in three 32-bit limbs, divided by 10^9 twice
+    uint32_t limb[3];
+    const unsigned __int128 big = (unsigned __int128)m << e;
+    limb[0] = (uint32_t)big;
+    limb[1] = (uint32_t)(big >> 32);
+    limb[2] = (uint32_t)(big >> 64);
+    for (int c = 2; c >= 0; --c) {
+      uint64_t r = 0;
+      for (int i = 2; i >= 0; --i) {
+        const uint64_t cur = (r << 32) | limb[i];
+        limb[i] = (uint32_t)(cur / 1000000000ull);
+        r = cur % 1000000000ull;
+      }
+      chunk[c] = (uint32_t)r;
+    }
+    frac = 0;
+  } else {
+    const int k = -e;
+    uint64_t n = 0;  // round-half-up(m * 100 / 2^k); m * 100 < 2^60
+    if (k <= 62) n = (m * 100ull + (1ull << (k - 1))) >> k;
+    frac = (uint32_t)(n % 100ull);
+    const uint64_t ip = n / 100ull;  // < 2^53
+    chunk[2] = (uint32_t)(ip % 1000000000ull);
+    chunk[1] = (uint32_t)(ip / 1000000000ull);  // < 10^7
+  }
+  bool started = false;
+  for (int c = 0; c < 3; ++c) {
+    uint32_t v = chunk[c];
+    char d[9];
+    for (int i = 8; i >= 0; --i) {
+      d[i] = (char)('0' + v % 10u);
+      v /= 10u;
+    }
+    for (int i = 0; i < 9; ++i) {
+      if (!started && d[i] == '0' && !(c == 2 && i == 8)) continue;
+      started = true;
+      out[o++] = d[i];
+    }
+  }
+  out[o++] = '.';
+  out[o++] = (char)('0' + frac / 10u);
+  out[o++] = (char)('0' + frac % 10u);
+  return o;
+}
+
+// array index key (ECMA-262 6.1.7): the canonical decimal string of an integer in 0 .. 2^32 - 2.
+// OrdinaryOwnPropertyKeys lists such keys first, ascending, before the string keys in creation order.
+__device__ __forceinline__ bool array_index_key(const uint8_t* __restrict__ s, int n, uint32_t* value) {
+  if (n < 1 || n > 10 || (n > 1 && s[0] == '0')) return false;
+  uint64_t v = 0;
+  for (int i = 0; i < n; ++i) {
+    if (s[i] < '0' || s[i] > '9') return false;
+    v = v * 10 + (uint64_t)(s[i] - '0');
+  }
+  if (v > 4294967294ull) return false;
+  *value = (uint32_t)v;
+  return true;
+}
+
+__device__ __forceinline__ bool bytes_equal(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n) {
+  for (int i = 0; i < n; ++i)
+    if (a[i] != b[i]) return false;
+  return true;
+}
+
+struct Ranked {  // a distinct issue: where it was first seen, how often, and its place in Object.entries order
+  int first;
+  int count;
+  unsigned long long order;  // array-index keys: their value; other keys: 2^32 + creation position
+};
+// does a come before b after Object.entries(...).sort((a, b) => b[1] - a[1])?  (the sort is stable)
+__device__ __forceinline__ bool ranks_before(const Ranked& a, const Ranked& b) {
+  return a.count != b.count ? a.count > b.count : a.order < b.order;
+}
+
+__global__ void __launch_bounds__(128) compute_metrics_kernel(pie_archive_view v, int32_t* __restrict__ out,
+                                                              uint8_t* __restrict__ text, int64_t stride) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= v.n_shows) return;
+  const int e0 = v.entry_offsets[s], e1 = v.entry_offsets[s + 1];
+  int planned = 0, completed = 0, no_launch = 0, abort_ = 0, dn = 0;
+  double sum = 0.0;  // delays.reduce((a, b) => a + b, 0): left to right
+  // pass 1: counts; which of the first 64 entries carry an issue (status !== 'Completed' && primaryIssue)
+  unsigned long long carries = 0;
+  for (int e = e0; e < e1; ++e) {
+    {
+      const int b = v.planned.offsets[e], n = v.planned.offsets[e + 1] - b;
+      planned += equals_exact(v.planned.data + b, n, "Yes");
+    }
+    const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
+    const uint8_t* st = v.status.data + sb;
+    const bool comp = equals_exact(st, sn, "Completed");
+    completed += comp;
+    no_launch += equals_exact(st, sn, "No-launch");
+    abort_ += equals_exact(st, sn, "Abort");
+    if (v.delay_valid[e]) {  // typeof v === 'number'
+      sum = sum + v.delay_sec[e];
+      ++dn;
+    }
+    if (!comp && v.primary_issue.offsets[e + 1] > v.primary_issue.offsets[e] && e - e0 < 64) carries |= 1ull << (e - e0);
+  }
+  auto carries_issue = [&](int e) -> bool {
+    if (e - e0 < 64) return (carries >> (e - e0)) & 1ull;
+    const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
+    return !equals_exact(v.status.data + sb, sn, "Completed") && v.primary_issue.offsets[e + 1] > v.primary_issue.offsets[e];
+  };
+  // pass 2: the first carrier of every distinct issue counts the later ones and enters the ranking
+  Ranked top[3] = {{-1, 0, 0}, {-1, 0, 0}, {-1, 0, 0}};
+  unsigned int created = 0;  // string keys created so far
+  for (int e = e0; e < e1; ++e) {
+    if (!carries_issue(e)) continue;
+    const int b = v.primary_issue.offsets[e], n = v.primary_issue.offsets[e + 1] - b;
+    const uint8_t* p = v.primary_issue.data + b;
+    bool first = true;
+    for (int j = e0; j < e && first; ++j) {
+      if (!carries_issue(j)) continue;
+      const int jb = v.primary_issue.offsets[j], jn = v.primary_issue.offsets[j + 1] - jb;
+      if (jn == n && bytes_equal(v.primary_issue.data + jb, p, n)) first = false;
+    }
+    if (!first) continue;
+    Ranked r{e, 1, 0};
+    for (int j = e + 1; j < e1; ++j) {
+      if (!carries_issue(j)) continue;
+      const int jb = v.primary_issue.offsets[j], jn = v.primary_issue.offsets[j + 1] - jb;
+      r.count += (jn == n && bytes_equal(v.primary_issue.data + jb, p, n));
+    }
+    uint32_t index;
+    if (array_index_key(p, n, &index)) r.order = index;
+    else r.order = (1ull << 32) + created++;
+    // insert into the three-slot ranking
+    if (top[2].first < 0 || ranks_before(r, top[2])) {
+      top[2] = r;
+      if (top[1].first < 0 || ranks_before(top[2], top[1])) {
+        const Ranked t = top[1]; top[1] = top[2]; top[2] = t;
+        if (top[0].first < 0 || ranks_before(top[1], top[0])) {
+          const Ranked u = top[0]; top[0] = top[1]; top[1] = u;
+        }
+      }
+    }
+  }
+  int rate = 0;
+  if (planned) {
+    const double q = ((double)completed / (double)planned) * 100.0;  // two IEEE operations, as written in the source
+    const double r = floor(q);
+    rate = (int)((q - r >= 0.5) ? r + 1.0 : r);  // Math.round: ties toward +inf
+  }
+  out[PIE_CM_SUCCESS_RATE * stride + s] = rate;
+  out[PIE_CM_COMPLETED * stride + s] = completed;
+  out[PIE_CM_NO_LAUNCH * stride + s] = no_launch;
+  out[PIE_CM_ABORT * stride + s] = abort_;
+  out[PIE_CM_TOP0 * stride + s] = top[0].first;
+  out[PIE_CM_TOP1 * stride + s] = top[1].first;
+  out[PIE_CM_TOP2 * stride + s] = top[2].first;
+  __align__(16) char buf[PIE_CM_TEXT];
+#pragma unroll
+  for (int i = 0; i < PIE_CM_TEXT; ++i) buf[i] = 0;
+  int len;
+  if (dn) {
+    len = js_to_fixed2(sum / (double)dn, buf);
+  } else {
+    buf[0] = '0'; buf[1] = '.'; buf[2] = '0'; buf[3] = '0';
+    len = 4;
+  }
+  out[PIE_CM_AVG_LEN * stride + s] = len;
+  uint4* dst = reinterpret_cast<uint4*>(text + PIE_CM_TEXT * s);  // 32-byte slots of a 16-byte aligned buffer
+  const uint4* src = reinterpret_cast<const uint4*>(buf);
+  dst[0] = src[0];
+  dst[1] = src[1];
+}
+
+cudaError_t launch_compute_metrics(const pie_archive_view& v, int32_t* metrics_i32, uint8_t* avg_delay_text,
+                                   int64_t stride, cudaStream_t stream) {
+  if (v.n_shows == 0) return cudaSuccess;
+  compute_metrics_kernel<<<(unsigned)((v.n_shows + 127) / 128), 128, 0, stream>>>(v, metrics_i32, avg_delay_text, stride);
+  g_launches += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace pie

@@ -480,6 +480,72 @@ int pie_show_stats_host(const pie_archive_view* hv, int32_t* stats_i32, double* 
   return analytics_host_locked(hv, 0, stats_i32, stats_f64, stride, nullptr);
 }
 
+int pie_compute_metrics_dev(const pie_archive_view* v, int32_t* metrics_i32, uint8_t* avg_delay_text, int64_t stride,
+                            void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_view_common(v))) return rc;
+  if (!metrics_i32 || !avg_delay_text) return fail(PIE_ERR_INVALID_ARG, "output is NULL");
+  if (stride < v->n_shows) return fail(PIE_ERR_INVALID_ARG, "stride < n_shows");
+  if (!v->planned.offsets || !v->status.offsets || !v->primary_issue.offsets)
+    return fail(PIE_ERR_INVALID_ARG, "computeMetrics reads planned, status and primary_issue: one is NULL");
+  if (v->n_entries > 0 && (!v->delay_sec || !v->delay_valid)) return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
+  if (reinterpret_cast<uintptr_t>(avg_delay_text) & 15) return fail(PIE_ERR_INVALID_ARG, "avg_delay_text must be 16-byte aligned");
+  PIE_CUDA(pie::launch_compute_metrics(*v, metrics_i32, avg_delay_text, stride, (cudaStream_t)stream));
+  return PIE_OK;
+}
+
+int pie_compute_metrics_host(const pie_archive_view* hv, int32_t* metrics_i32, uint8_t* avg_delay_text, int64_t stride) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_view_common(hv))) return rc;
+  const int64_t S = hv->n_shows, E = hv->n_entries;
+  if (!metrics_i32 || !avg_delay_text) return fail(PIE_ERR_INVALID_ARG, "output is NULL");
+  if (stride < S) return fail(PIE_ERR_INVALID_ARG, "stride < n_shows");
+  if (S > 0 && (hv->entry_offsets[0] != 0 || hv->entry_offsets[S] != E))
+    return fail(PIE_ERR_INVALID_ARG, "entry_offsets must run from 0 to n_entries");
+  if (E > 0 && (!hv->delay_sec || !hv->delay_valid)) return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
+  uint64_t bytes = 0;
+  StrColPlan p_planned, p_status, p_issue;
+  if ((rc = plan_strcol(p_planned, &hv->planned, nullptr, E, &bytes, "planned"))) return rc;
+  if ((rc = plan_strcol(p_status, &hv->status, nullptr, E, &bytes, "status"))) return rc;
+  if ((rc = plan_strcol(p_issue, &hv->primary_issue, nullptr, E, &bytes, "primary_issue"))) return rc;
+  const int64_t Sc = S > 0 ? S : 1;
+  bytes += pad(4 * (uint64_t)(S + 1)) + pad(8 * (uint64_t)E) + pad((uint64_t)E);
+  bytes += pad(4ull * PIE_CM_COUNT * Sc) + pad((uint64_t)PIE_CM_TEXT * Sc);
+  if ((rc = g_arena.reserve(bytes))) return rc;
+  cudaStream_t st = g_arena.stream;
+  g_cur = &g_arena;
+  g_cur_stream = st;
+  uint64_t h2d = 0;
+  pie_archive_view dv;
+  memset(&dv, 0, sizeof(dv));
+  dv.n_shows = S;
+  dv.n_entries = E;
+  if ((rc = upload_array(hv->entry_offsets, S + 1, &dv.entry_offsets, &h2d))) return rc;
+  p_planned.dst = &dv.planned; p_status.dst = &dv.status; p_issue.dst = &dv.primary_issue;
+  if ((rc = upload_strcol(p_planned, &h2d))) return rc;
+  if ((rc = upload_strcol(p_status, &h2d))) return rc;
+  if ((rc = upload_strcol(p_issue, &h2d))) return rc;
+  if ((rc = upload_array(hv->delay_sec, E, &dv.delay_sec, &h2d))) return rc;
+  if ((rc = upload_array(hv->delay_valid, E, &dv.delay_valid, &h2d))) return rc;
+  int32_t* d_out = (int32_t*)g_arena.take(4ull * PIE_CM_COUNT * Sc);
+  uint8_t* d_text = (uint8_t*)g_arena.take((uint64_t)PIE_CM_TEXT * Sc);
+  PIE_CUDA(pie::launch_compute_metrics(dv, d_out, d_text, Sc, st));
+  uint64_t d2h = 0;
+  if (S > 0) {
+    PIE_CUDA(cudaMemcpy2DAsync(metrics_i32, 4 * (uint64_t)stride, d_out, 4 * (uint64_t)Sc, 4 * (uint64_t)S, PIE_CM_COUNT,
+                               cudaMemcpyDeviceToHost, st));
+    PIE_CUDA(cudaMemcpyAsync(avg_delay_text, d_text, (uint64_t)PIE_CM_TEXT * (uint64_t)S, cudaMemcpyDeviceToHost, st));
+    d2h = (4ull * PIE_CM_COUNT + PIE_CM_TEXT) * (uint64_t)S;
+  }
+  PIE_CUDA(cudaStreamSynchronize(st));
+  g_last_h2d = h2d;
+  g_last_d2h = d2h;
+  return PIE_OK;
+}
+
 uint64_t pie_csv_rows_scratch_bytes(int64_t n_entries) { return pie::csv_scratch_bytes(n_entries); }
 
 static int export_rows_dev(RowFormat format, const pie_archive_view* v, int64_t* row_offsets, uint8_t* out_data,

@@ -32,6 +32,10 @@ cudaError_t launch_payload_rows(const pie_archive_view& dev_view, int64_t* row_o
 int csv_set_force_slow(int on);
 cudaError_t csv_read_slow_tiles(const void* scratch, int64_t n_entries, unsigned int* out, cudaStream_t stream);
 
+// live_metrics.cu: computeMetrics(show) per show; metrics_i32 is int32[PIE_CM_COUNT][stride], text 32 bytes per show
+cudaError_t launch_compute_metrics(const pie_archive_view& dev_view, int32_t* metrics_i32, uint8_t* avg_delay_text,
+                                   int64_t stride, cudaStream_t stream);
+
 // archive_daily.cu
 uint64_t daily_scratch_bytes(int64_t n_shows);
 cudaError_t launch_daily_summary(const pie_archive_view& dev_view, const int32_t* stats_i32,

@@ -243,3 +243,39 @@ def archive_payloads(table: ArchiveTable) -> CsvRows:
     """JSON.stringify(buildArchiveEntryPayload(show, entry)) for every entry of every show (one row each,
     reference webhookDispatcher.js:315-330 and :527-540)."""
     return _rows(table, archive_payloads_dev, "pie_archive_payloads_host")
+
+
+@dataclass
+class LiveMetrics:
+    """computeMetrics(show) for every show (reference public/app.js:5024-5047): int32 planes
+    [PIE_CM_COUNT][S] (success rate, status counts, topIssues as entry rows, length of avgDelay) and the
+    avgDelay text, 32 bytes per show."""
+    i32: torch.Tensor   # [PIE_CM_COUNT, S]
+    text: torch.Tensor  # uint8 [S, PIE_CM_TEXT]
+
+    def avg_delay(self, s: int) -> str:
+        n = int(self.i32[_lib.CM_AVG_LEN][s])
+        return bytes(self.text[s, :n].cpu().numpy()).decode("ascii")
+
+
+def compute_metrics_dev(table: ArchiveTable, i32: torch.Tensor, text: torch.Tensor) -> None:
+    """Enqueue the live-metrics kernel on torch's current stream (no sync)."""
+    _lib.ensure_init()
+    view = table.view()
+    _lib.check(_lib.load().pie_compute_metrics_dev(C.byref(view), i32.data_ptr(), text.data_ptr(), i32.shape[1],
+                                                   _stream_ptr()))
+
+
+def compute_metrics(table: ArchiveTable) -> LiveMetrics:
+    _lib.ensure_init()
+    S = table.n_shows
+    Sc = max(S, 1)
+    dev = table.device if table.is_cuda else "cpu"
+    i32 = torch.empty((_lib.PIE_CM_COUNT, Sc), dtype=torch.int32, device=dev)
+    text = torch.empty((Sc, _lib.PIE_CM_TEXT), dtype=torch.uint8, device=dev)
+    if table.is_cuda:
+        compute_metrics_dev(table, i32, text)
+    else:
+        view = table.view()
+        _lib.check(_lib.load().pie_compute_metrics_host(C.byref(view), i32.data_ptr(), text.data_ptr(), Sc))
+    return LiveMetrics(i32[:, :S], text[:S])
