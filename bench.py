@@ -314,6 +314,21 @@ def main():
                                                       "primary_issue", "sub_issue")])
     payload_bytes = sum(c.nbytes() for c in payload_cols) + 4 * (S + 1) + payload_total + 8 * (E + 1)
     del pbufs, psizing
+    # ... and computeMetrics(show) for every show (live show header)
+    m_i32 = torch.empty((_lib.PIE_CM_COUNT, S), dtype=torch.int32, device=dev)
+    m_text = torch.empty((S, _lib.PIE_CM_TEXT), dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        ops.compute_metrics_dev(table, m_i32, m_text)
+    torch.cuda.synchronize()
+    p0.record()
+    for _ in range(n_payload_runs):
+        ops.compute_metrics_dev(table, m_i32, m_text)
+    p1.record()
+    torch.cuda.synchronize()
+    metrics_ms = p0.elapsed_time(p1) / n_payload_runs
+    metrics_bytes = (sum(table.entry_cols[k].nbytes() for k in ("planned", "status", "primary_issue")) + 9 * E
+                     + 4 * (S + 1) + (4 * _lib.PIE_CM_COUNT + _lib.PIE_CM_TEXT) * S)
+    del m_i32, m_text
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     import ctypes as C
@@ -406,6 +421,10 @@ def main():
                     "ms_per_launch": payload_ms, "algorithmic_bytes": payload_bytes, "json_bytes_out": payload_total,
                     "achieved_gbs": gbs(payload_bytes, payload_ms), "frac": gbs(payload_bytes, payload_ms) / peak,
                     "entries_per_s": E / (payload_ms * 1e-3)},
+                "computeMetrics per show (compute_metrics_kernel, not part of the step)": {
+                    "ms_per_launch": metrics_ms, "algorithmic_bytes": metrics_bytes,
+                    "achieved_gbs": gbs(metrics_bytes, metrics_ms), "frac": gbs(metrics_bytes, metrics_ms) / peak,
+                    "entries_per_s": E / (metrics_ms * 1e-3)},
             },
         },
     }
