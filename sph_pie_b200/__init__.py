@@ -8,11 +8,16 @@ package is the host-side mirror of the reference's functions.  There is no CPU f
 from . import _lib
 from ._lib import JsRangeError, PieError, UnsupportedDateError
 from .archive import (ALL_METRIC_KEYS, ARCHIVE_METRIC_KEYS, PRIMARY_ISSUES, buildArchiveDailyGroups,
-                      computeArchiveShowStats, computeArchiveShowStatsMany, getOrCreateGroupMetricSummary)
+                      computeArchiveShowStats, computeArchiveShowStatsMany, computeMetrics, computeMetricsMany,
+                      getOrCreateGroupMetricSummary)
 from .columnar import ArchiveTable, StrCol, StrListCol, pack_shows
+from .webhook import (EXPORT_COLUMNS, archiveEntryPayloadBodies, archiveEntryPayloadBodiesMany,
+                      buildArchiveEntryPayload, buildCsvRows, buildCsvRowsMany, buildMessagePayload, exportShowAsCsv)
 
 __all__ = [
     "ALL_METRIC_KEYS", "ARCHIVE_METRIC_KEYS", "PRIMARY_ISSUES", "ArchiveTable", "StrCol", "StrListCol",
     "JsRangeError", "PieError", "UnsupportedDateError", "buildArchiveDailyGroups", "computeArchiveShowStats",
-    "computeArchiveShowStatsMany", "getOrCreateGroupMetricSummary", "pack_shows",
+    "computeArchiveShowStatsMany", "getOrCreateGroupMetricSummary", "pack_shows", "computeMetrics",
+    "computeMetricsMany", "EXPORT_COLUMNS", "archiveEntryPayloadBodies", "archiveEntryPayloadBodiesMany",
+    "buildArchiveEntryPayload", "buildCsvRows", "buildCsvRowsMany", "buildMessagePayload", "exportShowAsCsv",
 ]
