@@ -444,11 +444,21 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                : "memory");
 }
 constexpr int kBarWorkers = 1, kBarTotalReady = 2, kBarBaseReady = 3;  // named barriers (0 = __syncthreads)
+constexpr int kBarItemsReady = 4, kBarFillsDone = 5;                    // workers <-> number warps
 __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync %0, %1;" ::"n"(kBarWorkers), "n"(kWorkers) : "memory"); }
 template <int kBar>
 __device__ __forceinline__ void bar_arrive_workers_and_lookback() {
   __threadfence_block();
   asm volatile("bar.arrive %0, %1;" ::"n"(kBar), "n"(kWorkers + 32) : "memory");
+}
+template <int kBar, int kCount>
+__device__ __forceinline__ void bar_arrive_n() {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"n"(kBar), "n"(kCount) : "memory");
+}
+template <int kBar, int kCount>
+__device__ __forceinline__ void bar_sync_n() {
+  asm volatile("bar.sync %0, %1;" ::"n"(kBar), "n"(kCount) : "memory");
 }
 template <int kBar>
 __device__ __forceinline__ void bar_sync_workers_and_lookback() {
@@ -500,6 +510,7 @@ struct CsvSmem {
   long long cur_tile[2];                        // workers -> look-back warp
   uint32_t bump;                                // next free byte of the current stage's bump area
   uint32_t overflow;                            // the bump area ran out
+  uint32_t fill_skip;                           // the tile's queued cells need no bytes (slow path)
   uint32_t done;
   uint8_t num_len[2][kRows];                    // by stage
 };
@@ -1112,6 +1123,20 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       const uint32_t s = it & 1u, ph = (it >> 1) & 1u;
       uint8_t* stage = s_dyn + kSmemOffStage + s * kStageStride;
       const StageInfo& info = sm.info[s];
+      if (it > 0) {
+        // The cells the workers queued for the PREVIOUS tile (csvEscape / join / JSON escapes) get their
+        // bytes here, one item per thread, the two kinds from opposite ends — while the workers add up
+        // lengths, publish and flush; they need the bytes only when they write.
+        bar_sync_n<kBarItemsReady, kWorkers + 32 * kNumberWarps>();
+        if (!sm.fill_skip && !sm.overflow) {
+          uint8_t* prev = s_dyn + kSmemOffStage + (s ^ 1u) * kStageStride;
+          const uint32_t n_word = sm.n_word_items, n_quote = sm.n_quote_items;
+          for (uint32_t i = (uint32_t)row; i < n_word; i += 32 * kNumberWarps) fill_item<kJson>(prev, sm.word_items[i], false);
+          for (uint32_t i = 32 * kNumberWarps - 1 - (uint32_t)row; i < n_quote; i += 32 * kNumberWarps)
+            fill_item<kJson>(prev, sm.quote_items[i], true);
+        }
+        bar_arrive_n<kBarFillsDone, kWorkers + 32 * kNumberWarps>();
+      }
       mbar_wait_relaxed(smem_u32(&sm.full[s]), ph);
       if (info.tile < 0) return;
       double value = 0.0;
@@ -1237,6 +1262,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     const bool have = r < rows;
     bool slow = info.slow != 0;  // uniform
     bool published = false;
+    bool items_signalled = false;
 
     if (!slow) {
       if (tid == 0) {
@@ -1244,6 +1270,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
         sm.overflow = 0;
         sm.n_word_items = 0;
         sm.n_quote_items = 0;
+        sm.fill_skip = 0;
       }
       workers_sync();  // also: every worker has left the previous tile's write phase (cell table)
       PIE_PHASE(1);
@@ -1335,13 +1362,9 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       PIE_PHASE(3);  // this thread's entry-level cells
       workers_sync();
       PIE_PHASE(4);  // waiting for the other warps' cells
-      // ---- cells 2. the queued cells get their bytes (one item per thread; the two kinds from opposite
-      // ends of the CTA); rows pick up their show's cells; bytes per group of 6 consecutive columns
-      if (!sm.overflow) {
-        const uint32_t n_word = sm.n_word_items, n_quote = sm.n_quote_items;
-        for (uint32_t i = tid; i < n_word; i += kWorkers) fill_item<kJson>(stage, sm.word_items[i], false);
-        for (uint32_t i = kWorkers - 1 - tid; i < n_quote; i += kWorkers) fill_item<kJson>(stage, sm.quote_items[i], true);
-      }
+      // ---- lengths.  (The queued cells get their bytes from the number warps meanwhile.)
+      bar_arrive_n<kBarItemsReady, kWorkers + 32 * kNumberWarps>();  // the number warps fill the queued cells
+      items_signalled = true;
       PIE_PHASE(9);
       slow = sm.overflow != 0;  // the bump area or a fill queue ran out (uniform: written before the barrier)
       if (!slow) {
@@ -1375,7 +1398,13 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       // ---- slow path (uniform for the CTA).  If the fast path already published this tile's total, the
       // measure below recomputes the same row lengths; only the quote masks are new.
       finish_pending();
-      if (tid == 0) atomicAdd(sc.slow_tiles, 1u);
+      if (tid == 0) {
+        atomicAdd(sc.slow_tiles, 1u);
+        sm.fill_skip = 1;
+      }
+      // the number warps go through "items ready / fills done" once per tile whatever path it takes
+      if (!items_signalled) bar_arrive_n<kBarItemsReady, kWorkers + 32 * kNumberWarps>();
+      bar_sync_n<kBarFillsDone, kWorkers + 32 * kNumberWarps>();
       workers_sync();
       slow_measure<kJson>(v, tab, sc, sm, s_num, qmask, s, e0, rows);
       workers_sync();
@@ -1396,6 +1425,8 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     bar_arrive_workers_and_lookback<kBarTotalReady>();  // this tile's look-back starts now ...
     finish_pending();                                   // ... while the previous tile leaves s_out
     PIE_PHASE(6);  // wait for the previous tile's offset + its flush
+    bar_sync_n<kBarFillsDone, kWorkers + 32 * kNumberWarps>();  // the queued cells have their bytes
+    PIE_PHASE(10);
     if (write) {
       // ---- write.  Thread (r, g) streams its 6 consecutive cells into the shared output tile.  Lanes of
       // a warp = 32 consecutive rows on the SAME column at every step, so cell lengths (and with them the
