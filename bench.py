@@ -46,6 +46,14 @@ def parse_args():
     return ap.parse_args()
 
 
+def note(msg: str) -> None:
+    """Progress line on stderr (never stdout: stdout carries exactly one JSON line)."""
+    print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,9 +262,11 @@ def main():
         ops.daily_summary_dev(table, bufs, args.tz)
         ops.csv_rows_dev(table, cbufs)
 
+    note(f"table resident: {S} shows, {E} entries; warm-up")
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
+    note("warm-up done; timed steps")
     assert int(bufs.status[0]) == 0 and int(cbufs.total) == csv_total
     n_groups = int(bufs.n_groups)
 
@@ -292,6 +302,7 @@ def main():
     daily_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
     csv_ms = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
 
+    note(f"timed steps done: {total_ms / args.steps:.3f} ms per step")
     # ---- outside the step: archive entry payloads (JSON Lines) on the same resident table — the next row of
     # the scope table (DESIGN.md §0 f), timed alone with CUDA events on the launch stream
     psizing = ops.CsvBuffers(E, 0, dev)
@@ -330,6 +341,7 @@ def main():
                      + 4 * (S + 1) + (4 * _lib.PIE_CM_COUNT + _lib.PIE_CM_TEXT) * S)
     del m_i32, m_text
 
+    note("payload rows and live metrics timed; end-to-end leg (host buffers)")
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     import ctypes as C
 
@@ -357,6 +369,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
+    note(f"end-to-end leg done: {e2e_s / e2e_steps * 1e3:.1f} ms per step")
     if world > 1:
         import torch.distributed as dist
 

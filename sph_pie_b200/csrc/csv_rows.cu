@@ -406,21 +406,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "PIE_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra PIE_DONE;\n"
-      "bra PIE_WAIT;\n"
-      "PIE_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-// Same for the warps that run AHEAD of the workers (producer, number warps): their waits are long and not
-// on the critical path, so they sleep between polls instead of spinning on the issue slots.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -434,8 +419,38 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Watchdog for the kernel's spin waits (mbarriers, look-back): the protocol below cannot deadlock by
+// construction, but a wait that outlives kWatchdogNs means it did — trap, so that the host sees a launch
+// failure instead of a kernel that never returns.
+constexpr unsigned long long kWatchdogNs = 10ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct Watchdog {
+  unsigned long long start = 0;
+  uint32_t polls = 0;
+  __device__ __forceinline__ void poll() {
+    if ((++polls & 0x3FFu) != 0) return;
+    const unsigned long long now = global_ns();
+    if (start == 0) start = now;
+    else if (now - start > kWatchdogNs) __trap();
+  }
+};
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  Watchdog dog;
+  while (!mbar_try_wait(bar, parity)) dog.poll();
+}
+// Same for the warps that run AHEAD of the workers (producer, number warps): their waits are long and not
+// on the critical path, so they sleep between polls instead of spinning on the issue slots.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(400);
+  Watchdog dog;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(400);
+    dog.polls += 0x3Fu;  // a poll here stands for ~0.5 us: check the clock every 16 of them
+    dog.poll();
+  }
 }
 // global -> shared, 16-byte aligned on both sides, bytes a multiple of 16; completion on the mbarrier
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -1005,12 +1020,15 @@ __device__ __forceinline__ void look_back(const CsvScratch& sc, CsvSmem& sm, uin
     const int64_t j = idx - lane;
     unsigned long long st;
     unsigned ns = 32;
+    Watchdog dog;
     for (;;) {
       st = 2ull << kStatusShift;  // before tile 0: an empty prefix
       if (j >= 0) st = state[j];
       if (!__any_sync(0xFFFFFFFFu, (st >> kStatusShift) == 0)) break;
       __nanosleep(ns);  // the tiles we wait for are still measuring: do not hammer L2 / the issue slots
       if (ns < 512) ns <<= 1;
+      dog.polls += 0x3Fu;
+      dog.poll();
     }
     const uint32_t is_prefix = __ballot_sync(0xFFFFFFFFu, (st >> kStatusShift) == 2);
     const int stop = is_prefix ? (__ffs(is_prefix) - 1) : 32;  // nearest tile that already knows its prefix
