@@ -3,8 +3,11 @@
 // twin public/app.js:5582-5612, :6025-6034) mapped over every entry of every show — what
 // dispatchShowEvent puts in csv.rows (:571) and exportShowAsCsv joins with '\n' (public/app.js:5567).
 //
+// The same kernel, with another row format, writes JSON.stringify(buildArchiveEntryPayload(show, entry)) per
+// entry (:315-330, the bodies dispatchShowEvent('show.archived') posts, :520-540): see RowTable below.
+//
 // Output = one string column: row i is out_data[row_offsets[i] .. row_offsets[i+1]-1) and is followed
-// by one '\n', so a show's CSV body is a single contiguous slice.
+// by one '\n', so a show's CSV body is a single contiguous slice (and the payload output is JSON Lines).
 //
 // ONE pass over the inputs, by a PERSISTENT, warp-specialised kernel.  A CTA loops over
 // tiles of kRows consecutive entries (claimed from a counter, so tile ids start in order):

@@ -131,24 +131,35 @@ __global__ void __launch_bounds__(128) compute_metrics_kernel(pie_archive_view v
   const int e0 = v.entry_offsets[s], e1 = v.entry_offsets[s + 1];
   int planned = 0, completed = 0, no_launch = 0, abort_ = 0, dn = 0;
   double sum = 0.0;  // delays.reduce((a, b) => a + b, 0): left to right
-  // pass 1: counts; which of the first 64 entries carry an issue (status !== 'Completed' && primaryIssue)
+  // pass 1: counts; which of the first 64 entries carry an issue (status !== 'Completed' && primaryIssue).
+  // The strings are compared as aligned 32-bit words (exact match: all mask bytes 0xFF); there is no store in
+  // the loop, so the unrolled iterations' loads overlap.
   unsigned long long carries = 0;
+#pragma unroll 4
   for (int e = e0; e < e1; ++e) {
-    {
-      const int b = v.planned.offsets[e], n = v.planned.offsets[e + 1] - b;
-      planned += equals_exact(v.planned.data + b, n, "Yes");
-    }
+    const int pb = v.planned.offsets[e], pn = v.planned.offsets[e + 1] - pb;
     const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
-    const uint8_t* st = v.status.data + sb;
-    const bool comp = equals_exact(st, sn, "Completed");
+    const int in = v.primary_issue.offsets[e + 1] - v.primary_issue.offsets[e];
+    const bool dvalid = v.delay_valid[e] != 0;
+    const double d = v.delay_sec[e];
+    uint32_t xp[1], xs[3];
+    fetch_words_raw<1>(v.planned.data + pb, pn == 3 ? 3 : 0, xp);
+    fetch_words_raw<3>(v.status.data + sb, (sn == 9 || sn == 5) ? sn : 0, xs);
+    planned += (pn == 3 && (xp[0] & 0xFFFFFFu) == lit_word("Yes", 0));
+    const bool nine = sn == 9, five = sn == 5;
+    const bool comp = nine && xs[0] == lit_word("Completed", 0) && xs[1] == lit_word("Completed", 1) &&
+                      (xs[2] & 0xFFu) == lit_word("Completed", 2);
+    const bool nol = nine && xs[0] == lit_word("No-launch", 0) && xs[1] == lit_word("No-launch", 1) &&
+                     (xs[2] & 0xFFu) == lit_word("No-launch", 2);
+    const bool abo = five && xs[0] == lit_word("Abort", 0) && (xs[1] & 0xFFu) == lit_word("Abort", 1);
     completed += comp;
-    no_launch += equals_exact(st, sn, "No-launch");
-    abort_ += equals_exact(st, sn, "Abort");
-    if (v.delay_valid[e]) {  // typeof v === 'number'
-      sum = sum + v.delay_sec[e];
+    no_launch += nol;
+    abort_ += abo;
+    if (dvalid) {  // typeof v === 'number'
+      sum = sum + d;
       ++dn;
     }
-    if (!comp && v.primary_issue.offsets[e + 1] > v.primary_issue.offsets[e] && e - e0 < 64) carries |= 1ull << (e - e0);
+    if (!comp && in > 0 && e - e0 < 64) carries |= 1ull << (e - e0);
   }
   auto carries_issue = [&](int e) -> bool {
     if (e - e0 < 64) return (carries >> (e - e0)) & 1ull;
