@@ -13,8 +13,8 @@ A step = one pass of the path over one batch:
              day (public/app.js:3401-3502, :3898-3953)
   export     buildCsvRow(buildTableRow(show, entry)) for every entry (server/webhookDispatcher.js:276-342)
   value : entries/s, table resident in HBM, kernels only (CUDA events on the launch stream)
-  e2e   : entries/s through pie_archive_analytics_host + pie_csv_rows_host (HOST buffers in, HOST
-          results out, H2D + kernels + D2H inside the timed region)
+  e2e   : entries/s through pie_archive_step_host (HOST buffers in, HOST results out, H2D + kernels + D2H inside
+          the timed region)
 """
 from __future__ import annotations
 
@@ -352,12 +352,15 @@ def main():
     hview = host.view()
     h_total = C.c_uint64(0)
 
+    h_dout = hout.daily_out()
+
     def e2e_step():
-        ops.archive_analytics(host, args.tz, hout)  # returns after its D2H copies have completed
-        a = _lib.last_transfer_bytes()
-        _lib.check(lib.pie_csv_rows_host(C.byref(hview), h_off.data_ptr(), h_csv.data_ptr(), csv_total, C.byref(h_total)))
-        b = _lib.last_transfer_bytes()
-        return a[0] + b[0], a[1] + b[1]
+        # one call: show statistics + daily summaries + CSV rows on one pipelined upload; it returns after every
+        # device->host copy has completed
+        _lib.check(lib.pie_archive_step_host(C.byref(hview), args.tz, hout.stats_i32.data_ptr(), hout.stats_f64.data_ptr(),
+                                             hout.S, C.byref(h_dout), h_off.data_ptr(), h_csv.data_ptr(), csv_total,
+                                             C.byref(h_total)))
+        return _lib.last_transfer_bytes()
 
     for _ in range(2):
         h2d, d2h = e2e_step()
@@ -415,7 +418,7 @@ def main():
         "dtype": "u8/int32/f64", "data": "synthetic",
         "config": workload_config(args, S, E),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "pie_archive_analytics_host + pie_csv_rows_host (pinned host buffers in and out)"},
+                "steps": e2e_steps, "api": "pie_archive_step_host (statistics + daily summaries + CSV rows; pinned host buffers in and out)"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {  # the dominant kernel of the step: export_rows_kernel<csv>
@@ -478,9 +481,12 @@ def reference_scale(args, dev):
     data = torch.empty(cpu.csv_data.numel(), dtype=torch.uint8, pin_memory=True)
     view, total, lib = pinned.view(), C.c_uint64(0), _lib.load()
 
+    dout = hout.daily_out()
+
     def gpu_step():
-        ops.archive_analytics(pinned, args.tz, hout)
-        _lib.check(lib.pie_csv_rows_host(C.byref(view), off.data_ptr(), data.data_ptr(), data.numel(), C.byref(total)))
+        _lib.check(lib.pie_archive_step_host(C.byref(view), args.tz, hout.stats_i32.data_ptr(), hout.stats_f64.data_ptr(),
+                                             hout.S, C.byref(dout), off.data_ptr(), data.data_ptr(), data.numel(),
+                                             C.byref(total)))
 
     for _ in range(5):
         gpu_step()

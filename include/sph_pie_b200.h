@@ -197,6 +197,16 @@ int pie_csv_rows_host(const pie_archive_view* host_view, int64_t* row_offsets, u
  * previous value; rows <= 0 only queries.  Default 2^20. */
 int64_t pie_set_csv_chunk_rows(int64_t rows);
 
+/* ---- one call for the archive workspace: pie_archive_analytics_host + pie_csv_rows_host on ONE upload.
+ * The rows' pipeline already brings status, launched, primaryIssue and delaySec to the device chunk by chunk, so the
+ * show statistics are computed per chunk on the resident columns, and the daily groups / summaries once at the end;
+ * uploads, kernels and downloads of consecutive chunks overlap (PCIe is full duplex).  Arguments and results are
+ * those of the two calls it replaces; stats_i32 / stats_f64 may both be NULL.  Errors: what either call returns
+ * (a show's PIE_ERR_RANGE / PIE_ERR_UNSUPPORTED_DATE takes precedence over PIE_ERR_CAPACITY). */
+int pie_archive_step_host(const pie_archive_view* host_view, int32_t tz_offset_minutes, int32_t* stats_i32,
+                          double* stats_f64, int64_t stats_stride, const pie_daily_out* host_out,
+                          int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity, uint64_t* total_bytes);
+
 /* ---- live show metrics: replaces computeMetrics(show) (public/app.js:5024-5047), the header strip of a show
  * (success rate, status counts, average delay, top issues), for every show of the batch.
  * metrics_i32 is int32[PIE_CM_COUNT][stride], plane-major like the statistics tables:

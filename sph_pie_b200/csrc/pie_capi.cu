@@ -333,6 +333,63 @@ int pie_daily_summary_dev(const pie_archive_view* v, const int32_t* stats_i32, c
   return PIE_OK;
 }
 
+// Device-side pie_daily_out carved from an arena, and its way back to the caller's host arrays.
+static void* alloc_daily_out(Arena& a, int64_t S, int64_t Sc, pie_daily_out* dout) {
+  memset(dout, 0, sizeof(*dout));
+  dout->stride = Sc;
+  dout->show_day_start = (int64_t*)a.take(8ull * Sc);
+  dout->group_day_start = (int64_t*)a.take(8ull * Sc);
+  dout->show_order = (int32_t*)a.take(4ull * Sc);
+  dout->group_offsets = (int32_t*)a.take(4ull * (Sc + 1));
+  dout->summary_f64 = (double*)a.take(8ull * PIE_DF_COUNT * PIE_N_METRICS * Sc);
+  dout->summary_count = (int32_t*)a.take(4ull * PIE_N_METRICS * Sc);
+  dout->n_groups = (int64_t*)a.take(16);
+  dout->status = (int32_t*)a.take(16);
+  return a.take(pie::daily_scratch_bytes(S));
+}
+static uint64_t daily_out_bytes(int64_t S, int64_t Sc) {
+  return pad(pie::daily_scratch_bytes(S)) + pad(8ull * Sc) * 2 + pad(4ull * Sc) + pad(4ull * (Sc + 1)) +
+         pad(8ull * PIE_DF_COUNT * PIE_N_METRICS * Sc) + pad(4ull * PIE_N_METRICS * Sc) + pad(64);
+}
+// waits for the kernels on `st`, raises what a show raised, then copies the groups out
+static int download_daily(const pie_daily_out* hout, const pie_daily_out& dout, int64_t S, int64_t Sc, cudaStream_t st,
+                          uint64_t* d2h) {
+  PIE_CUDA(cudaMemcpyAsync(hout->n_groups, dout.n_groups, 8, cudaMemcpyDeviceToHost, st));
+  PIE_CUDA(cudaMemcpyAsync(hout->status, dout.status, 8, cudaMemcpyDeviceToHost, st));
+  PIE_CUDA(cudaStreamSynchronize(st));
+  *d2h += 16;
+  if (hout->status[0] != 0) {
+    const int code = hout->status[0];
+    return fail(code, code == PIE_ERR_RANGE ? "RangeError: Invalid time value (show %d)"
+                                            : "show %d: date/time is not an ECMA-262 date-time string",
+                hout->status[1]);
+  }
+  const int64_t G = *hout->n_groups;
+  if (S > 0) {
+    PIE_CUDA(cudaMemcpyAsync(hout->show_day_start, dout.show_day_start, 8 * (uint64_t)S, cudaMemcpyDeviceToHost, st));
+    PIE_CUDA(cudaMemcpyAsync(hout->show_order, dout.show_order, 4 * (uint64_t)S, cudaMemcpyDeviceToHost, st));
+    *d2h += 12 * (uint64_t)S;
+  }
+  PIE_CUDA(cudaMemcpyAsync(hout->group_offsets, dout.group_offsets, 4 * (uint64_t)(G + 1), cudaMemcpyDeviceToHost, st));
+  *d2h += 4 * (uint64_t)(G + 1);
+  if (G > 0) {
+    PIE_CUDA(cudaMemcpyAsync(hout->group_day_start, dout.group_day_start, 8 * (uint64_t)G, cudaMemcpyDeviceToHost, st));
+    PIE_CUDA(cudaMemcpy2DAsync(hout->summary_f64, 8 * (uint64_t)hout->stride, dout.summary_f64, 8 * (uint64_t)Sc,
+                               8 * (uint64_t)G, PIE_DF_COUNT * PIE_N_METRICS, cudaMemcpyDeviceToHost, st));
+    PIE_CUDA(cudaMemcpy2DAsync(hout->summary_count, 4 * (uint64_t)hout->stride, dout.summary_count, 4 * (uint64_t)Sc,
+                               4 * (uint64_t)G, PIE_N_METRICS, cudaMemcpyDeviceToHost, st));
+    *d2h += (8ull + 8ull * PIE_DF_COUNT * PIE_N_METRICS + 4ull * PIE_N_METRICS) * (uint64_t)G;
+  }
+  return PIE_OK;
+}
+static int check_daily_out(const pie_daily_out* hout, int64_t S) {
+  if (hout->stride < S) return fail(PIE_ERR_INVALID_ARG, "pie_daily_out.stride < n_shows");
+  if (!hout->show_day_start || !hout->show_order || !hout->group_day_start || !hout->group_offsets ||
+      !hout->summary_f64 || !hout->summary_count || !hout->n_groups || !hout->status)
+    return fail(PIE_ERR_INVALID_ARG, "pie_daily_out has a NULL array");
+  return PIE_OK;
+}
+
 static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_minutes, int32_t* stats_i32,
                                  double* stats_f64, int64_t stats_stride, const pie_daily_out* hout) {
   int rc = ensure_init();
@@ -349,10 +406,7 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   if (S > 0 && hv->entry_offsets[0] != 0) return fail(PIE_ERR_INVALID_ARG, "entry_offsets[0] must be 0");
   if (E > 0 && (!hv->delay_sec || !hv->delay_valid)) return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
   if (want_daily) {
-    if (hout->stride < S) return fail(PIE_ERR_INVALID_ARG, "pie_daily_out.stride < n_shows");
-    if (!hout->show_day_start || !hout->show_order || !hout->group_day_start || !hout->group_offsets ||
-        !hout->summary_f64 || !hout->summary_count || !hout->n_groups || !hout->status)
-      return fail(PIE_ERR_INVALID_ARG, "pie_daily_out has a NULL array");
+    if ((rc = check_daily_out(hout, S))) return rc;
     if (S > 0 && !hv->created_at) return fail(PIE_ERR_INVALID_ARG, "created_at is NULL");
   }
 
@@ -371,9 +425,7 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   bytes += pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc);                  // stats planes
   if (want_daily) {
     bytes += 2 * pad(8 * (uint64_t)Sc) + pad(8 * (uint64_t)E);                             // created, archived, entry_ts
-    bytes += pad(pie::daily_scratch_bytes(S));
-    bytes += pad(8ull * Sc) * 2 + pad(4ull * Sc) + pad(4ull * (Sc + 1));                    // day_start, group_day, order, goffs
-    bytes += pad(8ull * PIE_DF_COUNT * PIE_N_METRICS * Sc) + pad(4ull * PIE_N_METRICS * Sc) + pad(64);
+    bytes += daily_out_bytes(S, Sc);
   }
   if ((rc = g_arena.reserve(bytes))) return rc;
   cudaStream_t st = g_arena.stream;
@@ -409,16 +461,7 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   pie_daily_out dout;
   memset(&dout, 0, sizeof(dout));
   if (want_daily) {
-    dout.stride = Sc;
-    dout.show_day_start = (int64_t*)g_arena.take(8ull * Sc);
-    dout.group_day_start = (int64_t*)g_arena.take(8ull * Sc);
-    dout.show_order = (int32_t*)g_arena.take(4ull * Sc);
-    dout.group_offsets = (int32_t*)g_arena.take(4ull * (Sc + 1));
-    dout.summary_f64 = (double*)g_arena.take(8ull * PIE_DF_COUNT * PIE_N_METRICS * Sc);
-    dout.summary_count = (int32_t*)g_arena.take(4ull * PIE_N_METRICS * Sc);
-    dout.n_groups = (int64_t*)g_arena.take(16);
-    dout.status = (int32_t*)g_arena.take(16);
-    void* dscratch = g_arena.take(pie::daily_scratch_bytes(S));
+    void* dscratch = alloc_daily_out(g_arena, S, Sc, &dout);
     PIE_CUDA(pie::launch_daily_summary(dv, d_si, d_sf, Sc, tz_offset_minutes, dout, dscratch, g_sm_count, st));
   }
 
@@ -431,32 +474,10 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
     d2h += (4ull * PIE_SI_COUNT + 8ull * PIE_SF_COUNT) * (uint64_t)S;
   }
   if (want_daily) {
-    PIE_CUDA(cudaMemcpyAsync(hout->n_groups, dout.n_groups, 8, cudaMemcpyDeviceToHost, st));
-    PIE_CUDA(cudaMemcpyAsync(hout->status, dout.status, 8, cudaMemcpyDeviceToHost, st));
-    PIE_CUDA(cudaStreamSynchronize(st));
-    d2h += 16;
-    if (hout->status[0] != 0) {
-      g_last_h2d = h2d; g_last_d2h = d2h;
-      const int code = hout->status[0];
-      return fail(code, code == PIE_ERR_RANGE ? "RangeError: Invalid time value (show %d)"
-                                              : "show %d: date/time is not an ECMA-262 date-time string",
-                  hout->status[1]);
-    }
-    const int64_t G = *hout->n_groups;
-    if (S > 0) {
-      PIE_CUDA(cudaMemcpyAsync(hout->show_day_start, dout.show_day_start, 8 * (uint64_t)S, cudaMemcpyDeviceToHost, st));
-      PIE_CUDA(cudaMemcpyAsync(hout->show_order, dout.show_order, 4 * (uint64_t)S, cudaMemcpyDeviceToHost, st));
-      d2h += 12 * (uint64_t)S;
-    }
-    PIE_CUDA(cudaMemcpyAsync(hout->group_offsets, dout.group_offsets, 4 * (uint64_t)(G + 1), cudaMemcpyDeviceToHost, st));
-    d2h += 4 * (uint64_t)(G + 1);
-    if (G > 0) {
-      PIE_CUDA(cudaMemcpyAsync(hout->group_day_start, dout.group_day_start, 8 * (uint64_t)G, cudaMemcpyDeviceToHost, st));
-      PIE_CUDA(cudaMemcpy2DAsync(hout->summary_f64, 8 * (uint64_t)hout->stride, dout.summary_f64, 8 * (uint64_t)Sc,
-                                 8 * (uint64_t)G, PIE_DF_COUNT * PIE_N_METRICS, cudaMemcpyDeviceToHost, st));
-      PIE_CUDA(cudaMemcpy2DAsync(hout->summary_count, 4 * (uint64_t)hout->stride, dout.summary_count, 4 * (uint64_t)Sc,
-                                 4 * (uint64_t)G, PIE_N_METRICS, cudaMemcpyDeviceToHost, st));
-      d2h += (8ull + 8ull * PIE_DF_COUNT * PIE_N_METRICS + 4ull * PIE_N_METRICS) * (uint64_t)G;
+    g_last_h2d = h2d;
+    if ((rc = download_daily(hout, dout, S, Sc, st, &d2h))) {
+      g_last_d2h = d2h;
+      return rc;
     }
   }
   PIE_CUDA(cudaStreamSynchronize(st));
@@ -662,8 +683,18 @@ int64_t pie_set_csv_chunk_rows(int64_t rows) {
   return old;
 }
 
+// The analytics that ride on the export pipeline (pie_archive_step_host): show statistics per chunk on the columns
+// the rows need anyway, the daily summary once at the end.
+struct StepAnalytics {
+  int32_t tz_offset_minutes;
+  int32_t* stats_i32;
+  double* stats_f64;
+  int64_t stats_stride;
+  const pie_daily_out* hout;
+};
+
 static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_t* row_offsets, uint8_t* out_data,
-                            uint64_t out_capacity, uint64_t* total_bytes) {
+                            uint64_t out_capacity, uint64_t* total_bytes, const StepAnalytics* an = nullptr) {
   std::lock_guard<std::mutex> lock(g_host_mutex);
   int rc = ensure_init();
   if (rc) return rc;
@@ -673,6 +704,48 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
   if (S > 0 && (hv->entry_offsets[0] != 0 || hv->entry_offsets[S] != E))
     return fail(PIE_ERR_INVALID_ARG, "entry_offsets must run from 0 to n_entries");
   if ((rc = g_pipe.init())) return rc;
+
+  // ---- analytics riding along: the per-batch arrays of the daily summary go up first, on the upload stream
+  const int64_t Sc = S > 0 ? S : 1;
+  uint64_t an_h2d = 0;
+  int32_t* d_si = nullptr;
+  double* d_sf = nullptr;
+  pie_archive_view dv_all;
+  pie_daily_out dout;
+  void* dscratch = nullptr;
+  memset(&dv_all, 0, sizeof(dv_all));
+  if (an) {
+    if (format != kFormatCsv) return fail(PIE_ERR_INVALID_ARG, "the step rides on the CSV rows");
+    if (an->tz_offset_minutes < -24 * 60 || an->tz_offset_minutes > 24 * 60)
+      return fail(PIE_ERR_INVALID_ARG, "tz_offset_minutes out of range");
+    if (!an->hout) return fail(PIE_ERR_INVALID_ARG, "pie_daily_out is NULL");
+    if ((an->stats_i32 != nullptr) != (an->stats_f64 != nullptr))
+      return fail(PIE_ERR_INVALID_ARG, "stats_i32 and stats_f64 go together");
+    if (an->stats_i32 && an->stats_stride < S) return fail(PIE_ERR_INVALID_ARG, "stats_stride < n_shows");
+    if ((rc = check_daily_out(an->hout, S))) return rc;
+    if (S > 0 && !hv->created_at) return fail(PIE_ERR_INVALID_ARG, "created_at is NULL");
+    uint64_t bytes = 0;
+    StrColPlan p_date, p_time;
+    const bool has_date = hv->show_date.offsets != nullptr, has_time = has_date && hv->show_time.offsets != nullptr;
+    if (has_date && (rc = plan_strcol(p_date, &hv->show_date, nullptr, S, &bytes, "show_date"))) return rc;
+    if (has_time && (rc = plan_strcol(p_time, &hv->show_time, nullptr, S, &bytes, "show_time"))) return rc;
+    bytes += pad(4 * (uint64_t)(S + 1)) + 2 * pad(8 * (uint64_t)Sc) + pad(8 * (uint64_t)E);
+    bytes += pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc) + daily_out_bytes(S, Sc);
+    if ((rc = g_arena.reserve(bytes))) return rc;
+    g_cur = &g_arena;
+    g_cur_stream = g_pipe.h2d;
+    dv_all.n_shows = S;
+    dv_all.n_entries = E;
+    if ((rc = upload_array(hv->entry_offsets, S + 1, &dv_all.entry_offsets, &an_h2d))) return rc;
+    if (S > 0 && (rc = upload_array(hv->created_at, S, &dv_all.created_at, &an_h2d))) return rc;
+    if (hv->archived_at && (rc = upload_array(hv->archived_at, S, &dv_all.archived_at, &an_h2d))) return rc;
+    if (hv->entry_ts && (rc = upload_array(hv->entry_ts, E, &dv_all.entry_ts, &an_h2d))) return rc;
+    if (has_date) { p_date.dst = &dv_all.show_date; if ((rc = upload_strcol(p_date, &an_h2d))) return rc; }
+    if (has_time) { p_time.dst = &dv_all.show_time; if ((rc = upload_strcol(p_time, &an_h2d))) return rc; }
+    d_si = (int32_t*)g_arena.take(4ull * PIE_SI_COUNT * Sc);
+    d_sf = (double*)g_arena.take(8ull * PIE_SF_COUNT * Sc);
+    dscratch = alloc_daily_out(g_arena, S, Sc, &dout);
+  }
 
   // chunks of ~kCsvChunkRows rows, cut at show boundaries
   std::vector<CsvChunk> chunks;
@@ -712,6 +785,8 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
       PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[slot ^ 1], g_pipe.h2d));
     }
     PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.h2d_done[slot], 0));
+    if (an && c.s1 > c.s0)  // the chunk's shows: status, launched, primaryIssue and delaySec are resident for the rows
+      PIE_CUDA(pie::launch_show_stats(c.dev, d_si + c.s0, d_sf + c.s0, Sc, g_sm_count, g_pipe.cmp));
     // pass 1: sizes only (row offsets + total), so the output can be placed and sized exactly
     PIE_CUDA(launch_rows(format, c.dev, c.d_offsets, nullptr, 0, bias, c.d_total, c.scratch, g_pipe.cmp));
     PIE_CUDA(cudaMemcpyAsync(g_pipe.h_total, c.d_total, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
@@ -742,6 +817,22 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
     PIE_CUDA(cudaEventRecord(g_pipe.d2h_done[slot], g_pipe.d2h));
     bias += total;
   }
+  int an_rc = PIE_OK;
+  if (an) {
+    // the first chunk's upload was enqueued after the per-batch arrays on the same stream, so the compute stream
+    // (which waited for that chunk) already sees them
+    PIE_CUDA(pie::launch_daily_summary(dv_all, d_si, d_sf, Sc, an->tz_offset_minutes, dout, dscratch, g_sm_count,
+                                       g_pipe.cmp));
+    if (an->stats_i32 && S > 0) {
+      PIE_CUDA(cudaMemcpy2DAsync(an->stats_i32, 4 * (uint64_t)an->stats_stride, d_si, 4 * (uint64_t)Sc, 4 * (uint64_t)S,
+                                 PIE_SI_COUNT, cudaMemcpyDeviceToHost, g_pipe.cmp));
+      PIE_CUDA(cudaMemcpy2DAsync(an->stats_f64, 8 * (uint64_t)an->stats_stride, d_sf, 8 * (uint64_t)Sc, 8 * (uint64_t)S,
+                                 PIE_SF_COUNT, cudaMemcpyDeviceToHost, g_pipe.cmp));
+      d2h += (4ull * PIE_SI_COUNT + 8ull * PIE_SF_COUNT) * (uint64_t)S;
+    }
+    an_rc = download_daily(an->hout, dout, S, Sc, g_pipe.cmp, &d2h);
+    h2d += an_h2d;
+  }
   PIE_CUDA(cudaStreamSynchronize(g_pipe.d2h));
   PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
   row_offsets[E] = (int64_t)bias;
@@ -750,10 +841,18 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
   g_last_d2h = d2h + 8;
   g_cur = &g_arena;
   g_cur_stream = g_arena.stream;
+  if (an_rc) return an_rc;  // RangeError / unsupported date raised by a show (pie_last_error has the text)
   if (overflow)
     return fail(PIE_ERR_CAPACITY, "the rows need %llu bytes, the caller's buffer holds %llu", bias,
                 (unsigned long long)out_capacity);
   return PIE_OK;
+}
+
+int pie_archive_step_host(const pie_archive_view* hv, int32_t tz_offset_minutes, int32_t* stats_i32, double* stats_f64,
+                          int64_t stats_stride, const pie_daily_out* host_out, int64_t* row_offsets, uint8_t* out_data,
+                          uint64_t out_capacity, uint64_t* total_bytes) {
+  const StepAnalytics an{tz_offset_minutes, stats_i32, stats_f64, stats_stride, host_out};
+  return export_rows_host(kFormatCsv, hv, row_offsets, out_data, out_capacity, total_bytes, &an);
 }
 
 int pie_csv_rows_host(const pie_archive_view* hv, int64_t* row_offsets, uint8_t* out_data, uint64_t out_capacity,

@@ -279,3 +279,32 @@ def compute_metrics(table: ArchiveTable) -> LiveMetrics:
         view = table.view()
         _lib.check(_lib.load().pie_compute_metrics_host(C.byref(view), i32.data_ptr(), text.data_ptr(), Sc))
     return LiveMetrics(i32[:, :S], text[:S])
+
+
+def archive_step(table: ArchiveTable, tz_offset_minutes: int = 0, out: "HostOutputs" = None,
+                 row_offsets: torch.Tensor = None, data: torch.Tensor = None):
+    """Host table in, everything the archive workspace shows out, through ONE pipelined upload: show statistics,
+    daily groups + metric summaries and the CSV rows (pie_archive_step_host).  With `row_offsets` / `data`
+    preallocated (pinned, data.numel() = the CSV size) one call does the whole job; otherwise the CSV size is
+    queried first.  Returns (ShowStats, DailySummary, CsvRows)."""
+    _lib.ensure_init()
+    assert not table.is_cuda
+    lib = _lib.load()
+    S, E = table.n_shows, table.n_entries
+    h = out if out is not None else HostOutputs(S)
+    view = table.view()
+    total = C.c_uint64(0)
+    if row_offsets is None:
+        row_offsets = torch.empty(E + 1, dtype=torch.int64)
+    if data is None:
+        _lib.check(lib.pie_csv_rows_host(C.byref(view), row_offsets.data_ptr(), None, 0, C.byref(total)))
+        data = torch.empty(max(int(total.value), 1), dtype=torch.uint8)
+    dout = h.daily_out()
+    _lib.check(lib.pie_archive_step_host(C.byref(view), tz_offset_minutes, h.stats_i32.data_ptr(), h.stats_f64.data_ptr(),
+                                         h.S, C.byref(dout), row_offsets.data_ptr(), data.data_ptr(), data.numel(),
+                                         C.byref(total)))
+    G = int(h.n_groups[0])
+    return (ShowStats(h.stats_i32[:, :S], h.stats_f64[:, :S]),
+            DailySummary(G, h.show_day_start[:S], h.show_order[:S], h.group_day_start[:G], h.group_offsets[:G + 1],
+                         h.summary_f64[:, :, :G], h.summary_count[:, :G]),
+            CsvRows(row_offsets, data[:int(total.value)]))

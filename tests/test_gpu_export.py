@@ -222,3 +222,37 @@ def test_many_tiny_shows_and_empty_shows(cuda):
     table = pack_shows(shows)
     assert_same_rows(ops.csv_rows(table.to(cuda)), table)
     assert_same_rows(ops.csv_rows(table), table)
+
+
+def test_archive_step_host_equals_the_two_calls(cuda):
+    """pie_archive_step_host = pie_archive_analytics_host + pie_csv_rows_host on one upload: identical statistics,
+    daily groups, summaries and CSV bytes, also when the batch is streamed in many chunks."""
+    lib = _lib.load()
+    host = synth_archive(6000, seed=13, shuffle_days=True, missing_created_frac=0.05).pin()
+    st_ref, daily_ref = ops.archive_analytics(host, -300)
+    rows_ref = ops.csv_rows(host)
+
+    def same(a, b):
+        return torch.equal(a.view(torch.int64) if a.dtype.is_floating_point else a,
+                           b.view(torch.int64) if b.dtype.is_floating_point else b)
+
+    old = lib.pie_set_csv_chunk_rows(0)
+    try:
+        for chunk_rows in (old, 2500, 64):
+            lib.pie_set_csv_chunk_rows(chunk_rows)
+            st, daily, rows = ops.archive_step(host, -300)
+            assert same(st.i32, st_ref.i32) and same(st.f64.contiguous(), st_ref.f64.contiguous())
+            assert daily.n_groups == daily_ref.n_groups
+            for name in ("show_day_start", "show_order", "group_day_start", "group_offsets", "summary_f64", "summary_count"):
+                assert same(getattr(daily, name).contiguous(), getattr(daily_ref, name).contiguous()), name
+            assert torch.equal(rows.row_offsets, rows_ref.row_offsets) and torch.equal(rows.data, rows_ref.data)
+    finally:
+        lib.pie_set_csv_chunk_rows(old)
+    # a show outside the time range raises the same error as the analytics call, whatever the rows did
+    from sph_pie_b200.columnar import pack_shows as pack
+    bad = pack([{"id": "a", "createdAt": 8.64e15 + 1, "entries": [{"id": "x"}]}])
+    with pytest.raises(_lib.JsRangeError):
+        ops.archive_step(bad, 0)
+    # empty batch
+    st, daily, rows = ops.archive_step(pack([]), 0)
+    assert daily.n_groups == 0 and rows.data.numel() == 0
