@@ -409,7 +409,7 @@ def main():
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("shows") == S:
-            k = tj["kernels"].get("export_rows_kernel") or tj["kernels"]["csv_rows_kernel"]
+            k = tj["kernels"].get("export_rows_kernel<csv>") or tj["kernels"]["csv_rows_kernel"]
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
 
     out = {
