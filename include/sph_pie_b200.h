@@ -256,8 +256,9 @@ int pie_archive_payloads_dev(const pie_archive_view* dev_view, int64_t* row_offs
 int pie_archive_payloads_host(const pie_archive_view* host_view, int64_t* row_offsets, uint8_t* out_data,
                               uint64_t out_capacity, uint64_t* total_bytes);
 
-/* Test hooks of the export-row kernel.  A tile (160 consecutive rows) whose column bytes or CSV do not
- * fit the kernel's shared-memory staging takes a slower warp-per-row path; `on` = 1 forces every tile
+/* Test hooks of the export-row kernel.  A tile (32..160 consecutive rows, planned per launch from the batch's
+ * average row width) whose column bytes or CSV do not fit the kernel's shared-memory staging takes a slower
+ * warp-per-row path; `on` = 1 forces every tile
  * through it, 0 restores the default, < 0 only queries; returns the previous value.
  * pie_debug_csv_slow_tiles reads how many tiles of the most recent pie_csv_rows_dev launch that used
  * `scratch` took that path (synchronises `stream`). */

@@ -87,13 +87,16 @@ struct CsvScratch {
   unsigned long long* tile_state;  // [n_tiles] packed (status, value); zeroed before launch
   unsigned int* tile_counter;      // [1] dynamic tile ids; zeroed before launch
   unsigned int* slow_tiles;        // [1] tiles that took the slow path (diagnostics); zeroed before launch
+  unsigned int* tile_rows;         // [1] rows per tile of this launch (plan_tile_rows), 32 .. kRows
   unsigned int* col_dirty;         // [24] column c holds at least one " , \n \r somewhere; zeroed before launch
   int32_t* entry_show;             // [n_entries]
 };
 
 static inline uint64_t align256(uint64_t x) { return (x + 255) & ~(uint64_t)255; }
 constexpr uint64_t kCtlBytes = 2048;  // tile counter, slow-tile counter, column flags; developer counters from byte 256
-__host__ __device__ static inline int64_t csv_tiles(int64_t n_entries) { return (n_entries + kRows - 1) / kRows; }
+constexpr int kMinTileRows = 32;  // a launch on wide rows uses tiles of fewer rows (plan_tile_rows)
+// tiles a batch can have at most (the tile-state array is sized for it)
+__host__ __device__ static inline int64_t csv_tiles(int64_t n_entries) { return (n_entries + kMinTileRows - 1) / kMinTileRows; }
 
 uint64_t csv_scratch_bytes(int64_t n_entries) {
   const uint64_t e = (uint64_t)(n_entries > 0 ? n_entries : 1);
@@ -110,6 +113,7 @@ static CsvScratch carve_csv(void* scratch, int64_t n_entries) {
   s.tile_state = (unsigned long long*)p; p += align256(8 * (uint64_t)csv_tiles(e));
   s.tile_counter = (unsigned int*)p;
   s.slow_tiles = (unsigned int*)(p + 16);
+  s.tile_rows = (unsigned int*)(p + 32);
   s.col_dirty = (unsigned int*)(p + 64);
   p += kCtlBytes;
   s.entry_show = (int32_t*)p;
@@ -128,7 +132,7 @@ cudaError_t csv_read_slow_tiles(const void* scratch, int64_t n_entries, unsigned
   {
     unsigned long long ph[64];
     cudaMemcpy(ph, sc.tile_counter + 64, sizeof(ph), cudaMemcpyDeviceToHost);
-    const long long tiles = csv_tiles(n_entries);
+    const long long tiles = (n_entries + kRows - 1) / kRows;  // of full tiles (a launch on wide rows has more)
     for (int i = 0; i < 12; ++i)
       fprintf(stderr, "phase %2d: cycles per tile, first thread of group 0..3: %7llu %7llu %7llu %7llu\n", i,
               ph[i] / tiles, ph[16 + i] / tiles, ph[32 + i] / tiles, ph[48 + i] / tiles);
@@ -359,6 +363,59 @@ static RowTable make_payload_table(const pie_archive_view& v) {
   return t;
 }
 static_assert(kCols == 24, "the row formats above are laid out for 24 cells");
+
+// ---- rows per tile of a launch ------------------------------------------------------------------------
+// A tile's column bytes, offset slices and output must fit the shared-memory stage and output tile; tiles
+// that do not take the slow path, which is ~20x slower.  So a batch of wide rows (long free text) is cut into
+// tiles of fewer rows: from the AVERAGE bytes per row of the batch (one thread reads the ~50 end offsets),
+// with a margin; a tile that is still too large goes the slow way.
+__global__ void plan_tile_rows_kernel(const __grid_constant__ RowTable tab, int64_t n_shows, int64_t n_entries,
+                                      int stage_bytes, int out_bytes, const unsigned int* __restrict__ col_dirty,
+                                      unsigned int* __restrict__ tile_rows) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double entry_bytes = 0, show_bytes = 0, literal_bytes = 0, arrays_per_row = 4 + 9;  // show index, delaySec + validity
+  double bump_bytes = 0;  // cells that may be written out again (escaped / joined), per row
+  const double E = (double)(n_entries > 0 ? n_entries : 1), S = (double)(n_shows > 0 ? n_shows : 1);
+  for (int c = 0; c < kCols; ++c) {
+    const CellDesc& d = tab.cell[c];
+    if (d.kind == kCellLiteral) literal_bytes += d.lit_len;
+    if (d.kind == kCellYesNo) literal_bytes += d.lit_no_len;
+    if (d.kind != kCellString && d.kind != kCellJoined && d.kind != kCellYesNo) continue;
+    const int64_t n = d.per_entry ? n_entries : n_shows;
+    int64_t first = 0, last = n;
+    double items = 0;
+    if (d.kind == kCellJoined) {
+      first = d.list_offsets[0];
+      last = d.list_offsets[n];
+      items = (double)(last - first);
+    }
+    const double bytes = (double)(d.offsets[last] - d.offsets[first]);
+    // a column that holds a byte to escape anywhere, and every list column, may have each cell written out a second
+    // time (a little longer) in the bump area: count all of it — falling off the fast path costs far more than
+    // a smaller tile
+    const bool may_copy = d.kind != kCellYesNo && (col_dirty[c] != 0 || d.kind == kCellJoined);
+    if (d.per_entry) {
+      entry_bytes += bytes;
+      arrays_per_row += 4.0 + 4.0 * items / E;
+      if (may_copy) bump_bytes += 1.1 * bytes / E + 4.0;
+    } else {
+      show_bytes += bytes;
+      arrays_per_row += (4.0 + 4.0 * items / S) * S / E;
+      if (may_copy) bump_bytes += (1.1 * bytes / S + 4.0) * S / E;
+    }
+  }
+  // staged per row: the entry-level bytes, the row's share of its show's bytes and of the offset slices, the bump
+  // area; 10 % on top for the 16-byte rounding of ~50 ranges and rows longer than the average
+  const double in_per_row = 1.10 * (entry_bytes / E + show_bytes / E + arrays_per_row + bump_bytes);
+  // written per row: every cell (a show's cells are repeated on each of its rows), separators, literal text; quotes
+  // and escapes add, blanked cells subtract: 10 %
+  const double out_per_row = 1.10 * (entry_bytes / E + show_bytes / S + kCols + literal_bytes);
+  double rows = fmin((stage_bytes - kLiteralBytes - 2048) / in_per_row, out_bytes / out_per_row);
+  int r = rows >= kRows ? kRows : (int)rows;
+  r = (r / 32) * 32;
+  if (r < kMinTileRows) r = kMinTileRows;
+  *tile_rows = (unsigned int)r;
+}
 
 // ---- pre-pass: which columns can need quoting at all? -----------------------------------------------
 // Most columns of an archive (ids, dates, enumerations, names) never contain a byte that needs escaping.  One
@@ -935,10 +992,10 @@ __device__ __forceinline__ void issue_range(const Range& r, const RangePlan& p, 
 }
 
 __device__ __forceinline__ void produce_tile(const pie_archive_view& v, const RowTable& tab, const CsvScratch& sc,
-                                             StageInfo& info, uint8_t* stage, uint32_t bar, int64_t tile, int force_slow,
-                                             int lane) {
-  const int64_t e0 = tile * kRows;
-  const int rows = (v.n_entries - e0 < kRows) ? (int)(v.n_entries - e0) : kRows;
+                                             StageInfo& info, uint8_t* stage, uint32_t bar, int64_t tile, int tile_rows,
+                                             int force_slow, int lane) {
+  const int64_t e0 = tile * tile_rows;
+  const int rows = (v.n_entries - e0 < tile_rows) ? (int)(v.n_entries - e0) : tile_rows;
   const int32_t s0 = sc.entry_show[e0], s1 = sc.entry_show[e0 + rows - 1];
   Range rb{0, 0}, ro{0, 0}, ri{0, 0};  // heap bytes, offsets slice, item offsets slice
   uint32_t b0 = 0;
@@ -1080,7 +1137,8 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
   uint8_t* s_out = s_dyn;  // kOutBytes + 32
   CsvSmem& sm = *reinterpret_cast<CsvSmem*>(s_dyn + kSmemOffState);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t n_tiles = csv_tiles(v.n_entries);
+  const int tile_rows = (int)*sc.tile_rows;  // rows per tile of this launch: kRows unless the rows are wide
+  const int64_t n_tiles = (v.n_entries + tile_rows - 1) / tile_rows;
 
   if (tid == 0) {
     mbar_init(smem_u32(&sm.full[0]), 1);
@@ -1119,7 +1177,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
         return;
       }
       produce_tile(v, tab, sc, sm.info[s], s_dyn + kSmemOffStage + s * kStageStride, smem_u32(&sm.full[s]), tile,
-                   force_slow, lane);
+                   tile_rows, force_slow, lane);
     }
   }
 
@@ -1278,7 +1336,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       bar_arrive_workers_and_lookback<kBarTotalReady>();
       return;
     }
-    const int64_t e0 = tile * kRows;
+    const int64_t e0 = tile * tile_rows;
     const int rows = info.rows;
     const bool have = r < rows;
     bool slow = info.slow != 0;  // uniform
@@ -1519,11 +1577,13 @@ static cudaError_t launch_rows(const pie_archive_view& v, const RowTable& tab, i
     column_dirty_kernel<kJson><<<dim3((unsigned)blocks, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries,
                                                                                  sc.col_dirty);
   }
+  plan_tile_rows_kernel<<<1, 32, 0, stream>>>(tab, v.n_shows, v.n_entries, kStageBytes, kOutBytes, sc.col_dirty,
+                                              sc.tile_rows);
   const int64_t tiles = csv_tiles(v.n_entries);
   const unsigned grid = (unsigned)(tiles < resident_ctas ? tiles : resident_ctas);
   export_rows_kernel<kJson><<<grid, kCtaThreads, kSmemBytes, stream>>>(v, tab, sc, row_offsets, out_data, capacity, bias,
                                                                       total_out, g_force_slow);
-  g_launches += 3;
+  g_launches += 4;
   return cudaGetLastError();
 }
 

@@ -207,7 +207,7 @@ def archive_payloads_dev(table: ArchiveTable, bufs: CsvBuffers, size_only: bool 
 
 
 def csv_slow_tiles(table: ArchiveTable, bufs: CsvBuffers) -> int:
-    """Tiles (160 rows) of the last csv_rows_dev launch on `bufs` that did not fit the kernel's
+    """Tiles (32..160 rows) of the last csv_rows_dev launch on `bufs` that did not fit the kernel's
     shared-memory staging and took the warp-per-row path (test / tuning hook)."""
     n = C.c_uint32(0)
     _lib.check(_lib.load().pie_debug_csv_slow_tiles(bufs.scratch.data_ptr(), table.n_entries, C.byref(n), _stream_ptr()))

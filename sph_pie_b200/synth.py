@@ -112,7 +112,7 @@ def _uuid_like(n: int, gen: torch.Generator, device) -> StrCol:
 
 def synth_archive(n_shows: int, seed: int = 0, device="cpu", max_entries: int = 21, shows_per_day: int = 5,
                   shuffle_days: bool = False, dirty: bool = True, start_ms: int = 1704067200000,
-                  missing_created_frac: float = 0.0) -> ArchiveTable:
+                  missing_created_frac: float = 0.0, notes_repeat: int = 1) -> ArchiveTable:
     """`n_shows` shows with 0..max_entries entries each (21 seeded operators, one entry per operator
     per show: sqlProvider.js:434-457), up to `shows_per_day` shows per calendar day
     (sqlProvider.js:427), ascending by createdAt unless `shuffle_days`."""
@@ -224,7 +224,8 @@ def synth_archive(n_shows: int, seed: int = 0, device="cpu", max_entries: int = 
         "operator_name": strcol_from_codes(within % 21, NAME_VOCAB),
         "battery_id": _numbered("B-", torch.randint(1, 400, (E,), generator=gen, device=device), 3),
         "command_rx": strcol_from_codes(_choice(E, yn_p, gen, device), yn_vocab),
-        "notes": strcol_from_codes(torch.randint(0, len(NOTES_VOCAB), (E,), generator=gen, device=device), NOTES_VOCAB),
+        "notes": strcol_from_codes(torch.randint(0, len(NOTES_VOCAB), (E,), generator=gen, device=device),
+                                   [n * notes_repeat for n in NOTES_VOCAB]),  # notes_repeat > 1: long free text
     }
     act_n = torch.randint(0, 3, (E,), generator=gen, device=device)
     act_lo = torch.zeros(E + 1, dtype=torch.int64, device=device)
