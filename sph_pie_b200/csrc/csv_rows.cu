@@ -88,7 +88,8 @@ struct CsvScratch {
   unsigned int* tile_counter;      // [1] dynamic tile ids; zeroed before launch
   unsigned int* slow_tiles;        // [1] tiles that took the slow path (diagnostics); zeroed before launch
   unsigned int* tile_rows;         // [1] rows per tile of this launch (plan_tile_rows), 32 .. kRows
-  unsigned int* col_dirty;         // [24] column c holds at least one " , \n \r somewhere; zeroed before launch
+  unsigned int* col_dirty;         // [24] column c holds at least one byte to escape somewhere; zeroed before launch
+  unsigned int* col_dirty_chunks;  // [24] how many of its 16-byte chunks do (for plan_tile_rows); zeroed before launch
   int32_t* entry_show;             // [n_entries]
 };
 
@@ -115,6 +116,7 @@ static CsvScratch carve_csv(void* scratch, int64_t n_entries) {
   s.slow_tiles = (unsigned int*)(p + 16);
   s.tile_rows = (unsigned int*)(p + 32);
   s.col_dirty = (unsigned int*)(p + 64);
+  s.col_dirty_chunks = (unsigned int*)(p + 160);
   p += kCtlBytes;
   s.entry_show = (int32_t*)p;
   return s;
@@ -371,39 +373,58 @@ static_assert(kCols == 24, "the row formats above are laid out for 24 cells");
 // with a margin; a tile that is still too large goes the slow way.
 __global__ void plan_tile_rows_kernel(const __grid_constant__ RowTable tab, int64_t n_shows, int64_t n_entries,
                                       int stage_bytes, int out_bytes, const unsigned int* __restrict__ col_dirty,
+                                      const unsigned int* __restrict__ col_dirty_chunks,
                                       unsigned int* __restrict__ tile_rows) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double entry_bytes = 0, show_bytes = 0, literal_bytes = 0, arrays_per_row = 4 + 9;  // show index, delaySec + validity
+  // one warp, lane c = column c (the end offsets of the columns are read in parallel), sums by shuffles
+  const int c = threadIdx.x;
+  double entry_bytes = 0, show_bytes = 0, literal_bytes = 0, arrays_per_row = 0;
   double bump_bytes = 0;  // cells that may be written out again (escaped / joined), per row
   const double E = (double)(n_entries > 0 ? n_entries : 1), S = (double)(n_shows > 0 ? n_shows : 1);
-  for (int c = 0; c < kCols; ++c) {
+  if (c < kCols) {
     const CellDesc& d = tab.cell[c];
-    if (d.kind == kCellLiteral) literal_bytes += d.lit_len;
-    if (d.kind == kCellYesNo) literal_bytes += d.lit_no_len;
-    if (d.kind != kCellString && d.kind != kCellJoined && d.kind != kCellYesNo) continue;
-    const int64_t n = d.per_entry ? n_entries : n_shows;
-    int64_t first = 0, last = n;
-    double items = 0;
-    if (d.kind == kCellJoined) {
-      first = d.list_offsets[0];
-      last = d.list_offsets[n];
-      items = (double)(last - first);
-    }
-    const double bytes = (double)(d.offsets[last] - d.offsets[first]);
-    // a column that holds a byte to escape anywhere, and every list column, may have each cell written out a second
-    // time (a little longer) in the bump area: count all of it — falling off the fast path costs far more than
-    // a smaller tile
-    const bool may_copy = d.kind != kCellYesNo && (col_dirty[c] != 0 || d.kind == kCellJoined);
-    if (d.per_entry) {
-      entry_bytes += bytes;
-      arrays_per_row += 4.0 + 4.0 * items / E;
-      if (may_copy) bump_bytes += 1.1 * bytes / E + 4.0;
-    } else {
-      show_bytes += bytes;
-      arrays_per_row += (4.0 + 4.0 * items / S) * S / E;
-      if (may_copy) bump_bytes += (1.1 * bytes / S + 4.0) * S / E;
+    if (d.kind == kCellLiteral) literal_bytes = d.lit_len;
+    if (d.kind == kCellYesNo) literal_bytes = d.lit_no_len;
+    if (d.kind == kCellString || d.kind == kCellJoined || d.kind == kCellYesNo) {
+      const int64_t n = d.per_entry ? n_entries : n_shows;
+      int64_t first = 0, last = n;
+      double items = 0;
+      if (d.kind == kCellJoined) {
+        first = d.list_offsets[0];
+        last = d.list_offsets[n];
+        items = (double)(last - first);
+      }
+      const double bytes = (double)(d.offsets[last] - d.offsets[first]);
+      // A cell that holds a byte to escape, and a list cell of several items, is written out a second time (a
+      // little longer) in the bump area.  List columns: all of them.  Other columns: the share of their 16-byte
+      // chunks that hold such a byte, times 3 (a cell is a few chunks) — generous, because falling off the fast
+      // path costs far more than a smaller tile.
+      double copy_share = 0;
+      if (d.kind == kCellJoined) copy_share = 1;
+      else if (d.kind == kCellString && col_dirty[c]) {
+        const double chunks = bytes / 16.0;
+        copy_share = chunks < 64 ? 1.0 : fmin(1.0, 3.0 * (double)col_dirty_chunks[c] / chunks + 0.02);
+      }
+      if (d.per_entry) {
+        entry_bytes = bytes;
+        arrays_per_row = 4.0 + 4.0 * items / E;
+        bump_bytes = copy_share * (1.1 * bytes / E + 4.0);
+      } else {
+        show_bytes = bytes;
+        arrays_per_row = (4.0 + 4.0 * items / S) * S / E;
+        bump_bytes = copy_share * (1.1 * bytes / S + 4.0) * S / E;
+      }
     }
   }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    entry_bytes += __shfl_xor_sync(0xFFFFFFFFu, entry_bytes, o);
+    show_bytes += __shfl_xor_sync(0xFFFFFFFFu, show_bytes, o);
+    literal_bytes += __shfl_xor_sync(0xFFFFFFFFu, literal_bytes, o);
+    arrays_per_row += __shfl_xor_sync(0xFFFFFFFFu, arrays_per_row, o);
+    bump_bytes += __shfl_xor_sync(0xFFFFFFFFu, bump_bytes, o);
+  }
+  if (c != 0) return;
+  arrays_per_row += 4 + 9;  // the rows' show indices, delaySec + validity
   // staged per row: the entry-level bytes, the row's share of its show's bytes and of the offset slices, the bump
   // area; 10 % on top for the 16-byte rounding of ~50 ranges and rows longer than the average
   const double in_per_row = 1.10 * (entry_bytes / E + show_bytes / E + arrays_per_row + bump_bytes);
@@ -423,7 +444,8 @@ __global__ void plan_tile_rows_kernel(const __grid_constant__ RowTable tab, int6
 // per-column flag; the row kernel then skips the per-cell scan for clean columns altogether.
 template <bool kJson>
 __global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant__ RowTable tab, int64_t n_shows,
-                                                           int64_t n_entries, unsigned int* __restrict__ col_dirty) {
+                                                           int64_t n_entries, unsigned int* __restrict__ col_dirty,
+                                                           unsigned int* __restrict__ col_dirty_chunks) {
   const int col = blockIdx.y;
   const CellDesc& d = tab.cell[col];
   if (d.kind != kCellString && d.kind != kCellJoined) return;
@@ -437,13 +459,15 @@ __global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant
   if (b1 <= b0) return;
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(d.data + b0), a1 = reinterpret_cast<uintptr_t>(d.data + b1);
   const uintptr_t w0 = (a0 + 15) & ~static_cast<uintptr_t>(15), w1 = a1 & ~static_cast<uintptr_t>(15);
-  uint32_t flags = 0;
+  uint32_t flags = 0, dirty_chunks = 0;
   if (w1 > w0) {  // full 16-byte chunks inside the heap
     const int64_t chunks = static_cast<int64_t>((w1 - w0) >> 4);
     const uint4* __restrict__ p = reinterpret_cast<const uint4*>(w0);
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (int64_t)gridDim.x * blockDim.x) {
       const uint4 x = __ldg(p + c);
-      flags |= special_flags<kJson>(x.x) | special_flags<kJson>(x.y) | special_flags<kJson>(x.z) | special_flags<kJson>(x.w);
+      const uint32_t f = special_flags<kJson>(x.x) | special_flags<kJson>(x.y) | special_flags<kJson>(x.z) | special_flags<kJson>(x.w);
+      flags |= f;
+      dirty_chunks += (f != 0);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {  // the < 16 bytes at either end (or a heap shorter than a chunk)
@@ -451,7 +475,13 @@ __global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant
     for (uintptr_t a = a0 + threadIdx.x; a < head_end; a += 32) flags |= is_special_byte<kJson>(*reinterpret_cast<const uint8_t*>(a));
     for (uintptr_t a = tail_begin + threadIdx.x; a < a1; a += 32) flags |= is_special_byte<kJson>(*reinterpret_cast<const uint8_t*>(a));
   }
-  if (__any_sync(0xFFFFFFFFu, flags != 0) && (threadIdx.x & 31) == 0) atomicOr(&col_dirty[col], 1u);
+  if (__any_sync(0xFFFFFFFFu, flags != 0)) {  // rare
+    dirty_chunks = __reduce_add_sync(0xFFFFFFFFu, dirty_chunks);
+    if ((threadIdx.x & 31) == 0) {
+      atomicOr(&col_dirty[col], 1u);
+      if (dirty_chunks) atomicAdd(&col_dirty_chunks[col], dirty_chunks);
+    }
+  }
 }
 
 // ---- PTX: mbarrier, 1-D TMA bulk copy, named barriers ----------------------------------------------
@@ -1575,10 +1605,10 @@ static cudaError_t launch_rows(const pie_archive_view& v, const RowTable& tab, i
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     column_dirty_kernel<kJson><<<dim3((unsigned)blocks, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries,
-                                                                                 sc.col_dirty);
+                                                                                 sc.col_dirty, sc.col_dirty_chunks);
   }
   plan_tile_rows_kernel<<<1, 32, 0, stream>>>(tab, v.n_shows, v.n_entries, kStageBytes, kOutBytes, sc.col_dirty,
-                                              sc.tile_rows);
+                                              sc.col_dirty_chunks, sc.tile_rows);
   const int64_t tiles = csv_tiles(v.n_entries);
   const unsigned grid = (unsigned)(tiles < resident_ctas ? tiles : resident_ctas);
   export_rows_kernel<kJson><<<grid, kCtaThreads, kSmemBytes, stream>>>(v, tab, sc, row_offsets, out_data, capacity, bias,
