@@ -49,7 +49,13 @@ typedef enum pie_status {
   PIE_ERR_UNSUPPORTED_DATE = -4, /* show.date/time not in the ECMA-262 date-time format; V8's legacy
                                     Date.parse fallback is implementation-defined and not provided */
   PIE_ERR_CAPACITY = -5,         /* caller's output buffer too small; required size is reported */
-  PIE_ERR_NO_DEVICE = -6         /* no sm_100 device visible: there is NO CPU fallback */
+  PIE_ERR_NO_DEVICE = -6,        /* no sm_100 device visible: there is NO CPU fallback */
+  PIE_ERR_SCHEMA = -7,           /* JSON ingest: a stored document is not a provider-normalised show (a text field
+                                    that is neither string nor null, delaySec that is neither number nor null, a
+                                    string holding a lone surrogate): what pack_shows raises TypeError for */
+  PIE_ERR_UNSUPPORTED_JSON = -8  /* JSON ingest: valid JSON outside what the kernel decides exactly — a known key
+                                    twice in one object, nesting deeper than 64, bytes that are not UTF-8, a number
+                                    of more than 19 significant digits on a rounding boundary */
 } pie_status;
 
 typedef struct pie_strcol {
@@ -264,6 +270,94 @@ int pie_archive_payloads_host(const pie_archive_view* host_view, int64_t* row_of
  * `scratch` took that path (synchronises `stream`). */
 int pie_debug_csv_force_slow_path(int on);
 int pie_debug_csv_slow_tiles(const void* scratch, int64_t n_entries, uint32_t* slow_tiles, void* stream);
+
+/* ---- JSON ingest: replaces `rows.map(row => this._mapArchiveRow(row)).filter(Boolean)` (server/storage/
+ * sqlProvider.js:230-234; _mapArchiveRow :892-926 — JSON.parse(row.data), null unless the value is an object) and
+ * `rows.map(r => JSON.parse(r.data))` (:78-82), projected on the archive table: the stored `data` texts (written by
+ * JSON.stringify(show), :682 / :696) of a batch of rows go in, the columnar table every other entry point reads
+ * comes out, without the documents ever existing as JS objects.  One document per show:
+ *   docs.data[docs.offsets[s] .. docs.offsets[s+1])  UTF-8 JSON text (ECMA-404), each document < 2 GiB.
+ * Projection (what pack_shows does with JSON.parse's result; keys in any order, unknown keys skipped whatever
+ * they hold):
+ *   show:  id date time label leadPilot monkeyLead notes -> text columns (string; null / absent = '');
+ *          crew -> list of strings when it is an array (null elements = ''), else empty;
+ *          createdAt archivedAt -> the number when it is a finite number, else NaN;
+ *          entries -> one row per element when it is an array (an element that is not an object is a row without
+ *          fields), else none.
+ *   entry: id unitId planned launched status primaryIssue subIssue otherDetail severity rootCause operator batteryId
+ *          commandRx notes -> text; actions -> list of strings; delaySec -> number (delay_valid 1) or null / absent
+ *          (0); ts -> finite number or NaN.
+ *   Numbers are correctly rounded binary64 (StringToNumber), strings are unescaped to UTF-8 (surrogate-pair
+ *   escapes become one 4-byte sequence).
+ * doc_status[s]: 0 = a show; 1 = dropped — the text is not JSON, or JSON that is not an object / array (the
+ *   reference maps the row to null and filters it out); its table row is the empty show (no entries, '' texts, NaN
+ *   times), which every analytics entry point skips; callers that need the reference's row COUNT compact by it.
+ * Anything else fails loudly: PIE_ERR_SCHEMA / PIE_ERR_UNSUPPORTED_JSON (see pie_status) / PIE_ERR_CAPACITY (a
+ * heap or row count of 2 GiB and more: split the batch), reported with the first offending document.
+ *
+ * Two device calls, because the caller owns the memory of the table:
+ *   1. pie_ingest_measure_dev: walks every document once; totals_dev[PIE_INGEST_TOTALS] receive the bytes of the 23
+ *      string heaps, n_entries and the item counts of crew / actions; status_dev[2] = {pie_status, document};
+ *      `scratch` (pie_ingest_scratch_bytes(n_docs)) keeps where each document's part of every column starts.
+ *   2. the caller reads totals/status, allocates the table (offsets: rows + 1 elements) and calls
+ *      pie_ingest_fill_dev with the same docs / scratch / doc_status: the second walk writes everything.
+ *      Not to be called when status[0] != 0. */
+#define PIE_INGEST_HEAPS 23
+enum {
+  /* 0..22: bytes of the string heaps in table order: show_id, show_date, show_time, show_label, lead_pilot,
+   * monkey_lead, show_notes, crew.items, entry_id, unit_id, planned, launched, status, primary_issue, sub_issue,
+   * other_detail, severity, root_cause, operator_name, battery_id, command_rx, notes, actions.items */
+  PIE_IT_ENTRIES = 23,      /* n_entries */
+  PIE_IT_CREW_ITEMS = 24,   /* rows of crew.items */
+  PIE_IT_ACTION_ITEMS = 25, /* rows of actions.items */
+  PIE_INGEST_TOTALS = 26
+};
+
+typedef struct pie_json_docs {
+  int64_t n_docs;
+  const int64_t* offsets; /* [n_docs + 1] */
+  const uint8_t* data;    /* inside an allocation that starts 8-byte aligned (any cudaMalloc / torch tensor): the
+                             kernels read the aligned 8-byte words that hold a document's bytes */
+} pie_json_docs;
+
+typedef struct pie_strcol_mut {
+  int32_t* offsets;
+  uint8_t* data;
+} pie_strcol_mut;
+typedef struct pie_strlistcol_mut {
+  int32_t* list_offsets;
+  pie_strcol_mut items;
+} pie_strlistcol_mut;
+/* pie_archive_view with writable pointers: same fields, same order, same layout — a filled table is read by the
+ * other entry points through a cast / field-wise copy. */
+typedef struct pie_archive_table {
+  int64_t n_shows;
+  int64_t n_entries;
+  int32_t* entry_offsets;
+  pie_strcol_mut show_id, show_date, show_time, show_label, lead_pilot, monkey_lead, show_notes;
+  pie_strlistcol_mut crew;
+  double* created_at;
+  double* archived_at;
+  pie_strcol_mut entry_id, unit_id, planned, launched, status, primary_issue, sub_issue, other_detail, severity,
+      root_cause, operator_name, battery_id, command_rx, notes;
+  pie_strlistcol_mut actions;
+  double* delay_sec;
+  uint8_t* delay_valid;
+  double* entry_ts;
+} pie_archive_table;
+
+uint64_t pie_ingest_scratch_bytes(int64_t n_docs);
+int pie_ingest_measure_dev(const pie_json_docs* dev_docs, void* scratch, uint8_t* doc_status, int64_t* totals_dev,
+                           int32_t* status_dev, void* stream);
+int pie_ingest_fill_dev(const pie_json_docs* dev_docs, const void* scratch, const uint8_t* doc_status,
+                        const pie_archive_table* dev_table, void* stream);
+/* Host variant: uploads the texts, runs both passes, downloads the table.  `host_table` receives pointers into
+ * pinned memory OWNED BY THE LIBRARY (valid until the next pie_ingest_host call or pie_ingest_host_release);
+ * doc_status is the caller's [n_docs]; totals (may be NULL) as above; *bad_doc (may be NULL) = the offending
+ * document of a failing call, else -1. */
+int pie_ingest_host(const pie_json_docs* host_docs, pie_archive_table* host_table, uint8_t* doc_status,
+                    int64_t* totals, int64_t* bad_doc);
+void pie_ingest_host_release(void);
 
 /* ---- self tests (device code paths that replace an IEEE operation by a faster exact sequence) */
 /* Compares the shared-reciprocal quotient used for the rate columns with IEEE a/b for every

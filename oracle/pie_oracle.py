@@ -658,3 +658,127 @@ def archive_entry_payload_json(show=UNDEFINED, entry=UNDEFINED) -> str:
             text = json_quote(js_string(value))
         parts.append(json_quote(key) + ":" + text)
     return "{" + ",".join(parts) + "}"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# stored documents -> shows: JSON.parse(row.data) as _mapArchiveRow does it (server/storage/sqlProvider.js:892-926)
+# ---------------------------------------------------------------------------------------------------------
+SHOW_DOC_KEYS = ("id", "date", "time", "label", "leadPilot", "monkeyLead", "notes", "crew", "createdAt", "archivedAt",
+                 "entries")
+ENTRY_DOC_KEYS = ("id", "unitId", "planned", "launched", "status", "primaryIssue", "subIssue", "otherDetail",
+                  "severity", "rootCause", "operator", "batteryId", "commandRx", "notes", "actions", "delaySec", "ts")
+MAX_JSON_DEPTH = 64  # deeper nesting is reported, not parsed (the kernel's kind stack)
+
+
+class UnsupportedJson(ValueError):
+    """Valid JSON the ingest path declines to decide: PIE_ERR_UNSUPPORTED_JSON."""
+
+
+class JsObject(dict):
+    """JSON.parse's object: a dict that remembers which keys the text held more than once."""
+    dup_keys: frozenset = frozenset()
+
+
+def _pairs_hook(pairs):
+    obj = JsObject()
+    dups = set()
+    for k, v in pairs:
+        if k in obj:
+            dups.add(k)
+        obj[k] = v  # the last one wins, as in JSON.parse
+    obj.dup_keys = frozenset(dups)
+    return obj
+
+
+def _reject_constant(name):
+    raise ValueError(f"{name} is not JSON")  # Python's json accepts NaN / Infinity / -Infinity; ECMA-404 does not
+
+
+def _nesting_depth(text: str) -> int:
+    depth = deepest = 0
+    in_string = escaped = False
+    for ch in text:
+        if in_string:
+            if escaped:
+                escaped = False
+            elif ch == "\\":
+                escaped = True
+            elif ch == '"':
+                in_string = False
+        elif ch == '"':
+            in_string = True
+        elif ch in "[{":
+            depth += 1
+            deepest = max(deepest, depth)
+        elif ch in "]}":
+            depth -= 1
+    return deepest
+
+
+def js_json_parse(text: str):
+    """JSON.parse(text) on the Python image of JS values: every number is a Number (binary64, correctly rounded,
+    overflow -> Infinity), objects are JsObject.  Raises ValueError where JSON.parse throws SyntaxError.  Python's
+    json module is the parser — an implementation of the same grammar that shares nothing with the kernel."""
+    import json
+
+    return json.loads(text, parse_int=float, parse_float=float, parse_constant=_reject_constant,
+                      object_pairs_hook=_pairs_hook)
+
+
+def map_archive_row(data):
+    """_mapArchiveRow(row) (sqlProvider.js:892-926) as far as row.data goes: the parsed show, or None when the
+    text does not parse or the value is not an object (`!show || typeof show !== 'object'`; arrays ARE objects).
+    `data` is the column's UTF-8 bytes or a str.  Raises UnsupportedJson for what the ingest path reports instead of
+    deciding: bytes that are not UTF-8, nesting deeper than 64, a known key twice in the show or in an entry."""
+    bad_utf8 = False
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        try:
+            text = bytes(data).decode("utf-8")
+        except UnicodeDecodeError:
+            bad_utf8 = True
+            text = bytes(data).decode("utf-8", errors="replace")
+    else:
+        text = data
+    try:
+        show = js_json_parse(text)
+    except RecursionError:
+        raise UnsupportedJson("nesting deeper than 64")
+    except ValueError:
+        return None
+    if bad_utf8:
+        raise UnsupportedJson("the text is not UTF-8")
+    if _nesting_depth(text) > MAX_JSON_DEPTH:
+        raise UnsupportedJson("nesting deeper than 64")
+    if show is None or not isinstance(show, (dict, list)):
+        return None
+    if isinstance(show, JsObject):
+        if show.dup_keys & set(SHOW_DOC_KEYS):
+            raise UnsupportedJson("a show key twice")
+        entries = show.get("entries")
+        if isinstance(entries, list):
+            for e in entries:
+                if isinstance(e, JsObject) and e.dup_keys & set(ENTRY_DOC_KEYS):
+                    raise UnsupportedJson("an entry key twice")
+    return show
+
+
+def js_json_stringify(value) -> str:
+    """JSON.stringify(value) for the values a stored show is made of (ECMA-262 25.5.2): objects in insertion order,
+    no whitespace, Number::toString for finite numbers, null for NaN / Infinity, QuoteJSONString for strings."""
+    if value is None:
+        return "null"
+    if value is True:
+        return "true"
+    if value is False:
+        return "false"
+    if isinstance(value, (int, float)):
+        f = float(value)
+        return js_number_to_string(f) if math.isfinite(f) else "null"
+    if isinstance(value, str):
+        return json_quote(value)
+    if isinstance(value, (list, tuple)):
+        return "[" + ",".join(js_json_stringify(v) for v in value) + "]"
+    if isinstance(value, dict):
+        return "{" + ",".join(json_quote(k) + ":" + js_json_stringify(v) for k, v in value.items()
+                              if v is not UNDEFINED) + "}"
+    raise TypeError(type(value).__name__)

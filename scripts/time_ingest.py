@@ -1,0 +1,67 @@
+"""Times the JSON-ingest kernels on the GPU: a sample of stored documents (json.dumps of a synthetic archive),
+replicated on the device to the bench size, through pie_ingest_measure_dev + pie_ingest_fill_dev.
+usage: python scripts/time_ingest.py [sample_shows=16384] [copies=64] [iters=5]"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sph_pie_b200 import _lib, ops  # noqa: E402
+from sph_pie_b200.synth import synth_archive, table_to_shows  # noqa: E402
+
+
+def replicated_docs(sample_shows, copies, device, seed=0):
+    host = synth_archive(sample_shows, seed=seed)
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+    host.delay_valid[lost] = 0
+    docs = [json.dumps(s, ensure_ascii=False, separators=(",", ":")) for s in table_to_shows(host)]
+    one = ops.JsonDocs.from_texts(docs)
+    n, nbytes = one.n_docs, int(one.offsets[-1])
+    text = torch.cat([one.data[:nbytes].to(device).repeat(copies), torch.zeros(8, dtype=torch.uint8, device=device)])
+    lens = (one.offsets[1:] - one.offsets[:-1]).to(device).repeat(copies)
+    offsets = torch.zeros(n * copies + 1, dtype=torch.int64, device=device)
+    torch.cumsum(lens, 0, out=offsets[1:])
+    return ops.JsonDocs(offsets, text), host.n_entries * copies, nbytes * copies
+
+
+def main():
+    sample = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+    copies = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    dev = torch.device("cuda:0")
+    _lib.init(0)
+    t0 = time.time()
+    docs, n_entries, nbytes = replicated_docs(sample, copies, dev)
+    print(f"docs={docs.n_docs} entries={n_entries} text={nbytes / 1e9:.3f} GB (built in {time.time() - t0:.1f}s)", flush=True)
+    bufs = ops.IngestBuffers(docs.n_docs, dev)
+    ops.ingest_measure_dev(docs, bufs)
+    totals = bufs.totals.cpu().tolist()
+    assert bufs.status.cpu().tolist()[0] == 0
+    table = ops.alloc_ingest_table(docs.n_docs, totals, dev)
+    out_bytes = table.nbytes()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tm = tf = 0.0
+    for it in range(iters + 2):
+        ev[0].record()
+        ops.ingest_measure_dev(docs, bufs)
+        ev[1].record()
+        ops.ingest_fill_dev(docs, bufs, table)
+        ev[2].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            tm += ev[0].elapsed_time(ev[1])
+            tf += ev[1].elapsed_time(ev[2])
+    tm, tf = tm / iters, tf / iters
+    print(json.dumps({"docs": docs.n_docs, "entries": n_entries, "text_gb": nbytes / 1e9, "table_gb": out_bytes / 1e9,
+                      "measure_ms": tm, "fill_ms": tf, "total_ms": tm + tf,
+                      "text_gbs_measure": nbytes / tm / 1e6, "text_gbs_total": nbytes / (tm + tf) / 1e6,
+                      "algorithmic_gbs": (2 * nbytes + out_bytes) / (tm + tf) / 1e6,
+                      "entries_per_s": n_entries / (tm + tf) * 1e3}))
+
+
+if __name__ == "__main__":
+    main()

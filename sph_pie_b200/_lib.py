@@ -27,6 +27,13 @@ PIE_ERR_RANGE = -3
 PIE_ERR_UNSUPPORTED_DATE = -4
 PIE_ERR_CAPACITY = -5
 PIE_ERR_NO_DEVICE = -6
+PIE_ERR_SCHEMA = -7
+PIE_ERR_UNSUPPORTED_JSON = -8
+
+# JSON ingest: totals[0..22] = bytes of the string heaps in table order, then the row counts
+PIE_INGEST_HEAPS = 23
+PIE_IT_ENTRIES, PIE_IT_CREW_ITEMS, PIE_IT_ACTION_ITEMS = 23, 24, 25
+PIE_INGEST_TOTALS = 26
 
 # plane indices (include/sph_pie_b200.h)
 SI_TOTAL, SI_COMPLETED, SI_NO_LAUNCH, SI_ABORT, SI_LAUNCHED, SI_DELAY_COUNT = range(6)
@@ -63,6 +70,10 @@ class ArchiveViewC(C.Structure):
     )
 
 
+class JsonDocsC(C.Structure):
+    _fields_ = [("n_docs", C.c_int64), ("offsets", C.c_void_p), ("data", C.c_void_p)]
+
+
 class DailyOutC(C.Structure):
     _fields_ = [
         ("stride", C.c_int64),
@@ -91,6 +102,14 @@ class JsRangeError(PieError, ValueError):
 
 class UnsupportedDateError(PieError, NotImplementedError):
     """show.date/time is outside the ECMA-262 date-time grammar (V8 legacy parsing not provided)."""
+
+
+class SchemaError(PieError, TypeError):
+    """A stored document is not a provider-normalised show (what pack_shows raises TypeError for)."""
+
+
+class UnsupportedJsonError(PieError, ValueError):
+    """Valid JSON the ingest kernels decline to decide (duplicate known key, depth > 64, not UTF-8, undecided number)."""
 
 
 _lib = None
@@ -127,6 +146,14 @@ SIGNATURES = {
     "pie_debug_csv_slow_tiles": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32), C.c_void_p]),
     "pie_csv_rows_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64,
                                     C.POINTER(C.c_uint64)]),
+    "pie_ingest_scratch_bytes": (C.c_uint64, [C.c_int64]),
+    "pie_ingest_measure_dev": (C.c_int, [C.POINTER(JsonDocsC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
+    "pie_ingest_fill_dev": (C.c_int, [C.POINTER(JsonDocsC), C.c_void_p, C.c_void_p, C.POINTER(ArchiveViewC),
+                                      C.c_void_p]),
+    "pie_ingest_host": (C.c_int, [C.POINTER(JsonDocsC), C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_int64)]),
+    "pie_ingest_host_release": (None, []),
     "pie_archive_analytics_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                              C.POINTER(DailyOutC)]),
 }
@@ -163,6 +190,10 @@ def check(rc: int) -> None:
         raise JsRangeError(rc, msg)
     if rc == PIE_ERR_UNSUPPORTED_DATE:
         raise UnsupportedDateError(rc, msg)
+    if rc == PIE_ERR_SCHEMA:
+        raise SchemaError(rc, msg)
+    if rc == PIE_ERR_UNSUPPORTED_JSON:
+        raise UnsupportedJsonError(rc, msg)
     raise PieError(rc, msg)
 
 

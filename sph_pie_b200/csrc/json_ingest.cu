@@ -1,0 +1,317 @@
+// JSON ingest: the stored show documents (show_archive.data / shows.data, written by JSON.stringify at
+// server/storage/sqlProvider.js:682, :696) parsed on the GPU straight into the columnar archive table — what
+// `rows.map(row => this._mapArchiveRow(row)).filter(Boolean)` (sqlProvider.js:230-234, :892-926: JSON.parse, drop
+// what is not an object) followed by the projection on the table's schema (columnar.py pack_shows) does.
+//
+// A document is ~0.5 KB per entry of sequential grammar; 2^20 of them are independent.  So: ONE THREAD PER DOCUMENT
+// walks its text with a complete ECMA-404 recogniser (strings with every escape and UTF-8 validation, numbers,
+// literals, nesting checked against a 64-level kind stack), which costs ~0.3 warp-instructions per byte when the
+// lanes stay converged — cheaper than any warp-cooperative structural index at this document size.  The text is
+// read through the read-only path 8 aligned bytes at a time with the next word already in flight.
+//
+//   pass 1  ingest_measure_kernel   per document: entries, items of crew / actions, unescaped bytes of each of the 23
+//                                   string heaps; syntax errors make the document a dropped row (all counts zero)
+//   scan    ingest_scan_*           exclusive prefix sums of the 26 count planes over the documents, totals
+//   pass 2  ingest_fill_kernel      the same walk (same template) with every counter started at its prefix: offsets,
+//                                   unescaped bytes, numbers (pie_numparse.cuh, correctly rounded)
+//
+// Restrictions that fail loudly (pie_status in the status word, first offending document): a text field that is not
+// a string / null, delaySec that is not a number / null, a string with a lone surrogate escape (pack_shows raises
+// TypeError for these: the table holds provider-normalised documents); a known key twice in one object
+// (JSON.stringify never writes that; JSON.parse would keep the last); nesting deeper than 64; bytes that are not
+// UTF-8; a number the Eisel-Lemire parser cannot decide (> 19 significant digits on a rounding boundary).
+#include "pie_device.cuh"
+#include "pie_kernels.h"
+#include "pie_json_walk.cuh"
+
+namespace pie {
+
+namespace {
+
+using namespace jw;
+
+__device__ const uint64_t g_pow5_dev[PIE_POW5_128_N][2] = PIE_POW5_128_INIT;
+
+constexpr int kIngestThreads = 128;
+
+struct IngestScratch {
+  uint32_t* planes;          // [kPlanes][stride]: pass 1 counts, then exclusive prefixes
+  int64_t stride;
+  unsigned long long* block_sums;  // [kPlanes][nblk]
+  unsigned long long* err_key;     // min over documents of (doc << 8 | code): the first hard error
+};
+
+constexpr int kScanItems = 4;
+constexpr int kScanThreads = 1024;
+constexpr int kScanChunk = kScanItems * kScanThreads;
+
+__global__ void ingest_init_kernel(unsigned long long* err_key) { *err_key = ~0ull; }
+
+__global__ void __launch_bounds__(kIngestThreads) ingest_measure_kernel(const int64_t* __restrict__ doc_offsets,
+                                                                         const uint8_t* __restrict__ text, int64_t n_docs,
+                                                                         IngestScratch sc, uint8_t* __restrict__ doc_status) {
+  const int64_t s = (int64_t)blockIdx.x * kIngestThreads + threadIdx.x;
+  if (s >= n_docs) return;
+  uint32_t cnt[kPlanes];
+#pragma unroll
+  for (int p = 0; p < kPlanes; ++p) cnt[p] = 0;
+  DocCursor c;
+  c.open(text, doc_offsets[s], doc_offsets[s + 1]);
+  IngestOut none{};
+  const int r = walk_document<false>(c, cnt, none, s, Pow5Table{g_pow5_dev});
+  if (r != kDocOk) {
+#pragma unroll
+    for (int p = 0; p < kPlanes; ++p) cnt[p] = 0;
+    if (r != kDocDropped) atomicMin(sc.err_key, ((unsigned long long)s << 8) | (unsigned long long)r);
+  }
+  doc_status[s] = r == kDocOk ? 0 : 1;
+#pragma unroll
+  for (int p = 0; p < kPlanes; ++p) sc.planes[p * sc.stride + s] = cnt[p];
+}
+
+// exclusive scan of every plane over the documents: chunk sums, scan of the chunk sums (one CTA per plane), then the
+// chunks in place
+__global__ void __launch_bounds__(kScanThreads) ingest_scan_sums_kernel(IngestScratch sc, int64_t n, int nblk) {
+  const int p = blockIdx.y;
+  const uint32_t* x = sc.planes + p * sc.stride;
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+  unsigned long long v = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + k * kScanThreads + threadIdx.x;
+    if (i < n) v += x[i];
+  }
+  __shared__ unsigned long long warp_sums[32];
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = warp_sums[threadIdx.x];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0) sc.block_sums[(int64_t)p * nblk + blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(1024) ingest_scan_blocks_kernel(IngestScratch sc, int nblk, int64_t* __restrict__ totals,
+                                                                   int32_t* __restrict__ status) {
+  const int p = blockIdx.x;
+  unsigned long long* b = sc.block_sums + (int64_t)p * nblk;
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + threadIdx.x;
+    const unsigned long long x = i < nblk ? b[i] : 0;
+    unsigned long long v = x;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, v, d);
+      if ((threadIdx.x & 31) >= d) v += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      unsigned long long ws = warp_sums[threadIdx.x];
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, ws, d);
+        if (threadIdx.x >= d) ws += t;
+      }
+      warp_sums[threadIdx.x] = ws;
+    }
+    __syncthreads();
+    const unsigned long long before = carry + ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + v - x;
+    if (i < nblk) b[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    totals[p] = (int64_t)carry;
+    // offsets are int32: a heap or a row count of 2 GiB and more does not fit (split the batch)
+    if (carry > 0x7fffffffull) atomicMin(sc.err_key, (0xffffffffffull << 8) | (unsigned long long)(-PIE_ERR_CAPACITY));
+  }
+  // the status word, once every plane is through (the last CTA to get here writes it)
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    // block_sums[kPlanes * nblk] doubles as the arrival counter
+    last = atomicAdd(sc.block_sums + (int64_t)kPlanes * nblk, 1ull) == (unsigned long long)(gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long k = atomicAdd(sc.err_key, 0ull);
+    if (k == ~0ull) {
+      status[0] = 0;
+      status[1] = -1;
+    } else {
+      status[0] = -(int32_t)(k & 0xff);
+      const unsigned long long doc = k >> 8;
+      status[1] = doc >= 0x7fffffffull ? -1 : (int32_t)doc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) ingest_scan_apply_kernel(IngestScratch sc, int64_t n, int nblk) {
+  const int p = blockIdx.y;
+  uint32_t* x = sc.planes + p * sc.stride;
+  const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
+  uint32_t item[kScanItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    item[k] = base + k < n ? x[base + k] : 0;
+    sum += item[k];
+  }
+  uint32_t v = sum;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) >= d) v += t;
+  }
+  __shared__ uint32_t warp_sums[32];
+  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t ws = warp_sums[threadIdx.x];
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, ws, d);
+      if (threadIdx.x >= d) ws += t;
+    }
+    warp_sums[threadIdx.x] = ws;
+  }
+  __syncthreads();
+  uint32_t run = (uint32_t)sc.block_sums[(int64_t)p * nblk + blockIdx.x] + ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0) +
+                 v - sum;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) x[base + k] = run;
+    run += item[k];
+  }
+}
+
+__global__ void __launch_bounds__(kIngestThreads) ingest_fill_kernel(const int64_t* __restrict__ doc_offsets,
+                                                                      const uint8_t* __restrict__ text, int64_t n_docs,
+                                                                      IngestScratch sc, const uint8_t* __restrict__ doc_status,
+                                                                      IngestOut out) {
+  const int64_t s = (int64_t)blockIdx.x * kIngestThreads + threadIdx.x;
+  if (n_docs == 0) {  // the terminal offsets of an empty table
+    if (s == 0) {
+      for (int h = 0; h < kHeaps; ++h) out.off[h][0] = 0;
+      out.entry_offsets[0] = 0;
+      out.crew_list[0] = 0;
+      out.actions_list[0] = 0;
+    }
+    return;
+  }
+  if (s >= n_docs) return;
+  uint32_t cnt[kPlanes];
+#pragma unroll
+  for (int p = 0; p < kPlanes; ++p) cnt[p] = sc.planes[p * sc.stride + s];
+  // the show's row: every text field starts where the previous show's ended (an absent key is '')
+#pragma unroll
+  for (int h = 0; h < 7; ++h) out.off[h][s] = (int32_t)cnt[h];
+  out.entry_offsets[s] = (int32_t)cnt[kPlaneEntries];
+  out.crew_list[s] = (int32_t)cnt[kPlaneCrewItems];
+  out.created_at[s] = jw_nan();
+  out.archived_at[s] = jw_nan();
+  if (doc_status[s] == 0) {
+    DocCursor c;
+    c.open(text, doc_offsets[s], doc_offsets[s + 1]);
+    walk_document<true>(c, cnt, out, s, Pow5Table{g_pow5_dev});
+  }
+  if (s == n_docs - 1) {  // the terminal offsets: where the last document ended
+#pragma unroll
+    for (int h = 0; h < 7; ++h) out.off[h][n_docs] = (int32_t)cnt[h];
+    out.entry_offsets[n_docs] = (int32_t)cnt[kPlaneEntries];
+    out.crew_list[n_docs] = (int32_t)cnt[kPlaneCrewItems];
+    out.off[kHeapCrew][cnt[kPlaneCrewItems]] = (int32_t)cnt[kHeapCrew];
+    const uint32_t rows = cnt[kPlaneEntries];
+#pragma unroll
+    for (int h = kHeapEntry0; h < kHeapEntry0 + 14; ++h) out.off[h][rows] = (int32_t)cnt[h];
+    out.actions_list[rows] = (int32_t)cnt[kPlaneActionItems];
+    out.off[kHeapActions][cnt[kPlaneActionItems]] = (int32_t)cnt[kHeapActions];
+  }
+}
+
+int scan_blocks(int64_t n_docs) { return (int)((n_docs + kScanChunk - 1) / kScanChunk) + (n_docs == 0 ? 1 : 0); }
+
+IngestScratch carve(void* scratch, int64_t n_docs) {
+  IngestScratch sc;
+  const int64_t stride = ((n_docs > 0 ? n_docs : 1) + 31) & ~(int64_t)31;
+  uint8_t* p = (uint8_t*)scratch;
+  sc.planes = (uint32_t*)p;
+  sc.stride = stride;
+  p += (uint64_t)kPlanes * stride * 4;
+  sc.block_sums = (unsigned long long*)p;
+  p += ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8;
+  sc.err_key = (unsigned long long*)p;
+  return sc;
+}
+
+IngestOut make_out(const pie_archive_table& t) {
+  IngestOut o;
+  const pie_strcol_mut* show_cols[7] = {&t.show_id, &t.show_date, &t.show_time, &t.show_label, &t.lead_pilot, &t.monkey_lead,
+                                        &t.show_notes};
+  const pie_strcol_mut* entry_cols[14] = {&t.entry_id, &t.unit_id, &t.planned, &t.launched, &t.status, &t.primary_issue,
+                                          &t.sub_issue, &t.other_detail, &t.severity, &t.root_cause, &t.operator_name,
+                                          &t.battery_id, &t.command_rx, &t.notes};
+  for (int h = 0; h < 7; ++h) { o.off[h] = show_cols[h]->offsets; o.data[h] = show_cols[h]->data; }
+  o.off[kHeapCrew] = t.crew.items.offsets;
+  o.data[kHeapCrew] = t.crew.items.data;
+  for (int h = 0; h < 14; ++h) { o.off[kHeapEntry0 + h] = entry_cols[h]->offsets; o.data[kHeapEntry0 + h] = entry_cols[h]->data; }
+  o.off[kHeapActions] = t.actions.items.offsets;
+  o.data[kHeapActions] = t.actions.items.data;
+  o.entry_offsets = t.entry_offsets;
+  o.crew_list = t.crew.list_offsets;
+  o.actions_list = t.actions.list_offsets;
+  o.created_at = t.created_at;
+  o.archived_at = t.archived_at;
+  o.delay_sec = t.delay_sec;
+  o.delay_valid = t.delay_valid;
+  o.entry_ts = t.entry_ts;
+  return o;
+}
+
+}  // namespace
+
+uint64_t ingest_scratch_bytes(int64_t n_docs) {
+  const int64_t stride = ((n_docs > 0 ? n_docs : 1) + 31) & ~(int64_t)31;
+  return (uint64_t)kPlanes * stride * 4 + ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8 + 64;
+}
+
+cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint8_t* doc_status, int64_t* totals,
+                                  int32_t* status, cudaStream_t stream) {
+  const int64_t n = docs.n_docs;
+  IngestScratch sc = carve(scratch, n);
+  const int nblk = scan_blocks(n);
+  cudaError_t e = cudaMemsetAsync(sc.block_sums, 0, ((uint64_t)kPlanes * nblk + 1) * 8, stream);
+  if (e != cudaSuccess) return e;
+  ingest_init_kernel<<<1, 1, 0, stream>>>(sc.err_key);
+  ++g_launches;
+  if (n > 0) {
+    ingest_measure_kernel<<<(unsigned)((n + kIngestThreads - 1) / kIngestThreads), kIngestThreads, 0, stream>>>(
+        docs.offsets, docs.data, n, sc, doc_status);
+    ingest_scan_sums_kernel<<<dim3(nblk, kPlanes), kScanThreads, 0, stream>>>(sc, n, nblk);
+    g_launches += 2;
+  }
+  ingest_scan_blocks_kernel<<<kPlanes, 1024, 0, stream>>>(sc, nblk, totals, status);
+  ++g_launches;
+  if (n > 0) {
+    ingest_scan_apply_kernel<<<dim3(nblk, kPlanes), kScanThreads, 0, stream>>>(sc, n, nblk);
+    ++g_launches;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ingest_fill(const pie_json_docs& docs, const void* scratch, const uint8_t* doc_status,
+                               const pie_archive_table& table, cudaStream_t stream) {
+  const int64_t n = docs.n_docs;
+  IngestScratch sc = carve(const_cast<void*>(scratch), n);
+  const int64_t threads = n > 0 ? n : 1;
+  ingest_fill_kernel<<<(unsigned)((threads + kIngestThreads - 1) / kIngestThreads), kIngestThreads, 0, stream>>>(
+      docs.offsets, docs.data, n, sc, doc_status, make_out(table));
+  ++g_launches;
+  return cudaGetLastError();
+}
+
+}  // namespace pie

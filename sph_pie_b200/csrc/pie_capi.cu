@@ -865,6 +865,185 @@ int pie_archive_payloads_host(const pie_archive_view* hv, int64_t* row_offsets, 
   return export_rows_host(kFormatPayload, hv, row_offsets, out_data, out_capacity, total_bytes);
 }
 
+/* ---- JSON ingest ---------------------------------------------------------------------------------------- */
+uint64_t pie_ingest_scratch_bytes(int64_t n_docs) { return pie::ingest_scratch_bytes(n_docs > 0 ? n_docs : 0); }
+
+static int check_docs(const pie_json_docs* d) {
+  if (!d) return fail(PIE_ERR_INVALID_ARG, "docs is NULL");
+  if (d->n_docs < 0 || d->n_docs > 0x7FFFFFF0LL) return fail(PIE_ERR_INVALID_ARG, "n_docs out of range (batches of < 2^31 documents)");
+  if (!d->offsets) return fail(PIE_ERR_INVALID_ARG, "docs.offsets is NULL");
+  return PIE_OK;
+}
+
+int pie_ingest_measure_dev(const pie_json_docs* d, void* scratch, uint8_t* doc_status, int64_t* totals_dev,
+                           int32_t* status_dev, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_docs(d))) return rc;
+  if (!scratch || !doc_status || !totals_dev || !status_dev) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  if (d->n_docs > 0 && !d->data) return fail(PIE_ERR_INVALID_ARG, "docs.data is NULL");
+  if (reinterpret_cast<uintptr_t>(scratch) & 7) return fail(PIE_ERR_INVALID_ARG, "scratch must be 8-byte aligned");
+  PIE_CUDA(pie::launch_ingest_measure(*d, scratch, doc_status, totals_dev, status_dev, (cudaStream_t)stream));
+  return PIE_OK;
+}
+
+static int check_table(const pie_archive_table* t) {
+  if (!t) return fail(PIE_ERR_INVALID_ARG, "table is NULL");
+  const pie_strcol_mut* cols[23] = {&t->show_id, &t->show_date, &t->show_time, &t->show_label, &t->lead_pilot, &t->monkey_lead,
+                                    &t->show_notes, &t->crew.items, &t->entry_id, &t->unit_id, &t->planned, &t->launched,
+                                    &t->status, &t->primary_issue, &t->sub_issue, &t->other_detail, &t->severity, &t->root_cause,
+                                    &t->operator_name, &t->battery_id, &t->command_rx, &t->notes, &t->actions.items};
+  for (int i = 0; i < 23; ++i)
+    if (!cols[i]->offsets || !cols[i]->data) return fail(PIE_ERR_INVALID_ARG, "table: string column %d has a NULL pointer", i);
+  if (!t->entry_offsets || !t->crew.list_offsets || !t->actions.list_offsets || !t->created_at || !t->archived_at ||
+      !t->delay_sec || !t->delay_valid || !t->entry_ts)
+    return fail(PIE_ERR_INVALID_ARG, "table: a NULL column");
+  return PIE_OK;
+}
+
+int pie_ingest_fill_dev(const pie_json_docs* d, const void* scratch, const uint8_t* doc_status, const pie_archive_table* t,
+                        void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_docs(d))) return rc;
+  if ((rc = check_table(t))) return rc;
+  if (!scratch || !doc_status) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  PIE_CUDA(pie::launch_ingest_fill(*d, scratch, doc_status, *t, (cudaStream_t)stream));
+  return PIE_OK;
+}
+
+namespace {
+OutBuffer g_ingest_out;           // the device image of the table
+uint8_t* g_ingest_host = nullptr; // its pinned host image (what pie_ingest_host hands out)
+uint64_t g_ingest_host_cap = 0;
+
+// lays the table out in one block (the same on the device and on the host): returns the block size
+uint64_t layout_table(pie_archive_table* t, uint8_t* base, int64_t n_docs, const int64_t* totals) {
+  uint64_t off = 0;
+  auto take = [&](uint64_t bytes) {
+    uint8_t* p = base + off;
+    off += (bytes + 255) & ~(uint64_t)255;
+    return p;
+  };
+  const int64_t E = totals[PIE_IT_ENTRIES];
+  pie_strcol_mut* show_cols[7] = {&t->show_id, &t->show_date, &t->show_time, &t->show_label, &t->lead_pilot, &t->monkey_lead,
+                                  &t->show_notes};
+  pie_strcol_mut* entry_cols[14] = {&t->entry_id, &t->unit_id, &t->planned, &t->launched, &t->status, &t->primary_issue,
+                                    &t->sub_issue, &t->other_detail, &t->severity, &t->root_cause, &t->operator_name,
+                                    &t->battery_id, &t->command_rx, &t->notes};
+  t->n_shows = n_docs;
+  t->n_entries = E;
+  t->entry_offsets = (int32_t*)take(4 * (uint64_t)(n_docs + 1));
+  for (int h = 0; h < 7; ++h) {
+    show_cols[h]->offsets = (int32_t*)take(4 * (uint64_t)(n_docs + 1));
+    show_cols[h]->data = take((uint64_t)totals[h] + 8);
+  }
+  t->crew.list_offsets = (int32_t*)take(4 * (uint64_t)(n_docs + 1));
+  t->crew.items.offsets = (int32_t*)take(4 * (uint64_t)(totals[PIE_IT_CREW_ITEMS] + 1));
+  t->crew.items.data = take((uint64_t)totals[7] + 8);
+  t->created_at = (double*)take(8 * (uint64_t)(n_docs + 1));
+  t->archived_at = (double*)take(8 * (uint64_t)(n_docs + 1));
+  for (int h = 0; h < 14; ++h) {
+    entry_cols[h]->offsets = (int32_t*)take(4 * (uint64_t)(E + 1));
+    entry_cols[h]->data = take((uint64_t)totals[8 + h] + 8);
+  }
+  t->actions.list_offsets = (int32_t*)take(4 * (uint64_t)(E + 1));
+  t->actions.items.offsets = (int32_t*)take(4 * (uint64_t)(totals[PIE_IT_ACTION_ITEMS] + 1));
+  t->actions.items.data = take((uint64_t)totals[22] + 8);
+  t->delay_sec = (double*)take(8 * (uint64_t)(E + 1));
+  t->delay_valid = take((uint64_t)E + 8);
+  t->entry_ts = (double*)take(8 * (uint64_t)(E + 1));
+  return off;
+}
+}  // namespace
+
+void pie_ingest_host_release(void) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (g_ingest_host) cudaFreeHost(g_ingest_host);
+  g_ingest_host = nullptr;
+  g_ingest_host_cap = 0;
+}
+
+int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint8_t* doc_status, int64_t* totals_out,
+                    int64_t* bad_doc) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (bad_doc) *bad_doc = -1;
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_docs(hd))) return rc;
+  if (!host_table) return fail(PIE_ERR_INVALID_ARG, "host_table is NULL");
+  const int64_t n = hd->n_docs;
+  if (n > 0 && !doc_status) return fail(PIE_ERR_INVALID_ARG, "doc_status is NULL");
+  const int64_t first = hd->offsets[0], last = hd->offsets[n];
+  if (first < 0 || last < first) return fail(PIE_ERR_INVALID_ARG, "docs.offsets must ascend from a non-negative value");
+  if (last > first && !hd->data) return fail(PIE_ERR_INVALID_ARG, "docs.data is NULL");
+  for (int64_t s = 0; s < n; ++s) {
+    const int64_t len = hd->offsets[s + 1] - hd->offsets[s];
+    if (len < 0) return fail(PIE_ERR_INVALID_ARG, "docs.offsets decrease at document %lld", (long long)s);
+    if (len >= 0x7FFFFFF0LL) return fail(PIE_ERR_INVALID_ARG, "document %lld is 2 GiB or more", (long long)s);
+  }
+  const uint64_t text_bytes = (uint64_t)(last - first);
+  const uint64_t scratch_bytes = pie::ingest_scratch_bytes(n);
+  uint64_t bytes = pad(8 * (uint64_t)(n + 1)) + pad(text_bytes + 16) + pad(scratch_bytes) + pad((uint64_t)n + 1) + pad(8 * PIE_INGEST_TOTALS) +
+                   pad(8);
+  if ((rc = g_arena.reserve(bytes))) return rc;
+  cudaStream_t st = g_arena.stream;
+  g_cur = &g_arena;
+  g_cur_stream = st;
+  uint64_t h2d = 0, d2h = 0;
+  pie_json_docs dd;
+  dd.n_docs = n;
+  const int64_t* d_off = nullptr;
+  if ((rc = upload_array(hd->offsets, n + 1, &d_off, &h2d))) return rc;
+  dd.offsets = d_off;
+  // the text keeps its host offsets; its first byte lands 8-byte aligned, like every document start the cursor aligns down to
+  uint8_t* d_text = (uint8_t*)g_arena.take(text_bytes + 16);
+  const uint64_t skew = (uint64_t)first & 7;
+  if (text_bytes) PIE_CUDA(cudaMemcpyAsync(d_text + skew, hd->data + first, text_bytes, cudaMemcpyHostToDevice, st));
+  h2d += text_bytes;
+  dd.data = d_text + skew - first;
+  void* d_scratch = g_arena.take(scratch_bytes);
+  uint8_t* d_status_bytes = (uint8_t*)g_arena.take((uint64_t)n + 1);
+  int64_t* d_totals = (int64_t*)g_arena.take(8 * PIE_INGEST_TOTALS);
+  int32_t* d_status = (int32_t*)g_arena.take(8);
+  PIE_CUDA(pie::launch_ingest_measure(dd, d_scratch, d_status_bytes, d_totals, d_status, st));
+  int64_t totals[PIE_INGEST_TOTALS];
+  int32_t status[2];
+  PIE_CUDA(cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+  PIE_CUDA(cudaMemcpyAsync(status, d_status, sizeof(status), cudaMemcpyDeviceToHost, st));
+  if (n > 0) PIE_CUDA(cudaMemcpyAsync(doc_status, d_status_bytes, (uint64_t)n, cudaMemcpyDeviceToHost, st));
+  PIE_CUDA(cudaStreamSynchronize(st));
+  d2h += sizeof(totals) + sizeof(status) + (uint64_t)n;
+  g_last_h2d = h2d;
+  g_last_d2h = d2h;
+  if (totals_out) memcpy(totals_out, totals, sizeof(totals));
+  if (status[0] != 0) {
+    if (bad_doc) *bad_doc = status[1];
+    const char* what = status[0] == PIE_ERR_SCHEMA ? "is not a provider-normalised show"
+                       : status[0] == PIE_ERR_UNSUPPORTED_JSON ? "is JSON the ingest kernels do not decide"
+                                                               : "makes a heap or row count reach 2 GiB: split the batch";
+    return fail(status[0], "document %d %s", status[1], what);
+  }
+  pie_archive_table dt, ht;
+  const uint64_t block = layout_table(&dt, nullptr, n, totals);
+  if ((rc = g_ingest_out.ensure(block ? block : 256))) return rc;
+  layout_table(&dt, g_ingest_out.base, n, totals);
+  if (block > g_ingest_host_cap) {
+    if (g_ingest_host) cudaFreeHost(g_ingest_host);
+    g_ingest_host = nullptr;
+    g_ingest_host_cap = 0;
+    PIE_CUDA(cudaHostAlloc((void**)&g_ingest_host, block, cudaHostAllocDefault));
+    g_ingest_host_cap = block;
+  }
+  layout_table(&ht, g_ingest_host, n, totals);
+  PIE_CUDA(pie::launch_ingest_fill(dd, d_scratch, d_status_bytes, dt, st));
+  PIE_CUDA(cudaMemcpyAsync(g_ingest_host, g_ingest_out.base, block, cudaMemcpyDeviceToHost, st));
+  PIE_CUDA(cudaStreamSynchronize(st));
+  g_last_d2h = d2h + block;
+  *host_table = ht;
+  return PIE_OK;
+}
+
 int pie_selftest_fast_div(int32_t max_b, uint64_t* mismatches) {
   int rc = ensure_init();
   if (rc) return rc;

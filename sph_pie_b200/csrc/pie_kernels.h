@@ -36,6 +36,13 @@ cudaError_t csv_read_slow_tiles(const void* scratch, int64_t n_entries, unsigned
 cudaError_t launch_compute_metrics(const pie_archive_view& dev_view, int32_t* metrics_i32, uint8_t* avg_delay_text,
                                    int64_t stride, cudaStream_t stream);
 
+// json_ingest.cu: stored show documents -> the columnar table, two walks (measure, scan, fill)
+uint64_t ingest_scratch_bytes(int64_t n_docs);
+cudaError_t launch_ingest_measure(const pie_json_docs& dev_docs, void* scratch, uint8_t* doc_status, int64_t* totals,
+                                  int32_t* status, cudaStream_t stream);
+cudaError_t launch_ingest_fill(const pie_json_docs& dev_docs, const void* scratch, const uint8_t* doc_status,
+                               const pie_archive_table& dev_table, cudaStream_t stream);
+
 // archive_daily.cu
 uint64_t daily_scratch_bytes(int64_t n_shows);
 cudaError_t launch_daily_summary(const pie_archive_view& dev_view, const int32_t* stats_i32,

@@ -104,61 +104,78 @@ PIE_NP_HD bool eisel_lemire(uint64_t w, int64_t q, const Pow5Table& tab, uint64_
   return true;
 }
 
-// Parses a JSON number (ECMA-404: -? (0 | [1-9][0-9]*) (. [0-9]+)? ([eE] [+-]? [0-9]+)?) at s[0..n) and returns how
-// many bytes it took in *used (the caller checks what follows).  *value receives the correctly rounded double.
-PIE_NP_HD int parse_json_number(const uint8_t* s, int64_t n, const Pow5Table& tab, double* value, int64_t* used) {
-  int64_t i = 0;
+// Byte source over memory (the ingest kernel has its own, register-buffered one): peek() is the current byte or -1 at
+// the end, next() steps over it.
+struct MemSource {
+  const uint8_t* s;
+  int64_t n, i;
+  PIE_NP_HD int peek() const { return i < n ? (int)s[i] : -1; }
+  PIE_NP_HD void next() { ++i; }
+};
+
+PIE_NP_HD bool np_is_digit(int c) { return (unsigned)(c - '0') <= 9u; }
+
+// Parses a JSON number (ECMA-404: -? (0 | [1-9][0-9]*) (. [0-9]+)? ([eE] [+-]? [0-9]+)?) from `src`, which is left on
+// the first byte that is not part of the number (the caller checks what follows).  *value receives the correctly
+// rounded double.  kCompute = false only checks the grammar (values the caller throws away).
+template <bool kCompute, class Src>
+PIE_NP_HD int parse_json_number_from(Src& src, const Pow5Table& tab, double* value) {
   bool neg = false;
-  if (i < n && s[i] == '-') { neg = true; ++i; }
-  if (i >= n || s[i] < '0' || s[i] > '9') return kNumSyntax;
+  if (src.peek() == '-') { neg = true; src.next(); }
+  if (!np_is_digit(src.peek())) return kNumSyntax;
   uint64_t w = 0;       // up to 19 significant digits
   int digits = 0;       // significant digits taken into w
   int64_t exp10 = 0;    // value = w * 10^exp10 (before the explicit exponent)
   bool dropped_nonzero = false;
-  if (s[i] == '0') {
-    ++i;
-    if (i < n && s[i] >= '0' && s[i] <= '9') return kNumSyntax;  // no leading zeros
+  if (src.peek() == '0') {
+    src.next();
+    if (np_is_digit(src.peek())) return kNumSyntax;  // no leading zeros
   } else {
-    for (; i < n && s[i] >= '0' && s[i] <= '9'; ++i) {
-      if (digits < 19) { w = w * 10 + (uint64_t)(s[i] - '0'); ++digits; }
-      else { ++exp10; dropped_nonzero |= (s[i] != '0'); }
+    for (int c = src.peek(); np_is_digit(c); src.next(), c = src.peek()) {
+      if (!kCompute) continue;
+      if (digits < 19) { w = w * 10 + (uint64_t)(c - '0'); ++digits; }
+      else { if (exp10 < 1000000) ++exp10; dropped_nonzero |= (c != '0'); }
     }
   }
-  if (i < n && s[i] == '.') {
-    ++i;
-    if (i >= n || s[i] < '0' || s[i] > '9') return kNumSyntax;
-    for (; i < n && s[i] >= '0' && s[i] <= '9'; ++i) {
+  if (src.peek() == '.') {
+    src.next();
+    if (!np_is_digit(src.peek())) return kNumSyntax;
+    for (int c = src.peek(); np_is_digit(c); src.next(), c = src.peek()) {
+      if (!kCompute) continue;
       if (digits < 19) {
-        if (w != 0 || s[i] != '0') { w = w * 10 + (uint64_t)(s[i] - '0'); ++digits; }  // leading zeros are not significant
-        --exp10;
+        if (w != 0 || c != '0') { w = w * 10 + (uint64_t)(c - '0'); ++digits; }  // leading zeros are not significant
+        if (exp10 > -1000000) --exp10;
       } else {
-        dropped_nonzero |= (s[i] != '0');
+        dropped_nonzero |= (c != '0');
       }
     }
   }
-  if (i < n && (s[i] == 'e' || s[i] == 'E')) {
-    ++i;
+  if (src.peek() == 'e' || src.peek() == 'E') {
+    src.next();
     bool eneg = false;
-    if (i < n && (s[i] == '+' || s[i] == '-')) { eneg = s[i] == '-'; ++i; }
-    if (i >= n || s[i] < '0' || s[i] > '9') return kNumSyntax;
+    if (src.peek() == '+' || src.peek() == '-') { eneg = src.peek() == '-'; src.next(); }
+    if (!np_is_digit(src.peek())) return kNumSyntax;
     int64_t e = 0;
-    for (; i < n && s[i] >= '0' && s[i] <= '9'; ++i)
-      if (e < 100000) e = e * 10 + (s[i] - '0');  // saturates: anything this large over- or underflows anyway
+    for (int c = src.peek(); np_is_digit(c); src.next(), c = src.peek())
+      if (e < 10000000) e = e * 10 + (c - '0');  // saturates: anything this large over- or underflows anyway
     exp10 += eneg ? -e : e;
   }
-  *used = i;
+  if (!kCompute) return kNumOk;
   const uint64_t sign = neg ? 0x8000000000000000ull : 0;
   if (w == 0) { *value = np_bits_to_double(sign); return kNumOk; }
-  if (!dropped_nonzero && w < (1ull << 53)) {
-    // one IEEE operation on exact operands is correctly rounded
-    const double p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
-                            1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
-    if (exp10 >= -22 && exp10 <= 22) {
-      double d = (double)w;
-      d = exp10 < 0 ? d / p10[-exp10] : d * p10[exp10];
-      *value = neg ? -d : d;
-      return kNumOk;
-    }
+  if (!dropped_nonzero && w < (1ull << 53) && exp10 >= -22 && exp10 <= 22) {
+    // one IEEE operation on exact operands is correctly rounded (the powers up to 10^22 are exact doubles)
+    double p = 1.0;
+    const int64_t a = exp10 < 0 ? -exp10 : exp10;
+    if (a & 1) p *= 1e1;
+    if (a & 2) p *= 1e2;
+    if (a & 4) p *= 1e4;
+    if (a & 8) p *= 1e8;
+    if (a & 16) p *= 1e16;
+    double d = (double)w;
+    d = exp10 < 0 ? d / p : d * p;
+    *value = neg ? -d : d;
+    return kNumOk;
   }
   uint64_t bits;
   if (!eisel_lemire(w, exp10, tab, &bits)) return kNumUndecided;
@@ -168,6 +185,14 @@ PIE_NP_HD int parse_json_number(const uint8_t* s, int64_t n, const Pow5Table& ta
   }
   *value = np_bits_to_double(bits | sign);
   return kNumOk;
+}
+
+// The same over s[0..n): *used = how many bytes the number took.
+PIE_NP_HD int parse_json_number(const uint8_t* s, int64_t n, const Pow5Table& tab, double* value, int64_t* used) {
+  MemSource src{s, n, 0};
+  const int rc = parse_json_number_from<true>(src, tab, value);
+  *used = src.i;
+  return rc;
 }
 
 }  // namespace pie

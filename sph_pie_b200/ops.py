@@ -308,3 +308,165 @@ def archive_step(table: ArchiveTable, tz_offset_minutes: int = 0, out: "HostOutp
             DailySummary(G, h.show_day_start[:S], h.show_order[:S], h.group_day_start[:G], h.group_offsets[:G + 1],
                          h.summary_f64[:, :, :G], h.summary_count[:, :G]),
             CsvRows(row_offsets, data[:int(total.value)]))
+
+
+# ---- JSON ingest: stored show documents -> archive table (pie_ingest_*) ---------------------------------------
+@dataclass
+class JsonDocs:
+    """The `data` texts of a batch of rows (show_archive.data, sqlProvider.js:696): document s is
+    data[offsets[s] : offsets[s+1]] (UTF-8 JSON).  Tensors on the CPU (pinned or not) or on the GPU."""
+    offsets: torch.Tensor  # int64 [n + 1]
+    data: torch.Tensor     # uint8
+
+    @property
+    def n_docs(self) -> int:
+        return self.offsets.numel() - 1
+
+    @property
+    def is_cuda(self) -> bool:
+        return self.data.is_cuda
+
+    def to(self, device, non_blocking=False) -> "JsonDocs":
+        return JsonDocs(self.offsets.to(device, non_blocking=non_blocking), self.data.to(device, non_blocking=non_blocking))
+
+    def pin(self) -> "JsonDocs":
+        return JsonDocs(self.offsets.pin_memory(), self.data.pin_memory())
+
+    def c(self) -> _lib.JsonDocsC:
+        return _lib.JsonDocsC(self.n_docs, self.offsets.data_ptr(), self.data.data_ptr())
+
+    @staticmethod
+    def from_texts(texts) -> "JsonDocs":
+        import numpy as np
+
+        enc = [t.encode("utf-8") if isinstance(t, str) else bytes(t) for t in texts]
+        offs = np.zeros(len(enc) + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in enc], out=offs[1:])
+        data = np.zeros(int(offs[-1]) + 8, dtype=np.uint8)  # +8: never an empty tensor
+        data[:offs[-1]] = np.frombuffer(b"".join(enc), dtype=np.uint8)
+        return JsonDocs(torch.from_numpy(offs), torch.from_numpy(data))
+
+
+def alloc_ingest_table(n_docs: int, totals, device) -> ArchiveTable:
+    """An archive table with exactly the room pie_ingest_measure_* counted (totals[PIE_INGEST_TOTALS])."""
+    from .columnar import StrCol, StrListCol
+
+    E, crew_items, action_items = (int(totals[_lib.PIE_IT_ENTRIES]), int(totals[_lib.PIE_IT_CREW_ITEMS]),
+                                   int(totals[_lib.PIE_IT_ACTION_ITEMS]))
+
+    def col(rows, heap):
+        return StrCol(torch.empty(rows + 1, dtype=torch.int32, device=device),
+                      torch.empty(int(totals[heap]) + 8, dtype=torch.uint8, device=device))
+
+    f64 = lambda n: torch.empty(n, dtype=torch.float64, device=device)
+    i32 = lambda n: torch.empty(n, dtype=torch.int32, device=device)
+    return ArchiveTable(
+        n_shows=n_docs, n_entries=E, entry_offsets=i32(n_docs + 1),
+        show_cols={name: col(n_docs, h) for h, name in enumerate(_lib.SHOW_STR_COLS)},
+        crew=StrListCol(i32(n_docs + 1), col(crew_items, 7)),
+        created_at=f64(n_docs), archived_at=f64(n_docs),
+        entry_cols={name: col(E, 8 + h) for h, name in enumerate(_lib.ENTRY_STR_COLS)},
+        actions=StrListCol(i32(E + 1), col(action_items, 22)),
+        delay_sec=f64(E), delay_valid=torch.empty(E, dtype=torch.uint8, device=device), entry_ts=f64(E))
+
+
+def _raise_ingest_status(code: int, doc: int) -> None:
+    if code == 0:
+        return
+    what = {_lib.PIE_ERR_SCHEMA: "is not a provider-normalised show (a text field that is not a string, delaySec that "
+                                 "is not a number, or a lone surrogate)",
+            _lib.PIE_ERR_UNSUPPORTED_JSON: "is JSON the ingest path does not decide (duplicate known key, nesting "
+                                           "deeper than 64, not UTF-8, or a number on a rounding boundary)",
+            _lib.PIE_ERR_CAPACITY: "a string heap or row count reaches 2 GiB: split the batch"}.get(code, "failed")
+    cls = {_lib.PIE_ERR_SCHEMA: _lib.SchemaError, _lib.PIE_ERR_UNSUPPORTED_JSON: _lib.UnsupportedJsonError}.get(
+        code, _lib.PieError)
+    err = cls(code, (f"document {doc} " if doc >= 0 else "") + what)
+    err.doc = doc
+    raise err
+
+
+class IngestBuffers:
+    """Scratch and small outputs of the two ingest calls for up to n_docs documents (reused across calls)."""
+
+    def __init__(self, n_docs: int, device):
+        lib = _lib.load()
+        self.scratch = torch.empty(int(lib.pie_ingest_scratch_bytes(n_docs)), dtype=torch.uint8, device=device)
+        self.doc_status = torch.empty(max(n_docs, 1), dtype=torch.uint8, device=device)
+        self.totals = torch.zeros(_lib.PIE_INGEST_TOTALS, dtype=torch.int64, device=device)
+        self.status = torch.zeros(2, dtype=torch.int32, device=device)
+
+
+def ingest_measure_dev(docs: JsonDocs, bufs: IngestBuffers) -> None:
+    """First walk + scans on torch's current stream (no sync): bufs.totals / bufs.status / bufs.doc_status."""
+    _lib.ensure_init()
+    d = docs.c()
+    _lib.check(_lib.load().pie_ingest_measure_dev(C.byref(d), bufs.scratch.data_ptr(), bufs.doc_status.data_ptr(),
+                                                  bufs.totals.data_ptr(), bufs.status.data_ptr(), _stream_ptr()))
+
+
+def ingest_fill_dev(docs: JsonDocs, bufs: IngestBuffers, table: ArchiveTable) -> None:
+    """Second walk on torch's current stream (no sync) into a table allocated from bufs.totals."""
+    d = docs.c()
+    view = table.view()
+    _lib.check(_lib.load().pie_ingest_fill_dev(C.byref(d), bufs.scratch.data_ptr(), bufs.doc_status.data_ptr(),
+                                               C.byref(view), _stream_ptr()))
+
+
+def ingest_json(docs: JsonDocs, bufs: IngestBuffers = None):
+    """Stored show documents -> (ArchiveTable, doc_status uint8[n]): what
+    `rows.map(row => this._mapArchiveRow(row))` (sqlProvider.js:230-234, :892-926) parses, laid out as the table
+    every other operator reads.  doc_status[s] = 1 marks a row the reference drops (`.filter(Boolean)`); its
+    table row is the empty show.  CUDA-resident docs give a CUDA-resident table (pie_ingest_measure_dev /
+    pie_ingest_fill_dev); host docs go through pie_ingest_host and give a host table."""
+    _lib.ensure_init()
+    lib = _lib.load()
+    n = docs.n_docs
+    if docs.is_cuda:
+        bufs = bufs or IngestBuffers(n, docs.data.device)
+        ingest_measure_dev(docs, bufs)
+        totals = bufs.totals.cpu().tolist()  # synchronises: the table is sized from it
+        code, doc = bufs.status.cpu().tolist()
+        _raise_ingest_status(code, doc)
+        table = alloc_ingest_table(n, totals, docs.data.device)
+        ingest_fill_dev(docs, bufs, table)
+        return table, bufs.doc_status[:n]
+    d = docs.c()
+    view = _lib.ArchiveViewC()
+    doc_status = torch.empty(max(n, 1), dtype=torch.uint8)
+    totals = torch.zeros(_lib.PIE_INGEST_TOTALS, dtype=torch.int64)
+    bad = C.c_int64(-1)
+    rc = lib.pie_ingest_host(C.byref(d), C.byref(view), doc_status.data_ptr(), totals.data_ptr(), C.byref(bad))
+    if rc in (_lib.PIE_ERR_SCHEMA, _lib.PIE_ERR_UNSUPPORTED_JSON, _lib.PIE_ERR_CAPACITY):
+        _raise_ingest_status(rc, int(bad.value))
+    _lib.check(rc)
+    table = _table_from_library_view(view, n, totals.tolist())
+    return table, doc_status[:n]
+
+
+def _table_from_library_view(view: "_lib.ArchiveViewC", n_docs: int, totals) -> ArchiveTable:
+    """Copies the library-owned pinned result of pie_ingest_host into tensors the caller owns."""
+    import numpy as np
+    from .columnar import StrCol, StrListCol
+
+    def arr(ptr, n, dtype):
+        if n == 0 or not ptr:
+            return torch.zeros(0, dtype=dtype)
+        size = n * torch.empty(0, dtype=dtype).element_size()
+        buf = (C.c_uint8 * size).from_address(ptr)
+        return torch.from_numpy(np.frombuffer(buf, dtype=np.uint8).copy()).view(dtype)
+
+    E, crew_items, action_items = (int(totals[_lib.PIE_IT_ENTRIES]), int(totals[_lib.PIE_IT_CREW_ITEMS]),
+                                   int(totals[_lib.PIE_IT_ACTION_ITEMS]))
+
+    def col(c, rows, heap):
+        return StrCol(arr(c.offsets, rows + 1, torch.int32), arr(c.data, int(totals[heap]), torch.uint8))
+
+    return ArchiveTable(
+        n_shows=n_docs, n_entries=E, entry_offsets=arr(view.entry_offsets, n_docs + 1, torch.int32),
+        show_cols={name: col(getattr(view, name), n_docs, h) for h, name in enumerate(_lib.SHOW_STR_COLS)},
+        crew=StrListCol(arr(view.crew.list_offsets, n_docs + 1, torch.int32), col(view.crew.items, crew_items, 7)),
+        created_at=arr(view.created_at, n_docs, torch.float64), archived_at=arr(view.archived_at, n_docs, torch.float64),
+        entry_cols={name: col(getattr(view, name), E, 8 + h) for h, name in enumerate(_lib.ENTRY_STR_COLS)},
+        actions=StrListCol(arr(view.actions.list_offsets, E + 1, torch.int32), col(view.actions.items, action_items, 22)),
+        delay_sec=arr(view.delay_sec, E, torch.float64), delay_valid=arr(view.delay_valid, E, torch.uint8),
+        entry_ts=arr(view.entry_ts, E, torch.float64))

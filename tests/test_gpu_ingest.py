@@ -1,0 +1,165 @@
+"""JSON ingest on the GPU — the stored show documents (reference server/storage/sqlProvider.js:682/:696 write them,
+:230-234 / :892-926 read them back with JSON.parse) parsed into the columnar table by pie_ingest_* — against the
+oracle (pie_oracle.map_archive_row + the table packer).  Bit-exact tables through both the device-resident and the
+host-buffer entry points; the cases are those of tests/test_ingest_cpu.py plus sizes only the GPU handles."""
+import json
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_c
+import pie_oracle as po
+import test_ingest_cpu as cases
+from ingest_helpers import assert_tables_equal, oracle_ingest, stored_doc
+from sph_pie_b200 import _lib, ops
+from sph_pie_b200.synth import synth_archive, table_to_shows
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_check(cuda, docs, what="", host_too=True):
+    ref_table, ref_status = oracle_ingest(docs)
+    jd = ops.JsonDocs.from_texts(docs)
+    table, status = ops.ingest_json(jd.to(cuda))
+    torch.cuda.synchronize()
+    assert table.is_cuda
+    assert np.array_equal(status.cpu().numpy(), ref_status), f"{what} doc_status (dev)"
+    assert_tables_equal(table, ref_table, what + " dev")
+    if host_too:
+        htable, hstatus = ops.ingest_json(jd)
+        assert not htable.is_cuda
+        assert np.array_equal(hstatus.numpy(), ref_status), f"{what} doc_status (host)"
+        assert_tables_equal(htable, ref_table, what + " host")
+    return table
+
+
+@pytest.mark.parametrize("style", ["stringify", "ascii", "pretty", "shuffled"])
+def test_synthetic_archive_round_trips(cuda, style):
+    rng = random.Random(3)
+    host = synth_archive(310, seed=11, missing_created_frac=0.1)
+    docs = [stored_doc(s, rng, style) for s in table_to_shows(host)]
+    table = gpu_check(cuda, docs, style)
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+    host.delay_valid[lost] = 0
+    assert_tables_equal(table, host, style + " vs the source table")
+
+
+@pytest.mark.parametrize("style", ["stringify", "ascii", "pretty", "shuffled"])
+def test_hostile_strings_and_numbers(cuda, style):
+    rng = random.Random(5)
+    shows = [cases.hostile_show(rng, rng.randrange(0, 6)) for _ in range(400)]
+    gpu_check(cuda, [stored_doc(s, rng, style) for s in shows], style)
+
+
+def test_projection_rules_and_damaged_documents(cuda):
+    import inspect
+
+    # the document list of the CPU test, verbatim
+    src = inspect.getsource(cases.test_projection_rules)
+    env = {}
+    exec(src.replace("def test_projection_rules():", "def docs_only():").replace("    check(docs)", "    return docs"), env)
+    gpu_check(cuda, env["docs_only"](), "projection rules")
+    rng = random.Random(9)
+    show = cases.hostile_show(rng, 2)
+    doc = stored_doc(show, rng, "ascii")
+    docs = [doc[:k] for k in range(len(doc) + 1)]
+    for _ in range(3000):
+        k = rng.randrange(len(doc))
+        docs.append(doc[:k] + rng.choice('"\\{}[]:,0-9.eE+tfn ux\n\t\x01a') + doc[k + 1:])
+    keep = []
+    for d in docs:
+        try:
+            oracle_ingest([d])
+            keep.append(d)
+        except (TypeError, po.UnsupportedJson):
+            pass
+    gpu_check(cuda, keep, "damaged")
+
+
+def test_schema_and_unsupported_documents_fail_loudly(cuda):
+    good = '{"id":"fine","entries":[{"id":"e"}]}'
+    for d in cases.SCHEMA_DOCS:
+        for docs in (ops.JsonDocs.from_texts([good, d, good, '{"id":7}']),):
+            for jd in (docs, docs.to(cuda)):
+                with pytest.raises(_lib.SchemaError) as ei:
+                    ops.ingest_json(jd)
+                assert ei.value.code == _lib.PIE_ERR_SCHEMA and ei.value.doc == 1, d
+                assert isinstance(ei.value, TypeError)
+    for d in cases.UNSUPPORTED_DOCS:
+        docs = ops.JsonDocs.from_texts([good, good, d, '{"id":7}'])
+        for jd in (docs, docs.to(cuda)):
+            with pytest.raises(_lib.UnsupportedJsonError) as ei:
+                ops.ingest_json(jd)
+            assert ei.value.doc == 2, d
+
+
+def test_numbers_and_ragged_documents(cuda):
+    rng = np.random.default_rng(17)
+    xs = rng.integers(0, 2 ** 64, 20000, dtype=np.uint64).view(np.float64)
+    xs = xs[np.isfinite(xs)]
+    texts = [repr(float(x)) for x in xs] + ["%.17e" % x for x in xs[:5000]]
+    docs = ['{"createdAt":%s,"entries":[{"delaySec":%s,"ts":%s},{"delaySec":%s}]}' % (a, a, a, b)
+            for a, b in zip(texts, reversed(texts))]
+    gpu_check(cuda, docs, "numbers")
+    gpu_check(cuda, [], "empty batch")
+    gpu_check(cuda, [""], "one empty text")
+    big = {"id": "big", "notes": "x" * 70000, "entries": [{"notes": "y" * 5000, "actions": ["a"] * 300}] * 40}
+    docs = [json.dumps(big), "{}", json.dumps({"entries": [{}] * 1000}), "[]", json.dumps(big)[:-1], '{"id":"z"}'] * 3
+    gpu_check(cuda, docs, "ragged")
+
+
+def test_larger_archive_and_the_operators_downstream(cuda):
+    """40k shows: the ingested table is the source table, and the operators give the same results on it."""
+    host = synth_archive(40000, seed=21)
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+    host.delay_valid[lost] = 0
+    host.delay_sec[lost] = 0.0
+    docs = [json.dumps(s, ensure_ascii=False, separators=(",", ":")) for s in table_to_shows(host)]
+    jd = ops.JsonDocs.from_texts(docs)
+    table, status = ops.ingest_json(jd.to(cuda))
+    assert int(status.sum()) == 0
+    assert_tables_equal(table, host, "40k shows")
+    htable, _ = ops.ingest_json(jd)
+    assert_tables_equal(htable, host, "40k shows, host entry point")
+    ref_stats, ref_daily, rc, _ = oracle_c.archive_analytics(host, tz_offset_minutes=60)
+    assert rc == 0
+    stats, daily = ops.archive_analytics(table, tz_offset_minutes=60)
+    assert torch.equal(stats.i32.cpu(), ref_stats.i32) and torch.equal(stats.f64.cpu().view(torch.int64), ref_stats.f64.view(torch.int64))
+    rows = ops.csv_rows(table)
+    ref_offsets, ref_csv = oracle_c.csv_rows(host)
+    assert torch.equal(rows.row_offsets.cpu(), ref_offsets) and torch.equal(rows.data.cpu(), ref_csv)
+
+
+def test_replicated_batch_at_scale(cuda):
+    """Size-independent property at a batch the oracle cannot walk: k copies of a batch ingest to k copies of its
+    table (2^18 documents, ~1.2 GB of text)."""
+    host = synth_archive(4096, seed=33)
+    docs = [json.dumps(s, ensure_ascii=False, separators=(",", ":")) for s in table_to_shows(host)]
+    docs[100] = docs[100][:-1]  # one dropped row per copy
+    one = ops.JsonDocs.from_texts(docs)
+    n, nbytes = one.n_docs, int(one.offsets[-1])
+    k = 64
+    text = one.data[:nbytes].to(cuda).repeat(k)
+    text = torch.cat([text, torch.zeros(8, dtype=torch.uint8, device=cuda)])
+    lens = (one.offsets[1:] - one.offsets[:-1]).to(cuda).repeat(k)
+    offsets = torch.zeros(n * k + 1, dtype=torch.int64, device=cuda)
+    torch.cumsum(lens, 0, out=offsets[1:])
+    base, base_status = ops.ingest_json(one.to(cuda))
+    table, status = ops.ingest_json(ops.JsonDocs(offsets, text))
+    torch.cuda.synchronize()
+    assert table.n_shows == n * k and table.n_entries == base.n_entries * k
+    assert torch.equal(status.view(k, n), base_status.view(1, n).expand(k, n))
+    E = base.n_entries
+    eo = table.entry_offsets[:-1].view(k, n) - (torch.arange(k, device=cuda, dtype=torch.int32) * E).view(k, 1)
+    assert torch.equal(eo, base.entry_offsets[:-1].view(1, n).expand(k, n))
+    for name, col in base.entry_cols.items():
+        big = table.entry_cols[name]
+        nb = int(col.offsets[E])
+        assert int(big.offsets[E * k]) == nb * k, name
+        assert torch.equal(big.data[:nb * k].view(k, nb), col.data[:nb].view(1, nb).expand(k, nb)), name
+        lens_big = (big.offsets[1:E * k + 1] - big.offsets[:E * k]).view(k, E)
+        assert torch.equal(lens_big, (col.offsets[1:E + 1] - col.offsets[:E]).view(1, E).expand(k, E)), name
+    assert torch.equal(table.delay_sec.view(torch.int64).view(k, E), base.delay_sec.view(torch.int64).view(1, E).expand(k, E))
+    assert torch.equal(table.delay_valid.view(k, E), base.delay_valid.view(1, E).expand(k, E))

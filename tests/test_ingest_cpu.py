@@ -1,0 +1,174 @@
+"""The ingest kernels' document walk (sph_pie_b200/csrc/pie_json_walk.cuh), built for the HOST by
+tests/native/ingest_host.cpp, against the oracle: pie_oracle.map_archive_row (JSON.parse as _mapArchiveRow applies it,
+reference server/storage/sqlProvider.js:892-926; Python's json module is the parser) + the table packer.  Bit-exact
+tables.  The same cases run on the GPU in tests/test_gpu_ingest.py; this file needs no GPU."""
+import json
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import pie_oracle as po
+from ingest_helpers import assert_tables_equal, host_ingest, oracle_ingest, stored_doc
+from sph_pie_b200 import _lib
+from sph_pie_b200.synth import synth_archive, table_to_shows
+
+HOSTILE = ['"', "\\", "/", "\b", "\f", "\n", "\r", "\t", "\x00", "\x1f", "\x7f", "é", "ß", "漢", "字", "🚁", "𝄞", " ",
+           "﻿", "a", "Z", " ", ",", ":", "{", "}", "[", "]", "\\u0041", "\\n", "null", "true", "1e5"]
+
+
+def hostile_text(rng, n):
+    return "".join(rng.choice(HOSTILE) for _ in range(n))
+
+
+def hostile_show(rng, n_entries):
+    t = lambda: hostile_text(rng, rng.randrange(0, 12))
+    show = {"id": t(), "date": "2024-03-0%d" % rng.randrange(1, 9), "time": t(), "label": t(), "showNumber": rng.choice([None, 3.0, 1e21]),
+            "calendarEventId": t(), "eventName": t(), "crew": [t() for _ in range(rng.randrange(0, 4))], "leadPilot": t(),
+            "monkeyLead": t(), "notes": t(), "disciplineId": "drones", "entries": [],
+            "createdAt": rng.choice([1704067200000.0, 1.5, -0.0, 1e-7, 123456789012345680000.0, None]),
+            "updatedAt": 1704067200001.0, "archivedAt": rng.choice([1704067200000.5, None, 4.9e-324])}
+    for _ in range(n_entries):
+        show["entries"].append({
+            "id": t(), "ts": rng.choice([1704067200123.0, None, 0.0]), "unitId": t(), "planned": rng.choice(["Yes", "No", ""]),
+            "launched": t(), "status": rng.choice(["Completed", "Abort", t()]), "primaryIssue": t(), "subIssue": t(),
+            "otherDetail": t(), "severity": t(), "rootCause": t(), "actions": [t() for _ in range(rng.randrange(0, 3))],
+            "operator": t(), "batteryId": t(),
+            "delaySec": rng.choice([None, 0.0, 12.5, -3.0, 1e300, 5e-324, 0.1, 123456.789, 2.0 ** 53, 1 / 3]),
+            "commandRx": t(), "notes": t()})
+    return show
+
+
+def check(docs, what=""):
+    ref_table, ref_status = oracle_ingest(docs)
+    table, status, err = host_ingest(docs)
+    assert err == (0, -1), (what, err)
+    assert np.array_equal(status, ref_status), f"{what} doc_status"
+    assert_tables_equal(table, ref_table, what)
+    return table
+
+
+@pytest.mark.parametrize("style", ["stringify", "ascii", "pretty", "shuffled"])
+def test_synthetic_archive_round_trips(style):
+    rng = random.Random(3)
+    host = synth_archive(300, seed=11, missing_created_frac=0.1)
+    shows = table_to_shows(host)
+    docs = [stored_doc(s, rng, style) for s in shows]
+    table = check(docs, style)
+    # and it is the table the documents came from, except what JSON cannot carry: a NaN / Infinity delaySec is
+    # written as null (JSON.stringify), i.e. comes back absent
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+    host.delay_valid[lost] = 0
+    assert_tables_equal(table, host, style + " vs the table the documents came from")
+
+
+@pytest.mark.parametrize("style", ["stringify", "ascii", "pretty", "shuffled"])
+def test_hostile_strings_and_numbers(style):
+    rng = random.Random(5)
+    shows = [hostile_show(rng, rng.randrange(0, 6)) for _ in range(200)]
+    check([stored_doc(s, rng, style) for s in shows], style)
+
+
+def test_projection_rules():
+    docs = [
+        '{}', '[]', '[1,{"id":"x"}]', 'null', 'true', '12', '"text"', '', '   ', '{"id":"a"} ', ' \t\r\n{"id":"b"}\n',
+        '{"id":null,"date":null,"crew":null,"entries":null,"createdAt":null}',
+        '{"crew":{"0":"a"},"entries":{"length":1},"createdAt":"1704067200000","archivedAt":true}',
+        '{"crew":["a",null,"b"],"entries":[null,1,"x",[{"id":"no"}],{},true,{"id":"yes","actions":[null,"go",""]}]}',
+        '{"entries":[{"delaySec":null},{"delaySec":0},{"delaySec":-0},{"delaySec":1e400},{"delaySec":-1e400},{"ts":1e400}]}',
+        '{"unknown":{"id":"inner","entries":[{"id":"deep"}]},"id":"outer","more":[[[],[{}]],{"a":{"b":[1,2,{"c":null}]}}]}',
+        '{"entries":[{"actions":"not a list","ts":"12"},{"actions":{"a":1},"ts":false},{"actions":[]}]}',
+        '{"id":"\\ud83d\\ude81 \\u00e9\\u6f22 \\"q\\" \\\\ \\/ \\b\\f\\n\\r\\t \\u0000"}',
+        '{"i\\u0064":"escaped key","\\u0065ntries":[{"\\u0069d":"e1"}]}',
+        '{"ID":"case matters","Id":"x","id ":"y"," id":"z","entries ":[{}]}',
+        '{"createdAt":1704067200000,"archivedAt":1.7040672e12,"entries":[{"ts":1704067200000.5,"delaySec":12.5}]}',
+        '{"createdAt":0.1e1,"archivedAt":-0,"entries":[{"delaySec":1E2},{"delaySec":1e+2},{"delaySec":100e-2}]}',
+        '{"a":1,}', '{"a" 1}', '{"a":1 "b":2}', '{,}', '[,]', '[1,]', '{"a"}', '{"a":}', '{a:1}', "{'a':1}", '{"a":01}', '{"a":1.}',
+        '{"a":.5}', '{"a":+1}', '{"a":1e}', '{"a":0x10}', '{"a":tru}', '{"a":nul}', '{"a":True}', '{"a":NaN}', '{"a":Infinity}',
+        '{"a":-Infinity}', '{"a":-}', '{"a":"\\x41"}', '{"a":"\\u12"}', '{"a":"\\u12G4"}', '{"a":"tab\there"}', '{"a":"nl\nhere"}',
+        '{"a":"unterminated}', '{"a":"x"', '{"a":"x"}}', '{"a":"x"}]', '{"a":"x"} {}', '{"a":"x"}x', '}{', ']', '{]', '[}', '{"a":[}',
+        '{"a":{]}', '[1 2]', '{"a":1:2}', '{"a"::1}', '{"a":1,,"b":2}', '﻿{"id":"bom"}', '{"a":"\\"}', '{"a":"\\',
+        '{"id":"a"}\x00', '\x00{"id":"a"}', '{"id":"a",\x0b"date":"b"}', '{"id":"a",\xa0"date":"b"}',
+        '{"id":"del \x7f ok"}', '{"entries":[{"id":"1"},{"id":"2"}],"id":"after entries","crew":["z"]}',
+        '1e5', '-', '-0', '0.0', '"a" "b"', 'nulll', 'null null',
+    ]
+    check(docs)
+
+
+def test_every_prefix_and_single_byte_damage_of_a_document():
+    rng = random.Random(9)
+    show = hostile_show(rng, 2)
+    show["label"] = 'q"\\\né\U0001F681'
+    doc = stored_doc(show, rng, "ascii")  # pure ASCII: any cut / substitution leaves valid UTF-8
+    docs = [doc[:k] for k in range(len(doc) + 1)]
+    for _ in range(1500):
+        k = rng.randrange(len(doc))
+        docs.append(doc[:k] + rng.choice('"\\{}[]:,0-9.eE+tfn ux\n\t\x01a') + doc[k + 1:])
+    for _ in range(500):
+        k = rng.randrange(len(doc))
+        docs.append(doc[:k] + doc[k + 1:])
+    # a damaged document may also be a schema / duplicate-key case: those are compared one by one below
+    keep, special = [], []
+    for d in docs:
+        try:
+            oracle_ingest([d])
+            keep.append(d)
+        except (TypeError, po.UnsupportedJson):
+            special.append(d)
+    check(keep)
+    for d in special:
+        _, _, err = host_ingest([d])
+        assert err[0] in (_lib.PIE_ERR_SCHEMA, _lib.PIE_ERR_UNSUPPORTED_JSON) and err[1] == 0, (d, err)
+
+
+SCHEMA_DOCS = [
+    '{"id":5}', '{"label":true}', '{"notes":{}}', '{"date":[]}', '{"crew":[1]}', '{"crew":[{}]}', '{"crew":["a",false]}',
+    '{"entries":[{"status":1}]}', '{"entries":[{"delaySec":"12"}]}', '{"entries":[{"delaySec":true}]}', '{"entries":[{"delaySec":[]}]}',
+    '{"entries":[{"delaySec":{}}]}', '{"entries":[{"actions":[1]}]}', '{"entries":[{"actions":[[]]}]}', '{"entries":[{"notes":false}]}',
+    '{"id":"\\ud800"}', '{"id":"\\udc00x"}', '{"id":"\\ud800\\u0041"}', '{"entries":[{"id":"\\ud83dx\\ude81"}]}', '{"crew":["\\udfff"]}',
+]
+UNSUPPORTED_DOCS = [
+    '{"id":"a","id":"b"}', '{"entries":[],"entries":[]}', '{"entries":[{"ts":1,"ts":2}]}', '{"entries":[{"id":"a","\\u0069d":"b"}]}',
+    "[" * 65 + "]" * 65, '{"x":' + "[" * 64 + "]" * 64 + "}",
+    b'{"id":"\xff"}', b'{"id":"\xc0\xaf"}', b'{"id":"\xe2\x82"}', b'{"id":"\xed\xa0\x80"}', b'{"x":"\xf4\x90\x80\x80"}', b'{"\x80":1}',
+]
+
+
+def test_schema_and_unsupported_documents_fail_loudly():
+    good = '{"id":"fine","entries":[{"id":"e"}]}'
+    for d in SCHEMA_DOCS:
+        with pytest.raises(TypeError):
+            oracle_ingest([good, d])
+        _, _, err = host_ingest([good, d, good, '{"id":7}'])
+        assert err == (_lib.PIE_ERR_SCHEMA, 1), (d, err)
+    for d in UNSUPPORTED_DOCS:
+        with pytest.raises(po.UnsupportedJson):
+            oracle_ingest([good, good, d])
+        _, _, err = host_ingest([good, good, d, '{"id":7}'])
+        assert err == (_lib.PIE_ERR_UNSUPPORTED_JSON, 2), (d, err)
+    # not errors: the same things where the table does not look, nesting of exactly 64, a dropped row that also has them
+    fine = ['{"x":{"id":5,"id":6},"y":[{"delaySec":"12"}]}', "[" * 64 + "]" * 64, '{"x":' + "[" * 63 + "]" * 63 + "}",
+            '{"id":5', '{"id":"a","id":"b"', '{"showNumber":5,"updatedAt":"x","entries":[{"extra":{"status":1}}]}']
+    check(fine)
+
+
+def test_numbers_are_correctly_rounded():
+    rng = np.random.default_rng(17)
+    xs = rng.integers(0, 2 ** 64, 4000, dtype=np.uint64).view(np.float64)
+    xs = xs[np.isfinite(xs)]
+    texts = [repr(float(x)) for x in xs] + ["%.17e" % x for x in xs[:1500]] + [po.js_number_to_string(float(x)) for x in xs[:1500]]
+    texts += ["0", "-0", "1e22", "1e23", "9007199254740993", "123456789012345678901234567890", "0.000001", "1E5", "5e-324",
+              "2.4703282292062327e-324", "1.7976931348623157e308", "1.7976931348623159e308", "4.4501477170144023e-308"]
+    docs = ['{"createdAt":%s,"entries":[{"delaySec":%s,"ts":%s},{"delaySec":%s}]}' % (a, a, a, b)
+            for a, b in zip(texts, reversed(texts))]
+    check(docs)
+
+
+def test_empty_batch_and_ragged_documents():
+    check([])
+    check([""])
+    check(["{}"] * 3)
+    big = {"id": "big", "notes": "x" * 70000, "entries": [{"notes": "y" * 5000, "actions": ["a"] * 300}] * 40}
+    docs = [json.dumps(big), "{}", json.dumps({"entries": [{}] * 1000}), "[]", json.dumps(big)[:-1], '{"id":"z"}']
+    check(docs)
