@@ -3,11 +3,13 @@
 // `rows.map(row => this._mapArchiveRow(row)).filter(Boolean)` (sqlProvider.js:230-234, :892-926: JSON.parse, drop
 // what is not an object) followed by the projection on the table's schema (columnar.py pack_shows) does.
 //
-// A document is ~0.5 KB per entry of sequential grammar; 2^20 of them are independent.  So: ONE THREAD PER DOCUMENT
-// walks its text with a complete ECMA-404 recogniser (strings with every escape and UTF-8 validation, numbers,
-// literals, nesting checked against a 64-level kind stack), which costs ~0.3 warp-instructions per byte when the
-// lanes stay converged — cheaper than any warp-cooperative structural index at this document size.  The text is
-// read through the read-only path 8 aligned bytes at a time with the next word already in flight.
+// A document is ~0.4 KB per entry of sequential grammar; 2^20 of them are independent.  So: ONE THREAD WALKS ONE
+// DOCUMENT AT A TIME with a complete ECMA-404 recogniser (strings with every escape and UTF-8 validation, numbers,
+// literals, nesting checked against a 64-level kind stack) written as a resumable state machine
+// (pie_json_walk.cuh): a step is one token, or up to 8 bytes of a string found with word-wide byte tests.  The
+// kernels are persistent: a lane takes its next document from a counter the moment its current one ends, so a warp
+// never waits for its longest document and its lanes meet in two blocks of code (string step, token step).  The
+// text is read through the read-only path 8 aligned bytes at a time with the next word already in flight.
 //
 //   pass 1  ingest_measure_kernel   per document: entries, items of crew / actions, unescaped bytes of each of the 23
 //                                   string heaps; syntax errors make the document a dropped row (all counts zero)
@@ -37,36 +39,93 @@ constexpr int kIngestThreads = 128;
 struct IngestScratch {
   uint32_t* planes;          // [kPlanes][stride]: pass 1 counts, then exclusive prefixes
   int64_t stride;
-  unsigned long long* block_sums;  // [kPlanes][nblk]
+  unsigned long long* block_sums;  // [kPlanes][nblk] + the arrival counter of the scan
   unsigned long long* err_key;     // min over documents of (doc << 8 | code): the first hard error
+  unsigned long long* next_doc;    // [2] the next document to hand out in pass 1 / pass 2
 };
 
 constexpr int kScanItems = 4;
 constexpr int kScanThreads = 1024;
 constexpr int kScanChunk = kScanItems * kScanThreads;
 
-__global__ void ingest_init_kernel(unsigned long long* err_key) { *err_key = ~0ull; }
+__global__ void ingest_init_kernel(IngestScratch sc) {
+  *sc.err_key = ~0ull;
+  sc.next_doc[0] = 0;
+  sc.next_doc[1] = 0;
+}
 
-__global__ void __launch_bounds__(kIngestThreads) ingest_measure_kernel(const int64_t* __restrict__ doc_offsets,
-                                                                         const uint8_t* __restrict__ text, int64_t n_docs,
-                                                                         IngestScratch sc, uint8_t* __restrict__ doc_status) {
-  const int64_t s = (int64_t)blockIdx.x * kIngestThreads + threadIdx.x;
-  if (s >= n_docs) return;
+// Both passes: every lane walks documents until none is left.
+template <bool kFill>
+__global__ void __launch_bounds__(kIngestThreads) ingest_walk_kernel(const int64_t* __restrict__ doc_offsets,
+                                                                      const uint8_t* __restrict__ text, int64_t n_docs,
+                                                                      IngestScratch sc, uint8_t* __restrict__ doc_status,
+                                                                      IngestOut out) {
+  const Pow5Table pow5{g_pow5_dev};
   uint32_t cnt[kPlanes];
+  DocWalker<kFill> w;
+  bool active = false;
+  int64_t s = 0;
+  for (;;) {
+    int r = kDocRunning;
+    if (!active) {
+      s = (int64_t)atomicAdd(sc.next_doc + (kFill ? 1 : 0), 1ull);
+      if (s >= n_docs) break;
+      bool walk = true;
+      if (kFill) {
 #pragma unroll
-  for (int p = 0; p < kPlanes; ++p) cnt[p] = 0;
-  DocCursor c;
-  c.open(text, doc_offsets[s], doc_offsets[s + 1]);
-  IngestOut none{};
-  const int r = walk_document<false>(c, cnt, none, s, Pow5Table{g_pow5_dev});
-  if (r != kDocOk) {
+        for (int p = 0; p < kPlanes; ++p) cnt[p] = sc.planes[p * sc.stride + s];
+        // the show's row: every text field starts where the previous show's ended (an absent key is '')
 #pragma unroll
-    for (int p = 0; p < kPlanes; ++p) cnt[p] = 0;
-    if (r != kDocDropped) atomicMin(sc.err_key, ((unsigned long long)s << 8) | (unsigned long long)r);
+        for (int h = 0; h < 7; ++h) out.off[h][s] = (int32_t)cnt[h];
+        out.entry_offsets[s] = (int32_t)cnt[kPlaneEntries];
+        out.crew_list[s] = (int32_t)cnt[kPlaneCrewItems];
+        out.created_at[s] = jw_nan();
+        out.archived_at[s] = jw_nan();
+        walk = doc_status[s] == 0;  // a dropped row stays the empty show
+      } else {
+#pragma unroll
+        for (int p = 0; p < kPlanes; ++p) cnt[p] = 0;
+      }
+      if (walk) {
+        w.begin(text, doc_offsets[s], doc_offsets[s + 1], s);
+        active = true;
+      } else {
+        r = kDocDropped;
+      }
+    }
+    if (active) r = w.step(cnt, out, pow5);
+    if (r == kDocRunning) continue;
+    active = false;
+    if (!kFill) {
+      if (r != kDocOk) {
+#pragma unroll
+        for (int p = 0; p < kPlanes; ++p) cnt[p] = 0;
+        if (r != kDocDropped) atomicMin(sc.err_key, ((unsigned long long)s << 8) | (unsigned long long)r);
+      }
+      doc_status[s] = r == kDocOk ? 0 : 1;
+#pragma unroll
+      for (int p = 0; p < kPlanes; ++p) sc.planes[p * sc.stride + s] = cnt[p];
+    } else if (s == n_docs - 1) {  // the terminal offsets: where the last document ended
+#pragma unroll
+      for (int h = 0; h < 7; ++h) out.off[h][n_docs] = (int32_t)cnt[h];
+      out.entry_offsets[n_docs] = (int32_t)cnt[kPlaneEntries];
+      out.crew_list[n_docs] = (int32_t)cnt[kPlaneCrewItems];
+      out.off[kHeapCrew][cnt[kPlaneCrewItems]] = (int32_t)cnt[kHeapCrew];
+      const uint32_t rows = cnt[kPlaneEntries];
+#pragma unroll
+      for (int h = kHeapEntry0; h < kHeapEntry0 + 14; ++h) out.off[h][rows] = (int32_t)cnt[h];
+      out.actions_list[rows] = (int32_t)cnt[kPlaneActionItems];
+      out.off[kHeapActions][cnt[kPlaneActionItems]] = (int32_t)cnt[kHeapActions];
+    }
   }
-  doc_status[s] = r == kDocOk ? 0 : 1;
-#pragma unroll
-  for (int p = 0; p < kPlanes; ++p) sc.planes[p * sc.stride + s] = cnt[p];
+}
+
+// the terminal offsets of an empty table
+__global__ void ingest_empty_kernel(IngestOut out) {
+  for (int h = 0; h < kHeaps; ++h) out.off[h][0] = 0;
+  out.entry_offsets[0] = 0;
+  out.crew_list[0] = 0;
+  out.actions_list[0] = 0;
 }
 
 // exclusive scan of every plane over the documents: chunk sums, scan of the chunk sums (one CTA per plane), then the
@@ -189,48 +248,11 @@ __global__ void __launch_bounds__(kScanThreads) ingest_scan_apply_kernel(IngestS
   }
 }
 
-__global__ void __launch_bounds__(kIngestThreads) ingest_fill_kernel(const int64_t* __restrict__ doc_offsets,
-                                                                      const uint8_t* __restrict__ text, int64_t n_docs,
-                                                                      IngestScratch sc, const uint8_t* __restrict__ doc_status,
-                                                                      IngestOut out) {
-  const int64_t s = (int64_t)blockIdx.x * kIngestThreads + threadIdx.x;
-  if (n_docs == 0) {  // the terminal offsets of an empty table
-    if (s == 0) {
-      for (int h = 0; h < kHeaps; ++h) out.off[h][0] = 0;
-      out.entry_offsets[0] = 0;
-      out.crew_list[0] = 0;
-      out.actions_list[0] = 0;
-    }
-    return;
-  }
-  if (s >= n_docs) return;
-  uint32_t cnt[kPlanes];
-#pragma unroll
-  for (int p = 0; p < kPlanes; ++p) cnt[p] = sc.planes[p * sc.stride + s];
-  // the show's row: every text field starts where the previous show's ended (an absent key is '')
-#pragma unroll
-  for (int h = 0; h < 7; ++h) out.off[h][s] = (int32_t)cnt[h];
-  out.entry_offsets[s] = (int32_t)cnt[kPlaneEntries];
-  out.crew_list[s] = (int32_t)cnt[kPlaneCrewItems];
-  out.created_at[s] = jw_nan();
-  out.archived_at[s] = jw_nan();
-  if (doc_status[s] == 0) {
-    DocCursor c;
-    c.open(text, doc_offsets[s], doc_offsets[s + 1]);
-    walk_document<true>(c, cnt, out, s, Pow5Table{g_pow5_dev});
-  }
-  if (s == n_docs - 1) {  // the terminal offsets: where the last document ended
-#pragma unroll
-    for (int h = 0; h < 7; ++h) out.off[h][n_docs] = (int32_t)cnt[h];
-    out.entry_offsets[n_docs] = (int32_t)cnt[kPlaneEntries];
-    out.crew_list[n_docs] = (int32_t)cnt[kPlaneCrewItems];
-    out.off[kHeapCrew][cnt[kPlaneCrewItems]] = (int32_t)cnt[kHeapCrew];
-    const uint32_t rows = cnt[kPlaneEntries];
-#pragma unroll
-    for (int h = kHeapEntry0; h < kHeapEntry0 + 14; ++h) out.off[h][rows] = (int32_t)cnt[h];
-    out.actions_list[rows] = (int32_t)cnt[kPlaneActionItems];
-    out.off[kHeapActions][cnt[kPlaneActionItems]] = (int32_t)cnt[kHeapActions];
-  }
+// persistent: as many CTAs as can be resident (16 per SM at most), fewer for small batches
+unsigned walk_blocks(int64_t n_docs) {
+  const int64_t want = (n_docs + kIngestThreads - 1) / kIngestThreads;
+  const int64_t cap = (int64_t)PIE_SM_COUNT_B200 * 16;
+  return (unsigned)(want < cap ? want : cap);
 }
 
 int scan_blocks(int64_t n_docs) { return (int)((n_docs + kScanChunk - 1) / kScanChunk) + (n_docs == 0 ? 1 : 0); }
@@ -245,6 +267,7 @@ IngestScratch carve(void* scratch, int64_t n_docs) {
   sc.block_sums = (unsigned long long*)p;
   p += ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8;
   sc.err_key = (unsigned long long*)p;
+  sc.next_doc = sc.err_key + 1;
   return sc;
 }
 
@@ -286,11 +309,11 @@ cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint
   const int nblk = scan_blocks(n);
   cudaError_t e = cudaMemsetAsync(sc.block_sums, 0, ((uint64_t)kPlanes * nblk + 1) * 8, stream);
   if (e != cudaSuccess) return e;
-  ingest_init_kernel<<<1, 1, 0, stream>>>(sc.err_key);
+  ingest_init_kernel<<<1, 1, 0, stream>>>(sc);
   ++g_launches;
   if (n > 0) {
-    ingest_measure_kernel<<<(unsigned)((n + kIngestThreads - 1) / kIngestThreads), kIngestThreads, 0, stream>>>(
-        docs.offsets, docs.data, n, sc, doc_status);
+    ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, doc_status,
+                                                                            IngestOut{});
     ingest_scan_sums_kernel<<<dim3(nblk, kPlanes), kScanThreads, 0, stream>>>(sc, n, nblk);
     g_launches += 2;
   }
@@ -307,9 +330,13 @@ cudaError_t launch_ingest_fill(const pie_json_docs& docs, const void* scratch, c
                                const pie_archive_table& table, cudaStream_t stream) {
   const int64_t n = docs.n_docs;
   IngestScratch sc = carve(const_cast<void*>(scratch), n);
-  const int64_t threads = n > 0 ? n : 1;
-  ingest_fill_kernel<<<(unsigned)((threads + kIngestThreads - 1) / kIngestThreads), kIngestThreads, 0, stream>>>(
-      docs.offsets, docs.data, n, sc, doc_status, make_out(table));
+  cudaError_t e = cudaMemsetAsync(sc.next_doc + 1, 0, 8, stream);  // pass 2 may run more than once per pass 1
+  if (e != cudaSuccess) return e;
+  if (n > 0)
+    ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc,
+                                                                           const_cast<uint8_t*>(doc_status), make_out(table));
+  else
+    ingest_empty_kernel<<<1, 1, 0, stream>>>(make_out(table));
   ++g_launches;
   return cudaGetLastError();
 }

@@ -47,10 +47,18 @@ constexpr int kHeapEntry0 = 8;
 constexpr int kHeapActions = 22;
 constexpr int kMaxDepth = 64;
 
+PIE_JW_HD int jw_ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)x) - 1;
+#else
+  return __builtin_ctzll(x);
+#endif
+}
+
 // ---- the document text, 8 aligned bytes at a time ---------------------------------------------------------------
 struct DocCursor {
   const uint64_t* w;  // next word to request
-  uint64_t cur, nxt;  // bytes not yet consumed (low byte first); the word after
+  uint64_t cur, nxt;  // bytes not yet consumed (low byte first, zero above them); the word after
   int left;           // valid bytes in cur (0 = end of the document)
   int words_left;     // words not yet moved into cur
   int tail_bytes;     // valid bytes of the last word
@@ -74,14 +82,29 @@ struct DocCursor {
     w = first + 1;
     if (words_left > 0) nxt = jw_load_word(w++);
   }
-  PIE_JW_HD int peek() const { return left > 0 ? (int)(cur & 0xFF) : -1; }
-  PIE_JW_HD void next() {
-    cur >>= 8;
-    if (--left == 0 && words_left > 0) {
+  PIE_JW_HD void refill() {
+    if (words_left > 0) {
       cur = nxt;
       --words_left;
       left = words_left == 0 ? tail_bytes : 8;
       if (words_left > 0) nxt = jw_load_word(w++);
+    } else {
+      cur = 0;
+    }
+  }
+  PIE_JW_HD int peek() const { return left > 0 ? (int)(cur & 0xFF) : -1; }
+  PIE_JW_HD void next() {
+    cur >>= 8;
+    if (--left == 0) refill();
+  }
+  // steps over n <= left bytes
+  PIE_JW_HD void advance(int n) {
+    if (n >= left) {
+      left = 0;
+      refill();
+    } else {
+      cur >>= 8 * n;
+      left -= n;
     }
   }
 };
@@ -136,132 +159,6 @@ PIE_JW_HD int match_entry_key(uint32_t len, uint64_t k0, uint64_t k1) {
   return -1;
 }
 
-// ---- strings ------------------------------------------------------------------------------------------------------
-// where the unescaped bytes of a string go: nowhere (dst == nullptr: only counted), to memory, or — for keys — into
-// two words that are compared with the known keys
-template <bool kKey>
-struct StrSink {
-  uint8_t* dst;
-  uint32_t len;
-  uint64_t k0, k1;
-  PIE_JW_HD void put(uint32_t b) {
-    if (kKey) {
-      if (len < 8) k0 |= (uint64_t)b << (8 * len);
-      else if (len < 16) k1 |= (uint64_t)b << (8 * (len - 8));
-    } else if (dst) {
-      dst[len] = (uint8_t)b;
-    }
-    ++len;
-  }
-};
-
-enum StrResult { kStrOk = 0, kStrSyntax = 1, kStrBadUtf8 = 2 };
-
-PIE_JW_HD int hex_value(int c) {
-  if (c >= '0' && c <= '9') return c - '0';
-  c |= 0x20;
-  if (c >= 'a' && c <= 'f') return c - 'a' + 10;
-  return -1;
-}
-
-// The cursor stands behind the opening quote; on success it stands behind the closing one.  *lone is set when an
-// escape names a surrogate code unit without its partner (a JS string that has no UTF-8 form).
-template <bool kKey>
-PIE_JW_NOINLINE int scan_string(DocCursor& c, StrSink<kKey>& out, bool* lone) {
-  uint32_t high = 0;  // pending high surrogate of a \uD8xx escape
-  for (;;) {
-    const int ch = c.peek();
-    if (ch < 0) return kStrSyntax;
-    c.next();
-    if (ch == '\\') {
-      const int e = c.peek();
-      if (e < 0) return kStrSyntax;
-      c.next();
-      uint32_t cp;
-      if (e == 'u') {
-        cp = 0;
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-          const int h = hex_value(c.peek());
-          if (h < 0) return kStrSyntax;
-          c.next();
-          cp = cp * 16 + (uint32_t)h;
-        }
-        if (high) {
-          if (cp >= 0xDC00 && cp <= 0xDFFF) {
-            cp = 0x10000 + ((high - 0xD800) << 10) + (cp - 0xDC00);
-            high = 0;
-            out.put(0xF0 | (cp >> 18));
-            out.put(0x80 | ((cp >> 12) & 0x3F));
-            out.put(0x80 | ((cp >> 6) & 0x3F));
-            out.put(0x80 | (cp & 0x3F));
-            continue;
-          }
-          *lone = true;  // the pending one stays alone; this unit starts over
-          out.put(0xE0 | (high >> 12)); out.put(0x80 | ((high >> 6) & 0x3F)); out.put(0x80 | (high & 0x3F));
-          high = 0;
-        }
-        if (cp >= 0xD800 && cp <= 0xDBFF) { high = cp; continue; }
-        if (cp >= 0xDC00 && cp <= 0xDFFF) *lone = true;
-      } else {
-        switch (e) {
-          case '"': cp = '"'; break;
-          case '\\': cp = '\\'; break;
-          case '/': cp = '/'; break;
-          case 'b': cp = 8; break;
-          case 'f': cp = 12; break;
-          case 'n': cp = 10; break;
-          case 'r': cp = 13; break;
-          case 't': cp = 9; break;
-          default: return kStrSyntax;
-        }
-        if (high) {
-          *lone = true;
-          out.put(0xE0 | (high >> 12)); out.put(0x80 | ((high >> 6) & 0x3F)); out.put(0x80 | (high & 0x3F));
-          high = 0;
-        }
-      }
-      if (cp < 0x80) {
-        out.put(cp);
-      } else if (cp < 0x800) {
-        out.put(0xC0 | (cp >> 6));
-        out.put(0x80 | (cp & 0x3F));
-      } else {
-        out.put(0xE0 | (cp >> 12));
-        out.put(0x80 | ((cp >> 6) & 0x3F));
-        out.put(0x80 | (cp & 0x3F));
-      }
-      continue;
-    }
-    if (high) {
-      *lone = true;
-      out.put(0xE0 | (high >> 12)); out.put(0x80 | ((high >> 6) & 0x3F)); out.put(0x80 | (high & 0x3F));
-      high = 0;
-    }
-    if (ch == '"') return kStrOk;
-    if (ch < 0x20) return kStrSyntax;  // control characters must be escaped
-    out.put((uint32_t)ch);
-    if (ch >= 0x80) {  // UTF-8: well-formed sequences only (Unicode table 3-7)
-      int need;
-      int lo = 0x80, hi = 0xBF;
-      if (ch < 0xC2) return kStrBadUtf8;
-      if (ch < 0xE0) need = 1;
-      else if (ch < 0xF0) { need = 2; if (ch == 0xE0) lo = 0xA0; if (ch == 0xED) hi = 0x9F; }
-      else if (ch < 0xF5) { need = 3; if (ch == 0xF0) lo = 0x90; if (ch == 0xF4) hi = 0x8F; }
-      else return kStrBadUtf8;
-#pragma unroll 1
-      for (int k = 0; k < need; ++k) {
-        const int b = c.peek();
-        if (b < lo || b > hi) return kStrBadUtf8;
-        c.next();
-        out.put((uint32_t)b);
-        lo = 0x80;
-        hi = 0xBF;
-      }
-    }
-  }
-}
-
 // ---- the walk -----------------------------------------------------------------------------------------------------
 struct IngestOut {
   int32_t* off[kHeaps];
@@ -286,28 +183,111 @@ enum DocResult : int {
   // hard errors (the call fails): values = -pie_status
   kDocSchema = -PIE_ERR_SCHEMA,
   kDocUnsupported = -PIE_ERR_UNSUPPORTED_JSON,
+  kDocRunning = 100,  // step(): the document is not through yet
 };
 
-// cnt[p]: pass 1 = what the document adds to plane p; pass 2 = the running position in plane p
+PIE_JW_HD int hex_value(int c) {
+  if (c >= '0' && c <= '9') return c - '0';
+  c |= 0x20;
+  if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+  return -1;
+}
+
+// The walk is a resumable state machine: step() takes one token of the grammar, or up to 8 bytes of the string it
+// is inside of, and returns.  The kernels run it in a loop in which every lane fetches its next document as soon
+// as its current one ends, so that the lanes of a warp — each somewhere else in some document — meet in two blocks
+// of code (the string step and the token step) instead of waiting for the longest document of the warp.
+//   cnt[p]: pass 1 = what the document adds to plane p; pass 2 = the running position in plane p
 template <bool kFill>
-PIE_JW_HD int walk_document(DocCursor& c, uint32_t (&cnt)[kPlanes], const IngestOut& out, int64_t s,
-                            const Pow5Table& pow5) {
-  int depth = 0;
-  uint64_t kinds = 0;  // bit d: the container open at depth d+1 is an object
-  int sem = kSemTop, saved_sem = kSemDone, skip_base = 0;
-  int expect = kXValue;
-  int key = -1;  // key of the member whose value comes next (show / entry objects)
-  uint32_t seen_show = 0, seen_entry = 0;
-  int hard = 0;  // first hard error met; reported only if the document is JSON at all
-  bool top_is_object = false;
+struct DocWalker {
+  DocCursor c;
+  int64_t s;  // the document (row of the show columns)
+  // grammar
+  uint64_t kinds;  // bit d: the container open at depth d+1 is an object
+  int depth, sem, saved_sem, skip_base, expect;
+  int key;  // key of the member whose value comes next (show / entry objects), -1 = not one the table holds
+  uint32_t seen_show, seen_entry;
+  int hard;  // first hard error met; reported only if the document is JSON at all
+  bool top_is_object;
   // the open entry
-  double e_delay = 0.0, e_ts = 0.0;
-  bool e_valid = false;
-  uint32_t e_row = 0;
+  double e_delay, e_ts;
+  bool e_valid;
+  uint32_t e_row;
+  // the open string
+  int str_mode;  // 0 none, 1 key, 2 value
+  int str_heap;  // value: the heap that takes it, -1 = only recognised
+  uint32_t str_len;
+  uint64_t k0, k1;  // key: its first 16 bytes
+  uint8_t* dst;     // value, pass 2: where its bytes go
+  uint32_t high;    // pending high surrogate of a \uD8xx escape
+  bool lone;        // an escape named a surrogate without its partner (a JS string that has no UTF-8 form)
 
-#define PIE_HARD(code) do { if (!hard) hard = (code); } while (0)
+  PIE_JW_HD void begin(const uint8_t* text, int64_t from, int64_t to, int64_t doc) {
+    c.open(text, from, to);
+    s = doc;
+    kinds = 0;
+    depth = 0;
+    sem = kSemTop;
+    saved_sem = kSemDone;
+    skip_base = 0;
+    expect = kXValue;
+    key = -1;
+    seen_show = seen_entry = 0;
+    hard = 0;
+    top_is_object = false;
+    e_delay = e_ts = 0.0;
+    e_valid = false;
+    e_row = 0;
+    str_mode = 0;
+    str_heap = -1;
+    str_len = 0;
+    k0 = k1 = 0;
+    dst = nullptr;
+    high = 0;
+    lone = false;
+  }
+  PIE_JW_HD void set_hard(int code) { if (!hard) hard = code; }
 
-  auto begin_entry = [&]() {
+  PIE_JW_HD void put(uint32_t b) {
+    if (str_mode == 1) {
+      if (str_len < 8) k0 |= (uint64_t)b << (8 * str_len);
+      else if (str_len < 16) k1 |= (uint64_t)b << (8 * (str_len - 8));
+    } else if (kFill && dst) {
+      dst[str_len] = (uint8_t)b;
+    }
+    ++str_len;
+  }
+  PIE_JW_HD void put3(uint32_t cp) {
+    put(0xE0 | (cp >> 12));
+    put(0x80 | ((cp >> 6) & 0x3F));
+    put(0x80 | (cp & 0x3F));
+  }
+  PIE_JW_HD void flush_high() {  // a high surrogate that no low one followed
+    if (high) {
+      lone = true;
+      put3(high);
+      high = 0;
+    }
+  }
+  // n (1..8) plain bytes, the low bytes of `chunk` (zero above them)
+  PIE_JW_HD void put_run(uint64_t chunk, int n) {
+    if (str_mode == 1) {
+      if (str_len < 8) {
+        k0 |= chunk << (8 * str_len);
+        if (str_len > 0 && str_len + n > 8) k1 |= chunk >> (8 * (8 - str_len));
+      } else if (str_len < 16) {
+        k1 |= chunk << (8 * (str_len - 8));
+      }
+    } else if (kFill && dst) {
+      uint8_t* p = dst + str_len;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < n) p[k] = (uint8_t)(chunk >> (8 * k));
+    }
+    str_len += (uint32_t)n;
+  }
+
+  PIE_JW_HD void begin_entry(uint32_t (&cnt)[kPlanes], const IngestOut& out) {
     e_row = cnt[kPlaneEntries]++;
     seen_entry = 0;
     e_delay = 0.0;
@@ -318,35 +298,169 @@ PIE_JW_HD int walk_document(DocCursor& c, uint32_t (&cnt)[kPlanes], const Ingest
       for (int h = kHeapEntry0; h < kHeapEntry0 + 14; ++h) out.off[h][e_row] = (int32_t)cnt[h];
       out.actions_list[e_row] = (int32_t)cnt[kPlaneActionItems];
     }
-  };
-  auto end_entry = [&]() {
+  }
+  PIE_JW_HD void end_entry(const IngestOut& out) {
     if (kFill) {
       out.delay_sec[e_row] = e_delay;
       out.delay_valid[e_row] = e_valid ? 1 : 0;
       out.entry_ts[e_row] = e_ts;
     }
-  };
+  }
+  // a value is through: what may follow it (a comma right behind it is taken at once)
+  PIE_JW_HD void after_value() {
+    if (depth == 0) {
+      expect = kXEnd;
+      return;
+    }
+    expect = kXCommaOrClose;
+    if (c.peek() == ',') {
+      c.next();
+      expect = ((kinds >> (depth - 1)) & 1) ? kXKey : kXValue;
+    }
+  }
 
-  for (;;) {
+  // ---- inside a string: up to 8 plain bytes at once, then whatever ends the run
+  PIE_JW_HD int string_step(uint32_t (&cnt)[kPlanes]) {
+    if (c.left == 0) return kDocDropped;  // the text ends inside the string
+    const uint64_t x = c.cur;
+    const uint64_t k80 = 0x8080808080808080ull, k01 = 0x0101010101010101ull;
+    const uint64_t q = x ^ (k01 * 0x22), bs = x ^ (k01 * 0x5C);
+    // 0x80 in every byte that is >= 0x80, < 0x20, '"' or '\\' — exact up to and including the first such byte
+    const uint64_t special = (x & k80) | ((x - k01 * 0x20) & ~x & k80) | ((q - k01) & ~q & k80) | ((bs - k01) & ~bs & k80);
+    int n = special ? (jw_ctz64(special) >> 3) : 8;
+    if (n > c.left) n = c.left;
+    if (n > 0) {
+      flush_high();
+      put_run(n == 8 ? x : (x & ((1ull << (8 * n)) - 1)), n);
+      c.advance(n);
+      if (c.left == 0 || n == 8) return kDocRunning;
+      // the rest of this word starts with the byte that ended the run: take it in the same step
+      const uint64_t y = c.cur & 0xFF;
+      if (!(y == '"' || y == '\\' || y < 0x20 || y >= 0x80)) return kDocRunning;
+    }
+    const int ch = c.peek();
+    c.next();
+    if (ch == '"') {
+      flush_high();
+      const int mode = str_mode;
+      str_mode = 0;
+      if (mode == 1) {
+        if (sem == kSemShow) {
+          key = match_show_key(str_len, k0, k1);
+          if (key >= 0) { if (seen_show >> key & 1) set_hard(kDocUnsupported); seen_show |= 1u << key; }
+        } else if (sem == kSemEntry) {
+          key = match_entry_key(str_len, k0, k1);
+          if (key >= 0) { if (seen_entry >> key & 1) set_hard(kDocUnsupported); seen_entry |= 1u << key; }
+        }
+        expect = kXColon;
+        if (c.peek() == ':') { c.next(); expect = kXValue; }
+      } else {
+        if (str_heap >= 0) {
+          cnt[str_heap] += str_len;
+          if (lone) set_hard(kDocSchema);
+        }
+        after_value();
+      }
+      return kDocRunning;
+    }
+    if (ch == '\\') {
+      const int e = c.peek();
+      if (e < 0) return kDocDropped;
+      c.next();
+      uint32_t cp;
+      if (e == 'u') {
+        cp = 0;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const int h = hex_value(c.peek());
+          if (h < 0) return kDocDropped;
+          c.next();
+          cp = cp * 16 + (uint32_t)h;
+        }
+        if (high) {
+          if (cp >= 0xDC00 && cp <= 0xDFFF) {
+            cp = 0x10000 + ((high - 0xD800) << 10) + (cp - 0xDC00);
+            high = 0;
+            put(0xF0 | (cp >> 18));
+            put(0x80 | ((cp >> 12) & 0x3F));
+            put(0x80 | ((cp >> 6) & 0x3F));
+            put(0x80 | (cp & 0x3F));
+            return kDocRunning;
+          }
+          flush_high();  // the pending one stays alone; this unit starts over
+        }
+        if (cp >= 0xD800 && cp <= 0xDBFF) { high = cp; return kDocRunning; }
+        if (cp >= 0xDC00 && cp <= 0xDFFF) lone = true;
+      } else {
+        switch (e) {
+          case '"': cp = '"'; break;
+          case '\\': cp = '\\'; break;
+          case '/': cp = '/'; break;
+          case 'b': cp = 8; break;
+          case 'f': cp = 12; break;
+          case 'n': cp = 10; break;
+          case 'r': cp = 13; break;
+          case 't': cp = 9; break;
+          default: return kDocDropped;
+        }
+        flush_high();
+      }
+      if (cp < 0x80) {
+        put(cp);
+      } else if (cp < 0x800) {
+        put(0xC0 | (cp >> 6));
+        put(0x80 | (cp & 0x3F));
+      } else {
+        put3(cp);
+      }
+      return kDocRunning;
+    }
+    if (ch < 0x20) return kDocDropped;  // control characters must be escaped
+    // ch >= 0x80.  UTF-8: well-formed sequences only (Unicode table 3-7); anything else is reported, and the walk
+    // goes on as if the bytes were text so that "is it JSON at all" is still answered
+    flush_high();
+    put((uint32_t)ch);
+    int need = 0;
+    int lo = 0x80, hi = 0xBF;
+    if (ch < 0xC2) set_hard(kDocUnsupported);
+    else if (ch < 0xE0) need = 1;
+    else if (ch < 0xF0) { need = 2; if (ch == 0xE0) lo = 0xA0; if (ch == 0xED) hi = 0x9F; }
+    else if (ch < 0xF5) { need = 3; if (ch == 0xF0) lo = 0x90; if (ch == 0xF4) hi = 0x8F; }
+    else set_hard(kDocUnsupported);
+#pragma unroll 1
+    for (int k = 0; k < need; ++k) {
+      const int b = c.peek();
+      if (b < lo || b > hi) { set_hard(kDocUnsupported); break; }
+      c.next();
+      put((uint32_t)b);
+      lo = 0x80;
+      hi = 0xBF;
+    }
+    return kDocRunning;
+  }
+
+  // ---- between strings: one token of the grammar
+  PIE_JW_HD int token_step(uint32_t (&cnt)[kPlanes], const IngestOut& out, const Pow5Table& pow5) {
     int ch = c.peek();
     while (ch == ' ' || ch == '\n' || ch == '\r' || ch == '\t') { c.next(); ch = c.peek(); }
     if (ch < 0) {
       if (expect != kXEnd) return kDocDropped;
-      break;
+      if (hard) return hard;
+      return top_is_object ? kDocOk : kDocDropped;
     }
     if (expect == kXEnd) return kDocDropped;  // something after the value
     c.next();
 
-    // ---- punctuation the grammar state asks for
+    // punctuation the grammar state asks for
     if (expect == kXColon) {
       if (ch != ':') return kDocDropped;
       expect = kXValue;
-      continue;
+      return kDocRunning;
     }
     bool closing = false;
     if (expect == kXCommaOrClose) {
       const bool in_object = (kinds >> (depth - 1)) & 1;
-      if (ch == ',') { expect = in_object ? kXKey : kXValue; continue; }
+      if (ch == ',') { expect = in_object ? kXKey : kXValue; return kDocRunning; }
       if (ch != (in_object ? '}' : ']')) return kDocDropped;
       closing = true;
     } else if (expect == kXKeyOrClose && ch == '}') {
@@ -357,41 +471,29 @@ PIE_JW_HD int walk_document(DocCursor& c, uint32_t (&cnt)[kPlanes], const Ingest
     if (closing) {
       --depth;
       if (sem == kSemSkip) { if (depth == skip_base) sem = saved_sem; }
-      else if (sem == kSemEntry) { end_entry(); sem = kSemEntries; }
+      else if (sem == kSemEntry) { end_entry(out); sem = kSemEntries; }
       else if (sem == kSemActions) sem = kSemEntry;
       else if (sem == kSemShow) sem = kSemDone;
       else sem = kSemShow;  // crew, entries
-      expect = depth == 0 ? kXEnd : kXCommaOrClose;
-      continue;
+      after_value();
+      return kDocRunning;
     }
 
-    // ---- a key
+    // a key
     if (expect == kXKeyOrClose || expect == kXKey) {
       if (ch != '"') return kDocDropped;
-      bool lone = false;
-      if (sem == kSemShow || sem == kSemEntry) {
-        StrSink<true> sink{nullptr, 0, 0, 0};
-        const int r = scan_string<true>(c, sink, &lone);
-        if (r == kStrSyntax) return kDocDropped;
-        if (r == kStrBadUtf8) return kDocUnsupported;
-        if (sem == kSemShow) {
-          key = match_show_key(sink.len, sink.k0, sink.k1);
-          if (key >= 0) { if (seen_show >> key & 1) PIE_HARD(kDocUnsupported); seen_show |= 1u << key; }
-        } else {
-          key = match_entry_key(sink.len, sink.k0, sink.k1);
-          if (key >= 0) { if (seen_entry >> key & 1) PIE_HARD(kDocUnsupported); seen_entry |= 1u << key; }
-        }
-      } else {
-        StrSink<false> sink{nullptr, 0, 0, 0};
-        const int r = scan_string<false>(c, sink, &lone);
-        if (r == kStrSyntax) return kDocDropped;
-        if (r == kStrBadUtf8) return kDocUnsupported;
-      }
-      expect = kXColon;
-      continue;
+      str_mode = 1;
+      str_heap = -1;
+      str_len = 0;
+      k0 = k1 = 0;
+      dst = nullptr;
+      high = 0;
+      lone = false;
+      key = -1;
+      return kDocRunning;
     }
 
-    // ---- a value (expect is kXValue, or kXValueOrClose with something that is not ']').  Its role:
+    // a value (expect is kXValue, or kXValueOrClose with something that is not ']').  Its role:
     //   heap >= 0   a text field of the table: string or null, anything else is a schema error
     //   is_item     an element of crew / actions: counted even when null
     //   num_role    1 createdAt, 2 archivedAt, 3 ts (a finite number or absent), 4 delaySec (number | null)
@@ -417,9 +519,9 @@ PIE_JW_HD int walk_document(DocCursor& c, uint32_t (&cnt)[kPlanes], const Ingest
       heap = kHeapActions;
       is_item = true;
     } else if (at == kSemEntries) {
-      begin_entry();  // whatever the element is, it is a row: a non-object has no fields (pack_shows: `e = {}`)
+      begin_entry(cnt, out);  // whatever the element is, it is a row: a non-object has no fields (pack_shows: `e = {}`)
       if (ch == '{') open_sem = kSemEntry;
-      else end_entry();
+      else end_entry(out);
     } else if (at == kSemTop) {
       if (ch == '{') { open_sem = kSemShow; top_is_object = true; }
       else if (ch == '[') { top_is_object = true; }  // typeof [] === 'object': an empty show, not a dropped row
@@ -433,7 +535,7 @@ PIE_JW_HD int walk_document(DocCursor& c, uint32_t (&cnt)[kPlanes], const Ingest
 
     if (ch == '{' || ch == '[') {
       if (depth >= kMaxDepth) return kDocUnsupported;
-      if (heap >= 0 || num_role == 4) PIE_HARD(kDocSchema);
+      if (heap >= 0 || num_role == 4) set_hard(kDocSchema);
       if (ch == '{') kinds |= 1ull << depth;
       else kinds &= ~(1ull << depth);
       if (open_sem == kSemSkip) {
@@ -443,21 +545,19 @@ PIE_JW_HD int walk_document(DocCursor& c, uint32_t (&cnt)[kPlanes], const Ingest
       }
       ++depth;
       expect = ch == '{' ? kXKeyOrClose : kXValueOrClose;
-      continue;
+      return kDocRunning;
     }
     if (ch == '"') {
-      bool lone = false;
-      StrSink<false> sink{nullptr, 0, 0, 0};
-      if (heap >= 0 && kFill) sink.dst = out.data[heap] + cnt[heap];
-      const int r = scan_string<false>(c, sink, &lone);
-      if (r == kStrSyntax) return kDocDropped;
-      if (r == kStrBadUtf8) return kDocUnsupported;
-      if (heap >= 0) {
-        cnt[heap] += sink.len;
-        if (lone) PIE_HARD(kDocSchema);
-      }
-      if (num_role == 4) PIE_HARD(kDocSchema);  // delaySec: number or null
-    } else if (ch == '-' || (ch >= '0' && ch <= '9')) {
+      str_mode = 2;
+      str_heap = heap;
+      str_len = 0;
+      dst = (kFill && heap >= 0) ? out.data[heap] + cnt[heap] : nullptr;
+      high = 0;
+      lone = false;
+      if (num_role == 4) set_hard(kDocSchema);  // delaySec: number or null
+      return kDocRunning;
+    }
+    if (ch == '-' || (ch >= '0' && ch <= '9')) {
       // the number parser wants the first byte back: a source that replays it
       struct Replay {
         DocCursor& c;
@@ -470,8 +570,8 @@ PIE_JW_HD int walk_document(DocCursor& c, uint32_t (&cnt)[kPlanes], const Ingest
       if (num_role) r = parse_json_number_from<true>(src, pow5, &v);
       else r = parse_json_number_from<false>(src, pow5, &v);
       if (r == kNumSyntax) return kDocDropped;
-      if (r == kNumUndecided) PIE_HARD(kDocUnsupported);
-      if (heap >= 0) PIE_HARD(kDocSchema);
+      if (r == kNumUndecided) set_hard(kDocUnsupported);
+      if (heap >= 0) set_hard(kDocSchema);
       if (num_role == 4) { e_delay = v; e_valid = true; }
       else if (num_role == 3) e_ts = jw_is_finite(v) ? v : jw_nan();
       else if (num_role && kFill) (num_role == 1 ? out.created_at : out.archived_at)[s] = jw_is_finite(v) ? v : jw_nan();
@@ -482,14 +582,17 @@ PIE_JW_HD int walk_document(DocCursor& c, uint32_t (&cnt)[kPlanes], const Ingest
         if (c.peek() != *lit) return kDocDropped;
         c.next();
       }
-      if (ch != 'n' && (heap >= 0 || num_role == 4)) PIE_HARD(kDocSchema);  // true / false where text / a number belongs
+      if (ch != 'n' && (heap >= 0 || num_role == 4)) set_hard(kDocSchema);  // true / false where text / a number belongs
     }
-    expect = depth == 0 ? kXEnd : kXCommaOrClose;
+    after_value();
+    return kDocRunning;
   }
-#undef PIE_HARD
-  if (hard) return hard;
-  return top_is_object ? kDocOk : kDocDropped;
-}
+
+  PIE_JW_HD int step(uint32_t (&cnt)[kPlanes], const IngestOut& out, const Pow5Table& pow5) {
+    if (str_mode != 0) return string_step(cnt);
+    return token_step(cnt, out, pow5);
+  }
+};
 
 }  // namespace jw
 }  // namespace pie

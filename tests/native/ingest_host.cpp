@@ -45,9 +45,10 @@ extern "C" void ingest_host_measure(const uint8_t* text, const int64_t* offsets,
   status[1] = -1;
   for (int64_t s = 0; s < n_docs; ++s) {
     uint32_t cnt[kPlanes] = {0};
-    DocCursor c;
-    c.open(text, offsets[s], offsets[s + 1]);
-    const int r = walk_document<false>(c, cnt, none, s, pow5);
+    DocWalker<false> w;
+    w.begin(text, offsets[s], offsets[s + 1], s);
+    int r;
+    while ((r = w.step(cnt, none, pow5)) == kDocRunning) {}
     if (r != kDocOk) {
       memset(cnt, 0, sizeof(cnt));
       if (r != kDocDropped && status[0] == 0) { status[0] = -r; status[1] = (int32_t)s; }
@@ -86,9 +87,9 @@ extern "C" void ingest_host_fill(const uint8_t* text, const int64_t* offsets, in
     out.created_at[s] = jw_nan();
     out.archived_at[s] = jw_nan();
     if (doc_status[s] == 0) {
-      DocCursor c;
-      c.open(text, offsets[s], offsets[s + 1]);
-      walk_document<true>(c, cnt, out, s, pow5);
+      DocWalker<true> w;
+      w.begin(text, offsets[s], offsets[s + 1], s);
+      while (w.step(cnt, out, pow5) == kDocRunning) {}
     }
     if (s == n_docs - 1) {
       for (int h = 0; h < 7; ++h) out.off[h][n_docs] = (int32_t)cnt[h];
