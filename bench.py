@@ -341,7 +341,11 @@ def main():
                      + 4 * (S + 1) + (4 * _lib.PIE_CM_COUNT + _lib.PIE_CM_TEXT) * S)
     del m_i32, m_text
 
-    note("payload rows and live metrics timed; end-to-end leg (host buffers)")
+    # ... and the JSON ingest of the stored documents: a sample archive written out as
+    # show_archive.data texts, repeated on the device to the bench's number of shows
+    ingest = ingest_leg(args, dev, S, n_payload_runs, note)
+
+    note("payload rows, live metrics and JSON ingest timed; end-to-end leg (host buffers)")
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     import ctypes as C
 
@@ -437,6 +441,8 @@ def main():
                     "ms_per_launch": payload_ms, "algorithmic_bytes": payload_bytes, "json_bytes_out": payload_total,
                     "achieved_gbs": gbs(payload_bytes, payload_ms), "frac": gbs(payload_bytes, payload_ms) / peak,
                     "entries_per_s": E / (payload_ms * 1e-3)},
+                "JSON ingest of stored documents (ingest_walk_kernel x2 + scans, not part of the step)":
+                    dict(ingest, frac=ingest["achieved_gbs"] / peak),
                 "computeMetrics per show (compute_metrics_kernel, not part of the step)": {
                     "ms_per_launch": metrics_ms, "algorithmic_bytes": metrics_bytes,
                     "achieved_gbs": gbs(metrics_bytes, metrics_ms), "frac": gbs(metrics_bytes, metrics_ms) / peak,
@@ -457,6 +463,87 @@ def main():
     print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def ingest_leg(args, dev, n_shows, runs, note):
+    """pie_ingest_measure_dev + pie_ingest_fill_dev on device-resident texts (CUDA events), then pie_ingest_host with
+    pinned host texts in and the host table out (wall clock), then json.loads of the sample on one core."""
+    import ctypes as C
+
+    import torch
+
+    from sph_pie_b200 import _lib, ops
+    from sph_pie_b200.synth import synth_stored_docs
+
+    sample = min(n_shows, 8192)
+    copies = max(1, n_shows // sample)
+    docs, n_entries, text_bytes, texts = synth_stored_docs(sample, copies, dev, seed=4321)
+    bufs = ops.IngestBuffers(docs.n_docs, dev)
+    ops.ingest_measure_dev(docs, bufs)
+    totals = bufs.totals.cpu().tolist()
+    assert bufs.status.cpu().tolist()[0] == 0
+    table = ops.alloc_ingest_table(docs.n_docs, totals, dev)
+    table_bytes = table.nbytes()
+    for _ in range(2):
+        ops.ingest_measure_dev(docs, bufs)
+        ops.ingest_fill_dev(docs, bufs, table)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tm = tf = 0.0
+    for _ in range(runs):
+        ev[0].record()
+        ops.ingest_measure_dev(docs, bufs)
+        ev[1].record()
+        ops.ingest_fill_dev(docs, bufs, table)
+        ev[2].record()
+        torch.cuda.synchronize()
+        tm += ev[0].elapsed_time(ev[1]) / runs
+        tf += ev[1].elapsed_time(ev[2]) / runs
+    note(f"JSON ingest on the device: {tm:.2f} + {tf:.2f} ms for {text_bytes / 1e9:.2f} GB of text")
+    # host buffers through the C ABI
+    lib = _lib.load()
+    hdocs = docs.to("cpu").pin()
+    del table, docs
+    d = hdocs.c()
+    view = _lib.ArchiveViewC()
+    st = torch.empty(hdocs.n_docs, dtype=torch.uint8)
+    tot = torch.zeros(_lib.PIE_INGEST_TOTALS, dtype=torch.int64)
+    bad = C.c_int64(-1)
+
+    def host_call():
+        _lib.check(lib.pie_ingest_host(C.byref(d), C.byref(view), st.data_ptr(), tot.data_ptr(), C.byref(bad)))
+
+    host_call()
+    host_call()
+    h_runs = max(2, min(runs, 4))
+    t0 = time.perf_counter()
+    for _ in range(h_runs):
+        host_call()
+    host_s = (time.perf_counter() - t0) / h_runs
+    h2d, d2h = _lib.last_transfer_bytes()
+    lib.pie_ingest_host_release()
+    # one core of the host through Python's json module (C accelerated; parse only, no projection on the table)
+    t0 = time.perf_counter()
+    parsed = 0
+    while time.perf_counter() - t0 < 2.0:
+        for t in texts:
+            json.loads(t)
+        parsed += 1
+    cpu_s = (time.perf_counter() - t0) / parsed
+    sample_bytes = sum(len(t.encode("utf-8")) for t in texts)
+    alg = 2 * text_bytes + table_bytes + 2 * 4 * 26 * hdocs.n_docs
+    ms = tm + tf
+    return {
+        "ms_per_launch": ms, "measure_ms": tm, "fill_ms": tf, "documents": hdocs.n_docs, "entries": n_entries,
+        "text_bytes": text_bytes, "table_bytes": table_bytes, "algorithmic_bytes": alg,
+        "achieved_gbs": alg / (ms * 1e-3) / 1e9, "text_gbs": text_bytes / (ms * 1e-3) / 1e9,
+        "entries_per_s": n_entries / (ms * 1e-3),
+        "e2e_host": {"api": "pie_ingest_host (pinned texts in, host table out)", "ms": host_s * 1e3,
+                     "entries_per_s": n_entries / host_s, "text_gbs": text_bytes / host_s / 1e9,
+                     "h2d_bytes": h2d, "d2h_bytes": d2h},
+        "cpu_json_loads": {"what": "json.loads of the sample's documents, one core, parse only", "text_mbs":
+                           sample_bytes / cpu_s / 1e6, "sample_documents": len(texts)},
+        "workload": f"{sample} synthetic shows written as JSON documents (json.dumps, no whitespace), x{copies} on the device",
+    }
 
 
 def reference_scale(args, dev):

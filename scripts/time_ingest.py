@@ -11,21 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sph_pie_b200 import _lib, ops  # noqa: E402
-from sph_pie_b200.synth import synth_archive, table_to_shows  # noqa: E402
-
-
-def replicated_docs(sample_shows, copies, device, seed=0):
-    host = synth_archive(sample_shows, seed=seed)
-    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
-    host.delay_valid[lost] = 0
-    docs = [json.dumps(s, ensure_ascii=False, separators=(",", ":")) for s in table_to_shows(host)]
-    one = ops.JsonDocs.from_texts(docs)
-    n, nbytes = one.n_docs, int(one.offsets[-1])
-    text = torch.cat([one.data[:nbytes].to(device).repeat(copies), torch.zeros(8, dtype=torch.uint8, device=device)])
-    lens = (one.offsets[1:] - one.offsets[:-1]).to(device).repeat(copies)
-    offsets = torch.zeros(n * copies + 1, dtype=torch.int64, device=device)
-    torch.cumsum(lens, 0, out=offsets[1:])
-    return ops.JsonDocs(offsets, text), host.n_entries * copies, nbytes * copies
+from sph_pie_b200.synth import synth_stored_docs  # noqa: E402
 
 
 def main():
@@ -35,7 +21,7 @@ def main():
     dev = torch.device("cuda:0")
     _lib.init(0)
     t0 = time.time()
-    docs, n_entries, nbytes = replicated_docs(sample, copies, dev)
+    docs, n_entries, nbytes, _ = synth_stored_docs(sample, copies, dev)
     print(f"docs={docs.n_docs} entries={n_entries} text={nbytes / 1e9:.3f} GB (built in {time.time() - t0:.1f}s)", flush=True)
     bufs = ops.IngestBuffers(docs.n_docs, dev)
     ops.ingest_measure_dev(docs, bufs)

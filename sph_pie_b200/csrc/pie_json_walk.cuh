@@ -588,9 +588,26 @@ struct DocWalker {
     return kDocRunning;
   }
 
+  // One step = one member of an object (key, colon, value when it is a scalar) or one element of an array, so that
+  // the lanes of a warp — which walk documents of the same make — meet again at every member: the token code runs
+  // for all of them together, and the string loops differ only in their trip counts.
   PIE_JW_HD int step(uint32_t (&cnt)[kPlanes], const IngestOut& out, const Pow5Table& pow5) {
-    if (str_mode != 0) return string_step(cnt);
-    return token_step(cnt, out, pow5);
+    int r = kDocRunning;
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {  // the key, then its value
+      if (str_mode == 0) {
+        r = token_step(cnt, out, pow5);
+        if (r != kDocRunning || str_mode == 0) return r;
+      }
+      const bool was_key = str_mode == 1;
+#pragma unroll 1
+      do {
+        r = string_step(cnt);
+        if (r != kDocRunning) return r;
+      } while (str_mode != 0);
+      if (!was_key || expect != kXValue) break;
+    }
+    return r;
   }
 };
 

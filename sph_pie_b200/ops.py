@@ -358,7 +358,8 @@ def alloc_ingest_table(n_docs: int, totals, device) -> ArchiveTable:
         return StrCol(torch.empty(rows + 1, dtype=torch.int32, device=device),
                       torch.empty(int(totals[heap]) + 8, dtype=torch.uint8, device=device))
 
-    f64 = lambda n: torch.empty(n, dtype=torch.float64, device=device)
+    # one spare element: a column of no rows still has an address (the ABI rejects NULL columns)
+    f64 = lambda n: torch.empty(n + 1, dtype=torch.float64, device=device)[:n]
     i32 = lambda n: torch.empty(n, dtype=torch.int32, device=device)
     return ArchiveTable(
         n_shows=n_docs, n_entries=E, entry_offsets=i32(n_docs + 1),
@@ -367,7 +368,7 @@ def alloc_ingest_table(n_docs: int, totals, device) -> ArchiveTable:
         created_at=f64(n_docs), archived_at=f64(n_docs),
         entry_cols={name: col(E, 8 + h) for h, name in enumerate(_lib.ENTRY_STR_COLS)},
         actions=StrListCol(i32(E + 1), col(action_items, 22)),
-        delay_sec=f64(E), delay_valid=torch.empty(E, dtype=torch.uint8, device=device), entry_ts=f64(E))
+        delay_sec=f64(E), delay_valid=torch.empty(E + 1, dtype=torch.uint8, device=device)[:E], entry_ts=f64(E))
 
 
 def _raise_ingest_status(code: int, doc: int) -> None:

@@ -291,3 +291,24 @@ def table_to_shows(table: ArchiveTable) -> List[dict]:
             show["entries"].append(entry)
         shows.append(show)
     return shows
+
+
+def synth_stored_docs(sample_shows: int, copies: int, device, seed: int = 0):
+    """Synthetic `show_archive.data` texts at bench size: a sample archive written out as JSON documents (one per
+    show, no whitespace, keys in provider order) and repeated `copies` times on `device`.
+    Returns (JsonDocs, n_entries, text_bytes, sample_docs: List[str])."""
+    import json
+
+    from .ops import JsonDocs
+
+    host = synth_archive(sample_shows, seed=seed)
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)  # JSON has no NaN / Infinity: stored as null
+    host.delay_valid[lost] = 0
+    texts = [json.dumps(s, ensure_ascii=False, separators=(",", ":")) for s in table_to_shows(host)]
+    one = JsonDocs.from_texts(texts)
+    n, nbytes = one.n_docs, int(one.offsets[-1])
+    text = torch.cat([one.data[:nbytes].to(device).repeat(copies), torch.zeros(8, dtype=torch.uint8, device=device)])
+    lens = (one.offsets[1:] - one.offsets[:-1]).to(device).repeat(copies)
+    offsets = torch.zeros(n * copies + 1, dtype=torch.int64, device=device)
+    torch.cumsum(lens, 0, out=offsets[1:])
+    return JsonDocs(offsets, text), host.n_entries * copies, nbytes * copies, texts
