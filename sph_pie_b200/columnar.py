@@ -24,6 +24,15 @@ ENTRY_KEY_TO_COL = {"id": "entry_id", "unitId": "unit_id", "planned": "planned",
                     "notes": "notes"}
 
 
+def _ptr(t: torch.Tensor) -> int:
+    """data_ptr(), except that an empty VIEW of a real allocation keeps its address (torch reports 0 for every
+    tensor without elements; the C ABI takes NULL for 'column absent')."""
+    p = t.data_ptr()
+    if p == 0 and t.numel() == 0:
+        p = t.untyped_storage().data_ptr() + t.storage_offset() * t.element_size() if t.untyped_storage().nbytes() else 0
+    return p
+
+
 @dataclass
 class StrCol:
     offsets: torch.Tensor  # int32 [n + 1]
@@ -43,7 +52,7 @@ class StrCol:
         return bytes(self.data[int(o[i]):int(o[i + 1])].cpu().numpy()).decode("utf-8")
 
     def c(self) -> _lib.StrColC:
-        return _lib.StrColC(self.offsets.data_ptr(), self.data.data_ptr())
+        return _lib.StrColC(_ptr(self.offsets), _ptr(self.data))
 
 
 @dataclass
@@ -61,7 +70,7 @@ class StrListCol:
         return self.list_offsets.numel() * 4 + self.items.nbytes()
 
     def c(self) -> _lib.StrListColC:
-        return _lib.StrListColC(self.list_offsets.data_ptr(), self.items.c())
+        return _lib.StrListColC(_ptr(self.list_offsets), self.items.c())
 
 
 def strcol_from_strings(values: List[str]) -> StrCol:
@@ -149,18 +158,18 @@ class ArchiveTable:
         v = _lib.ArchiveViewC()
         v.n_shows = self.n_shows
         v.n_entries = self.n_entries
-        v.entry_offsets = self.entry_offsets.data_ptr()
+        v.entry_offsets = _ptr(self.entry_offsets)
         for name in _lib.SHOW_STR_COLS:
             setattr(v, name, self.show_cols[name].c())
         v.crew = self.crew.c()
-        v.created_at = self.created_at.data_ptr()
-        v.archived_at = self.archived_at.data_ptr()
+        v.created_at = _ptr(self.created_at)
+        v.archived_at = _ptr(self.archived_at)
         for name in _lib.ENTRY_STR_COLS:
             setattr(v, name, self.entry_cols[name].c())
         v.actions = self.actions.c()
-        v.delay_sec = self.delay_sec.data_ptr()
-        v.delay_valid = self.delay_valid.data_ptr()
-        v.entry_ts = self.entry_ts.data_ptr()
+        v.delay_sec = _ptr(self.delay_sec)
+        v.delay_valid = _ptr(self.delay_valid)
+        v.entry_ts = _ptr(self.entry_ts)
         return v
 
     def slice_shows(self, s0: int, s1: int) -> "ArchiveTable":

@@ -193,10 +193,11 @@ PIE_JW_HD int hex_value(int c) {
   return -1;
 }
 
-// The walk is a resumable state machine: step() takes one token of the grammar, or up to 8 bytes of the string it
-// is inside of, and returns.  The kernels run it in a loop in which every lane fetches its next document as soon
-// as its current one ends, so that the lanes of a warp — each somewhere else in some document — meet in two blocks
-// of code (the string step and the token step) instead of waiting for the longest document of the warp.
+// The walk is a resumable state machine: step() takes one token of the grammar and, when that token opens a string,
+// the string to its closing quote (8 bytes at a time).  The kernels run it in a loop in which every lane fetches
+// its next document as soon as its current one ends, and in which the warp VOTES on the kind of token it serves
+// next (next_class(): strings first, then numbers, then the rest), so that lanes — each somewhere else in some
+// document — are held until they want the same code instead of every lane paying for the union of all paths.
 //   cnt[p]: pass 1 = what the document adds to plane p; pass 2 = the running position in plane p
 template <bool kFill>
 struct DocWalker {
@@ -221,6 +222,7 @@ struct DocWalker {
   uint8_t* dst;     // value, pass 2: where its bytes go
   uint32_t high;    // pending high surrogate of a \uD8xx escape
   bool lone;        // an escape named a surrogate without its partner (a JS string that has no UTF-8 form)
+  bool str_closed;  // the closing quote has been taken, close_string() is due
 
   PIE_JW_HD void begin(const uint8_t* text, int64_t from, int64_t to, int64_t doc) {
     c.open(text, from, to);
@@ -245,6 +247,7 @@ struct DocWalker {
     dst = nullptr;
     high = 0;
     lone = false;
+    str_closed = false;
   }
   PIE_JW_HD void set_hard(int code) { if (!hard) hard = code; }
 
@@ -319,6 +322,31 @@ struct DocWalker {
     }
   }
 
+  // the string that just closed: a key names the member, a value is counted into its heap
+  PIE_JW_HD void close_string(uint32_t (&cnt)[kPlanes]) {
+    const int mode = str_mode;
+    str_mode = 0;
+    str_closed = false;
+    if (mode == 1) {
+      if (sem == kSemShow) {
+        key = match_show_key(str_len, k0, k1);
+        if (key >= 0) { if (seen_show >> key & 1) set_hard(kDocUnsupported); seen_show |= 1u << key; }
+      } else if (sem == kSemEntry) {
+        key = match_entry_key(str_len, k0, k1);
+        if (key >= 0) { if (seen_entry >> key & 1) set_hard(kDocUnsupported); seen_entry |= 1u << key; }
+      }
+      expect = kXColon;
+      if (c.peek() == ':') { c.next(); expect = kXValue; }
+    } else {
+      if (str_heap >= 0) {
+        cnt[str_heap] += str_len;
+        if (lone) set_hard(kDocSchema);
+      }
+      after_value();
+    }
+  }
+  PIE_JW_HD bool in_string() const { return str_mode != 0 && !str_closed; }
+
   // ---- inside a string: up to 8 plain bytes at once, then whatever ends the run
   PIE_JW_HD int string_step(uint32_t (&cnt)[kPlanes]) {
     if (c.left == 0) return kDocDropped;  // the text ends inside the string
@@ -340,27 +368,9 @@ struct DocWalker {
     }
     const int ch = c.peek();
     c.next();
-    if (ch == '"') {
+    if (ch == '"') {  // the closing quote: what follows from it (close_string) is left to the caller, after its loop
       flush_high();
-      const int mode = str_mode;
-      str_mode = 0;
-      if (mode == 1) {
-        if (sem == kSemShow) {
-          key = match_show_key(str_len, k0, k1);
-          if (key >= 0) { if (seen_show >> key & 1) set_hard(kDocUnsupported); seen_show |= 1u << key; }
-        } else if (sem == kSemEntry) {
-          key = match_entry_key(str_len, k0, k1);
-          if (key >= 0) { if (seen_entry >> key & 1) set_hard(kDocUnsupported); seen_entry |= 1u << key; }
-        }
-        expect = kXColon;
-        if (c.peek() == ':') { c.next(); expect = kXValue; }
-      } else {
-        if (str_heap >= 0) {
-          cnt[str_heap] += str_len;
-          if (lone) set_hard(kDocSchema);
-        }
-        after_value();
-      }
+      str_closed = true;
       return kDocRunning;
     }
     if (ch == '\\') {
@@ -588,10 +598,35 @@ struct DocWalker {
     return kDocRunning;
   }
 
-  // One step = one member of an object (key, colon, value when it is a scalar) or one element of an array, so that
-  // the lanes of a warp — which walk documents of the same make — meet again at every member: the token code runs
-  // for all of them together, and the string loops differ only in their trip counts.
+  // What the document needs next, for the warp's vote (json_ingest.cu): 0 = string work (inside a string, or an
+  // opening quote is next), 1 = a number is next, 2 = any other token (brackets, literals, stray punctuation, the end).
+  PIE_JW_HD int next_class() {
+    if (str_mode != 0) return 0;
+    int ch = c.peek();
+    while (ch == ' ' || ch == '\n' || ch == '\r' || ch == '\t') { c.next(); ch = c.peek(); }
+    if (ch == '"') return 0;
+    if (ch == '-' || (ch >= '0' && ch <= '9')) return 1;
+    return 2;
+  }
+  // One step: the next token, and when that opens a string (or the walk is inside one) the string to its end.
+  // The kernels run the same three parts with the warp's votes between them (json_ingest.cu).
   PIE_JW_HD int step(uint32_t (&cnt)[kPlanes], const IngestOut& out, const Pow5Table& pow5) {
+    int r = kDocRunning;
+    if (str_mode == 0) {
+      r = token_step(cnt, out, pow5);
+      if (r != kDocRunning) return r;
+    }
+#pragma unroll 1
+    while (in_string()) {
+      r = string_step(cnt);
+      if (r != kDocRunning) return r;
+    }
+    if (str_closed) close_string(cnt);
+    return r;
+  }
+  // One member of an object (key, colon, and the value when it is a scalar) or one element of an array per step:
+  // fewer turns of the caller's loop than step().
+  PIE_JW_HD int step_member(uint32_t (&cnt)[kPlanes], const IngestOut& out, const Pow5Table& pow5) {
     int r = kDocRunning;
 #pragma unroll 1
     for (int part = 0; part < 2; ++part) {  // the key, then its value
@@ -601,10 +636,11 @@ struct DocWalker {
       }
       const bool was_key = str_mode == 1;
 #pragma unroll 1
-      do {
+      while (in_string()) {
         r = string_step(cnt);
         if (r != kDocRunning) return r;
-      } while (str_mode != 0);
+      }
+      if (str_closed) close_string(cnt);
       if (!was_key || expect != kXValue) break;
     }
     return r;

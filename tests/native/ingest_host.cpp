@@ -47,8 +47,8 @@ extern "C" void ingest_host_measure(const uint8_t* text, const int64_t* offsets,
     uint32_t cnt[kPlanes] = {0};
     DocWalker<false> w;
     w.begin(text, offsets[s], offsets[s + 1], s);
-    int r;
-    while ((r = w.step(cnt, none, pow5)) == kDocRunning) {}
+    int r;  // this pass by members, the other by tokens: both drivers of the walk are exercised, and must agree
+    while ((r = w.step_member(cnt, none, pow5)) == kDocRunning) {}
     if (r != kDocOk) {
       memset(cnt, 0, sizeof(cnt));
       if (r != kDocDropped && status[0] == 0) { status[0] = -r; status[1] = (int32_t)s; }
