@@ -8,9 +8,8 @@
 // literals, nesting checked against a 64-level kind stack) written as a resumable state machine
 // (pie_json_walk.cuh): a step is one token, or up to 8 bytes of a string found with word-wide byte tests.  The
 // kernels are persistent: a lane takes its next document from a counter the moment its current one ends, so a warp
-// never waits for its longest document; and a warp votes on the kind of token it serves next, which holds lanes
-// back until they want the same code (documents of one make then walk in step).  The text is read through the
-// read-only path 8 aligned bytes at a time with the next word already in flight.
+// never waits for its longest document.  The text is read through the read-only path 8 aligned bytes at a time with
+// the next word already in flight.
 //
 //   pass 1  ingest_measure_kernel   per document: entries, items of crew / actions, unescaped bytes of each of the 23
 //                                   string heaps; syntax errors make the document a dropped row (all counts zero)
@@ -35,9 +34,6 @@ using namespace jw;
 
 __device__ const uint64_t g_pow5_dev[PIE_POW5_128_N][2] = PIE_POW5_128_INIT;
 
-#ifndef PIE_INGEST_SCHED
-#define PIE_INGEST_SCHED 0  // how the lanes of a warp take turns (variants measured in profiles/ncu_r01_ingest_summary.md)
-#endif
 constexpr int kIngestThreads = 128;
 
 struct IngestScratch {
@@ -100,73 +96,13 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_walk_kernel(const int64
         }
       }
     }
-#if PIE_INGEST_SCHED == 0
-    // every lane takes its next step; lanes that ran out of documents leave
-    if (exhausted) break;
-    if (active) r = w.step(cnt, out, pow5);
-#elif PIE_INGEST_SCHED == 1
-    // the same, with the warp brought back together once per turn
-    if (__all_sync(0xffffffffu, exhausted)) break;
-    if (active) r = w.step(cnt, out, pow5);
-#elif PIE_INGEST_SCHED == 5
-    // a member (key and scalar value) per turn
-    if (exhausted) break;
-    if (active) r = w.step_member(cnt, out, pow5);
-#elif PIE_INGEST_SCHED == 6
-    // a whole document per turn
+    // a whole document per turn (measured against warp votes on the token kind, warp-uniform string loops and
+    // token- / member-sized turns in profiles/ncu_r01_ingest_summary.md: the fewer turns, the faster)
     if (exhausted) break;
     if (active) {
 #pragma unroll 1
       do { r = w.step_member(cnt, out, pow5); } while (r == kDocRunning);
     }
-#elif PIE_INGEST_SCHED == 7
-    // eight members per turn
-    if (exhausted) break;
-    if (active) {
-#pragma unroll 1
-      for (int k = 0; k < 8 && r == kDocRunning; ++k) r = w.step_member(cnt, out, pow5);
-    }
-#elif PIE_INGEST_SCHED == 4
-    // a member per turn, its parts taken by the whole warp together: key token, key string (a loop the warp goes
-    // round together), close; then the same for the value of the lanes whose key was followed by one
-    if (__all_sync(0xffffffffu, exhausted)) break;
-    bool go = active;
-#pragma unroll 1
-    for (int part = 0; part < 2; ++part) {
-      if (go && r == kDocRunning && w.str_mode == 0) r = w.token_step(cnt, out, pow5);
-      const bool was_key = w.str_mode == 1;
-      while (__any_sync(0xffffffffu, go && r == kDocRunning && w.in_string())) {
-        if (go && r == kDocRunning && w.in_string()) r = w.string_step(cnt);
-      }
-      if (go && r == kDocRunning && w.str_closed) w.close_string(cnt);
-      go = go && r == kDocRunning && was_key && w.expect == kXValue;
-      if (!__any_sync(0xffffffffu, go)) break;
-    }
-#elif PIE_INGEST_SCHED == 3
-    // no classes: everybody's token together, then the strings in a loop the whole warp goes round, then the closes
-    if (__all_sync(0xffffffffu, exhausted)) break;
-    if (active && w.str_mode == 0) r = w.token_step(cnt, out, pow5);
-    while (__any_sync(0xffffffffu, active && r == kDocRunning && w.in_string())) {
-      if (active && r == kDocRunning && w.in_string()) r = w.string_step(cnt);
-    }
-    if (active && r == kDocRunning && w.str_closed) w.close_string(cnt);
-#else
-    // The warp serves one kind of token at a time: strings (the bulk of every document) while any lane has one,
-    // numbers when every lane is held at a number or beyond, then everything else.  A held lane loses nothing but
-    // time, and documents of the same make fall into step.  The full-mask votes also bring the warp back together
-    // once per turn; lanes that ran out of documents keep voting (class 3: nothing) until the whole warp has.
-    const int want = active ? w.next_class() : 3;
-    const unsigned strings = __ballot_sync(0xffffffffu, want == 0), numbers = __ballot_sync(0xffffffffu, want == 1);
-    const unsigned others = __ballot_sync(0xffffffffu, want == 2), fresh = __ballot_sync(0xffffffffu, !active && !exhausted);
-    if (!(strings | numbers | others | fresh)) break;  // every lane is out of documents (a warp-uniform exit)
-    const int serve = strings ? 0 : (numbers ? 1 : 2);
-    const bool served = want == serve;
-    if (served && w.str_mode == 0) r = w.token_step(cnt, out, pow5);
-    while (__any_sync(0xffffffffu, served && r == kDocRunning && w.in_string())) {
-      if (served && r == kDocRunning && w.in_string()) r = w.string_step(cnt);
-    }
-    if (served && r == kDocRunning && w.str_closed) w.close_string(cnt);
-#endif
     if (r == kDocRunning) continue;
     active = false;
     if (!kFill) {

@@ -194,10 +194,8 @@ PIE_JW_HD int hex_value(int c) {
 }
 
 // The walk is a resumable state machine: step() takes one token of the grammar and, when that token opens a string,
-// the string to its closing quote (8 bytes at a time).  The kernels run it in a loop in which every lane fetches
-// its next document as soon as its current one ends, and in which the warp VOTES on the kind of token it serves
-// next (next_class(): strings first, then numbers, then the rest), so that lanes — each somewhere else in some
-// document — are held until they want the same code instead of every lane paying for the union of all paths.
+// the string to its closing quote (8 bytes at a time); step_member() a key with its scalar value.  The kernels run
+// it in a loop in which every lane fetches its next document as soon as its current one ends.
 //   cnt[p]: pass 1 = what the document adds to plane p; pass 2 = the running position in plane p
 template <bool kFill>
 struct DocWalker {
@@ -598,18 +596,7 @@ struct DocWalker {
     return kDocRunning;
   }
 
-  // What the document needs next, for the warp's vote (json_ingest.cu): 0 = string work (inside a string, or an
-  // opening quote is next), 1 = a number is next, 2 = any other token (brackets, literals, stray punctuation, the end).
-  PIE_JW_HD int next_class() {
-    if (str_mode != 0) return 0;
-    int ch = c.peek();
-    while (ch == ' ' || ch == '\n' || ch == '\r' || ch == '\t') { c.next(); ch = c.peek(); }
-    if (ch == '"') return 0;
-    if (ch == '-' || (ch >= '0' && ch <= '9')) return 1;
-    return 2;
-  }
   // One step: the next token, and when that opens a string (or the walk is inside one) the string to its end.
-  // The kernels run the same three parts with the warp's votes between them (json_ingest.cu).
   PIE_JW_HD int step(uint32_t (&cnt)[kPlanes], const IngestOut& out, const Pow5Table& pow5) {
     int r = kDocRunning;
     if (str_mode == 0) {
