@@ -6,11 +6,12 @@ as such.  The compute lives in libsphpie_b200.so (CUDA, C ABI in include/sph_pie
 package is the host-side mirror of the reference's functions.  There is no CPU fallback.
 """
 from . import _lib
-from ._lib import JsRangeError, PieError, UnsupportedDateError
+from ._lib import JsRangeError, PieError, SchemaError, UnsupportedDateError, UnsupportedJsonError
 from .archive import (ALL_METRIC_KEYS, ARCHIVE_METRIC_KEYS, PRIMARY_ISSUES, buildArchiveDailyGroups,
                       computeArchiveShowStats, computeArchiveShowStatsMany, computeMetrics, computeMetricsMany,
                       getOrCreateGroupMetricSummary)
 from .columnar import ArchiveTable, StrCol, StrListCol, pack_shows
+from .storage import listArchivedShows, mapArchiveRows
 from .webhook import (EXPORT_COLUMNS, archiveEntryPayloadBodies, archiveEntryPayloadBodiesMany,
                       buildArchiveEntryPayload, buildCsvRows, buildCsvRowsMany, buildMessagePayload, exportShowAsCsv)
 
@@ -20,4 +21,5 @@ __all__ = [
     "computeArchiveShowStatsMany", "getOrCreateGroupMetricSummary", "pack_shows", "computeMetrics",
     "computeMetricsMany", "EXPORT_COLUMNS", "archiveEntryPayloadBodies", "archiveEntryPayloadBodiesMany",
     "buildArchiveEntryPayload", "buildCsvRows", "buildCsvRowsMany", "buildMessagePayload", "exportShowAsCsv",
+    "SchemaError", "UnsupportedJsonError", "listArchivedShows", "mapArchiveRows",
 ]

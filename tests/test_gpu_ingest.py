@@ -165,3 +165,28 @@ def test_replicated_batch_at_scale(cuda):
         assert torch.equal(lens_big, (col.offsets[1:E + 1] - col.offsets[:E]).view(1, E).expand(k, E)), name
     assert torch.equal(table.delay_sec.view(torch.int64).view(k, E), base.delay_sec.view(torch.int64).view(1, E).expand(k, E))
     assert torch.equal(table.delay_valid.view(k, E), base.delay_valid.view(1, E).expand(k, E))
+
+
+def test_mirror_api_list_archived_shows(cuda):
+    """listArchivedShows(rows): JSON.parse per row, rows that map to null filtered out (sqlProvider.js:230-234)."""
+    from sph_pie_b200 import listArchivedShows, mapArchiveRows
+    from sph_pie_b200.columnar import pack_shows
+
+    shows = table_to_shows(synth_archive(50, seed=2))
+    rows = [{"data": po.js_json_stringify(s)} for s in shows]
+    rows[3] = {"data": "{not json"}
+    rows[10] = {"data": "null"}
+    rows[11] = "42"
+    rows[20] = {"data": None}
+    rows.append({"data": "[]"})  # an array is an object: kept, as an empty show
+    table, dropped = mapArchiveRows(rows)
+    assert dropped.nonzero().flatten().tolist() == [3, 10, 11, 20]
+    kept = [po.map_archive_row((r["data"] if r["data"] is not None else "null") if isinstance(r, dict) else r) for r in rows]
+    kept = [k for k in kept if k is not None]
+    for device in ("cuda", "cpu"):
+        got = listArchivedShows(rows, device=device)
+        assert got.n_shows == len(rows) - 4
+        assert_tables_equal(got, pack_shows(kept), "listArchivedShows " + device)
+        st = ops.show_stats(got)
+        ref = oracle_c.show_stats(pack_shows(kept))
+        assert torch.equal(st.i32.cpu(), ref.i32)
