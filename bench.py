@@ -521,6 +521,20 @@ def ingest_leg(args, dev, n_shows, runs, note):
     host_s = (time.perf_counter() - t0) / h_runs
     h2d, d2h = _lib.last_transfer_bytes()
     lib.pie_ingest_host_release()
+    # the whole workspace from the stored texts: upload, ingest, statistics + daily summaries + CSV rows on the
+    # device-resident table, results back in pinned host buffers (ops.archive_step_from_json)
+    st, dl, rows, _ = ops.archive_step_from_json(hdocs, args.tz)
+    hout = ops.HostOutputs(hdocs.n_docs, pinned=True)
+    h_off = torch.empty(rows.row_offsets.numel(), dtype=torch.int64, pin_memory=True)
+    h_csv = torch.empty(rows.data.numel(), dtype=torch.uint8, pin_memory=True)
+    del st, dl
+    ops.archive_step_from_json(hdocs, args.tz, hout, h_off, h_csv)
+    t0 = time.perf_counter()
+    for _ in range(h_runs):
+        ops.archive_step_from_json(hdocs, args.tz, hout, h_off, h_csv)
+    json_step_s = (time.perf_counter() - t0) / h_runs
+    json_step_d2h = h_csv.numel() + 8 * h_off.numel() + (4 * _lib.PIE_SI_COUNT + 8 * _lib.PIE_SF_COUNT) * hdocs.n_docs
+    del rows, hout, h_off, h_csv
     # one core of the host through Python's json module (C accelerated; parse only, no projection on the table)
     t0 = time.perf_counter()
     parsed = 0
@@ -540,6 +554,10 @@ def ingest_leg(args, dev, n_shows, runs, note):
         "e2e_host": {"api": "pie_ingest_host (pinned texts in, host table out)", "ms": host_s * 1e3,
                      "entries_per_s": n_entries / host_s, "text_gbs": text_bytes / host_s / 1e9,
                      "h2d_bytes": h2d, "d2h_bytes": d2h},
+        "e2e_json_to_outputs": {"api": "ops.archive_step_from_json: pinned texts in; ingest, statistics, daily summaries "
+                                       "and CSV rows on the device; pinned results out",
+                                "ms": json_step_s * 1e3, "entries_per_s": n_entries / json_step_s,
+                                "h2d_bytes": text_bytes + 8 * (hdocs.n_docs + 1), "d2h_bytes_at_least": json_step_d2h},
         "cpu_json_loads": {"what": "json.loads of the sample's documents, one core, parse only", "text_mbs":
                            sample_bytes / cpu_s / 1e6, "sample_documents": len(texts)},
         "workload": f"{sample} synthetic shows written as JSON documents (json.dumps, no whitespace), x{copies} on the device",

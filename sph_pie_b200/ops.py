@@ -471,3 +471,59 @@ def _table_from_library_view(view: "_lib.ArchiveViewC", n_docs: int, totals) -> 
         actions=StrListCol(arr(view.actions.list_offsets, E + 1, torch.int32), col(view.actions.items, action_items, 22)),
         delay_sec=arr(view.delay_sec, E, torch.float64), delay_valid=arr(view.delay_valid, E, torch.uint8),
         entry_ts=arr(view.entry_ts, E, torch.float64))
+
+
+def archive_step_from_json(docs: JsonDocs, tz_offset_minutes: int = 0, out: "HostOutputs" = None,
+                           row_offsets: torch.Tensor = None, data: torch.Tensor = None, device="cuda"):
+    """The archive workspace computed from the provider's stored texts: host documents in (pinned for speed), GPU
+    ingest, show statistics + daily summaries + CSV rows on the device-resident table, host results out.  The table
+    itself never leaves the GPU and no show object is ever built — the composition a binding of the reference would
+    make of pie_ingest_*_dev, pie_show_stats_dev, pie_daily_summary_dev and pie_csv_rows_dev.
+    Returns (ShowStats, DailySummary, CsvRows, dropped bool[n_docs]); `out` / `row_offsets` / `data` are reused when
+    given (data.numel() must be at least the CSV size)."""
+    _lib.ensure_init()
+    assert not docs.is_cuda
+    dev = torch.device(device)
+    n = docs.n_docs
+    d = docs.to(dev, non_blocking=True)
+    ib = IngestBuffers(n, dev)
+    ingest_measure_dev(d, ib)
+    totals = ib.totals.cpu().tolist()
+    code, doc = ib.status.cpu().tolist()
+    _raise_ingest_status(code, doc)
+    table = alloc_ingest_table(n, totals, dev)
+    ingest_fill_dev(d, ib, table)
+    S, E = n, table.n_entries
+    db = DailyBuffers(S, E, dev)
+    show_stats_dev(table, db)
+    daily_summary_dev(table, db, tz_offset_minutes)
+    sizing = CsvBuffers(E, 0, dev)
+    csv_rows_dev(table, sizing, size_only=True)
+    csv_total = int(sizing.total.cpu())  # synchronises
+    cb = CsvBuffers(E, csv_total, dev)
+    cb.scratch = sizing.scratch
+    csv_rows_dev(table, cb)
+    h = out if out is not None else HostOutputs(S, pinned=True)
+    if row_offsets is None:
+        row_offsets = torch.empty(E + 1, dtype=torch.int64, pin_memory=True)
+    if data is None:
+        data = torch.empty(max(csv_total, 1), dtype=torch.uint8, pin_memory=True)
+    assert data.numel() >= csv_total and row_offsets.numel() >= E + 1
+    Sc = db.S
+    for name in ("stats_i32", "stats_f64", "summary_f64", "summary_count"):
+        getattr(h, name)[..., :Sc].copy_(getattr(db, name), non_blocking=True)
+    for name in ("show_day_start", "show_order", "group_day_start"):
+        getattr(h, name)[:Sc].copy_(getattr(db, name), non_blocking=True)
+    h.group_offsets[:Sc + 1].copy_(db.group_offsets, non_blocking=True)
+    h.n_groups.copy_(db.n_groups, non_blocking=True)
+    h.status.copy_(db.status, non_blocking=True)
+    row_offsets[:E + 1].copy_(cb.row_offsets, non_blocking=True)
+    data[:csv_total].copy_(cb.data[:csv_total], non_blocking=True)
+    dropped = ib.doc_status[:n].bool().cpu()
+    torch.cuda.synchronize(dev)
+    _raise_daily_status(int(h.status[0]), int(h.status[1]))
+    G = int(h.n_groups[0])
+    stats = ShowStats(h.stats_i32[:, :S], h.stats_f64[:, :S])
+    daily = DailySummary(G, h.show_day_start[:S], h.show_order[:S], h.group_day_start[:G], h.group_offsets[:G + 1],
+                         h.summary_f64[:, :, :G], h.summary_count[:, :G])
+    return stats, daily, CsvRows(row_offsets[:E + 1], data[:csv_total]), dropped

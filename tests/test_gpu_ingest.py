@@ -190,3 +190,22 @@ def test_mirror_api_list_archived_shows(cuda):
         st = ops.show_stats(got)
         ref = oracle_c.show_stats(pack_shows(kept))
         assert torch.equal(st.i32.cpu(), ref.i32)
+
+
+def test_archive_step_from_stored_texts(cuda):
+    """Host texts -> GPU ingest -> statistics, daily summaries and CSV rows -> host: the same results as the
+    operators on the source table (which the C oracle checks)."""
+    host = synth_archive(3000, seed=41, shuffle_days=True)
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+    host.delay_valid[lost] = 0
+    host.delay_sec[lost] = 0.0
+    docs = ops.JsonDocs.from_texts([json.dumps(s, ensure_ascii=False, separators=(",", ":")) for s in table_to_shows(host)])
+    stats, daily, rows, dropped = ops.archive_step_from_json(docs.pin(), tz_offset_minutes=-300)
+    assert not bool(dropped.any())
+    ref_stats, ref_daily, rc, _ = oracle_c.archive_analytics(host, tz_offset_minutes=-300)
+    assert rc == 0
+    from helpers import assert_analytics_equal
+
+    assert_analytics_equal((stats, daily), (ref_stats, ref_daily), "from JSON")
+    ref_offsets, ref_csv = oracle_c.csv_rows(host)
+    assert torch.equal(rows.row_offsets, ref_offsets) and torch.equal(rows.data, ref_csv)
