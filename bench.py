@@ -343,7 +343,8 @@ def main():
 
     # ... and the JSON ingest of the stored documents: a sample archive written out as
     # show_archive.data texts, repeated on the device to the bench's number of shows
-    ingest = ingest_leg(args, dev, S, n_payload_runs, note)
+    # (N = 1 only, like the CPU baseline: it is reported by rank 0 and would only add pinned memory on the others)
+    ingest = ingest_leg(args, dev, S, n_payload_runs, note) if world == 1 else None
 
     note("payload rows, live metrics and JSON ingest timed; end-to-end leg (host buffers)")
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
@@ -442,7 +443,7 @@ def main():
                     "achieved_gbs": gbs(payload_bytes, payload_ms), "frac": gbs(payload_bytes, payload_ms) / peak,
                     "entries_per_s": E / (payload_ms * 1e-3)},
                 "JSON ingest of stored documents (ingest_walk_kernel x2 + scans, not part of the step)":
-                    dict(ingest, frac=ingest["achieved_gbs"] / peak),
+                    dict(ingest, frac=ingest["achieved_gbs"] / peak) if ingest else None,
                 "computeMetrics per show (compute_metrics_kernel, not part of the step)": {
                     "ms_per_launch": metrics_ms, "algorithmic_bytes": metrics_bytes,
                     "achieved_gbs": gbs(metrics_bytes, metrics_ms), "frac": gbs(metrics_bytes, metrics_ms) / peak,

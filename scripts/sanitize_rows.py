@@ -30,3 +30,18 @@ for table in (host, long_show):
     ops.archive_analytics(dev, -300)
     ops.compute_metrics(dev)
 print("ok")
+
+# JSON ingest: both walks, hostile documents included (escapes, surrogate pairs, damaged texts, ragged sizes)
+import json  # noqa: E402
+
+from sph_pie_b200.synth import table_to_shows  # noqa: E402
+
+texts = [json.dumps(s, ensure_ascii=(i % 2 == 0)) for i, s in enumerate(table_to_shows(host.slice_shows(0, min(shows, 500))))]
+texts += ['{"id":"\\ud83d\\ude81 \\u00e9","entries":[null,{"delaySec":1e-7,"actions":["a",null]}]}', "", "{", '{"id":"cut',
+          "[" * 64 + "]" * 64, json.dumps({"notes": "x" * 70000, "entries": [{}] * 700}), "null"]
+docs = ops.JsonDocs.from_texts(texts)
+for d in (docs, docs.to("cuda:0")):
+    table, status = ops.ingest_json(d)
+    assert int(status.sum()) == 4, status.sum()
+torch.cuda.synchronize()
+print("ingest ok", table.n_shows, table.n_entries)

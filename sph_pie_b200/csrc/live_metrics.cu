@@ -4,8 +4,9 @@
 // delay as (sum / n).toFixed(2), and the three most frequent primary issues of the entries that did not
 // complete.
 //
-// A thread per show.  The entries of a show are a run of consecutive rows, so the threads of a warp read
-// nearby rows of the same columns (the rows of ~32 consecutive shows: a few KB per column).  The issue
+// A CTA per 128 shows, whose entries are one contiguous row range of the entry columns: the rows are classified
+// row-parallel (coalesced loads, a byte + a double per row into shared memory), then a thread per show walks its
+// rows in entry order from shared memory (the left-to-right float sum needs the order).  The issue
 // ranking needs no per-show table of distinct strings: an entry that is the FIRST carrier of its issue
 // counts the later carriers and enters a three-slot ranking; "first" and "later" are decided by comparing
 // strings — O(k^2) in the k entries of the show that carry an issue, k <= 21 by the reference's own rules
@@ -124,43 +125,71 @@ __device__ __forceinline__ bool ranks_before(const Ranked& a, const Ranked& b) {
   return a.count != b.count ? a.count > b.count : a.order < b.order;
 }
 
-__global__ void __launch_bounds__(128) compute_metrics_kernel(pie_archive_view v, int32_t* __restrict__ out,
-                                                              uint8_t* __restrict__ text, int64_t stride) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= v.n_shows) return;
-  const int e0 = v.entry_offsets[s], e1 = v.entry_offsets[s + 1];
+constexpr int kCmShows = 128;   // shows per CTA: a thread per show in the show-parallel phases
+constexpr int kCmChunk = 2048;  // rows of the entry columns staged in shared memory per round
+
+// what pass 1 needs of a row, in one byte
+constexpr uint32_t kCmPlanned = 1, kCmCompleted = 2, kCmNoLaunch = 4, kCmAbort = 8, kCmDelay = 16, kCmCarries = 32;
+
+__global__ void __launch_bounds__(kCmShows) compute_metrics_kernel(pie_archive_view v, int32_t* __restrict__ out,
+                                                                   uint8_t* __restrict__ text, int64_t stride) {
+  __shared__ double sm_delay[kCmChunk];
+  __shared__ uint8_t sm_code[kCmChunk];
+  const int64_t s_first = (int64_t)blockIdx.x * kCmShows;
+  const int64_t s_last = (s_first + kCmShows < v.n_shows ? s_first + kCmShows : v.n_shows);  // one past
+  const int64_t s = s_first + threadIdx.x;
+  const bool mine = s < v.n_shows;
+  const int e0 = mine ? v.entry_offsets[s] : 0, e1 = mine ? v.entry_offsets[s + 1] : 0;
+  const int tile_begin = v.entry_offsets[s_first], tile_end = v.entry_offsets[s_last];
   int planned = 0, completed = 0, no_launch = 0, abort_ = 0, dn = 0;
   double sum = 0.0;  // delays.reduce((a, b) => a + b, 0): left to right
-  // pass 1: counts; which of the first 64 entries carry an issue (status !== 'Completed' && primaryIssue).
-  // The strings are compared as aligned 32-bit words (exact match: all mask bytes 0xFF); there is no store in
-  // the loop, so the unrolled iterations' loads overlap.
-  unsigned long long carries = 0;
-#pragma unroll 4
-  for (int e = e0; e < e1; ++e) {
-    const int pb = v.planned.offsets[e], pn = v.planned.offsets[e + 1] - pb;
-    const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
-    const int in = v.primary_issue.offsets[e + 1] - v.primary_issue.offsets[e];
-    const bool dvalid = v.delay_valid[e] != 0;
-    const double d = v.delay_sec[e];
-    uint32_t xp[1], xs[3];
-    fetch_words_raw<1>(v.planned.data + pb, pn == 3 ? 3 : 0, xp);
-    fetch_words_raw<3>(v.status.data + sb, (sn == 9 || sn == 5) ? sn : 0, xs);
-    planned += (pn == 3 && (xp[0] & 0xFFFFFFu) == lit_word("Yes", 0));
-    const bool nine = sn == 9, five = sn == 5;
-    const bool comp = nine && xs[0] == lit_word("Completed", 0) && xs[1] == lit_word("Completed", 1) &&
-                      (xs[2] & 0xFFu) == lit_word("Completed", 2);
-    const bool nol = nine && xs[0] == lit_word("No-launch", 0) && xs[1] == lit_word("No-launch", 1) &&
-                     (xs[2] & 0xFFu) == lit_word("No-launch", 2);
-    const bool abo = five && xs[0] == lit_word("Abort", 0) && (xs[1] & 0xFFu) == lit_word("Abort", 1);
-    completed += comp;
-    no_launch += nol;
-    abort_ += abo;
-    if (dvalid) {  // typeof v === 'number'
-      sum = sum + d;
-      ++dn;
+  unsigned long long carries = 0;  // which of the first 64 entries carry an issue (status !== 'Completed' && primaryIssue)
+  // pass 1.  The rows of the CTA's shows are one contiguous range of the entry columns, taken in rounds of kCmChunk:
+  //   phase A, row-parallel (consecutive threads read consecutive rows: coalesced): the strings are compared as
+  //            aligned 32-bit words (exact match) and every row becomes one byte, its delay one double;
+  //   phase B, show-parallel: a thread walks the rows of its show in entry order from shared memory.
+  for (int c0 = tile_begin; c0 < tile_end; c0 += kCmChunk) {
+    const int c1 = tile_end - c0 > kCmChunk ? c0 + kCmChunk : tile_end;
+    for (int e = c0 + (int)threadIdx.x; e < c1; e += kCmShows) {
+      const int pb = v.planned.offsets[e], pn = v.planned.offsets[e + 1] - pb;
+      const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
+      const int in = v.primary_issue.offsets[e + 1] - v.primary_issue.offsets[e];
+      const bool dvalid = v.delay_valid[e] != 0;
+      uint32_t xp[1], xs[3];
+      fetch_words_raw<1>(v.planned.data + pb, pn == 3 ? 3 : 0, xp);
+      fetch_words_raw<3>(v.status.data + sb, (sn == 9 || sn == 5) ? sn : 0, xs);
+      const bool nine = sn == 9, five = sn == 5;
+      const bool comp = nine && xs[0] == lit_word("Completed", 0) && xs[1] == lit_word("Completed", 1) &&
+                        (xs[2] & 0xFFu) == lit_word("Completed", 2);
+      const bool nol = nine && xs[0] == lit_word("No-launch", 0) && xs[1] == lit_word("No-launch", 1) &&
+                       (xs[2] & 0xFFu) == lit_word("No-launch", 2);
+      const bool abo = five && xs[0] == lit_word("Abort", 0) && (xs[1] & 0xFFu) == lit_word("Abort", 1);
+      uint32_t code = (pn == 3 && (xp[0] & 0xFFFFFFu) == lit_word("Yes", 0)) ? kCmPlanned : 0;
+      code |= comp ? kCmCompleted : 0;
+      code |= nol ? kCmNoLaunch : 0;
+      code |= abo ? kCmAbort : 0;
+      code |= dvalid ? kCmDelay : 0;  // typeof v === 'number'
+      code |= (!comp && in > 0) ? kCmCarries : 0;
+      sm_code[e - c0] = (uint8_t)code;
+      sm_delay[e - c0] = dvalid ? v.delay_sec[e] : 0.0;
     }
-    if (!comp && in > 0 && e - e0 < 64) carries |= 1ull << (e - e0);
+    __syncthreads();
+    const int b0 = e0 > c0 ? e0 : c0, b1 = e1 < c1 ? e1 : c1;
+    for (int e = b0; e < b1; ++e) {
+      const uint32_t code = sm_code[e - c0];
+      planned += code & kCmPlanned;
+      completed += (code >> 1) & 1;
+      no_launch += (code >> 2) & 1;
+      abort_ += (code >> 3) & 1;
+      if (code & kCmDelay) {
+        sum = sum + sm_delay[e - c0];
+        ++dn;
+      }
+      if ((code & kCmCarries) && e - e0 < 64) carries |= 1ull << (e - e0);
+    }
+    __syncthreads();
   }
+  if (!mine) return;
   auto carries_issue = [&](int e) -> bool {
     if (e - e0 < 64) return (carries >> (e - e0)) & 1ull;
     const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
@@ -233,7 +262,8 @@ __global__ void __launch_bounds__(128) compute_metrics_kernel(pie_archive_view v
 cudaError_t launch_compute_metrics(const pie_archive_view& v, int32_t* metrics_i32, uint8_t* avg_delay_text,
                                    int64_t stride, cudaStream_t stream) {
   if (v.n_shows == 0) return cudaSuccess;
-  compute_metrics_kernel<<<(unsigned)((v.n_shows + 127) / 128), 128, 0, stream>>>(v, metrics_i32, avg_delay_text, stride);
+  compute_metrics_kernel<<<(unsigned)((v.n_shows + kCmShows - 1) / kCmShows), kCmShows, 0, stream>>>(v, metrics_i32,
+                                                                                                    avg_delay_text, stride);
   g_launches += 1;
   return cudaGetLastError();
 }

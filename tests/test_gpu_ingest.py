@@ -209,3 +209,58 @@ def test_archive_step_from_stored_texts(cuda):
     assert_analytics_equal((stats, daily), (ref_stats, ref_daily), "from JSON")
     ref_offsets, ref_csv = oracle_c.csv_rows(host)
     assert torch.equal(rows.row_offsets, ref_offsets) and torch.equal(rows.data, ref_csv)
+
+
+def test_fill_walk_stays_inside_the_table(cuda):
+    """The second walk writes through positions it computes itself: every byte of slack behind every column it is
+    handed must come back untouched (compute-sanitizer is not available on the GPU pool)."""
+    rng = random.Random(77)
+    shows = [cases.hostile_show(rng, rng.randrange(0, 9)) for _ in range(700)]
+    docs = [stored_doc(s, rng, rng.choice(["stringify", "ascii", "pretty", "shuffled"])) for s in shows]
+    docs += ["", "{", '{"id":"cut', "[]", json.dumps({"notes": "x" * 70000, "entries": [{}] * 700})]
+    jd = ops.JsonDocs.from_texts(docs).to(cuda)
+    bufs = ops.IngestBuffers(jd.n_docs, cuda)
+    ops.ingest_measure_dev(jd, bufs)
+    totals = bufs.totals.cpu().tolist()
+    assert bufs.status.cpu().tolist()[0] == 0
+    slack = 64
+    padded = [t + slack for t in totals]  # rows and bytes: every column gets 64 spare elements
+    table = ops.alloc_ingest_table(jd.n_docs + 0, padded, cuda)
+    tensors = [table.entry_offsets, table.created_at, table.archived_at, table.delay_sec, table.delay_valid, table.entry_ts,
+               table.crew.list_offsets, table.crew.items.offsets, table.crew.items.data, table.actions.list_offsets,
+               table.actions.items.offsets, table.actions.items.data]
+    for c in list(table.show_cols.values()) + list(table.entry_cols.values()):
+        tensors += [c.offsets, c.data]
+    for t in tensors:
+        t.view(torch.uint8).fill_(0xA5)
+    ops.ingest_fill_dev(jd, bufs, table)
+    torch.cuda.synchronize()
+    S, E = jd.n_docs, totals[_lib.PIE_IT_ENTRIES]
+    ci, ai = totals[_lib.PIE_IT_CREW_ITEMS], totals[_lib.PIE_IT_ACTION_ITEMS]
+
+    def untouched(t, used, what):
+        tail = t[used:].contiguous().view(torch.uint8)  # (the show-level columns are exactly n_docs (+ 1) long: no tail)
+        assert bool((tail == 0xA5).all()), what
+
+    # the table was allocated for E + 64 entries etc.: rows used are known from the true totals
+    untouched(table.entry_offsets, S + 1, "entry_offsets")
+    untouched(table.created_at, S, "created_at")
+    untouched(table.delay_sec, E, "delay_sec")
+    untouched(table.delay_valid, E, "delay_valid")
+    untouched(table.entry_ts, E, "entry_ts")
+    untouched(table.crew.list_offsets, S + 1, "crew.list_offsets")
+    untouched(table.crew.items.offsets, ci + 1, "crew.items.offsets")
+    untouched(table.crew.items.data, totals[7], "crew.items.data")
+    untouched(table.actions.list_offsets, E + 1, "actions.list_offsets")
+    untouched(table.actions.items.offsets, ai + 1, "actions.items.offsets")
+    untouched(table.actions.items.data, totals[22], "actions.items.data")
+    for h, name in enumerate(_lib.SHOW_STR_COLS):
+        untouched(table.show_cols[name].offsets, S + 1, name)
+        untouched(table.show_cols[name].data, totals[h], name)
+    for h, name in enumerate(_lib.ENTRY_STR_COLS):
+        untouched(table.entry_cols[name].offsets, E + 1, name)
+        untouched(table.entry_cols[name].data, totals[8 + h], name)
+    # and what it did write is the oracle's table
+    ref, _ = oracle_ingest(docs)
+    table.n_entries = E
+    assert_tables_equal(table, ref, "padded table")
