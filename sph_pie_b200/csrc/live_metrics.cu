@@ -109,9 +109,15 @@ __device__ __forceinline__ bool array_index_key(const uint8_t* __restrict__ s, i
   return true;
 }
 
-__device__ __forceinline__ bool bytes_equal(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n) {
-  for (int i = 0; i < n; ++i)
-    if (a[i] != b[i]) return false;
+// a[0..n) == b[0..n), four bytes at a time (aligned words, funnel-shifted to the strings' alignment)
+__device__ __forceinline__ bool words_equal(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n) {
+  for (int i = 0; i < n; i += 4) {
+    const int m = n - i < 4 ? n - i : 4;
+    uint32_t xa[1], xb[1];
+    fetch_words<1>(a + i, m, xa);
+    fetch_words<1>(b + i, m, xb);
+    if (xa[0] != xb[0]) return false;
+  }
   return true;
 }
 
@@ -135,6 +141,11 @@ __global__ void __launch_bounds__(kCmShows) compute_metrics_kernel(pie_archive_v
                                                                    uint8_t* __restrict__ text, int64_t stride) {
   __shared__ double sm_delay[kCmChunk];
   __shared__ uint8_t sm_code[kCmChunk];
+  __shared__ uint8_t sm_show[kCmChunk];    // which of the CTA's shows a row belongs to
+  __shared__ uint16_t sm_queue[kCmChunk];  // the rows that carry an issue, in any order
+  __shared__ uint16_t sm_rank[kCmChunk];   // a first carrier: how many rows of its show carry its issue; else 0
+  __shared__ uint16_t sm_print[kCmChunk];  // a carrier's issue in 16 bits (length, first byte): unequal prints, unequal strings
+  __shared__ int sm_queued;
   const int64_t s_first = (int64_t)blockIdx.x * kCmShows;
   const int64_t s_last = (s_first + kCmShows < v.n_shows ? s_first + kCmShows : v.n_shows);  // one past
   const int64_t s = s_first + threadIdx.x;
@@ -148,8 +159,12 @@ __global__ void __launch_bounds__(kCmShows) compute_metrics_kernel(pie_archive_v
   //   phase A, row-parallel (consecutive threads read consecutive rows: coalesced): the strings are compared as
   //            aligned 32-bit words (exact match) and every row becomes one byte, its delay one double;
   //   phase B, show-parallel: a thread walks the rows of its show in entry order from shared memory.
+  if (threadIdx.x == 0) sm_queued = 0;  // (a CTA whose shows have no rows at all never enters the loop)
+  __syncthreads();
   for (int c0 = tile_begin; c0 < tile_end; c0 += kCmChunk) {
     const int c1 = tile_end - c0 > kCmChunk ? c0 + kCmChunk : tile_end;
+    if (threadIdx.x == 0) sm_queued = 0;
+    __syncthreads();
     for (int e = c0 + (int)threadIdx.x; e < c1; e += kCmShows) {
       const int pb = v.planned.offsets[e], pn = v.planned.offsets[e + 1] - pb;
       const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
@@ -172,11 +187,16 @@ __global__ void __launch_bounds__(kCmShows) compute_metrics_kernel(pie_archive_v
       code |= (!comp && in > 0) ? kCmCarries : 0;
       sm_code[e - c0] = (uint8_t)code;
       sm_delay[e - c0] = dvalid ? v.delay_sec[e] : 0.0;
+      if (code & kCmCarries) {
+        sm_queue[atomicAdd(&sm_queued, 1)] = (uint16_t)(e - c0);
+        sm_print[e - c0] = (uint16_t)(((in > 255 ? 255 : in) << 8) | v.primary_issue.data[v.primary_issue.offsets[e]]);
+      }
     }
     __syncthreads();
     const int b0 = e0 > c0 ? e0 : c0, b1 = e1 < c1 ? e1 : c1;
     for (int e = b0; e < b1; ++e) {
       const uint32_t code = sm_code[e - c0];
+      sm_show[e - c0] = (uint8_t)threadIdx.x;
       planned += code & kCmPlanned;
       completed += (code >> 1) & 1;
       no_launch += (code >> 2) & 1;
@@ -189,32 +209,10 @@ __global__ void __launch_bounds__(kCmShows) compute_metrics_kernel(pie_archive_v
     }
     __syncthreads();
   }
-  if (!mine) return;
-  auto carries_issue = [&](int e) -> bool {
-    if (e - e0 < 64) return (carries >> (e - e0)) & 1ull;
-    const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
-    return !equals_exact(v.status.data + sb, sn, "Completed") && v.primary_issue.offsets[e + 1] > v.primary_issue.offsets[e];
-  };
-  // pass 2: the first carrier of every distinct issue counts the later ones and enters the ranking
   Ranked top[3] = {{-1, 0, 0}, {-1, 0, 0}, {-1, 0, 0}};
   unsigned int created = 0;  // string keys created so far
-  for (int e = e0; e < e1; ++e) {
-    if (!carries_issue(e)) continue;
-    const int b = v.primary_issue.offsets[e], n = v.primary_issue.offsets[e + 1] - b;
-    const uint8_t* p = v.primary_issue.data + b;
-    bool first = true;
-    for (int j = e0; j < e && first; ++j) {
-      if (!carries_issue(j)) continue;
-      const int jb = v.primary_issue.offsets[j], jn = v.primary_issue.offsets[j + 1] - jb;
-      if (jn == n && bytes_equal(v.primary_issue.data + jb, p, n)) first = false;
-    }
-    if (!first) continue;
-    Ranked r{e, 1, 0};
-    for (int j = e + 1; j < e1; ++j) {
-      if (!carries_issue(j)) continue;
-      const int jb = v.primary_issue.offsets[j], jn = v.primary_issue.offsets[j + 1] - jb;
-      r.count += (jn == n && bytes_equal(v.primary_issue.data + jb, p, n));
-    }
+  auto enter = [&](int e, int count, const uint8_t* p, int n) {  // a distinct issue, met first in row e
+    Ranked r{e, count, 0};
     uint32_t index;
     if (array_index_key(p, n, &index)) r.order = index;
     else r.order = (1ull << 32) + created++;
@@ -228,7 +226,68 @@ __global__ void __launch_bounds__(kCmShows) compute_metrics_kernel(pie_archive_v
         }
       }
     }
+  };
+  // pass 2: the first carrier of every distinct issue counts the later ones and enters the ranking.
+  if (tile_end - tile_begin <= kCmChunk) {
+    // The usual case — all rows of the CTA's shows were one round, and their codes are still in shared memory:
+    //   phase C, carrier-parallel (a lane per queued row, all lanes busy): compare the row's issue with the other
+    //            carriers of its show — an equal one before it: not the first; equal ones after it: counted;
+    //   phase D, show-parallel: a thread ranks the first carriers of its show in entry order.
+    const int c0 = tile_begin;
+    const int queued = sm_queued;
+    for (int qi = threadIdx.x; qi < queued; qi += kCmShows) {
+      const int e = c0 + sm_queue[qi];
+      const int64_t sh = s_first + sm_show[e - c0];
+      const int r0 = v.entry_offsets[sh], r1 = v.entry_offsets[sh + 1];
+      const int b = v.primary_issue.offsets[e], n = v.primary_issue.offsets[e + 1] - b;
+      const uint8_t* p = v.primary_issue.data + b;
+      const uint32_t print = sm_print[e - c0];
+      int count = 1;
+      for (int j = r0; j < r1; ++j) {
+        if (j == e || !(sm_code[j - c0] & kCmCarries) || sm_print[j - c0] != print) continue;
+        const int jb = v.primary_issue.offsets[j], jn = v.primary_issue.offsets[j + 1] - jb;
+        if (jn != n || !words_equal(v.primary_issue.data + jb, p, n)) continue;
+        if (j < e) { count = 0; break; }
+        ++count;
+      }
+      sm_rank[e - c0] = (uint16_t)(count > 0xFFFF ? 0xFFFF : count);
+    }
+    __syncthreads();
+    if (mine) {
+      for (int e = e0; e < e1; ++e) {
+        if (!(sm_code[e - c0] & kCmCarries) || sm_rank[e - c0] == 0) continue;
+        const int b = v.primary_issue.offsets[e], n = v.primary_issue.offsets[e + 1] - b;
+        enter(e, sm_rank[e - c0], v.primary_issue.data + b, n);
+      }
+    }
+  } else if (mine) {
+    // shows longer than a round: the same, thread per show on the columns themselves
+    auto carries_issue = [&](int e) -> bool {
+      if (e - e0 < 64) return (carries >> (e - e0)) & 1ull;
+      const int sb = v.status.offsets[e], sn = v.status.offsets[e + 1] - sb;
+      return !equals_exact(v.status.data + sb, sn, "Completed") && v.primary_issue.offsets[e + 1] > v.primary_issue.offsets[e];
+    };
+    for (int e = e0; e < e1; ++e) {
+      if (!carries_issue(e)) continue;
+      const int b = v.primary_issue.offsets[e], n = v.primary_issue.offsets[e + 1] - b;
+      const uint8_t* p = v.primary_issue.data + b;
+      bool first = true;
+      for (int j = e0; j < e && first; ++j) {
+        if (!carries_issue(j)) continue;
+        const int jb = v.primary_issue.offsets[j], jn = v.primary_issue.offsets[j + 1] - jb;
+        if (jn == n && words_equal(v.primary_issue.data + jb, p, n)) first = false;
+      }
+      if (!first) continue;
+      int count = 1;
+      for (int j = e + 1; j < e1; ++j) {
+        if (!carries_issue(j)) continue;
+        const int jb = v.primary_issue.offsets[j], jn = v.primary_issue.offsets[j + 1] - jb;
+        count += (jn == n && words_equal(v.primary_issue.data + jb, p, n));
+      }
+      enter(e, count, p, n);
+    }
   }
+  if (!mine) return;
   int rate = 0;
   if (planned) {
     const double q = ((double)completed / (double)planned) * 100.0;  // two IEEE operations, as written in the source
