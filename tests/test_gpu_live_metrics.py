@@ -78,3 +78,17 @@ def test_sliced_table_metrics(cuda):
     for k in (_lib.CM_TOP0, _lib.CM_TOP1, _lib.CM_TOP2):  # entry rows are numbered inside the batch
         i32[k] = torch.where(i32[k] >= 0, i32[k] - e0, i32[k])
     assert torch.equal(got.i32, i32) and torch.equal(got.text, whole.text[1000:2200])
+
+
+def test_long_shows_and_look_alike_issues(cuda):
+    """Tiles longer than one shared-memory round (the thread-per-show path), shows that straddle CTAs, and issue
+    strings that agree in length and first byte (the 16-bit print passes them to the full comparison)."""
+    alike = ["Tracking lost", "Tracking lose", "Tracking losé"[:13], "T" + "x" * 12, "Tracking lost", "T" * 300, "T" * 299 + "U",
+             "T" * 300, "", "Tracking lost"]
+    shows = [{"entries": [{"status": "Abort", "planned": "Yes", "delaySec": float(i % 7), "primaryIssue": alike[i % len(alike)]}
+                          for i in range(n)]} for n in (5000, 3, 0, 2049, 2048, 700, 1, 130)]
+    shows += [{"entries": [{"status": "Abort" if i % 3 else "Completed", "primaryIssue": alike[(i * 7 + j) % len(alike)]}
+                           for i in range(j % 23)]} for j in range(400)]
+    table = pack_shows(shows)
+    assert_same(ops.compute_metrics(table.to(cuda)), table)
+    assert_same(ops.compute_metrics(table), table)
