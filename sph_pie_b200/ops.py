@@ -527,3 +527,158 @@ def archive_step_from_json(docs: JsonDocs, tz_offset_minutes: int = 0, out: "Hos
     daily = DailySummary(G, h.show_day_start[:S], h.show_order[:S], h.group_day_start[:G], h.group_offsets[:G + 1],
                          h.summary_f64[:, :, :G], h.summary_count[:, :G])
     return stats, daily, CsvRows(row_offsets[:E + 1], data[:csv_total]), dropped
+
+
+_PIPE_STREAMS = {}
+
+
+def archive_step_from_json_pipelined(docs: JsonDocs, tz_offset_minutes: int = 0, out: "HostOutputs" = None,
+                                     row_offsets: torch.Tensor = None, data: torch.Tensor = None, device="cuda",
+                                     chunk_docs: int = 131072):
+    """archive_step_from_json with the batch cut into chunks of documents that move through three streams: while
+    chunk c is ingested and its statistics / CSV rows are computed, chunk c+1 uploads and the CSV of chunk c-1
+    downloads (PCIe is full duplex).  Shows are independent, so a chunk is a complete little batch; only the daily
+    grouping needs all of them, and it reads a few show-level columns that are kept and joined at the end.
+    `row_offsets` (int64 [>= n_entries + 1]) and `data` (uint8 [>= CSV bytes]) must be given (pinned): their sizes
+    come from a first unpipelined call.  Same results as archive_step_from_json.  Chunks must stay large: a lane
+    needs ~3.5 ms for a 4 KB document, so a walk of fewer than ~10^5 documents leaves the GPU waiting on latency."""
+    from .columnar import StrCol, StrListCol
+
+    _lib.ensure_init()
+    lib = _lib.load()
+    assert not docs.is_cuda and row_offsets is not None and data is not None
+    dev = torch.device(device)
+    n = docs.n_docs
+    h = out if out is not None else HostOutputs(n, pinned=True)
+    # the same three streams on every call: torch's allocator caches blocks per stream
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _PIPE_STREAMS:
+        _PIPE_STREAMS[key] = tuple(torch.cuda.Stream(dev) for _ in range(3))
+    s_up, s_run, s_down = _PIPE_STREAMS[key]
+    torch.cuda.current_stream(dev).synchronize()
+    host_off = docs.offsets
+    bounds = list(range(0, n, chunk_docs)) + [n]
+    chunks = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
+    max_bytes = max((int(host_off[b]) - int(host_off[a]) for a, b in chunks), default=0)
+    with torch.cuda.stream(s_up):
+        offs_dev = host_off.to(dev, non_blocking=True)
+        slots = [torch.empty(max_bytes + 64, dtype=torch.uint8, device=dev) for _ in range(2)]
+    up_done = [torch.cuda.Event() for _ in chunks]
+    slot_free = [torch.cuda.Event(), torch.cuda.Event()]
+    run_done = [torch.cuda.Event() for _ in chunks]
+    db = DailyBuffers(n, 0, dev)  # the statistics planes of the whole batch; chunks write their column ranges
+    totals_host = torch.zeros(_lib.PIE_INGEST_TOTALS + 2, dtype=torch.int64, pin_memory=True)
+    csv_total_host = torch.zeros(1, dtype=torch.int64, pin_memory=True)
+    ibufs = [IngestBuffers(min(chunk_docs, max(n, 1)), dev) for _ in range(2)]
+    keep, doc_status = [], torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    ev = torch.cuda.Event()
+
+    def upload(c):
+        a, b = chunks[c]
+        first, last = int(host_off[a]), int(host_off[b])
+        with torch.cuda.stream(s_up):
+            if c >= 2:
+                s_up.wait_event(slot_free[c % 2])  # the chunk that used this slot is through its second walk
+            skew = first & 7
+            slots[c % 2][skew:skew + last - first].copy_(docs.data[first:last], non_blocking=True)
+            up_done[c].record(s_up)
+        return _lib.JsonDocsC(b - a, offs_dev.data_ptr() + 8 * a, slots[c % 2].data_ptr() + skew - first)
+
+    e_base, csv_base = 0, 0
+    pending = upload(0) if chunks else None
+    for c, (a, b) in enumerate(chunks):
+        d = pending
+        if c + 1 < len(chunks):
+            pending = upload(c + 1)
+        ib = ibufs[c % 2]
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(up_done[c])
+            _lib.check(lib.pie_ingest_measure_dev(C.byref(d), ib.scratch.data_ptr(), doc_status.data_ptr() + a,
+                                                  ib.totals.data_ptr(), ib.status.data_ptr(), s_run.cuda_stream))
+            totals_host[:_lib.PIE_INGEST_TOTALS].copy_(ib.totals, non_blocking=True)
+            totals_host[_lib.PIE_INGEST_TOTALS:].copy_(ib.status, non_blocking=True)
+            ev.record(s_run)
+        ev.synchronize()
+        totals = totals_host[:_lib.PIE_INGEST_TOTALS].tolist()
+        code, doc = int(totals_host[-2]), int(totals_host[-1])
+        if code:
+            torch.cuda.synchronize(dev)
+            _raise_ingest_status(code, doc + a if doc >= 0 else doc)
+        with torch.cuda.stream(s_run):
+            table = alloc_ingest_table(b - a, totals, dev)
+            view = table.view()
+            _lib.check(lib.pie_ingest_fill_dev(C.byref(d), ib.scratch.data_ptr(), doc_status.data_ptr() + a, C.byref(view),
+                                               s_run.cuda_stream))
+            slot_free[c % 2].record(s_run)
+            E_c = table.n_entries
+            _lib.check(lib.pie_show_stats_dev(C.byref(view), db.stats_i32.data_ptr() + 4 * a, db.stats_f64.data_ptr() + 8 * a,
+                                              db.S, s_run.cuda_stream))
+            cb = CsvBuffers(E_c, 0, dev)
+            _lib.check(lib.pie_csv_rows_dev(C.byref(view), cb.row_offsets.data_ptr(), None, 0, cb.total.data_ptr(),
+                                            cb.scratch.data_ptr(), s_run.cuda_stream))
+            csv_total_host.copy_(cb.total, non_blocking=True)
+            ev.record(s_run)
+        ev.synchronize()
+        csv_c = int(csv_total_host[0])
+        assert csv_base + csv_c <= data.numel() and e_base + E_c + 1 <= row_offsets.numel(), "row_offsets / data too small"
+        with torch.cuda.stream(s_run):
+            csv_dev = torch.empty(max(csv_c, 1), dtype=torch.uint8, device=dev)
+            _lib.check(lib.pie_csv_rows_dev(C.byref(view), cb.row_offsets.data_ptr(), csv_dev.data_ptr(), csv_c,
+                                            cb.total.data_ptr(), cb.scratch.data_ptr(), s_run.cuda_stream))
+            if csv_base:
+                cb.row_offsets += csv_base
+            run_done[c].record(s_run)
+        with torch.cuda.stream(s_down):
+            s_down.wait_event(run_done[c])
+            data[csv_base:csv_base + csv_c].copy_(csv_dev[:csv_c], non_blocking=True)
+            row_offsets[e_base:e_base + E_c + 1].copy_(cb.row_offsets, non_blocking=True)
+        keep.append((table, (cb, csv_dev, totals), None, e_base))
+        e_base += E_c
+        csv_base += csv_c
+    # the daily groups read show-level columns of every chunk: join them (offsets rebased) and run the summary once
+    with torch.cuda.stream(s_run):
+        def join_col(name):
+            heap = _lib.SHOW_STR_COLS.index(name)
+            cols = [StrCol(t.show_cols[name].offsets, t.show_cols[name].data[:int(k[2][heap])]) for t, k, _, _ in keep]
+            sizes = [int(c.data.numel()) for c in cols]
+            bases = [0]
+            for z in sizes[:-1]:
+                bases.append(bases[-1] + z)
+            offs = [c.offsets[:t.n_shows] + bs for c, bs, (t, _, _, _) in zip(cols, bases, keep)]
+            last = cols[-1].offsets[keep[-1][0].n_shows:keep[-1][0].n_shows + 1] + bases[-1]
+            return StrCol(torch.cat(offs + [last]).to(torch.int32), torch.cat([c.data for c in cols]))
+
+        if keep:
+            eo = torch.cat([t.entry_offsets[:t.n_shows] + eb for t, _, _, eb in keep]
+                           + [torch.tensor([e_base], dtype=torch.int32, device=dev)]).to(torch.int32)
+            empty = StrCol(torch.zeros(n + 1, dtype=torch.int32, device=dev), torch.zeros(8, dtype=torch.uint8, device=dev))
+            skinny = ArchiveTable(
+                n_shows=n, n_entries=e_base, entry_offsets=eo,
+                show_cols={k: (join_col(k) if k in ("show_date", "show_time") else empty) for k in _lib.SHOW_STR_COLS},
+                crew=StrListCol(torch.zeros(n + 1, dtype=torch.int32, device=dev), empty),
+                created_at=torch.cat([t.created_at for t, _, _, _ in keep]),
+                archived_at=torch.cat([t.archived_at for t, _, _, _ in keep]),
+                entry_cols={k: empty for k in _lib.ENTRY_STR_COLS}, actions=StrListCol(eo, empty),
+                delay_sec=torch.zeros(1, dtype=torch.float64, device=dev), delay_valid=torch.zeros(1, dtype=torch.uint8, device=dev),
+                entry_ts=torch.cat([t.entry_ts for t, _, _, _ in keep] + [torch.zeros(1, dtype=torch.float64, device=dev)]))
+            daily_summary_dev(skinny, db, tz_offset_minutes)
+        Sc = db.S
+        for name in ("stats_i32", "stats_f64", "summary_f64", "summary_count"):
+            getattr(h, name)[..., :Sc].copy_(getattr(db, name), non_blocking=True)
+        for name in ("show_day_start", "show_order", "group_day_start"):
+            getattr(h, name)[:Sc].copy_(getattr(db, name), non_blocking=True)
+        h.group_offsets[:Sc + 1].copy_(db.group_offsets, non_blocking=True)
+        h.n_groups.copy_(db.n_groups, non_blocking=True)
+        h.status.copy_(db.status, non_blocking=True)
+    dropped = doc_status[:n].bool().cpu()
+    torch.cuda.synchronize(dev)
+    if not keep:
+        h.n_groups.zero_()
+        h.status.zero_()
+        row_offsets[0] = 0
+    _raise_daily_status(int(h.status[0]), int(h.status[1]))
+    G = int(h.n_groups[0])
+    stats = ShowStats(h.stats_i32[:, :n], h.stats_f64[:, :n])
+    daily = DailySummary(G, h.show_day_start[:n], h.show_order[:n], h.group_day_start[:G], h.group_offsets[:G + 1],
+                         h.summary_f64[:, :, :G], h.summary_count[:, :G])
+    return stats, daily, CsvRows(row_offsets[:e_base + 1], data[:csv_base]), dropped

@@ -265,3 +265,34 @@ def test_fill_walk_stays_inside_the_table(cuda):
     table.n_entries = E
     table.delay_sec, table.delay_valid, table.entry_ts = table.delay_sec[:E], table.delay_valid[:E], table.entry_ts[:E]
     assert_tables_equal(table, ref, "padded table")
+
+
+@pytest.mark.parametrize("chunk_docs", [700, 1 << 16])
+def test_pipelined_step_from_stored_texts(cuda, chunk_docs):
+    """The chunked, three-stream composition gives what the single-batch one gives (dropped rows, shuffled days and
+    an empty show in the middle of a chunk included)."""
+    host = synth_archive(3000, seed=43, shuffle_days=True, missing_created_frac=0.05)
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+    host.delay_valid[lost] = 0
+    texts = [json.dumps(s, ensure_ascii=False, separators=(",", ":")) for s in table_to_shows(host)]
+    texts[5] = "{broken"
+    texts[699] = "null"
+    texts[700] = '{"id":"no entries","date":"2024-02-03","time":"10:00"}'
+    texts[2999] = texts[2999][:-2]
+    docs = ops.JsonDocs.from_texts(texts).pin()
+    s1, d1, r1, x1 = ops.archive_step_from_json(docs, tz_offset_minutes=120)
+    off = torch.empty(r1.row_offsets.numel(), dtype=torch.int64, pin_memory=True)
+    csv = torch.empty(r1.data.numel(), dtype=torch.uint8, pin_memory=True)
+    s2, d2, r2, x2 = ops.archive_step_from_json_pipelined(docs, 120, None, off, csv, chunk_docs=chunk_docs)
+    from helpers import assert_analytics_equal
+
+    assert torch.equal(x1, x2) and x1.nonzero().flatten().tolist() == [5, 699, 2999]
+    assert_analytics_equal((s2, d2), (s1, d1), "pipelined")
+    assert torch.equal(r1.row_offsets, r2.row_offsets) and torch.equal(r1.data, r2.data)
+    # and against the oracle on what the documents hold
+    ref_table, _ = oracle_ingest(texts)
+    ref_stats, ref_daily, rc, _ = oracle_c.archive_analytics(ref_table, tz_offset_minutes=120)
+    assert rc == 0
+    assert_analytics_equal((s2, d2), (ref_stats, ref_daily), "pipelined vs oracle")
+    ref_offsets, ref_csv = oracle_c.csv_rows(ref_table)
+    assert torch.equal(r2.row_offsets, ref_offsets) and torch.equal(r2.data, ref_csv)
