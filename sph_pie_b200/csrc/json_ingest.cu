@@ -41,8 +41,68 @@ struct IngestScratch {
   int64_t stride;
   unsigned long long* block_sums;  // [kPlanes][nblk] + the arrival counter of the scan
   unsigned long long* err_key;     // min over documents of (doc << 8 | code): the first hard error
-  unsigned long long* next_doc;    // [2] the next document to hand out in pass 1 / pass 2
+  unsigned long long* next_doc;    // [2] the next place of `order` to hand out in pass 1 / pass 2
+  uint32_t* buckets;               // [kOrderBuckets + 1] documents per length class, then where each class starts
+  int32_t* order;                  // [n_docs] the documents by length class
 };
+
+// Documents are handed to the warps in order of length (classes of 16 bytes), 32 neighbours of that order at a time:
+// documents of one length are almost always documents of one make (same number of entries, same keys), and 32 lanes
+// that start such documents together walk them in step — the same tokens in the same turns — instead of each lane
+// paying for the union of 32 unrelated paths.  Measured: 66 -> 51 ms per 2^20 documents.
+constexpr int kOrderBuckets = 4096;
+constexpr int kOrderShift = 4;
+
+__device__ __forceinline__ uint32_t length_class(const int64_t* __restrict__ doc_offsets, int64_t s) {
+  const int64_t c = (doc_offsets[s + 1] - doc_offsets[s]) >> kOrderShift;
+  return (uint32_t)(c < kOrderBuckets - 1 ? (c < 0 ? 0 : c) : kOrderBuckets - 1);
+}
+
+__global__ void __launch_bounds__(256) ingest_order_count_kernel(const int64_t* __restrict__ doc_offsets, int64_t n_docs,
+                                                                 IngestScratch sc) {
+  const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (s < n_docs) atomicAdd(sc.buckets + length_class(doc_offsets, s), 1u);
+}
+
+// counts -> where each class starts (exclusive scan of kOrderBuckets counters by one CTA of 1024 threads)
+__global__ void __launch_bounds__(1024) ingest_order_scan_kernel(IngestScratch sc) {
+  __shared__ uint32_t warp_sums[32];
+  constexpr int kPer = kOrderBuckets / 1024;
+  uint32_t item[kPer], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    item[k] = sc.buckets[threadIdx.x * kPer + k];
+    sum += item[k];
+  }
+  uint32_t v = sum;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) >= d) v += t;
+  }
+  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t ws = warp_sums[threadIdx.x];
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, ws, d);
+      if (threadIdx.x >= d) ws += t;
+    }
+    warp_sums[threadIdx.x] = ws;
+  }
+  __syncthreads();
+  uint32_t run = ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + v - sum;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    sc.buckets[threadIdx.x * kPer + k] = run;
+    run += item[k];
+  }
+}
+
+__global__ void __launch_bounds__(256) ingest_order_place_kernel(const int64_t* __restrict__ doc_offsets, int64_t n_docs,
+                                                                 IngestScratch sc) {
+  const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (s < n_docs) sc.order[atomicAdd(sc.buckets + length_class(doc_offsets, s), 1u)] = (int32_t)s;
+}
 
 constexpr int kScanItems = 4;
 constexpr int kScanThreads = 1024;
@@ -61,14 +121,20 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_walk_kernel(const int64
                                                                       IngestScratch sc, uint8_t* __restrict__ doc_status,
                                                                       IngestOut out) {
   const Pow5Table pow5{g_pow5_dev};
+  const int32_t* __restrict__ order = sc.order;
   uint32_t cnt[kPlanes];
   DocWalker<kFill> w;
   bool active = false, exhausted = false;
   int64_t s = 0;
   for (;;) {
     int r = kDocRunning;
-    if (!active && !exhausted) {
-      s = (int64_t)atomicAdd(sc.next_doc + (kFill ? 1 : 0), 1ull);
+    // the warp (all its lanes are between documents here) draws 32 places of the order at once
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(sc.next_doc + (kFill ? 1 : 0), 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const int64_t drawn = (int64_t)base + (threadIdx.x & 31);
+    if (!exhausted) {
+      s = drawn < n_docs ? order[drawn] : n_docs;
       if (s >= n_docs) {
         exhausted = true;
       } else {
@@ -98,11 +164,12 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_walk_kernel(const int64
     }
     // a whole document per turn (measured against warp votes on the token kind, warp-uniform string loops and
     // token- / member-sized turns in profiles/ncu_r01_ingest_summary.md: the fewer turns, the faster)
-    if (exhausted) break;
+    if (__all_sync(0xffffffffu, exhausted)) break;
     if (active) {
 #pragma unroll 1
       do { r = w.step_member(cnt, out, pow5); } while (r == kDocRunning);
     }
+    __syncwarp();
     if (r == kDocRunning) continue;
     active = false;
     if (!kFill) {
@@ -279,6 +346,10 @@ IngestScratch carve(void* scratch, int64_t n_docs) {
   p += ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8;
   sc.err_key = (unsigned long long*)p;
   sc.next_doc = sc.err_key + 1;
+  p = (uint8_t*)(sc.next_doc + 2);
+  sc.buckets = (uint32_t*)p;
+  p += 4 * (kOrderBuckets + 2);
+  sc.order = (int32_t*)p;
   return sc;
 }
 
@@ -310,7 +381,8 @@ IngestOut make_out(const pie_archive_table& t) {
 
 uint64_t ingest_scratch_bytes(int64_t n_docs) {
   const int64_t stride = ((n_docs > 0 ? n_docs : 1) + 31) & ~(int64_t)31;
-  return (uint64_t)kPlanes * stride * 4 + ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8 + 64;
+  return (uint64_t)kPlanes * stride * 4 + ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8 + 64 + 4 * (kOrderBuckets + 2) +
+         4 * (uint64_t)(n_docs > 0 ? n_docs : 1);
 }
 
 cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint8_t* doc_status, int64_t* totals,
@@ -320,9 +392,16 @@ cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint
   const int nblk = scan_blocks(n);
   cudaError_t e = cudaMemsetAsync(sc.block_sums, 0, ((uint64_t)kPlanes * nblk + 1) * 8, stream);
   if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(sc.buckets, 0, 4 * (kOrderBuckets + 2), stream);
+  if (e != cudaSuccess) return e;
   ingest_init_kernel<<<1, 1, 0, stream>>>(sc);
   ++g_launches;
   if (n > 0) {
+    const unsigned doc_blocks = (unsigned)((n + 255) / 256);
+    ingest_order_count_kernel<<<doc_blocks, 256, 0, stream>>>(docs.offsets, n, sc);
+    ingest_order_scan_kernel<<<1, 1024, 0, stream>>>(sc);
+    ingest_order_place_kernel<<<doc_blocks, 256, 0, stream>>>(docs.offsets, n, sc);
+    g_launches += 3;
     ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, doc_status,
                                                                             IngestOut{});
     ingest_scan_sums_kernel<<<dim3(nblk, kPlanes), kScanThreads, 0, stream>>>(sc, n, nblk);
