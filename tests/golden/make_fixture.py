@@ -31,6 +31,14 @@ PAYLOAD_JSON = ('{"showDate":"2024-07-04","showTime":"21:00","showNumber":"Indep
                 '"monkeyLead":"Nazar","operator":"Alex","monkeyId":"Drone-01","planned":true,"launched":true,'
                 '"commandReceived":true,"primaryIssue":"","subIssue":""}')
 assert po.archive_entry_payload_json(show, entry) == PAYLOAD_JSON
+# the text the provider would store for this show (JSON.stringify, sqlProvider.js:682), written out by hand:
+STORED_TEXT = ('{"id":"simulation-show","date":"2024-07-04","time":"21:00","label":"Independence Demo",'
+               '"crew":["Alex","Nazar"],"leadPilot":"Alex","monkeyLead":"Nazar","notes":"Verification run",'
+               '"entries":[{"id":"entry-001","unitId":"Drone-01","planned":"Yes","launched":"Yes","status":"Completed",'
+               '"actions":["Logged only"],"operator":"Alex","batteryId":"B-12","delaySec":0,"commandRx":"Yes",'
+               '"notes":"Green across the board"}]}')
+assert po.js_json_stringify({**show, "entries": [entry]}) == STORED_TEXT
+assert po.map_archive_row(STORED_TEXT) == {**show, "entries": [entry]}
 doc = {
     "source": "scripts/simulate-webhook.js:42-65 (show, entry); expected_* hand-derived, see make_fixture.py",
     "export_columns": po.EXPORT_COLUMNS,
@@ -41,6 +49,7 @@ doc = {
     "expected_csv_row": po.build_csv_row(row),
     "expected_archive_entry_payload": po.build_archive_entry_payload(show, entry),
     "expected_archive_payload_json": PAYLOAD_JSON,
+    "stored_text": STORED_TEXT,
     "expected_show_stats": po.compute_archive_show_stats({**show, "entries": [entry]}),
 }
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "webhook_fixture.json"), "w") as f:

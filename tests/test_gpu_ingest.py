@@ -296,3 +296,21 @@ def test_pipelined_step_from_stored_texts(cuda, chunk_docs):
     assert_analytics_equal((s2, d2), (ref_stats, ref_daily), "pipelined vs oracle")
     ref_offsets, ref_csv = oracle_c.csv_rows(ref_table)
     assert torch.equal(r2.row_offsets, ref_offsets) and torch.equal(r2.data, ref_csv)
+
+
+def test_reference_fixture_and_a_two_megabyte_document(cuda):
+    """The reference's fixture as stored text; and one document at the reference's body limit (2 MB, index.js:69) —
+    a single lane walks it (~1 s): slow, but right."""
+    import os
+
+    from sph_pie_b200.columnar import pack_shows
+
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "webhook_fixture.json")))
+    table = gpu_check(cuda, [fx["stored_text"]], "fixture")
+    assert_tables_equal(table, pack_shows([{**fx["show"], "entries": [fx["entry"]]}]), "fixture vs the objects")
+    rng = random.Random(1)
+    big = cases.hostile_show(rng, 0)
+    big["entries"] = [cases.hostile_show(rng, 1)["entries"][0] for _ in range(4500)]
+    text = stored_doc(big, rng, "stringify")
+    assert 1.5e6 < len(text.encode()) < 2.1e6
+    gpu_check(cuda, ["{}", text, fx["stored_text"]], "2 MB document", host_too=False)

@@ -174,3 +174,16 @@ def test_empty_batch_and_ragged_documents():
     big = {"id": "big", "notes": "x" * 70000, "entries": [{"notes": "y" * 5000, "actions": ["a"] * 300}] * 40}
     docs = [json.dumps(big), "{}", json.dumps({"entries": [{}] * 1000}), "[]", json.dumps(big)[:-1], '{"id":"z"}']
     check(docs)
+
+
+def test_reference_fixture_as_stored_text():
+    """The reference's one fixture (scripts/simulate-webhook.js:42-65) as the provider would store it."""
+    import os
+
+    from sph_pie_b200.columnar import pack_shows
+
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "webhook_fixture.json")))
+    table = check([fx["stored_text"]], "fixture")
+    assert_tables_equal(table, pack_shows([{**fx["show"], "entries": [fx["entry"]]}]), "fixture vs the objects")
+    assert table.entry_cols["unit_id"].get(0) == "Drone-01" and table.crew.items.get(1) == "Nazar"
+    assert float(table.delay_sec[0]) == 0.0 and int(table.delay_valid[0]) == 1
