@@ -349,8 +349,12 @@ typedef struct pie_archive_table {
 uint64_t pie_ingest_scratch_bytes(int64_t n_docs);
 int pie_ingest_measure_dev(const pie_json_docs* dev_docs, void* scratch, uint8_t* doc_status, int64_t* totals_dev,
                            int32_t* status_dev, void* stream);
+/* fill_scratch: device memory of pie_ingest_fill_scratch_bytes(n_entries) bytes, 32-byte aligned (the second walk
+ * writes one 96-byte row per entry there; a coalesced pass turns the rows into the entry columns).
+ * dev_table->n_shows must be n_docs and dev_table->n_entries the measured total. */
+uint64_t pie_ingest_fill_scratch_bytes(int64_t n_entries);
 int pie_ingest_fill_dev(const pie_json_docs* dev_docs, const void* scratch, const uint8_t* doc_status,
-                        const pie_archive_table* dev_table, void* stream);
+                        const pie_archive_table* dev_table, void* fill_scratch, void* stream);
 /* Host variant: uploads the texts, runs both passes, downloads the table.  `host_table` receives pointers into
  * pinned memory OWNED BY THE LIBRARY (valid until the next pie_ingest_host call or pie_ingest_host_release);
  * doc_status is the caller's [n_docs]; totals (may be NULL) as above; *bad_doc (may be NULL) = the offending

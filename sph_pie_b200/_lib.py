@@ -149,8 +149,9 @@ SIGNATURES = {
     "pie_ingest_scratch_bytes": (C.c_uint64, [C.c_int64]),
     "pie_ingest_measure_dev": (C.c_int, [C.POINTER(JsonDocsC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
+    "pie_ingest_fill_scratch_bytes": (C.c_uint64, [C.c_int64]),
     "pie_ingest_fill_dev": (C.c_int, [C.POINTER(JsonDocsC), C.c_void_p, C.c_void_p, C.POINTER(ArchiveViewC),
-                                      C.c_void_p]),
+                                      C.c_void_p, C.c_void_p]),
     "pie_ingest_host": (C.c_int, [C.POINTER(JsonDocsC), C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p,
                                   C.POINTER(C.c_int64)]),
     "pie_ingest_host_release": (None, []),

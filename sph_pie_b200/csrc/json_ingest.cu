@@ -196,6 +196,27 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_walk_kernel(const int64
   }
 }
 
+// entry rows -> the table's entry columns: 256 rows per CTA through shared memory, every access coalesced
+__global__ void __launch_bounds__(256) ingest_rows_to_columns_kernel(const EntryRow* __restrict__ rows, int64_t n_entries,
+                                                                     IngestOut out) {
+  constexpr int kWords = sizeof(EntryRow) / 4, kPitch = kWords + 1;  // 24 words a row; 25 in shared memory: no bank conflicts
+  __shared__ uint32_t tile[256 * kPitch];
+  const int64_t first = (int64_t)blockIdx.x * 256;
+  const int n = n_entries - first < 256 ? (int)(n_entries - first) : 256;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(rows + first);
+  for (int i = threadIdx.x; i < n * kWords; i += 256) tile[(i / kWords) * kPitch + i % kWords] = src[i];
+  __syncthreads();
+  if ((int)threadIdx.x >= n) return;
+  const uint32_t* r = tile + threadIdx.x * kPitch;
+  const int64_t e = first + threadIdx.x;
+#pragma unroll
+  for (int h = 0; h < 14; ++h) out.off[kHeapEntry0 + h][e] = (int32_t)r[h];
+  out.actions_list[e] = (int32_t)r[14];
+  out.delay_sec[e] = __longlong_as_double((long long)(((unsigned long long)r[17] << 32) | r[16]));
+  out.entry_ts[e] = __longlong_as_double((long long)(((unsigned long long)r[19] << 32) | r[18]));
+  out.delay_valid[e] = (uint8_t)r[20];
+}
+
 // the terminal offsets of an empty table
 __global__ void ingest_empty_kernel(IngestOut out) {
   for (int h = 0; h < kHeaps; ++h) out.off[h][0] = 0;
@@ -355,6 +376,7 @@ IngestScratch carve(void* scratch, int64_t n_docs) {
 
 IngestOut make_out(const pie_archive_table& t) {
   IngestOut o;
+  o.rows = nullptr;
   const pie_strcol_mut* show_cols[7] = {&t.show_id, &t.show_date, &t.show_time, &t.show_label, &t.lead_pilot, &t.monkey_lead,
                                         &t.show_notes};
   const pie_strcol_mut* entry_cols[14] = {&t.entry_id, &t.unit_id, &t.planned, &t.launched, &t.status, &t.primary_issue,
@@ -416,17 +438,26 @@ cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint
   return cudaGetLastError();
 }
 
+uint64_t ingest_fill_scratch_bytes(int64_t n_entries) { return sizeof(EntryRow) * (uint64_t)(n_entries > 0 ? n_entries : 1); }
+
 cudaError_t launch_ingest_fill(const pie_json_docs& docs, const void* scratch, const uint8_t* doc_status,
-                               const pie_archive_table& table, cudaStream_t stream) {
+                               const pie_archive_table& table, void* fill_scratch, cudaStream_t stream) {
   const int64_t n = docs.n_docs;
   IngestScratch sc = carve(const_cast<void*>(scratch), n);
   cudaError_t e = cudaMemsetAsync(sc.next_doc + 1, 0, 8, stream);  // pass 2 may run more than once per pass 1
   if (e != cudaSuccess) return e;
-  if (n > 0)
+  IngestOut out = make_out(table);
+  if (n > 0) {
+    out.rows = static_cast<EntryRow*>(fill_scratch);
     ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc,
-                                                                           const_cast<uint8_t*>(doc_status), make_out(table));
-  else
-    ingest_empty_kernel<<<1, 1, 0, stream>>>(make_out(table));
+                                                                           const_cast<uint8_t*>(doc_status), out);
+    if (table.n_entries > 0) {
+      ingest_rows_to_columns_kernel<<<(unsigned)((table.n_entries + 255) / 256), 256, 0, stream>>>(out.rows, table.n_entries, out);
+      ++g_launches;
+    }
+  } else {
+    ingest_empty_kernel<<<1, 1, 0, stream>>>(out);
+  }
   ++g_launches;
   return cudaGetLastError();
 }

@@ -901,19 +901,24 @@ static int check_table(const pie_archive_table* t) {
   return PIE_OK;
 }
 
+uint64_t pie_ingest_fill_scratch_bytes(int64_t n_entries) { return pie::ingest_fill_scratch_bytes(n_entries); }
+
 int pie_ingest_fill_dev(const pie_json_docs* d, const void* scratch, const uint8_t* doc_status, const pie_archive_table* t,
-                        void* stream) {
+                        void* fill_scratch, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;
   if ((rc = check_docs(d))) return rc;
   if ((rc = check_table(t))) return rc;
-  if (!scratch || !doc_status) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
-  PIE_CUDA(pie::launch_ingest_fill(*d, scratch, doc_status, *t, (cudaStream_t)stream));
+  if (!scratch || !doc_status || !fill_scratch) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  if (t->n_shows != d->n_docs || t->n_entries < 0) return fail(PIE_ERR_INVALID_ARG, "table.n_shows / n_entries do not match the documents");
+  if (reinterpret_cast<uintptr_t>(fill_scratch) & 31) return fail(PIE_ERR_INVALID_ARG, "fill_scratch must be 32-byte aligned");
+  PIE_CUDA(pie::launch_ingest_fill(*d, scratch, doc_status, *t, fill_scratch, (cudaStream_t)stream));
   return PIE_OK;
 }
 
 namespace {
 OutBuffer g_ingest_out;           // the device image of the table
+OutBuffer g_ingest_rows;          // the entry rows of the second walk
 uint8_t* g_ingest_host = nullptr; // its pinned host image (what pie_ingest_host hands out)
 uint64_t g_ingest_host_cap = 0;
 
@@ -1036,7 +1041,8 @@ int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint
     g_ingest_host_cap = block;
   }
   layout_table(&ht, g_ingest_host, n, totals);
-  PIE_CUDA(pie::launch_ingest_fill(dd, d_scratch, d_status_bytes, dt, st));
+  if ((rc = g_ingest_rows.ensure(pie::ingest_fill_scratch_bytes(totals[PIE_IT_ENTRIES])))) return rc;
+  PIE_CUDA(pie::launch_ingest_fill(dd, d_scratch, d_status_bytes, dt, g_ingest_rows.base, st));
   PIE_CUDA(cudaMemcpyAsync(g_ingest_host, g_ingest_out.base, block, cudaMemcpyDeviceToHost, st));
   PIE_CUDA(cudaStreamSynchronize(st));
   g_last_d2h = d2h + block;

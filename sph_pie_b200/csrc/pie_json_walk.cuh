@@ -160,7 +160,22 @@ PIE_JW_HD int match_entry_key(uint32_t len, uint64_t k0, uint64_t k1) {
 }
 
 // ---- the walk -----------------------------------------------------------------------------------------------------
+// What the second walk knows of an entry, written as ONE 96-byte row (three full 32-byte sectors) instead of 18
+// words scattered over 18 arrays — every lane keeps a sector open in L2 for each stream it writes, and ~130 k lanes
+// x 30 streams do not fit; json_ingest.cu turns the rows into the table's columns with coalesced accesses.
+struct alignas(32) EntryRow {
+  int32_t off[14];       // where the entry's text starts in each of the 14 entry heaps
+  int32_t actions_list;  // first item of its actions
+  int32_t pad0;
+  double delay;
+  double ts;
+  uint32_t valid;
+  uint32_t pad1[3];
+};
+static_assert(sizeof(EntryRow) == 96, "three sectors");
+
 struct IngestOut {
+  EntryRow* rows;  // nullptr: the entry columns are written directly (the host build of the walk)
   int32_t* off[kHeaps];
   uint8_t* data[kHeaps];
   int32_t* entry_offsets;
@@ -295,16 +310,35 @@ struct DocWalker {
     e_valid = false;
     e_ts = jw_nan();
     if (kFill) {
+      if (out.rows) {
+#if defined(__CUDA_ARCH__)
+        uint4* row = reinterpret_cast<uint4*>(out.rows + e_row);
+        row[0] = make_uint4(cnt[kHeapEntry0 + 0], cnt[kHeapEntry0 + 1], cnt[kHeapEntry0 + 2], cnt[kHeapEntry0 + 3]);
+        row[1] = make_uint4(cnt[kHeapEntry0 + 4], cnt[kHeapEntry0 + 5], cnt[kHeapEntry0 + 6], cnt[kHeapEntry0 + 7]);
+        row[2] = make_uint4(cnt[kHeapEntry0 + 8], cnt[kHeapEntry0 + 9], cnt[kHeapEntry0 + 10], cnt[kHeapEntry0 + 11]);
+        row[3] = make_uint4(cnt[kHeapEntry0 + 12], cnt[kHeapEntry0 + 13], cnt[kPlaneActionItems], 0u);
+#endif
+      } else {
 #pragma unroll
-      for (int h = kHeapEntry0; h < kHeapEntry0 + 14; ++h) out.off[h][e_row] = (int32_t)cnt[h];
-      out.actions_list[e_row] = (int32_t)cnt[kPlaneActionItems];
+        for (int h = kHeapEntry0; h < kHeapEntry0 + 14; ++h) out.off[h][e_row] = (int32_t)cnt[h];
+        out.actions_list[e_row] = (int32_t)cnt[kPlaneActionItems];
+      }
     }
   }
   PIE_JW_HD void end_entry(const IngestOut& out) {
     if (kFill) {
-      out.delay_sec[e_row] = e_delay;
-      out.delay_valid[e_row] = e_valid ? 1 : 0;
-      out.entry_ts[e_row] = e_ts;
+      if (out.rows) {
+#if defined(__CUDA_ARCH__)
+        uint4* row = reinterpret_cast<uint4*>(out.rows + e_row);
+        const unsigned long long d = (unsigned long long)__double_as_longlong(e_delay), t = (unsigned long long)__double_as_longlong(e_ts);
+        row[4] = make_uint4((uint32_t)d, (uint32_t)(d >> 32), (uint32_t)t, (uint32_t)(t >> 32));
+        row[5] = make_uint4(e_valid ? 1u : 0u, 0u, 0u, 0u);
+#endif
+      } else {
+        out.delay_sec[e_row] = e_delay;
+        out.delay_valid[e_row] = e_valid ? 1 : 0;
+        out.entry_ts[e_row] = e_ts;
+      }
     }
   }
   // a value is through: what may follow it (a comma right behind it is taken at once)

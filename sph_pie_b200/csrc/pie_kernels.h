@@ -40,8 +40,9 @@ cudaError_t launch_compute_metrics(const pie_archive_view& dev_view, int32_t* me
 uint64_t ingest_scratch_bytes(int64_t n_docs);
 cudaError_t launch_ingest_measure(const pie_json_docs& dev_docs, void* scratch, uint8_t* doc_status, int64_t* totals,
                                   int32_t* status, cudaStream_t stream);
+uint64_t ingest_fill_scratch_bytes(int64_t n_entries);
 cudaError_t launch_ingest_fill(const pie_json_docs& dev_docs, const void* scratch, const uint8_t* doc_status,
-                               const pie_archive_table& dev_table, cudaStream_t stream);
+                               const pie_archive_table& dev_table, void* fill_scratch, cudaStream_t stream);
 
 // archive_daily.cu
 uint64_t daily_scratch_bytes(int64_t n_shows);

@@ -395,6 +395,7 @@ class IngestBuffers:
         self.doc_status = torch.empty(max(n_docs, 1), dtype=torch.uint8, device=device)
         self.totals = torch.zeros(_lib.PIE_INGEST_TOTALS, dtype=torch.int64, device=device)
         self.status = torch.zeros(2, dtype=torch.int32, device=device)
+        self.fill_scratch = None  # the entry rows of the second walk: sized when the number of entries is known
 
 
 def ingest_measure_dev(docs: JsonDocs, bufs: IngestBuffers) -> None:
@@ -409,8 +410,12 @@ def ingest_fill_dev(docs: JsonDocs, bufs: IngestBuffers, table: ArchiveTable) ->
     """Second walk on torch's current stream (no sync) into a table allocated from bufs.totals."""
     d = docs.c()
     view = table.view()
-    _lib.check(_lib.load().pie_ingest_fill_dev(C.byref(d), bufs.scratch.data_ptr(), bufs.doc_status.data_ptr(),
-                                               C.byref(view), _stream_ptr()))
+    lib = _lib.load()
+    need = int(lib.pie_ingest_fill_scratch_bytes(table.n_entries))
+    if bufs.fill_scratch is None or bufs.fill_scratch.numel() < need:
+        bufs.fill_scratch = torch.empty(need, dtype=torch.uint8, device=docs.data.device)
+    _lib.check(lib.pie_ingest_fill_dev(C.byref(d), bufs.scratch.data_ptr(), bufs.doc_status.data_ptr(), C.byref(view),
+                                       bufs.fill_scratch.data_ptr(), _stream_ptr()))
 
 
 def ingest_json(docs: JsonDocs, bufs: IngestBuffers = None):
@@ -607,8 +612,11 @@ def archive_step_from_json_pipelined(docs: JsonDocs, tz_offset_minutes: int = 0,
         with torch.cuda.stream(s_run):
             table = alloc_ingest_table(b - a, totals, dev)
             view = table.view()
+            need = int(lib.pie_ingest_fill_scratch_bytes(table.n_entries))
+            if ib.fill_scratch is None or ib.fill_scratch.numel() < need:
+                ib.fill_scratch = torch.empty(need, dtype=torch.uint8, device=dev)
             _lib.check(lib.pie_ingest_fill_dev(C.byref(d), ib.scratch.data_ptr(), doc_status.data_ptr() + a, C.byref(view),
-                                               s_run.cuda_stream))
+                                               ib.fill_scratch.data_ptr(), s_run.cuda_stream))
             slot_free[c % 2].record(s_run)
             E_c = table.n_entries
             _lib.check(lib.pie_show_stats_dev(C.byref(view), db.stats_i32.data_ptr() + 4 * a, db.stats_f64.data_ptr() + 8 * a,

@@ -13,6 +13,7 @@ static const uint64_t kPow5[PIE_POW5_128_N][2] = PIE_POW5_128_INIT;
 
 static IngestOut make_out(const pie_archive_table& t) {
   IngestOut o;
+  o.rows = nullptr;
   const pie_strcol_mut* show_cols[7] = {&t.show_id, &t.show_date, &t.show_time, &t.show_label, &t.lead_pilot, &t.monkey_lead,
                                         &t.show_notes};
   const pie_strcol_mut* entry_cols[14] = {&t.entry_id, &t.unit_id, &t.planned, &t.launched, &t.status, &t.primary_issue,
