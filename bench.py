@@ -539,6 +539,11 @@ def ingest_leg(args, dev, n_shows, runs, note):
     for _ in range(h_runs):
         ops.archive_step_from_json_pipelined(hdocs, args.tz, hout, h_off, h_csv)
     json_pipe_s = (time.perf_counter() - t0) / h_runs
+    ops.archive_step_json_host(hdocs, args.tz, hout, h_off, h_csv)
+    t0 = time.perf_counter()
+    for _ in range(h_runs):
+        ops.archive_step_json_host(hdocs, args.tz, hout, h_off, h_csv)
+    json_abi_s = (time.perf_counter() - t0) / h_runs
     json_step_d2h = h_csv.numel() + 8 * h_off.numel() + (4 * _lib.PIE_SI_COUNT + 8 * _lib.PIE_SF_COUNT) * hdocs.n_docs
     del rows, hout, h_off, h_csv
     # one core of the host through Python's json module (C accelerated; parse only, no projection on the table)
@@ -563,6 +568,8 @@ def ingest_leg(args, dev, n_shows, runs, note):
         "e2e_json_to_outputs": {"api": "ops.archive_step_from_json: pinned texts in; ingest, statistics, daily summaries "
                                        "and CSV rows on the device; pinned results out",
                                 "ms": json_step_s * 1e3, "entries_per_s": n_entries / json_step_s,
+                                "c_abi_ms": json_abi_s * 1e3, "c_abi_entries_per_s": n_entries / json_abi_s,
+                                "c_abi": "pie_archive_step_json_host: the same as one C-ABI call (single batch)",
                                 "pipelined_ms": json_pipe_s * 1e3, "pipelined_entries_per_s": n_entries / json_pipe_s,
                                 "pipelined_api": "ops.archive_step_from_json_pipelined: the same in chunks of 131072 "
                                                  "documents over three streams (upload / kernels / download overlap)",

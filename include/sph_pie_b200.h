@@ -363,6 +363,21 @@ int pie_ingest_host(const pie_json_docs* host_docs, pie_archive_table* host_tabl
                     int64_t* totals, int64_t* bad_doc);
 void pie_ingest_host_release(void);
 
+/* ---- the archive workspace from the provider's stored texts in ONE call: pie_ingest_host + pie_archive_step_host
+ * without the table ever leaving the device — listArchivedShows (sqlProvider.js:230-234) feeding
+ * buildArchiveDailyGroups / getOrCreateGroupMetricSummary (public/app.js:3401-3502) and the CSV rows of every entry
+ * (server/webhookDispatcher.js:276-342).  host_docs / doc_status / bad_doc as pie_ingest_host; statistics and daily
+ * summaries as pie_archive_analytics_host (stats_* may both be NULL); CSV rows as pie_csv_rows_host, except that the
+ * number of rows is an output too: row_offsets has room for row_capacity elements (n_entries + 1 are needed) and
+ * out_data for out_capacity bytes.  *n_entries and *total_bytes are always set; row_offsets == out_data == NULL is a
+ * size query (analytics are still delivered); PIE_ERR_CAPACITY if either is too small.  A dropped document is an
+ * empty show: no rows, skipped by the daily grouping. */
+int pie_archive_step_json_host(const pie_json_docs* host_docs, int32_t tz_offset_minutes, uint8_t* doc_status,
+                               int32_t* stats_i32, double* stats_f64, int64_t stats_stride,
+                               const pie_daily_out* host_out, int64_t* row_offsets, int64_t row_capacity,
+                               uint8_t* out_data, uint64_t out_capacity, int64_t* n_entries, uint64_t* total_bytes,
+                               int64_t* bad_doc);
+
 /* ---- self tests (device code paths that replace an IEEE operation by a faster exact sequence) */
 /* Compares the shared-reciprocal quotient used for the rate columns with IEEE a/b for every
  * 0 <= a <= b <= max_b (max_b <= 4096, the largest b the kernels use it for); writes the number of

@@ -155,6 +155,9 @@ SIGNATURES = {
     "pie_ingest_host": (C.c_int, [C.POINTER(JsonDocsC), C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p,
                                   C.POINTER(C.c_int64)]),
     "pie_ingest_host_release": (None, []),
+    "pie_archive_step_json_host": (C.c_int, [C.POINTER(JsonDocsC), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                             C.POINTER(DailyOutC), C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64,
+                                             C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
     "pie_archive_analytics_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                              C.POINTER(DailyOutC)]),
 }

@@ -969,14 +969,14 @@ void pie_ingest_host_release(void) {
   g_ingest_host_cap = 0;
 }
 
-int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint8_t* doc_status, int64_t* totals_out,
-                    int64_t* bad_doc) {
-  std::lock_guard<std::mutex> lock(g_host_mutex);
+// Host texts -> the table in device memory (g_ingest_out): upload, first walk, sizes, second walk.  `extra` more
+// bytes are reserved in the arena for what the caller computes on the table.  Leaves the stream running.
+static int ingest_to_device(const pie_json_docs* hd, uint64_t extra, uint8_t* doc_status, int64_t* totals, int64_t* bad_doc,
+                            pie_archive_table* dt, uint64_t* block_bytes, uint64_t* h2d_out, uint64_t* d2h_out) {
   if (bad_doc) *bad_doc = -1;
   int rc = ensure_init();
   if (rc) return rc;
   if ((rc = check_docs(hd))) return rc;
-  if (!host_table) return fail(PIE_ERR_INVALID_ARG, "host_table is NULL");
   const int64_t n = hd->n_docs;
   if (n > 0 && !doc_status) return fail(PIE_ERR_INVALID_ARG, "doc_status is NULL");
   const int64_t first = hd->offsets[0], last = hd->offsets[n];
@@ -990,7 +990,7 @@ int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint
   const uint64_t text_bytes = (uint64_t)(last - first);
   const uint64_t scratch_bytes = pie::ingest_scratch_bytes(n);
   uint64_t bytes = pad(8 * (uint64_t)(n + 1)) + pad(text_bytes + 16) + pad(scratch_bytes) + pad((uint64_t)n + 1) + pad(8 * PIE_INGEST_TOTALS) +
-                   pad(8);
+                   pad(8) + extra;
   if ((rc = g_arena.reserve(bytes))) return rc;
   cudaStream_t st = g_arena.stream;
   g_cur = &g_arena;
@@ -1012,16 +1012,14 @@ int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint
   int64_t* d_totals = (int64_t*)g_arena.take(8 * PIE_INGEST_TOTALS);
   int32_t* d_status = (int32_t*)g_arena.take(8);
   PIE_CUDA(pie::launch_ingest_measure(dd, d_scratch, d_status_bytes, d_totals, d_status, st));
-  int64_t totals[PIE_INGEST_TOTALS];
   int32_t status[2];
-  PIE_CUDA(cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+  PIE_CUDA(cudaMemcpyAsync(totals, d_totals, 8 * PIE_INGEST_TOTALS, cudaMemcpyDeviceToHost, st));
   PIE_CUDA(cudaMemcpyAsync(status, d_status, sizeof(status), cudaMemcpyDeviceToHost, st));
   if (n > 0) PIE_CUDA(cudaMemcpyAsync(doc_status, d_status_bytes, (uint64_t)n, cudaMemcpyDeviceToHost, st));
   PIE_CUDA(cudaStreamSynchronize(st));
-  d2h += sizeof(totals) + sizeof(status) + (uint64_t)n;
-  g_last_h2d = h2d;
-  g_last_d2h = d2h;
-  if (totals_out) memcpy(totals_out, totals, sizeof(totals));
+  d2h += 8 * PIE_INGEST_TOTALS + sizeof(status) + (uint64_t)n;
+  *h2d_out = h2d;
+  *d2h_out = d2h;
   if (status[0] != 0) {
     if (bad_doc) *bad_doc = status[1];
     const char* what = status[0] == PIE_ERR_SCHEMA ? "is not a provider-normalised show"
@@ -1029,10 +1027,28 @@ int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint
                                                                : "makes a heap or row count reach 2 GiB: split the batch";
     return fail(status[0], "document %d %s", status[1], what);
   }
-  pie_archive_table dt, ht;
-  const uint64_t block = layout_table(&dt, nullptr, n, totals);
+  const uint64_t block = layout_table(dt, nullptr, n, totals);
   if ((rc = g_ingest_out.ensure(block ? block : 256))) return rc;
-  layout_table(&dt, g_ingest_out.base, n, totals);
+  layout_table(dt, g_ingest_out.base, n, totals);
+  if ((rc = g_ingest_rows.ensure(pie::ingest_fill_scratch_bytes(totals[PIE_IT_ENTRIES])))) return rc;
+  PIE_CUDA(pie::launch_ingest_fill(dd, d_scratch, d_status_bytes, *dt, g_ingest_rows.base, st));
+  *block_bytes = block;
+  return PIE_OK;
+}
+
+int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint8_t* doc_status, int64_t* totals_out,
+                    int64_t* bad_doc) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (!host_table) return fail(PIE_ERR_INVALID_ARG, "host_table is NULL");
+  int64_t totals[PIE_INGEST_TOTALS] = {0};
+  pie_archive_table dt, ht;
+  uint64_t block = 0, h2d = 0, d2h = 0;
+  int rc = ingest_to_device(hd, 0, doc_status, totals, bad_doc, &dt, &block, &h2d, &d2h);
+  g_last_h2d = h2d;
+  g_last_d2h = d2h;
+  if (totals_out) memcpy(totals_out, totals, sizeof(totals));
+  if (rc) return rc;
+  cudaStream_t st = g_arena.stream;
   if (block > g_ingest_host_cap) {
     if (g_ingest_host) cudaFreeHost(g_ingest_host);
     g_ingest_host = nullptr;
@@ -1040,13 +1056,87 @@ int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint
     PIE_CUDA(cudaHostAlloc((void**)&g_ingest_host, block, cudaHostAllocDefault));
     g_ingest_host_cap = block;
   }
-  layout_table(&ht, g_ingest_host, n, totals);
-  if ((rc = g_ingest_rows.ensure(pie::ingest_fill_scratch_bytes(totals[PIE_IT_ENTRIES])))) return rc;
-  PIE_CUDA(pie::launch_ingest_fill(dd, d_scratch, d_status_bytes, dt, g_ingest_rows.base, st));
+  layout_table(&ht, g_ingest_host, hd->n_docs, totals);
   PIE_CUDA(cudaMemcpyAsync(g_ingest_host, g_ingest_out.base, block, cudaMemcpyDeviceToHost, st));
   PIE_CUDA(cudaStreamSynchronize(st));
   g_last_d2h = d2h + block;
   *host_table = ht;
+  return PIE_OK;
+}
+
+namespace {
+OutBuffer g_json_csv;  // CSV scratch, row offsets and bytes of pie_archive_step_json_host
+}
+
+int pie_archive_step_json_host(const pie_json_docs* hd, int32_t tz_offset_minutes, uint8_t* doc_status, int32_t* stats_i32,
+                               double* stats_f64, int64_t stats_stride, const pie_daily_out* hout, int64_t* row_offsets,
+                               int64_t row_capacity, uint8_t* out_data, uint64_t out_capacity, int64_t* n_entries,
+                               uint64_t* total_bytes, int64_t* bad_doc) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (tz_offset_minutes < -24 * 60 || tz_offset_minutes > 24 * 60) return fail(PIE_ERR_INVALID_ARG, "tz_offset_minutes out of range");
+  if (!hd || !hout || !n_entries || !total_bytes) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  const int64_t S = hd->n_docs;
+  const bool want_stats = stats_i32 != nullptr || stats_f64 != nullptr;
+  if (want_stats && (!stats_i32 || !stats_f64)) return fail(PIE_ERR_INVALID_ARG, "stats_i32 and stats_f64 go together");
+  if (want_stats && stats_stride < S) return fail(PIE_ERR_INVALID_ARG, "stats_stride < n_docs");
+  int rc;
+  if (S >= 0 && (rc = check_daily_out(hout, S))) return rc;
+  const int64_t Sc = S > 0 ? S : 1;
+  const uint64_t extra = pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc) + daily_out_bytes(S, Sc) + pad(64);
+  int64_t totals[PIE_INGEST_TOTALS] = {0};
+  pie_archive_table dt;
+  uint64_t block = 0, h2d = 0, d2h = 0;
+  rc = ingest_to_device(hd, extra, doc_status, totals, bad_doc, &dt, &block, &h2d, &d2h);
+  g_last_h2d = h2d;
+  g_last_d2h = d2h;
+  if (rc) return rc;
+  cudaStream_t st = g_arena.stream;
+  const int64_t E = totals[PIE_IT_ENTRIES];
+  *n_entries = E;
+  // the table the kernels read: pie_archive_table and pie_archive_view share their layout
+  static_assert(sizeof(pie_archive_view) == sizeof(pie_archive_table), "the view is the table with const pointers");
+  pie_archive_view dv;
+  memcpy(&dv, &dt, sizeof(dv));
+  int32_t* d_si = (int32_t*)g_arena.take(4ull * PIE_SI_COUNT * Sc);
+  double* d_sf = (double*)g_arena.take(8ull * PIE_SF_COUNT * Sc);
+  PIE_CUDA(pie::launch_show_stats(dv, d_si, d_sf, Sc, g_sm_count, st));
+  pie_daily_out dout;
+  void* dscratch = alloc_daily_out(g_arena, S, Sc, &dout);
+  PIE_CUDA(pie::launch_daily_summary(dv, d_si, d_sf, Sc, tz_offset_minutes, dout, dscratch, g_sm_count, st));
+  // CSV rows: sizes first, then the bytes (row offsets of the size pass are final)
+  const uint64_t csv_scratch = pad(pie::csv_scratch_bytes(E)), off_bytes = pad(8 * (uint64_t)(E + 1));
+  if ((rc = g_json_csv.ensure(csv_scratch + off_bytes + pad(8)))) return rc;
+  void* d_cscratch = g_json_csv.base;
+  int64_t* d_rows = (int64_t*)(g_json_csv.base + csv_scratch);
+  unsigned long long* d_total = (unsigned long long*)(g_json_csv.base + csv_scratch + off_bytes);
+  PIE_CUDA(launch_rows(kFormatCsv, dv, d_rows, nullptr, 0, 0ull, d_total, d_cscratch, st));
+  unsigned long long total = 0;
+  PIE_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+  if (want_stats && S > 0) {
+    PIE_CUDA(cudaMemcpy2DAsync(stats_i32, 4 * (uint64_t)stats_stride, d_si, 4 * (uint64_t)Sc, 4 * (uint64_t)S, PIE_SI_COUNT,
+                               cudaMemcpyDeviceToHost, st));
+    PIE_CUDA(cudaMemcpy2DAsync(stats_f64, 8 * (uint64_t)stats_stride, d_sf, 8 * (uint64_t)Sc, 8 * (uint64_t)S, PIE_SF_COUNT,
+                               cudaMemcpyDeviceToHost, st));
+    d2h += (4ull * PIE_SI_COUNT + 8ull * PIE_SF_COUNT) * (uint64_t)S;
+  }
+  rc = download_daily(hout, dout, S, Sc, st, &d2h);  // synchronises: `total` is in
+  g_last_d2h = d2h;
+  if (rc) return rc;
+  *total_bytes = total;
+  if (!out_data || !row_offsets || out_capacity < total || row_capacity < E + 1) {
+    PIE_CUDA(cudaStreamSynchronize(st));
+    if (!out_data && !row_offsets) return PIE_OK;  // a size query
+    return fail(PIE_ERR_CAPACITY, "CSV needs %llu bytes and %lld row offsets (given %llu and %lld)", total,
+                (long long)(E + 1), (unsigned long long)out_capacity, (long long)row_capacity);
+  }
+  // the bytes: a second buffer after the offsets (grown without moving what the kernels above wrote)
+  static OutBuffer csv_bytes;
+  if ((rc = csv_bytes.ensure(total ? total : 256))) return rc;
+  PIE_CUDA(launch_rows(kFormatCsv, dv, d_rows, csv_bytes.base, total, 0ull, d_total, d_cscratch, st));
+  PIE_CUDA(cudaMemcpyAsync(row_offsets, d_rows, 8 * (uint64_t)(E + 1), cudaMemcpyDeviceToHost, st));
+  if (total) PIE_CUDA(cudaMemcpyAsync(out_data, csv_bytes.base, total, cudaMemcpyDeviceToHost, st));
+  PIE_CUDA(cudaStreamSynchronize(st));
+  g_last_d2h = d2h + 8 * (uint64_t)(E + 1) + total;
   return PIE_OK;
 }
 

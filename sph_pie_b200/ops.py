@@ -690,3 +690,40 @@ def archive_step_from_json_pipelined(docs: JsonDocs, tz_offset_minutes: int = 0,
     daily = DailySummary(G, h.show_day_start[:n], h.show_order[:n], h.group_day_start[:G], h.group_offsets[:G + 1],
                          h.summary_f64[:, :, :G], h.summary_count[:, :G])
     return stats, daily, CsvRows(row_offsets[:e_base + 1], data[:csv_base]), dropped
+
+
+def archive_step_json_host(docs: JsonDocs, tz_offset_minutes: int = 0, out: "HostOutputs" = None,
+                           row_offsets: torch.Tensor = None, data: torch.Tensor = None):
+    """pie_archive_step_json_host: the same as archive_step_from_json, as ONE call of the C ABI with host buffers in
+    and out (what a binding of the reference would call).  Without `row_offsets` / `data` the sizes are queried with
+    a first call."""
+    _lib.ensure_init()
+    assert not docs.is_cuda
+    lib = _lib.load()
+    n = docs.n_docs
+    h = out if out is not None else HostOutputs(n)
+    d = docs.c()
+    dout = h.daily_out()
+    status = torch.empty(max(n, 1), dtype=torch.uint8)
+    n_entries, total, bad = C.c_int64(0), C.c_uint64(0), C.c_int64(-1)
+
+    def call(off, dat):
+        rc = lib.pie_archive_step_json_host(
+            C.byref(d), tz_offset_minutes, status.data_ptr(), h.stats_i32.data_ptr(), h.stats_f64.data_ptr(), h.S,
+            C.byref(dout), off.data_ptr() if off is not None else None, off.numel() if off is not None else 0,
+            dat.data_ptr() if dat is not None else None, dat.numel() if dat is not None else 0,
+            C.byref(n_entries), C.byref(total), C.byref(bad))
+        if rc in (_lib.PIE_ERR_SCHEMA, _lib.PIE_ERR_UNSUPPORTED_JSON):
+            _raise_ingest_status(rc, int(bad.value))
+        _lib.check(rc)
+
+    if row_offsets is None or data is None:
+        call(None, None)
+        row_offsets = torch.empty(n_entries.value + 1, dtype=torch.int64)
+        data = torch.empty(max(total.value, 1), dtype=torch.uint8)
+    call(row_offsets, data)
+    E, G = n_entries.value, int(h.n_groups[0])
+    stats = ShowStats(h.stats_i32[:, :n], h.stats_f64[:, :n])
+    daily = DailySummary(G, h.show_day_start[:n], h.show_order[:n], h.group_day_start[:G], h.group_offsets[:G + 1],
+                         h.summary_f64[:, :, :G], h.summary_count[:, :G])
+    return stats, daily, CsvRows(row_offsets[:E + 1], data[:total.value]), status[:n].bool()

@@ -285,6 +285,19 @@ def test_pipelined_step_from_stored_texts(cuda, chunk_docs):
     off = torch.empty(r1.row_offsets.numel(), dtype=torch.int64, pin_memory=True)
     csv = torch.empty(r1.data.numel(), dtype=torch.uint8, pin_memory=True)
     s2, d2, r2, x2 = ops.archive_step_from_json_pipelined(docs, 120, None, off, csv, chunk_docs=chunk_docs)
+    if chunk_docs == 700:  # the one-call C entry point gives the same, with and without the size query
+        for args in ((), (None, torch.empty(off.numel(), dtype=torch.int64), torch.empty(csv.numel(), dtype=torch.uint8))):
+            s3, d3, r3, x3 = ops.archive_step_json_host(docs, 120, *args)
+            assert torch.equal(x1, x3)
+            from helpers import assert_analytics_equal as same
+
+            same((s3, d3), (s1, d1), "pie_archive_step_json_host")
+            assert torch.equal(r1.row_offsets, r3.row_offsets) and torch.equal(r1.data, r3.data)
+        with pytest.raises(_lib.PieError) as ei:  # too small a CSV buffer: PIE_ERR_CAPACITY, sizes reported
+            ops.archive_step_json_host(docs, 120, None, torch.empty(off.numel(), dtype=torch.int64), torch.empty(10, dtype=torch.uint8))
+        assert ei.value.code == _lib.PIE_ERR_CAPACITY
+        empty = ops.archive_step_json_host(ops.JsonDocs.from_texts([]), 0)
+        assert empty[1].n_groups == 0 and empty[2].row_offsets.tolist() == [0]
     from helpers import assert_analytics_equal
 
     assert torch.equal(x1, x2) and x1.nonzero().flatten().tolist() == [5, 699, 2999]
