@@ -116,7 +116,7 @@ __global__ void ingest_init_kernel(IngestScratch sc) {
 
 // Both passes: every lane walks documents until none is left.
 template <bool kFill>
-__global__ void __launch_bounds__(kIngestThreads, 8) ingest_walk_kernel(const int64_t* __restrict__ doc_offsets,
+__global__ void __launch_bounds__(kIngestThreads, kFill ? 8 : 10) ingest_walk_kernel(const int64_t* __restrict__ doc_offsets,
                                                                       const uint8_t* __restrict__ text, int64_t n_docs,
                                                                       IngestScratch sc, uint8_t* __restrict__ doc_status,
                                                                       IngestOut out) {
