@@ -13,7 +13,7 @@
 //
 //   pass 1  ingest_measure_kernel   per document: entries, items of crew / actions, unescaped bytes of each of the 23
 //                                   string heaps; syntax errors make the document a dropped row (all counts zero)
-//   scan    ingest_scan_*           exclusive prefix sums of the 26 count planes over the documents, totals
+//   scan    ingest_scan_*           exclusive prefix sums of the 26 counts over the documents (a row per document), totals
 //   pass 2  ingest_fill_kernel      the same walk (same template) with every counter started at its prefix: offsets,
 //                                   unescaped bytes, numbers (pie_numparse.cuh, correctly rounded)
 //
@@ -37,8 +37,8 @@ __device__ const uint64_t g_pow5_dev[PIE_POW5_128_N][2] = PIE_POW5_128_INIT;
 constexpr int kIngestThreads = 128;
 
 struct IngestScratch {
-  uint32_t* planes;          // [kPlanes][stride]: pass 1 counts, then exclusive prefixes
-  int64_t stride;
+  uint32_t* planes;          // [n_docs][kPlanes]: a document's 26 counts are one 104-byte row (pass 1 writes it, the
+  int64_t stride;            //   scans turn it into exclusive prefixes in place, pass 2 reads it) — not 26 scattered words
   unsigned long long* block_sums;  // [kPlanes][nblk] + the arrival counter of the scan
   unsigned long long* err_key;     // min over documents of (doc << 8 | code): the first hard error
   unsigned long long* next_doc;    // [2] the next place of `order` to hand out in pass 1 / pass 2
@@ -104,9 +104,8 @@ __global__ void __launch_bounds__(256) ingest_order_place_kernel(const int64_t* 
   if (s < n_docs) sc.order[atomicAdd(sc.buckets + length_class(doc_offsets, s), 1u)] = (int32_t)s;
 }
 
-constexpr int kScanItems = 4;
 constexpr int kScanThreads = 1024;
-constexpr int kScanChunk = kScanItems * kScanThreads;
+constexpr int kScanChunk = kScanThreads;  // documents per CTA of the scans: a thread holds one document's row
 
 __global__ void ingest_init_kernel(IngestScratch sc) {
   *sc.err_key = ~0ull;
@@ -141,7 +140,11 @@ __global__ void __launch_bounds__(kIngestThreads, kFill ? 8 : 10) ingest_walk_ke
         bool walk = true;
         if (kFill) {
 #pragma unroll
-          for (int p = 0; p < kPlanes; ++p) cnt[p] = sc.planes[p * sc.stride + s];
+          for (int p = 0; p < kPlanes; p += 2) {
+            const uint2 two = *reinterpret_cast<const uint2*>(sc.planes + s * kPlanes + p);
+            cnt[p] = two.x;
+            cnt[p + 1] = two.y;
+          }
           // the show's row: every text field starts where the previous show's ended (an absent key is '')
 #pragma unroll
           for (int h = 0; h < 7; ++h) out.off[h][s] = (int32_t)cnt[h];
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(kIngestThreads, kFill ? 8 : 10) ingest_walk_ke
       }
       doc_status[s] = r == kDocOk ? 0 : 1;
 #pragma unroll
-      for (int p = 0; p < kPlanes; ++p) sc.planes[p * sc.stride + s] = cnt[p];
+      for (int p = 0; p < kPlanes; p += 2) *reinterpret_cast<uint2*>(sc.planes + s * kPlanes + p) = make_uint2(cnt[p], cnt[p + 1]);
     } else if (s == n_docs - 1) {  // the terminal offsets: where the last document ended
 #pragma unroll
       for (int h = 0; h < 7; ++h) out.off[h][n_docs] = (int32_t)cnt[h];
@@ -225,26 +228,35 @@ __global__ void ingest_empty_kernel(IngestOut out) {
   out.actions_list[0] = 0;
 }
 
-// exclusive scan of every plane over the documents: chunk sums, scan of the chunk sums (one CTA per plane), then the
-// chunks in place
-__global__ void __launch_bounds__(kScanThreads) ingest_scan_sums_kernel(IngestScratch sc, int64_t n, int nblk) {
-  const int p = blockIdx.y;
-  const uint32_t* x = sc.planes + p * sc.stride;
-  const int64_t base = (int64_t)blockIdx.x * kScanChunk;
-  unsigned long long v = 0;
+// exclusive scan of every count over the documents: sums of 1024 documents per CTA, scan of the CTA sums (one CTA
+// per count), then the documents in place.  A thread holds its document's whole row.
+__device__ __forceinline__ void load_row(const IngestScratch& sc, int64_t s, int64_t n, uint32_t (&v)[kPlanes]) {
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const int64_t i = base + k * kScanThreads + threadIdx.x;
-    if (i < n) v += x[i];
+  for (int p = 0; p < kPlanes; p += 2) {
+    const uint2 two = s < n ? *reinterpret_cast<const uint2*>(sc.planes + s * kPlanes + p) : make_uint2(0u, 0u);
+    v[p] = two.x;
+    v[p + 1] = two.y;
   }
-  __shared__ unsigned long long warp_sums[32];
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) ingest_scan_sums_kernel(IngestScratch sc, int64_t n, int nblk) {
+  __shared__ unsigned long long warp_sums[kPlanes][32];
+  const int64_t s = (int64_t)blockIdx.x * kScanChunk + threadIdx.x;
+  uint32_t v[kPlanes];
+  load_row(sc, s, n, v);
+#pragma unroll
+  for (int p = 0; p < kPlanes; ++p) {
+    unsigned long long x = v[p];
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+    if ((threadIdx.x & 31) == 0) warp_sums[p][threadIdx.x >> 5] = x;
+  }
   __syncthreads();
   if (threadIdx.x < 32) {
-    v = warp_sums[threadIdx.x];
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-    if (threadIdx.x == 0) sc.block_sums[(int64_t)p * nblk + blockIdx.x] = v;
+    for (int p = 0; p < kPlanes; ++p) {
+      unsigned long long x = warp_sums[p][threadIdx.x];
+      for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+      if (threadIdx.x == 0) sc.block_sums[(int64_t)p * nblk + blockIdx.x] = x;
+    }
   }
 }
 
@@ -309,39 +321,41 @@ __global__ void __launch_bounds__(1024) ingest_scan_blocks_kernel(IngestScratch 
 }
 
 __global__ void __launch_bounds__(kScanThreads) ingest_scan_apply_kernel(IngestScratch sc, int64_t n, int nblk) {
-  const int p = blockIdx.y;
-  uint32_t* x = sc.planes + p * sc.stride;
-  const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
-  uint32_t item[kScanItems];
-  uint32_t sum = 0;
+  __shared__ uint32_t warp_sums[kPlanes][32];
+  const int64_t s = (int64_t)blockIdx.x * kScanChunk + threadIdx.x;
+  uint32_t v[kPlanes], incl[kPlanes];
+  load_row(sc, s, n, v);
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    item[k] = base + k < n ? x[base + k] : 0;
-    sum += item[k];
+  for (int p = 0; p < kPlanes; ++p) {
+    uint32_t x = v[p];
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, x, d);
+      if ((threadIdx.x & 31) >= d) x += t;
+    }
+    incl[p] = x;
+    if ((threadIdx.x & 31) == 31) warp_sums[p][threadIdx.x >> 5] = x;
   }
-  uint32_t v = sum;
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-    if ((threadIdx.x & 31) >= d) v += t;
-  }
-  __shared__ uint32_t warp_sums[32];
-  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = v;
   __syncthreads();
   if (threadIdx.x < 32) {
-    uint32_t ws = warp_sums[threadIdx.x];
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, ws, d);
-      if (threadIdx.x >= d) ws += t;
+    for (int p = 0; p < kPlanes; ++p) {
+      uint32_t ws = warp_sums[p][threadIdx.x];
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, ws, d);
+        if (threadIdx.x >= d) ws += t;
+      }
+      warp_sums[p][threadIdx.x] = ws;
     }
-    warp_sums[threadIdx.x] = ws;
   }
   __syncthreads();
-  uint32_t run = (uint32_t)sc.block_sums[(int64_t)p * nblk + blockIdx.x] + ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0) +
-                 v - sum;
+  if (s >= n) return;
 #pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    if (base + k < n) x[base + k] = run;
-    run += item[k];
+  for (int p = 0; p < kPlanes; p += 2) {
+    uint32_t two[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      two[k] = (uint32_t)sc.block_sums[(int64_t)(p + k) * nblk + blockIdx.x] +
+               ((threadIdx.x >> 5) ? warp_sums[p + k][(threadIdx.x >> 5) - 1] : 0) + incl[p + k] - v[p + k];
+    *reinterpret_cast<uint2*>(sc.planes + s * kPlanes + p) = make_uint2(two[0], two[1]);
   }
 }
 
@@ -426,13 +440,13 @@ cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint
     g_launches += 3;
     ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, doc_status,
                                                                             IngestOut{});
-    ingest_scan_sums_kernel<<<dim3(nblk, kPlanes), kScanThreads, 0, stream>>>(sc, n, nblk);
+    ingest_scan_sums_kernel<<<nblk, kScanThreads, 0, stream>>>(sc, n, nblk);
     g_launches += 2;
   }
   ingest_scan_blocks_kernel<<<kPlanes, 1024, 0, stream>>>(sc, nblk, totals, status);
   ++g_launches;
   if (n > 0) {
-    ingest_scan_apply_kernel<<<dim3(nblk, kPlanes), kScanThreads, 0, stream>>>(sc, n, nblk);
+    ingest_scan_apply_kernel<<<nblk, kScanThreads, 0, stream>>>(sc, n, nblk);
     ++g_launches;
   }
   return cudaGetLastError();
