@@ -555,6 +555,23 @@ def ingest_leg(args, dev, n_shows, runs, note):
         parsed += 1
     cpu_s = (time.perf_counter() - t0) / parsed
     sample_bytes = sum(len(t.encode("utf-8")) for t in texts)
+    # ... and the C port of the same path (oracle/pie_oracle.c: recursive descent + strtod, both passes, table out)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c
+
+    sample_docs = ops.JsonDocs.from_texts(texts)
+    sample_entries = n_entries // copies
+    port = {}
+    for label, threads in (("one_thread", 1), ("all_threads", oracle_c.max_threads())):
+        oracle_c.ingest(sample_docs, nthreads=threads)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 1.5:
+            table_c, _, err = oracle_c.ingest(sample_docs, nthreads=threads)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        assert err == (0, -1) and table_c.n_entries == sample_entries
+        port[label] = {"threads": threads, "text_mbs": sample_bytes / dt / 1e6, "entries_per_s": sample_entries / dt}
     alg = 2 * text_bytes + table_bytes + 2 * 4 * 26 * hdocs.n_docs
     ms = tm + tf
     return {
@@ -574,6 +591,8 @@ def ingest_leg(args, dev, n_shows, runs, note):
                                 "pipelined_api": "ops.archive_step_from_json_pipelined: the same in chunks of 131072 "
                                                  "documents over three streams (upload / kernels / download overlap)",
                                 "h2d_bytes": text_bytes + 8 * (hdocs.n_docs + 1), "d2h_bytes_at_least": json_step_d2h},
+        "cpu_port": dict(port, what="oracle/pie_oracle.c oracle_ingest_measure + oracle_ingest_fill on the sample's documents "
+                                    "(JSON text in, columnar table out), kind: port"),
         "cpu_json_loads": {"what": "json.loads of the sample's documents, one core, parse only", "text_mbs":
                            sample_bytes / cpu_s / 1e6, "sample_documents": len(texts)},
         "workload": f"{sample} synthetic shows written as JSON documents (json.dumps, no whitespace), x{copies} on the device",

@@ -28,8 +28,7 @@ def build(force: bool = False) -> str:
 def load():
     global _so
     if _so is None:
-        if not os.path.exists(SO_PATH):
-            build()
+        build()  # (re)builds when pie_oracle.c is newer
         so = C.CDLL(SO_PATH)
         so.oracle_show_stats.restype = C.c_int
         so.oracle_show_stats.argtypes = [C.POINTER(_lib.ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
@@ -126,3 +125,29 @@ def number_to_string_batch(xs):
     so.oracle_number_to_string_batch(xs.ctypes.data, n, out.ctypes.data, lens.ctypes.data)
     b = out.tobytes()
     return [b[i * 32:i * 32 + lens[i]].decode() for i in range(n)]
+
+
+def ingest(texts, nthreads: int = 1):
+    """The C restatement of JSON.parse + projection (oracle_ingest_*): (table | None, doc_status, (pie_status, doc)).
+    `texts`: list of str / bytes, or an ops.JsonDocs on the host."""
+    import numpy as np
+
+    from sph_pie_b200 import ops
+
+    docs = texts if isinstance(texts, ops.JsonDocs) else ops.JsonDocs.from_texts(texts)
+    so = load()
+    n = docs.n_docs
+    rows = np.zeros((max(n, 1), _lib.PIE_INGEST_TOTALS), dtype=np.uint32)
+    doc_status = np.zeros(max(n, 1), dtype=np.uint8)
+    totals = np.zeros(_lib.PIE_INGEST_TOTALS, dtype=np.int64)
+    status = np.zeros(2, dtype=np.int32)
+    p = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    so.oracle_ingest_measure(C.c_void_p(docs.data.data_ptr()), C.c_void_p(docs.offsets.data_ptr()), C.c_int64(n), p(rows),
+                             p(doc_status), p(totals), p(status), C.c_int(nthreads))
+    if status[0] != 0:
+        return None, doc_status[:n], (int(status[0]), int(status[1]))
+    table = ops.alloc_ingest_table(n, totals.tolist(), "cpu")
+    view = table.view()
+    so.oracle_ingest_fill(C.c_void_p(docs.data.data_ptr()), C.c_void_p(docs.offsets.data_ptr()), C.c_int64(n), p(rows),
+                          p(doc_status), p(totals), C.byref(view), C.c_int(nthreads))
+    return table, doc_status[:n], (0, -1)

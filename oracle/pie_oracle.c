@@ -809,3 +809,496 @@ int oracle_compute_metrics(const pie_archive_view* v, int32_t* out, uint8_t* tex
 void oracle_number_to_string_batch(const double* x, int64_t n, char* out, int32_t* lens) {
   for (int64_t i = 0; i < n; ++i) lens[i] = js_number_to_string(x[i], out + 32 * i);
 }
+
+/* =====================================================================================================
+ * Stored documents -> the archive table: JSON.parse(row.data) as _mapArchiveRow applies it (reference
+ * server/storage/sqlProvider.js:892-926: null unless the text parses to an object; arrays are objects) followed
+ * by the projection on the table's schema (sph_pie_b200/columnar.py pack_shows, i.e. sqlProvider.js:361-409).
+ * Written independently of the kernels: recursive descent over ECMA-404, a byte at a time, numbers by strtod
+ * (glibc: correctly rounded).  Two passes per document, as the table is laid out from the counts of the first.
+ * Also the CPU baseline of the ingest path.
+ * ===================================================================================================== */
+#define ING_PLANES 26
+#define ING_ENTRIES 23
+#define ING_CREW_ITEMS 24
+#define ING_ACTION_ITEMS 25
+#define ING_MAX_DEPTH 64
+
+typedef struct pie_strcol_mut_ { int32_t* offsets; uint8_t* data; } ing_col;
+
+typedef struct {
+  /* the 23 heaps in table order (7 show columns, crew items, 14 entry columns, action items) */
+  ing_col heap[23];
+  int32_t *entry_offsets, *crew_list, *actions_list;
+  double *created_at, *archived_at, *delay_sec, *entry_ts;
+  uint8_t* delay_valid;
+} ing_out;
+
+typedef struct {
+  const uint8_t *p, *end;
+  int depth;
+  int syntax;  /* the text is not JSON: the row is dropped */
+  int hard;    /* first of PIE_ERR_SCHEMA / PIE_ERR_UNSUPPORTED_JSON met (reported only if the text is JSON) */
+  int write;   /* second pass */
+  uint64_t pos[ING_PLANES];
+  const ing_out* out;
+  int64_t show;
+} ing;
+
+static void ing_hard(ing* j, int code) { if (!j->hard) j->hard = code; }
+static void ing_ws(ing* j) { while (j->p < j->end && (*j->p == ' ' || *j->p == '\t' || *j->p == '\n' || *j->p == '\r')) ++j->p; }
+static int ing_hex(int c) {
+  if (c >= '0' && c <= '9') return c - '0';
+  if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+  if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+  return -1;
+}
+
+/* a string, the cursor on its opening quote.  dst (may be NULL) receives the unescaped UTF-8; *len its length;
+ * key (may be NULL) the first 31 bytes, NUL-terminated; *lone: an escape named an unpaired surrogate */
+static void ing_string(ing* j, uint8_t* dst, uint64_t* len, char* key, int* lone) {
+  uint64_t n = 0;
+  uint32_t high = 0;
+  *lone = 0;
+#define ING_PUT(b) do { uint8_t b_ = (uint8_t)(b); if (dst) dst[n] = b_; if (key && n < 31) key[n] = (char)b_; ++n; } while (0)
+#define ING_PUT3(cp) do { ING_PUT(0xE0 | ((cp) >> 12)); ING_PUT(0x80 | (((cp) >> 6) & 0x3F)); ING_PUT(0x80 | ((cp) & 0x3F)); } while (0)
+  ++j->p;
+  for (;;) {
+    if (j->p >= j->end) { j->syntax = 1; break; }
+    uint32_t c = *j->p++;
+    if (c == '\\') {
+      if (j->p >= j->end) { j->syntax = 1; break; }
+      const int e = *j->p++;
+      uint32_t cp;
+      if (e == 'u') {
+        if (j->end - j->p < 4) { j->syntax = 1; break; }
+        cp = 0;
+        for (int k = 0; k < 4; ++k) {
+          const int h = ing_hex(j->p[k]);
+          if (h < 0) { j->syntax = 1; break; }
+          cp = cp * 16 + (uint32_t)h;
+        }
+        if (j->syntax) break;
+        j->p += 4;
+        if (high) {
+          if (cp >= 0xDC00 && cp <= 0xDFFF) {
+            const uint32_t full = 0x10000 + ((high - 0xD800) << 10) + (cp - 0xDC00);
+            high = 0;
+            ING_PUT(0xF0 | (full >> 18)); ING_PUT(0x80 | ((full >> 12) & 0x3F)); ING_PUT(0x80 | ((full >> 6) & 0x3F)); ING_PUT(0x80 | (full & 0x3F));
+            continue;
+          }
+          *lone = 1;
+          ING_PUT3(high);
+          high = 0;
+        }
+        if (cp >= 0xD800 && cp <= 0xDBFF) { high = cp; continue; }
+        if (cp >= 0xDC00 && cp <= 0xDFFF) *lone = 1;
+      } else {
+        switch (e) {
+          case '"': cp = '"'; break; case '\\': cp = '\\'; break; case '/': cp = '/'; break; case 'b': cp = 8; break;
+          case 'f': cp = 12; break; case 'n': cp = 10; break; case 'r': cp = 13; break; case 't': cp = 9; break;
+          default: j->syntax = 1; cp = 0; break;
+        }
+        if (j->syntax) break;
+        if (high) { *lone = 1; ING_PUT3(high); high = 0; }
+      }
+      if (cp < 0x80) ING_PUT(cp);
+      else if (cp < 0x800) { ING_PUT(0xC0 | (cp >> 6)); ING_PUT(0x80 | (cp & 0x3F)); }
+      else ING_PUT3(cp);
+      continue;
+    }
+    if (high) { *lone = 1; ING_PUT3(high); high = 0; }
+    if (c == '"') break;
+    if (c < 0x20) { j->syntax = 1; break; }
+    ING_PUT(c);
+    if (c >= 0x80) { /* UTF-8, well-formed sequences only (Unicode table 3-7); otherwise reported, walk goes on */
+      int need = 0;
+      uint32_t lo = 0x80, hi = 0xBF;
+      if (c < 0xC2) ing_hard(j, PIE_ERR_UNSUPPORTED_JSON);
+      else if (c < 0xE0) need = 1;
+      else if (c < 0xF0) { need = 2; if (c == 0xE0) lo = 0xA0; if (c == 0xED) hi = 0x9F; }
+      else if (c < 0xF5) { need = 3; if (c == 0xF0) lo = 0x90; if (c == 0xF4) hi = 0x8F; }
+      else ing_hard(j, PIE_ERR_UNSUPPORTED_JSON);
+      for (int k = 0; k < need; ++k) {
+        if (j->p >= j->end || *j->p < lo || *j->p > hi) { ing_hard(j, PIE_ERR_UNSUPPORTED_JSON); break; }
+        ING_PUT(*j->p++);
+        lo = 0x80; hi = 0xBF;
+      }
+    }
+  }
+#undef ING_PUT3
+#undef ING_PUT
+  if (key) key[n < 31 ? n : 31] = 0;
+  *len = n;
+}
+
+/* a number, the cursor on '-' or a digit: grammar by hand, value by strtod */
+static double ing_number(ing* j) {
+  const uint8_t* s = j->p;
+  if (j->p < j->end && *j->p == '-') ++j->p;
+  if (j->p >= j->end || *j->p < '0' || *j->p > '9') { j->syntax = 1; return 0; }
+  if (*j->p == '0') { ++j->p; if (j->p < j->end && *j->p >= '0' && *j->p <= '9') { j->syntax = 1; return 0; } }
+  else while (j->p < j->end && *j->p >= '0' && *j->p <= '9') ++j->p;
+  if (j->p < j->end && *j->p == '.') {
+    ++j->p;
+    if (j->p >= j->end || *j->p < '0' || *j->p > '9') { j->syntax = 1; return 0; }
+    while (j->p < j->end && *j->p >= '0' && *j->p <= '9') ++j->p;
+  }
+  if (j->p < j->end && (*j->p == 'e' || *j->p == 'E')) {
+    ++j->p;
+    if (j->p < j->end && (*j->p == '+' || *j->p == '-')) ++j->p;
+    if (j->p >= j->end || *j->p < '0' || *j->p > '9') { j->syntax = 1; return 0; }
+    while (j->p < j->end && *j->p >= '0' && *j->p <= '9') ++j->p;
+  }
+  const size_t n = (size_t)(j->p - s);
+  char stack[128];
+  char* buf = n < sizeof(stack) ? stack : (char*)malloc(n + 1);
+  memcpy(buf, s, n);
+  buf[n] = 0;
+  const double v = strtod(buf, NULL);
+  if (buf != stack) free(buf);
+  return v;
+}
+
+static int ing_literal(ing* j, const char* lit) {
+  const size_t n = strlen(lit);
+  if ((size_t)(j->end - j->p) < n || memcmp(j->p, lit, n) != 0) { j->syntax = 1; return 0; }
+  j->p += n;
+  return 1;
+}
+
+/* any value, validated and thrown away */
+static void ing_skip(ing* j) {
+  ing_ws(j);
+  if (j->p >= j->end) { j->syntax = 1; return; }
+  const int c = *j->p;
+  if (c == '"') { uint64_t n; int lone; ing_string(j, NULL, &n, NULL, &lone); return; }
+  if (c == '-' || (c >= '0' && c <= '9')) { ing_number(j); return; }
+  if (c == 't') { ing_literal(j, "true"); return; }
+  if (c == 'f') { ing_literal(j, "false"); return; }
+  if (c == 'n') { ing_literal(j, "null"); return; }
+  if (c != '{' && c != '[') { j->syntax = 1; return; }
+  if (j->depth >= ING_MAX_DEPTH) { j->hard = PIE_ERR_UNSUPPORTED_JSON; j->syntax = 2; return; } /* 2: stop, not a drop */
+  ++j->depth;
+  ++j->p;
+  const int close = c == '{' ? '}' : ']';
+  ing_ws(j);
+  if (j->p < j->end && *j->p == close) { ++j->p; --j->depth; return; }
+  for (;;) {
+    if (c == '{') {
+      ing_ws(j);
+      if (j->p >= j->end || *j->p != '"') { j->syntax = 1; return; }
+      uint64_t n; int lone;
+      ing_string(j, NULL, &n, NULL, &lone);
+      if (j->syntax) return;
+      ing_ws(j);
+      if (j->p >= j->end || *j->p != ':') { j->syntax = 1; return; }
+      ++j->p;
+    }
+    ing_skip(j);
+    if (j->syntax) return;
+    ing_ws(j);
+    if (j->p >= j->end) { j->syntax = 1; return; }
+    if (*j->p == ',') { ++j->p; continue; }
+    if (*j->p == close) { ++j->p; --j->depth; return; }
+    j->syntax = 1;
+    return;
+  }
+}
+
+/* a value that belongs in text heap h: string or null, anything else is a schema error (and still has to be JSON) */
+static void ing_text(ing* j, int h) {
+  ing_ws(j);
+  if (j->p < j->end && *j->p == '"') {
+    uint64_t n; int lone;
+    ing_string(j, j->write ? j->out->heap[h].data + j->pos[h] : NULL, &n, NULL, &lone);
+    j->pos[h] += n;
+    if (lone) ing_hard(j, PIE_ERR_SCHEMA);
+    return;
+  }
+  if (j->p < j->end && *j->p == 'n') { ing_literal(j, "null"); return; }
+  ing_hard(j, PIE_ERR_SCHEMA);
+  ing_skip(j);
+}
+
+/* crew / actions: a list of strings when the value is an array, else empty */
+static void ing_list(ing* j, int h, int items) {
+  ing_ws(j);
+  if (j->p >= j->end || *j->p != '[') { ing_skip(j); return; }
+  if (j->depth >= ING_MAX_DEPTH) { j->hard = PIE_ERR_UNSUPPORTED_JSON; j->syntax = 2; return; }
+  ++j->depth;
+  ++j->p;
+  ing_ws(j);
+  if (j->p < j->end && *j->p == ']') { ++j->p; --j->depth; return; }
+  for (;;) {
+    if (j->write) j->out->heap[h].offsets[j->pos[items]] = (int32_t)j->pos[h];
+    ++j->pos[items];
+    ing_text(j, h);
+    if (j->syntax) return;
+    ing_ws(j);
+    if (j->p >= j->end) { j->syntax = 1; return; }
+    if (*j->p == ',') { ++j->p; continue; }
+    if (*j->p == ']') { ++j->p; --j->depth; return; }
+    j->syntax = 1;
+    return;
+  }
+}
+
+/* a finite number, or absent (NaN) */
+static double ing_time(ing* j) {
+  ing_ws(j);
+  if (j->p < j->end && (*j->p == '-' || (*j->p >= '0' && *j->p <= '9'))) {
+    const double v = ing_number(j);
+    return isfinite(v) ? v : NAN;
+  }
+  ing_skip(j);
+  return NAN;
+}
+
+static const char* const kIngShowKeys[11] = {"id", "date", "time", "label", "leadPilot", "monkeyLead", "notes", "crew",
+                                             "createdAt", "archivedAt", "entries"};
+static const char* const kIngEntryKeys[17] = {"id", "unitId", "planned", "launched", "status", "primaryIssue", "subIssue",
+                                              "otherDetail", "severity", "rootCause", "operator", "batteryId", "commandRx",
+                                              "notes", "actions", "delaySec", "ts"};
+static int ing_key_index(const char* const* keys, int nkeys, const char* key, uint64_t len) {
+  if (len > 30) return -1;
+  for (int i = 0; i < nkeys; ++i)
+    if (strlen(keys[i]) == len && memcmp(keys[i], key, len) == 0) return i;
+  return -1;
+}
+
+/* the members of an object whose '{' has been taken: calls member(j, key index or -1) with the cursor behind ':' */
+static void ing_entry(ing* j) { /* the cursor on the element of `entries`, whatever it is */
+  const uint64_t row = j->pos[ING_ENTRIES]++;
+  double delay = 0.0, ts = NAN;
+  int valid = 0;
+  if (j->write) {
+    for (int h = 0; h < 14; ++h) j->out->heap[8 + h].offsets[row] = (int32_t)j->pos[8 + h];
+    j->out->actions_list[row] = (int32_t)j->pos[ING_ACTION_ITEMS];
+  }
+  ing_ws(j);
+  if (j->p < j->end && *j->p == '{') {
+    if (j->depth >= ING_MAX_DEPTH) { j->hard = PIE_ERR_UNSUPPORTED_JSON; j->syntax = 2; return; }
+    ++j->depth;
+    ++j->p;
+    uint32_t seen = 0;
+    ing_ws(j);
+    if (j->p < j->end && *j->p == '}') { ++j->p; --j->depth; }
+    else for (;;) {
+      ing_ws(j);
+      if (j->p >= j->end || *j->p != '"') { j->syntax = 1; return; }
+      char key[32]; uint64_t klen; int lone;
+      ing_string(j, NULL, &klen, key, &lone);
+      if (j->syntax) return;
+      ing_ws(j);
+      if (j->p >= j->end || *j->p != ':') { j->syntax = 1; return; }
+      ++j->p;
+      const int k = ing_key_index(kIngEntryKeys, 17, key, klen);
+      if (k >= 0) { if (seen >> k & 1) ing_hard(j, PIE_ERR_UNSUPPORTED_JSON); seen |= 1u << k; }
+      if (k >= 0 && k < 14) ing_text(j, 8 + k);
+      else if (k == 14) ing_list(j, 22, ING_ACTION_ITEMS);
+      else if (k == 15) { /* delaySec: number | null */
+        ing_ws(j);
+        if (j->p < j->end && (*j->p == '-' || (*j->p >= '0' && *j->p <= '9'))) { delay = ing_number(j); valid = 1; }
+        else if (j->p < j->end && *j->p == 'n') ing_literal(j, "null");
+        else { ing_hard(j, PIE_ERR_SCHEMA); ing_skip(j); }
+      } else if (k == 16) ts = ing_time(j);
+      else ing_skip(j);
+      if (j->syntax) return;
+      ing_ws(j);
+      if (j->p >= j->end) { j->syntax = 1; return; }
+      if (*j->p == ',') { ++j->p; continue; }
+      if (*j->p == '}') { ++j->p; --j->depth; break; }
+      j->syntax = 1;
+      return;
+    }
+  } else {
+    ing_skip(j); /* not an object: a row without fields */
+    if (j->syntax) return;
+  }
+  if (j->write) {
+    j->out->delay_sec[row] = delay;
+    j->out->delay_valid[row] = (uint8_t)valid;
+    j->out->entry_ts[row] = ts;
+  }
+}
+
+/* one document; returns 0 kept, 1 dropped, or a negative pie_status */
+static int ing_document(ing* j) {
+  ing_ws(j);
+  int is_object = 0;
+  if (j->p < j->end && *j->p == '{') {
+    is_object = 1;
+    j->depth = 1;
+    ++j->p;
+    uint32_t seen = 0;
+    ing_ws(j);
+    if (j->p < j->end && *j->p == '}') { ++j->p; }
+    else for (;;) {
+      ing_ws(j);
+      if (j->p >= j->end || *j->p != '"') { j->syntax = 1; break; }
+      char key[32]; uint64_t klen; int lone;
+      ing_string(j, NULL, &klen, key, &lone);
+      if (j->syntax) break;
+      ing_ws(j);
+      if (j->p >= j->end || *j->p != ':') { j->syntax = 1; break; }
+      ++j->p;
+      const int k = ing_key_index(kIngShowKeys, 11, key, klen);
+      if (k >= 0) { if (seen >> k & 1) ing_hard(j, PIE_ERR_UNSUPPORTED_JSON); seen |= 1u << k; }
+      if (k >= 0 && k < 7) ing_text(j, k);
+      else if (k == 7) ing_list(j, 7, ING_CREW_ITEMS);
+      else if (k == 8 || k == 9) {
+        const double v = ing_time(j);
+        if (j->write) (k == 8 ? j->out->created_at : j->out->archived_at)[j->show] = v;
+      } else if (k == 10) {
+        ing_ws(j);
+        if (j->p < j->end && *j->p == '[') {
+          ++j->depth;
+          ++j->p;
+          ing_ws(j);
+          if (j->p < j->end && *j->p == ']') { ++j->p; --j->depth; }
+          else for (;;) {
+            ing_entry(j);
+            if (j->syntax) break;
+            ing_ws(j);
+            if (j->p >= j->end) { j->syntax = 1; break; }
+            if (*j->p == ',') { ++j->p; continue; }
+            if (*j->p == ']') { ++j->p; --j->depth; break; }
+            j->syntax = 1;
+            break;
+          }
+        } else ing_skip(j);
+      } else ing_skip(j);
+      if (j->syntax) break;
+      ing_ws(j);
+      if (j->p >= j->end) { j->syntax = 1; break; }
+      if (*j->p == ',') { ++j->p; continue; }
+      if (*j->p == '}') { ++j->p; break; }
+      j->syntax = 1;
+      break;
+    }
+  } else if (j->p < j->end && *j->p == '[') {
+    is_object = 1; /* typeof [] === 'object': an empty show */
+    ing_skip(j);
+  } else {
+    ing_skip(j);
+  }
+  if (j->syntax == 2) return PIE_ERR_UNSUPPORTED_JSON; /* too deep: reported at once */
+  if (!j->syntax) { ing_ws(j); if (j->p < j->end) j->syntax = 1; }
+  if (j->syntax) return 1;
+  if (j->hard) return j->hard;
+  return is_object ? 0 : 1;
+}
+
+typedef struct {
+  const uint8_t* text; const int64_t* offsets; int64_t d0, d1;
+  uint32_t* rows; /* [n][26] */
+  uint8_t* doc_status;
+  const ing_out* out;
+  int write;
+  int64_t bad_doc; int bad_code;
+} ing_job;
+
+static void* ing_worker(void* arg) {
+  ing_job* job = (ing_job*)arg;
+  job->bad_doc = -1;
+  job->bad_code = 0;
+  for (int64_t s = job->d0; s < job->d1; ++s) {
+    ing j;
+    memset(&j, 0, sizeof(j));
+    j.p = job->text + job->offsets[s];
+    j.end = job->text + job->offsets[s + 1];
+    j.write = job->write;
+    j.out = job->out;
+    j.show = s;
+    uint32_t* row = job->rows + s * ING_PLANES;
+    if (job->write) {
+      for (int p = 0; p < ING_PLANES; ++p) j.pos[p] = row[p];
+      for (int h = 0; h < 7; ++h) job->out->heap[h].offsets[s] = (int32_t)j.pos[h];
+      job->out->entry_offsets[s] = (int32_t)j.pos[ING_ENTRIES];
+      job->out->crew_list[s] = (int32_t)j.pos[ING_CREW_ITEMS];
+      job->out->created_at[s] = NAN;
+      job->out->archived_at[s] = NAN;
+      if (job->doc_status[s] == 0) ing_document(&j);
+      continue;
+    }
+    const int r = ing_document(&j);
+    if (r != 0) {
+      memset(j.pos, 0, sizeof(j.pos));
+      if (r < 0 && job->bad_doc < 0) { job->bad_doc = s; job->bad_code = r; }
+    }
+    job->doc_status[s] = r == 0 ? 0 : 1;
+    for (int p = 0; p < ING_PLANES; ++p) row[p] = (uint32_t)j.pos[p];
+  }
+  return NULL;
+}
+
+static void ing_run(ing_job* proto, int64_t n, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > n) nthreads = n > 0 ? (int)n : 1;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
+  ing_job* jobs = (ing_job*)malloc(sizeof(ing_job) * (size_t)nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    jobs[t] = *proto;
+    jobs[t].d0 = n * t / nthreads;
+    jobs[t].d1 = n * (t + 1) / nthreads;
+    pthread_create(&th[t], NULL, ing_worker, &jobs[t]);
+  }
+  proto->bad_doc = -1;
+  proto->bad_code = 0;
+  for (int t = 0; t < nthreads; ++t) {
+    pthread_join(th[t], NULL);
+    if (jobs[t].bad_doc >= 0 && proto->bad_doc < 0) { proto->bad_doc = jobs[t].bad_doc; proto->bad_code = jobs[t].bad_code; }
+  }
+  free(jobs);
+  free(th);
+}
+
+/* first pass: rows[n][26] receive the counts and are turned into exclusive prefixes; totals[26]; status = {code, doc} */
+int oracle_ingest_measure(const uint8_t* text, const int64_t* offsets, int64_t n_docs, uint32_t* rows, uint8_t* doc_status,
+                          int64_t* totals, int32_t* status, int nthreads) {
+  ing_job job;
+  memset(&job, 0, sizeof(job));
+  job.text = text; job.offsets = offsets; job.rows = rows; job.doc_status = doc_status;
+  ing_run(&job, n_docs, nthreads);
+  status[0] = job.bad_code;
+  status[1] = (int32_t)job.bad_doc;
+  for (int p = 0; p < ING_PLANES; ++p) {
+    uint64_t run = 0;
+    for (int64_t s = 0; s < n_docs; ++s) {
+      const uint32_t v = rows[s * ING_PLANES + p];
+      rows[s * ING_PLANES + p] = (uint32_t)run;
+      run += v;
+    }
+    totals[p] = (int64_t)run;
+    if (run > 0x7fffffffull && status[0] == 0) { status[0] = PIE_ERR_CAPACITY; status[1] = -1; }
+  }
+  return 0;
+}
+
+/* second pass into a table sized from the totals (same field order as pie_archive_view) */
+int oracle_ingest_fill(const uint8_t* text, const int64_t* offsets, int64_t n_docs, uint32_t* rows, uint8_t* doc_status,
+                       const int64_t* totals, const pie_archive_table* t, int nthreads) {
+  ing_out out;
+  const pie_strcol_mut* cols[23] = {&t->show_id, &t->show_date, &t->show_time, &t->show_label, &t->lead_pilot, &t->monkey_lead,
+                                    &t->show_notes, &t->crew.items, &t->entry_id, &t->unit_id, &t->planned, &t->launched,
+                                    &t->status, &t->primary_issue, &t->sub_issue, &t->other_detail, &t->severity, &t->root_cause,
+                                    &t->operator_name, &t->battery_id, &t->command_rx, &t->notes, &t->actions.items};
+  for (int h = 0; h < 23; ++h) { out.heap[h].offsets = cols[h]->offsets; out.heap[h].data = cols[h]->data; }
+  out.entry_offsets = t->entry_offsets; out.crew_list = t->crew.list_offsets; out.actions_list = t->actions.list_offsets;
+  out.created_at = t->created_at; out.archived_at = t->archived_at; out.delay_sec = t->delay_sec;
+  out.entry_ts = t->entry_ts; out.delay_valid = t->delay_valid;
+  ing_job job;
+  memset(&job, 0, sizeof(job));
+  job.text = text; job.offsets = offsets; job.rows = rows; job.doc_status = doc_status; job.out = &out; job.write = 1;
+  ing_run(&job, n_docs, nthreads);
+  /* the terminal offsets */
+  for (int h = 0; h < 7; ++h) out.heap[h].offsets[n_docs] = (int32_t)totals[h];
+  out.entry_offsets[n_docs] = (int32_t)totals[ING_ENTRIES];
+  out.crew_list[n_docs] = (int32_t)totals[ING_CREW_ITEMS];
+  out.heap[7].offsets[totals[ING_CREW_ITEMS]] = (int32_t)totals[7];
+  for (int h = 8; h < 22; ++h) out.heap[h].offsets[totals[ING_ENTRIES]] = (int32_t)totals[h];
+  out.actions_list[totals[ING_ENTRIES]] = (int32_t)totals[ING_ACTION_ITEMS];
+  out.heap[22].offsets[totals[ING_ACTION_ITEMS]] = (int32_t)totals[22];
+  return 0;
+}

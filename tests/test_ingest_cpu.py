@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+import oracle_c
 import pie_oracle as po
 from ingest_helpers import assert_tables_equal, host_ingest, oracle_ingest, stored_doc
 from sph_pie_b200 import _lib
@@ -41,11 +42,18 @@ def hostile_show(rng, n_entries):
 
 
 def check(docs, what=""):
+    """Three implementations on the same texts: the Python oracle (json module + packer), the C oracle (recursive
+    descent + strtod, oracle/pie_oracle.c) and the kernels' walk built for the host."""
     ref_table, ref_status = oracle_ingest(docs)
     table, status, err = host_ingest(docs)
     assert err == (0, -1), (what, err)
     assert np.array_equal(status, ref_status), f"{what} doc_status"
     assert_tables_equal(table, ref_table, what)
+    for threads in (1, 3):
+        ctable, cstatus, cerr = oracle_c.ingest(docs, nthreads=threads)
+        assert cerr == (0, -1), (what, cerr)
+        assert np.array_equal(cstatus, ref_status), f"{what} doc_status (C oracle)"
+        assert_tables_equal(ctable, ref_table, what + " C oracle")
     return table
 
 
@@ -122,6 +130,7 @@ def test_every_prefix_and_single_byte_damage_of_a_document():
     for d in special:
         _, _, err = host_ingest([d])
         assert err[0] in (_lib.PIE_ERR_SCHEMA, _lib.PIE_ERR_UNSUPPORTED_JSON) and err[1] == 0, (d, err)
+        assert oracle_c.ingest([d])[2][1] == 0, d
 
 
 SCHEMA_DOCS = [
@@ -144,11 +153,13 @@ def test_schema_and_unsupported_documents_fail_loudly():
             oracle_ingest([good, d])
         _, _, err = host_ingest([good, d, good, '{"id":7}'])
         assert err == (_lib.PIE_ERR_SCHEMA, 1), (d, err)
+        assert oracle_c.ingest([good, d, good, '{"id":7}'])[2] == (_lib.PIE_ERR_SCHEMA, 1), d
     for d in UNSUPPORTED_DOCS:
         with pytest.raises(po.UnsupportedJson):
             oracle_ingest([good, good, d])
         _, _, err = host_ingest([good, good, d, '{"id":7}'])
         assert err == (_lib.PIE_ERR_UNSUPPORTED_JSON, 2), (d, err)
+        assert oracle_c.ingest([good, good, d, '{"id":7}'])[2] == (_lib.PIE_ERR_UNSUPPORTED_JSON, 2), d
     # not errors: the same things where the table does not look, nesting of exactly 64, a dropped row that also has them
     fine = ['{"x":{"id":5,"id":6},"y":[{"delaySec":"12"}]}', "[" * 64 + "]" * 64, '{"x":' + "[" * 63 + "]" * 63 + "}",
             '{"id":5', '{"id":"a","id":"b"', '{"showNumber":5,"updatedAt":"x","entries":[{"extra":{"status":1}}]}']
