@@ -328,3 +328,19 @@ def test_reference_fixture_and_a_two_megabyte_document(cuda):
     text = stored_doc(big, rng, "stringify")
     assert 1.5e6 < len(text.encode()) < 2.1e6
     gpu_check(cuda, ["{}", text, fx["stored_text"]], "2 MB document", host_too=False)
+
+
+def test_random_json_on_the_gpu(cuda):
+    """The random documents of tests/test_ingest_cpu.py (any JSON value anywhere, random whitespace) on the GPU."""
+    rng = random.Random(2025)
+    docs = [cases.random_document(rng) for _ in range(8000)]
+    fine, schema, unsupported = cases.classify(docs)
+    assert len(fine) > 1500 and len(schema) > 1500
+    gpu_check(cuda, fine, "random JSON", host_too=False)
+    mixed = fine[:50] + [schema[0]] + fine[50:100] + [schema[1]]
+    with pytest.raises(_lib.SchemaError) as ei:
+        ops.ingest_json(ops.JsonDocs.from_texts(mixed).to(cuda))
+    assert ei.value.doc == 50
+    for d in schema[:300]:
+        with pytest.raises(_lib.SchemaError):
+            ops.ingest_json(ops.JsonDocs.from_texts([d]).to(cuda))

@@ -198,3 +198,62 @@ def test_reference_fixture_as_stored_text():
     assert_tables_equal(table, pack_shows([{**fx["show"], "entries": [fx["entry"]]}]), "fixture vs the objects")
     assert table.entry_cols["unit_id"].get(0) == "Drone-01" and table.crew.items.get(1) == "Nazar"
     assert float(table.delay_sec[0]) == 0.0 and int(table.delay_valid[0]) == 1
+
+
+def random_json_value(rng, depth=0):
+    """Any JSON value, biased towards the shapes the projection looks at (strings / numbers / null / arrays /
+    objects with known and unknown keys in any position), with random whitespace."""
+    ws = lambda: rng.choice(["", "", "", " ", "\n", "\t ", "\r\n  "])
+    kind = rng.random()
+    if depth > 5:
+        kind = min(kind, 0.55)
+    if kind < 0.25:
+        return json.dumps(hostile_text(rng, rng.randrange(0, 8)), ensure_ascii=rng.random() < 0.5)
+    if kind < 0.40:
+        return rng.choice(["0", "-0", "12", "1.5", "-3e2", "1E+2", "0.000001", "1704067200000", "9007199254740993", "1e400", "5e-324"])
+    if kind < 0.55:
+        return rng.choice(["null", "true", "false"])
+    if kind < 0.75:
+        items = [random_json_value(rng, depth + 1) for _ in range(rng.randrange(0, 4))]
+        return "[" + ws() + ("," + ws()).join(items) + ws() + "]"
+    keys = list(po.SHOW_DOC_KEYS) + list(po.ENTRY_DOC_KEYS) + ["x", "showNumber", "", "é", "entries ", "ID"]
+    members = []
+    for k in rng.sample(keys, rng.randrange(0, 7)):  # sample: no key twice in one object
+        members.append(json.dumps(k) + ws() + ":" + ws() + random_json_value(rng, depth + 1))
+    return "{" + ws() + ("," + ws()).join(members) + ws() + "}"
+
+
+def random_document(rng):
+    """A show-shaped document whose every value is random JSON: most are schema errors, many are fine."""
+    return random_json_value(rng, 0) if rng.random() < 0.3 else (
+        "{" + ",".join(json.dumps(k) + ":" + (
+            "[" + ",".join(random_json_value(rng, 2) for _ in range(rng.randrange(0, 4))) + "]" if k == "entries" and rng.random() < 0.7
+            else random_json_value(rng, 1)) for k in rng.sample(list(po.SHOW_DOC_KEYS) + ["x", "y"], rng.randrange(0, 8))) + "}")
+
+
+def classify(docs):
+    """Split random documents by what the oracle says of them: fine / schema error / unsupported."""
+    fine, schema, unsupported = [], [], []
+    for d in docs:
+        try:
+            oracle_ingest([d])
+            fine.append(d)
+        except TypeError:
+            schema.append(d)
+        except po.UnsupportedJson:
+            unsupported.append(d)
+    return fine, schema, unsupported
+
+
+def test_random_json_three_ways():
+    rng = random.Random(2024)
+    docs = [random_document(rng) for _ in range(6000)]
+    fine, schema, unsupported = classify(docs)
+    assert len(fine) > 1000 and len(schema) > 1000, (len(fine), len(schema), len(unsupported))
+    check(fine, "random JSON")
+    for d in schema[:1500]:
+        assert host_ingest([d])[2] == (_lib.PIE_ERR_SCHEMA, 0), d
+        assert oracle_c.ingest([d])[2] == (_lib.PIE_ERR_SCHEMA, 0), d
+    for d in unsupported:  # (a document may also hold a schema error: which of the two is met first is not specified)
+        assert host_ingest([d])[2] in ((_lib.PIE_ERR_UNSUPPORTED_JSON, 0), (_lib.PIE_ERR_SCHEMA, 0)), d
+        assert oracle_c.ingest([d])[2] in ((_lib.PIE_ERR_UNSUPPORTED_JSON, 0), (_lib.PIE_ERR_SCHEMA, 0)), d
