@@ -782,3 +782,90 @@ def js_json_stringify(value) -> str:
         return "{" + ",".join(json_quote(k) + ":" + js_json_stringify(v) for k, v in value.items()
                               if v is not UNDEFINED) + "}"
     raise TypeError(type(value).__name__)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# _mapArchiveRow in full: the row's timestamp columns over the document's fields (sqlProvider.js:905-918)
+# ---------------------------------------------------------------------------------------------------------
+_JS_WS = "\t\n\v\f\r                  　﻿"
+
+
+def js_string_to_number(s: str) -> float:
+    """StringToNumber (ECMA-262 7.1.4.1.1): white space trimmed, '' -> 0, decimal literals (optional sign, `.5`, `5.`,
+    exponents), Infinity, 0x / 0o / 0b integers; anything else NaN."""
+    import re
+
+    t = s.strip(_JS_WS)
+    if t == "":
+        return 0.0
+    m = re.fullmatch(r"0[xX]([0-9a-fA-F]+)|0[oO]([0-7]+)|0[bB]([01]+)", t)
+    if m:
+        base = 16 if m.group(1) else 8 if m.group(2) else 2
+        return float(int(m.group(1) or m.group(2) or m.group(3), base))
+    if re.fullmatch(r"[+-]?Infinity", t):
+        return -math.inf if t[0] == "-" else math.inf
+    if re.fullmatch(r"[+-]?([0-9]+\.?[0-9]*([eE][+-]?[0-9]+)?|\.[0-9]+([eE][+-]?[0-9]+)?)", t):
+        return float(t)  # Python's float(): the same correctly rounded value
+    return math.nan
+
+
+def js_to_number(v) -> float:
+    """ToNumber for the values a row or a parsed document can hold."""
+    if v is UNDEFINED:
+        return math.nan
+    if v is None:
+        return 0.0
+    if v is True:
+        return 1.0
+    if v is False:
+        return 0.0
+    if isinstance(v, (int, float)):
+        return float(v)
+    if isinstance(v, str):
+        return js_string_to_number(v)
+    if isinstance(v, list):  # ToPrimitive: join(',') — [] -> '' -> 0, [5] -> '5' -> 5
+        return js_string_to_number(js_array_join(v, ","))
+    return math.nan  # objects: '[object Object]'
+
+
+def get_timestamp(v):
+    """_getTimestamp(value) (sqlProvider.js:970-985): a finite number as it is; else Number(value) when finite (so null
+    is 0, '12' is 12, true is 1); else Date.parse of a string.  Date.parse is NOT restated here (V8's legacy parser):
+    a string that is not numeric raises NotImplementedError instead of guessing."""
+    if js_is_number(v) and math.isfinite(v):
+        return float(v)
+    n = js_to_number(v)
+    if math.isfinite(n):
+        return n
+    if isinstance(v, str):
+        raise NotImplementedError(f"Date.parse({v!r})")
+    return None
+
+
+def map_archive_row_full(row):
+    """_mapArchiveRow(row) (sqlProvider.js:892-926) for a row {data, archived_at?, created_at?, deleted_at?}: a missing
+    key is undefined, None is SQL NULL."""
+    if not row:
+        return None
+    show = map_archive_row(row.get("data") if row.get("data") is not None else "null")
+    if show is None:
+        return None
+    if isinstance(show, list):  # an array: properties are set on it, it has no fields of its own
+        show = JsObject()
+    get = lambda o, k: o[k] if k in o else UNDEFINED  # noqa: E731
+    archived = get_timestamp(get(row, "archived_at"))
+    if archived is None:
+        archived = get_timestamp(get(show, "archivedAt"))
+    stored_created = get_timestamp(get(row, "created_at"))
+    created = get_timestamp(get(show, "createdAt"))
+    if created is None:
+        created = stored_created
+    if archived is not None:
+        show["archivedAt"] = archived
+    if created is not None:
+        show["createdAt"] = created
+    if not isinstance(show.get("entries"), list):
+        show["entries"] = []
+    if not isinstance(show.get("crew"), list):
+        show["crew"] = []
+    return show

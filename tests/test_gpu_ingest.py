@@ -344,3 +344,35 @@ def test_random_json_on_the_gpu(cuda):
     for d in schema[:300]:
         with pytest.raises(_lib.SchemaError):
             ops.ingest_json(ops.JsonDocs.from_texts([d]).to(cuda))
+
+
+def test_map_archive_rows_with_the_rows_timestamp_columns(cuda):
+    """_mapArchiveRow in full (sqlProvider.js:892-926): archived_at of the row over the document's archivedAt, the
+    document's createdAt over created_at, NULL columns (Number(null) = 0), a column the SELECT left out."""
+    from sph_pie_b200 import mapArchiveRows
+    from sph_pie_b200.columnar import pack_shows
+
+    shows = table_to_shows(synth_archive(40, seed=9, missing_created_frac=0.5))
+    rows = []
+    for i, s in enumerate(shows):
+        # a timestamp the document does not have is ABSENT (the provider never stores null there; _getTimestamp would
+        # turn a null into 0, which the table — null and absent are one value — does not model: DESIGN.md §2)
+        s = {k: v for k, v in s.items() if not (k in ("createdAt", "archivedAt") and v is None)}
+        row = {"data": po.js_json_stringify(s)}
+        if i % 4 != 3:
+            row["archived_at"] = str(1704067200000 + i) if i % 5 else " 1.7040672e12 "
+        if i % 3 == 0:
+            row["created_at"] = None
+        elif i % 3 == 1:
+            row["created_at"] = po.js_number_to_string(1700000000000.0 + i)
+        rows.append(row)
+    rows[7]["data"] = "{broken"
+    rows[8]["data"] = "[]"
+    want = [po.map_archive_row_full(r) for r in rows]
+    for device in ("cuda", "cpu"):
+        table, dropped = mapArchiveRows(rows, device=device)
+        assert dropped.nonzero().flatten().tolist() == [7]
+        ref = pack_shows(want)
+        assert_tables_equal(table, ref, "mapArchiveRows with row columns " + device)
+    with pytest.raises(NotImplementedError):
+        mapArchiveRows([{"data": "{}", "archived_at": "2024-01-01"}])

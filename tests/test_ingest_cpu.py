@@ -257,3 +257,22 @@ def test_random_json_three_ways():
     for d in unsupported:  # (a document may also hold a schema error: which of the two is met first is not specified)
         assert host_ingest([d])[2] in ((_lib.PIE_ERR_UNSUPPORTED_JSON, 0), (_lib.PIE_ERR_SCHEMA, 0)), d
         assert oracle_c.ingest([d])[2] in ((_lib.PIE_ERR_UNSUPPORTED_JSON, 0), (_lib.PIE_ERR_SCHEMA, 0)), d
+
+
+def test_row_timestamps_host_logic():
+    """storage._row_timestamp (the product's host side of _getTimestamp, sqlProvider.js:970-985) against the oracle."""
+    import math
+
+    from sph_pie_b200 import storage
+
+    values = [storage._MISSING, None, True, False, 5, 5.5, -0.0, "", "  ", " 12 ", "1e3", ".5", "5.", "0x1F", "0b11", "0o17", "+7",
+              "-7.25", "1704067200000", "1e+21", float("inf"), float("nan"), "\ufeff42\u3000", "00012"]
+    for v in values:
+        got = storage._row_timestamp(v)
+        want = po.get_timestamp(po.UNDEFINED if v is storage._MISSING else v)
+        assert (want is None and math.isnan(got)) or got == want, (v, got, want)
+    for v in ["abc", "2024-01-01T00:00:00Z", "Infinity", "-Infinity", "１２", "-0x1", "1_000", "12px", "0x", "1e"]:
+        with pytest.raises(NotImplementedError):
+            storage._row_timestamp(v)
+        with pytest.raises(NotImplementedError):
+            po.get_timestamp(v)
