@@ -7,15 +7,18 @@
 // DOCUMENT AT A TIME with a complete ECMA-404 recogniser (strings with every escape and UTF-8 validation, numbers,
 // literals, nesting checked against a 64-level kind stack) written as a resumable state machine
 // (pie_json_walk.cuh): a step is one token, or up to 8 bytes of a string found with word-wide byte tests.  The
-// kernels are persistent: a lane takes its next document from a counter the moment its current one ends, so a warp
-// never waits for its longest document.  The text is read through the read-only path 8 aligned bytes at a time with
-// the next word already in flight.
+// kernels are persistent, and documents are handed out by LENGTH CLASS, 32 neighbours of that order to a warp at a
+// time: documents of one length are almost always of one make, and lanes that start them together walk them roughly
+// in step.  The text is read through the read-only path 8 aligned bytes at a time with the next word in flight.
 //
-//   pass 1  ingest_measure_kernel   per document: entries, items of crew / actions, unescaped bytes of each of the 23
-//                                   string heaps; syntax errors make the document a dropped row (all counts zero)
-//   scan    ingest_scan_*           exclusive prefix sums of the 26 counts over the documents (a row per document), totals
-//   pass 2  ingest_fill_kernel      the same walk (same template) with every counter started at its prefix: offsets,
-//                                   unescaped bytes, numbers (pie_numparse.cuh, correctly rounded)
+//   order   ingest_order_*              counting sort of the documents by length class (16 bytes)
+//   pass 1  ingest_walk_kernel<false>   per document: entries, items of crew / actions, unescaped bytes of each of the
+//                                       23 string heaps — one 104-byte row; syntax errors make the document a dropped
+//                                       row (all counts zero)
+//   scan    ingest_scan_*               exclusive prefix sums of the 26 counts over the documents, in place; totals
+//   pass 2  ingest_walk_kernel<true>    the same walk (same template) with every counter started at its prefix:
+//                                       unescaped bytes in place, one 96-byte row per entry (offsets, numbers)
+//           ingest_rows_to_columns      the entry rows into the table's entry columns, coalesced
 //
 // Restrictions that fail loudly (pie_status in the status word, first offending document): a text field that is not
 // a string / null, delaySec that is not a number / null, a string with a lone surrogate escape (pack_shows raises
