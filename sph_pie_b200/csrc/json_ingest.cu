@@ -11,7 +11,7 @@
 // time: documents of one length are almost always of one make, and lanes that start them together walk them roughly
 // in step.  The text is read through the read-only path 8 aligned bytes at a time with the next word in flight.
 //
-//   order   ingest_order_*              counting sort of the documents by length class (16 bytes)
+//   order   ingest_order_*              counting sort of the documents by length
 //   pass 1  ingest_walk_kernel<false>   per document: entries, items of crew / actions, unescaped bytes of each of the
 //                                       23 string heaps — one 104-byte row; syntax errors make the document a dropped
 //                                       row (all counts zero)
@@ -49,12 +49,12 @@ struct IngestScratch {
   int32_t* order;                  // [n_docs] the documents by length class
 };
 
-// Documents are handed to the warps in order of length (classes of 16 bytes), 32 neighbours of that order at a time:
+// Documents are handed to the warps in order of length (to the byte, up to 16 KB; longer ones share a class), 32 neighbours of that order at a time:
 // documents of one length are almost always documents of one make (same number of entries, same keys), and 32 lanes
 // that start such documents together walk them in step — the same tokens in the same turns — instead of each lane
 // paying for the union of 32 unrelated paths.  Measured: 66 -> 51 ms per 2^20 documents.
-constexpr int kOrderBuckets = 4096;
-constexpr int kOrderShift = 4;
+constexpr int kOrderBuckets = 16384;
+constexpr int kOrderShift = 0;
 
 __device__ __forceinline__ uint32_t length_class(const int64_t* __restrict__ doc_offsets, int64_t s) {
   const int64_t c = (doc_offsets[s + 1] - doc_offsets[s]) >> kOrderShift;
