@@ -97,14 +97,35 @@ struct DocCursor {
     cur >>= 8;
     if (--left == 0) refill();
   }
-  // steps over n <= left bytes
+  // The next up-to-8 bytes of the text wherever the cursor stands in its word: what is left of the current word with
+  // the start of the next one behind it.  *avail = how many of them are text (8 except at the end of the document).
+  // A string is then scanned in ceil(length / 8) steps whatever its phase against the aligned words — lanes that walk
+  // documents of the same make stay in step even after one value was a byte longer in one of them.
+  PIE_JW_HD uint64_t window(int* avail) const {
+    uint64_t w8 = cur;
+    int n = left;
+    if (left < 8 && words_left > 0) {
+      w8 |= nxt << (8 * left);  // left >= 1 here: a cursor with bytes to come never rests on an empty word
+      n = left + (words_left == 1 ? tail_bytes : 8);
+      if (n > 8) n = 8;
+    }
+    *avail = n;
+    return w8;
+  }
+  // steps over n bytes of the window
   PIE_JW_HD void advance(int n) {
-    if (n >= left) {
-      left = 0;
-      refill();
-    } else {
+    if (n < left) {
       cur >>= 8 * n;
       left -= n;
+      return;
+    }
+    n -= left;
+    left = 0;
+    refill();
+    if (n > 0) {  // into the next word: n < 8 of its bytes
+      cur >>= 8 * n;
+      left -= n;
+      if (left == 0) refill();
     }
   }
 };
@@ -392,13 +413,14 @@ struct DocWalker {
       PIE_EXTRA3(high);
       high = 0;
     }
-    const uint64_t x = c.cur;
+    int avail;
+    const uint64_t x = c.window(&avail);
     const uint64_t k80 = 0x8080808080808080ull, k01 = 0x0101010101010101ull;
     const uint64_t q = x ^ (k01 * 0x22), bs = x ^ (k01 * 0x5C);
     // 0x80 in every byte that is >= 0x80, < 0x20, '"' or '\\' — exact up to and including the first such byte
     const uint64_t special = (x & k80) | ((x - k01 * 0x20) & ~x & k80) | ((q - k01) & ~q & k80) | ((bs - k01) & ~bs & k80);
     int n = special ? (jw_ctz64(special) >> 3) : 8;
-    if (n > c.left) n = c.left;
+    if (n > avail) n = avail;
     if (extra_n) n = 0;  // (rare) the lone surrogate's bytes go first; the plain run waits for the next step
     bool at_special = true;
     if (n > 0) {
