@@ -376,3 +376,30 @@ def test_map_archive_rows_with_the_rows_timestamp_columns(cuda):
         assert_tables_equal(table, ref, "mapArchiveRows with row columns " + device)
     with pytest.raises(NotImplementedError):
         mapArchiveRows([{"data": "{}", "archived_at": "2024-01-01"}])
+
+
+def test_documents_that_do_not_start_at_offset_zero(cuda):
+    """A slice of a larger text buffer: offsets[0] != 0, every alignment of the first byte (both entry points and the
+    one-call step)."""
+    rng = random.Random(12)
+    shows = [cases.hostile_show(rng, rng.randrange(0, 5)) for _ in range(40)]
+    for i, s in enumerate(shows):  # timestamps the daily grouping accepts (an out-of-range one is a RangeError there)
+        s["createdAt"], s["archivedAt"] = 1704067200000.0 + 3600000.0 * i, None
+    texts = [stored_doc(s, rng, "stringify") for s in shows]
+    ref, ref_status = oracle_ingest(texts)
+    base = ops.JsonDocs.from_texts(texts)
+    nbytes = int(base.offsets[-1])
+    for lead in (1, 5, 8, 13, 64):
+        data = torch.cat([torch.full((lead,), ord("}"), dtype=torch.uint8), base.data[:nbytes], torch.full((9,), ord("{"), dtype=torch.uint8)])
+        docs = ops.JsonDocs(base.offsets + lead, data)
+        for d in (docs, docs.to(cuda)):
+            table, status = ops.ingest_json(d)
+            assert np.array_equal(status.cpu().numpy(), ref_status)
+            assert_tables_equal(table, ref, f"lead {lead}")
+        st, dl, rows, dropped = ops.archive_step_json_host(docs, 0)
+        ref_rows = ops.csv_rows(ref)
+        assert torch.equal(rows.row_offsets, ref_rows.row_offsets) and torch.equal(rows.data, ref_rows.data)
+        # a window inside the buffer: the middle documents only
+        sub = ops.JsonDocs(docs.offsets[10:31].clone(), docs.data)
+        table, status = ops.ingest_json(sub.to(cuda))
+        assert_tables_equal(table, oracle_ingest(texts[10:30])[0], f"lead {lead} middle")
