@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(1024) ingest_order_scan_kernel(IngestScratch s
 __global__ void __launch_bounds__(256) ingest_order_place_kernel(const int64_t* __restrict__ doc_offsets, int64_t n_docs,
                                                                  IngestScratch sc) {
   const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (s < n_docs) sc.order[atomicAdd(sc.buckets + length_class(doc_offsets, s), 1u)] = (int32_t)s;
+  // longest first: the documents drawn last are the short ones, so the kernel does not end on a few lanes still walking
+  // the longest documents
+  if (s < n_docs) sc.order[n_docs - 1 - atomicAdd(sc.buckets + length_class(doc_offsets, s), 1u)] = (int32_t)s;
 }
 
 constexpr int kScanThreads = 1024;
