@@ -155,6 +155,10 @@ void pie_host_free(void* p);
 void pie_last_transfer_bytes(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 /* Cumulative number of CUDA kernels this library has launched in this process. */
 uint64_t pie_kernel_launch_count(void);
+/* The *_host entry points keep their device staging arenas, output buffers, streams, events and pinned bounce memory
+ * between calls (grow-only).  pie_release gives all of it back — for a long-lived host process (the Node server a
+ * binding would live in) after a large batch; the next call allocates again.  Synchronises the device. */
+int pie_release(void);
 
 /* ---- archive statistics: replaces computeArchiveShowStats (public/app.js:3898-3953), called per
  * show from buildArchiveDailyGroups (:3429-3432).  Reads: entry_offsets, status, launched,

@@ -124,6 +124,7 @@ SIGNATURES = {
     "pie_host_free": (None, [C.c_void_p]),
     "pie_last_transfer_bytes": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pie_kernel_launch_count": (C.c_uint64, []),
+    "pie_release": (C.c_int, []),
     "pie_show_stats_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pie_show_stats_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64]),
     "pie_daily_scratch_bytes": (C.c_uint64, [C.c_int64]),

@@ -21,7 +21,8 @@
 
 namespace pie {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
+int g_sm_count = 0;
 
 // tunables (overridable with -D for scripts/sweep_stats.py; defaults are the measured best)
 #ifndef PIE_STATS_THREADS

@@ -1602,7 +1602,7 @@ static cudaError_t launch_rows(const pie_archive_view& v, const RowTable& tab, i
   expand_entry_show_kernel<<<(unsigned)((v.n_shows + 255) / 256), 256, 0, stream>>>(v, sc.entry_show);
   {
     int64_t blocks = (v.n_entries * 3 + 255) / 256;  // ~ a 16-byte chunk per thread for the widest heaps
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > sm_count_or_default() * 8) blocks = sm_count_or_default() * 8;
     if (blocks < 1) blocks = 1;
     column_dirty_kernel<kJson><<<dim3((unsigned)blocks, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries,
                                                                                  sc.col_dirty, sc.col_dirty_chunks);

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kScanThreads) ingest_scan_apply_kernel(IngestS
 // ~14 — a lane needs ~3.5 ms per 4 KB document, so a launch is latency-bound until every SM is full.)
 unsigned walk_blocks(int64_t n_docs) {
   const int64_t want = (n_docs + kIngestThreads - 1) / kIngestThreads;
-  const int64_t cap = (int64_t)PIE_SM_COUNT_B200 * 16;
+  const int64_t cap = (int64_t)sm_count_or_default() * 16;
   return (unsigned)(want < cap ? want : cap);
 }
 

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "pie_kernels.h"
@@ -14,7 +15,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
-int g_sm_count = 0;
+using pie::g_sm_count;  // set by pie_init; the launchers size their grids from it
 std::mutex g_host_mutex;  // host entry points share one arena + stream
 
 int fail(int code, const char* fmt, ...) {
@@ -88,6 +89,53 @@ int plan_strcol(StrColPlan& p, const pie_strcol* src, pie_strcol* dst, int64_t n
   return PIE_OK;
 }
 
+// first <= off[i] <= off[i+1] <= last for every row: with off[0] = first and off[n] = last that is "never decreases".
+// A malformed interior offset would make the kernels read outside the staged range.  Returns the first bad row or -1.
+int64_t first_decrease(const int32_t* off, int64_t n) {
+  int64_t i = 0;
+  for (; i + 1024 <= n; i += 1024) {  // branch-free blocks (vectorised), located only on failure
+    int bad = 0;
+    for (int64_t k = i; k < i + 1024; ++k) bad |= off[k + 1] < off[k];
+    if (bad) break;
+  }
+  for (; i < n; ++i)
+    if (off[i + 1] < off[i]) return i;
+  return -1;
+}
+
+struct OffsetsCheck {
+  const int32_t* off;
+  int64_t n;
+  const char* name;
+};
+// Checks every offsets array of a batch on a few host threads (the pass is ~4 bytes per row and column; it runs
+// while the previous chunk is on the device).
+int check_offsets(const std::vector<OffsetsCheck>& arrays) {
+  int64_t rows = 0;
+  for (const OffsetsCheck& a : arrays) rows += a.n;
+  std::vector<int64_t> bad(arrays.size(), -1);
+  auto run = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i)
+      if (arrays[i].off && arrays[i].n > 0) bad[i] = first_decrease(arrays[i].off, arrays[i].n);
+  };
+  const size_t nt = rows > (int64_t)1 << 20 ? 4 : 1;
+  if (nt == 1) {
+    run(0, arrays.size());
+  } else {
+    std::vector<std::thread> pool;
+    const size_t per = (arrays.size() + nt - 1) / nt;
+    for (size_t t = 0; t < nt; ++t) {
+      const size_t lo = t * per, hi = lo + per < arrays.size() ? lo + per : arrays.size();
+      if (lo < hi) pool.emplace_back(run, lo, hi);
+    }
+    for (std::thread& th : pool) th.join();
+  }
+  for (size_t i = 0; i < arrays.size(); ++i)
+    if (bad[i] >= 0)
+      return fail(PIE_ERR_INVALID_ARG, "column %s: offsets decrease at row %lld", arrays[i].name, (long long)bad[i]);
+  return PIE_OK;
+}
+
 int upload_strcol(const StrColPlan& p, uint64_t* h2d) {
   int32_t* d_off = (int32_t*)g_cur->take(4 * (uint64_t)(p.n + 1));
   const uint64_t nbytes = (uint64_t)(p.last - p.first);
@@ -120,6 +168,16 @@ int check_view_common(const pie_archive_view* v) {
 }
 
 uint64_t g_last_h2d = 0, g_last_d2h = 0;
+
+// Every *_host entry point enqueues copies into the caller's buffers.  Whatever way it is left — an error in the
+// middle included — none of them may still be in flight: the caller is free to release its memory when the call
+// returns.  (On the success path the stream is already idle and this costs nothing.)
+struct StreamDrain {
+  const cudaStream_t* stream;  // read at scope exit: the arena creates its stream on first use
+  ~StreamDrain() {
+    if (*stream) cudaStreamSynchronize(*stream);
+  }
+};
 
 // Grow-only device buffer for outputs whose size is only known after a device pass (CSV bytes):
 // growing it must not move the inputs already staged in an arena.
@@ -205,6 +263,17 @@ int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_
   }
   if (csv && E > 0 && (!hv->delay_sec || !hv->delay_valid))
     return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
+  {
+    std::vector<OffsetsCheck> checks;
+    checks.push_back({hv->entry_offsets, S, "entry_offsets"});
+    for (int i = 0; i < kCols; ++i)
+      if (format_reads(format, i)) checks.push_back({cols[i].src->offsets, cols[i].n, cols[i].name});
+    for (int i = 0; csv && i < 2; ++i) {
+      checks.push_back({lists[i].src->list_offsets, lists[i].n, lists[i].name});
+      checks.push_back({item_src[i].offsets, item_plans[i].n, lists[i].name});
+    }
+    if ((rc = check_offsets(checks))) return rc;
+  }
   if ((rc = g_cur->reserve(bytes))) return rc;
   if (!g_cur_stream) g_cur_stream = g_cur->stream;
   dv->n_shows = S;
@@ -267,7 +336,7 @@ int pie_init(int device) {
   PIE_CUDA(cudaGetDevice(&dev));
   cudaDeviceProp prop;
   PIE_CUDA(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10)
+  if (prop.major != 10 || prop.minor != 0)  // the `a` targets are not forward compatible: sm_103 has no image here
     return fail(PIE_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major,
                 prop.minor);
   g_sm_count = prop.multiProcessorCount;
@@ -420,6 +489,13 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   const bool has_time = has_date && hv->show_time.offsets;
   if (has_date && (rc = plan_strcol(p_date, &hv->show_date, nullptr, S, &bytes, "show_date"))) return rc;
   if (has_time && (rc = plan_strcol(p_time, &hv->show_time, nullptr, S, &bytes, "show_time"))) return rc;
+  {
+    std::vector<OffsetsCheck> checks = {{hv->entry_offsets, S, "entry_offsets"}, {hv->status.offsets, E, "status"},
+                                        {hv->launched.offsets, E, "launched"}, {hv->primary_issue.offsets, E, "primary_issue"}};
+    if (has_date) checks.push_back({hv->show_date.offsets, S, "show_date"});
+    if (has_time) checks.push_back({hv->show_time.offsets, S, "show_time"});
+    if ((rc = check_offsets(checks))) return rc;
+  }
   const int64_t Sc = S > 0 ? S : 1;
   bytes += pad(4 * (uint64_t)(S + 1)) + pad(8 * (uint64_t)E) + pad((uint64_t)E);          // offsets, delay, valid
   bytes += pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc);                  // stats planes
@@ -431,6 +507,7 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   cudaStream_t st = g_arena.stream;
   g_cur = &g_arena;
   g_cur_stream = st;
+  StreamDrain drain_on_exit{&g_arena.stream};
 
   // ---- H2D
   uint64_t h2d = 0, d2h = 0;
@@ -532,6 +609,9 @@ int pie_compute_metrics_host(const pie_archive_view* hv, int32_t* metrics_i32, u
   if ((rc = plan_strcol(p_planned, &hv->planned, nullptr, E, &bytes, "planned"))) return rc;
   if ((rc = plan_strcol(p_status, &hv->status, nullptr, E, &bytes, "status"))) return rc;
   if ((rc = plan_strcol(p_issue, &hv->primary_issue, nullptr, E, &bytes, "primary_issue"))) return rc;
+  if ((rc = check_offsets({{hv->entry_offsets, S, "entry_offsets"}, {hv->planned.offsets, E, "planned"},
+                           {hv->status.offsets, E, "status"}, {hv->primary_issue.offsets, E, "primary_issue"}})))
+    return rc;
   const int64_t Sc = S > 0 ? S : 1;
   bytes += pad(4 * (uint64_t)(S + 1)) + pad(8 * (uint64_t)E) + pad((uint64_t)E);
   bytes += pad(4ull * PIE_CM_COUNT * Sc) + pad((uint64_t)PIE_CM_TEXT * Sc);
@@ -539,6 +619,7 @@ int pie_compute_metrics_host(const pie_archive_view* hv, int32_t* metrics_i32, u
   cudaStream_t st = g_arena.stream;
   g_cur = &g_arena;
   g_cur_stream = st;
+  StreamDrain drain_on_exit{&g_arena.stream};
   uint64_t h2d = 0;
   pie_archive_view dv;
   memset(&dv, 0, sizeof(dv));
@@ -703,7 +784,19 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
   const int64_t S = hv->n_shows, E = hv->n_entries;
   if (S > 0 && (hv->entry_offsets[0] != 0 || hv->entry_offsets[S] != E))
     return fail(PIE_ERR_INVALID_ARG, "entry_offsets must run from 0 to n_entries");
+  if ((rc = check_offsets({{hv->entry_offsets, S, "entry_offsets"}}))) return rc;  // the chunking below walks it
   if ((rc = g_pipe.init())) return rc;
+  // Whatever way this function is left, nothing it enqueued may still be writing the caller's buffers (or reading
+  // an arena the next call resets): drain the three streams and hand the upload helpers back to the default arena.
+  struct PipeDrain {
+    ~PipeDrain() {
+      cudaStreamSynchronize(g_pipe.h2d);
+      cudaStreamSynchronize(g_pipe.cmp);
+      cudaStreamSynchronize(g_pipe.d2h);
+      g_cur = &g_arena;
+      g_cur_stream = g_arena.stream;
+    }
+  } drain_on_exit;
 
   // ---- analytics riding along: the per-batch arrays of the daily summary go up first, on the upload stream
   const int64_t Sc = S > 0 ? S : 1;
@@ -729,6 +822,12 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
     const bool has_date = hv->show_date.offsets != nullptr, has_time = has_date && hv->show_time.offsets != nullptr;
     if (has_date && (rc = plan_strcol(p_date, &hv->show_date, nullptr, S, &bytes, "show_date"))) return rc;
     if (has_time && (rc = plan_strcol(p_time, &hv->show_time, nullptr, S, &bytes, "show_time"))) return rc;
+    {
+      std::vector<OffsetsCheck> checks;
+      if (has_date) checks.push_back({hv->show_date.offsets, S, "show_date"});
+      if (has_time) checks.push_back({hv->show_time.offsets, S, "show_time"});
+      if ((rc = check_offsets(checks))) return rc;
+    }
     bytes += pad(4 * (uint64_t)(S + 1)) + 2 * pad(8 * (uint64_t)Sc) + pad(8 * (uint64_t)E);
     bytes += pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc) + daily_out_bytes(S, Sc);
     if ((rc = g_arena.reserve(bytes))) return rc;
@@ -1040,6 +1139,7 @@ int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint
                     int64_t* bad_doc) {
   std::lock_guard<std::mutex> lock(g_host_mutex);
   if (!host_table) return fail(PIE_ERR_INVALID_ARG, "host_table is NULL");
+  StreamDrain drain_on_exit{&g_arena.stream};
   int64_t totals[PIE_INGEST_TOTALS] = {0};
   pie_archive_table dt, ht;
   uint64_t block = 0, h2d = 0, d2h = 0;
@@ -1065,7 +1165,8 @@ int pie_ingest_host(const pie_json_docs* hd, pie_archive_table* host_table, uint
 }
 
 namespace {
-OutBuffer g_json_csv;  // CSV scratch, row offsets and bytes of pie_archive_step_json_host
+OutBuffer g_json_csv;        // CSV scratch and row offsets of pie_archive_step_json_host
+OutBuffer g_json_csv_bytes;  // ... and the CSV bytes (grown without moving what the kernels before wrote)
 }
 
 int pie_archive_step_json_host(const pie_json_docs* hd, int32_t tz_offset_minutes, uint8_t* doc_status, int32_t* stats_i32,
@@ -1076,6 +1177,7 @@ int pie_archive_step_json_host(const pie_json_docs* hd, int32_t tz_offset_minute
   if (tz_offset_minutes < -24 * 60 || tz_offset_minutes > 24 * 60) return fail(PIE_ERR_INVALID_ARG, "tz_offset_minutes out of range");
   if (!hd || !hout || !n_entries || !total_bytes) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
   const int64_t S = hd->n_docs;
+  StreamDrain drain_on_exit{&g_arena.stream};
   const bool want_stats = stats_i32 != nullptr || stats_f64 != nullptr;
   if (want_stats && (!stats_i32 || !stats_f64)) return fail(PIE_ERR_INVALID_ARG, "stats_i32 and stats_f64 go together");
   if (want_stats && stats_stride < S) return fail(PIE_ERR_INVALID_ARG, "stats_stride < n_docs");
@@ -1130,13 +1232,58 @@ int pie_archive_step_json_host(const pie_json_docs* hd, int32_t tz_offset_minute
                 (long long)(E + 1), (unsigned long long)out_capacity, (long long)row_capacity);
   }
   // the bytes: a second buffer after the offsets (grown without moving what the kernels above wrote)
-  static OutBuffer csv_bytes;
+  OutBuffer& csv_bytes = g_json_csv_bytes;
   if ((rc = csv_bytes.ensure(total ? total : 256))) return rc;
   PIE_CUDA(launch_rows(kFormatCsv, dv, d_rows, csv_bytes.base, total, 0ull, d_total, d_cscratch, st));
   PIE_CUDA(cudaMemcpyAsync(row_offsets, d_rows, 8 * (uint64_t)(E + 1), cudaMemcpyDeviceToHost, st));
   if (total) PIE_CUDA(cudaMemcpyAsync(out_data, csv_bytes.base, total, cudaMemcpyDeviceToHost, st));
   PIE_CUDA(cudaStreamSynchronize(st));
   g_last_d2h = d2h + 8 * (uint64_t)(E + 1) + total;
+  return PIE_OK;
+}
+
+/* Gives back everything the host entry points keep between calls: the device arenas and output buffers (they only
+ * ever grow), the pinned host image of pie_ingest_host, the streams and events.  The next call allocates afresh. */
+int pie_release(void) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (g_sm_count <= 0) return PIE_OK;  // never initialised: nothing is held
+  PIE_CUDA(cudaDeviceSynchronize());
+  auto free_arena = [](Arena& a, bool owns_stream) {
+    if (a.base) cudaFree(a.base);
+    if (a.stream && owns_stream) cudaStreamDestroy(a.stream);
+    a = Arena();
+  };
+  auto free_out = [](OutBuffer& b) {
+    if (b.base) cudaFree(b.base);
+    b = OutBuffer();
+  };
+  free_arena(g_arena, true);
+  free_arena(g_pipe_in[0], false);  // they borrow the pipeline's upload stream
+  free_arena(g_pipe_in[1], false);
+  free_out(g_pipe.out[0]);
+  free_out(g_pipe.out[1]);
+  free_out(g_ingest_out);
+  free_out(g_ingest_rows);
+  free_out(g_json_csv);
+  free_out(g_json_csv_bytes);
+  if (g_ingest_host) cudaFreeHost(g_ingest_host);
+  g_ingest_host = nullptr;
+  g_ingest_host_cap = 0;
+  if (g_pipe.h2d) {
+    cudaStreamDestroy(g_pipe.h2d);
+    cudaStreamDestroy(g_pipe.cmp);
+    cudaStreamDestroy(g_pipe.d2h);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(g_pipe.h2d_done[i]);
+      cudaEventDestroy(g_pipe.kernel_done[i]);
+      cudaEventDestroy(g_pipe.d2h_done[i]);
+    }
+    cudaFreeHost(g_pipe.h_total);
+    g_pipe = CsvPipeline();
+  }
+  g_cur = &g_arena;
+  g_cur_stream = nullptr;
+  cudaGetLastError();
   return PIE_OK;
 }
 

@@ -3,12 +3,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/sph_pie_b200.h"
 
 namespace pie {
 
 // cumulative number of kernels this library has launched (bench.py reports it as gpu_launches)
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
+// SMs of the device pie_init selected (grids are sized from it); 0 before pie_init
+extern int g_sm_count;
+inline int sm_count_or_default() { return g_sm_count > 0 ? g_sm_count : 148; }
 
 // archive_stats.cu
 cudaError_t launch_show_stats(const pie_archive_view& dev_view, int32_t* stats_i32, double* stats_f64,

@@ -15,6 +15,8 @@ import torch
 
 from .columnar import ArchiveTable
 
+PIE_DAY_NONE = -(2 ** 63)  # include/sph_pie_b200.h
+
 
 @dataclass
 class ShardPlan:
@@ -33,12 +35,21 @@ def plan_day_shards(entry_offsets: torch.Tensor, show_day: torch.Tensor, world: 
     S = show_day.numel()
     if world < 1:
         raise ValueError("world must be >= 1")
-    day = show_day.cpu()
+    day = show_day.cpu().clone()
     eo = entry_offsets.cpu().to(torch.int64)
-    if S > 1 and bool((day[1:] < day[:-1]).any()):
-        raise ValueError("archive is not ordered by day: cannot shard by day range")
     if S == 0:
         return ShardPlan([(0, 0)] * world)
+    # A show without a usable timestamp (PIE_DAY_NONE: buildArchiveDailyGroups skips it, public/app.js:3408-3411; a
+    # row the JSON ingest dropped is one) belongs to no day: it takes the day of the show before it — it may sit in
+    # any shard, its statistics are per show and no group contains it — and neither breaks the order nor makes a cut.
+    none = day == PIE_DAY_NONE
+    if bool(none.any()):
+        idx = torch.arange(S)
+        last_valid = torch.cummax(torch.where(none, torch.full_like(idx, -1), idx), 0).values
+        first_valid = int((~none).nonzero()[0]) if bool((~none).any()) else 0
+        day = day[torch.where(last_valid < 0, torch.full_like(idx, first_valid), last_valid)]
+    if S > 1 and bool((day[1:] < day[:-1]).any()):
+        raise ValueError("archive is not ordered by day: cannot shard by day range")
     # candidate cut points: show indices where a new day starts
     starts = torch.nonzero(day[1:] != day[:-1]).flatten() + 1
     cuts = torch.cat([torch.zeros(1, dtype=torch.int64), starts, torch.tensor([S], dtype=torch.int64)])

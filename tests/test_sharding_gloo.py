@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_shows, tz, ret):
+def _worker(rank, world, port, n_shows, tz, ret, holes=False):
     for p in (ROOT, os.path.join(ROOT, "oracle")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -32,6 +32,15 @@ def _worker(rank, world, port, n_shows, tz, ret):
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     table = synth_archive(n_shows, seed=21)  # same table on every rank (seeded)
+    if holes:  # shows without any usable timestamp in the middle of the archive (a dropped row is one): no day at all
+        from sph_pie_b200.columnar import pack_shows
+        from sph_pie_b200.synth import table_to_shows
+
+        shows = table_to_shows(table)
+        for i in (0, 7, 8, n_shows // 2, n_shows - 1):
+            shows[i] = None
+        shows[11] = dict(shows[11], createdAt=None, archivedAt=None, date="", entries=[])
+        table = pack_shows(shows)
 
     def compute(t):
         st, daily, rc, _ = oracle_c.archive_analytics(t, tz)
@@ -39,6 +48,8 @@ def _worker(rank, world, port, n_shows, tz, ret):
         return st, daily
 
     whole_st, whole_daily = compute(table)
+    if holes:
+        assert int((whole_daily.show_day_start == -(2 ** 63)).sum()) == 6
     local = run_sharded(table, whole_daily.show_day_start, rank, world, compute)
     merged = gather_to_rank0(local, rank, world)
     if rank == 0:
@@ -55,12 +66,13 @@ def _worker(rank, world, port, n_shows, tz, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_shows,tz", [(2, 1000, 0), (2, 37, -480), (3, 500, 330)])
-def test_day_sharded_equals_single_process(built, world, n_shows, tz):
+@pytest.mark.parametrize("world,n_shows,tz,holes", [(2, 1000, 0, False), (2, 37, -480, False), (3, 500, 330, False),
+                                                    (2, 60, 0, True)])
+def test_day_sharded_equals_single_process(built, world, n_shows, tz, holes):
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_shows, tz, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_shows, tz, ret, holes)) for r in range(world)]
     for p in procs:
         p.start()
     ok = ret.get(timeout=120)
@@ -83,4 +95,9 @@ def test_plan_cuts_only_at_day_boundaries():
             assert b in (0, 3, 5, 9, 10)  # a new day starts at every cut
     with pytest.raises(ValueError):
         plan_day_shards(eo, torch.tensor([0, 1, 0, 1, 1, 2, 2, 2, 2, 5]), 2)
+    # shows without a day (PIE_DAY_NONE) neither break the order nor make a cut
+    none = -(2 ** 63)
+    plan = plan_day_shards(eo, torch.tensor([none, 0, 0, 1, none, 1, 2, 2, none, 5]), 2)
+    assert plan.bounds[0][0] == 0 and plan.bounds[-1][1] == 10 and plan.bounds[0][1] in (3, 6, 9)
+    assert plan_day_shards(eo, torch.full((10,), none), 2).bounds == [(0, 10), (10, 10)]  # no day, no cut
     assert plan_day_shards(torch.zeros(1, dtype=torch.int64), torch.zeros(0, dtype=torch.int64), 3).bounds == [(0, 0)] * 3
