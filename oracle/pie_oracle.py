@@ -869,3 +869,270 @@ def map_archive_row_full(row):
     if not isinstance(show.get("crew"), list):
         show["crew"] = []
     return show
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Date.parse for the one format ECMA-262 specifies (21.4.1.32), as far as _getTimestamp (sqlProvider.js:978-982)
+# can meet it in a stored document: YYYY-MM-DD (UTC) and YYYY-MM-DDTHH:mm[:ss[.sss]][Z|+HH:mm|-HH:mm] (local time
+# when no offset is given).  Everything else is V8's legacy parser and is not restated: NotImplementedError.
+# ---------------------------------------------------------------------------------------------------------
+def js_date_parse(s: str, tz_offset_minutes: int = 0) -> float:
+    import re
+
+    m = re.fullmatch(r"(\d{4})-(\d{2})-(\d{2})(?:T(\d{2}):(\d{2})(?::(\d{2})(?:\.(\d{3}))?)?(Z|[+-]\d{2}:\d{2})?)?", s)
+    if not m:
+        raise NotImplementedError(f"Date.parse({s!r}): outside the ECMA-262 date-time format")
+    y, mo, d = int(m.group(1)), int(m.group(2)), int(m.group(3))
+    date_only = m.group(4) is None
+    h, mi = (int(m.group(4)), int(m.group(5))) if not date_only else (0, 0)
+    sec = int(m.group(6)) if m.group(6) else 0
+    ms = int(m.group(7)) if m.group(7) else 0
+    off = m.group(8)
+    if off and off != "Z":
+        oh, om = int(off[1:3]), int(off[4:6])
+        if oh > 23 or om > 59:
+            return math.nan
+    if not (1 <= mo <= 12 and 1 <= d <= 31 and h <= 24 and mi <= 59 and sec <= 59):
+        return math.nan
+    if h == 24 and (mi or sec or ms):
+        return math.nan
+    if d > days_in_month(y, mo):
+        raise NotImplementedError(f"Date.parse({s!r}): a day past the end of the month (engines disagree)")
+    local = ((days_from_civil(y, mo, d) * 24 + h) * 60 + mi) * 60000 + sec * 1000 + ms
+    if date_only or off == "Z":
+        return float(local)
+    if off:
+        sign = -1 if off[0] == "-" else 1
+        return float(local - sign * (int(off[1:3]) * 60 + int(off[4:6])) * 60000)
+    return float(local - tz_offset_minutes * 60000)
+
+
+def get_timestamp_tz(v, tz_offset_minutes: int = 0):
+    """_getTimestamp(value) (sqlProvider.js:970-985) with its Date.parse leg for the ECMA-262 format."""
+    if js_is_number(v) and math.isfinite(v):
+        return float(v)
+    n = js_to_number(v)
+    if math.isfinite(n):
+        return n
+    if isinstance(v, str):
+        parsed = js_date_parse(v, tz_offset_minutes)
+        if math.isfinite(parsed):
+            return parsed
+    return None
+
+
+def _nullish(a, b):
+    return b if a is None else a
+
+
+def map_archive_row_all(row, tz_offset_minutes: int = 0):
+    """_mapArchiveRow(row) (sqlProvider.js:892-926) in full: the row's archived_at / created_at / deleted_at columns
+    against the document's own fields, every one through _getTimestamp (null -> 0, numeric text -> its number, an
+    ISO date-time text -> Date.parse); deletedAt set or deleted; entries / crew made arrays."""
+    if not row:
+        return None
+    show = map_archive_row(row.get("data") if row.get("data") is not None else "null")
+    if show is None:
+        return None
+    if isinstance(show, list):
+        show = JsObject()
+    get = lambda o, k: o[k] if k in o else UNDEFINED  # noqa: E731
+    ts = lambda v: get_timestamp_tz(v, tz_offset_minutes)  # noqa: E731
+    archived = _nullish(ts(get(row, "archived_at")), ts(get(show, "archivedAt")))
+    created = _nullish(ts(get(show, "createdAt")), ts(get(row, "created_at")))
+    deleted = _nullish(ts(get(row, "deleted_at")), ts(get(show, "deletedAt")))
+    if archived is not None:
+        show["archivedAt"] = archived
+    if created is not None:
+        show["createdAt"] = created
+    if deleted is not None:
+        show["deletedAt"] = deleted
+    else:
+        show.pop("deletedAt", None)
+    if not isinstance(show.get("entries"), list):
+        show["entries"] = []
+    if not isinstance(show.get("crew"), list):
+        show["crew"] = []
+    return show
+
+
+# ---------------------------------------------------------------------------------------------------------
+# archive maintenance decisions (server/storage/sqlProvider.js:758-816, :863-890, :991-1009)
+# ---------------------------------------------------------------------------------------------------------
+AUTO_ARCHIVE_WINDOW_MS = 12 * 60 * 60 * 1000  # sqlProvider.js:9
+ARCHIVE_RETENTION_MONTHS = 2                  # sqlProvider.js:10
+UNDATED_KEY = "__undated__"                   # sqlProvider.js:774
+
+
+def archive_daily_shows_decision(rows_data, now_ms: float, tz_offset_minutes: int = 0):
+    """The decision of _archiveDailyShows (sqlProvider.js:758-816) for the rows of `shows`: which rows are archived
+    now, and in which order they are saved / dispatched.  Rows whose text does not parse to an object are skipped
+    (:767-772).  Groups are keyed by show.date.trim() (or '__undated__'), in order of first appearance (a Map); a
+    group is due when now - earliest >= 12 h, earliest = min over the group of _getTimestamp(item.createdAt) where
+    item.createdAt = _getTimestamp(show.createdAt) ?? _getTimestamp(show.updatedAt) — and _getTimestamp(null) is 0
+    (Number(null)), so a show without any usable timestamp counts as created at the epoch (:783-792).
+    Returns (due: list[bool] per row, order: row indices in the order the reference archives them)."""
+    ts = lambda v: get_timestamp_tz(v, tz_offset_minutes)  # noqa: E731
+    groups = {}
+    for i, data in enumerate(rows_data):
+        show = map_archive_row(data if data is not None else "null")  # JSON.parse + `typeof show !== 'object'`
+        if show is None:
+            continue
+        date = show.get("date") if isinstance(show, dict) else UNDEFINED
+        key = js_trim(date) if isinstance(date, str) and js_trim(date) else UNDATED_KEY
+        get = lambda k: show[k] if isinstance(show, dict) and k in show else UNDEFINED  # noqa: E731
+        created = _nullish(ts(get("createdAt")), ts(get("updatedAt")))
+        groups.setdefault(key, []).append((i, created))
+    due = [False] * len(rows_data)
+    order = []
+    for items in groups.values():
+        earliest = None
+        for _, created in items:
+            value = ts(created)  # created is a number or None; _getTimestamp(null) === 0
+            if value is None:
+                continue
+            if earliest is None or value < earliest:
+                earliest = value
+        if earliest is None:
+            continue
+        if now_ms - earliest >= AUTO_ARCHIVE_WINDOW_MS:
+            for i, _ in items:
+                due[i] = True
+                order.append(i)
+    return due, order
+
+
+def js_time_clip(t: float) -> float:
+    """TimeClip (ECMA-262 21.4.1.31): NaN beyond +-8.64e15, else truncated toward zero."""
+    if not math.isfinite(t) or abs(t) > 8.64e15:
+        return math.nan
+    return float(math.trunc(t)) + 0.0
+
+
+def add_months(timestamp, months: int, tz_offset_minutes: int = 0):
+    """_addMonths(timestamp, months) (sqlProvider.js:999-1009): new Date(timestamp), setMonth(getMonth() + months) in
+    LOCAL time (a fixed-offset zone here), getTime().  setMonth keeps the day of the month and lets MakeDay carry an
+    overflow into the following month (31 Dec + 2 months = 3 Mar, or 2 Mar in a leap year)."""
+    if not (js_is_number(timestamp) and math.isfinite(timestamp)):
+        return timestamp
+    t = js_time_clip(float(timestamp))
+    if math.isnan(t):
+        return timestamp
+    off = tz_offset_minutes * 60000
+    local = int(t) + off
+    day, in_day = local // 86400000, local % 86400000
+    y, m, d = civil_from_days(day)
+    m0 = (m - 1) + months
+    ym, mn = y + m0 // 12, m0 % 12
+    new_day = days_from_civil(ym, mn + 1, 1) + d - 1
+    v = float(new_day * 86400000 + in_day - off)
+    return js_time_clip(v)
+
+
+def is_archive_expired(created_at, now_ms: float, tz_offset_minutes: int = 0) -> bool:
+    """_isArchiveExpired (sqlProvider.js:991-997): now >= _addMonths(createdAt, 2); false for a non-finite createdAt
+    (and for an expiry that TimeClip turned into NaN)."""
+    if not (js_is_number(created_at) and math.isfinite(created_at)):
+        return False
+    expiry = add_months(created_at, ARCHIVE_RETENTION_MONTHS, tz_offset_minutes)
+    return bool(now_ms >= expiry)  # NaN compares false
+
+
+def purge_expired_archives_decision(rows, now_ms: float, tz_offset_minutes: int = 0):
+    """_purgeExpiredArchives (sqlProvider.js:863-890) for rows {data, created_at}: expired[i].  A text that does not
+    parse leaves show null; `show?.createdAt` of anything that is not an object is undefined, so the row's own
+    created_at column decides."""
+    ts = lambda v: get_timestamp_tz(v, tz_offset_minutes)  # noqa: E731
+    out = []
+    for row in rows:
+        data = row.get("data")
+        try:
+            show = js_json_parse(data if isinstance(data, str) else bytes(data).decode("utf-8"))
+        except (ValueError, RecursionError, TypeError, AttributeError):
+            show = None
+        doc_created = show["createdAt"] if isinstance(show, dict) and "createdAt" in show else UNDEFINED
+        created = _nullish(ts(doc_created), ts(row["created_at"] if "created_at" in row else UNDEFINED))
+        out.append(False if created is None else is_archive_expired(created, now_ms, tz_offset_minutes))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the schemaVersion 2 show payload (server/webhookDispatcher.js:460-496, :545-585)
+# ---------------------------------------------------------------------------------------------------------
+def normalize_entry_list(show):
+    """normalizeEntryList (webhookDispatcher.js:460-470): {...entry, actions: Array.isArray(entry?.actions) ?
+    entry.actions : []} for every element when show.entries is an array, else []."""
+    if not js_truthy(show):
+        return []
+    entries = js_get(show, "entries")
+    if not isinstance(entries, list):
+        return []
+    out = []
+    for entry in entries:
+        e = dict(entry) if isinstance(entry, dict) else {}  # spreading a non-object copies no own properties
+        actions = js_get(entry, "actions")
+        e["actions"] = actions if isinstance(actions, list) else []  # an existing key keeps its place
+        out.append(e)
+    return out
+
+
+def build_show_summary(show=UNDEFINED):
+    """buildShowSummary (webhookDispatcher.js:472-488): `|| ''` for the texts, `?? null` for the four timestamps."""
+    show = {} if show is UNDEFINED else show
+    crew = js_get(show, "crew")
+
+    def g(k):
+        return js_or(js_get(show, k), "")
+
+    def n(k):
+        v = js_get(show, k)
+        return None if (v is UNDEFINED or v is None) else v
+
+    return {"id": g("id"), "label": g("label"), "date": g("date"), "time": g("time"),
+            "crew": crew if isinstance(crew, list) else [], "leadPilot": g("leadPilot"), "monkeyLead": g("monkeyLead"),
+            "notes": g("notes"), "createdAt": n("createdAt"), "updatedAt": n("updatedAt"), "archivedAt": n("archivedAt"),
+            "deletedAt": n("deletedAt")}
+
+
+def normalize_meta(meta):
+    """normalizeMeta (webhookDispatcher.js:490-496): a shallow copy of a non-empty plain object, else null."""
+    if not isinstance(meta, dict) or not meta:
+        return None
+    return dict(meta)
+
+
+def dispatch_show_payload(event, show, dispatched_at: str, target_url, target_method, meta=UNDEFINED):
+    """The payload object dispatchShowEvent builds for every event but 'show.archived'
+    (webhookDispatcher.js:545-584): schemaVersion 2, the table / csv / message views of every entry, the show summary
+    twice and the entries as they are.  `dispatched_at` stands for new Date().toISOString(), the target for
+    activeConfig.url / .method."""
+    show = show if isinstance(show, dict) else {}
+    crew = js_get(show, "crew")
+    normalized = dict(show)
+    normalized["crew"] = crew if isinstance(crew, list) else []
+    normalized["entries"] = normalize_entry_list(show)
+    summary = build_show_summary(normalized)
+    table_rows = [build_table_row(normalized, e) for e in normalized["entries"]]
+
+    def cell(row, c):
+        v = js_get(row, c)
+        return "" if (v is UNDEFINED or v is None) else v  # ?? ''
+
+    payload = {
+        "event": event, "schemaVersion": 2, "dispatchedAt": dispatched_at,
+        "target": {"url": target_url, "method": target_method},
+        "table": {"columns": list(EXPORT_COLUMNS), "rows": [[cell(r, c) for c in EXPORT_COLUMNS] for r in table_rows]},
+        "csv": {"header": list(EXPORT_COLUMNS), "rows": [build_csv_row(r) for r in table_rows]},
+        "message": {"show": summary, "entries": table_rows},
+        "show": summary,
+        "entries": normalized["entries"],
+    }
+    m = normalize_meta(meta)
+    if m:
+        payload["meta"] = m
+    return payload
+
+
+def show_payload_json(event, show, dispatched_at: str, target_url, target_method, meta=UNDEFINED) -> str:
+    """JSON.stringify of that payload — the request body axios sends (sendWebhookPayload, :362-373)."""
+    return js_json_stringify(dispatch_show_payload(event, show, dispatched_at, target_url, target_method, meta))

@@ -118,7 +118,7 @@ int check_offsets(const std::vector<OffsetsCheck>& arrays) {
     for (size_t i = lo; i < hi; ++i)
       if (arrays[i].off && arrays[i].n > 0) bad[i] = first_decrease(arrays[i].off, arrays[i].n);
   };
-  const size_t nt = rows > (int64_t)1 << 20 ? 4 : 1;
+  const size_t nt = rows > (int64_t)1 << 20 ? 8 : 1;
   if (nt == 1) {
     run(0, arrays.size());
   } else {
@@ -875,7 +875,14 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
     const int slot = k & 1;
     CsvChunk& c = chunks[(size_t)k];
     const int64_t Ec = c.e1 - c.e0;
+    PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.h2d_done[slot], 0));
+    if (an && c.s1 > c.s0)  // the chunk's shows: status, launched, primaryIssue and delaySec are resident for the rows
+      PIE_CUDA(pie::launch_show_stats(c.dev, d_si + c.s0, d_sf + c.s0, Sc, g_sm_count, g_pipe.cmp));
+    // pass 1: sizes only (row offsets + total), so the output can be placed and sized exactly
+    PIE_CUDA(launch_rows(format, c.dev, c.d_offsets, nullptr, 0, bias, c.d_total, c.scratch, g_pipe.cmp));
+    PIE_CUDA(cudaMemcpyAsync(g_pipe.h_total, c.d_total, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
     if (k + 1 < K) {  // prefetch the next chunk into the other input arena once chunk k-1's kernels have left it
+      // (after this chunk's kernels are enqueued: the host's check of the next chunk's offsets overlaps them)
       if (k >= 1) {  // ... and its row offsets (which live in that arena) have been copied out
         PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.kernel_done[slot ^ 1], 0));
         PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.d2h_done[slot ^ 1], 0));
@@ -883,12 +890,6 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
       if ((rc = upload_chunk(&chunks[(size_t)k + 1], slot ^ 1, &h2d, format))) return rc;
       PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[slot ^ 1], g_pipe.h2d));
     }
-    PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.h2d_done[slot], 0));
-    if (an && c.s1 > c.s0)  // the chunk's shows: status, launched, primaryIssue and delaySec are resident for the rows
-      PIE_CUDA(pie::launch_show_stats(c.dev, d_si + c.s0, d_sf + c.s0, Sc, g_sm_count, g_pipe.cmp));
-    // pass 1: sizes only (row offsets + total), so the output can be placed and sized exactly
-    PIE_CUDA(launch_rows(format, c.dev, c.d_offsets, nullptr, 0, bias, c.d_total, c.scratch, g_pipe.cmp));
-    PIE_CUDA(cudaMemcpyAsync(g_pipe.h_total, c.d_total, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
     PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
     const unsigned long long total = *g_pipe.h_total;
     d2h += 8;
