@@ -88,8 +88,9 @@ struct CsvScratch {
   unsigned int* tile_counter;      // [1] dynamic tile ids; zeroed before launch
   unsigned int* slow_tiles;        // [1] tiles that took the slow path (diagnostics); zeroed before launch
   unsigned int* tile_rows;         // [1] rows per tile of this launch (plan_tile_rows), 32 .. kRows
-  unsigned int* col_dirty;         // [24] column c holds at least one byte to escape somewhere; zeroed before launch
-  unsigned int* col_dirty_chunks;  // [24] how many of its 16-byte chunks do (for plan_tile_rows); zeroed before launch
+  unsigned int* col_dirty;         // [24] the sample of column c met a byte to escape (plan_tile_rows only); zeroed before launch
+  unsigned int* col_dirty_chunks;  // [24] how many of its sampled 16-byte chunks did; zeroed before launch
+  unsigned int* col_sampled_chunks;  // [24] how many chunks were sampled; zeroed before launch
   int32_t* entry_show;             // [n_entries]
 };
 
@@ -117,6 +118,7 @@ static CsvScratch carve_csv(void* scratch, int64_t n_entries) {
   s.tile_rows = (unsigned int*)(p + 32);
   s.col_dirty = (unsigned int*)(p + 64);
   s.col_dirty_chunks = (unsigned int*)(p + 160);
+  s.col_sampled_chunks = (unsigned int*)(p + 768);  // behind the developer counters (bytes 256 .. 767)
   p += kCtlBytes;
   s.entry_show = (int32_t*)p;
   return s;
@@ -374,6 +376,7 @@ static_assert(kCols == 24, "the row formats above are laid out for 24 cells");
 __global__ void plan_tile_rows_kernel(const __grid_constant__ RowTable tab, int64_t n_shows, int64_t n_entries,
                                       int stage_bytes, int out_bytes, const unsigned int* __restrict__ col_dirty,
                                       const unsigned int* __restrict__ col_dirty_chunks,
+                                      const unsigned int* __restrict__ col_sampled_chunks,
                                       unsigned int* __restrict__ tile_rows) {
   // one warp, lane c = column c (the end offsets of the columns are read in parallel), sums by shuffles
   const int c = threadIdx.x;
@@ -395,14 +398,15 @@ __global__ void plan_tile_rows_kernel(const __grid_constant__ RowTable tab, int6
       }
       const double bytes = (double)(d.offsets[last] - d.offsets[first]);
       // A cell that holds a byte to escape, and a list cell of several items, is written out a second time (a
-      // little longer) in the bump area.  List columns: all of them.  Other columns: the share of their 16-byte
-      // chunks that hold such a byte, times 3 (a cell is a few chunks) — generous, because falling off the fast
-      // path costs far more than a smaller tile.
+      // little longer) in the bump area.  List columns: all of them.  Other columns: the share of their (sampled)
+      // 16-byte chunks that hold such a byte, times 3 (a cell is a few chunks) — generous, because falling off the
+      // fast path costs far more than a smaller tile; a column whose sample was clean still gets 2 %.
       double copy_share = 0;
       if (d.kind == kCellJoined) copy_share = 1;
-      else if (d.kind == kCellString && col_dirty[c]) {
-        const double chunks = bytes / 16.0;
-        copy_share = chunks < 64 ? 1.0 : fmin(1.0, 3.0 * (double)col_dirty_chunks[c] / chunks + 0.02);
+      else if (d.kind == kCellString) {
+        const double sampled = (double)col_sampled_chunks[c];
+        copy_share = 0.02;
+        if (col_dirty[c]) copy_share = sampled < 64 ? 1.0 : fmin(1.0, 3.0 * (double)col_dirty_chunks[c] / sampled + 0.02);
       }
       if (d.per_entry) {
         entry_bytes = bytes;
@@ -438,14 +442,17 @@ __global__ void plan_tile_rows_kernel(const __grid_constant__ RowTable tab, int6
   *tile_rows = (unsigned int)r;
 }
 
-// ---- pre-pass: which columns can need quoting at all? -----------------------------------------------
-// Most columns of an archive (ids, dates, enumerations, names) never contain a byte that needs escaping.  One
-// streaming pass over every column's byte heap (a 128-bit load per thread and step) sets a
-// per-column flag; the row kernel then skips the per-cell scan for clean columns altogether.
+// ---- how much of a column needs escaping?  (an estimate, for the tile plan only) ---------------------------------
+// The row kernel decides per cell from a bitmask of the staged bytes (build_special_mask below), so nothing has to
+// be known about a column beforehand; only plan_tile_rows wants to know roughly which share of a column's cells will
+// be written out a second time (escaped) in the bump area.  A sample is enough for that: up to kSampleChunks evenly
+// spaced 16-byte chunks of every column heap (~1.5 MB read in all, instead of a sweep over every byte).
+constexpr int kSampleChunks = 4096;
 template <bool kJson>
-__global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant__ RowTable tab, int64_t n_shows,
-                                                           int64_t n_entries, unsigned int* __restrict__ col_dirty,
-                                                           unsigned int* __restrict__ col_dirty_chunks) {
+__global__ void __launch_bounds__(256) column_sample_kernel(const __grid_constant__ RowTable tab, int64_t n_shows,
+                                                            int64_t n_entries, unsigned int* __restrict__ col_dirty,
+                                                            unsigned int* __restrict__ col_dirty_chunks,
+                                                            unsigned int* __restrict__ col_sampled_chunks) {
   const int col = blockIdx.y;
   const CellDesc& d = tab.cell[col];
   if (d.kind != kCellString && d.kind != kCellJoined) return;
@@ -459,29 +466,25 @@ __global__ void __launch_bounds__(256) column_dirty_kernel(const __grid_constant
   if (b1 <= b0) return;
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(d.data + b0), a1 = reinterpret_cast<uintptr_t>(d.data + b1);
   const uintptr_t w0 = (a0 + 15) & ~static_cast<uintptr_t>(15), w1 = a1 & ~static_cast<uintptr_t>(15);
-  uint32_t flags = 0, dirty_chunks = 0;
-  if (w1 > w0) {  // full 16-byte chunks inside the heap
-    const int64_t chunks = static_cast<int64_t>((w1 - w0) >> 4);
-    const uint4* __restrict__ p = reinterpret_cast<const uint4*>(w0);
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += (int64_t)gridDim.x * blockDim.x) {
-      const uint4 x = __ldg(p + c);
-      const uint32_t f = special_flags<kJson>(x.x) | special_flags<kJson>(x.y) | special_flags<kJson>(x.z) | special_flags<kJson>(x.w);
-      flags |= f;
-      dirty_chunks += (f != 0);
-    }
+  if (w1 <= w0) {  // a heap shorter than a chunk: "dirty" is the safe answer
+    if (blockIdx.x == 0 && threadIdx.x == 0) { col_dirty[col] = 1; col_dirty_chunks[col] = 1; col_sampled_chunks[col] = 1; }
+    return;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 32) {  // the < 16 bytes at either end (or a heap shorter than a chunk)
-    const uintptr_t head_end = (w1 > w0) ? w0 : a1, tail_begin = (w1 > w0) ? w1 : a1;
-    for (uintptr_t a = a0 + threadIdx.x; a < head_end; a += 32) flags |= is_special_byte<kJson>(*reinterpret_cast<const uint8_t*>(a));
-    for (uintptr_t a = tail_begin + threadIdx.x; a < a1; a += 32) flags |= is_special_byte<kJson>(*reinterpret_cast<const uint8_t*>(a));
+  const int64_t chunks = static_cast<int64_t>((w1 - w0) >> 4);
+  const int64_t samples = chunks < kSampleChunks ? chunks : kSampleChunks;
+  const uint4* __restrict__ p = reinterpret_cast<const uint4*>(w0);
+  uint32_t dirty_chunks = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < samples; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 x = __ldg(p + (i * chunks) / samples);
+    const uint32_t f = special_flags<kJson>(x.x) | special_flags<kJson>(x.y) | special_flags<kJson>(x.z) | special_flags<kJson>(x.w);
+    dirty_chunks += (f != 0);
   }
-  if (__any_sync(0xFFFFFFFFu, flags != 0)) {  // rare
-    dirty_chunks = __reduce_add_sync(0xFFFFFFFFu, dirty_chunks);
-    if ((threadIdx.x & 31) == 0) {
-      atomicOr(&col_dirty[col], 1u);
-      if (dirty_chunks) atomicAdd(&col_dirty_chunks[col], dirty_chunks);
-    }
+  dirty_chunks = __reduce_add_sync(0xFFFFFFFFu, dirty_chunks);
+  if ((threadIdx.x & 31) == 0 && dirty_chunks) {
+    atomicOr(&col_dirty[col], 1u);
+    atomicAdd(&col_dirty_chunks[col], dirty_chunks);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) col_sampled_chunks[col] = (unsigned int)samples;
 }
 
 // ---- PTX: mbarrier, 1-D TMA bulk copy, named barriers ----------------------------------------------
@@ -579,6 +582,7 @@ struct StageInfo {
   uint32_t n_tile_shows;
   uint32_t slow;              // the tile does not fit the stage: slow path
   uint32_t bump0;             // first free byte behind the staged ranges
+  uint32_t heap_end;          // the staged column bytes are [kLiteralBytes, heap_end): what build_special_mask scans
   uint32_t delta[kCols];      // staged address of heap byte b of column c = delta[c] + b
   uint32_t off_base[kCols];   // staged address of the column's first offset word (offsets[e0] / offsets[show0] /
                               // list_offsets[...] for the two list columns)
@@ -603,13 +607,13 @@ struct CsvSmem {
   StageInfo info[2];
   uint32_t cell[kRows * kCellStride];           // (src:16 | len:16 << 16) of cell (r, c) at r*kCellStride + c
   uint32_t shcell[kMaxShowSlots][kMaxTileShows];  // the same for the show-level cells of the tile's shows
+  uint32_t special[kStageBytes / 32 + 4];       // bit b: staged byte b of the current tile needs escaping (build_special_mask)
   uint32_t qmask[kRows];                        // slow path: per-row quote masks
   FillItem word_items[kMaxFillItems];           // cells to materialise through the word-wise stream ...
   FillItem quote_items[kMaxFillItems];          // ... and byte by byte ('"' to double)
   uint32_t n_word_items, n_quote_items;
   uint32_t group[kGroups][kRows];               // bytes of a row's group
   uint32_t row_start[2][kRows];                 // byte offset of the row inside the tile, by tile parity
-  uint32_t col_dirty[kCols];
   uint32_t warp_sum[kRows / 32];
   uint32_t tile_total[2];                       // by tile parity (the flush of a tile is deferred by one tile)
   long long cur_tile[2];                        // workers -> look-back warp
@@ -746,12 +750,58 @@ struct ByteStream {
 // staged).
 // CSV: a special cell is wrapped in '"' and its '"' are doubled.  JSON: the specials are escaped in place
 // (the enclosing quotes belong to the row format).  `extra` = bytes the escaping adds inside the cell.
+// Exact per-byte flags (0x80 in every byte of x that needs escaping), for the bitmask below — the *_flags tests
+// above are exact only as "any byte of the word".
+__device__ __forceinline__ uint32_t control_bytes_exact(uint32_t x) {  // bytes below 0x20
+  return ~(((x & 0x7F7F7F7Fu) + 0x60606060u) | x) & 0x80808080u;
+}
+template <bool kJson>
+__device__ __forceinline__ uint32_t special_bytes_exact(uint32_t x) {
+  if (kJson) return zero_bytes_exact(x ^ 0x22222222u) | zero_bytes_exact(x ^ 0x5C5C5C5Cu) | control_bytes_exact(x);
+  return zero_bytes_exact(x ^ 0x22222222u) | zero_bytes_exact(x ^ 0x2C2C2C2Cu) | zero_bytes_exact(x ^ 0x0A0A0A0Au) |
+         zero_bytes_exact(x ^ 0x0D0D0D0Du);
+}
+// the four 0x80 flags of a word as a nibble (bit j = byte j)
+__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t f) { return ((f >> 7) * 0x01020408u) >> 24 & 0xFu; }
+
+// One bit per staged byte of the tile: does it need escaping?  Built by the workers when a stage has landed (a
+// 16-byte chunk per thread and step, ~35 KB per tile), it answers "does this cell need csvEscape / JSON escapes" for
+// EVERY cell of EVERY column with two loads and a shift.  No column is known
+// to be clean beforehand, and no pre-pass over the archive is needed to find out (the round-1 kernel swept every
+// column heap once per launch: 1.5 GB of extra reads per step).
+template <bool kJson>
+__device__ __forceinline__ void build_special_mask(uint32_t* __restrict__ mask, const uint8_t* __restrict__ stage,
+                                                   uint32_t heap_end, int tid) {
+  const uint32_t first = (uint32_t)kLiteralBytes >> 4, last = (heap_end + 15u) >> 4;  // 16-byte chunks
+  uint16_t* m16 = reinterpret_cast<uint16_t*>(mask);
+  const uint4* chunk = reinterpret_cast<const uint4*>(stage);
+  for (uint32_t i = first + (uint32_t)tid; i < last; i += kWorkers) {
+    const uint4 x = chunk[i];
+    const uint32_t bits = flags_to_nibble(special_bytes_exact<kJson>(x.x)) | flags_to_nibble(special_bytes_exact<kJson>(x.y)) << 4 |
+                          flags_to_nibble(special_bytes_exact<kJson>(x.z)) << 8 | flags_to_nibble(special_bytes_exact<kJson>(x.w)) << 12;
+    m16[i] = (uint16_t)bits;
+  }
+}
+// any bit of mask[src .. src+n) set?  (n >= 1)
+__device__ __forceinline__ bool mask_any(const uint32_t* __restrict__ mask, uint32_t src, uint32_t n) {
+  uint32_t w = src >> 5;
+  const uint32_t sh = src & 31u, avail = 32u - sh;
+  const uint32_t head = mask[w] >> sh;
+  if (n <= avail) return (head & (0xFFFFFFFFu >> (32u - n))) != 0;
+  uint32_t acc = head;
+  n -= avail;
+  for (++w; n >= 32u; n -= 32u, ++w) acc |= mask[w];
+  if (n) acc |= mask[w] & (0xFFFFFFFFu >> (32u - n));
+  return acc != 0;
+}
+
 template <bool kJson>
 __device__ __forceinline__ uint32_t plan_cell(CsvSmem& sm, uint8_t* stage, const int32_t* item_offsets, uint32_t delta,
-                                              bool dirty, uint32_t src, uint32_t n, int items) {
+                                              uint32_t src, uint32_t n, int items) {
   uint32_t extra = 0;
-  const bool special = dirty && n > 0 && smem_scan_special<kJson>(stage, src, n, extra);
+  const bool special = n > 0 && mask_any(sm.special, src, n);
   if (!special && items <= 1) return pack_cell(src, n);
+  if (special) smem_scan_special<kJson>(stage, src, n, extra);  // how many bytes escaping adds (the rare path)
   const uint32_t out_len = n + (items > 1 ? (uint32_t)(items - 1) : 0u) + extra + ((special && !kJson) ? 2u : 0u);
   const uint32_t alloc = (out_len + 3u) & ~3u;      // the word-wise stream may fill its last word
   const uint32_t p = atomicAdd(&sm.bump, alloc);    // stays 4-byte aligned
@@ -1085,6 +1135,7 @@ __device__ __forceinline__ void produce_tile(const pie_archive_view& v, const Ro
     info.n_tile_shows = (uint32_t)(s1 - s0 + 1);
     info.slow = fits ? 0u : 1u;
     info.bump0 = (used + 3u) & ~3u;
+    info.heap_end = (uint32_t)kLiteralBytes + tb;
     if (fits) mbar_expect_tx(bar, bulk_total);
   }
   __syncwarp();
@@ -1180,7 +1231,6 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     mbar_fence_init();
     sm.done = 0;
   }
-  if (tid < kCols) sm.col_dirty[tid] = sc.col_dirty[tid];
   // the row format's literal text goes to the head of both stages; the cells that are always the same
   // literal are entered in the cell table once
   for (int i = tid; i < 2 * kLiteralBytes; i += kCtaThreads)
@@ -1373,6 +1423,11 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
     bool published = false;
     bool items_signalled = false;
 
+    uint32_t cells[kGroupCols];  // the six cells this thread writes, (src:16 | len:16 << 16)
+#pragma unroll
+    for (int k = 0; k < kGroupCols; ++k) cells[k] = 0;
+    uint32_t my_start = 0;   // where this thread's group starts in the tile image
+    uint32_t tile_total = 0;
     if (!slow) {
       if (tid == 0) {
         sm.bump = info.bump0;
@@ -1381,7 +1436,9 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
         sm.n_quote_items = 0;
         sm.fill_skip = 0;
       }
-      workers_sync();  // also: every worker has left the previous tile's write phase (cell table)
+      // which staged bytes need escaping: one bit each, for every column (see build_special_mask)
+      build_special_mask<kJson>(sm.special, stage, info.heap_end, tid);
+      workers_sync();  // the mask is complete; also: every worker has left the previous tile's write phase (cell table)
       PIE_PHASE(1);
       // ---- cells 1. show-level cells once per show of the tile; entry-level cells: thread (r, g) takes
       // the value cells tab.owned[g] (the expensive ones — Array.join, free text — on different groups)
@@ -1406,10 +1463,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
             }
           }
           const uint32_t src = (info.delta[col] + b) & 0xFFFFu;
-          uint32_t c = pack_cell(src, n);
-          if ((sm.col_dirty[col] && n) || items > 1)
-            c = plan_cell<kJson>(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
-          sm.shcell[slot][i] = c;
+          sm.shcell[slot][i] = plan_cell<kJson>(sm, stage, io, info.delta[col], src, n, items);
         }
       }
       PIE_PHASE(2);  // show-level cells
@@ -1460,9 +1514,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
             if (d.kind == kCellYesNo) {  // toYesNoBoolean picks one of two literals
               c = is_yes(stage + src, (int)n) ? pack_cell(d.lit, d.lit_len) : pack_cell(d.lit_no, d.lit_no_len);
             } else if (!(d.blank_if_completed && completed)) {
-              c = pack_cell(src, n);
-              if ((sm.col_dirty[col] && n) || items > 1)
-                c = plan_cell<kJson>(sm, stage, io, info.delta[col], sm.col_dirty[col] != 0, src, n, items);
+              c = plan_cell<kJson>(sm, stage, io, info.delta[col], src, n, items);
             }
           }
           row_cells[col] = c;
@@ -1477,29 +1529,59 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       PIE_PHASE(9);
       slow = sm.overflow != 0;  // the bump area or a fill queue ran out (uniform: written before the barrier)
       if (!slow) {
-        // ---- lengths: a row thread picks up its show's cells, adds up the row and its four groups
-        uint32_t row_len = 0;
-        if (row_thread && rt < rows) {
-          uint32_t* row_cells = sm.cell + rt * kCellStride;
-          const int show_i = stage_i32(stage, info.show_idx_base)[rt] - info.show0;
+        // ---- lengths.  Thread (r, g) collects the six cells it is going to write — its show's cells from the
+        // per-tile table, the entry's from the cell table — in registers, and publishes the bytes of its group; then
+        // every thread adds up its row, and every warp (32 consecutive rows of one group) scans its rows itself.
+        uint32_t glen = 0;
+        if (have) {
+          const int show_i = stage_i32(stage, info.show_idx_base)[r] - info.show0;
+          const uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
 #pragma unroll
-          for (int col = 0; col < kCols; ++col) {
-            if (col % kGroupCols == 0) sm.group[col / kGroupCols][rt] = row_len;  // where the group starts in the row
-            uint32_t c;
-            const int slot = tab.cell[col].show_slot;
-            if (slot >= 0) {
-              c = sm.shcell[slot][show_i];
-              row_cells[col] = c;
-            } else {
-              c = row_cells[col];
-            }
-            row_len += (c >> 16) + 1u;  // + the cell's separator byte
+          for (int k = 0; k < kGroupCols; ++k) {
+            const int slot = tab.cell[g * kGroupCols + k].show_slot;
+            cells[k] = slot >= 0 ? sm.shcell[slot][show_i] : row_cells[k];
+            glen += (cells[k] >> 16) + 1u;  // + the cell's separator byte
           }
         }
-        scan_rows_and_publish(tile, row_len, par);
+        sm.group[g][r] = glen;
+        workers_sync();
+        uint32_t row_len = 0;
+#pragma unroll
+        for (int gg = 0; gg < kGroups; ++gg) {
+          const uint32_t x = sm.group[gg][r];
+          row_len += x;
+          if (gg < g) my_start += x;
+        }
+        uint32_t incl = row_len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int blk = r >> 5;  // a warp = 32 consecutive rows of one group (kRows is a multiple of 32)
+        if (g == 0 && lane == 31) sm.warp_sum[blk] = incl;
+        workers_sync();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kRows / 32; ++w) {
+          const uint32_t x = sm.warp_sum[w];
+          total += x;
+          if (w < blk) before += x;
+        }
+        const uint32_t row_start = before + incl - row_len;
+        my_start += row_start;
+        if (g == 0) sm.row_start[par][r] = row_start;  // for the row offsets (flush) — and the slow path
+        if (tid == 0) {
+          sm.tile_total[par] = total;
+          sm.cur_tile[par] = tile;
+          // (status, value) travel in one 64-bit word and nothing else is read through it: no fence needed
+          reinterpret_cast<volatile unsigned long long*>(sc.tile_state)[tile] =
+              (tile == 0 ? kPrefix : kAggregate) | (unsigned long long)total;
+        }
+        tile_total = total;
         PIE_PHASE(5);  // cells 2 + scans
         published = true;
-        if (write && sm.tile_total[par] > (uint32_t)kOutBytes) slow = true;  // uniform
+        if (write && total > (uint32_t)kOutBytes) slow = true;  // uniform
       }
     }
 
@@ -1518,7 +1600,7 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       slow_measure<kJson>(v, tab, sc, sm, s_num, qmask, s, e0, rows);
       workers_sync();
       if (!published) scan_rows_and_publish(tile, (row_thread && rt < rows) ? sm.group[0][rt] : 0u, par);
-      const uint32_t tile_total = sm.tile_total[par];
+      tile_total = sm.tile_total[par];
       bar_arrive_workers_and_lookback<kBarTotalReady>();
       if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));  // nothing of the stage's staged ranges is read any more
       bar_sync_workers_and_lookback<kBarBaseReady>();
@@ -1530,7 +1612,6 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       continue;
     }
 
-    const uint32_t tile_total = sm.tile_total[par];
     bar_arrive_workers_and_lookback<kBarTotalReady>();  // this tile's look-back starts now ...
     finish_pending();                                   // ... while the previous tile leaves s_out
     PIE_PHASE(6);  // wait for the previous tile's offset + its flush
@@ -1545,13 +1626,8 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       workers_sync();  // the previous tile has left s_out
       PIE_PHASE(8);    // ... waiting for that
       if (have) {
-        const uint32_t o = sm.row_start[par][r] + (g ? sm.group[g][r] : 0u);
-        const uint32_t* row_cells = sm.cell + r * kCellStride + g * kGroupCols;
-        uint32_t cells[kGroupCols];
-#pragma unroll
-        for (int k = 0; k < kGroupCols; ++k) cells[k] = row_cells[k];
         ByteStream<true> out;
-        out.init(s_out + o);
+        out.init(s_out + my_start);
 #pragma unroll
         for (int k = 0; k < kGroupCols; ++k) {
           out.append(stage, cells[k] & 0xFFFFu, cells[k] >> 16, tab.cell[g * kGroupCols + k].sep, 1u);
@@ -1600,15 +1676,11 @@ static cudaError_t launch_rows(const pie_archive_view& v, const RowTable& tab, i
     configured_device = dev;
   }
   expand_entry_show_kernel<<<(unsigned)((v.n_shows + 255) / 256), 256, 0, stream>>>(v, sc.entry_show);
-  {
-    int64_t blocks = (v.n_entries * 3 + 255) / 256;  // ~ a 16-byte chunk per thread for the widest heaps
-    if (blocks > sm_count_or_default() * 8) blocks = sm_count_or_default() * 8;
-    if (blocks < 1) blocks = 1;
-    column_dirty_kernel<kJson><<<dim3((unsigned)blocks, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries,
-                                                                                 sc.col_dirty, sc.col_dirty_chunks);
-  }
+  // the tile plan wants a rough idea of how many cells will be escaped: a sample of every column, not a sweep
+  column_sample_kernel<kJson><<<dim3(kSampleChunks / 256, kCols), 256, 0, stream>>>(tab, v.n_shows, v.n_entries, sc.col_dirty,
+                                                                                 sc.col_dirty_chunks, sc.col_sampled_chunks);
   plan_tile_rows_kernel<<<1, 32, 0, stream>>>(tab, v.n_shows, v.n_entries, kStageBytes, kOutBytes, sc.col_dirty,
-                                              sc.col_dirty_chunks, sc.tile_rows);
+                                              sc.col_dirty_chunks, sc.col_sampled_chunks, sc.tile_rows);
   const int64_t tiles = csv_tiles(v.n_entries);
   const unsigned grid = (unsigned)(tiles < resident_ctas ? tiles : resident_ctas);
   export_rows_kernel<kJson><<<grid, kCtaThreads, kSmemBytes, stream>>>(v, tab, sc, row_offsets, out_data, capacity, bias,

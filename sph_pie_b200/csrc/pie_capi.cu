@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -75,11 +76,33 @@ struct StrColPlan {
   pie_strcol* dst;
   int64_t n;
   int32_t first, last;
+  const char* name;
 };
+
+// The offsets arrays uploaded since the last begin_checks(): validated on the device (validate.cu) before any kernel
+// walks them.  Filled by the upload helpers, under g_host_mutex.
+struct PendingChecks {
+  pie::OffsetsBatch batch;
+  const char* names[pie::kMaxOffsetsArrays];
+  void clear() { batch.count = 0; }
+  void add(const int32_t* dev_off, int64_t n, int32_t first, int32_t last, const char* name) {
+    if (n <= 0 || batch.count >= pie::kMaxOffsetsArrays) return;  // (a batch has at most 27 arrays)
+    names[batch.count] = name;
+    batch.a[batch.count++] = pie::OffsetsArray{dev_off, n, first, last};
+  }
+};
+PendingChecks g_checks;
+int32_t* g_check_flags = nullptr;  // device, [3][kMaxOffsetsArrays]: one set for the arena path, one per pipeline slot
+
+int ensure_check_flags();
+// enqueue the check of everything uploaded since clear(), flags -> `host_flags` (any host memory) on `st`
+int enqueue_checks(const PendingChecks& c, int set, int32_t* host_flags, cudaStream_t st);
+// after `st` was synchronised: PIE_ERR_INVALID_ARG naming the first malformed array
+int report_checks(const PendingChecks& c, const int32_t* host_flags);
 
 // bytes needed on the device for a string column of n rows
 int plan_strcol(StrColPlan& p, const pie_strcol* src, pie_strcol* dst, int64_t n, uint64_t* bytes, const char* name) {
-  p.src = src; p.dst = dst; p.n = n;
+  p.src = src; p.dst = dst; p.n = n; p.name = name;
   if (!src->offsets) return fail(PIE_ERR_INVALID_ARG, "column %s: offsets is NULL", name);
   p.first = src->offsets[0];
   p.last = src->offsets[n];
@@ -103,36 +126,33 @@ int64_t first_decrease(const int32_t* off, int64_t n) {
   return -1;
 }
 
-struct OffsetsCheck {
-  const int32_t* off;
-  int64_t n;
-  const char* name;
-};
-// Checks every offsets array of a batch on a few host threads (the pass is ~4 bytes per row and column; it runs
-// while the previous chunk is on the device).
-int check_offsets(const std::vector<OffsetsCheck>& arrays) {
-  int64_t rows = 0;
-  for (const OffsetsCheck& a : arrays) rows += a.n;
-  std::vector<int64_t> bad(arrays.size(), -1);
-  auto run = [&](size_t lo, size_t hi) {
-    for (size_t i = lo; i < hi; ++i)
-      if (arrays[i].off && arrays[i].n > 0) bad[i] = first_decrease(arrays[i].off, arrays[i].n);
-  };
-  const size_t nt = rows > (int64_t)1 << 20 ? 8 : 1;
-  if (nt == 1) {
-    run(0, arrays.size());
-  } else {
-    std::vector<std::thread> pool;
-    const size_t per = (arrays.size() + nt - 1) / nt;
-    for (size_t t = 0; t < nt; ++t) {
-      const size_t lo = t * per, hi = lo + per < arrays.size() ? lo + per : arrays.size();
-      if (lo < hi) pool.emplace_back(run, lo, hi);
-    }
-    for (std::thread& th : pool) th.join();
-  }
-  for (size_t i = 0; i < arrays.size(); ++i)
-    if (bad[i] >= 0)
-      return fail(PIE_ERR_INVALID_ARG, "column %s: offsets decrease at row %lld", arrays[i].name, (long long)bad[i]);
+// entry_offsets is walked by the host itself (chunking, slicing): checked here, on the host (4 bytes per show)
+int check_entry_offsets(const int32_t* off, int64_t n) {
+  const int64_t bad = (off && n > 0) ? first_decrease(off, n) : -1;
+  if (bad >= 0) return fail(PIE_ERR_INVALID_ARG, "column entry_offsets: offsets decrease at row %lld", (long long)bad);
+  return PIE_OK;
+}
+
+int ensure_check_flags() {
+  if (g_check_flags) return PIE_OK;
+  PIE_CUDA(cudaMalloc(&g_check_flags, sizeof(int32_t) * 3 * pie::kMaxOffsetsArrays));
+  return PIE_OK;
+}
+int enqueue_checks(const PendingChecks& c, int set, int32_t* host_flags, cudaStream_t st) {
+  static const bool skip = getenv("PIE_DEBUG_SKIP_OFFSET_CHECK") != nullptr;  // timing experiments only
+  memset(host_flags, 0, sizeof(int32_t) * pie::kMaxOffsetsArrays);
+  if (skip || c.batch.count == 0) return PIE_OK;
+  int rc = ensure_check_flags();
+  if (rc) return rc;
+  int32_t* d = g_check_flags + set * pie::kMaxOffsetsArrays;
+  PIE_CUDA(pie::launch_offsets_check(c.batch, d, st));
+  PIE_CUDA(cudaMemcpyAsync(host_flags, d, sizeof(int32_t) * pie::kMaxOffsetsArrays, cudaMemcpyDeviceToHost, st));
+  return PIE_OK;
+}
+int report_checks(const PendingChecks& c, const int32_t* host_flags) {
+  for (int i = 0; i < c.batch.count; ++i)
+    if (host_flags[i])
+      return fail(PIE_ERR_INVALID_ARG, "column %s: offsets decrease or leave the column's heap", c.names[i]);
   return PIE_OK;
 }
 
@@ -145,6 +165,7 @@ int upload_strcol(const StrColPlan& p, uint64_t* h2d) {
     PIE_CUDA(cudaMemcpyAsync(d_data, p.src->data + p.first, nbytes, cudaMemcpyHostToDevice, g_cur_stream));
   p.dst->offsets = d_off;
   p.dst->data = d_data - p.first;  // offsets keep their host values
+  g_checks.add(d_off, p.n, p.first, p.last, p.name);
   *h2d += 4 * (uint64_t)(p.n + 1) + nbytes;
   return PIE_OK;
 }
@@ -263,17 +284,7 @@ int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_
   }
   if (csv && E > 0 && (!hv->delay_sec || !hv->delay_valid))
     return fail(PIE_ERR_INVALID_ARG, "delay_sec/delay_valid is NULL");
-  {
-    std::vector<OffsetsCheck> checks;
-    checks.push_back({hv->entry_offsets, S, "entry_offsets"});
-    for (int i = 0; i < kCols; ++i)
-      if (format_reads(format, i)) checks.push_back({cols[i].src->offsets, cols[i].n, cols[i].name});
-    for (int i = 0; csv && i < 2; ++i) {
-      checks.push_back({lists[i].src->list_offsets, lists[i].n, lists[i].name});
-      checks.push_back({item_src[i].offsets, item_plans[i].n, lists[i].name});
-    }
-    if ((rc = check_offsets(checks))) return rc;
-  }
+  if ((rc = check_entry_offsets(hv->entry_offsets, S))) return rc;
   if ((rc = g_cur->reserve(bytes))) return rc;
   if (!g_cur_stream) g_cur_stream = g_cur->stream;
   dv->n_shows = S;
@@ -284,6 +295,7 @@ int upload_export_view(const pie_archive_view* hv, pie_archive_view* dv, uint64_
   if (!csv) return PIE_OK;
   for (int i = 0; i < 2; ++i) {
     if ((rc = upload_array(lists[i].src->list_offsets, lists[i].n + 1, &lists[i].dst->list_offsets, h2d))) return rc;
+    g_checks.add(lists[i].dst->list_offsets, lists[i].n, item_first[i], item_first[i] + (int32_t)item_plans[i].n, lists[i].name);
     if ((rc = upload_strcol(item_plans[i], h2d))) return rc;
     lists[i].dst->items.offsets -= item_first[i];  // list offsets keep their host (absolute) values
   }
@@ -489,13 +501,7 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   const bool has_time = has_date && hv->show_time.offsets;
   if (has_date && (rc = plan_strcol(p_date, &hv->show_date, nullptr, S, &bytes, "show_date"))) return rc;
   if (has_time && (rc = plan_strcol(p_time, &hv->show_time, nullptr, S, &bytes, "show_time"))) return rc;
-  {
-    std::vector<OffsetsCheck> checks = {{hv->entry_offsets, S, "entry_offsets"}, {hv->status.offsets, E, "status"},
-                                        {hv->launched.offsets, E, "launched"}, {hv->primary_issue.offsets, E, "primary_issue"}};
-    if (has_date) checks.push_back({hv->show_date.offsets, S, "show_date"});
-    if (has_time) checks.push_back({hv->show_time.offsets, S, "show_time"});
-    if ((rc = check_offsets(checks))) return rc;
-  }
+  if ((rc = check_entry_offsets(hv->entry_offsets, S))) return rc;
   const int64_t Sc = S > 0 ? S : 1;
   bytes += pad(4 * (uint64_t)(S + 1)) + pad(8 * (uint64_t)E) + pad((uint64_t)E);          // offsets, delay, valid
   bytes += pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc);                  // stats planes
@@ -515,6 +521,7 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
   memset(&dv, 0, sizeof(dv));
   dv.n_shows = S;
   dv.n_entries = E;
+  g_checks.clear();
   if ((rc = upload_array(hv->entry_offsets, S + 1, &dv.entry_offsets, &h2d))) return rc;
   p_status.dst = &dv.status; p_launched.dst = &dv.launched; p_issue.dst = &dv.primary_issue;
   if ((rc = upload_strcol(p_status, &h2d))) return rc;
@@ -529,6 +536,12 @@ static int analytics_host_locked(const pie_archive_view* hv, int32_t tz_offset_m
     if (has_date) { p_date.dst = &dv.show_date; if ((rc = upload_strcol(p_date, &h2d))) return rc; }
     if (has_time) { p_time.dst = &dv.show_time; if ((rc = upload_strcol(p_time, &h2d))) return rc; }
   }
+
+  // ---- the uploaded offsets, checked on the device before any kernel walks them
+  int32_t check_flags[pie::kMaxOffsetsArrays];
+  if ((rc = enqueue_checks(g_checks, 0, check_flags, st))) return rc;
+  PIE_CUDA(cudaStreamSynchronize(st));
+  if ((rc = report_checks(g_checks, check_flags))) return rc;
 
   // ---- kernels
   int32_t* d_si = (int32_t*)g_arena.take(4ull * PIE_SI_COUNT * Sc);
@@ -609,9 +622,7 @@ int pie_compute_metrics_host(const pie_archive_view* hv, int32_t* metrics_i32, u
   if ((rc = plan_strcol(p_planned, &hv->planned, nullptr, E, &bytes, "planned"))) return rc;
   if ((rc = plan_strcol(p_status, &hv->status, nullptr, E, &bytes, "status"))) return rc;
   if ((rc = plan_strcol(p_issue, &hv->primary_issue, nullptr, E, &bytes, "primary_issue"))) return rc;
-  if ((rc = check_offsets({{hv->entry_offsets, S, "entry_offsets"}, {hv->planned.offsets, E, "planned"},
-                           {hv->status.offsets, E, "status"}, {hv->primary_issue.offsets, E, "primary_issue"}})))
-    return rc;
+  if ((rc = check_entry_offsets(hv->entry_offsets, S))) return rc;
   const int64_t Sc = S > 0 ? S : 1;
   bytes += pad(4 * (uint64_t)(S + 1)) + pad(8 * (uint64_t)E) + pad((uint64_t)E);
   bytes += pad(4ull * PIE_CM_COUNT * Sc) + pad((uint64_t)PIE_CM_TEXT * Sc);
@@ -625,6 +636,7 @@ int pie_compute_metrics_host(const pie_archive_view* hv, int32_t* metrics_i32, u
   memset(&dv, 0, sizeof(dv));
   dv.n_shows = S;
   dv.n_entries = E;
+  g_checks.clear();
   if ((rc = upload_array(hv->entry_offsets, S + 1, &dv.entry_offsets, &h2d))) return rc;
   p_planned.dst = &dv.planned; p_status.dst = &dv.status; p_issue.dst = &dv.primary_issue;
   if ((rc = upload_strcol(p_planned, &h2d))) return rc;
@@ -632,6 +644,10 @@ int pie_compute_metrics_host(const pie_archive_view* hv, int32_t* metrics_i32, u
   if ((rc = upload_strcol(p_issue, &h2d))) return rc;
   if ((rc = upload_array(hv->delay_sec, E, &dv.delay_sec, &h2d))) return rc;
   if ((rc = upload_array(hv->delay_valid, E, &dv.delay_valid, &h2d))) return rc;
+  int32_t check_flags[pie::kMaxOffsetsArrays];
+  if ((rc = enqueue_checks(g_checks, 0, check_flags, st))) return rc;
+  PIE_CUDA(cudaStreamSynchronize(st));
+  if ((rc = report_checks(g_checks, check_flags))) return rc;
   int32_t* d_out = (int32_t*)g_arena.take(4ull * PIE_CM_COUNT * Sc);
   uint8_t* d_text = (uint8_t*)g_arena.take((uint64_t)PIE_CM_TEXT * Sc);
   PIE_CUDA(pie::launch_compute_metrics(dv, d_out, d_text, Sc, st));
@@ -703,7 +719,7 @@ struct CsvPipeline {
       PIE_CUDA(cudaEventCreateWithFlags(&kernel_done[i], cudaEventDisableTiming));
       PIE_CUDA(cudaEventCreateWithFlags(&d2h_done[i], cudaEventDisableTiming));
     }
-    PIE_CUDA(cudaHostAlloc(&h_total, 64, cudaHostAllocDefault));
+    PIE_CUDA(cudaHostAlloc(&h_total, 512, cudaHostAllocDefault));  // [0] a chunk's total; +64: its check flags; +256: the step's
     return PIE_OK;
   }
 };
@@ -717,6 +733,7 @@ struct CsvChunk {
   void* scratch;
   int64_t* d_offsets;
   unsigned long long* d_total;
+  PendingChecks checks;  // the chunk's offsets arrays on the device, to be validated before its kernels run
 };
 
 static void slice_col(pie_strcol* c, int64_t first) { if (c->offsets) c->offsets += first; }
@@ -749,8 +766,10 @@ static int upload_chunk(CsvChunk* c, int slot, uint64_t* h2d, RowFormat format) 
   const int64_t E = c->e1 - c->e0;
   memset(&c->dev, 0, sizeof(c->dev));
   const uint64_t extra = pad(pie::csv_scratch_bytes(E)) + pad(8 * (uint64_t)(E + 1)) + pad(64);
+  g_checks.clear();
   int rc = upload_export_view(&c->host, &c->dev, extra + (extra >> 2), h2d, format);  // +25 %: later chunks rarely regrow
   if (rc) return rc;
+  c->checks = g_checks;
   c->scratch = g_cur->take(pie::csv_scratch_bytes(E));
   c->d_offsets = (int64_t*)g_cur->take(8 * (uint64_t)(E + 1));
   c->d_total = (unsigned long long*)g_cur->take(16);
@@ -784,7 +803,7 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
   const int64_t S = hv->n_shows, E = hv->n_entries;
   if (S > 0 && (hv->entry_offsets[0] != 0 || hv->entry_offsets[S] != E))
     return fail(PIE_ERR_INVALID_ARG, "entry_offsets must run from 0 to n_entries");
-  if ((rc = check_offsets({{hv->entry_offsets, S, "entry_offsets"}}))) return rc;  // the chunking below walks it
+  if ((rc = check_entry_offsets(hv->entry_offsets, S))) return rc;  // the chunking below walks it
   if ((rc = g_pipe.init())) return rc;
   // Whatever way this function is left, nothing it enqueued may still be writing the caller's buffers (or reading
   // an arena the next call resets): drain the three streams and hand the upload helpers back to the default arena.
@@ -806,6 +825,8 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
   pie_archive_view dv_all;
   pie_daily_out dout;
   void* dscratch = nullptr;
+  PendingChecks an_checks;
+  an_checks.clear();
   memset(&dv_all, 0, sizeof(dv_all));
   if (an) {
     if (format != kFormatCsv) return fail(PIE_ERR_INVALID_ARG, "the step rides on the CSV rows");
@@ -822,17 +843,12 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
     const bool has_date = hv->show_date.offsets != nullptr, has_time = has_date && hv->show_time.offsets != nullptr;
     if (has_date && (rc = plan_strcol(p_date, &hv->show_date, nullptr, S, &bytes, "show_date"))) return rc;
     if (has_time && (rc = plan_strcol(p_time, &hv->show_time, nullptr, S, &bytes, "show_time"))) return rc;
-    {
-      std::vector<OffsetsCheck> checks;
-      if (has_date) checks.push_back({hv->show_date.offsets, S, "show_date"});
-      if (has_time) checks.push_back({hv->show_time.offsets, S, "show_time"});
-      if ((rc = check_offsets(checks))) return rc;
-    }
     bytes += pad(4 * (uint64_t)(S + 1)) + 2 * pad(8 * (uint64_t)Sc) + pad(8 * (uint64_t)E);
     bytes += pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc) + daily_out_bytes(S, Sc);
     if ((rc = g_arena.reserve(bytes))) return rc;
     g_cur = &g_arena;
     g_cur_stream = g_pipe.h2d;
+    g_checks.clear();
     dv_all.n_shows = S;
     dv_all.n_entries = E;
     if ((rc = upload_array(hv->entry_offsets, S + 1, &dv_all.entry_offsets, &an_h2d))) return rc;
@@ -844,6 +860,7 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
     d_si = (int32_t*)g_arena.take(4ull * PIE_SI_COUNT * Sc);
     d_sf = (double*)g_arena.take(8ull * PIE_SF_COUNT * Sc);
     dscratch = alloc_daily_out(g_arena, S, Sc, &dout);
+    an_checks = g_checks;
   }
 
   // chunks of ~kCsvChunkRows rows, cut at show boundaries
@@ -876,6 +893,8 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
     CsvChunk& c = chunks[(size_t)k];
     const int64_t Ec = c.e1 - c.e0;
     PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.h2d_done[slot], 0));
+    int32_t* chunk_flags = reinterpret_cast<int32_t*>(g_pipe.h_total + 8);
+    if ((rc = enqueue_checks(c.checks, 1 + slot, chunk_flags, g_pipe.cmp))) return rc;
     if (an && c.s1 > c.s0)  // the chunk's shows: status, launched, primaryIssue and delaySec are resident for the rows
       PIE_CUDA(pie::launch_show_stats(c.dev, d_si + c.s0, d_sf + c.s0, Sc, g_sm_count, g_pipe.cmp));
     // pass 1: sizes only (row offsets + total), so the output can be placed and sized exactly
@@ -891,6 +910,7 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
       PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[slot ^ 1], g_pipe.h2d));
     }
     PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
+    if ((rc = report_checks(c.checks, chunk_flags))) return rc;
     const unsigned long long total = *g_pipe.h_total;
     d2h += 8;
     const bool want_data = out_data != nullptr && !overflow && bias + total <= out_capacity;
@@ -921,6 +941,10 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
   if (an) {
     // the first chunk's upload was enqueued after the per-batch arrays on the same stream, so the compute stream
     // (which waited for that chunk) already sees them
+    int32_t* an_flags = reinterpret_cast<int32_t*>(g_pipe.h_total + 32);
+    if ((rc = enqueue_checks(an_checks, 0, an_flags, g_pipe.cmp))) return rc;
+    PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
+    if ((rc = report_checks(an_checks, an_flags))) return rc;
     PIE_CUDA(pie::launch_daily_summary(dv_all, d_si, d_sf, Sc, an->tz_offset_minutes, dout, dscratch, g_sm_count,
                                        g_pipe.cmp));
     if (an->stats_i32 && S > 0) {
@@ -1270,6 +1294,8 @@ int pie_release(void) {
   if (g_ingest_host) cudaFreeHost(g_ingest_host);
   g_ingest_host = nullptr;
   g_ingest_host_cap = 0;
+  if (g_check_flags) cudaFree(g_check_flags);
+  g_check_flags = nullptr;
   if (g_pipe.h2d) {
     cudaStreamDestroy(g_pipe.h2d);
     cudaStreamDestroy(g_pipe.cmp);

@@ -15,6 +15,20 @@ extern std::atomic<unsigned long long> g_launches;
 extern int g_sm_count;
 inline int sm_count_or_default() { return g_sm_count > 0 ? g_sm_count : 148; }
 
+// validate.cu: the offsets arrays of a host batch, checked (and disarmed) on the device
+constexpr int kMaxOffsetsArrays = 32;
+struct OffsetsArray {
+  const int32_t* off;  // device, n + 1 elements
+  int64_t n;
+  int32_t first, last;  // every offset must lie in [first, last] and never decrease
+};
+struct OffsetsBatch {
+  OffsetsArray a[kMaxOffsetsArrays];
+  int count;
+};
+// flags: device int32[kMaxOffsetsArrays]; flags[i] != 0 afterwards: array i was malformed (and now holds empty rows)
+cudaError_t launch_offsets_check(const OffsetsBatch& batch, int32_t* flags, cudaStream_t stream);
+
 // archive_stats.cu
 cudaError_t launch_show_stats(const pie_archive_view& dev_view, int32_t* stats_i32, double* stats_f64,
                               int64_t stride, int sm_count, cudaStream_t stream);
