@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PIE_ABI_VERSION 1
+#define PIE_ABI_VERSION 2 /* 2: pie_archive_view / _table end with updated_at, deleted_at, time_kind */
 #define PIE_N_ISSUES 10   /* public/app.js:1-13 PRIMARY_ISSUES */
 #define PIE_N_METRICS 19  /* public/app.js:21-86 ARCHIVE_METRIC_DEFS (9) + issue:<name> (10), :3955-3994 */
 #define PIE_N_EXPORT_COLUMNS 24 /* server/webhookDispatcher.js:15-19 EXPORT_COLUMNS */
@@ -89,7 +89,29 @@ typedef struct pie_archive_view {
   const double* delay_sec;    /* value (may be NaN/Inf when delay_valid) */
   const uint8_t* delay_valid; /* 0 = null/undefined, 1 = a JS number */
   const double* entry_ts;     /* ms since epoch; NaN when absent */
+
+  /* ABI 2 — what the provider's own code asks of a stored document (_getTimestamp, sqlProvider.js:970-985, coerces:
+   * null is 0, '12' is 12, an ISO text goes through Date.parse) needs more than "a finite number or not".  All three
+   * may be NULL (then every NaN above counts as an absent field). */
+  const double* updated_at;   /* show.updatedAt, like created_at */
+  const double* deleted_at;   /* show.deletedAt, like created_at */
+  const uint8_t* time_kind;   /* [n_shows][PIE_TF_COUNT]: what the field holds when it is not a finite number, PIE_TK_* */
 } pie_archive_view;
+
+/* fields of time_kind, and their values.  PIE_TK_STRING: the NaN in the field's value array carries, in its low 51
+ * bits, the byte offset (in pie_json_docs.data) of the string's first character — the JSON ingest puts it there, and
+ * pie_get_timestamps_dev reads the text back from the documents. */
+enum { PIE_TF_CREATED = 0, PIE_TF_UPDATED = 1, PIE_TF_ARCHIVED = 2, PIE_TF_DELETED = 3, PIE_TF_COUNT = 4 };
+enum {
+  PIE_TK_ABSENT = 0,    /* undefined: no such key */
+  PIE_TK_NUMBER = 1,    /* a finite number: the value array holds it */
+  PIE_TK_NULL = 2,
+  PIE_TK_TRUE = 3,
+  PIE_TK_FALSE = 4,
+  PIE_TK_STRING = 5,
+  PIE_TK_OTHER = 6,     /* an array or an object */
+  PIE_TK_NONFINITE = 7  /* a number that is not finite (1e999 in the text; NaN / Infinity in a packed document) */
+};
 
 /* ---- planes of the per-show statistics table -------------------------------------------------
  * stats_i32 is int32[PIE_SI_COUNT][stride], stats_f64 is double[PIE_SF_COUNT][stride], plane-major
@@ -285,7 +307,8 @@ int pie_debug_csv_slow_tiles(const void* scratch, int64_t n_entries, uint32_t* s
  * they hold):
  *   show:  id date time label leadPilot monkeyLead notes -> text columns (string; null / absent = '');
  *          crew -> list of strings when it is an array (null elements = ''), else empty;
- *          createdAt archivedAt -> the number when it is a finite number, else NaN;
+ *          createdAt archivedAt updatedAt deletedAt -> the number when it is a finite number, else NaN, and
+ *          time_kind says what else the field holds (null, a boolean, a string ...);
  *          entries -> one row per element when it is an array (an element that is not an object is a row without
  *          fields), else none.
  *   entry: id unitId planned launched status primaryIssue subIssue otherDetail severity rootCause operator batteryId
@@ -348,6 +371,9 @@ typedef struct pie_archive_table {
   double* delay_sec;
   uint8_t* delay_valid;
   double* entry_ts;
+  double* updated_at;  /* ABI 2: may be NULL (not written) */
+  double* deleted_at;
+  uint8_t* time_kind;
 } pie_archive_table;
 
 uint64_t pie_ingest_scratch_bytes(int64_t n_docs);
@@ -381,6 +407,45 @@ int pie_archive_step_json_host(const pie_json_docs* host_docs, int32_t tz_offset
                                const pie_daily_out* host_out, int64_t* row_offsets, int64_t row_capacity,
                                uint8_t* out_data, uint64_t out_capacity, int64_t* n_entries, uint64_t* total_bytes,
                                int64_t* bad_doc);
+
+/* ---- _getTimestamp(value) (server/storage/sqlProvider.js:970-985) for the four time fields of every show of an
+ * ingested table: a finite number as it is; else Number(value) when that is finite (null -> 0, true -> 1, '' -> 0,
+ * ' 12 ' -> 12, '0x10' -> 16); else Date.parse of a string; else null (NaN here).  Date.parse is provided for the
+ * format ECMA-262 specifies (YYYY-MM-DD, and YYYY-MM-DDTHH:mm[:ss[.sss]] with an optional Z / +-HH:mm, local time of a
+ * fixed-offset zone otherwise); any other text is PIE_ERR_UNSUPPORTED_DATE (V8's legacy parser is implementation-
+ * defined), an array or object in a time field PIE_ERR_SCHEMA (Number([5]) is 5: not restated).  `dev_docs` are the
+ * documents the table was ingested from (needed when a field holds a string; may be NULL otherwise -> PIE_ERR_SCHEMA
+ * if one does).  status_dev[2] = {pie_status, first offending show}.  Arrays of `out` may be NULL. */
+typedef struct pie_doc_times {
+  double* created_at; /* [n_shows] each; NaN = null */
+  double* updated_at;
+  double* archived_at;
+  double* deleted_at;
+} pie_doc_times;
+int pie_get_timestamps_dev(const pie_archive_view* dev_view, const pie_json_docs* dev_docs, int32_t tz_offset_minutes,
+                           const pie_doc_times* dev_out, int32_t* status_dev, void* stream);
+
+/* ---- archive maintenance decisions (server/storage/sqlProvider.js).
+ * pie_archive_due_dev: which rows of `shows` _archiveDailyShows (:758-816) archives now.  Rows are grouped by
+ * show.date.trim() ('__undated__' when it is empty; `show_date` holds '' for a date that is not a string); a group is
+ * due when now - earliest >= 12 h, earliest = the smallest `created[s]` of the group, a NaN (null) counting as 0 —
+ * _getTimestamp(null) is 0 (:784), so one show without a usable timestamp makes its whole date group due.
+ *   created[s]      _getTimestamp(show.createdAt) ?? _getTimestamp(show.updatedAt): pie_get_timestamps_dev's
+ *                   created_at where it is not NaN, else its updated_at
+ *   doc_status[s]   != 0: the row did not parse to an object and is skipped (:767-772); may be NULL
+ *   due[s]          1 = archived now
+ *   group_first[s]  the first row of s's date group: the reference archives and dispatches the due rows in the order
+ *                   (group_first, s) — groups in order of first appearance (a Map), rows in row order; -1 = skipped
+ * Reads: show_date.  scratch: pie_archive_due_scratch_bytes(n_shows) bytes of device memory. */
+uint64_t pie_archive_due_scratch_bytes(int64_t n_shows);
+int pie_archive_due_dev(const pie_archive_view* dev_view, const uint8_t* doc_status, const double* created, double now_ms,
+                        uint8_t* due, int32_t* group_first, void* scratch, void* stream);
+/* pie_archive_expired_dev: _purgeExpiredArchives (:863-890): expired[s] = created[s] is not NaN and
+ * now >= _addMonths(created[s], 2) (:991-1009): new Date(t) (TimeClip), setMonth(getMonth() + 2) in LOCAL time — a
+ * fixed-offset zone — where a day past the end of the target month carries over (31 Dec -> 3 Mar, 2 Mar in a leap
+ * year), getTime().  created[s] = _getTimestamp(show?.createdAt) ?? _getTimestamp(row.created_at). */
+int pie_archive_expired_dev(const double* created, int64_t n, double now_ms, int32_t tz_offset_minutes, uint8_t* expired,
+                            void* stream);
 
 /* ---- self tests (device code paths that replace an IEEE operation by a faster exact sequence) */
 /* Compares the shared-reciprocal quotient used for the rate columns with IEEE a/b for every

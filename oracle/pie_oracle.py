@@ -664,7 +664,7 @@ def archive_entry_payload_json(show=UNDEFINED, entry=UNDEFINED) -> str:
 # stored documents -> shows: JSON.parse(row.data) as _mapArchiveRow does it (server/storage/sqlProvider.js:892-926)
 # ---------------------------------------------------------------------------------------------------------
 SHOW_DOC_KEYS = ("id", "date", "time", "label", "leadPilot", "monkeyLead", "notes", "crew", "createdAt", "archivedAt",
-                 "entries")
+                 "entries", "updatedAt", "deletedAt")
 ENTRY_DOC_KEYS = ("id", "unitId", "planned", "launched", "status", "primaryIssue", "subIssue", "otherDetail",
                   "severity", "rootCause", "operator", "batteryId", "commandRx", "notes", "actions", "delaySec", "ts")
 MAX_JSON_DEPTH = 64  # deeper nesting is reported, not parsed (the kernel's kind stack)

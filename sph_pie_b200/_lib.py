@@ -35,6 +35,11 @@ PIE_INGEST_HEAPS = 23
 PIE_IT_ENTRIES, PIE_IT_CREW_ITEMS, PIE_IT_ACTION_ITEMS = 23, 24, 25
 PIE_INGEST_TOTALS = 26
 
+# time fields of a show and what they can hold (pie_archive_view.time_kind)
+TF_CREATED, TF_UPDATED, TF_ARCHIVED, TF_DELETED = range(4)
+PIE_TF_COUNT = 4
+(TK_ABSENT, TK_NUMBER, TK_NULL, TK_TRUE, TK_FALSE, TK_STRING, TK_OTHER, TK_NONFINITE) = range(8)
+
 # plane indices (include/sph_pie_b200.h)
 SI_TOTAL, SI_COMPLETED, SI_NO_LAUNCH, SI_ABORT, SI_LAUNCHED, SI_DELAY_COUNT = range(6)
 SI_ISSUE_COUNT0 = 6
@@ -67,7 +72,14 @@ class ArchiveViewC(C.Structure):
         + [(n, StrColC) for n in ENTRY_STR_COLS]
         + [("actions", StrListColC), ("delay_sec", C.c_void_p), ("delay_valid", C.c_void_p),
            ("entry_ts", C.c_void_p)]
+        # ABI 2: the document's other two time fields and what the four hold when it is not a finite number
+        + [("updated_at", C.c_void_p), ("deleted_at", C.c_void_p), ("time_kind", C.c_void_p)]
     )
+
+
+class DocTimesC(C.Structure):
+    _fields_ = [("created_at", C.c_void_p), ("updated_at", C.c_void_p), ("archived_at", C.c_void_p),
+                ("deleted_at", C.c_void_p)]
 
 
 class JsonDocsC(C.Structure):
@@ -159,6 +171,12 @@ SIGNATURES = {
     "pie_archive_step_json_host": (C.c_int, [C.POINTER(JsonDocsC), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                              C.POINTER(DailyOutC), C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64,
                                              C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
+    "pie_get_timestamps_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.POINTER(JsonDocsC), C.c_int32, C.POINTER(DocTimesC),
+                                         C.c_void_p, C.c_void_p]),
+    "pie_archive_due_scratch_bytes": (C.c_uint64, [C.c_int64]),
+    "pie_archive_due_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "pie_archive_expired_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
     "pie_archive_analytics_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                              C.POINTER(DailyOutC)]),
 }

@@ -109,6 +109,26 @@ def _norm_time(v) -> float:
     return f if math.isfinite(f) else math.nan
 
 
+_ABSENT = object()
+
+
+def _time_kind(v, what: str) -> int:
+    """What a show's time field holds (_lib.TK_*).  A string is recorded as a string, but not its text: the table
+    points into the stored documents for that, which only the JSON ingest can do (pie_get_timestamps_dev reports
+    PIE_ERR_SCHEMA when asked to coerce a packed table's text timestamp)."""
+    if v is _ABSENT:
+        return _lib.TK_ABSENT
+    if v is None:
+        return _lib.TK_NULL
+    if v is True:
+        return _lib.TK_TRUE
+    if v is False:
+        return _lib.TK_FALSE
+    if isinstance(v, (int, float)):
+        return _lib.TK_NUMBER if math.isfinite(float(v)) else _lib.TK_NONFINITE
+    return _lib.TK_STRING if isinstance(v, str) else _lib.TK_OTHER
+
+
 @dataclass
 class ArchiveTable:
     n_shows: int
@@ -123,6 +143,11 @@ class ArchiveTable:
     delay_sec: torch.Tensor
     delay_valid: torch.Tensor
     entry_ts: torch.Tensor
+    # ABI 2 (optional): show.updatedAt / show.deletedAt like created_at, and what each of the four time fields holds
+    # when it is not a finite number: uint8 [n_shows, 4] of _lib.TK_* (created, updated, archived, deleted)
+    updated_at: Optional[torch.Tensor] = None
+    deleted_at: Optional[torch.Tensor] = None
+    time_kind: Optional[torch.Tensor] = None
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -139,7 +164,8 @@ class ArchiveTable:
             {k: f_col(c) for k, c in self.show_cols.items()}, f_col(self.crew),
             f_tensor(self.created_at), f_tensor(self.archived_at),
             {k: f_col(c) for k, c in self.entry_cols.items()}, f_col(self.actions),
-            f_tensor(self.delay_sec), f_tensor(self.delay_valid), f_tensor(self.entry_ts))
+            f_tensor(self.delay_sec), f_tensor(self.delay_valid), f_tensor(self.entry_ts),
+            *(None if t is None else f_tensor(t) for t in (self.updated_at, self.deleted_at, self.time_kind)))
 
     def to(self, device, non_blocking=False) -> "ArchiveTable":
         return self._map(lambda t: t.to(device, non_blocking=non_blocking), lambda c: c.to(device, non_blocking))
@@ -150,6 +176,7 @@ class ArchiveTable:
     def nbytes(self) -> int:
         n = self.entry_offsets.numel() * 4 + (self.created_at.numel() + self.archived_at.numel()) * 8
         n += self.delay_sec.numel() * 8 + self.delay_valid.numel() + self.entry_ts.numel() * 8
+        n += sum(t.numel() * t.element_size() for t in (self.updated_at, self.deleted_at, self.time_kind) if t is not None)
         n += sum(c.nbytes() for c in self.show_cols.values()) + sum(c.nbytes() for c in self.entry_cols.values())
         return n + self.crew.nbytes() + self.actions.nbytes()
 
@@ -170,6 +197,9 @@ class ArchiveTable:
         v.delay_sec = _ptr(self.delay_sec)
         v.delay_valid = _ptr(self.delay_valid)
         v.entry_ts = _ptr(self.entry_ts)
+        v.updated_at = _ptr(self.updated_at) if self.updated_at is not None else None
+        v.deleted_at = _ptr(self.deleted_at) if self.deleted_at is not None else None
+        v.time_kind = _ptr(self.time_kind) if self.time_kind is not None else None
         return v
 
     def slice_shows(self, s0: int, s1: int) -> "ArchiveTable":
@@ -189,7 +219,8 @@ class ArchiveTable:
             {k: sl_col(c, s0, s1) for k, c in self.show_cols.items()}, sl_list(self.crew, s0, s1),
             self.created_at[s0:s1], self.archived_at[s0:s1],
             {k: sl_col(c, e0, e1) for k, c in self.entry_cols.items()}, sl_list(self.actions, e0, e1),
-            self.delay_sec[e0:e1], self.delay_valid[e0:e1], self.entry_ts[e0:e1])
+            self.delay_sec[e0:e1], self.delay_valid[e0:e1], self.entry_ts[e0:e1],
+            *(None if t is None else t[s0:s1] for t in (self.updated_at, self.deleted_at, self.time_kind)))
 
 
 def _list_col(lists: List[List[str]]) -> StrListCol:
@@ -209,6 +240,7 @@ def pack_shows(shows: List[Optional[dict]]) -> ArchiveTable:
     entry_vals = {c: [] for c in ENTRY_KEY_TO_COL.values()}
     crew, actions = [], []
     created, archived, delay, delay_valid, ets = [], [], [], [], []
+    updated, deleted, kinds = [], [], []
     entry_offsets = [0]
     for si, show in enumerate(shows):
         show = show if isinstance(show, dict) else {}
@@ -218,6 +250,10 @@ def pack_shows(shows: List[Optional[dict]]) -> ArchiveTable:
         crew.append([_norm_str(x, f"shows[{si}].crew[]") for x in cr] if isinstance(cr, list) else [])
         created.append(_norm_time(show.get("createdAt")))
         archived.append(_norm_time(show.get("archivedAt")))
+        updated.append(_norm_time(show.get("updatedAt")))
+        deleted.append(_norm_time(show.get("deletedAt")))
+        kinds.append([_time_kind(show.get(k, _ABSENT), f"shows[{si}].{k}")
+                      for k in ("createdAt", "updatedAt", "archivedAt", "deletedAt")])
         entries = show.get("entries")
         entries = entries if isinstance(entries, list) else []
         for ei, e in enumerate(entries):
@@ -250,4 +286,7 @@ def pack_shows(shows: List[Optional[dict]]) -> ArchiveTable:
         delay_sec=torch.tensor(delay, dtype=torch.float64),
         delay_valid=torch.tensor(delay_valid, dtype=torch.uint8),
         entry_ts=torch.tensor(ets, dtype=torch.float64),
+        updated_at=torch.tensor(updated, dtype=torch.float64),
+        deleted_at=torch.tensor(deleted, dtype=torch.float64),
+        time_kind=torch.tensor(kinds, dtype=torch.uint8).reshape(len(shows), 4),
     )

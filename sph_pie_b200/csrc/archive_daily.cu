@@ -60,74 +60,6 @@ static DailyScratch carve(void* scratch, int64_t n_shows) {
   return d;
 }
 
-// ---------------------------------------------------------------------------------------------
-// ECMA-262 21.4.1.32 date-time string `${date}T${time}` (public/app.js:4122-4124).
-// returns 1 parsed (ms in *out), 0 -> NaN (illegal element values; the chain continues),
-// -1 unsupported (outside the specified grammar: V8's legacy parser would decide).
-__device__ __forceinline__ int two_digits(const uint8_t* s) {
-  uint32_t a = s[0] - '0', b = s[1] - '0';
-  return (a > 9 || b > 9) ? -1 : (int)(a * 10 + b);
-}
-
-__device__ __forceinline__ int64_t days_from_civil(int64_t y, int m, int d) {
-  y -= m <= 2;
-  const int64_t era = (y >= 0 ? y : y - 399) / 400;
-  const int64_t yoe = y - era * 400;
-  const int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
-  const int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
-  return era * 146097 + doe - 719468;
-}
-
-__device__ int parse_show_date_time(const uint8_t* ds, int dn, const uint8_t* ts, int tn, int64_t tz_off_ms,
-                                    double* out) {
-  const uint8_t dflt[5] = {'0', '0', ':', '0', '0'};
-  if (tn == 0) { ts = dflt; tn = 5; }
-  if (dn != 10 || ds[4] != '-' || ds[7] != '-') return -1;
-  const int y1 = two_digits(ds), y2 = two_digits(ds + 2), mo = two_digits(ds + 5), d = two_digits(ds + 8);
-  if (y1 < 0 || y2 < 0 || mo < 0 || d < 0) return -1;
-  if (tn < 5 || ts[2] != ':') return -1;
-  const int h = two_digits(ts), mi = two_digits(ts + 3);
-  if (h < 0 || mi < 0) return -1;
-  int pos = 5, sec = 0, ms = 0;
-  if (pos < tn && ts[pos] == ':') {
-    if (pos + 3 > tn) return -1;
-    sec = two_digits(ts + pos + 1);
-    if (sec < 0) return -1;
-    pos += 3;
-    if (pos < tn && ts[pos] == '.') {
-      if (pos + 4 > tn) return -1;
-      const uint32_t a = ts[pos + 1] - '0', b = ts[pos + 2] - '0', c = ts[pos + 3] - '0';
-      if (a > 9 || b > 9 || c > 9) return -1;
-      ms = (int)(a * 100 + b * 10 + c);
-      pos += 4;
-    }
-  }
-  bool has_off = false;
-  int64_t off_ms = 0;
-  if (pos < tn) {
-    if (ts[pos] == 'Z' && pos + 1 == tn) {
-      has_off = true;
-    } else if ((ts[pos] == '+' || ts[pos] == '-') && pos + 6 == tn && ts[pos + 3] == ':') {
-      const int oh = two_digits(ts + pos + 1), om = two_digits(ts + pos + 4);
-      if (oh < 0 || om < 0) return -1;
-      if (oh > 23 || om > 59) return 0;
-      off_ms = (int64_t)(oh * 60 + om) * 60000 * (ts[pos] == '-' ? -1 : 1);
-      has_off = true;
-    } else {
-      return -1;
-    }
-  }
-  const int year = y1 * 100 + y2;
-  if (mo < 1 || mo > 12 || d < 1 || d > 31 || h > 24 || mi > 59 || sec > 59) return 0;
-  if (h == 24 && (mi || sec || ms)) return 0;
-  const bool leap = (year % 4 == 0) && (year % 100 != 0 || year % 400 == 0);
-  const int dim = (mo == 2) ? (leap ? 29 : 28) : ((mo == 4 || mo == 6 || mo == 9 || mo == 11) ? 30 : 31);
-  if (d > dim) return -1;  // e.g. Feb 30: engines disagree (V8 rolls over, others NaN)
-  const int64_t local = ((days_from_civil(year, mo, d) * 24 + h) * 60 + mi) * 60000 + sec * 1000 + ms;
-  *out = (double)(local - (has_off ? off_ms : tz_off_ms));
-  return 1;
-}
-
 __global__ void daily_init_kernel(DailyMeta* meta) {
   meta->err = ~0ull;
   meta->or_bits = 0;

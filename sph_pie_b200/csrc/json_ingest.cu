@@ -157,6 +157,9 @@ __global__ void __launch_bounds__(kIngestThreads, kFill ? 8 : 10) ingest_walk_ke
           out.crew_list[s] = (int32_t)cnt[kPlaneCrewItems];
           out.created_at[s] = jw_nan();
           out.archived_at[s] = jw_nan();
+          if (out.time_val[PIE_TF_UPDATED]) out.time_val[PIE_TF_UPDATED][s] = jw_nan();
+          if (out.time_val[PIE_TF_DELETED]) out.time_val[PIE_TF_DELETED][s] = jw_nan();
+          if (out.time_kind) *reinterpret_cast<uint32_t*>(out.time_kind + s * PIE_TF_COUNT) = 0u;  // four PIE_TK_ABSENT
           walk = doc_status[s] == 0;  // a dropped row stays the empty show
         } else {
 #pragma unroll
@@ -415,6 +418,12 @@ IngestOut make_out(const pie_archive_table& t) {
   o.delay_sec = t.delay_sec;
   o.delay_valid = t.delay_valid;
   o.entry_ts = t.entry_ts;
+  o.time_val[PIE_TF_CREATED] = t.created_at;
+  o.time_val[PIE_TF_UPDATED] = t.updated_at;
+  o.time_val[PIE_TF_ARCHIVED] = t.archived_at;
+  o.time_val[PIE_TF_DELETED] = t.deleted_at;
+  o.time_kind = t.time_kind;
+  o.text = nullptr;  // set by the launcher
   return o;
 }
 
@@ -466,6 +475,7 @@ cudaError_t launch_ingest_fill(const pie_json_docs& docs, const void* scratch, c
   cudaError_t e = cudaMemsetAsync(sc.next_doc + 1, 0, 8, stream);  // pass 2 may run more than once per pass 1
   if (e != cudaSuccess) return e;
   IngestOut out = make_out(table);
+  out.text = docs.data;
   if (n > 0) {
     out.rows = static_cast<EntryRow*>(fill_scratch);
     ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc,

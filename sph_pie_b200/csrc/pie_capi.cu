@@ -93,6 +93,7 @@ struct PendingChecks {
 };
 PendingChecks g_checks;
 int32_t* g_check_flags = nullptr;  // device, [3][kMaxOffsetsArrays]: one set for the arena path, one per pipeline slot
+unsigned long long* g_maint_err = nullptr;  // device word: the first offending show of pie_get_timestamps_dev
 
 int ensure_check_flags();
 // enqueue the check of everything uploaded since clear(), flags -> `host_flags` (any host memory) on `st`
@@ -1082,6 +1083,9 @@ uint64_t layout_table(pie_archive_table* t, uint8_t* base, int64_t n_docs, const
   t->delay_sec = (double*)take(8 * (uint64_t)(E + 1));
   t->delay_valid = take((uint64_t)E + 8);
   t->entry_ts = (double*)take(8 * (uint64_t)(E + 1));
+  t->updated_at = (double*)take(8 * (uint64_t)(n_docs + 1));
+  t->deleted_at = (double*)take(8 * (uint64_t)(n_docs + 1));
+  t->time_kind = take(PIE_TF_COUNT * (uint64_t)(n_docs + 1));
   return off;
 }
 }  // namespace
@@ -1296,6 +1300,8 @@ int pie_release(void) {
   g_ingest_host_cap = 0;
   if (g_check_flags) cudaFree(g_check_flags);
   g_check_flags = nullptr;
+  if (g_maint_err) cudaFree(g_maint_err);
+  g_maint_err = nullptr;
   if (g_pipe.h2d) {
     cudaStreamDestroy(g_pipe.h2d);
     cudaStreamDestroy(g_pipe.cmp);
@@ -1311,6 +1317,47 @@ int pie_release(void) {
   g_cur = &g_arena;
   g_cur_stream = nullptr;
   cudaGetLastError();
+  return PIE_OK;
+}
+
+/* ---- _getTimestamp of the documents' time fields; archive maintenance decisions ---------------------------- */
+int pie_get_timestamps_dev(const pie_archive_view* v, const pie_json_docs* docs, int32_t tz_offset_minutes,
+                           const pie_doc_times* out, int32_t* status_dev, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!v || !out || !status_dev) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  if (v->n_shows < 0 || v->n_shows > 0x7FFFFFF0LL) return fail(PIE_ERR_INVALID_ARG, "n_shows out of range");
+  if (tz_offset_minutes < -24 * 60 || tz_offset_minutes > 24 * 60) return fail(PIE_ERR_INVALID_ARG, "tz_offset_minutes out of range");
+  if (docs && docs->n_docs > 0 && !docs->data) return fail(PIE_ERR_INVALID_ARG, "docs.data is NULL");
+  if (!g_maint_err) {
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    if (!g_maint_err) PIE_CUDA(cudaMalloc(&g_maint_err, 8));
+  }
+  PIE_CUDA(pie::launch_get_timestamps(*v, docs, tz_offset_minutes, *out, status_dev, g_maint_err, (cudaStream_t)stream));
+  return PIE_OK;
+}
+
+uint64_t pie_archive_due_scratch_bytes(int64_t n_shows) { return pie::archive_due_scratch_bytes(n_shows > 0 ? n_shows : 0); }
+
+int pie_archive_due_dev(const pie_archive_view* v, const uint8_t* doc_status, const double* created, double now_ms,
+                        uint8_t* due, int32_t* group_first, void* scratch, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!v || !due || !group_first || !scratch) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  if (v->n_shows < 0 || v->n_shows > 0x3FFFFFF0LL) return fail(PIE_ERR_INVALID_ARG, "n_shows out of range (batches of < 2^30 shows)");
+  if (v->n_shows > 0 && (!created || !v->show_date.offsets)) return fail(PIE_ERR_INVALID_ARG, "created / show_date is NULL");
+  if (reinterpret_cast<uintptr_t>(scratch) & 15) return fail(PIE_ERR_INVALID_ARG, "scratch must be 16-byte aligned");
+  PIE_CUDA(pie::launch_archive_due(*v, doc_status, created, now_ms, due, group_first, scratch, (cudaStream_t)stream));
+  return PIE_OK;
+}
+
+int pie_archive_expired_dev(const double* created, int64_t n, double now_ms, int32_t tz_offset_minutes, uint8_t* expired,
+                            void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!created || !expired))) return fail(PIE_ERR_INVALID_ARG, "NULL argument / negative size");
+  if (tz_offset_minutes < -24 * 60 || tz_offset_minutes > 24 * 60) return fail(PIE_ERR_INVALID_ARG, "tz_offset_minutes out of range");
+  PIE_CUDA(pie::launch_archive_expired(created, n, now_ms, tz_offset_minutes, expired, (cudaStream_t)stream));
   return PIE_OK;
 }
 

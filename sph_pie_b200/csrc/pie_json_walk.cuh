@@ -92,6 +92,11 @@ struct DocCursor {
       cur = 0;
     }
   }
+  // address of the next byte the cursor will hand out
+  PIE_JW_HD const uint8_t* position() const {
+    const uint8_t* word = reinterpret_cast<const uint8_t*>(w - 1);  // the last word fetched: nxt, or cur at the end
+    return words_left > 0 ? word - left : word + tail_bytes - left;
+  }
   PIE_JW_HD int peek() const { return left > 0 ? (int)(cur & 0xFF) : -1; }
   PIE_JW_HD void next() {
     cur >>= 8;
@@ -140,7 +145,7 @@ PIE_JW_HD constexpr uint64_t key_word(const char (&s)[L], int from) {
 }
 #define PIE_KEY_IS(lit) (len == sizeof(lit) - 1 && k0 == key_word(lit, 0) && k1 == key_word(lit, 8))
 
-enum ShowKey { kSkCrew = 7, kSkCreatedAt = 8, kSkArchivedAt = 9, kSkEntries = 10 };
+enum ShowKey { kSkCrew = 7, kSkCreatedAt = 8, kSkArchivedAt = 9, kSkEntries = 10, kSkUpdatedAt = 11, kSkDeletedAt = 12 };
 enum EntryKey { kEkActions = 14, kEkDelaySec = 15, kEkTs = 16 };
 
 // keys of the show document in the order of the table's show columns (columnar.py SHOW_KEY_TO_COL), then the rest
@@ -156,6 +161,8 @@ PIE_JW_HD int match_show_key(uint32_t len, uint64_t k0, uint64_t k1) {
   if (PIE_KEY_IS("createdAt")) return kSkCreatedAt;
   if (PIE_KEY_IS("archivedAt")) return kSkArchivedAt;
   if (PIE_KEY_IS("entries")) return kSkEntries;
+  if (PIE_KEY_IS("updatedAt")) return kSkUpdatedAt;
+  if (PIE_KEY_IS("deletedAt")) return kSkDeletedAt;
   return -1;
 }
 // keys of an entry in the order of the table's entry columns (ENTRY_KEY_TO_COL)
@@ -207,6 +214,12 @@ struct IngestOut {
   double* delay_sec;
   uint8_t* delay_valid;
   double* entry_ts;
+  // the four time fields of the show (PIE_TF_*): value arrays (created_at / archived_at above are two of them; the
+  // other two may be nullptr), what a field holds when it is not a finite number (may be nullptr), and the text the
+  // documents are in — a string in a time field is recorded by the place of its first character
+  double* time_val[PIE_TF_COUNT];
+  uint8_t* time_kind;
+  const uint8_t* text;
 };
 
 enum Sem : int { kSemTop = 0, kSemShow, kSemCrew, kSemEntries, kSemEntry, kSemActions, kSemSkip, kSemDone };
@@ -590,13 +603,16 @@ struct DocWalker {
     //   is_item     an element of crew / actions: counted even when null
     //   num_role    1 createdAt, 2 archivedAt, 3 ts (a finite number or absent), 4 delaySec (number | null)
     int heap = -1, num_role = 0;
+    int time_field = -1;  // the value belongs to one of the show's time fields (PIE_TF_*)
     bool is_item = false;
     int open_sem = kSemSkip;  // what an opening bracket starts
     const int at = sem;
     if (at == kSemShow) {
       if (key >= 0 && key < 7) heap = key;
-      else if (key == kSkCreatedAt) num_role = 1;
-      else if (key == kSkArchivedAt) num_role = 2;
+      else if (key == kSkCreatedAt) { num_role = 1; time_field = PIE_TF_CREATED; }
+      else if (key == kSkArchivedAt) { num_role = 2; time_field = PIE_TF_ARCHIVED; }
+      else if (key == kSkUpdatedAt) { num_role = 5; time_field = PIE_TF_UPDATED; }
+      else if (key == kSkDeletedAt) { num_role = 6; time_field = PIE_TF_DELETED; }
       else if (key == kSkCrew && ch == '[') open_sem = kSemCrew;
       else if (key == kSkEntries && ch == '[') open_sem = kSemEntries;
     } else if (at == kSemEntry) {
@@ -625,6 +641,13 @@ struct DocWalker {
       ++cnt[items];
     }
 
+    if (kFill && time_field >= 0) {  // what the field holds, for _getTimestamp's coercions (rare keys: four a document)
+      const int kind = (ch == '{' || ch == '[') ? PIE_TK_OTHER : ch == '"' ? PIE_TK_STRING : ch == 'n' ? PIE_TK_NULL
+                       : ch == 't' ? PIE_TK_TRUE : ch == 'f' ? PIE_TK_FALSE : PIE_TK_NUMBER;  // a number: settled below
+      if (out.time_kind) out.time_kind[s * PIE_TF_COUNT + time_field] = (uint8_t)kind;
+      if (ch == '"' && out.time_val[time_field])  // NaN whose payload is where the string's text starts
+        out.time_val[time_field][s] = np_bits_to_double(0x7ff8000000000000ull | ((uint64_t)(c.position() - out.text) & 0x7ffffffffffffull));
+    }
     if (ch == '{' || ch == '[') {
       if (depth >= kMaxDepth) return kDocUnsupported;
       if (heap >= 0 || num_role == 4) set_hard(kDocSchema);
@@ -666,7 +689,10 @@ struct DocWalker {
       if (heap >= 0) set_hard(kDocSchema);
       if (num_role == 4) { e_delay = v; e_valid = true; }
       else if (num_role == 3) e_ts = jw_is_finite(v) ? v : jw_nan();
-      else if (num_role && kFill) (num_role == 1 ? out.created_at : out.archived_at)[s] = jw_is_finite(v) ? v : jw_nan();
+      else if (num_role && kFill) {
+        if (out.time_val[time_field]) out.time_val[time_field][s] = jw_is_finite(v) ? v : jw_nan();
+        if (!jw_is_finite(v) && out.time_kind) out.time_kind[s * PIE_TF_COUNT + time_field] = PIE_TK_NONFINITE;
+      }
     } else {
       const char* lit = ch == 't' ? "rue" : ch == 'f' ? "alse" : ch == 'n' ? "ull" : nullptr;
       if (!lit) return kDocDropped;

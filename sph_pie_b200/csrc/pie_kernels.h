@@ -63,6 +63,16 @@ uint64_t ingest_fill_scratch_bytes(int64_t n_entries);
 cudaError_t launch_ingest_fill(const pie_json_docs& dev_docs, const void* scratch, const uint8_t* doc_status,
                                const pie_archive_table& dev_table, void* fill_scratch, cudaStream_t stream);
 
+// archive_maintenance.cu: _getTimestamp of the documents' time fields; the archive / purge decisions
+cudaError_t launch_get_timestamps(const pie_archive_view& dev_view, const pie_json_docs* dev_docs, int32_t tz_offset_minutes,
+                                  const pie_doc_times& out, int32_t* status, unsigned long long* err_scratch,
+                                  cudaStream_t stream);
+uint64_t archive_due_scratch_bytes(int64_t n_shows);
+cudaError_t launch_archive_due(const pie_archive_view& dev_view, const uint8_t* doc_status, const double* created, double now_ms,
+                               uint8_t* due, int32_t* group_first, void* scratch, cudaStream_t stream);
+cudaError_t launch_archive_expired(const double* created, int64_t n, double now_ms, int32_t tz_offset_minutes,
+                                   uint8_t* expired, cudaStream_t stream);
+
 // archive_daily.cu
 uint64_t daily_scratch_bytes(int64_t n_shows);
 cudaError_t launch_daily_summary(const pie_archive_view& dev_view, const int32_t* stats_i32,

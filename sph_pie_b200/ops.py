@@ -368,7 +368,9 @@ def alloc_ingest_table(n_docs: int, totals, device) -> ArchiveTable:
         created_at=f64(n_docs), archived_at=f64(n_docs),
         entry_cols={name: col(E, 8 + h) for h, name in enumerate(_lib.ENTRY_STR_COLS)},
         actions=StrListCol(i32(E + 1), col(action_items, 22)),
-        delay_sec=f64(E), delay_valid=torch.empty(E + 1, dtype=torch.uint8, device=device)[:E], entry_ts=f64(E))
+        delay_sec=f64(E), delay_valid=torch.empty(E + 1, dtype=torch.uint8, device=device)[:E], entry_ts=f64(E),
+        updated_at=f64(n_docs), deleted_at=f64(n_docs),
+        time_kind=torch.zeros((n_docs + 1, _lib.PIE_TF_COUNT), dtype=torch.uint8, device=device)[:n_docs])
 
 
 def _raise_ingest_status(code: int, doc: int) -> None:
@@ -475,7 +477,9 @@ def _table_from_library_view(view: "_lib.ArchiveViewC", n_docs: int, totals) -> 
         entry_cols={name: col(getattr(view, name), E, 8 + h) for h, name in enumerate(_lib.ENTRY_STR_COLS)},
         actions=StrListCol(arr(view.actions.list_offsets, E + 1, torch.int32), col(view.actions.items, action_items, 22)),
         delay_sec=arr(view.delay_sec, E, torch.float64), delay_valid=arr(view.delay_valid, E, torch.uint8),
-        entry_ts=arr(view.entry_ts, E, torch.float64))
+        entry_ts=arr(view.entry_ts, E, torch.float64),
+        updated_at=arr(view.updated_at, n_docs, torch.float64), deleted_at=arr(view.deleted_at, n_docs, torch.float64),
+        time_kind=arr(view.time_kind, n_docs * _lib.PIE_TF_COUNT, torch.uint8).reshape(n_docs, _lib.PIE_TF_COUNT))
 
 
 def archive_step_from_json(docs: JsonDocs, tz_offset_minutes: int = 0, out: "HostOutputs" = None,
@@ -727,3 +731,72 @@ def archive_step_json_host(docs: JsonDocs, tz_offset_minutes: int = 0, out: "Hos
     daily = DailySummary(G, h.show_day_start[:n], h.show_order[:n], h.group_day_start[:G], h.group_offsets[:G + 1],
                          h.summary_f64[:, :, :G], h.summary_count[:, :G])
     return stats, daily, CsvRows(row_offsets[:E + 1], data[:total.value]), status[:n].bool()
+
+
+# ---- _getTimestamp of the documents' time fields; archive maintenance decisions (pie_get_timestamps_dev, pie_archive_*) ----
+@dataclass
+class DocTimes:
+    """_getTimestamp(show.createdAt / updatedAt / archivedAt / deletedAt) (sqlProvider.js:970-985) per show: float64
+    [n_shows] each, NaN where the reference's function returns null."""
+    created_at: torch.Tensor
+    updated_at: torch.Tensor
+    archived_at: torch.Tensor
+    deleted_at: torch.Tensor
+
+
+def _raise_times_status(code: int, show: int) -> None:
+    if code == 0:
+        return
+    if code == _lib.PIE_ERR_UNSUPPORTED_DATE:
+        raise _lib.UnsupportedDateError(code, f"show {show}: a text timestamp that is neither numeric nor an ECMA-262 date-time string")
+    if code == _lib.PIE_ERR_SCHEMA:
+        raise _lib.SchemaError(code, f"show {show}: a time field holds an array / object, or a text and the documents were not given")
+    raise _lib.PieError(code, f"timestamps failed at show {show}")
+
+
+def get_timestamps(table: ArchiveTable, docs: "JsonDocs" = None, tz_offset_minutes: int = 0) -> DocTimes:
+    """_getTimestamp for the four time fields of every show of a CUDA-resident table (`docs`: the CUDA-resident
+    documents it was ingested from, needed when a field holds a string)."""
+    _lib.ensure_init()
+    assert table.is_cuda, "pie_get_timestamps_dev works on a device-resident table"
+    dev, S = table.device, table.n_shows
+    out = [torch.empty(max(S, 1), dtype=torch.float64, device=dev) for _ in range(4)]
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    view = table.view()
+    d = docs.c() if docs is not None else None
+    times = _lib.DocTimesC(*(t.data_ptr() for t in out))
+    _lib.check(_lib.load().pie_get_timestamps_dev(C.byref(view), C.byref(d) if d is not None else None, tz_offset_minutes,
+                                                  C.byref(times), status.data_ptr(), _stream_ptr()))
+    code, show = status.cpu().tolist()
+    _raise_times_status(code, show)
+    return DocTimes(*(t[:S] for t in out))
+
+
+def archive_due(table: ArchiveTable, created: torch.Tensor, now_ms: float, doc_status: torch.Tensor = None):
+    """The decision of _archiveDailyShows (sqlProvider.js:758-816) for the rows of a CUDA-resident table: (due uint8[S],
+    group_first int32[S]).  created[s] = _getTimestamp(createdAt) ?? _getTimestamp(updatedAt) (NaN = null)."""
+    _lib.ensure_init()
+    assert table.is_cuda
+    lib, dev, S = _lib.load(), table.device, table.n_shows
+    due = torch.zeros(max(S, 1), dtype=torch.uint8, device=dev)
+    first = torch.full((max(S, 1),), -1, dtype=torch.int32, device=dev)
+    scratch = torch.empty(int(lib.pie_archive_due_scratch_bytes(S)), dtype=torch.uint8, device=dev)
+    view = table.view()
+    created = created.to(dev, torch.float64).contiguous()
+    _lib.check(lib.pie_archive_due_dev(C.byref(view), doc_status.data_ptr() if doc_status is not None else None,
+                                       created.data_ptr() if S else None, float(now_ms), due.data_ptr(), first.data_ptr(),
+                                       scratch.data_ptr(), _stream_ptr()))
+    return due[:S], first[:S]
+
+
+def archive_expired(created: torch.Tensor, now_ms: float, tz_offset_minutes: int = 0) -> torch.Tensor:
+    """_purgeExpiredArchives' decision (sqlProvider.js:863-890, _addMonths :999-1009): expired uint8[n] for
+    created[n] = _getTimestamp(show?.createdAt) ?? _getTimestamp(row.created_at) (NaN = null), on the GPU."""
+    _lib.ensure_init()
+    assert created.is_cuda
+    created = created.to(torch.float64).contiguous()
+    n = created.numel()
+    out = torch.zeros(max(n, 1), dtype=torch.uint8, device=created.device)
+    _lib.check(_lib.load().pie_archive_expired_dev(created.data_ptr() if n else None, n, float(now_ms), tz_offset_minutes,
+                                                   out.data_ptr() if n else None, _stream_ptr()))
+    return out[:n]

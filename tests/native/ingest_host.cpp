@@ -33,6 +33,12 @@ static IngestOut make_out(const pie_archive_table& t) {
   o.delay_sec = t.delay_sec;
   o.delay_valid = t.delay_valid;
   o.entry_ts = t.entry_ts;
+  o.time_val[PIE_TF_CREATED] = t.created_at;
+  o.time_val[PIE_TF_UPDATED] = t.updated_at;
+  o.time_val[PIE_TF_ARCHIVED] = t.archived_at;
+  o.time_val[PIE_TF_DELETED] = t.deleted_at;
+  o.time_kind = t.time_kind;
+  o.text = nullptr;
   return o;
 }
 
@@ -71,7 +77,8 @@ extern "C" void ingest_host_measure(const uint8_t* text, const int64_t* offsets,
 extern "C" void ingest_host_fill(const uint8_t* text, const int64_t* offsets, int64_t n_docs, const uint32_t* planes,
                                  const uint8_t* doc_status, const pie_archive_table* table) {
   const Pow5Table pow5{kPow5};
-  const IngestOut out = make_out(*table);
+  IngestOut out = make_out(*table);
+  out.text = text;
   if (n_docs == 0) {
     for (int h = 0; h < kHeaps; ++h) out.off[h][0] = 0;
     out.entry_offsets[0] = 0;
@@ -87,6 +94,9 @@ extern "C" void ingest_host_fill(const uint8_t* text, const int64_t* offsets, in
     out.crew_list[s] = (int32_t)cnt[kPlaneCrewItems];
     out.created_at[s] = jw_nan();
     out.archived_at[s] = jw_nan();
+    if (out.time_val[PIE_TF_UPDATED]) out.time_val[PIE_TF_UPDATED][s] = jw_nan();
+    if (out.time_val[PIE_TF_DELETED]) out.time_val[PIE_TF_DELETED][s] = jw_nan();
+    if (out.time_kind) memset(out.time_kind + s * PIE_TF_COUNT, 0, PIE_TF_COUNT);
     if (doc_status[s] == 0) {
       DocWalker<true> w;
       w.begin(text, offsets[s], offsets[s + 1], s);

@@ -22,15 +22,16 @@ def test_library_exports_every_declared_symbol(built):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/sph_pie_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.pie_abi_version() == 1
+    assert lib.pie_abi_version() == 2
 
 
 def test_struct_layouts_match_header(built):
     import ctypes as C
 
     assert C.sizeof(_lib.StrColC) == 16 and C.sizeof(_lib.StrListColC) == 24
-    # 3 scalars/pointers + 7 strcols + strlist + 2 ptr + 14 strcols + strlist + 3 ptr
-    assert C.sizeof(_lib.ArchiveViewC) == 8 * 3 + 16 * 7 + 24 + 16 + 16 * 14 + 24 + 24
+    # 3 scalars/pointers + 7 strcols + strlist + 2 ptr + 14 strcols + strlist + 3 ptr + (ABI 2) 3 ptr
+    assert C.sizeof(_lib.ArchiveViewC) == 8 * 3 + 16 * 7 + 24 + 16 + 16 * 14 + 24 + 24 + 24
+    assert C.sizeof(_lib.DocTimesC) == 32
     assert C.sizeof(_lib.DailyOutC) == 8 * 9
 
 

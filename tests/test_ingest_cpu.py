@@ -271,8 +271,102 @@ def test_row_timestamps_host_logic():
         got = storage._row_timestamp(v)
         want = po.get_timestamp(po.UNDEFINED if v is storage._MISSING else v)
         assert (want is None and math.isnan(got)) or got == want, (v, got, want)
-    for v in ["abc", "2024-01-01T00:00:00Z", "Infinity", "-Infinity", "１２", "-0x1", "1_000", "12px", "0x", "1e"]:
+    for v in ["abc", "Infinity", "-Infinity", "１２", "-0x1", "1_000", "12px", "0x", "1e", "2024-02-30", "01/02/2024",
+              "2024-01-01 00:00:00", "Mon, 01 Jan 2024 00:00:00 GMT"]:
         with pytest.raises(NotImplementedError):
             storage._row_timestamp(v)
         with pytest.raises(NotImplementedError):
-            po.get_timestamp(v)
+            po.get_timestamp_tz(v)
+    # the Date.parse leg, for the one format ECMA-262 specifies (a date-only form is UTC, a date-time without offset
+    # is local time): the product's host side against the oracle and against hand-derived values
+    day = 1704067200000.0  # 2024-01-01T00:00:00Z
+    for text, tz, want in [("2024-01-01", 0, day), ("2024-01-01", -480, day), ("2024-01-01T00:00:00.000Z", 330, day),
+                           ("2024-01-01T00:00", 0, day), ("2024-01-01T00:00", -480, day + 480 * 60000),
+                           ("2024-01-01T05:30:15.250+05:30", 0, day + 15250), ("2024-01-01T24:00", 0, day + 86400000),
+                           ("2024-13-01", 0, None), ("2024-01-01T25:00", 0, None), ("2024-01-01T24:00:01", 0, None),
+                           ("2024-01-01T00:00+24:00", 0, None)]:
+        got = storage._row_timestamp(text, tz)
+        assert po.get_timestamp_tz(text, tz) == want, text
+        assert (want is None and math.isnan(got)) or got == want, (text, got, want)
+
+
+def test_time_fields_and_their_kinds():
+    """ABI 2: updatedAt / deletedAt and what each of the four time fields holds when it is not a finite number — the
+    walker (built for the host) against the table packer on JSON.parse's values; a text is recorded by its place."""
+    docs = [
+        '{"id":"a","createdAt":1704067200000,"updatedAt":1704067200001.5,"archivedAt":null,"deletedAt":true}',
+        '{"createdAt":null,"updatedAt":false,"deletedAt":null,"entries":[]}',
+        '{"id":"c"}',
+        '{"createdAt":1e999,"updatedAt":-1e999,"archivedAt":0,"deletedAt":-0}',
+        '[1,2]', 'null', '{"updatedAt":5e-324,"deletedAt":123456789012345680000}',
+    ]
+    got, status, err = host_ingest(docs)
+    assert err == (0, -1)
+    ref, ref_status = oracle_ingest(docs)
+    assert np.array_equal(status, ref_status)
+    assert_tables_equal(got, ref)
+    assert torch.equal(got.time_kind, ref.time_kind)
+    for name in ("updated_at", "deleted_at"):
+        a, b = getattr(got, name).numpy(), getattr(ref, name).numpy()
+        assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)].view(np.int64), b[~np.isnan(b)].view(np.int64))
+    K = _lib
+    assert got.time_kind.tolist()[0] == [K.TK_NUMBER, K.TK_NUMBER, K.TK_NULL, K.TK_TRUE]
+    assert got.time_kind.tolist()[3] == [K.TK_NONFINITE, K.TK_NONFINITE, K.TK_NUMBER, K.TK_NUMBER]
+    assert got.time_kind.tolist()[4] == [0, 0, 0, 0] and got.time_kind.tolist()[5] == [0, 0, 0, 0]
+
+    # strings, arrays and objects: the kind, and for a string the byte offset of its text in the NaN's payload
+    docs = ['{"createdAt":"1704067200000","updatedAt":"2024-01-01T00:00:00.000Z","archivedAt":[5],"deletedAt":{"a":1}}',
+            '{"id":"x","deletedAt":" 12 ","createdAt":""}']
+    got, status, err = host_ingest(docs)
+    assert err == (0, -1) and status.tolist() == [0, 0]
+    assert got.time_kind.tolist() == [[K.TK_STRING, K.TK_STRING, K.TK_OTHER, K.TK_OTHER], [K.TK_STRING, K.TK_ABSENT, K.TK_ABSENT, K.TK_STRING]]
+    text = "".join(docs).encode()
+    def text_at(x):
+        bits = int(np.float64(x).view(np.int64)) & 0x7FFFFFFFFFFFF
+        return text[bits:text.index(b'"', bits)].decode()
+    assert np.isnan(got.created_at[0].item()) and text_at(got.created_at[0].item()) == "1704067200000"
+    assert text_at(got.updated_at[0].item()) == "2024-01-01T00:00:00.000Z"
+    assert text_at(got.deleted_at[1].item()) == " 12 " and text_at(got.created_at[1].item()) == ""
+    # the packer records the same kinds (it has no text to point into: its NaNs carry no payload)
+    ref, _ = oracle_ingest(docs)
+    assert_tables_equal(got, ref)
+    assert torch.equal(got.time_kind, ref.time_kind)
+    # a time key twice is as undecided as any other known key twice
+    _, _, err = host_ingest(['{"updatedAt":1,"updatedAt":2}'])
+    assert err[0] == _lib.PIE_ERR_UNSUPPORTED_JSON
+
+
+def test_archive_maintenance_oracle_rules():
+    """The Python restatement of _archiveDailyShows' decision, _addMonths and _purgeExpiredArchives on hand-derived
+    cases (reference server/storage/sqlProvider.js:758-816, :863-890, :991-1009)."""
+    H = 3600 * 1000
+    now = 1704067200000.0 + 12 * H  # 2024-01-01T12:00Z
+    rows = ['{"date":"2024-01-01","createdAt":1704067200000}',            # exactly 12 h old: due (>=)
+            '{"date":" 2024-01-01 ","createdAt":1704067200001}',          # same group after trim: due with it
+            '{"date":"2024-01-02","createdAt":1704067200001}',            # 12 h minus 1 ms: not due
+            '{"date":"2024-01-03","updatedAt":"1704067200000"}',          # createdAt absent -> updatedAt, numeric text
+            '{"date":"2024-01-04"}',                                       # no timestamp at all: null -> 0 -> due
+            '{"date":"2024-01-02","createdAt":null}',                      # Number(null) = 0: drags its group along
+            'not json', '7', '{"createdAt":1}', '{"date":"  ","createdAt":9e15}', '[]']
+    due, order = po.archive_daily_shows_decision(rows, now)
+    assert due == [True, True, True, True, True, True, False, False, True, True, True]
+    # groups in order of first appearance, rows in row order; '__undated__' holds rows 8, 9 and the array
+    assert order == [0, 1, 2, 5, 3, 4, 8, 9, 10]
+    # setMonth keeps the day of the month and carries an overflow: 31 Dec + 2 months = 2 Mar in a leap year
+    d = lambda y, m, dd: float(po.days_from_civil(y, m, dd) * 86400000)
+    assert po.add_months(d(2023, 12, 31), 2) == d(2024, 3, 2)
+    assert po.add_months(d(2022, 12, 31), 2) == d(2023, 3, 3)
+    assert po.add_months(d(2024, 1, 15) + 5.75, 2) == d(2024, 3, 15) + 5  # new Date() truncates the fraction
+    assert po.add_months(d(2024, 11, 30), 2) == d(2025, 1, 30)
+    assert po.add_months(-1.0, 2) == d(1970, 3, 4) - 1  # 1969-12-31T23:59:59.999 -> 31 Feb 1970 = 3 Mar, same time of day
+    # local time: 2024-01-01T02:00Z is still 31 Dec, 18:00, at UTC-8 -> 31 Feb -> 2 Mar 18:00 local = 3 Mar 02:00Z
+    assert po.add_months(d(2024, 1, 1) + 2 * H, 2, -480) == d(2024, 3, 3) + 2 * H
+    assert po.add_months(8.64e15 + 1, 2) == 8.64e15 + 1 and np.isnan(po.add_months(8.64e15, 2))
+    assert po.is_archive_expired(d(2024, 1, 1), d(2024, 3, 1)) and not po.is_archive_expired(d(2024, 1, 1), d(2024, 3, 1) - 1)
+    rows = [{"data": '{"createdAt":%d}' % int(d(2024, 1, 1)), "created_at": "1"},   # the document's own field wins
+            {"data": "{}", "created_at": str(int(d(2024, 1, 1)))},                  # else the row's column (a text)
+            {"data": "broken", "created_at": None},                                  # Number(null) = 0: long expired
+            {"data": "{}"},                                                          # neither: skipped
+            {"data": '{"createdAt":"2024-01-01T00:00:00.000Z"}'}]                    # Date.parse
+    assert po.purge_expired_archives_decision(rows, d(2024, 3, 1)) == [True, True, True, False, True]
+    assert po.purge_expired_archives_decision(rows, d(2024, 3, 1) - 1) == [False, False, True, False, False]
