@@ -288,6 +288,28 @@ int pie_archive_payloads_dev(const pie_archive_view* dev_view, int64_t* row_offs
 int pie_archive_payloads_host(const pie_archive_view* host_view, int64_t* row_offsets, uint8_t* out_data,
                               uint64_t out_capacity, uint64_t* total_bytes);
 
+/* ---- the schemaVersion 2 show payload: replaces JSON.stringify of the object dispatchShowEvent builds for every
+ * event but 'show.archived' (server/webhookDispatcher.js:545-584, with buildShowSummary :472-488, normalizeEntryList
+ * :460-470, buildTableRow / buildCsvRow :276-342) for every show of a batch — one JSON document per show:
+ *   <head>"table":{"columns":[..],"rows":[[24 values],..]},"csv":{"header":[..],"rows":["<csv row>",..]},
+ *   "message":{"show":<summary>,"entries":[{24 members},..]},"show":<summary>,"entries":[{..},..]<tail>
+ * `head` is the text up to and including the comma before "table" — `{"event":..,"schemaVersion":2,"dispatchedAt":..,
+ * "target":{"url":..,"method":..},` — and `tail` what closes the document (`}` or `,"meta":{..}}`): the caller's
+ * strings, serialised by the caller (sph_pie_b200/webhook.py does it).  Table rows keep delaySec a JSON number ('' when
+ * null; null when it is not finite, as JSON.stringify writes NaN / Infinity); a csv row is one JSON string; the summary's
+ * four timestamps are `show.x ?? null` (numbers, booleans or null — a text / array there is PIE_ERR_SCHEMA: the table
+ * does not hold it).  `entries` are written in the provider's normalised shape (sqlProvider.js:384-409: id, ts, unitId,
+ * planned, launched, status, primaryIssue, subIssue, otherDetail, severity, rootCause, actions, operator, batteryId,
+ * delaySec, commandRx, notes) — what normalizeEntryList passes through for a stored show; keys the table does not
+ * hold are not carried.
+ * Document s is out_data[doc_offsets[s] .. doc_offsets[s+1]); doc_offsets has n_shows + 1 elements.  out_data == NULL
+ * sizes only; nothing is written past out_capacity and *total_bytes_dev reports the size needed.  status_dev[2] =
+ * {pie_status, first offending show}.  Reads every column incl. created_at .. time_kind.  All pointers device. */
+uint64_t pie_show_payloads_scratch_bytes(int64_t n_shows);
+int pie_show_payloads_dev(const pie_archive_view* dev_view, const uint8_t* head, int32_t head_len, const uint8_t* tail,
+                          int32_t tail_len, int64_t* doc_offsets, uint8_t* out_data, uint64_t out_capacity,
+                          uint64_t* total_bytes_dev, int32_t* status_dev, void* scratch, void* stream);
+
 /* Test hooks of the export-row kernel.  A tile (32..160 consecutive rows, planned per launch from the batch's
  * average row width) whose column bytes or CSV do not fit the kernel's shared-memory staging takes a slower
  * warp-per-row path; `on` = 1 forces every tile

@@ -171,6 +171,9 @@ SIGNATURES = {
     "pie_archive_step_json_host": (C.c_int, [C.POINTER(JsonDocsC), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                              C.POINTER(DailyOutC), C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64,
                                              C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
+    "pie_show_payloads_scratch_bytes": (C.c_uint64, [C.c_int64]),
+    "pie_show_payloads_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pie_get_timestamps_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.POINTER(JsonDocsC), C.c_int32, C.POINTER(DocTimesC),
                                          C.c_void_p, C.c_void_p]),
     "pie_archive_due_scratch_bytes": (C.c_uint64, [C.c_int64]),

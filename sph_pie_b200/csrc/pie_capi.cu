@@ -1320,6 +1320,26 @@ int pie_release(void) {
   return PIE_OK;
 }
 
+/* ---- the schemaVersion 2 show payload ------------------------------------------------------------------------ */
+uint64_t pie_show_payloads_scratch_bytes(int64_t n_shows) { return pie::show_payload_scratch_bytes(n_shows > 0 ? n_shows : 0); }
+
+int pie_show_payloads_dev(const pie_archive_view* v, const uint8_t* head, int32_t head_len, const uint8_t* tail,
+                          int32_t tail_len, int64_t* doc_offsets, uint8_t* out_data, uint64_t out_capacity,
+                          uint64_t* total_bytes_dev, int32_t* status_dev, void* scratch, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if ((rc = check_view_common(v))) return rc;
+  if ((rc = check_export_view_dev(v, kFormatCsv))) return rc;  // every column the CSV rows read
+  if (!doc_offsets || !total_bytes_dev || !status_dev || !scratch) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  if (head_len < 0 || tail_len < 0 || (head_len > 0 && !head) || (tail_len > 0 && !tail))
+    return fail(PIE_ERR_INVALID_ARG, "head / tail");
+  if (v->n_shows > 0 && (!v->created_at || !v->archived_at)) return fail(PIE_ERR_INVALID_ARG, "created_at / archived_at is NULL");
+  if (reinterpret_cast<uintptr_t>(scratch) & 255) return fail(PIE_ERR_INVALID_ARG, "scratch must be 256-byte aligned");
+  PIE_CUDA(pie::launch_show_payloads(*v, head, head_len, tail, tail_len, doc_offsets, out_data, out_data ? out_capacity : 0,
+                                     (unsigned long long*)total_bytes_dev, status_dev, scratch, (cudaStream_t)stream));
+  return PIE_OK;
+}
+
 /* ---- _getTimestamp of the documents' time fields; archive maintenance decisions ---------------------------- */
 int pie_get_timestamps_dev(const pie_archive_view* v, const pie_json_docs* docs, int32_t tz_offset_minutes,
                            const pie_doc_times* out, int32_t* status_dev, void* stream) {

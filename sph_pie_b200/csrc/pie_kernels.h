@@ -63,6 +63,12 @@ uint64_t ingest_fill_scratch_bytes(int64_t n_entries);
 cudaError_t launch_ingest_fill(const pie_json_docs& dev_docs, const void* scratch, const uint8_t* doc_status,
                                const pie_archive_table& dev_table, void* fill_scratch, cudaStream_t stream);
 
+// show_payload.cu: the schemaVersion 2 payload document of every show
+uint64_t show_payload_scratch_bytes(int64_t n_shows);
+cudaError_t launch_show_payloads(const pie_archive_view& dev_view, const uint8_t* head, int head_len, const uint8_t* tail,
+                                 int tail_len, int64_t* doc_offsets, uint8_t* out, uint64_t capacity,
+                                 unsigned long long* total, int32_t* status, void* scratch, cudaStream_t stream);
+
 // archive_maintenance.cu: _getTimestamp of the documents' time fields; the archive / purge decisions
 cudaError_t launch_get_timestamps(const pie_archive_view& dev_view, const pie_json_docs* dev_docs, int32_t tz_offset_minutes,
                                   const pie_doc_times& out, int32_t* status, unsigned long long* err_scratch,

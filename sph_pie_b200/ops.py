@@ -800,3 +800,47 @@ def archive_expired(created: torch.Tensor, now_ms: float, tz_offset_minutes: int
     _lib.check(_lib.load().pie_archive_expired_dev(created.data_ptr() if n else None, n, float(now_ms), tz_offset_minutes,
                                                    out.data_ptr() if n else None, _stream_ptr()))
     return out[:n]
+
+
+# ---- the schemaVersion 2 show payload (pie_show_payloads_dev) ---------------------------------------------------------
+@dataclass
+class ShowPayloads:
+    """One JSON document per show: document s = data[doc_offsets[s] : doc_offsets[s+1]]."""
+    doc_offsets: torch.Tensor  # int64 [n_shows + 1]
+    data: torch.Tensor         # uint8
+
+    def documents(self):
+        o = self.doc_offsets.cpu().tolist()
+        b = bytes(self.data.cpu().numpy())
+        return [b[o[i]:o[i + 1]].decode("utf-8") for i in range(len(o) - 1)]
+
+
+def show_payloads(table: ArchiveTable, head: bytes, tail: bytes) -> ShowPayloads:
+    """JSON.stringify of dispatchShowEvent's schemaVersion 2 payload (webhookDispatcher.js:545-584) for every show of a
+    CUDA-resident table; `head` / `tail` are the serialised texts around the per-show part (webhook.payload_frame)."""
+    _lib.ensure_init()
+    assert table.is_cuda
+    lib, dev, S = _lib.load(), table.device, table.n_shows
+    h = torch.tensor(list(head) or [0], dtype=torch.uint8, device=dev)
+    t = torch.tensor(list(tail) or [0], dtype=torch.uint8, device=dev)
+    offs = torch.zeros(S + 1, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    scratch = torch.empty(int(lib.pie_show_payloads_scratch_bytes(S)) + 256, dtype=torch.uint8, device=dev)
+    sptr = (scratch.data_ptr() + 255) & ~255
+    view = table.view()
+
+    def call(out, cap):
+        _lib.check(lib.pie_show_payloads_dev(C.byref(view), h.data_ptr(), len(head), t.data_ptr(), len(tail), offs.data_ptr(),
+                                             out, cap, total.data_ptr(), status.data_ptr(), sptr, _stream_ptr()))
+        code, show = status.cpu().tolist()
+        if code == _lib.PIE_ERR_SCHEMA:
+            raise _lib.SchemaError(code, f"show {show}: a time field holds a text, an array or an object (the table does not hold the value)")
+        if code:
+            raise _lib.PieError(code, f"show payloads failed at show {show}")
+
+    call(None, 0)
+    n = int(total.cpu())
+    data = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    call(data.data_ptr(), n)
+    return ShowPayloads(offs, data[:n])

@@ -9,6 +9,9 @@ the pure re-shaping functions (object <-> column order) are plain host code, as 
     archiveEntryPayloadBodies(show)      JSON.stringify(buildArchiveEntryPayload(show, entry)) for every entry: the
                                          bodies dispatchShowEvent('show.archived') posts one by one (:520-540)
     buildArchiveEntryPayload(show, entry)  :315-330, as an object (parsed back from the GPU's JSON text)
+    showEventPayloadBodies(shows, event, ...)  JSON.stringify of the schemaVersion 2 payload dispatchShowEvent builds for
+                                         every other event (:545-584), one request body per show
+    buildShowSummary(show)               :472-488, as an object (parsed back from the GPU's JSON text)
 """
 from __future__ import annotations
 
@@ -67,3 +70,43 @@ def buildArchiveEntryPayload(show: Optional[dict] = None, entry: Optional[dict] 
     s = dict(show) if isinstance(show, dict) else {}
     s["entries"] = [entry if isinstance(entry, dict) else {}]
     return json.loads(archiveEntryPayloadBodies(s)[0])
+
+
+def _json_quote(text: str) -> str:
+    """QuoteJSONString (ECMA-262 25.5.2.3) of a caller-supplied string (event name, URL ...)."""
+    import json
+
+    return json.dumps(text, ensure_ascii=False)
+
+
+def payload_frame(event: str, dispatchedAt: str, targetUrl: str, targetMethod: str, meta: Optional[dict] = None):
+    """The texts around the per-show part of the schemaVersion 2 payload (webhookDispatcher.js:557-565, :580-583):
+    (head, tail) as UTF-8 bytes.  `meta` is normalizeMeta's result: a non-empty plain object is appended, anything
+    else leaves the key out; its values go through Python's json (strings, numbers, booleans, null, nesting)."""
+    import json
+
+    head = ('{"event":' + _json_quote(event) + ',"schemaVersion":2,"dispatchedAt":' + _json_quote(dispatchedAt) +
+            ',"target":{"url":' + _json_quote(targetUrl) + ',"method":' + _json_quote(targetMethod) + '},')
+    tail = "}"
+    if isinstance(meta, dict) and meta:
+        tail = ',"meta":' + json.dumps(meta, ensure_ascii=False, separators=(",", ":")) + "}"
+    return head.encode("utf-8"), tail.encode("utf-8")
+
+
+def showEventPayloadBodies(shows: List[Optional[dict]], event: str, dispatchedAt: str, targetUrl: str, targetMethod: str,
+                           meta: Optional[dict] = None, device="cuda") -> List[str]:
+    """The request body dispatchShowEvent(event, show, meta) posts for every show (any event but 'show.archived'), in one
+    launch.  Shows are provider-normalised documents (their entries carry the 17 stored keys)."""
+    from .ops import show_payloads
+
+    table = pack_shows(shows).to(device)
+    head, tail = payload_frame(event, dispatchedAt, targetUrl, targetMethod, meta)
+    return show_payloads(table, head, tail).documents()
+
+
+def buildShowSummary(show: Optional[dict] = None, device="cuda") -> dict:
+    """buildShowSummary(show) (reference :472-488), computed on the GPU like the bulk call and parsed back."""
+    import json
+
+    body = showEventPayloadBodies([show if isinstance(show, dict) else {}], "", "", "", "", None, device)[0]
+    return json.loads(body)["show"]

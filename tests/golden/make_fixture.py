@@ -39,6 +39,34 @@ STORED_TEXT = ('{"id":"simulation-show","date":"2024-07-04","time":"21:00","labe
                '"notes":"Green across the board"}]}')
 assert po.js_json_stringify({**show, "entries": [entry]}) == STORED_TEXT
 assert po.map_archive_row(STORED_TEXT) == {**show, "entries": [entry]}
+# the schemaVersion 2 body dispatchShowEvent('show.updated', {...show, entries: [entry]}) would post
+# (server/webhookDispatcher.js:545-584), written out by hand from the object literals there:
+COLS = ('["showId","showDate","showTime","showLabel","crew","leadPilot","monkeyLead","showNotes","entryId","unitId","planned",'
+        '"launched","status","primaryIssue","subIssue","otherDetail","severity","rootCause","actions","operator","batteryId",'
+        '"delaySec","commandRx","notes"]')
+SUMMARY = ('{"id":"simulation-show","label":"Independence Demo","date":"2024-07-04","time":"21:00","crew":["Alex","Nazar"],'
+           '"leadPilot":"Alex","monkeyLead":"Nazar","notes":"Verification run","createdAt":null,"updatedAt":null,'
+           '"archivedAt":null,"deletedAt":null}')
+SHOW_PAYLOAD_JSON = (
+    '{"event":"show.updated","schemaVersion":2,"dispatchedAt":"2024-07-05T04:00:00.000Z",'
+    '"target":{"url":"http://127.0.0.1:4101/hook","method":"POST"},'
+    '"table":{"columns":' + COLS + ',"rows":[["simulation-show","2024-07-04","21:00","Independence Demo","Alex|Nazar","Alex",'
+    '"Nazar","Verification run","entry-001","Drone-01","Yes","Yes","Completed","","","","","","Logged only","Alex","B-12",0,"Yes",'
+    '"Green across the board"]]},'
+    '"csv":{"header":' + COLS + ',"rows":["simulation-show,2024-07-04,21:00,Independence Demo,Alex|Nazar,Alex,Nazar,'
+    'Verification run,entry-001,Drone-01,Yes,Yes,Completed,,,,,,Logged only,Alex,B-12,0,Yes,Green across the board"]},'
+    '"message":{"show":' + SUMMARY + ',"entries":[{"showId":"simulation-show","showDate":"2024-07-04","showTime":"21:00",'
+    '"showLabel":"Independence Demo","crew":"Alex|Nazar","leadPilot":"Alex","monkeyLead":"Nazar","showNotes":"Verification run",'
+    '"entryId":"entry-001","unitId":"Drone-01","planned":"Yes","launched":"Yes","status":"Completed","primaryIssue":"",'
+    '"subIssue":"","otherDetail":"","severity":"","rootCause":"","actions":"Logged only","operator":"Alex","batteryId":"B-12",'
+    '"delaySec":0,"commandRx":"Yes","notes":"Green across the board"}]},'
+    '"show":' + SUMMARY + ','
+    '"entries":[{"id":"entry-001","unitId":"Drone-01","planned":"Yes","launched":"Yes","status":"Completed",'
+    '"actions":["Logged only"],"operator":"Alex","batteryId":"B-12","delaySec":0,"commandRx":"Yes",'
+    '"notes":"Green across the board"}]}')
+assert po.show_payload_json("show.updated", {**show, "entries": [entry]}, "2024-07-05T04:00:00.000Z",
+                            "http://127.0.0.1:4101/hook", "POST") == SHOW_PAYLOAD_JSON
+assert json.loads(SHOW_PAYLOAD_JSON)["schemaVersion"] == 2
 doc = {
     "source": "scripts/simulate-webhook.js:42-65 (show, entry); expected_* hand-derived, see make_fixture.py",
     "export_columns": po.EXPORT_COLUMNS,
@@ -50,6 +78,7 @@ doc = {
     "expected_archive_entry_payload": po.build_archive_entry_payload(show, entry),
     "expected_archive_payload_json": PAYLOAD_JSON,
     "stored_text": STORED_TEXT,
+    "expected_show_payload_json": SHOW_PAYLOAD_JSON,
     "expected_show_stats": po.compute_archive_show_stats({**show, "entries": [entry]}),
 }
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "webhook_fixture.json"), "w") as f:

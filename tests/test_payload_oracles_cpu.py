@@ -78,3 +78,35 @@ def test_c_payload_edge_rows(built):
     assert rows[1] == ('{"showDate":"d\\"q","showTime":"t\\\\b","showNumber":"l\\nf","leadPilot":"\\u0001",'
                        '"monkeyLead":"\\u001f\x7f","operator":"","monkeyId":"","planned":false,"launched":false,'
                        '"commandReceived":false,"primaryIssue":"","subIssue":""}')
+
+
+def test_show_payload_oracle_on_the_fixture_and_its_rules():
+    """The schemaVersion 2 payload (reference server/webhookDispatcher.js:460-496, :545-584): the hand-written body of
+    the reference's fixture, and the rules that differ from the row builders (`?? null` against `|| ''`)."""
+    import os
+
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "webhook_fixture.json")))
+    show = {**fx["show"], "entries": [fx["entry"]]}
+    body = po.show_payload_json("show.updated", show, "2024-07-05T04:00:00.000Z", "http://127.0.0.1:4101/hook", "POST")
+    assert body == fx["expected_show_payload_json"]
+    parsed = json.loads(body)
+    assert list(parsed) == ["event", "schemaVersion", "dispatchedAt", "target", "table", "csv", "message", "show", "entries"]
+    assert parsed["table"]["rows"][0] == fx["expected_table_row"] and parsed["csv"]["rows"][0] == fx["expected_csv_row"]
+    assert parsed["message"]["entries"][0] == fx["expected_message"]
+    # buildShowSummary: texts `|| ''`, timestamps `?? null` (0 and false survive, undefined and null become null)
+    s = po.build_show_summary({"id": 0, "label": None, "crew": "x", "createdAt": 0, "updatedAt": False, "archivedAt": None})
+    assert s == {"id": "", "label": "", "date": "", "time": "", "crew": [], "leadPilot": "", "monkeyLead": "", "notes": "",
+                 "createdAt": 0, "updatedAt": False, "archivedAt": None, "deletedAt": None}
+    # normalizeEntryList: a missing / non-array actions becomes [], an existing key keeps its place, a new one goes last
+    assert po.normalize_entry_list({"entries": [{"a": 1, "actions": "x", "b": 2}, {"a": 1}, None, 5]}) == [
+        {"a": 1, "actions": [], "b": 2}, {"a": 1, "actions": []}, {"actions": []}, {"actions": []}]
+    assert list(po.normalize_entry_list({"entries": [{"a": 1, "actions": "x", "b": 2}]})[0]) == ["a", "actions", "b"]
+    assert po.normalize_entry_list({"entries": {"0": 1}}) == [] and po.normalize_entry_list(None) == []
+    # meta: only a non-empty plain object is attached; a number that is not finite is null in JSON
+    assert "meta" not in po.dispatch_show_payload("e", show, "t", "u", "m", {})
+    assert "meta" not in po.dispatch_show_payload("e", show, "t", "u", "m", [1])
+    assert po.dispatch_show_payload("e", show, "t", "u", "m", {"k": 1})["meta"] == {"k": 1}
+    nan_show = {"entries": [{"delaySec": float("nan"), "status": "Abort"}, {"delaySec": float("inf")}]}
+    p = json.loads(po.show_payload_json("e", nan_show, "t", "u", "m"))
+    assert p["table"]["rows"][0][21] is None and p["entries"][1]["delaySec"] is None
+    assert p["csv"]["rows"][0].split(",")[21] == "NaN" and p["csv"]["rows"][1].split(",")[21] == "Infinity"
