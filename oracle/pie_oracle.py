@@ -925,7 +925,7 @@ def _nullish(a, b):
     return b if a is None else a
 
 
-def map_archive_row_all(row, tz_offset_minutes: int = 0):
+def map_archive_row_all(row, tz_offset_minutes: int = 0, provider: str = "sql"):
     """_mapArchiveRow(row) (sqlProvider.js:892-926) in full: the row's archived_at / created_at / deleted_at columns
     against the document's own fields, every one through _getTimestamp (null -> 0, numeric text -> its number, an
     ISO date-time text -> Date.parse); deletedAt set or deleted; entries / crew made arrays."""
@@ -939,7 +939,10 @@ def map_archive_row_all(row, tz_offset_minutes: int = 0):
     get = lambda o, k: o[k] if k in o else UNDEFINED  # noqa: E731
     ts = lambda v: get_timestamp_tz(v, tz_offset_minutes)  # noqa: E731
     archived = _nullish(ts(get(row, "archived_at")), ts(get(show, "archivedAt")))
-    created = _nullish(ts(get(show, "createdAt")), ts(get(row, "created_at")))
+    if provider == "postgres":  # postgresProvider.js:721 asks the row first
+        created = _nullish(ts(get(row, "created_at")), ts(get(show, "createdAt")))
+    else:                       # sqlProvider.js:906-907
+        created = _nullish(ts(get(show, "createdAt")), ts(get(row, "created_at")))
     deleted = _nullish(ts(get(row, "deleted_at")), ts(get(show, "deletedAt")))
     if archived is not None:
         show["archivedAt"] = archived

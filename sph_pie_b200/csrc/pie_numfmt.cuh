@@ -8,7 +8,7 @@
 // Notation: ECMA-262's rules (fixed for 1e-7 <= |x| < 1e21, exponent form otherwise).
 //
 // Every function is __host__ __device__ so the same code is unit-tested on the CPU
-// (tests/native/numfmt_host_test.cu against printf/strtod and Python's repr) and runs in the
+// (tests/native/numfmt_host.cpp against printf/strtod and Python's repr) and runs in the
 // export kernels.  This is used for entry.delaySec in buildTableRow -> csvEscape(String(value))
 // (reference server/webhookDispatcher.js:301, :333).
 #pragma once

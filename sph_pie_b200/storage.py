@@ -5,6 +5,7 @@ are and come back as the columnar archive table the analytics and export operato
 materialised as an object.  There is no CPU fallback."""
 from __future__ import annotations
 
+import datetime
 import math
 import re
 from typing import Iterable, Tuple, Union
@@ -73,6 +74,11 @@ def _row_timestamp(v, tz_offset_minutes: int = 0) -> float:
     if isinstance(v, (int, float)):
         f = float(v)
         return f if math.isfinite(f) else math.nan
+    if isinstance(v, datetime.datetime):  # a TIMESTAMPTZ column of the Postgres provider: pg hands back a Date, Number(date) = its time value
+        if v.tzinfo is None:
+            v = v.replace(tzinfo=datetime.timezone.utc)
+        delta = v - datetime.datetime(1970, 1, 1, tzinfo=datetime.timezone.utc)
+        return float(delta.days * 86400000 + delta.seconds * 1000 + delta.microseconds // 1000)
     if isinstance(v, str):
         t = v.strip(_JS_WS)
         if t == "":
@@ -97,7 +103,8 @@ def _text(row: Row):
     return row
 
 
-def mapArchiveRows(rows: Iterable[Row], device="cuda", tz_offset_minutes: int = 0) -> Tuple[ArchiveTable, torch.Tensor]:
+def mapArchiveRows(rows: Iterable[Row], device="cuda", tz_offset_minutes: int = 0,
+                   provider: str = "sql") -> Tuple[ArchiveTable, torch.Tensor]:
     """rows.map(row => this._mapArchiveRow(row)) for a batch (sqlProvider.js:892-926): (table, dropped) where dropped[i]
     is True for the rows the reference maps to null (text that is not JSON, or not an object); their table rows are
     empty shows.  Rows given as dicts may carry the `archived_at` / `created_at` / `deleted_at` columns of the SELECT.
@@ -106,6 +113,7 @@ def mapArchiveRows(rows: Iterable[Row], device="cuda", tz_offset_minutes: int = 
       archivedAt = _getTimestamp(row.archived_at) ?? _getTimestamp(show.archivedAt)   set when not null
       createdAt  = _getTimestamp(show.createdAt) ?? _getTimestamp(row.created_at)     set when not null
       deletedAt  = _getTimestamp(row.deleted_at) ?? _getTimestamp(show.deletedAt)     set when not null, else deleted
+    provider="postgres" restates postgresProvider.js:711-741 instead, which prefers the ROW's created_at.
     The table stays in HBM for the operators that follow; there is no CPU path."""
     from . import _lib
 
@@ -127,7 +135,10 @@ def mapArchiveRows(rows: Iterable[Row], device="cuda", tz_offset_minutes: int = 
         return torch.where(torch.isfinite(a), a, b)
 
     archived = torch.where(keep, first(column("archived_at"), times.archived_at), nan)
-    created = torch.where(keep, first(times.created_at, column("created_at")), nan)
+    if provider == "postgres":
+        created = torch.where(keep, first(column("created_at"), times.created_at), nan)
+    else:
+        created = torch.where(keep, first(times.created_at, column("created_at")), nan)
     deleted = torch.where(keep, first(column("deleted_at"), times.deleted_at), nan)
     kind = table.time_kind.clone()
     number = torch.full_like(kind[:, 0], _lib.TK_NUMBER)

@@ -73,8 +73,8 @@ def test_unsupported_time_texts_fail_loudly(cuda):
     assert ops.get_timestamps(table, docs, 0).created_at.tolist() == [5.0]
 
 
-@pytest.mark.parametrize("tz", [0, -420])
-def test_map_archive_rows_in_full(cuda, tz):
+@pytest.mark.parametrize("tz,provider", [(0, "sql"), (-420, "sql"), (0, "postgres")])
+def test_map_archive_rows_in_full(cuda, tz, provider):
     """storage.mapArchiveRows against _mapArchiveRow as the oracle restates it, row columns included."""
     rng = random.Random(5)
     cols = [None, "1704067200000", " 1704067200001 ", "", "2024-02-03T04:05:06.007Z", 17.5, "0x10"]
@@ -90,8 +90,8 @@ def test_map_archive_rows_in_full(cuda, tz):
                 row[c] = rng.choice(cols)
         rows.append(row)
     rows += [{"data": "broken", "created_at": "5"}, {"data": "[]", "archived_at": "7"}, {"data": None}, "null", '{"id":"plain text row"}']
-    table, dropped = storage.mapArchiveRows(rows, cuda, tz)
-    want = [po.map_archive_row_all(r if isinstance(r, dict) else {"data": r}, tz) for r in rows]
+    table, dropped = storage.mapArchiveRows(rows, cuda, tz, provider)
+    want = [po.map_archive_row_all(r if isinstance(r, dict) else {"data": r}, tz, provider) for r in rows]
     assert dropped.cpu().tolist() == [w is None for w in want]
     created, archived, deleted = (_nan_to_none(t) for t in (table.created_at, table.archived_at, table.deleted_at))
     kinds = table.time_kind.cpu().tolist()
