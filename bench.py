@@ -172,20 +172,62 @@ def cpu_baseline_run(host_table, tz, nthreads, min_seconds=1.0, max_reps=8):
             return host_table.n_entries * reps / dt, reps, dt
 
 
-def make_table(args, rank, local):
-    """The synthetic archive of one rank, the SAME table in both arms (`--impl b200` and `--impl reference`): it is
-    generated with torch's CUDA generator when a GPU is visible (both arms run on the same box, so seed -> table is
-    one function) and with the CPU generator otherwise (`data_generator` in the config says which).  Each rank owns a
-    disjoint range of days (weak scaling, no data-path collective)."""
+def make_table(args, rank, world, local):
+    """The synthetic archive this rank works on, the SAME table in both arms (`--impl b200` and `--impl reference`): it
+    is generated with torch's CUDA generator when a GPU is visible (both arms run on the same box, so seed -> table is
+    one function) and with the CPU generator otherwise (`data_generator` in the config says which).
+    N = 1: one segment of `--shows` shows.  N > 1: ONE archive of N such segments (weak scaling), cut into N day ranges
+    balanced by entries (sharding.plan_day_shards on the archive's skeleton); a rank assembles its own range, which
+    usually spans two stored segments (sharding.assemble_shard).  No data-path collective either way.
+    Returns (table, generator, (s0, s1))."""
     import torch
 
+    from sph_pie_b200.sharding import assemble_shard, segment_skeleton
     from sph_pie_b200.synth import synth_archive
 
-    days_per_rank = (args.shows + 4) // 5
     gen_dev = torch.device("cuda", local) if torch.cuda.is_available() else torch.device("cpu")
-    table = synth_archive(args.shows, seed=1234 + rank, device=gen_dev,
-                          start_ms=1704067200000 + rank * days_per_rank * 86400000)
-    return table, ("torch cuda generator" if gen_dev.type == "cuda" else "torch cpu generator")
+    generator = "torch cuda generator" if gen_dev.type == "cuda" else "torch cpu generator"
+    if world == 1:
+        return synth_archive(args.shows, seed=1234, device=gen_dev), generator, (0, args.shows)
+    seeds = [1234 + k for k in range(world)]
+    eo, day = segment_skeleton(args.shows, seeds, gen_dev)
+    table, span = assemble_shard(args.shows, seeds, eo, day, rank, world, gen_dev)
+    return table, generator, span
+
+
+def bind_host_side(local: int, world: int):
+    """Give this rank its own CPUs before any pinned buffer is allocated: the CPUs of the GPU's NUMA node (sysfs), split
+    evenly among the local ranks on that node; all CPUs split evenly when the platform reports no node (a VM).  The
+    end-to-end leg is bound by the host side of the PCIe copies, and N ranks sharing one set of cores and one first-touch
+    node is the worst case."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        nodes = []
+        for i in range(world):
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(i)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            path = f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node"
+            nodes.append(int(open(path).read()) if os.path.exists(path) else -1)
+        allowed = sorted(os.sched_getaffinity(0))
+        node = nodes[local]
+        cpus = allowed
+        if node >= 0 and os.path.exists(f"/sys/devices/system/node/node{node}/cpulist"):
+            on_node = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                on_node.update(range(int(lo), int(hi or lo) + 1))
+            cpus = [c for c in allowed if c in on_node] or allowed
+        peers = [r for r in range(world) if nodes[r] == node]
+        k, n = peers.index(local), len(peers)
+        mine = cpus[k * len(cpus) // n:(k + 1) * len(cpus) // n] or cpus
+        os.sched_setaffinity(0, mine)
+        info = {"numa_node": node, "cpus": f"{mine[0]}-{mine[-1]}", "n_cpus": len(mine), "ranks_on_node": n}
+    except Exception as e:  # no NVML / no sysfs: stay where the launcher put us, and say so
+        info["error"] = repr(e)
+    return info
 
 
 def run_reference(args):
@@ -199,8 +241,7 @@ def run_reference(args):
 
     oracle_c.build()
     threads = oracle_c.max_threads()
-    shows = args.shows
-    table, generator = make_table(args, 0, local)
+    table, generator, _ = make_table(args, 0, world, local)  # at N > 1: rank 0's day range of the one archive
     table = table.to("cpu")
     warmup = max(args.warmup, 3)
     step = CpuStep(table, args.tz, threads)  # construction = one warm pass
@@ -211,6 +252,7 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     value = table.n_entries * args.steps / dt
+    shows = table.n_shows
     sample = f"{shows} shows / {table.n_entries} entries per step, C port of the path (oracle/pie_oracle.c), " \
              f"show statistics and export rows on {threads} threads, daily grouping on 1"
     print(json.dumps({
@@ -347,8 +389,9 @@ def main():
 
     _lib.init(local)
     lib = _lib.load()
+    affinity = bind_host_side(local, world)  # before any pinned allocation: first touch decides where host pages live
 
-    table, generator = make_table(args, rank, local)
+    table, generator, span = make_table(args, rank, world, local)
     S, E = table.n_shows, table.n_entries
     warmup = max(args.warmup, 3)
     bufs = ops.DailyBuffers(S, E, dev)
@@ -510,6 +553,46 @@ def main():
                         "what": "pie_archive_step_host with pageable (malloc'd) caller buffers in and out"}
         del pout, p_off, p_csv
         note(f"pageable end-to-end: {p_s * 1e3:.1f} ms per step")
+    # the host-side ceiling of that leg: nothing but the same bytes over PCIe — pinned H2D and D2H at once, on every rank
+    # at the same time (what N ranks sharing one host can move at best)
+    up = torch.empty(max(h2d, 1), dtype=torch.uint8, pin_memory=True)
+    down = torch.empty(max(d2h, 1), dtype=torch.uint8, pin_memory=True)
+    d_up, d_down = torch.empty_like(up, device=dev), torch.empty_like(down, device=dev)
+    s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copy_only():
+        with torch.cuda.stream(s_up):
+            d_up.copy_(up, non_blocking=True)
+        with torch.cuda.stream(s_down):
+            down.copy_(d_down, non_blocking=True)
+        torch.cuda.synchronize()
+
+    copy_only()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        copy_only()
+    ceiling_s = (time.perf_counter() - t0) / 3
+    del up, down, d_up, d_down
+    my_e2e_ms = e2e_s / e2e_steps * 1e3
+    per_rank_ms, per_rank_ceiling_ms, spans = [my_e2e_ms], [ceiling_s * 1e3], [list(span)]
+    n_groups_total, days_disjoint = n_groups, True
+    if world > 1:
+        import torch.distributed as dist
+
+        mine = torch.tensor([my_e2e_ms, ceiling_s * 1e3, float(span[0]), float(span[1]), float(n_groups),
+                             float(bufs.group_day_start[0]) if n_groups else 0.0,
+                             float(bufs.group_day_start[n_groups - 1]) if n_groups else 0.0], dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        every = [x.cpu().tolist() for x in every]
+        per_rank_ms = [x[0] for x in every]
+        per_rank_ceiling_ms = [x[1] for x in every]
+        spans = [[int(x[2]), int(x[3])] for x in every]
+        n_groups_total = int(sum(x[4] for x in every))
+        # the stitched daily table is the ranks' tables one after the other: their day ranges must not meet
+        days_disjoint = all(every[r][6] < every[r + 1][5] for r in range(world - 1) if every[r][4] and every[r + 1][4])
+        ceiling_s = max(per_rank_ceiling_ms) / 1e3
     if world > 1:
         import torch.distributed as dist
 
@@ -566,7 +649,14 @@ def main():
         "config": workload_config(args, S, E, generator),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "pie_archive_step_host (statistics + daily summaries + CSV rows; pinned host buffers in and out)",
-                "pageable": e2e_pageable},
+                "pageable": e2e_pageable, "per_rank_ms": per_rank_ms,
+                "copy_ceiling": {"value": total_entries / ceiling_s, "unit": UNIT, "per_rank_ms": per_rank_ceiling_ms,
+                                 "what": "the same H2D + D2H bytes per rank as plain pinned copies, both directions at once, "
+                                         "all ranks at the same time: the host side's best case for this leg"},
+                "host_binding": affinity},
+        "sharding": {"archive": f"one archive of {world} segment(s) x {args.shows} shows, day ranges balanced by entries "
+                                "(sharding.plan_day_shards); no data-path collective",
+                     "show_ranges": spans, "n_groups_total": n_groups_total, "day_ranges_disjoint": days_disjoint},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "parity_checked": parity,

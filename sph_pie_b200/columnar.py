@@ -290,3 +290,65 @@ def pack_shows(shows: List[Optional[dict]]) -> ArchiveTable:
         deleted_at=torch.tensor(deleted, dtype=torch.float64),
         time_kind=torch.tensor(kinds, dtype=torch.uint8).reshape(len(shows), 4),
     )
+
+
+def _concat_strcols(cols: List[StrCol], rows: List[int]) -> StrCol:
+    """Rows [0, rows[i]) of every column, one after the other; offsets rebased onto one compact heap."""
+    offs, datas, base = [], [], 0
+    for c, n in zip(cols, rows):
+        o = c.offsets[:n + 1].to(torch.int64)
+        first, last = int(o[0]), int(o[n])
+        offs.append(o[:n] - first + base)
+        datas.append(c.data[first:last])
+        base += last - first
+    if base >= 2 ** 31:
+        raise ValueError("string column exceeds 2 GiB: split the batch")
+    dev = cols[0].offsets.device
+    offs.append(torch.tensor([base], dtype=torch.int64, device=dev))
+    return StrCol(torch.cat(offs).to(torch.int32), torch.cat(datas) if datas else torch.zeros(0, dtype=torch.uint8, device=dev))
+
+
+def _concat_lists(cols: List[StrListCol], rows: List[int]) -> StrListCol:
+    lo, items, item_rows, base = [], [], [], 0
+    for c, n in zip(cols, rows):
+        l = c.list_offsets[:n + 1].to(torch.int64)
+        first, last = int(l[0]), int(l[n])
+        lo.append(l[:n] - first + base)
+        items.append(StrCol(c.items.offsets[first:last + 1], c.items.data))
+        item_rows.append(last - first)
+        base += last - first
+    dev = cols[0].list_offsets.device
+    lo.append(torch.tensor([base], dtype=torch.int64, device=dev))
+    return StrListCol(torch.cat(lo).to(torch.int32), _concat_strcols(items, item_rows))
+
+
+def concat_tables(parts: List[ArchiveTable]) -> ArchiveTable:
+    """The shows of several tables (slices included), one after the other, as one compact table on the parts' device:
+    what a rank whose day range spans more than one stored segment assembles (sharding.py)."""
+    parts = [p for p in parts if p.n_shows > 0] or parts[:1]
+    S = [p.n_shows for p in parts]
+    E = [p.n_entries for p in parts]
+    dev = parts[0].entry_offsets.device
+    eo, base = [], 0
+    for p in parts:
+        o = p.entry_offsets[:p.n_shows + 1].to(torch.int64)
+        eo.append(o[:p.n_shows] - int(o[0]) + base)
+        base += p.n_entries
+    eo.append(torch.tensor([base], dtype=torch.int64, device=dev))
+
+    def opt(name):
+        vals = [getattr(p, name) for p in parts]
+        return None if any(v is None for v in vals) else torch.cat([v[:n] for v, n in zip(vals, S)])
+
+    return ArchiveTable(
+        n_shows=sum(S), n_entries=sum(E), entry_offsets=torch.cat(eo).to(torch.int32),
+        show_cols={k: _concat_strcols([p.show_cols[k] for p in parts], S) for k in parts[0].show_cols},
+        crew=_concat_lists([p.crew for p in parts], S),
+        created_at=torch.cat([p.created_at[:n] for p, n in zip(parts, S)]),
+        archived_at=torch.cat([p.archived_at[:n] for p, n in zip(parts, S)]),
+        entry_cols={k: _concat_strcols([p.entry_cols[k] for p in parts], E) for k in parts[0].entry_cols},
+        actions=_concat_lists([p.actions for p in parts], E),
+        delay_sec=torch.cat([p.delay_sec[:n] for p, n in zip(parts, E)]),
+        delay_valid=torch.cat([p.delay_valid[:n] for p, n in zip(parts, E)]),
+        entry_ts=torch.cat([p.entry_ts[:n] for p, n in zip(parts, E)]),
+        updated_at=opt("updated_at"), deleted_at=opt("deleted_at"), time_kind=opt("time_kind"))

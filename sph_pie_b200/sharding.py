@@ -67,6 +67,48 @@ def plan_day_shards(entry_offsets: torch.Tensor, show_day: torch.Tensor, world: 
     return ShardPlan(bounds)
 
 
+def segment_skeleton(shows_per_segment: int, seeds: List[int], device):
+    """(entry_offsets int64[S+1], day int64[S]) of ONE synthetic archive made of len(seeds) stored segments —
+    segment k = synth_archive(shows_per_segment, seed=seeds[k]) moved to its own range of days — without building any
+    of them (synth.synth_skeleton): what every rank needs to plan the day shards."""
+    from .synth import synth_skeleton
+
+    days_per_segment = (shows_per_segment + 4) // 5
+    n_per, days = [], []
+    for k, seed in enumerate(seeds):
+        n, d = synth_skeleton(shows_per_segment, seed, device)
+        n_per.append(n)
+        days.append(d + k * days_per_segment)
+    n_per = torch.cat(n_per)
+    eo = torch.zeros(n_per.numel() + 1, dtype=torch.int64, device=n_per.device)
+    torch.cumsum(n_per, 0, out=eo[1:])
+    return eo, torch.cat(days)
+
+
+def assemble_shard(shows_per_segment: int, seeds: List[int], entry_offsets: torch.Tensor, day: torch.Tensor, rank: int,
+                   world: int, device, start_ms: int = 1704067200000):
+    """This rank's day range of the segmented archive as one compact table on `device`: the shard plan comes from the
+    skeleton; only the segments the range touches are generated (a range balanced by entries rarely ends on a segment
+    border), sliced and joined (columnar.concat_tables).  Returns (table, (s0, s1))."""
+    from .columnar import concat_tables
+    from .synth import synth_archive
+
+    s0, s1 = plan_day_shards(entry_offsets, day, world).range_of(rank)
+    days_per_segment = (shows_per_segment + 4) // 5
+
+    def segment(k):
+        return synth_archive(shows_per_segment, seed=seeds[k], device=device, start_ms=start_ms + k * days_per_segment * 86400000)
+
+    parts = []
+    for k in range(len(seeds)):
+        a, b = max(s0, k * shows_per_segment), min(s1, (k + 1) * shows_per_segment)
+        if a < b:
+            parts.append(segment(k).slice_shows(a - k * shows_per_segment, b - k * shows_per_segment))
+    if not parts:  # an empty range (more ranks than days): an empty table of the right shape
+        parts.append(segment(0).slice_shows(0, 0))
+    return concat_tables(parts), (s0, s1)
+
+
 def concat_daily(parts: List[dict]) -> dict:
     """Concatenate per-rank daily tables (rank order == day order)."""
     keys = ("group_day_start", "summary_f64", "summary_count")
@@ -77,6 +119,9 @@ def concat_daily(parts: List[dict]) -> dict:
     out["group_sizes"] = torch.cat([p["group_sizes"] for p in parts])
     out["stats_i32"] = torch.cat([p["stats_i32"] for p in parts], dim=1)
     out["stats_f64"] = torch.cat([p["stats_f64"] for p in parts], dim=1)
+    for extra in set(parts[0]) - set(out) - {"range"}:  # whatever else the ranks hand over (e.g. their CSV bytes)
+        if isinstance(parts[0][extra], torch.Tensor):
+            out[extra] = torch.cat([p[extra] for p in parts])
     del keys
     return out
 

@@ -118,7 +118,8 @@ def mapArchiveRows(rows: Iterable[Row], device="cuda", tz_offset_minutes: int = 
     from . import _lib
 
     rows = list(rows)
-    docs = ops.JsonDocs.from_texts([_text(r) for r in rows]).to(device)
+    want_host = str(device) == "cpu"  # the work is the GPU's either way; "cpu" only says where the table should end up
+    docs = ops.JsonDocs.from_texts([_text(r) for r in rows]).to("cuda" if want_host else device)
     table, status = ops.ingest_json(docs)
     dropped = status.bool()
     dev = table.created_at.device
@@ -148,6 +149,8 @@ def mapArchiveRows(rows: Iterable[Row], device="cuda", tz_offset_minutes: int = 
     kind[:, _lib.TF_CREATED] = torch.where(torch.isfinite(created), number, kind[:, _lib.TF_CREATED])
     kind[:, _lib.TF_DELETED] = torch.where(torch.isfinite(deleted), number, torch.zeros_like(number))
     table.archived_at, table.created_at, table.deleted_at, table.time_kind = archived, created, deleted, kind
+    if want_host:
+        return table.to("cpu"), dropped.cpu()
     return table, dropped
 
 

@@ -256,6 +256,17 @@ def synth_archive(n_shows: int, seed: int = 0, device="cpu", max_entries: int = 
         delay_sec=delay, delay_valid=valid.to(torch.uint8), entry_ts=entry_ts)
 
 
+def synth_skeleton(n_shows: int, seed: int = 0, device="cpu", max_entries: int = 21, shows_per_day: int = 5):
+    """(entries per show int64[n], day index int64[n]) of synth_archive(n_shows, seed, device) without building it: the
+    generator's first draw is the entry counts, and an unshuffled archive has `shows_per_day` shows on each day.  What
+    a rank needs of the OTHER segments of a sharded archive to plan the day ranges (sharding.plan_day_shards)."""
+    device = torch.device(device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    n_per = torch.randint(0, max_entries + 1, (n_shows,), generator=gen, device=device)
+    return n_per, torch.arange(n_shows, device=device) // shows_per_day
+
+
 def table_to_shows(table: ArchiveTable) -> List[dict]:
     """Inverse of pack_shows for SMALL tables: the JSON documents the table stands for."""
     import math
