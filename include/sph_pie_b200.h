@@ -424,6 +424,10 @@ void pie_ingest_host_release(void);
  * out_data for out_capacity bytes.  *n_entries and *total_bytes are always set; row_offsets == out_data == NULL is a
  * size query (analytics are still delivered); PIE_ERR_CAPACITY if either is too small.  A dropped document is an
  * empty show: no rows, skipped by the daily grouping. */
+/* A full request on more than this many documents runs in chunks of that many over three streams (the next chunk's text
+ * goes up and the previous chunk's rows go down while a chunk is ingested).  Returns the previous value; docs <= 0 only
+ * queries.  Default 262144. */
+int64_t pie_set_json_chunk_docs(int64_t docs);
 int pie_archive_step_json_host(const pie_json_docs* host_docs, int32_t tz_offset_minutes, uint8_t* doc_status,
                                int32_t* stats_i32, double* stats_f64, int64_t stats_stride,
                                const pie_daily_out* host_out, int64_t* row_offsets, int64_t row_capacity,

@@ -31,3 +31,15 @@ for name, fn in (("single", ops.archive_step_from_json), ("pipelined", ops.archi
             fn(hdocs, 0, hout, h_off, h_csv, **kw)
         dt = (time.perf_counter() - t0) / 3
         print(f"{name} chunk={chunk}: {dt * 1e3:.1f} ms, {n_entries / dt / 1e6:.1f} M entries/s", flush=True)
+
+lib = _lib.load()
+for chunk in (1 << 30, 65536, 131072, 262144):
+    old = lib.pie_set_json_chunk_docs(chunk)
+    ops.archive_step_json_host(hdocs, 0, hout, h_off, h_csv)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ops.archive_step_json_host(hdocs, 0, hout, h_off, h_csv)
+    dt = (time.perf_counter() - t0) / 3
+    lib.pie_set_json_chunk_docs(old)
+    print(f"pie_archive_step_json_host chunk_docs={chunk if chunk < 1 << 30 else 'single batch'}: {dt * 1e3:.1f} ms, "
+          f"{n_entries / dt / 1e6:.1f} M entries/s", flush=True)

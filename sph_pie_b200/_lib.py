@@ -147,6 +147,7 @@ SIGNATURES = {
     "pie_csv_rows_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     "pie_set_csv_chunk_rows": (C.c_int64, [C.c_int64]),
+    "pie_set_json_chunk_docs": (C.c_int64, [C.c_int64]),
     "pie_archive_step_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.POINTER(DailyOutC), C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pie_compute_metrics_dev": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -1072,8 +1072,8 @@ __device__ __forceinline__ void issue_range(const Range& r, const RangePlan& p, 
 }
 
 __device__ __forceinline__ void produce_tile(const pie_archive_view& v, const RowTable& tab, const CsvScratch& sc,
-                                             StageInfo& info, uint8_t* stage, uint32_t bar, int64_t tile, int tile_rows,
-                                             int force_slow, int lane) {
+                                             StageInfo& info, uint8_t* stage, uint32_t bar, uint32_t empty_bar,
+                                             uint32_t empty_parity, int64_t tile, int tile_rows, int force_slow, int lane) {
   const int64_t e0 = tile * tile_rows;
   const int rows = (v.n_entries - e0 < tile_rows) ? (int)(v.n_entries - e0) : tile_rows;
   const int32_t s0 = sc.entry_show[e0], s1 = sc.entry_show[e0 + rows - 1];
@@ -1116,6 +1116,9 @@ __device__ __forceinline__ void produce_tile(const pie_archive_view& v, const Ro
   for (int o = 16; o; o >>= 1) bulk_total += __shfl_xor_sync(0xFFFFFFFFu, bulk_total, o);
   const bool fits = used <= (uint32_t)kStageBytes && (s1 - s0) < kMaxTileShows && !force_slow;
 
+  // Everything above — the range ends, the only dependent global loads of the kernel — was computed while the workers
+  // were still busy with what the stage held; only now does the producer need the stage itself.
+  mbar_wait_relaxed(empty_bar, empty_parity);
   if (lane < kCols) {
     info.delta[lane] = region_b + (uint32_t)(rb.begin - pb.lo) - b0;
     info.off_base[lane] = region_o + (uint32_t)(ro.begin - po.lo);
@@ -1248,16 +1251,16 @@ __global__ void __launch_bounds__(kCtaThreads, PIE_CSV_MIN_BLOCKS)
       long long tile = 0;
       if (lane == 0) tile = (long long)atomicAdd(sc.tile_counter, 1u);  // tiles start in id order: look-back cannot deadlock
       tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
-      mbar_wait_relaxed(smem_u32(&sm.empty[s]), ph ^ 1u);  // the workers are done with what the stage held
       if (tile >= n_tiles) {
+        mbar_wait_relaxed(smem_u32(&sm.empty[s]), ph ^ 1u);  // the workers are done with what the stage held
         if (lane == 0) {
           sm.info[s].tile = -1;
           mbar_arrive(smem_u32(&sm.full[s]));
         }
         return;
       }
-      produce_tile(v, tab, sc, sm.info[s], s_dyn + kSmemOffStage + s * kStageStride, smem_u32(&sm.full[s]), tile,
-                   tile_rows, force_slow, lane);
+      produce_tile(v, tab, sc, sm.info[s], s_dyn + kSmemOffStage + s * kStageStride, smem_u32(&sm.full[s]),
+                   smem_u32(&sm.empty[s]), ph ^ 1u, tile, tile_rows, force_slow, lane);
     }
   }
 

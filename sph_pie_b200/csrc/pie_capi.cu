@@ -1198,6 +1198,248 @@ OutBuffer g_json_csv;        // CSV scratch and row offsets of pie_archive_step_
 OutBuffer g_json_csv_bytes;  // ... and the CSV bytes (grown without moving what the kernels before wrote)
 }
 
+
+// ---- the same in chunks of documents over three streams ---------------------------------------------------------
+// Shows are independent: a chunk of documents is ingested, its statistics and CSV rows are computed and its rows go
+// back to the host while the next chunk's text is still on its way up (PCIe is full duplex) — a single batch
+// spends 80 ms uploading 4.4 GB before the first kernel runs and 60 ms downloading after the last.  Only the daily
+// grouping needs every show: the chunks' tables stay on the device, their show-level columns are joined at the end
+// and the summary runs once.
+static int64_t kJsonChunkDocs = 262144;  // pie_set_json_chunk_docs (tests exercise the multi-chunk path)
+
+namespace {
+struct JsonChunkState {
+  OutBuffer text[2];      // the documents of a chunk (two in flight)
+  OutBuffer scratch[2];   // ingest scratch + totals + status + doc_status of a chunk
+  OutBuffer rows[2];      // the entry rows of the second walk
+  OutBuffer csv[2];       // CSV scratch + row offsets + total
+  OutBuffer csv_bytes[2];
+  std::vector<OutBuffer> tables;  // one per chunk: they stay until the daily summary has run
+  OutBuffer joined;       // the show-level columns of the whole batch, planes, daily outputs
+  cudaEvent_t text_free[2] = {nullptr, nullptr};
+  long long* h_small = nullptr;  // pinned: totals[26] + status[2] + csv total
+};
+JsonChunkState g_jc;
+}  // namespace
+
+int64_t pie_set_json_chunk_docs(int64_t docs) {
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  const int64_t old = kJsonChunkDocs;
+  if (docs > 0) kJsonChunkDocs = docs;
+  return old;
+}
+
+static int archive_step_json_chunked(const pie_json_docs* hd, int32_t tz_offset_minutes, uint8_t* doc_status, int32_t* stats_i32,
+                                     double* stats_f64, int64_t stats_stride, const pie_daily_out* hout, int64_t* row_offsets,
+                                     int64_t row_capacity, uint8_t* out_data, uint64_t out_capacity, int64_t* n_entries,
+                                     uint64_t* total_bytes, int64_t* bad_doc) {
+  int rc;
+  const int64_t S = hd->n_docs, Sc = S > 0 ? S : 1;
+  if ((rc = g_pipe.init())) return rc;
+  struct PipeDrain {
+    ~PipeDrain() {
+      cudaStreamSynchronize(g_pipe.h2d);
+      cudaStreamSynchronize(g_pipe.cmp);
+      cudaStreamSynchronize(g_pipe.d2h);
+    }
+  } drain_on_exit;
+  if (!g_jc.h_small) {
+    PIE_CUDA(cudaHostAlloc((void**)&g_jc.h_small, 512, cudaHostAllocDefault));
+    for (int i = 0; i < 2; ++i) PIE_CUDA(cudaEventCreateWithFlags(&g_jc.text_free[i], cudaEventDisableTiming));
+  }
+  const bool want_stats = stats_i32 != nullptr;
+  // chunks of documents
+  std::vector<int64_t> cut{0};
+  while (cut.back() < S) cut.push_back(cut.back() + kJsonChunkDocs < S ? cut.back() + kJsonChunkDocs : S);
+  const int K = (int)cut.size() - 1;
+  if ((int)g_jc.tables.size() < K) g_jc.tables.resize((size_t)K);
+  // whole-batch device arrays: document offsets, planes, doc_status
+  const uint64_t bytes = pad(8 * (uint64_t)(S + 1)) + pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc) + pad(64);
+  if ((rc = g_arena.reserve(bytes))) return rc;
+  int64_t* d_off = (int64_t*)g_arena.take(8 * (uint64_t)(S + 1));
+  int32_t* d_si = (int32_t*)g_arena.take(4ull * PIE_SI_COUNT * Sc);
+  double* d_sf = (double*)g_arena.take(8ull * PIE_SF_COUNT * Sc);
+  uint64_t h2d = 0, d2h = 0;
+  PIE_CUDA(cudaMemcpyAsync(d_off, hd->offsets, 8 * (uint64_t)(S + 1), cudaMemcpyHostToDevice, g_pipe.h2d));
+  h2d += 8 * (uint64_t)(S + 1);
+
+  struct Chunk {
+    pie_json_docs dd;
+    pie_archive_table dt;
+    int64_t totals[PIE_INGEST_TOTALS];
+    int64_t e_base;
+  };
+  std::vector<Chunk> ch((size_t)K);
+  auto upload = [&](int k) -> int {
+    const int slot = k & 1;
+    const int64_t first = hd->offsets[cut[(size_t)k]], last = hd->offsets[cut[(size_t)k + 1]];
+    const uint64_t nbytes = (uint64_t)(last - first);
+    if (k >= 2) PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_jc.text_free[slot], 0));  // chunk k-2 is through its second walk
+    int rc2 = g_jc.text[slot].ensure(nbytes + 64);
+    if (rc2) return rc2;
+    const uint64_t skew = (uint64_t)first & 7;
+    if (nbytes) PIE_CUDA(cudaMemcpyAsync(g_jc.text[slot].base + skew, hd->data + first, nbytes, cudaMemcpyHostToDevice, g_pipe.h2d));
+    h2d += nbytes;
+    ch[(size_t)k].dd.n_docs = cut[(size_t)k + 1] - cut[(size_t)k];
+    ch[(size_t)k].dd.offsets = d_off + cut[(size_t)k];
+    ch[(size_t)k].dd.data = g_jc.text[slot].base + skew - first;
+    PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[slot], g_pipe.h2d));
+    return PIE_OK;
+  };
+
+  unsigned long long bias = 0;
+  int64_t e_base = 0;
+  bool overflow = false;
+  if (K > 0 && (rc = upload(0))) return rc;
+  for (int k = 0; k < K; ++k) {
+    const int slot = k & 1;
+    Chunk& c = ch[(size_t)k];
+    const int64_t n = c.dd.n_docs, s0 = cut[(size_t)k];
+    const uint64_t scratch_bytes = pie::ingest_scratch_bytes(n);
+    if (k >= 2) {  // the slot's buffers are chunk k-2's until its rows and doc_status have left for the host
+      PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.d2h_done[slot], 0));
+      PIE_CUDA(cudaEventSynchronize(g_pipe.d2h_done[slot]));  // (a buffer that has to grow is freed: nothing may still read it)
+    }
+    if ((rc = g_jc.scratch[slot].ensure(pad(scratch_bytes) + pad((uint64_t)n + 1) + pad(8 * PIE_INGEST_TOTALS) + pad(16)))) return rc;
+    uint8_t* p = g_jc.scratch[slot].base;
+    void* d_scratch = p; p += pad(scratch_bytes);
+    uint8_t* d_docstat = p; p += pad((uint64_t)n + 1);
+    int64_t* d_totals = (int64_t*)p; p += pad(8 * PIE_INGEST_TOTALS);
+    int32_t* d_status = (int32_t*)p;
+    PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.h2d_done[slot], 0));
+    PIE_CUDA(pie::launch_ingest_measure(c.dd, d_scratch, d_docstat, d_totals, d_status, g_pipe.cmp));
+    PIE_CUDA(cudaMemcpyAsync(g_jc.h_small, d_totals, 8 * PIE_INGEST_TOTALS, cudaMemcpyDeviceToHost, g_pipe.cmp));
+    PIE_CUDA(cudaMemcpyAsync(g_jc.h_small + PIE_INGEST_TOTALS, d_status, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
+    if (k + 1 < K && (rc = upload(k + 1))) return rc;  // the next chunk's text goes up while this one is walked
+    PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
+    d2h += 8 * PIE_INGEST_TOTALS + 8;
+    memcpy(c.totals, g_jc.h_small, sizeof(c.totals));
+    const int32_t* status = reinterpret_cast<const int32_t*>(g_jc.h_small + PIE_INGEST_TOTALS);
+    if (status[0] != 0) {
+      if (bad_doc) *bad_doc = status[1] >= 0 ? s0 + status[1] : -1;
+      const char* what = status[0] == PIE_ERR_SCHEMA ? "is not a provider-normalised show"
+                         : status[0] == PIE_ERR_UNSUPPORTED_JSON ? "is JSON the ingest kernels do not decide"
+                                                                 : "makes a heap or row count reach 2 GiB: split the batch";
+      return fail(status[0], "document %lld %s", (long long)(s0 + status[1]), what);
+    }
+    const int64_t E = c.totals[PIE_IT_ENTRIES];
+    c.e_base = e_base;
+    const uint64_t block = layout_table(&c.dt, nullptr, n, c.totals);
+    if ((rc = g_jc.tables[(size_t)k].ensure(block ? block : 256))) return rc;
+    layout_table(&c.dt, g_jc.tables[(size_t)k].base, n, c.totals);
+    if ((rc = g_jc.rows[slot].ensure(pie::ingest_fill_scratch_bytes(E)))) return rc;
+    PIE_CUDA(pie::launch_ingest_fill(c.dd, d_scratch, d_docstat, c.dt, g_jc.rows[slot].base, g_pipe.cmp));
+    PIE_CUDA(cudaEventRecord(g_jc.text_free[slot], g_pipe.cmp));
+    pie_archive_view dv;
+    memcpy(&dv, &c.dt, sizeof(dv));
+    if (n > 0) PIE_CUDA(pie::launch_show_stats(dv, d_si + s0, d_sf + s0, Sc, g_sm_count, g_pipe.cmp));
+    const uint64_t csv_scratch = pad(pie::csv_scratch_bytes(E)), off_bytes = pad(8 * (uint64_t)(E + 1));
+    if ((rc = g_jc.csv[slot].ensure(csv_scratch + off_bytes + pad(8)))) return rc;
+    void* d_cscratch = g_jc.csv[slot].base;
+    int64_t* d_rows = (int64_t*)(g_jc.csv[slot].base + csv_scratch);
+    unsigned long long* d_total = (unsigned long long*)(g_jc.csv[slot].base + csv_scratch + off_bytes);
+    PIE_CUDA(launch_rows(kFormatCsv, dv, d_rows, nullptr, 0, bias, d_total, d_cscratch, g_pipe.cmp));
+    PIE_CUDA(cudaMemcpyAsync(g_jc.h_small + 32, d_total, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
+    PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
+    d2h += 8;
+    const unsigned long long total = (unsigned long long)g_jc.h_small[32];
+    const bool fits = out_data && row_offsets && bias + total <= out_capacity && e_base + E + 1 <= row_capacity;
+    if (!fits) overflow = true;
+    if (fits && !overflow) {
+      if ((rc = g_jc.csv_bytes[slot].ensure(total ? total : 256))) return rc;
+      PIE_CUDA(launch_rows(kFormatCsv, dv, d_rows, g_jc.csv_bytes[slot].base, total, bias, d_total, d_cscratch, g_pipe.cmp));
+    }
+    PIE_CUDA(cudaEventRecord(g_pipe.kernel_done[slot], g_pipe.cmp));
+    PIE_CUDA(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.kernel_done[slot], 0));
+    if (n > 0) PIE_CUDA(cudaMemcpyAsync(doc_status + s0, d_docstat, (uint64_t)n, cudaMemcpyDeviceToHost, g_pipe.d2h));
+    d2h += (uint64_t)n;
+    if (fits && !overflow) {
+      if (E > 0) PIE_CUDA(cudaMemcpyAsync(row_offsets + e_base, d_rows, 8 * (uint64_t)E, cudaMemcpyDeviceToHost, g_pipe.d2h));
+      if (total) PIE_CUDA(cudaMemcpyAsync(out_data + bias, g_jc.csv_bytes[slot].base, total, cudaMemcpyDeviceToHost, g_pipe.d2h));
+      d2h += 8 * (uint64_t)E + total;
+    }
+    PIE_CUDA(cudaEventRecord(g_pipe.d2h_done[slot], g_pipe.d2h));
+    bias += total;
+    e_base += E;
+  }
+  const int64_t E_all = e_base;
+  *n_entries = E_all;
+  *total_bytes = bias;
+
+  // ---- the daily groups read show-level columns of every chunk: join them, run the summary once
+  uint64_t date_bytes = 0, time_bytes = 0;
+  for (const Chunk& c : ch) { date_bytes += (uint64_t)c.totals[1]; time_bytes += (uint64_t)c.totals[2]; }
+  if (date_bytes >= 0x7FFFFFF0ull || time_bytes >= 0x7FFFFFF0ull || E_all >= 0x7FFFFFF0LL)
+    return fail(PIE_ERR_CAPACITY, "the batch's show dates / entries reach 2 GiB: split the batch");
+  const uint64_t jbytes = pad(4 * (uint64_t)(S + 1)) * 3 + pad(8 * (uint64_t)Sc) * 2 + pad(8 * (uint64_t)(E_all + 1)) + pad(date_bytes + 16) +
+                          pad(time_bytes + 16) + daily_out_bytes(S, Sc) + pad(64);
+  if ((rc = g_jc.joined.ensure(jbytes))) return rc;
+  Arena ja;
+  ja.base = g_jc.joined.base; ja.cap = g_jc.joined.cap; ja.used = 0;
+  int32_t* j_eo = (int32_t*)ja.take(4 * (uint64_t)(S + 1));
+  int32_t* j_date_off = (int32_t*)ja.take(4 * (uint64_t)(S + 1));
+  int32_t* j_time_off = (int32_t*)ja.take(4 * (uint64_t)(S + 1));
+  double* j_created = (double*)ja.take(8 * (uint64_t)Sc);
+  double* j_archived = (double*)ja.take(8 * (uint64_t)Sc);
+  double* j_ets = (double*)ja.take(8 * (uint64_t)(E_all + 1));
+  uint8_t* j_date = (uint8_t*)ja.take(date_bytes + 16);
+  uint8_t* j_time = (uint8_t*)ja.take(time_bytes + 16);
+  uint64_t db = 0, tb = 0;
+  for (int k = 0; k < K; ++k) {
+    const Chunk& c = ch[(size_t)k];
+    const int64_t n = c.dd.n_docs, s0 = cut[(size_t)k], E = c.totals[PIE_IT_ENTRIES];
+    const bool last = k + 1 == K;
+    PIE_CUDA(pie::launch_rebase_i32(j_eo + s0, c.dt.entry_offsets, n + (last ? 1 : 0), (int32_t)c.e_base, g_pipe.cmp));
+    PIE_CUDA(pie::launch_rebase_i32(j_date_off + s0, c.dt.show_date.offsets, n + (last ? 1 : 0), (int32_t)db, g_pipe.cmp));
+    PIE_CUDA(pie::launch_rebase_i32(j_time_off + s0, c.dt.show_time.offsets, n + (last ? 1 : 0), (int32_t)tb, g_pipe.cmp));
+    if (n > 0) {
+      PIE_CUDA(cudaMemcpyAsync(j_created + s0, c.dt.created_at, 8 * (uint64_t)n, cudaMemcpyDeviceToDevice, g_pipe.cmp));
+      PIE_CUDA(cudaMemcpyAsync(j_archived + s0, c.dt.archived_at, 8 * (uint64_t)n, cudaMemcpyDeviceToDevice, g_pipe.cmp));
+    }
+    if (E > 0) PIE_CUDA(cudaMemcpyAsync(j_ets + c.e_base, c.dt.entry_ts, 8 * (uint64_t)E, cudaMemcpyDeviceToDevice, g_pipe.cmp));
+    if (c.totals[1]) PIE_CUDA(cudaMemcpyAsync(j_date + db, c.dt.show_date.data, (uint64_t)c.totals[1], cudaMemcpyDeviceToDevice, g_pipe.cmp));
+    if (c.totals[2]) PIE_CUDA(cudaMemcpyAsync(j_time + tb, c.dt.show_time.data, (uint64_t)c.totals[2], cudaMemcpyDeviceToDevice, g_pipe.cmp));
+    db += (uint64_t)c.totals[1];
+    tb += (uint64_t)c.totals[2];
+  }
+  if (K == 0) {
+    PIE_CUDA(cudaMemsetAsync(j_eo, 0, 4, g_pipe.cmp));
+    PIE_CUDA(cudaMemsetAsync(j_date_off, 0, 4, g_pipe.cmp));
+    PIE_CUDA(cudaMemsetAsync(j_time_off, 0, 4, g_pipe.cmp));
+  }
+  pie_archive_view jv;
+  memset(&jv, 0, sizeof(jv));
+  jv.n_shows = S;
+  jv.n_entries = E_all;
+  jv.entry_offsets = j_eo;
+  jv.show_date.offsets = j_date_off; jv.show_date.data = j_date;
+  jv.show_time.offsets = j_time_off; jv.show_time.data = j_time;
+  jv.created_at = j_created;
+  jv.archived_at = j_archived;
+  jv.entry_ts = j_ets;
+  pie_daily_out dout;
+  void* dscratch = alloc_daily_out(ja, S, Sc, &dout);
+  PIE_CUDA(pie::launch_daily_summary(jv, d_si, d_sf, Sc, tz_offset_minutes, dout, dscratch, g_sm_count, g_pipe.cmp));
+  if (want_stats && S > 0) {
+    PIE_CUDA(cudaMemcpy2DAsync(stats_i32, 4 * (uint64_t)stats_stride, d_si, 4 * (uint64_t)Sc, 4 * (uint64_t)S, PIE_SI_COUNT,
+                               cudaMemcpyDeviceToHost, g_pipe.cmp));
+    PIE_CUDA(cudaMemcpy2DAsync(stats_f64, 8 * (uint64_t)stats_stride, d_sf, 8 * (uint64_t)Sc, 8 * (uint64_t)S, PIE_SF_COUNT,
+                               cudaMemcpyDeviceToHost, g_pipe.cmp));
+    d2h += (4ull * PIE_SI_COUNT + 8ull * PIE_SF_COUNT) * (uint64_t)S;
+  }
+  rc = download_daily(hout, dout, S, Sc, g_pipe.cmp, &d2h);
+  PIE_CUDA(cudaStreamSynchronize(g_pipe.d2h));
+  PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
+  if (row_offsets && !overflow) row_offsets[E_all] = (int64_t)bias;
+  g_last_h2d = h2d;
+  g_last_d2h = d2h + 8;
+  if (rc) return rc;
+  if (overflow)
+    return fail(PIE_ERR_CAPACITY, "CSV needs %llu bytes and %lld row offsets (given %llu and %lld)", bias, (long long)(E_all + 1),
+                (unsigned long long)out_capacity, (long long)row_capacity);
+  return PIE_OK;
+}
+
 int pie_archive_step_json_host(const pie_json_docs* hd, int32_t tz_offset_minutes, uint8_t* doc_status, int32_t* stats_i32,
                                double* stats_f64, int64_t stats_stride, const pie_daily_out* hout, int64_t* row_offsets,
                                int64_t row_capacity, uint8_t* out_data, uint64_t out_capacity, int64_t* n_entries,
@@ -1212,6 +1454,21 @@ int pie_archive_step_json_host(const pie_json_docs* hd, int32_t tz_offset_minute
   if (want_stats && stats_stride < S) return fail(PIE_ERR_INVALID_ARG, "stats_stride < n_docs");
   int rc;
   if (S >= 0 && (rc = check_daily_out(hout, S))) return rc;
+  if (out_data && row_offsets && S > kJsonChunkDocs) {  // a full request on a large batch: the pipelined form
+    if (bad_doc) *bad_doc = -1;
+    if ((rc = ensure_init())) return rc;
+    if ((rc = check_docs(hd))) return rc;
+    if (!doc_status) return fail(PIE_ERR_INVALID_ARG, "doc_status is NULL");
+    if (hd->offsets[0] < 0) return fail(PIE_ERR_INVALID_ARG, "docs.offsets must ascend from a non-negative value");
+    for (int64_t i = 0; i < S; ++i) {
+      const int64_t len = hd->offsets[i + 1] - hd->offsets[i];
+      if (len < 0) return fail(PIE_ERR_INVALID_ARG, "docs.offsets decrease at document %lld", (long long)i);
+      if (len >= 0x7FFFFFF0LL) return fail(PIE_ERR_INVALID_ARG, "document %lld is 2 GiB or more", (long long)i);
+    }
+    if (hd->offsets[S] > hd->offsets[0] && !hd->data) return fail(PIE_ERR_INVALID_ARG, "docs.data is NULL");
+    return archive_step_json_chunked(hd, tz_offset_minutes, doc_status, stats_i32, stats_f64, stats_stride, hout, row_offsets,
+                                     row_capacity, out_data, out_capacity, n_entries, total_bytes, bad_doc);
+  }
   const int64_t Sc = S > 0 ? S : 1;
   const uint64_t extra = pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc) + daily_out_bytes(S, Sc) + pad(64);
   int64_t totals[PIE_INGEST_TOTALS] = {0};
@@ -1295,6 +1552,16 @@ int pie_release(void) {
   free_out(g_ingest_rows);
   free_out(g_json_csv);
   free_out(g_json_csv_bytes);
+  for (int i = 0; i < 2; ++i) {
+    free_out(g_jc.text[i]); free_out(g_jc.scratch[i]); free_out(g_jc.rows[i]); free_out(g_jc.csv[i]); free_out(g_jc.csv_bytes[i]);
+    if (g_jc.text_free[i]) cudaEventDestroy(g_jc.text_free[i]);
+    g_jc.text_free[i] = nullptr;
+  }
+  for (OutBuffer& b : g_jc.tables) free_out(b);
+  g_jc.tables.clear();
+  free_out(g_jc.joined);
+  if (g_jc.h_small) cudaFreeHost(g_jc.h_small);
+  g_jc.h_small = nullptr;
   if (g_ingest_host) cudaFreeHost(g_ingest_host);
   g_ingest_host = nullptr;
   g_ingest_host_cap = 0;

@@ -28,6 +28,7 @@ struct OffsetsBatch {
 };
 // flags: device int32[kMaxOffsetsArrays]; flags[i] != 0 afterwards: array i was malformed (and now holds empty rows)
 cudaError_t launch_offsets_check(const OffsetsBatch& batch, int32_t* flags, cudaStream_t stream);
+cudaError_t launch_rebase_i32(int32_t* dst, const int32_t* src, int64_t n, int32_t add, cudaStream_t stream);
 
 // archive_stats.cu
 cudaError_t launch_show_stats(const pie_archive_view& dev_view, int32_t* stats_i32, double* stats_f64,

@@ -29,6 +29,22 @@ __global__ void __launch_bounds__(256) offsets_disarm_kernel(const __grid_consta
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) rebase_i32_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, int64_t n, int32_t add) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i] + add;
+}
+}  // namespace
+
+// dst[i] = src[i] + add: the offsets of a chunk's column moved onto the joined column of a batch
+cudaError_t launch_rebase_i32(int32_t* dst, const int32_t* src, int64_t n, int32_t add, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count_or_default() * 8;
+  rebase_i32_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, stream>>>(dst, src, n, add);
+  g_launches += 1;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_offsets_check(const OffsetsBatch& batch, int32_t* flags, cudaStream_t stream) {
   if (batch.count <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int32_t) * kMaxOffsetsArrays, stream);

@@ -298,6 +298,29 @@ def test_pipelined_step_from_stored_texts(cuda, chunk_docs):
         assert ei.value.code == _lib.PIE_ERR_CAPACITY
         empty = ops.archive_step_json_host(ops.JsonDocs.from_texts([]), 0)
         assert empty[1].n_groups == 0 and empty[2].row_offsets.tolist() == [0]
+        # ... and so does its pipelined form (chunks of documents over three streams, the chunks' show-level columns
+        # joined for the daily summary): chunk borders inside a day, a dropped row first / last in a chunk
+        from helpers import assert_analytics_equal as same
+
+        lib = _lib.load()
+        for chunk in (700, 256, 2999):
+            old = lib.pie_set_json_chunk_docs(chunk)
+            try:
+                for _ in range(2):  # the second call reuses every buffer of the first
+                    s4, d4, r4, x4 = ops.archive_step_json_host(docs, 120, None, torch.empty(off.numel(), dtype=torch.int64),
+                                                                torch.empty(csv.numel(), dtype=torch.uint8))
+                    assert torch.equal(x1, x4)
+                    same((s4, d4), (s1, d1), f"pie_archive_step_json_host in chunks of {chunk}")
+                    assert torch.equal(r1.row_offsets, r4.row_offsets) and torch.equal(r1.data, r4.data)
+                with pytest.raises(_lib.PieError) as ei:
+                    ops.archive_step_json_host(docs, 120, None, torch.empty(off.numel(), dtype=torch.int64), torch.empty(100000, dtype=torch.uint8))
+                assert ei.value.code == _lib.PIE_ERR_CAPACITY
+                bad = ops.JsonDocs.from_texts(texts[:1500] + ['{"entries":[{"delaySec":"text"}]}'] + texts[1500:])
+                with pytest.raises(_lib.SchemaError) as es:
+                    ops.archive_step_json_host(bad, 120, None, torch.empty(off.numel() + 8, dtype=torch.int64), torch.empty(csv.numel() + 64, dtype=torch.uint8))
+                assert es.value.doc == 1500
+            finally:
+                lib.pie_set_json_chunk_docs(old)
     from helpers import assert_analytics_equal
 
     assert torch.equal(x1, x2) and x1.nonzero().flatten().tolist() == [5, 699, 2999]
@@ -355,8 +378,8 @@ def test_map_archive_rows_with_the_rows_timestamp_columns(cuda):
     shows = table_to_shows(synth_archive(40, seed=9, missing_created_frac=0.5))
     rows = []
     for i, s in enumerate(shows):
-        # a timestamp the document does not have is ABSENT (the provider never stores null there; _getTimestamp would
-        # turn a null into 0, which the table — null and absent are one value — does not model: DESIGN.md §2)
+        # a timestamp the document does not have is ABSENT here (a null would count as 0 — Number(null) — which
+        # tests/test_gpu_maintenance.py covers with the full restatement of _mapArchiveRow)
         s = {k: v for k, v in s.items() if not (k in ("createdAt", "archivedAt") and v is None)}
         row = {"data": po.js_json_stringify(s)}
         if i % 4 != 3:
@@ -374,8 +397,12 @@ def test_map_archive_rows_with_the_rows_timestamp_columns(cuda):
         assert dropped.nonzero().flatten().tolist() == [7]
         ref = pack_shows(want)
         assert_tables_equal(table, ref, "mapArchiveRows with row columns " + device)
+    # a column that holds an ISO text goes through Date.parse (a date-only form is UTC); any other text is V8's
+    # legacy parser, which is not restated: it raises
+    t, _ = mapArchiveRows([{"data": "{}", "archived_at": "2024-01-01"}])
+    assert t.archived_at.tolist() == [1704067200000.0]
     with pytest.raises(NotImplementedError):
-        mapArchiveRows([{"data": "{}", "archived_at": "2024-01-01"}])
+        mapArchiveRows([{"data": "{}", "archived_at": "next tuesday"}])
 
 
 def test_documents_that_do_not_start_at_offset_zero(cuda):
