@@ -864,15 +864,28 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
     an_checks = g_checks;
   }
 
-  // chunks of ~kCsvChunkRows rows, cut at show boundaries
+  // chunks of ~kCsvChunkRows rows, cut at show boundaries.  The pipeline's ends are not overlapped — nothing
+  // downloads while the first chunk goes up, nothing uploads while the last comes down — so a large batch starts and
+  // ends on smaller chunks (a quarter, a half of the usual size).
   std::vector<CsvChunk> chunks;
+  const bool ramp = E >= 4 * kCsvChunkRows;
   for (int64_t s0 = 0; s0 < S || chunks.empty();) {
     CsvChunk c;
     c.s0 = s0;
     c.e0 = S > 0 ? hv->entry_offsets[s0] : 0;
+    int64_t want = kCsvChunkRows;
+    if (ramp) {
+      const int64_t left = E - c.e0;
+      if (chunks.empty()) want = kCsvChunkRows / 4;
+      else if (chunks.size() == 1) want = kCsvChunkRows / 2;
+      else if (left <= kCsvChunkRows / 4 + kCsvChunkRows / 8) want = left;           // the last one
+      else if (left <= kCsvChunkRows) want = left - kCsvChunkRows / 4;               // half, then a quarter
+      else if (left < 2 * kCsvChunkRows) want = left - kCsvChunkRows * 3 / 4;
+    }
+    if (want < 1) want = 1;  // (trailing shows without entries: the loop below must still take them)
     int64_t s1 = s0;
-    while (s1 < S && hv->entry_offsets[s1] - c.e0 < kCsvChunkRows) {
-      const int64_t step = (S - s1 > 4096 && hv->entry_offsets[s1 + 4096] - c.e0 < kCsvChunkRows) ? 4096 : 1;
+    while (s1 < S && hv->entry_offsets[s1] - c.e0 < want) {
+      const int64_t step = (S - s1 > 4096 && hv->entry_offsets[s1 + 4096] - c.e0 < want) ? 4096 : 1;
       s1 += step;
     }
     c.s1 = s1;
