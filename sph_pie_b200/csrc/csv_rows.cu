@@ -758,8 +758,12 @@ __device__ __forceinline__ uint32_t control_bytes_exact(uint32_t x) {  // bytes 
 template <bool kJson>
 __device__ __forceinline__ uint32_t special_bytes_exact(uint32_t x) {
   if (kJson) return zero_bytes_exact(x ^ 0x22222222u) | zero_bytes_exact(x ^ 0x5C5C5C5Cu) | control_bytes_exact(x);
-  return zero_bytes_exact(x ^ 0x22222222u) | zero_bytes_exact(x ^ 0x2C2C2C2Cu) | zero_bytes_exact(x ^ 0x0A0A0A0Au) |
-         zero_bytes_exact(x ^ 0x0D0D0D0Du);
+  // CSV: '"' ',' LF CR.  On the low seven bits of every byte, (b ^ c) + 0x7F carries into bit 7 unless b == c: an XOR
+  // and an ADD per character, the four results ANDed; a byte with its own bit 7 set is never one of the four.
+  const uint32_t y = x & 0x7F7F7F7Fu;
+  const uint32_t differs = ((y ^ 0x22222222u) + 0x7F7F7F7Fu) & ((y ^ 0x2C2C2C2Cu) + 0x7F7F7F7Fu) &
+                           ((y ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu) & ((y ^ 0x0D0D0D0Du) + 0x7F7F7F7Fu);
+  return ~(differs | x) & 0x80808080u;
 }
 // the four 0x80 flags of a word as a nibble (bit j = byte j)
 __device__ __forceinline__ uint32_t flags_to_nibble(uint32_t f) { return ((f >> 7) * 0x01020408u) >> 24 & 0xFu; }
@@ -782,16 +786,18 @@ __device__ __forceinline__ void build_special_mask(uint32_t* __restrict__ mask, 
     m16[i] = (uint16_t)bits;
   }
 }
-// any bit of mask[src .. src+n) set?  (n >= 1)
+// any bit of mask[src .. src+n) set?  (n >= 1)  Cells of up to 32 bytes — nearly all — take two loads and a funnel
+// shift whatever their phase against the mask's words: no branch on where the cell happens to start.
 __device__ __forceinline__ bool mask_any(const uint32_t* __restrict__ mask, uint32_t src, uint32_t n) {
   uint32_t w = src >> 5;
-  const uint32_t sh = src & 31u, avail = 32u - sh;
-  const uint32_t head = mask[w] >> sh;
-  if (n <= avail) return (head & (0xFFFFFFFFu >> (32u - n))) != 0;
-  uint32_t acc = head;
-  n -= avail;
-  for (++w; n >= 32u; n -= 32u, ++w) acc |= mask[w];
-  if (n) acc |= mask[w] & (0xFFFFFFFFu >> (32u - n));
+  const uint32_t sh = src & 31u;
+  const uint32_t window = __funnelshift_r(mask[w], mask[w + 1], sh);  // bits src .. src+31
+  if (n <= 32u) return (window & (0xFFFFFFFFu >> (32u - n))) != 0;
+  uint32_t acc = window;
+  n -= 32u;
+  src += 32u;
+  for (w = src >> 5; n >= 32u; n -= 32u, ++w) acc |= __funnelshift_r(mask[w], mask[w + 1], sh);
+  if (n) acc |= __funnelshift_r(mask[w], mask[w + 1], sh) & (0xFFFFFFFFu >> (32u - n));
   return acc != 0;
 }
 
