@@ -256,3 +256,46 @@ def test_archive_step_host_equals_the_two_calls(cuda):
     # empty batch
     st, daily, rows = ops.archive_step(pack([]), 0)
     assert daily.n_groups == 0 and rows.data.numel() == 0
+
+
+@pytest.mark.parametrize("fmt", ["csv", "payload"])
+def test_bump_area_swept_across_its_brim(cuda, fmt):
+    """The shared-memory bump allocator of the row kernel (csvEscape'd / joined / JSON-escaped cells are written out
+    behind the staged bytes) has nothing behind it but the delaySec strings and the next stage.  Shared memory cannot
+    be inspected from outside, so the canary is the output itself: free text whose every cell needs escaping, grown
+    step by step from 'the bump area is hardly used' to 'no tile fits any more', must give the oracle's bytes at every
+    step — an allocation that ran past its area would land in the number strings or the neighbouring stage and show
+    up in them — and the sweep must actually cross the brim (both kinds of tiles are seen)."""
+    from sph_pie_b200.columnar import StrCol
+    from sph_pie_b200.synth import strcol_from_codes
+
+    dev = cuda
+    seen_fast = seen_slow = False
+    for repeat in (1, 3, 6, 9, 12, 16, 24, 40):
+        host = synth_archive(1200, seed=60 + repeat, notes_repeat=1)
+        E = host.n_entries
+        g = torch.Generator().manual_seed(repeat)
+        # every note needs escaping (quotes, commas, line breaks, a backslash, a control character), lengths jitter
+        vocab = [('say "x", then\n' * k)[: 11 * k + j] + "\\\x01" for k in (repeat,) for j in range(7)]
+        for column in ("notes", "other_detail", "sub_issue", "operator_name"):  # two of them are read by each format
+            host.entry_cols[column] = strcol_from_codes(torch.randint(0, len(vocab), (E,), generator=g), vocab)
+        table = host.to(dev)
+        if fmt == "csv":
+            ref_off, ref_data = oracle_c.csv_rows(host)
+            fn = ops.csv_rows_dev
+        else:
+            ref_off, ref_data = oracle_c.payload_rows(host)
+            fn = ops.archive_payloads_dev
+        sizing = ops.CsvBuffers(E, 0, dev)
+        fn(table, sizing, size_only=True)
+        total = int(sizing.total.cpu())
+        assert total == ref_data.numel()
+        bufs = ops.CsvBuffers(E, total, dev)
+        fn(table, bufs)
+        slow = ops.csv_slow_tiles(table, bufs)
+        assert torch.equal(bufs.row_offsets.cpu(), ref_off), (fmt, repeat)
+        assert torch.equal(bufs.data[:total].cpu(), ref_data), (fmt, repeat)
+        n_tiles_min = (E + 159) // 160
+        seen_fast |= slow < n_tiles_min
+        seen_slow |= slow > 0
+    assert seen_fast and seen_slow
