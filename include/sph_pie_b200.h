@@ -426,7 +426,7 @@ void pie_ingest_host_release(void);
  * empty show: no rows, skipped by the daily grouping. */
 /* A full request on more than this many documents runs in chunks of that many over three streams (the next chunk's text
  * goes up and the previous chunk's rows go down while a chunk is ingested).  Returns the previous value; docs <= 0 only
- * queries.  Default 262144. */
+ * queries.  Default 131072. */
 int64_t pie_set_json_chunk_docs(int64_t docs);
 int pie_archive_step_json_host(const pie_json_docs* host_docs, int32_t tz_offset_minutes, uint8_t* doc_status,
                                int32_t* stats_i32, double* stats_f64, int64_t stats_stride,

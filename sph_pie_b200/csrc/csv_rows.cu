@@ -1665,7 +1665,7 @@ static cudaError_t launch_rows(const pie_archive_view& v, const RowTable& tab, i
   if (v.n_entries == 0) {
     err = cudaMemsetAsync(total_out, 0, 8, stream);
     if (err != cudaSuccess) return err;
-    return cudaMemcpyAsync(row_offsets, total_out, 8, cudaMemcpyDeviceToDevice, stream);  // 0; the caller adds its bias
+    return cudaMemcpyAsync(row_offsets, total_out, 8, cudaMemcpyDefault, stream);  // 0; the caller adds its bias
   }
   static int configured_device = -1, resident_ctas = 0;  // per instantiation
   int dev = 0;

@@ -97,7 +97,7 @@ unsigned long long* g_maint_err = nullptr;  // device word: the first offending 
 
 int ensure_check_flags();
 // enqueue the check of everything uploaded since clear(), flags -> `host_flags` (any host memory) on `st`
-int enqueue_checks(const PendingChecks& c, int set, int32_t* host_flags, cudaStream_t st);
+int enqueue_checks(const PendingChecks& c, int set, int32_t* host_flags, cudaStream_t st, bool mapped = false);
 // after `st` was synchronised: PIE_ERR_INVALID_ARG naming the first malformed array
 int report_checks(const PendingChecks& c, const int32_t* host_flags);
 
@@ -139,7 +139,8 @@ int ensure_check_flags() {
   PIE_CUDA(cudaMalloc(&g_check_flags, sizeof(int32_t) * 3 * pie::kMaxOffsetsArrays));
   return PIE_OK;
 }
-int enqueue_checks(const PendingChecks& c, int set, int32_t* host_flags, cudaStream_t st) {
+// mapped: host_flags is pinned memory the device can write (the pipelines: no copy engine involved)
+int enqueue_checks(const PendingChecks& c, int set, int32_t* host_flags, cudaStream_t st, bool mapped) {
   static const bool skip = getenv("PIE_DEBUG_SKIP_OFFSET_CHECK") != nullptr;  // timing experiments only
   memset(host_flags, 0, sizeof(int32_t) * pie::kMaxOffsetsArrays);
   if (skip || c.batch.count == 0) return PIE_OK;
@@ -147,7 +148,8 @@ int enqueue_checks(const PendingChecks& c, int set, int32_t* host_flags, cudaStr
   if (rc) return rc;
   int32_t* d = g_check_flags + set * pie::kMaxOffsetsArrays;
   PIE_CUDA(pie::launch_offsets_check(c.batch, d, st));
-  PIE_CUDA(cudaMemcpyAsync(host_flags, d, sizeof(int32_t) * pie::kMaxOffsetsArrays, cudaMemcpyDeviceToHost, st));
+  if (mapped) PIE_CUDA(pie::launch_offsets_flags_out(d, host_flags, st));
+  else PIE_CUDA(cudaMemcpyAsync(host_flags, d, sizeof(int32_t) * pie::kMaxOffsetsArrays, cudaMemcpyDeviceToHost, st));
   return PIE_OK;
 }
 int report_checks(const PendingChecks& c, const int32_t* host_flags) {
@@ -709,6 +711,7 @@ struct CsvPipeline {
   cudaStream_t h2d = nullptr, cmp = nullptr, d2h = nullptr;
   cudaEvent_t h2d_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
   OutBuffer out[2];
+  OutBuffer off[2];  // a chunk's row offsets + total: NOT in the input arena, which is refilled while they download
   unsigned long long* h_total = nullptr;  // pinned
   int init() {
     if (h2d) return PIE_OK;
@@ -725,6 +728,39 @@ struct CsvPipeline {
   }
 };
 static CsvPipeline g_pipe;
+
+// Developer aid (PIE_DEBUG_TIMELINE=1): when each chunk's upload, kernels and download finished, in ms since the call
+// began, printed to stderr — the only timeline tool there is without nsys.
+struct Timeline {
+  bool on = getenv("PIE_DEBUG_TIMELINE") != nullptr;
+  cudaEvent_t start = nullptr;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> what;
+  std::vector<int> chunk;
+  void begin(cudaStream_t st) {
+    if (!on) return;
+    cudaEventCreate(&start);
+    cudaEventRecord(start, st);
+  }
+  void mark(cudaStream_t st, const char* w, int k) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.push_back(e); what.push_back(w); chunk.push_back(k);
+  }
+  void report() {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    for (size_t i = 0; i < ev.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, start, ev[i]);
+      fprintf(stderr, "[timeline] chunk %2d %-10s %8.2f ms\n", chunk[i], what[i], ms);
+      cudaEventDestroy(ev[i]);
+    }
+    cudaEventDestroy(start);
+  }
+};
 
 struct CsvChunk {
   int64_t s0, s1, e0, e1;
@@ -772,8 +808,8 @@ static int upload_chunk(CsvChunk* c, int slot, uint64_t* h2d, RowFormat format) 
   if (rc) return rc;
   c->checks = g_checks;
   c->scratch = g_cur->take(pie::csv_scratch_bytes(E));
-  c->d_offsets = (int64_t*)g_cur->take(8 * (uint64_t)(E + 1));
-  c->d_total = (unsigned long long*)g_cur->take(16);
+  c->d_offsets = nullptr;  // in the slot's offsets buffer (export_rows_host)
+  c->d_total = nullptr;
   return PIE_OK;
 }
 
@@ -900,28 +936,38 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
   uint64_t h2d = 0, d2h = 0;
   unsigned long long bias = 0;
   bool overflow = false;
+  Timeline tl;
+  tl.begin(g_pipe.h2d);
   if ((rc = upload_chunk(&chunks[0], 0, &h2d, format))) return rc;
   PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[0], g_pipe.h2d));
+  tl.mark(g_pipe.h2d, "uploaded", 0);
   for (int k = 0; k < K; ++k) {
     const int slot = k & 1;
     CsvChunk& c = chunks[(size_t)k];
     const int64_t Ec = c.e1 - c.e0;
     PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.h2d_done[slot], 0));
     int32_t* chunk_flags = reinterpret_cast<int32_t*>(g_pipe.h_total + 8);
-    if ((rc = enqueue_checks(c.checks, 1 + slot, chunk_flags, g_pipe.cmp))) return rc;
+    if ((rc = enqueue_checks(c.checks, 1 + slot, chunk_flags, g_pipe.cmp, true))) return rc;
     if (an && c.s1 > c.s0)  // the chunk's shows: status, launched, primaryIssue and delaySec are resident for the rows
       PIE_CUDA(pie::launch_show_stats(c.dev, d_si + c.s0, d_sf + c.s0, Sc, g_sm_count, g_pipe.cmp));
-    // pass 1: sizes only (row offsets + total), so the output can be placed and sized exactly
-    PIE_CUDA(launch_rows(format, c.dev, c.d_offsets, nullptr, 0, bias, c.d_total, c.scratch, g_pipe.cmp));
-    PIE_CUDA(cudaMemcpyAsync(g_pipe.h_total, c.d_total, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
+    // the chunk's row offsets live in the slot's own buffer: chunk k-2's must have left for the host
+    if (k >= 2) PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.d2h_done[slot], 0));
+    if (g_pipe.off[slot].cap < 8 * (uint64_t)(Ec + 1) + 64) {
+      if (k >= 2) PIE_CUDA(cudaEventSynchronize(g_pipe.d2h_done[slot]));
+      if ((rc = g_pipe.off[slot].ensure(8 * (uint64_t)(Ec + 1) + (uint64_t)(Ec + 1) + 64))) return rc;
+    }
+    c.d_offsets = (int64_t*)g_pipe.off[slot].base;
+    c.d_total = (unsigned long long*)(g_pipe.off[slot].base + ((8 * (uint64_t)(Ec + 1) + 15) & ~(uint64_t)15));
+    // pass 1: sizes only (row offsets + total), so the output can be placed and sized exactly.  The total is written
+    // straight into mapped pinned memory: an 8-byte device-to-host copy would wait in the copy engine's queue behind
+    // the previous chunk's 300 MB download — and with it this chunk's second pass, and the next download.
+    PIE_CUDA(launch_rows(format, c.dev, c.d_offsets, nullptr, 0, bias, g_pipe.h_total, c.scratch, g_pipe.cmp));
     if (k + 1 < K) {  // prefetch the next chunk into the other input arena once chunk k-1's kernels have left it
       // (after this chunk's kernels are enqueued: the host's check of the next chunk's offsets overlaps them)
-      if (k >= 1) {  // ... and its row offsets (which live in that arena) have been copied out
-        PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.kernel_done[slot ^ 1], 0));
-        PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.d2h_done[slot ^ 1], 0));
-      }
+      if (k >= 1) PIE_CUDA(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.kernel_done[slot ^ 1], 0));
       if ((rc = upload_chunk(&chunks[(size_t)k + 1], slot ^ 1, &h2d, format))) return rc;
       PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[slot ^ 1], g_pipe.h2d));
+      tl.mark(g_pipe.h2d, "uploaded", k + 1);
     }
     PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
     if ((rc = report_checks(c.checks, chunk_flags))) return rc;
@@ -940,6 +986,7 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
                            g_pipe.cmp));
     }
     PIE_CUDA(cudaEventRecord(g_pipe.kernel_done[slot], g_pipe.cmp));
+    tl.mark(g_pipe.cmp, "kernels", k);
     PIE_CUDA(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.kernel_done[slot], 0));
     if (Ec > 0)
       PIE_CUDA(cudaMemcpyAsync(row_offsets + c.e0, c.d_offsets, 8 * (uint64_t)Ec, cudaMemcpyDeviceToHost, g_pipe.d2h));
@@ -949,6 +996,7 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
       d2h += total;
     }
     PIE_CUDA(cudaEventRecord(g_pipe.d2h_done[slot], g_pipe.d2h));
+    tl.mark(g_pipe.d2h, "downloaded", k);
     bias += total;
   }
   int an_rc = PIE_OK;
@@ -973,6 +1021,7 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
   }
   PIE_CUDA(cudaStreamSynchronize(g_pipe.d2h));
   PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
+  tl.report();
   row_offsets[E] = (int64_t)bias;
   *total_bytes = bias;
   g_last_h2d = h2d;
@@ -1218,7 +1267,7 @@ OutBuffer g_json_csv_bytes;  // ... and the CSV bytes (grown without moving what
 // spends 80 ms uploading 4.4 GB before the first kernel runs and 60 ms downloading after the last.  Only the daily
 // grouping needs every show: the chunks' tables stay on the device, their show-level columns are joined at the end
 // and the summary runs once.
-static int64_t kJsonChunkDocs = 262144;  // pie_set_json_chunk_docs (tests exercise the multi-chunk path)
+static int64_t kJsonChunkDocs = 131072;  // pie_set_json_chunk_docs (tests exercise the multi-chunk path)
 
 namespace {
 struct JsonChunkState {
@@ -1317,12 +1366,10 @@ static int archive_step_json_chunked(const pie_json_docs* hd, int32_t tz_offset_
     uint8_t* p = g_jc.scratch[slot].base;
     void* d_scratch = p; p += pad(scratch_bytes);
     uint8_t* d_docstat = p; p += pad((uint64_t)n + 1);
-    int64_t* d_totals = (int64_t*)p; p += pad(8 * PIE_INGEST_TOTALS);
-    int32_t* d_status = (int32_t*)p;
     PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.h2d_done[slot], 0));
-    PIE_CUDA(pie::launch_ingest_measure(c.dd, d_scratch, d_docstat, d_totals, d_status, g_pipe.cmp));
-    PIE_CUDA(cudaMemcpyAsync(g_jc.h_small, d_totals, 8 * PIE_INGEST_TOTALS, cudaMemcpyDeviceToHost, g_pipe.cmp));
-    PIE_CUDA(cudaMemcpyAsync(g_jc.h_small + PIE_INGEST_TOTALS, d_status, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
+    // (totals and status go straight into mapped pinned memory: no small copy behind a large download)
+    PIE_CUDA(pie::launch_ingest_measure(c.dd, d_scratch, d_docstat, (int64_t*)g_jc.h_small,
+                                        (int32_t*)(g_jc.h_small + PIE_INGEST_TOTALS), g_pipe.cmp));
     if (k + 1 < K && (rc = upload(k + 1))) return rc;  // the next chunk's text goes up while this one is walked
     PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
     d2h += 8 * PIE_INGEST_TOTALS + 8;
@@ -1351,8 +1398,7 @@ static int archive_step_json_chunked(const pie_json_docs* hd, int32_t tz_offset_
     void* d_cscratch = g_jc.csv[slot].base;
     int64_t* d_rows = (int64_t*)(g_jc.csv[slot].base + csv_scratch);
     unsigned long long* d_total = (unsigned long long*)(g_jc.csv[slot].base + csv_scratch + off_bytes);
-    PIE_CUDA(launch_rows(kFormatCsv, dv, d_rows, nullptr, 0, bias, d_total, d_cscratch, g_pipe.cmp));
-    PIE_CUDA(cudaMemcpyAsync(g_jc.h_small + 32, d_total, 8, cudaMemcpyDeviceToHost, g_pipe.cmp));
+    PIE_CUDA(launch_rows(kFormatCsv, dv, d_rows, nullptr, 0, bias, (unsigned long long*)(g_jc.h_small + 32), d_cscratch, g_pipe.cmp));
     PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
     d2h += 8;
     const unsigned long long total = (unsigned long long)g_jc.h_small[32];
@@ -1561,6 +1607,8 @@ int pie_release(void) {
   free_arena(g_pipe_in[1], false);
   free_out(g_pipe.out[0]);
   free_out(g_pipe.out[1]);
+  free_out(g_pipe.off[0]);
+  free_out(g_pipe.off[1]);
   free_out(g_ingest_out);
   free_out(g_ingest_rows);
   free_out(g_json_csv);

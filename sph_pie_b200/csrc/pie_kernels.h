@@ -28,6 +28,9 @@ struct OffsetsBatch {
 };
 // flags: device int32[kMaxOffsetsArrays]; flags[i] != 0 afterwards: array i was malformed (and now holds empty rows)
 cudaError_t launch_offsets_check(const OffsetsBatch& batch, int32_t* flags, cudaStream_t stream);
+// ... and hands the flags to the host through mapped pinned memory: a small device-to-host copy would queue behind
+// whatever large download occupies the copy engine
+cudaError_t launch_offsets_flags_out(const int32_t* flags, int32_t* mapped_host, cudaStream_t stream);
 cudaError_t launch_rebase_i32(int32_t* dst, const int32_t* src, int64_t n, int32_t add, cudaStream_t stream);
 
 // archive_stats.cu

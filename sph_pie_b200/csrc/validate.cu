@@ -35,6 +35,19 @@ __global__ void __launch_bounds__(256) rebase_i32_kernel(int32_t* __restrict__ d
 }
 }  // namespace
 
+namespace {
+// the flags, stored where the host can read them without a copy engine (mapped pinned memory)
+__global__ void offsets_flags_out_kernel(const int32_t* __restrict__ flags, int32_t* __restrict__ mapped_host) {
+  if (threadIdx.x < kMaxOffsetsArrays) mapped_host[threadIdx.x] = flags[threadIdx.x];
+}
+}  // namespace
+
+cudaError_t launch_offsets_flags_out(const int32_t* flags, int32_t* mapped_host, cudaStream_t stream) {
+  offsets_flags_out_kernel<<<1, kMaxOffsetsArrays, 0, stream>>>(flags, mapped_host);
+  g_launches += 1;
+  return cudaGetLastError();
+}
+
 // dst[i] = src[i] + add: the offsets of a chunk's column moved onto the joined column of a batch
 cudaError_t launch_rebase_i32(int32_t* dst, const int32_t* src, int64_t n, int32_t add, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
