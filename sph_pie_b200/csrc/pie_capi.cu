@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -710,6 +711,7 @@ static int64_t kCsvChunkRows = 1 << 20;  // pie_set_csv_chunk_rows (tests exerci
 struct CsvPipeline {
   cudaStream_t h2d = nullptr, cmp = nullptr, d2h = nullptr;
   cudaEvent_t h2d_done[2] = {nullptr, nullptr}, kernel_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+  cudaEvent_t daily_up = nullptr;  // the daily summary's per-batch arrays are on the device
   OutBuffer out[2];
   OutBuffer off[2];  // a chunk's row offsets + total: NOT in the input arena, which is refilled while they download
   unsigned long long* h_total = nullptr;  // pinned
@@ -723,6 +725,7 @@ struct CsvPipeline {
       PIE_CUDA(cudaEventCreateWithFlags(&kernel_done[i], cudaEventDisableTiming));
       PIE_CUDA(cudaEventCreateWithFlags(&d2h_done[i], cudaEventDisableTiming));
     }
+    PIE_CUDA(cudaEventCreateWithFlags(&daily_up, cudaEventDisableTiming));
     PIE_CUDA(cudaHostAlloc(&h_total, 512, cudaHostAllocDefault));  // [0] a chunk's total; +64: its check flags; +256: the step's
     return PIE_OK;
   }
@@ -864,6 +867,7 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
   void* dscratch = nullptr;
   PendingChecks an_checks;
   an_checks.clear();
+  std::function<int()> upload_daily_inputs;
   memset(&dv_all, 0, sizeof(dv_all));
   if (an) {
     if (format != kFormatCsv) return fail(PIE_ERR_INVALID_ARG, "the step rides on the CSV rows");
@@ -883,21 +887,28 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
     bytes += pad(4 * (uint64_t)(S + 1)) + 2 * pad(8 * (uint64_t)Sc) + pad(8 * (uint64_t)E);
     bytes += pad(4ull * PIE_SI_COUNT * Sc) + pad(8ull * PIE_SF_COUNT * Sc) + daily_out_bytes(S, Sc);
     if ((rc = g_arena.reserve(bytes))) return rc;
-    g_cur = &g_arena;
-    g_cur_stream = g_pipe.h2d;
-    g_checks.clear();
     dv_all.n_shows = S;
     dv_all.n_entries = E;
-    if ((rc = upload_array(hv->entry_offsets, S + 1, &dv_all.entry_offsets, &an_h2d))) return rc;
-    if (S > 0 && (rc = upload_array(hv->created_at, S, &dv_all.created_at, &an_h2d))) return rc;
-    if (hv->archived_at && (rc = upload_array(hv->archived_at, S, &dv_all.archived_at, &an_h2d))) return rc;
-    if (hv->entry_ts && (rc = upload_array(hv->entry_ts, E, &dv_all.entry_ts, &an_h2d))) return rc;
-    if (has_date) { p_date.dst = &dv_all.show_date; if ((rc = upload_strcol(p_date, &an_h2d))) return rc; }
-    if (has_time) { p_time.dst = &dv_all.show_time; if ((rc = upload_strcol(p_time, &an_h2d))) return rc; }
     d_si = (int32_t*)g_arena.take(4ull * PIE_SI_COUNT * Sc);
     d_sf = (double*)g_arena.take(8ull * PIE_SF_COUNT * Sc);
     dscratch = alloc_daily_out(g_arena, S, Sc, &dout);
-    an_checks = g_checks;
+    // The per-batch arrays the daily summary reads (130 MB per 2^20 shows) are needed only at the very end: they go up
+    // BEHIND the last chunk, while the rows are still being computed and downloaded, not in front of the first.
+    upload_daily_inputs = [&, p_date, p_time, has_date, has_time]() mutable -> int {
+      int rc2;
+      g_cur = &g_arena;
+      g_cur_stream = g_pipe.h2d;
+      g_checks.clear();
+      if ((rc2 = upload_array(hv->entry_offsets, S + 1, &dv_all.entry_offsets, &an_h2d))) return rc2;
+      if (S > 0 && (rc2 = upload_array(hv->created_at, S, &dv_all.created_at, &an_h2d))) return rc2;
+      if (hv->archived_at && (rc2 = upload_array(hv->archived_at, S, &dv_all.archived_at, &an_h2d))) return rc2;
+      if (hv->entry_ts && (rc2 = upload_array(hv->entry_ts, E, &dv_all.entry_ts, &an_h2d))) return rc2;
+      if (has_date) { p_date.dst = &dv_all.show_date; if ((rc2 = upload_strcol(p_date, &an_h2d))) return rc2; }
+      if (has_time) { p_time.dst = &dv_all.show_time; if ((rc2 = upload_strcol(p_time, &an_h2d))) return rc2; }
+      an_checks = g_checks;
+      PIE_CUDA(cudaEventRecord(g_pipe.daily_up, g_pipe.h2d));
+      return PIE_OK;
+    };
   }
 
   // chunks of ~kCsvChunkRows rows, cut at show boundaries.  The pipeline's ends are not overlapped — nothing
@@ -969,6 +980,8 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
       PIE_CUDA(cudaEventRecord(g_pipe.h2d_done[slot ^ 1], g_pipe.h2d));
       tl.mark(g_pipe.h2d, "uploaded", k + 1);
     }
+    if (an && K == 1 && (rc = upload_daily_inputs())) return rc;                                    // a single chunk
+    if (an && K > 1 && k + 1 == K - 1 && (rc = upload_daily_inputs())) return rc;                 // behind the last chunk
     PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
     if ((rc = report_checks(c.checks, chunk_flags))) return rc;
     const unsigned long long total = *g_pipe.h_total;
@@ -995,27 +1008,27 @@ static int export_rows_host(RowFormat format, const pie_archive_view* hv, int64_
       PIE_CUDA(cudaMemcpyAsync(out_data + bias, g_pipe.out[slot].base, total, cudaMemcpyDeviceToHost, g_pipe.d2h));
       d2h += total;
     }
+    if (an && an->stats_i32 && c.s1 > c.s0) {  // the chunk's columns of the statistics planes
+      const uint64_t ns = (uint64_t)(c.s1 - c.s0);
+      PIE_CUDA(cudaMemcpy2DAsync(an->stats_i32 + c.s0, 4 * (uint64_t)an->stats_stride, d_si + c.s0, 4 * (uint64_t)Sc, 4 * ns,
+                                 PIE_SI_COUNT, cudaMemcpyDeviceToHost, g_pipe.d2h));
+      PIE_CUDA(cudaMemcpy2DAsync(an->stats_f64 + c.s0, 8 * (uint64_t)an->stats_stride, d_sf + c.s0, 8 * (uint64_t)Sc, 8 * ns,
+                                 PIE_SF_COUNT, cudaMemcpyDeviceToHost, g_pipe.d2h));
+      d2h += (4ull * PIE_SI_COUNT + 8ull * PIE_SF_COUNT) * ns;
+    }
     PIE_CUDA(cudaEventRecord(g_pipe.d2h_done[slot], g_pipe.d2h));
     tl.mark(g_pipe.d2h, "downloaded", k);
     bias += total;
   }
   int an_rc = PIE_OK;
   if (an) {
-    // the first chunk's upload was enqueued after the per-batch arrays on the same stream, so the compute stream
-    // (which waited for that chunk) already sees them
+    PIE_CUDA(cudaStreamWaitEvent(g_pipe.cmp, g_pipe.daily_up, 0));  // the per-batch arrays went up behind the last chunk
     int32_t* an_flags = reinterpret_cast<int32_t*>(g_pipe.h_total + 32);
     if ((rc = enqueue_checks(an_checks, 0, an_flags, g_pipe.cmp))) return rc;
     PIE_CUDA(cudaStreamSynchronize(g_pipe.cmp));
     if ((rc = report_checks(an_checks, an_flags))) return rc;
     PIE_CUDA(pie::launch_daily_summary(dv_all, d_si, d_sf, Sc, an->tz_offset_minutes, dout, dscratch, g_sm_count,
                                        g_pipe.cmp));
-    if (an->stats_i32 && S > 0) {
-      PIE_CUDA(cudaMemcpy2DAsync(an->stats_i32, 4 * (uint64_t)an->stats_stride, d_si, 4 * (uint64_t)Sc, 4 * (uint64_t)S,
-                                 PIE_SI_COUNT, cudaMemcpyDeviceToHost, g_pipe.cmp));
-      PIE_CUDA(cudaMemcpy2DAsync(an->stats_f64, 8 * (uint64_t)an->stats_stride, d_sf, 8 * (uint64_t)Sc, 8 * (uint64_t)S,
-                                 PIE_SF_COUNT, cudaMemcpyDeviceToHost, g_pipe.cmp));
-      d2h += (4ull * PIE_SI_COUNT + 8ull * PIE_SF_COUNT) * (uint64_t)S;
-    }
     an_rc = download_daily(an->hout, dout, S, Sc, g_pipe.cmp, &d2h);
     h2d += an_h2d;
   }
@@ -1639,6 +1652,7 @@ int pie_release(void) {
       cudaEventDestroy(g_pipe.kernel_done[i]);
       cudaEventDestroy(g_pipe.d2h_done[i]);
     }
+    cudaEventDestroy(g_pipe.daily_up);
     cudaFreeHost(g_pipe.h_total);
     g_pipe = CsvPipeline();
   }
