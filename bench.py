@@ -491,6 +491,9 @@ def main():
                      + 4 * (S + 1) + (4 * _lib.PIE_CM_COUNT + _lib.PIE_CM_TEXT) * S)
     del m_i32, m_text
 
+    # ... and the rows widened in round 2: the schemaVersion 2 show payload and the provider's maintenance decisions
+    widened = widened_leg(table, dev, S, E, n_payload_runs, args.tz)
+
     # ... and the JSON ingest of the stored documents: a sample archive written out as
     # show_archive.data texts, repeated on the device to the bench's number of shows
     # (N = 1 only, like the CPU baseline: it is reported by rank 0 and would only add pinned memory on the others)
@@ -681,6 +684,10 @@ def main():
                     "entries_per_s": E / (payload_ms * 1e-3)},
                 "JSON ingest of stored documents (ingest_walk_kernel x2 + scans, not part of the step)":
                     dict(ingest, frac=ingest["achieved_gbs"] / peak, traffic=ingest_traffic) if ingest else None,
+                "schemaVersion 2 show payloads (payload_measure_kernel + scan + payload_write_kernel, not part of the step)":
+                    dict(widened["show_payloads"], frac=widened["show_payloads"]["achieved_gbs"] / peak),
+                "provider maintenance (get_timestamps + _archiveDailyShows + _purgeExpiredArchives decisions, not part of the step)":
+                    widened["maintenance"],
                 "computeMetrics per show (compute_metrics_kernel, not part of the step)": {
                     "ms_per_launch": metrics_ms, "algorithmic_bytes": metrics_bytes,
                     "achieved_gbs": gbs(metrics_bytes, metrics_ms), "frac": gbs(metrics_bytes, metrics_ms) / peak,
@@ -701,6 +708,76 @@ def main():
     print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def widened_leg(table, dev, S, E, runs, tz):
+    """CUDA-event times of pie_show_payloads_dev (sizing call + writing call, as a caller makes them) and of
+    pie_get_timestamps_dev + pie_archive_due_dev + pie_archive_expired_dev on the resident bench table."""
+    import ctypes as C
+
+    import torch
+
+    from sph_pie_b200 import _lib, ops
+    from sph_pie_b200.webhook import payload_frame
+
+    lib = _lib.load()
+    head, tail = payload_frame("show.updated", "2024-07-03T12:00:00.000Z", "https://example.invalid/hook", "POST", None)
+    first = ops.show_payloads(table, head, tail)          # sizes, allocates, writes; also the warm-up
+    total = int(first.data.numel())
+    h = torch.tensor(list(head), dtype=torch.uint8, device=dev)
+    t = torch.tensor(list(tail), dtype=torch.uint8, device=dev)
+    offs = torch.zeros(S + 1, dtype=torch.int64, device=dev)
+    tot = torch.zeros(1, dtype=torch.int64, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    scratch = torch.empty(int(lib.pie_show_payloads_scratch_bytes(S)) + 256, dtype=torch.uint8, device=dev)
+    sptr = (scratch.data_ptr() + 255) & ~255
+    view = table.view()
+    stream = torch.cuda.current_stream().cuda_stream
+    data = first.data
+
+    def payload_call():
+        _lib.check(lib.pie_show_payloads_dev(C.byref(view), h.data_ptr(), len(head), t.data_ptr(), len(tail), offs.data_ptr(),
+                                             data.data_ptr(), total, tot.data_ptr(), status.data_ptr(), sptr, stream))
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    payload_call()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(runs):
+        payload_call()
+    e1.record()
+    torch.cuda.synchronize()
+    payload_ms = e0.elapsed_time(e1) / runs
+    assert status.cpu().tolist()[0] == 0 and int(tot.cpu()) == total and torch.equal(offs, first.doc_offsets)
+    in_bytes = table.nbytes()                              # every column once
+    payload_bytes = in_bytes + total + 8 * (S + 1)
+    del first, data, scratch
+
+    # maintenance decisions on the same table
+    created = ops.get_timestamps(table, None, tz).created_at
+    now_ms = float(created[~torch.isnan(created)].max().cpu()) + 13 * 3600e3 if S else 0.0
+    ops.archive_due(table, created, now_ms)
+    ops.archive_expired(created, now_ms, tz)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(runs):
+        times = ops.get_timestamps(table, None, tz)       # includes its status read-back (a sync), as the caller pays it
+        due, _first = ops.archive_due(table, times.created_at, now_ms)
+        expired = ops.archive_expired(times.created_at, now_ms, tz)
+    e1.record()
+    torch.cuda.synchronize()
+    maint_ms = e0.elapsed_time(e1) / runs
+    return {
+        "show_payloads": {"ms_per_call": payload_ms, "algorithmic_bytes": payload_bytes, "json_bytes_out": total,
+                          "achieved_gbs": payload_bytes / (payload_ms * 1e-3) / 1e9, "shows_per_s": S / (payload_ms * 1e-3),
+                          "entries_per_s": E / (payload_ms * 1e-3),
+                          "what": "one call: measure pass + scan + write pass over every column; documents of ~"
+                                  f"{total // max(S, 1)} bytes"},
+        "maintenance": {"ms_per_round": maint_ms, "shows_per_s": S / (maint_ms * 1e-3), "due": int(due.sum().cpu()),
+                        "expired": int(expired.sum().cpu()),
+                        "what": "pie_get_timestamps_dev + pie_archive_due_dev + pie_archive_expired_dev, S-sized "
+                                "(no per-entry work), through the Python operators incl. their allocations and one status read-back"},
+    }
 
 
 def ingest_leg(args, dev, n_shows, runs, note):

@@ -15,7 +15,7 @@ import __graft_entry__ as entry  # noqa: E402
 
 # kernels launched by one call of the entry point the group stands for (csv_rows.cu launch_rows)
 GROUPS = {
-    "export_rows_csv": ["expand_entry_show_kernel", "column_dirty_kernel", "plan_tile_rows_kernel", "export_rows_kernel<csv>"],
+    "export_rows_csv": ["expand_entry_show_kernel", "column_sample_kernel", "plan_tile_rows_kernel", "export_rows_kernel<csv>"],
     "export_rows_json": ["export_rows_kernel<json>"],
     "ingest": ["ingest_order_count_kernel", "ingest_order_scan_kernel", "ingest_order_place_kernel", "ingest_init_kernel",
                "ingest_walk_kernel<measure>", "ingest_scan_sums_kernel", "ingest_scan_blocks_kernel",

@@ -423,16 +423,18 @@ __device__ __forceinline__ double metric_value(const int32_t* __restrict__ si, c
   return sf[(int64_t)(m - 4) * stride + s];
 }
 
-// One thread per daily group, all 19 metrics: the group's member list is read once.
+// One thread per (daily group, metric); blockIdx.y is the metric.  A group's sum has to run left to right, so a group
+// cannot be split further — but an archive with few days and many shows per day (the replicated sample of the ingest
+// bench: 2.6 ms with a thread per group) still gets 19x the threads, and on many small groups the 19 short walks of a
+// group run side by side instead of one after the other.
 __global__ void __launch_bounds__(128) daily_summary_kernel(const int32_t* __restrict__ si, const double* __restrict__ sf,
                                                             int64_t stats_stride, pie_daily_out out) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= *out.n_groups) return;
-  const int b = out.group_offsets[g], e = out.group_offsets[g + 1];
+  const int64_t n_groups = *out.n_groups;
+  const int m = (int)blockIdx.y;
   const double nan = quiet_nan();
   const int64_t plane = (int64_t)PIE_N_METRICS * out.stride;
-#pragma unroll 1
-  for (int m = 0; m < PIE_N_METRICS; ++m) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int b = out.group_offsets[g], e = out.group_offsets[g + 1];
     double sum = 0.0;
     long long kmin = kKeyHighest, kmax = kKeyLowest;  // Math.min / Math.max as integer min / max
     int n = 0;
@@ -478,7 +480,9 @@ cudaError_t launch_daily_summary(const pie_archive_view& v, const int32_t* si, c
   group_scan_kernel<<<1, 1024, 0, stream>>>(d, n > 0 ? nblk : 1, out);
   if (n > 0) {
     group_write_kernel<<<nblk, kThreads, 0, stream>>>(d, n, out);
-    daily_summary_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(si, sf, stats_stride, out);
+    int64_t gx = (n + 127) / 128;  // groups <= shows; the grid cannot know n_groups (it is on the device): stride loop
+    if (gx > (int64_t)sm_count * 2) gx = (int64_t)sm_count * 2;
+    daily_summary_kernel<<<dim3((unsigned)gx, PIE_N_METRICS), 128, 0, stream>>>(si, sf, stats_stride, out);
   }
   return cudaGetLastError();
 }
