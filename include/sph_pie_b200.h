@@ -319,6 +319,16 @@ int pie_show_payloads_dev(const pie_archive_view* dev_view, const uint8_t* head,
 int pie_debug_csv_force_slow_path(int on);
 int pie_debug_csv_slow_tiles(const void* scratch, int64_t n_entries, uint32_t* slow_tiles, void* stream);
 
+/* Debug knobs of the JSON ingest (tests, A/B timing).  The ingest decides documents of the provider's own shape
+ * (JSON.stringify of _normalizeShow's result, sqlProvider.js:361-409) a warp per document and hands every other
+ * document to the thread-per-document walk; results are identical either way.
+ * pie_debug_ingest_warp_path: 1 / 0 switches the warp path on / off, < 0 only queries; returns the previous value
+ * (off unless the environment variable PIE_INGEST_WARP_PATH=1 is set).
+ * pie_debug_ingest_declined: how many documents of the last pie_ingest_measure_dev on `scratch` the warp path
+ * declined (synchronises `stream`). */
+int pie_debug_ingest_warp_path(int on);
+int pie_debug_ingest_declined(const void* scratch, int64_t n_docs, uint32_t* declined, void* stream);
+
 /* ---- JSON ingest: replaces `rows.map(row => this._mapArchiveRow(row)).filter(Boolean)` (server/storage/
  * sqlProvider.js:230-234; _mapArchiveRow :892-926 — JSON.parse(row.data), null unless the value is an object) and
  * `rows.map(r => JSON.parse(r.data))` (:78-82), projected on the archive table: the stored `data` texts (written by

@@ -20,6 +20,13 @@ unit = sys.argv[4] if len(sys.argv) > 4 else "csv_rows"
 
 src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src_csv.splitlines()))
+# a report may hold several kernels: one "Kernel Name" line, one header and the instructions for each; take the
+# first section whose kernel name contains NCU_KERNEL (default: the first section)
+want = os.environ.get("NCU_KERNEL", "")
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] or [0]
+sec = next((i for i in starts if want in (rows[i][1] if len(rows[i]) > 1 else "")), starts[0])
+end = next((i for i in starts if i > sec), len(rows))
+rows = rows[sec:end]
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 col = {h: i for i, h in enumerate(hdr)}

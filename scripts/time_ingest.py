@@ -24,29 +24,40 @@ def main():
     docs, n_entries, nbytes, _ = synth_stored_docs(sample, copies, dev)
     print(f"docs={docs.n_docs} entries={n_entries} text={nbytes / 1e9:.3f} GB (built in {time.time() - t0:.1f}s)", flush=True)
     bufs = ops.IngestBuffers(docs.n_docs, dev)
-    ops.ingest_measure_dev(docs, bufs)
-    totals = bufs.totals.cpu().tolist()
-    assert bufs.status.cpu().tolist()[0] == 0
-    table = ops.alloc_ingest_table(docs.n_docs, totals, dev)
-    out_bytes = table.nbytes()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    tm = tf = 0.0
-    for it in range(iters + 2):
-        ev[0].record()
+    tables = {}
+    for path in ("warp", "walk"):  # the warp-per-document path, then the thread-per-document walk alone
+        ops.set_ingest_warp_path(1 if path == "warp" else 0)
         ops.ingest_measure_dev(docs, bufs)
-        ev[1].record()
-        ops.ingest_fill_dev(docs, bufs, table)
-        ev[2].record()
-        torch.cuda.synchronize()
-        if it >= 2:
-            tm += ev[0].elapsed_time(ev[1])
-            tf += ev[1].elapsed_time(ev[2])
-    tm, tf = tm / iters, tf / iters
-    print(json.dumps({"docs": docs.n_docs, "entries": n_entries, "text_gb": nbytes / 1e9, "table_gb": out_bytes / 1e9,
-                      "measure_ms": tm, "fill_ms": tf, "total_ms": tm + tf,
-                      "text_gbs_measure": nbytes / tm / 1e6, "text_gbs_total": nbytes / (tm + tf) / 1e6,
-                      "algorithmic_gbs": (2 * nbytes + out_bytes) / (tm + tf) / 1e6,
-                      "entries_per_s": n_entries / (tm + tf) * 1e3}))
+        totals = bufs.totals.cpu().tolist()
+        assert bufs.status.cpu().tolist()[0] == 0
+        declined = ops.ingest_declined(bufs, docs.n_docs) if path == "warp" else docs.n_docs
+        table = ops.alloc_ingest_table(docs.n_docs, totals, dev)
+        out_bytes = table.nbytes()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tm = tf = 0.0
+        for it in range(iters + 2):
+            ev[0].record()
+            ops.ingest_measure_dev(docs, bufs)
+            ev[1].record()
+            ops.ingest_fill_dev(docs, bufs, table)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                tm += ev[0].elapsed_time(ev[1])
+                tf += ev[1].elapsed_time(ev[2])
+        tm, tf = tm / iters, tf / iters
+        tables[path] = table
+        print(json.dumps({"path": path, "declined": declined, "docs": docs.n_docs, "entries": n_entries, "text_gb": nbytes / 1e9,
+                          "table_gb": out_bytes / 1e9, "measure_ms": tm, "fill_ms": tf, "total_ms": tm + tf,
+                          "text_gbs_measure": nbytes / tm / 1e6, "text_gbs_total": nbytes / (tm + tf) / 1e6,
+                          "algorithmic_gbs": (nbytes + out_bytes) / (tm + tf) / 1e6,
+                          "entries_per_s": n_entries / (tm + tf) * 1e3}), flush=True)
+    ops.set_ingest_warp_path(1)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from ingest_helpers import assert_tables_equal
+    assert_tables_equal(tables["warp"], tables["walk"], "warp path vs walk")
+    print("tables of both paths equal", flush=True)
 
 
 if __name__ == "__main__":

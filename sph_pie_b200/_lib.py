@@ -158,6 +158,8 @@ SIGNATURES = {
                                             C.POINTER(C.c_uint64)]),
     "pie_debug_csv_force_slow_path": (C.c_int, [C.c_int]),
     "pie_debug_csv_slow_tiles": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32), C.c_void_p]),
+    "pie_debug_ingest_warp_path": (C.c_int, [C.c_int]),
+    "pie_debug_ingest_declined": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32), C.c_void_p]),
     "pie_csv_rows_host": (C.c_int, [C.POINTER(ArchiveViewC), C.c_void_p, C.c_void_p, C.c_uint64,
                                     C.POINTER(C.c_uint64)]),
     "pie_ingest_scratch_bytes": (C.c_uint64, [C.c_int64]),

@@ -28,6 +28,9 @@
 #include "pie_device.cuh"
 #include "pie_kernels.h"
 #include "pie_json_walk.cuh"
+#include "pie_json_fast.cuh"
+
+#include <cstdlib>
 
 namespace pie {
 
@@ -46,7 +49,11 @@ struct IngestScratch {
   unsigned long long* err_key;     // min over documents of (doc << 8 | code): the first hard error
   unsigned long long* next_doc;    // [2] the next place of `order` to hand out in pass 1 / pass 2
   uint32_t* buckets;               // [kOrderBuckets + 1] documents per length class, then where each class starts
-  int32_t* order;                  // [n_docs] the documents by length class
+  int32_t* order;                  // [n_docs] the documents by length class; with the warp path: the documents it declined
+  // the warp-cooperative path (pie_json_fast.cuh)
+  unsigned long long* next_fast;   // [2] the next document a warp takes in pass 1 / pass 2
+  uint32_t* n_slow;                // documents on the list of the thread-per-document walk
+  uint8_t* route;                  // [n_docs] jf::kRouteFast: pass 1 accepted the document on the warp path
 };
 
 // Documents are handed to the warps in order of length (to the byte, up to 16 KB; longer ones share a class), 32 neighbours of that order at a time:
@@ -116,6 +123,47 @@ __global__ void ingest_init_kernel(IngestScratch sc) {
   *sc.err_key = ~0ull;
   sc.next_doc[0] = 0;
   sc.next_doc[1] = 0;
+  sc.next_fast[0] = 0;
+  sc.next_fast[1] = 0;
+  *sc.n_slow = 0;
+}
+
+// The warp-cooperative path: every warp takes documents in table order (neighbours in time write neighbouring parts
+// of every heap) until none is left.  Pass 1 hands what it declines to the list of the thread-per-document walk.
+template <bool kFill>
+__global__ void __launch_bounds__(jf::kFastThreads) ingest_fast_kernel(const int64_t* __restrict__ doc_offsets,
+                                                                       const uint8_t* __restrict__ text, int64_t n_docs,
+                                                                       IngestScratch sc, uint8_t* __restrict__ doc_status,
+                                                                       IngestOut out) {
+  extern __shared__ __align__(16) unsigned char fast_smem[];
+  jf::TablePointers& tp = *reinterpret_cast<jf::TablePointers*>(fast_smem);
+  jf::WarpShared& ws = reinterpret_cast<jf::WarpShared*>(fast_smem + ((sizeof(jf::TablePointers) + 15) & ~(size_t)15))[threadIdx.x >> 5];
+  if (kFill) {
+    for (int h = threadIdx.x; h < kHeaps; h += blockDim.x) {
+      tp.data[h] = out.data[h];
+      tp.off[h] = out.off[h];
+    }
+  }
+  __syncthreads();
+  const Pow5Table pow5{g_pow5_dev};
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned long long drawn = 0;
+    if (lane == 0) drawn = atomicAdd(sc.next_fast + (kFill ? 1 : 0), 1ull);
+    const int64_t s = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
+    if (s >= n_docs) break;
+    if (kFill) {
+      if (sc.route[s] != jf::kRouteFast) continue;
+      jf::fast_doc<true>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out, pow5);
+    } else {
+      const bool ok = jf::fast_doc<false>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out, pow5);
+      if (lane == 0) {
+        sc.route[s] = ok ? jf::kRouteFast : jf::kRouteSlow;
+        if (ok) doc_status[s] = 0;
+        else sc.order[atomicAdd(sc.n_slow, 1u)] = (int32_t)s;
+      }
+    }
+  }
 }
 
 // Both passes: every lane walks documents until none is left.
@@ -123,9 +171,11 @@ template <bool kFill>
 __global__ void __launch_bounds__(kIngestThreads, kFill ? 8 : 10) ingest_walk_kernel(const int64_t* __restrict__ doc_offsets,
                                                                       const uint8_t* __restrict__ text, int64_t n_docs,
                                                                       IngestScratch sc, uint8_t* __restrict__ doc_status,
-                                                                      IngestOut out) {
+                                                                      IngestOut out, const uint32_t* __restrict__ list_len) {
   const Pow5Table pow5{g_pow5_dev};
   const int32_t* __restrict__ order = sc.order;
+  // list_len: `order` is the list of what the warp path declined (in no particular order), not all the documents
+  const int64_t n_order = list_len ? (int64_t)*list_len : n_docs;
   uint32_t cnt[kPlanes];
   DocWalker<kFill> w;
   bool active = false, exhausted = false;
@@ -138,7 +188,7 @@ __global__ void __launch_bounds__(kIngestThreads, kFill ? 8 : 10) ingest_walk_ke
     base = __shfl_sync(0xffffffffu, base, 0);
     const int64_t drawn = (int64_t)base + (threadIdx.x & 31);
     if (!exhausted) {
-      s = drawn < n_docs ? order[drawn] : n_docs;
+      s = drawn < n_order ? order[drawn] : n_docs;
       if (s >= n_docs) {
         exhausted = true;
       } else {
@@ -393,7 +443,45 @@ IngestScratch carve(void* scratch, int64_t n_docs) {
   sc.buckets = (uint32_t*)p;
   p += 4 * (kOrderBuckets + 2);
   sc.order = (int32_t*)p;
+  p += 4 * (uint64_t)stride;
+  sc.next_fast = (unsigned long long*)p;
+  sc.n_slow = (uint32_t*)(sc.next_fast + 2);
+  p += 32;
+  sc.route = p;
   return sc;
+}
+
+// PIE_INGEST_WARP_PATH=0 keeps every document on the thread-per-document walk (the round-1 pipeline: A/B timing)
+std::atomic<int> g_warp_path{-1};  // -1: not decided yet (the environment decides)
+bool warp_path_enabled() {
+  int v = g_warp_path.load();
+  if (v < 0) {
+    const char* e = std::getenv("PIE_INGEST_WARP_PATH");
+    v = (e && e[0] == '1') ? 1 : 0;  // opt-in until it beats the walk on every workload (profiles/ncu_r02_ingest_summary.md)
+    g_warp_path.store(v);
+  }
+  return v != 0;
+}
+constexpr size_t kFastSmemBytes = ((sizeof(jf::TablePointers) + 15) & ~(size_t)15) + sizeof(jf::WarpShared) * jf::kFastWarps;
+
+template <bool kFill>
+cudaError_t fast_kernel_ready(int* blocks_per_sm) {
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    cudaError_t e = cudaFuncSetAttribute(ingest_fast_kernel<kFill>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes);
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ingest_fast_kernel<kFill>, jf::kFastThreads, kFastSmemBytes);
+    if (e != cudaSuccess) return e;
+    per_sm = n > 0 ? n : 1;
+  }
+  *blocks_per_sm = per_sm;
+  return cudaSuccess;
+}
+unsigned fast_blocks(int64_t n_docs, int per_sm) {
+  const int64_t want = (n_docs + jf::kFastWarps - 1) / jf::kFastWarps;
+  const int64_t cap = (int64_t)sm_count_or_default() * per_sm;
+  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
 IngestOut make_out(const pie_archive_table& t) {
@@ -429,10 +517,22 @@ IngestOut make_out(const pie_archive_table& t) {
 
 }  // namespace
 
+int ingest_set_warp_path(int on) {
+  const int old = warp_path_enabled() ? 1 : 0;
+  if (on >= 0) g_warp_path.store(on ? 1 : 0);
+  return old;
+}
+cudaError_t ingest_read_declined(const void* scratch, int64_t n_docs, unsigned int* out, cudaStream_t stream) {
+  IngestScratch sc = carve(const_cast<void*>(scratch), n_docs);
+  cudaError_t e = cudaMemcpyAsync(out, sc.n_slow, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(stream);
+}
+
 uint64_t ingest_scratch_bytes(int64_t n_docs) {
   const int64_t stride = ((n_docs > 0 ? n_docs : 1) + 31) & ~(int64_t)31;
   return (uint64_t)kPlanes * stride * 4 + ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8 + 64 + 4 * (kOrderBuckets + 2) +
-         4 * (uint64_t)(n_docs > 0 ? n_docs : 1);
+         4 * (uint64_t)stride + 32 + (uint64_t)stride;
 }
 
 cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint8_t* doc_status, int64_t* totals,
@@ -447,15 +547,28 @@ cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint
   ingest_init_kernel<<<1, 1, 0, stream>>>(sc);
   ++g_launches;
   if (n > 0) {
-    const unsigned doc_blocks = (unsigned)((n + 255) / 256);
-    ingest_order_count_kernel<<<doc_blocks, 256, 0, stream>>>(docs.offsets, n, sc);
-    ingest_order_scan_kernel<<<1, 1024, 0, stream>>>(sc);
-    ingest_order_place_kernel<<<doc_blocks, 256, 0, stream>>>(docs.offsets, n, sc);
-    g_launches += 3;
-    ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, doc_status,
-                                                                            IngestOut{});
+    if (warp_path_enabled()) {
+      // the warp path takes every document it can decide; what it declines goes on sc.order for the walk
+      int per_sm = 1;
+      e = fast_kernel_ready<false>(&per_sm);
+      if (e != cudaSuccess) return e;
+      ingest_fast_kernel<false><<<fast_blocks(n, per_sm), jf::kFastThreads, kFastSmemBytes, stream>>>(docs.offsets, docs.data, n, sc,
+                                                                                                   doc_status, IngestOut{});
+      ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, doc_status,
+                                                                              IngestOut{}, sc.n_slow);
+      g_launches += 2;
+    } else {
+      const unsigned doc_blocks = (unsigned)((n + 255) / 256);
+      ingest_order_count_kernel<<<doc_blocks, 256, 0, stream>>>(docs.offsets, n, sc);
+      ingest_order_scan_kernel<<<1, 1024, 0, stream>>>(sc);
+      ingest_order_place_kernel<<<doc_blocks, 256, 0, stream>>>(docs.offsets, n, sc);
+      g_launches += 3;
+      ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, doc_status,
+                                                                              IngestOut{}, nullptr);
+      ++g_launches;
+    }
     ingest_scan_sums_kernel<<<nblk, kScanThreads, 0, stream>>>(sc, n, nblk);
-    g_launches += 2;
+    ++g_launches;
   }
   ingest_scan_blocks_kernel<<<kPlanes, 1024, 0, stream>>>(sc, nblk, totals, status);
   ++g_launches;
@@ -474,12 +587,25 @@ cudaError_t launch_ingest_fill(const pie_json_docs& docs, const void* scratch, c
   IngestScratch sc = carve(const_cast<void*>(scratch), n);
   cudaError_t e = cudaMemsetAsync(sc.next_doc + 1, 0, 8, stream);  // pass 2 may run more than once per pass 1
   if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(sc.next_fast + 1, 0, 8, stream);
+  if (e != cudaSuccess) return e;
   IngestOut out = make_out(table);
   out.text = docs.data;
-  if (n > 0) {
+  if (n > 0 && warp_path_enabled()) {
+    // both kernels write the table's columns directly (the walk's entry rows are for when it takes every document)
+    int per_sm = 1;
+    e = fast_kernel_ready<true>(&per_sm);
+    if (e != cudaSuccess) return e;
+    out.rows = nullptr;
+    ingest_fast_kernel<true><<<fast_blocks(n, per_sm), jf::kFastThreads, kFastSmemBytes, stream>>>(docs.offsets, docs.data, n, sc,
+                                                                                                const_cast<uint8_t*>(doc_status), out);
+    ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc,
+                                                                           const_cast<uint8_t*>(doc_status), out, sc.n_slow);
+    ++g_launches;
+  } else if (n > 0) {
     out.rows = static_cast<EntryRow*>(fill_scratch);
     ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc,
-                                                                           const_cast<uint8_t*>(doc_status), out);
+                                                                           const_cast<uint8_t*>(doc_status), out, nullptr);
     if (table.n_entries > 0) {
       ingest_rows_to_columns_kernel<<<(unsigned)((table.n_entries + 255) / 256), 256, 0, stream>>>(out.rows, table.n_entries, out);
       ++g_launches;

@@ -694,6 +694,18 @@ int pie_archive_payloads_dev(const pie_archive_view* v, int64_t* row_offsets, ui
 
 int pie_debug_csv_force_slow_path(int on) { return pie::csv_set_force_slow(on); }
 
+int pie_debug_ingest_warp_path(int on) { return pie::ingest_set_warp_path(on); }
+
+int pie_debug_ingest_declined(const void* scratch, int64_t n_docs, uint32_t* declined, void* stream) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!scratch || !declined || n_docs < 0) return fail(PIE_ERR_INVALID_ARG, "NULL argument");
+  unsigned int n = 0;
+  PIE_CUDA(pie::ingest_read_declined(scratch, n_docs, &n, (cudaStream_t)stream));
+  *declined = n;
+  return PIE_OK;
+}
+
 int pie_debug_csv_slow_tiles(const void* scratch, int64_t n_entries, uint32_t* slow_tiles, void* stream) {
   int rc = ensure_init();
   if (rc) return rc;

@@ -420,6 +420,19 @@ def ingest_fill_dev(docs: JsonDocs, bufs: IngestBuffers, table: ArchiveTable) ->
                                        bufs.fill_scratch.data_ptr(), _stream_ptr()))
 
 
+def set_ingest_warp_path(on: int) -> int:
+    """Debug knob: the warp-per-document path of the ingest on (1) / off (0), < 0 only queries; returns the previous
+    value.  Results are identical either way (tests/test_gpu_ingest.py); off = the thread-per-document walk alone."""
+    return int(_lib.load().pie_debug_ingest_warp_path(int(on)))
+
+
+def ingest_declined(bufs: IngestBuffers, n_docs: int) -> int:
+    """How many documents of the last ingest_measure_dev on `bufs` the warp path declined (synchronises)."""
+    n = C.c_uint32(0)
+    _lib.check(_lib.load().pie_debug_ingest_declined(bufs.scratch.data_ptr(), n_docs, C.byref(n), _stream_ptr()))
+    return int(n.value)
+
+
 def ingest_json(docs: JsonDocs, bufs: IngestBuffers = None):
     """Stored show documents -> (ArchiveTable, doc_status uint8[n]): what
     `rows.map(row => this._mapArchiveRow(row))` (sqlProvider.js:230-234, :892-926) parses, laid out as the table

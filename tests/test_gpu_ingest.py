@@ -35,6 +35,141 @@ def gpu_check(cuda, docs, what="", host_too=True):
     return table
 
 
+@pytest.fixture(params=["warp", "walk"])
+def both_paths(request):
+    """Runs a test with the warp-per-document path on and off (off = the thread-per-document walk takes everything)."""
+    old = ops.set_ingest_warp_path(1 if request.param == "warp" else 0)
+    yield request.param
+    ops.set_ingest_warp_path(old)
+
+
+def canonical_shows(n, seed):
+    """Shows the way the provider normalises them (sqlProvider.js:361-409): every entry holds all of its 17 keys."""
+    host = synth_archive(n, seed=seed, missing_created_frac=0.1)
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+    host.delay_valid[lost] = 0
+    return table_to_shows(host)
+
+
+def declined_of(cuda, docs):
+    jd = ops.JsonDocs.from_texts(docs).to(cuda)
+    bufs = ops.IngestBuffers(jd.n_docs, cuda)
+    ops.ingest_measure_dev(jd, bufs)
+    return ops.ingest_declined(bufs, jd.n_docs)
+
+
+def test_warp_path_takes_the_providers_documents_and_declines_the_rest(cuda):
+    old = ops.set_ingest_warp_path(1)
+    try:
+        rng = random.Random(2)
+        shows = canonical_shows(300, 5)
+        docs = [stored_doc(s, rng, "stringify") for s in shows]
+        small = [d for d in docs if len(d.encode()) <= 8000]
+        assert len(small) > 250
+        assert declined_of(cuda, small) == 0  # every document of the provider's own shape is decided by a warp
+        gpu_check(cuda, docs, "canonical", host_too=False)
+        pretty = [stored_doc(s, rng, "pretty") for s in shows[:50]]
+        assert declined_of(cuda, pretty) == 50  # whitespace between tokens: the walk's business
+        assert declined_of(cuda, ["", "{", "[]", "null", '{"id":1}', '{"entries":[{}]}', '{"entries":[{"id":"a"}]}']) == 7
+        # shapes the warp path takes although they are not what the provider writes
+        assert declined_of(cuda, ["{}", '{"id":"a"}', '{"id":null,"x":1,"y":"z","entries":[],"crew":[]}', '{"crew":["a","b"]}']) == 0
+    finally:
+        ops.set_ingest_warp_path(old)
+
+
+def test_damaged_canonical_documents(cuda, both_paths):
+    """Every prefix and thousands of single-byte damages of documents of the provider's shape: whatever the warp path
+    accepts must be what the oracle makes of it; the rest goes to the walk.  Strings with escapes, non-ASCII text,
+    crew and actions lists are part of the documents."""
+    rng = random.Random(41)
+    shows = canonical_shows(40, 9)
+    notes = ['line\none "quoted" \\ back', "caf\u00e9 \u00fc \u20ac", "tab\there", "", "\u4e2d\u6587 \U0001f600 \x7f"]
+    for k, sh in enumerate(shows):
+        sh["notes"] = notes[k % 5]
+        sh["crew"] = ["Ann", 'B "ob"', "Zo\u00eb"][:k % 4]
+        for j, e in enumerate(sh["entries"]):
+            if j % 3 == 0:
+                e["actions"] = ["Swap battery", "Re\u00efnit", 'say "hi"\n'][:1 + j % 3]
+    docs = []
+    for sh in shows:
+        doc = stored_doc(sh, rng, "stringify")
+        if len(doc) < 2500 and len(docs) < 8000:
+            docs += [doc[:k] for k in range(len(doc) + 1)]
+    alphabet = '"\\{}[]:,0-9.eE+tfn ux\n\t\x01a\u00e9'
+    for sh in shows:
+        doc = stored_doc(sh, rng, "stringify")
+        docs.append(doc)
+        for _ in range(150):
+            k = rng.randrange(len(doc))
+            docs.append(doc[:k] + rng.choice(alphabet) + doc[k + 1:])
+        for _ in range(30):  # a character less, a character more
+            k = rng.randrange(len(doc))
+            docs.append(doc[:k] + doc[k + 1:])
+            docs.append(doc[:k] + rng.choice(alphabet) + doc[k:])
+    keep = []
+    for d in docs:
+        try:
+            oracle_ingest([d])
+            keep.append(d)
+        except (TypeError, po.UnsupportedJson):
+            pass
+    assert len(keep) > 5000
+    gpu_check(cuda, keep, "damaged canonical", host_too=False)
+
+
+def _outcome(jd):
+    try:
+        table, status = ops.ingest_json(jd)
+        torch.cuda.synchronize()
+        return ("ok", table, status.cpu())
+    except (_lib.UnsupportedJsonError, _lib.SchemaError) as e:
+        return ("error", type(e).__name__, e.doc)
+
+
+def test_raw_byte_damage_and_alignment(cuda):
+    """Damage below the character level (bytes that break UTF-8): both paths must do the same with every batch — the
+    same table, or the same error with the same document.  Then documents at every alignment of the text."""
+    rng = random.Random(43)
+    shows = canonical_shows(12, 13)
+    for sh in shows:
+        sh["label"] = "caf\u00e9 \u4e2d \U0001f600"
+    nasty = [0x80, 0xBF, 0xC0, 0xC2, 0xE0, 0xED, 0xF0, 0xF4, 0xF5, 0xFF, 0x00, 0x1F, 0x22, 0x5C, 0xA0, 0x9F, 0x8F, 0x90]
+    good = stored_doc(shows[0], rng, "stringify").encode()
+    old = ops.set_ingest_warp_path(1)
+    try:
+        n_err = n_ok = 0
+        for sh in shows:
+            raw = stored_doc(sh, rng, "stringify").encode("utf-8")
+            hi = [i for i, c in enumerate(raw) if c >= 0x80]
+            batch = []
+            for _ in range(60):
+                k = rng.choice(hi) + rng.randrange(-2, 3) if hi and rng.random() < 0.7 else rng.randrange(len(raw))
+                k = min(max(k, 0), len(raw) - 1)
+                batch.append(raw[:k] + bytes([rng.choice(nasty)]) + raw[k + 1:])
+            for b in batch:
+                jd = ops.JsonDocs.from_texts([good, b, good]).to(cuda)
+                ops.set_ingest_warp_path(1)
+                got = _outcome(jd)
+                ops.set_ingest_warp_path(0)
+                ref = _outcome(jd)
+                assert got[0] == ref[0], b
+                if got[0] == "error":
+                    assert got[1:] == ref[1:], b
+                    n_err += 1
+                else:
+                    assert torch.equal(got[2], ref[2]), b
+                    assert_tables_equal(got[1], ref[1], repr(b))
+                    n_ok += 1
+        assert n_err > 50 and n_ok > 50
+        ops.set_ingest_warp_path(1)
+        # every alignment: the same documents behind 0..40 bytes of another document
+        base = [stored_doc(sh, rng, "stringify") for sh in shows[:4]]
+        for pad in range(0, 41):
+            gpu_check(cuda, ["x" * pad] + base, f"pad {pad}", host_too=False)
+    finally:
+        ops.set_ingest_warp_path(old)
+
+
 @pytest.mark.parametrize("style", ["stringify", "ascii", "pretty", "shuffled"])
 def test_synthetic_archive_round_trips(cuda, style):
     rng = random.Random(3)
