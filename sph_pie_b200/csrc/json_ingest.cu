@@ -40,6 +40,12 @@ using namespace jw;
 
 __device__ const uint64_t g_pow5_dev[PIE_POW5_128_N][2] = PIE_POW5_128_INIT;
 
+constexpr jf::KeyTables key_tables_checked() {
+  bool clash = false;
+  return jf::make_key_tables(&clash);
+}
+__device__ const jf::KeyTables g_key_tables = key_tables_checked();
+
 constexpr int kIngestThreads = 128;
 
 struct IngestScratch {
@@ -53,7 +59,8 @@ struct IngestScratch {
   // the warp-cooperative path (pie_json_fast.cuh)
   unsigned long long* next_fast;   // [2] the next document a warp takes in pass 1 / pass 2
   uint32_t* n_slow;                // documents on the list of the thread-per-document walk
-  uint8_t* route;                  // [n_docs] jf::kRouteFast: pass 1 accepted the document on the warp path
+  uint8_t* route;                  // [n_docs] jf::kRouteFast / kRouteRecords: pass 1 accepted the document on the warp path
+  jf::RecCtx rec;                  // the records pass 1 leaves for pass 2 (pie_json_fast.cuh)
 };
 
 // Documents are handed to the warps in order of length (to the byte, up to 16 KB; longer ones share a class), 32 neighbours of that order at a time:
@@ -126,6 +133,7 @@ __global__ void ingest_init_kernel(IngestScratch sc) {
   sc.next_fast[0] = 0;
   sc.next_fast[1] = 0;
   *sc.n_slow = 0;
+  *sc.rec.cursor = 0;
 }
 
 // The warp-cooperative path: every warp takes documents in table order (neighbours in time write neighbouring parts
@@ -144,6 +152,8 @@ __global__ void __launch_bounds__(jf::kFastThreads) ingest_fast_kernel(const int
       tp.off[h] = out.off[h];
     }
   }
+  for (int i = threadIdx.x; i < (int)(sizeof(jf::KeyTables) / 8); i += blockDim.x)
+    reinterpret_cast<unsigned long long*>(&tp.keys)[i] = reinterpret_cast<const unsigned long long*>(&g_key_tables)[i];
   __syncthreads();
   const Pow5Table pow5{g_pow5_dev};
   const int lane = threadIdx.x & 31;
@@ -153,13 +163,17 @@ __global__ void __launch_bounds__(jf::kFastThreads) ingest_fast_kernel(const int
     const int64_t s = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
     if (s >= n_docs) break;
     if (kFill) {
-      if (sc.route[s] != jf::kRouteFast) continue;
-      jf::fast_doc<true>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out, pow5);
+      const uint8_t route = sc.route[s];
+      if (route == jf::kRouteRecords)
+        jf::fill_records(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, sc.planes + s * kPlanes, out, sc.rec);
+      else if (route == jf::kRouteFast)
+        jf::fast_doc<true>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out, pow5, sc.rec);
     } else {
-      const bool ok = jf::fast_doc<false>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out, pow5);
+      const int route = jf::fast_doc<false>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out,
+                                            pow5, sc.rec);
       if (lane == 0) {
-        sc.route[s] = ok ? jf::kRouteFast : jf::kRouteSlow;
-        if (ok) doc_status[s] = 0;
+        sc.route[s] = (uint8_t)route;
+        if (route != jf::kRouteSlow) doc_status[s] = 0;
         else sc.order[atomicAdd(sc.n_slow, 1u)] = (int32_t)s;
       }
     }
@@ -446,8 +460,14 @@ IngestScratch carve(void* scratch, int64_t n_docs) {
   p += 4 * (uint64_t)stride;
   sc.next_fast = (unsigned long long*)p;
   sc.n_slow = (uint32_t*)(sc.next_fast + 2);
+  sc.rec.cursor = sc.next_fast + 3;
   p += 32;
   sc.route = p;
+  p += (uint64_t)stride;  // a multiple of 32
+  sc.rec.doc_rec = (jf::DocRec*)p;
+  p += sizeof(jf::DocRec) * (uint64_t)stride;
+  sc.rec.pool = (unsigned long long*)p;
+  sc.rec.capacity = (unsigned long long)jf::kPoolUnitsPerDoc * (uint64_t)stride;
   return sc;
 }
 
@@ -532,7 +552,7 @@ cudaError_t ingest_read_declined(const void* scratch, int64_t n_docs, unsigned i
 uint64_t ingest_scratch_bytes(int64_t n_docs) {
   const int64_t stride = ((n_docs > 0 ? n_docs : 1) + 31) & ~(int64_t)31;
   return (uint64_t)kPlanes * stride * 4 + ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8 + 64 + 4 * (kOrderBuckets + 2) +
-         4 * (uint64_t)stride + 32 + (uint64_t)stride;
+         4 * (uint64_t)stride + 32 + (uint64_t)stride + (sizeof(jf::DocRec) + 8ull * jf::kPoolUnitsPerDoc) * (uint64_t)stride;
 }
 
 cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint8_t* doc_status, int64_t* totals,

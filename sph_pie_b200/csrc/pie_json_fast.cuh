@@ -35,42 +35,136 @@ namespace jf {
 
 using namespace jw;
 
-constexpr int kFastWarps = 8;
+constexpr int kFastWarps = 7;  // x 4 CTAs per SM: what the shared memory of a warp's lists allows
 constexpr int kFastThreads = kFastWarps * 32;
-constexpr int kFastMaxBytes = 8192;             // alignment skip + document length a warp takes
-constexpr int kFastWords = kFastMaxBytes / 32;  // 32-byte words of text
-constexpr int kFastMaxMembers = 768;
-constexpr int kFastMaxEntries = 128;
-constexpr int kFastMaxNumbers = 192;
-constexpr int kFastMaxEsc = 48;
-constexpr int kInlineCopy = 8;  // longer values are copied by the whole warp
+constexpr int kFastMaxBytes = 16384;   // alignment skip + document length a warp takes (positions are 14 bits)
+constexpr int kFastMaxQuotes = 1536;   // twice the strings: ~0.18 per byte in the provider's documents, so ~8.5 KB of them
+constexpr int kFastMaxMembers = 512;
+constexpr int kFastMaxEntries = 127;
+constexpr int kFastMaxNumbers = 128;
+constexpr int kFastMaxEsc = 32;
+constexpr int kFastMaxArrays = 64;
+constexpr int kInlineCopy = 16;  // longer values are copied by the whole warp
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kAllEntryKeys = 0x1ffffu;  // the 17 keys of an entry
-constexpr uint8_t kRouteSlow = 0, kRouteFast = 1;
+constexpr uint32_t kPosMask = 0x3fffu;
+constexpr uint8_t kRouteSlow = 0, kRouteFast = 1, kRouteRecords = 2;
 
+// Stage 1 leaves two lists, so that stage 2 never searches: the quotes that open or close a string in text order
+// (string i is the pair 2 i, 2 i + 1), and the members by their colons with what stage 2 would otherwise look up.
 struct alignas(16) WarpShared {
-  uint32_t q[kFastWords];   // quotes that open or close a string
-  uint32_t op[kFastWords];  // '{' '[' outside strings
-  uint32_t cl[kFastWords];  // '}' ']' outside strings
-  uint32_t lb[kFastWords];  // '{' outside strings
-  uint32_t bs[kFastWords];  // backslashes that start an escape
-  uint16_t ent[kFastWords];  // '{' before the word
-  uint16_t colon[kFastMaxMembers];
-  uint8_t depth[kFastWords];  // bracket depth before the word
-  uint32_t cnt[kPlanes];      // measure: what the document adds to each plane; fill: the running position in it
-  uint32_t seen[kFastMaxEntries];
-  uint32_t num[kFastMaxNumbers];  // position | entry << 13 | role << 21
-  uint32_t esc_src[kFastMaxEsc];  // position of the first byte | raw length << 16
-  uint32_t esc_dst[kFastMaxEsc];  // where it goes in its heap
-  uint8_t esc_heap[kFastMaxEsc];
-  uint32_t n_num, n_esc, seen_show, pad;
+  uint16_t qpos[kFastMaxQuotes];   // position | (an escape starts between the quote before and this one) << 15
+  uint32_t mem[kFastMaxMembers];   // colon position | index in qpos of the key's closing quote << 14 | (entry + 1, 0 = the show) << 25
+  uint32_t cnt[kPlanes];           // measure: what the document adds to each plane; fill: the running position in it
+  uint32_t seen[kFastMaxEntries + 1];
+  uint32_t num[kFastMaxNumbers];   // position | entry << 14 | role << 21
+  union {
+    struct {                          // pass 2 without records: values with escapes, unescaped at the end of the document
+      uint32_t esc_src[kFastMaxEsc];  // position of the first byte | raw length << 16
+      uint32_t esc_dst[kFastMaxEsc];  // where it goes in its heap
+      uint8_t esc_heap[kFastMaxEsc];
+    };
+    uint32_t arr[kFastMaxArrays][3];  // pass 1 with records: the crew / actions arrays, their elements' records come last
+  };
+  uint32_t n_num, n_esc, seen_show, n_arr, n_items, pad[3];
 };
 
-// what every warp of a CTA reads per value: the table's pointers, once in shared memory (indexing the kernel
-// parameter with a lane-dependent heap would serialise on the constant cache)
+// ---- records ------------------------------------------------------------------------------------------------------
+// What pass 1 knows of a document when it is through with it is everything pass 2 needs, so it writes it down: one
+// 8-byte record per member, then one per number and one per element of crew / actions, in a pool inside the scratch
+// area (kPoolUnitsPerDoc 8-byte units per document on average; a document that finds the pool full is parsed again by
+// pass 2 as before).  Pass 2 of such a document is a scatter: no index, no keys, no grammar.
+//   member  lo = first byte | raw length << 14 | has escapes << 28        hi = heap | entry << 5 | offset in the document's
+//           part of the heap << 12 | kind << 29
+//   number  lo = role | entry << 3, hi = 0; then the binary64
+//   element lo as a member's; hi = heap | offset << 5 | index in the document's part of the list << 19
+enum RecKind : uint32_t { kRecNone = 0, kRecText, kRecArray, kRecNullDelay, kRecNanTs, kRecTimeKind, kRecTimeString };
+constexpr int kPoolUnitsPerDoc = 288;
+struct DocRec {
+  unsigned long long members_at, extra_at;  // units into the pool
+  uint32_t members, numbers, items, pad;
+};
+struct RecCtx {
+  unsigned long long* pool;    // nullptr: no records
+  unsigned long long* cursor;  // units handed out
+  unsigned long long capacity;
+  DocRec* doc_rec;
+};
+
+// keys by a perfect hash of (first 8 bytes, length): one probe, one compare, no chain of 17 compares that parts the lanes
+struct KeySlot {
+  uint64_t k0, k1;
+  int32_t len, id;
+};
+constexpr uint32_t kShowKeyMul = 0x2265b1f5u, kEntryKeyMul = 0xab99254bu;
+__host__ __device__ constexpr uint32_t key_slot(uint64_t k0, uint32_t len, uint32_t mul) {
+  return ((((uint32_t)k0 ^ (uint32_t)(k0 >> 32)) + len) * mul) >> 27;
+}
+struct KeyTables {
+  KeySlot show[32], entry[32];
+};
+template <int L>
+__host__ __device__ constexpr void key_put(KeySlot (&t)[32], uint32_t mul, const char (&lit)[L], int id, bool* clash) {
+  const uint64_t k0 = key_word(lit, 0), k1 = key_word(lit, 8);
+  KeySlot& sl = t[key_slot(k0, L - 1, mul)];
+  if (sl.len != 0) *clash = true;
+  sl.k0 = k0;
+  sl.k1 = k1;
+  sl.len = L - 1;
+  sl.id = id;
+}
+__host__ __device__ constexpr KeyTables make_key_tables(bool* clash) {
+  KeyTables t{};
+  for (int i = 0; i < 32; ++i) {
+    t.show[i] = KeySlot{0, 0, 0, -1};
+    t.entry[i] = KeySlot{0, 0, 0, -1};
+  }
+  // the ids are those of match_show_key / match_entry_key (pie_json_walk.cuh)
+  key_put(t.show, kShowKeyMul, "id", 0, clash);
+  key_put(t.show, kShowKeyMul, "date", 1, clash);
+  key_put(t.show, kShowKeyMul, "time", 2, clash);
+  key_put(t.show, kShowKeyMul, "label", 3, clash);
+  key_put(t.show, kShowKeyMul, "leadPilot", 4, clash);
+  key_put(t.show, kShowKeyMul, "monkeyLead", 5, clash);
+  key_put(t.show, kShowKeyMul, "notes", 6, clash);
+  key_put(t.show, kShowKeyMul, "crew", kSkCrew, clash);
+  key_put(t.show, kShowKeyMul, "createdAt", kSkCreatedAt, clash);
+  key_put(t.show, kShowKeyMul, "archivedAt", kSkArchivedAt, clash);
+  key_put(t.show, kShowKeyMul, "entries", kSkEntries, clash);
+  key_put(t.show, kShowKeyMul, "updatedAt", kSkUpdatedAt, clash);
+  key_put(t.show, kShowKeyMul, "deletedAt", kSkDeletedAt, clash);
+  key_put(t.entry, kEntryKeyMul, "id", 0, clash);
+  key_put(t.entry, kEntryKeyMul, "unitId", 1, clash);
+  key_put(t.entry, kEntryKeyMul, "planned", 2, clash);
+  key_put(t.entry, kEntryKeyMul, "launched", 3, clash);
+  key_put(t.entry, kEntryKeyMul, "status", 4, clash);
+  key_put(t.entry, kEntryKeyMul, "primaryIssue", 5, clash);
+  key_put(t.entry, kEntryKeyMul, "subIssue", 6, clash);
+  key_put(t.entry, kEntryKeyMul, "otherDetail", 7, clash);
+  key_put(t.entry, kEntryKeyMul, "severity", 8, clash);
+  key_put(t.entry, kEntryKeyMul, "rootCause", 9, clash);
+  key_put(t.entry, kEntryKeyMul, "operator", 10, clash);
+  key_put(t.entry, kEntryKeyMul, "batteryId", 11, clash);
+  key_put(t.entry, kEntryKeyMul, "commandRx", 12, clash);
+  key_put(t.entry, kEntryKeyMul, "notes", 13, clash);
+  key_put(t.entry, kEntryKeyMul, "actions", kEkActions, clash);
+  key_put(t.entry, kEntryKeyMul, "delaySec", kEkDelaySec, clash);
+  key_put(t.entry, kEntryKeyMul, "ts", kEkTs, clash);
+  return t;
+}
+constexpr bool key_tables_clash() {
+  bool clash = false;
+  make_key_tables(&clash);
+  return clash;
+}
+static_assert(!key_tables_clash(), "the key hashes must be perfect");
+
+// what every warp of a CTA reads per value: the table's pointers and the key tables, once in shared memory (indexing
+// the kernel parameter / constant memory with a lane-dependent index would serialise on the constant cache)
 struct TablePointers {
   uint8_t* data[kHeaps];
   int32_t* off[kHeaps];
+  KeyTables keys;
 };
 
 struct Doc {
@@ -78,44 +172,6 @@ struct Doc {
   int skip, span;     // the document is ab[skip .. span)
   int nwords;
 };
-
-// ---- searches in the masks ----------------------------------------------------------------------------------------
-__device__ __forceinline__ int next_bit(const uint32_t* m, int p, int nwords) {  // first set bit behind position p
-  int w = p >> 5;
-  uint32_t x = m[w] & (0xfffffffeu << (p & 31));
-  while (!x) {
-    if (++w >= nwords) return -1;
-    x = m[w];
-  }
-  return w * 32 + __ffs(x) - 1;
-}
-__device__ __forceinline__ int prev_bit(const uint32_t* m, int p) {  // last set bit before position p
-  int w = p >> 5;
-  uint32_t x = m[w] & ((1u << (p & 31)) - 1u);
-  while (!x) {
-    if (--w < 0) return -1;
-    x = m[w];
-  }
-  return w * 32 + 31 - __clz(x);
-}
-__device__ __forceinline__ bool any_bit_between(const uint32_t* m, int a, int b) {  // any set bit in (a, b), a < b
-  const int wa = a >> 5, wb = b >> 5;
-  const uint32_t above = 0xfffffffeu << (a & 31), below = (1u << (b & 31)) - 1u;
-  if (wa == wb) return (m[wa] & above & below) != 0;
-  if (m[wa] & above) return true;
-  for (int w = wa + 1; w < wb; ++w)
-    if (m[w]) return true;
-  return (m[wb] & below) != 0;
-}
-__device__ __forceinline__ int depth_at(const WarpShared& ws, int p) {
-  const int w = p >> 5;
-  const uint32_t below = (1u << (p & 31)) - 1u;
-  return (int)ws.depth[w] + __popc(ws.op[w] & below) - __popc(ws.cl[w] & below);
-}
-__device__ __forceinline__ int entry_at(const WarpShared& ws, int p) {  // inside an entry: which one
-  const int w = p >> 5;
-  return (int)ws.ent[w] + __popc(ws.lb[w] & ((1u << (p & 31)) - 1u)) - 2;  // the show's brace and the entry's own
-}
 
 // the first 16 bytes of a key as the walk collects them (len <= 16)
 __device__ __forceinline__ void load_key(const uint8_t* p, int len, const uint8_t* limit, uint64_t* k0, uint64_t* k1) {
@@ -139,34 +195,63 @@ __device__ __forceinline__ void load_key(const uint8_t* p, int len, const uint8_
   *k0 = a0;
   *k1 = a1;
 }
+__device__ __forceinline__ int match_key(const KeySlot (&t)[32], uint32_t mul, int len, uint64_t k0, uint64_t k1) {
+  const KeySlot& sl = t[key_slot(k0, (uint32_t)len, mul)];
+  return (sl.len == len && sl.k0 == k0 && sl.k1 == k1) ? sl.id : -1;
+}
+
+// the 8 bytes at p (any alignment) from the aligned words that hold them; `limit`: the aligned end of the document's
+// last 32-byte word (bytes behind it read as zero)
+__device__ __forceinline__ uint64_t load8(const uint8_t* p, const uint8_t* limit) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const unsigned long long* w = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+  const int sh = (int)(a & 7) * 8;
+  const uint64_t w0 = __ldg(w);
+  if (!sh) return w0;
+  const uint64_t w1 = reinterpret_cast<const uint8_t*>(w + 1) < limit ? __ldg(w + 1) : 0ull;
+  return (w0 >> sh) | (w1 << (64 - sh));
+}
+// n (<= 8) bytes of x to dst
+__device__ __forceinline__ void store_upto8(uint8_t* dst, uint64_t x, int n) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < n) dst[k] = (uint8_t)(x >> (8 * k));
+}
+// len plain bytes from src to dst, 8 at a time
+__device__ __forceinline__ void copy_plain(const uint8_t* src, int len, uint8_t* dst, const uint8_t* limit) {
+  for (int i = 0; i < len; i += 8) store_upto8(dst + i, load8(src + i, limit), len - i);
+}
 
 // ---- escapes ------------------------------------------------------------------------------------------------------
-// what the escapes of the string (v, cq) save: raw bytes minus unescaped bytes; *bad when an escape is not one of
-// ECMA-404's, or names a surrogate (the walk decides those)
-__device__ __forceinline__ int escape_savings(const WarpShared& ws, const uint8_t* ab, int v, int cq, bool* bad) {
-  int saved = 0;
-  int p = v;
-  for (;;) {
-    const int w0 = p >> 5;
-    uint32_t x = ws.bs[w0] & (0xfffffffeu << (p & 31));
-    int w = w0;
-    while (!x && (w + 1) * 32 <= cq) x = ws.bs[++w];
-    if (!x) break;
-    p = w * 32 + __ffs(x) - 1;
-    if (p >= cq) break;
-    const uint8_t e = ab[p + 1];
+// what the escapes of the raw string ab[src .. src + raw) save: raw bytes minus unescaped bytes; *bad when an escape
+// is not one of ECMA-404's, or names a surrogate (the walk decides those).  Only called for strings stage 1 flagged.
+// Backslashes are found 8 bytes at a time.
+__device__ __forceinline__ int escape_savings(const uint8_t* ab, int src, int raw, const uint8_t* limit, bool* bad) {
+  int saved = 0, i = 0;
+  while (i < raw) {
+    {
+      const uint64_t x = load8(ab + src + i, limit) ^ 0x5c5c5c5c5c5c5c5cull;
+      const uint64_t hit = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;  // exact up to the first hit
+      const int j = hit ? (__ffsll((long long)hit) - 1) >> 3 : 8;
+      if (i + j >= raw) break;
+      i += j;
+      if (j == 8) continue;
+    }
+    const uint8_t e = i + 1 < raw ? ab[src + i + 1] : 0;
     if (e == 'u') {
-      if (p + 5 >= cq) { *bad = true; break; }
+      if (i + 5 >= raw) { *bad = true; break; }
       uint32_t cp = 0;
       for (int k = 2; k < 6; ++k) {
-        const int h = hex_value(ab[p + k]);
+        const int h = hex_value(ab[src + i + k]);
         if (h < 0) *bad = true;
         cp = cp * 16 + (uint32_t)(h & 15);
       }
       if (cp >= 0xD800 && cp <= 0xDFFF) *bad = true;
       saved += 6 - (cp < 0x80 ? 1 : cp < 0x800 ? 2 : 3);
+      i += 6;
     } else if (e == '"' || e == '\\' || e == '/' || e == 'b' || e == 'f' || e == 'n' || e == 'r' || e == 't') {
       saved += 1;
+      i += 2;
     } else {
       *bad = true;
       break;
@@ -175,17 +260,21 @@ __device__ __forceinline__ int escape_savings(const WarpShared& ws, const uint8_
   }
   return saved;
 }
-// the unescaped bytes of ab[src .. src + raw) to dst (escapes already validated); returns how many
-__device__ __forceinline__ int unescape_copy(const uint8_t* ab, int src, int raw, uint8_t* dst) {
+// the unescaped bytes of ab[src .. src + raw) to dst (escapes already validated); returns how many.  Plain runs go 8
+// bytes at a time.
+__device__ __forceinline__ int unescape_copy(const uint8_t* ab, int src, int raw, uint8_t* dst, const uint8_t* limit) {
   int i = 0, o = 0;
   while (i < raw) {
-    const uint8_t c = ab[src + i];
-    if (c != '\\') {
-      dst[o++] = c;
-      ++i;
-      continue;
-    }
-    const uint8_t e = ab[src + i + 1];
+    const uint64_t w = load8(ab + src + i, limit);
+    const uint64_t x = w ^ 0x5c5c5c5c5c5c5c5cull;
+    const uint64_t hit = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;
+    int run = hit ? (__ffsll((long long)hit) - 1) >> 3 : 8;
+    if (run > raw - i) run = raw - i;
+    store_upto8(dst + o, w, run);
+    o += run;
+    i += run;
+    if (run == 8 || i >= raw) continue;
+    const uint8_t e = ab[src + i + 1];  // the byte at i is a backslash
     if (e == 'u') {
       uint32_t cp = 0;
       for (int k = 2; k < 6; ++k) cp = cp * 16 + (uint32_t)(hex_value(ab[src + i + k]) & 15);
@@ -209,12 +298,13 @@ __device__ __forceinline__ int unescape_copy(const uint8_t* ab, int src, int raw
   return o;
 }
 
-// well-formed UTF-8 (Unicode table 3-7) in ab[a .. b): sequences that start here are followed to their end; bytes owed
-// to a sequence that starts before a belong to the lane that owns its lead
-__device__ __noinline__ bool utf8_ok(const uint8_t* ab, int a, int b, int skip, int span) {
-  int owed = 0;
-  for (int k = 1; k <= 3 && a - k >= skip; ++k) {
-    const uint8_t c = ab[a - k];
+// Well-formed UTF-8 (Unicode table 3-7) among the bytes >= 0x80 of a lane's word (`hib`: their positions, pos0: the
+// word's first position): sequences that start here are followed to their end (into the next word if need be);
+// continuation bytes owed to a sequence that starts in an earlier word belong to the lane that owns its lead.
+__device__ __noinline__ bool utf8_ok(const uint8_t* ab, uint32_t hib, int pos0, int skip, int span) {
+  int owed = 0;  // continuation bytes at the start of the word that a lead before it answers for
+  for (int k = 1; k <= 3 && pos0 - k >= skip; ++k) {
+    const uint8_t c = ab[pos0 - k];
     if ((c & 0xC0) == 0x80) continue;
     if (c >= 0xC2) {
       const int need = c >= 0xF0 ? 3 : c >= 0xE0 ? 2 : 1;
@@ -223,10 +313,13 @@ __device__ __noinline__ bool utf8_ok(const uint8_t* ab, int a, int b, int skip, 
     }
     break;
   }
-  int p = a + owed;
-  while (p < b) {
+  int done = owed;  // bytes of the word below this index are settled
+  while (hib) {
+    const int bit = __ffs(hib) - 1;
+    hib &= hib - 1;
+    if (bit < done) continue;
+    const int p = pos0 + bit;
     const uint8_t c = ab[p];
-    if (c < 0x80) { ++p; continue; }
     if (c < 0xC2 || c > 0xF4) return false;  // a continuation byte nobody owns, an overlong lead, beyond U+10FFFF
     int need = 1, lo = 0x80, hi = 0xBF;
     if (c >= 0xF0) { need = 3; if (c == 0xF0) lo = 0x90; if (c == 0xF4) hi = 0x8F; }
@@ -238,7 +331,7 @@ __device__ __noinline__ bool utf8_ok(const uint8_t* ab, int a, int b, int skip, 
       lo = 0x80;
       hi = 0xBF;
     }
-    p += need + 1;
+    done = bit + need + 1;
   }
   return true;
 }
@@ -262,18 +355,17 @@ __device__ __forceinline__ uint32_t find_escaped(uint32_t b, uint32_t cin, uint3
 }
 
 struct IndexTotals {
-  int members, entries, strings;
+  int members, entries, quotes;
 };
 
-// Builds the masks of the document in ws; false = declined.  kCheck (the measuring pass): every rule that makes
+// Builds the two lists of the document in ws; false = declined.  kCheck (the measuring pass): every rule that makes
 // "accepted" mean "a document of the shape in the header" that does not need a key or a value.
 template <bool kCheck>
 __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, IndexTotals* tot) {
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
-  uint32_t c_esc = 0, c_instr = 0, c_tops = 0;
-  int c_depth = 0, c_lb = 0, c_co = 0;
-  uint32_t oq_count = 0;
+  uint32_t c_esc = 0, c_instr = 0, c_tops = 0, c_bsq = 0;
+  int c_depth = 0, c_lb = 0, c_co = 0, c_q = 0;
   bool bad = false;
   const int nblk = (dc.nwords + 31) >> 5;
   for (int blk = 0; blk < nblk; ++blk) {
@@ -289,7 +381,7 @@ __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, Index
 #pragma unroll
       for (int k = 0; k < 8; ++k) L[k] = 0;
     }
-    uint32_t q = 0, bsl = 0, op = 0, cl = 0, lb = 0, rb = 0, co = 0, cm = 0, ctl = 0, hib = 0;
+    uint32_t q = 0, bsl = 0, op = 0, cl = 0, brm = 0, co = 0, cm = 0, hib = 0, ctl_any = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       // word w of the transposed copy holds the bytes at positions w, 8 + w, 16 + w, 24 + w of the lane's 32: a flag
@@ -299,20 +391,16 @@ __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, Index
       const uint32_t x = __byte_perm(__byte_perm(L[h], L[2 + h], sel), __byte_perm(L[4 + h], L[6 + h], sel), 0x5410);
       const uint32_t hi = x & 0x80808080u, y = x & 0x7f7f7f7fu;
       const uint32_t z = (y | 0x20202020u) ^ 0x7b7b7b7bu;  // 0 for [ {, 6 for ] }
-      const uint32_t fop = ~((z + 0x7f7f7f7fu) | hi) & 0x80808080u;
-      const uint32_t fcl = ~(((z ^ 0x06060606u) + 0x7f7f7f7fu) | hi) & 0x80808080u;
-      const uint32_t brace = y << 2;  // bit 5 tells { } from [ ]
       q |= eq_flags(y, hi, 0x22222222u) >> (7 - w);
       bsl |= eq_flags(y, hi, 0x5c5c5c5cu) >> (7 - w);
-      op |= fop >> (7 - w);
-      cl |= fcl >> (7 - w);
-      lb |= (fop & brace) >> (7 - w);
+      op |= (~((z + 0x7f7f7f7fu) | hi) & 0x80808080u) >> (7 - w);
+      cl |= (~(((z ^ 0x06060606u) + 0x7f7f7f7fu) | hi) & 0x80808080u) >> (7 - w);
+      brm |= ((y << 2) & 0x80808080u) >> (7 - w);  // bit 5 tells { } from [ ]
       co |= eq_flags(y, hi, 0x3a3a3a3au) >> (7 - w);
       if (kCheck) {
-        rb |= (fcl & brace) >> (7 - w);
         cm |= eq_flags(y, hi, 0x2c2c2c2cu) >> (7 - w);
-        ctl |= (~((y + 0x60606060u) | hi) & 0x80808080u) >> (7 - w);
         hib |= hi >> (7 - w);
+        ctl_any |= ~((y + 0x60606060u) | hi);  // bit 7: a byte below 0x20
       }
     }
     // bytes of the word that are the document's
@@ -323,7 +411,7 @@ __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, Index
       if (he > 32) he = 32;
       if (lo < 32 && he > lo) vm = (he >= 32 ? kFull : ((1u << he) - 1u)) & ~((1u << lo) - 1u);
     }
-    q &= vm; bsl &= vm; op &= vm; cl &= vm; lb &= vm; co &= vm;
+    q &= vm; bsl &= vm; op &= vm; cl &= vm; co &= vm;
     // escaped characters: the carry runs from lane to lane; a lane's carry out depends on its carry in only when all
     // its 32 bytes are backslashes, so this settles in two or three turns
     uint32_t esc = 0;
@@ -348,40 +436,68 @@ __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, Index
     if ((__popc(pm & lt) & 1) ^ c_instr) is = ~is;
     c_instr ^= __popc(pm) & 1u;
     is &= vm;
-    op &= ~is; cl &= ~is; lb &= ~is; co &= ~is;
-    const uint32_t oq = qr & is;
-    oq_count += __popc(oq);
-    // depth, entries and colons before the word
+    op &= ~is; cl &= ~is; co &= ~is;
+    const uint32_t lb = op & brm;
+    // depth, entries, colons and quotes before the word
     uint32_t sa = (uint32_t)__popc(op) | ((uint32_t)__popc(cl) << 16);
     uint32_t sb = (uint32_t)__popc(lb) | ((uint32_t)__popc(co) << 16);
-    const uint32_t own_a = sa, own_b = sb;
+    uint32_t sq = (uint32_t)__popc(qr);
+    const uint32_t own_a = sa, own_b = sb, own_q = sq;
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const uint32_t ta = __shfl_up_sync(kFull, sa, dlt), tb = __shfl_up_sync(kFull, sb, dlt);
-      if (lane >= dlt) { sa += ta; sb += tb; }
+      const uint32_t ta = __shfl_up_sync(kFull, sa, dlt), tb = __shfl_up_sync(kFull, sb, dlt), tq = __shfl_up_sync(kFull, sq, dlt);
+      if (lane >= dlt) { sa += ta; sb += tb; sq += tq; }
     }
     const uint32_t ex_a = sa - own_a, ex_b = sb - own_b;
     const int d0 = c_depth + (int)(ex_a & 0xffff) - (int)(ex_a >> 16);
     const int lb0 = c_lb + (int)(ex_b & 0xffff);
     const int co0 = c_co + (int)(ex_b >> 16);
+    const int q0 = c_q + (int)(sq - own_q);
     const uint32_t tot_a = __shfl_sync(kFull, sa, 31), tot_b = __shfl_sync(kFull, sb, 31);
     c_depth += (int)(tot_a & 0xffff) - (int)(tot_a >> 16);
     c_lb += (int)(tot_b & 0xffff);
     c_co += (int)(tot_b >> 16);
-    if (wi < dc.nwords) {
-      ws.q[wi] = qr;
-      ws.op[wi] = op;
-      ws.cl[wi] = cl;
-      ws.lb[wi] = lb;
-      ws.bs[wi] = bstart;
-      ws.ent[wi] = (uint16_t)lb0;
-      ws.depth[wi] = (uint8_t)(d0 < 0 ? 255 : d0 > 255 ? 255 : d0);
+    c_q += (int)__shfl_sync(kFull, sq, 31);
+    // the quotes, each with "an escape starts between the quote before and this one" (asked of closing quotes: the
+    // string has escapes).  What lies before a lane's first quote comes from the lanes below, back to the last quote.
+    {
+      const uint32_t G = __ballot_sync(kFull, qr != 0);
+      const uint32_t after_last = qr ? (bstart >> (31 - __clz(qr))) >> 1 : bstart;  // escape starts behind the lane's last quote
+      const uint32_t F = __ballot_sync(kFull, after_last != 0);
+      uint32_t before;  // an escape start between the last quote of the lanes below and this lane
+      if (G & lt) before = ((F & lt) >> (31 - __clz(G & lt))) != 0;
+      else before = ((F & lt) != 0) | c_bsq;
+      c_bsq = G ? ((F >> (31 - __clz(G))) != 0) : (c_bsq | (F != 0));
+      // the flagged quotes of the lane: the first quote behind each escape start, and the lane's first quote when an
+      // escape start waits below
+      uint32_t flagged = before ? (qr & (0u - qr)) : 0u;
+      for (uint32_t m = bstart; m; m &= m - 1) {
+        const uint32_t above = qr & ~((2u << (__ffs(m) - 1)) - 1u);
+        flagged |= above & (0u - above);
+      }
+      int idx = q0;
+      for (uint32_t m = qr; m; m &= m - 1, ++idx) {
+        const int bit = __ffs(m) - 1;
+        if (idx < kFastMaxQuotes) ws.qpos[idx] = (uint16_t)((uint32_t)(pos0 + bit) | (((flagged >> bit) & 1u) << 15));
+      }
+    }
+    // the members: a colon, the index of the quote before it (the key's closing quote), the entry it is in
+    {
       int idx = co0;
-      for (uint32_t m = co; m; m &= m - 1, ++idx)
-        if (idx < kFastMaxMembers) ws.colon[idx] = (uint16_t)(pos0 + __ffs(m) - 1);
+      for (uint32_t m = co; m; m &= m - 1, ++idx) {
+        const int bit = __ffs(m) - 1;
+        const uint32_t below = (1u << bit) - 1u;
+        const int d = d0 + __popc(op & below) - __popc(cl & below);
+        const int e1 = d == 3 ? lb0 + __popc(lb & below) - 1 : 0;  // entry + 1 (the show's own brace is the first)
+        const int kq = q0 + __popc(qr & below) - 1;
+        if (!(d == 1 || d == 3) || kq < 1 || e1 > kFastMaxEntries) bad = true;  // a colon in an array, or no key before it
+        if (idx < kFastMaxMembers)
+          ws.mem[idx] = (uint32_t)(pos0 + bit) | ((uint32_t)(kq & 0x7ff) << 14) | ((uint32_t)(e1 & 0x7f) << 25);
+      }
     }
     if (kCheck) {
-      rb &= vm & ~is; cm &= vm & ~is; ctl &= vm; hib &= vm;
+      cm &= vm & ~is; hib &= vm;
+      const uint32_t rb = cl & brm;
       const uint32_t lk = op & ~lb, rk = cl & ~rb;
       const uint32_t cq = qr & ~is;
       const uint32_t sc = vm & ~is & ~qr & ~(op | cl | co | cm);  // bytes of scalars
@@ -396,22 +512,28 @@ __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, Index
                      p_cm = (cm << 1) | ((pt >> 6) & 1), p_sc = (sc << 1) | ((pt >> 7) & 1);
       const uint32_t first = wi == 0 ? (1u << dc.skip) : 0u;
       uint32_t wrong = co & ~p_cq;                       // a colon follows a string
-      wrong |= oq & ~(p_lb | p_cm | p_co | p_lk);        // a string follows { , : [
+      wrong |= (qr & is) & ~(p_lb | p_cm | p_co | p_lk); // a string follows { , : [
       wrong |= lb & ~(p_lk | p_cm | first);              // { opens the document or an element
       wrong |= lk & ~p_co;                               // [ is a member's value
       wrong |= rb & ~(p_lb | p_cq | p_sc | p_rk);        // } follows { or a value
       wrong |= rk & ~(p_lk | p_cq | p_rb);               // ] follows [ or an element
       wrong |= cm & ~(p_cq | p_sc | p_rk | p_rb);        // , follows a value
       wrong |= (sc & ~p_sc) & ~p_co;                     // a scalar is a member's value
-      wrong |= ctl;                                      // control characters are nowhere
-      wrong |= hib & ~is;                                // bytes >= 0x80 only inside strings
       if (wrong) bad = true;
+      // control characters are nowhere in such a document.  The flags of the word's 32 bytes include its neighbours'
+      // bytes at the document's ends: look byte by byte there (a lane or two per document)
+      if (ctl_any & 0x80808080u) {
+        if (vm == kFull) bad = true;
+        else
+          for (uint32_t m = vm; m; m &= m - 1)
+            if (dc.ab[pos0 + __ffs(m) - 1] < 0x20) bad = true;
+      }
       // brackets: the kind follows from the depth ({ at 0 and 2, [ at 1 and 3), so matching pairs need no stack
       if (op | cl) {
         int d = d0;
         for (uint32_t m = op | cl; m; m &= m - 1) {
           const int bit = __ffs(m) - 1, pos = pos0 + bit;
-          const bool open = (op >> bit) & 1u, brc = ((lb | rb) >> bit) & 1u;
+          const bool open = (op >> bit) & 1u, brc = (brm >> bit) & 1u;
           bool ok;
           if (open) ok = brc ? ((d == 0 && pos == dc.skip) || d == 2) : (d == 1 || d == 3);
           else ok = brc ? (d == 3 || (d == 1 && pos == dc.span - 1)) : (d == 2 || d == 4);
@@ -419,16 +541,14 @@ __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, Index
           d += open ? 1 : -1;
         }
       }
-      if (hib && !utf8_ok(dc.ab, pos0 > dc.skip ? pos0 : dc.skip, pos0 + 32 < dc.span ? pos0 + 32 : dc.span, dc.skip, dc.span))
-        bad = true;
+      // bytes >= 0x80 outside strings are bytes of scalars, which stage 2 reads one by one; inside strings: UTF-8
+      if (hib && !utf8_ok(dc.ab, hib, pos0, dc.skip, dc.span)) bad = true;
     }
   }
-#pragma unroll
-  for (int dlt = 16; dlt > 0; dlt >>= 1) oq_count += __shfl_xor_sync(kFull, oq_count, dlt);
   tot->members = c_co;
   tot->entries = c_lb - 1;
-  tot->strings = (int)oq_count;
-  if (c_co > kFastMaxMembers || c_lb - 1 > kFastMaxEntries) bad = true;
+  tot->quotes = c_q;
+  if (c_co > kFastMaxMembers || c_lb - 1 > kFastMaxEntries || c_q > kFastMaxQuotes) bad = true;
   if (kCheck && (c_depth != 0 || c_instr != 0 || c_lb < 1)) bad = true;
   return !__any_sync(kFull, bad);
 }
@@ -449,30 +569,39 @@ __device__ __forceinline__ uint32_t group_prefix(int key, uint32_t val, uint32_t
   return sum;
 }
 
-// The elements of a crew / actions array that opens at `at` ('['): strings only.  kCopy = false: counts them and their
-// unescaped bytes; kCopy = true: writes offsets and bytes from (item0, dst0) on.  false = not the shape.
-template <bool kCopy>
-__device__ __forceinline__ bool walk_items(const WarpShared& ws, const Doc& dc, int at, uint32_t* n_items, uint32_t* n_bytes,
-                                           int32_t* off, uint8_t* data, uint32_t item0, uint32_t dst0) {
+// The elements of a crew / actions array that opens at `at` ('['): strings only; qi = the index in qpos of the first
+// quote behind the bracket.  kMode 0: counts them and their unescaped bytes; 1: writes offsets and bytes from
+// (item0, dst0) on; 2: writes their records (heap; item0 / dst0 relative to the document).  false = not the shape.
+template <int kMode>
+__device__ __forceinline__ bool walk_items(const WarpShared& ws, const Doc& dc, int at, int qi, int n_quotes, uint32_t* n_items,
+                                           uint32_t* n_bytes, int32_t* off, uint8_t* data, uint32_t item0, uint32_t dst0,
+                                           unsigned long long* recs = nullptr, uint32_t heap = 0) {
   uint32_t N = 0, B = 0;
   int pos = at + 1;
+  const uint8_t* limit = dc.ab + dc.nwords * 32;
   if (pos < dc.span && dc.ab[pos] != ']') {
     for (;;) {
-      if (pos >= dc.span || dc.ab[pos] != '"') return false;
-      const int cq = next_bit(ws.q, pos, dc.nwords);
-      if (cq < 0 || cq + 1 >= dc.span) return false;
+      if (qi + 1 >= n_quotes) return false;
+      const uint32_t qo = ws.qpos[qi], qc = ws.qpos[qi + 1];
+      if ((int)(qo & kPosMask) != pos) return false;  // the element is not a string
+      const int cq = (int)(qc & kPosMask);
+      if (cq + 1 >= dc.span) return false;
       const int raw = cq - pos - 1;
       int len = raw;
-      const bool esc = raw > 0 && any_bit_between(ws.bs, pos, cq);
-      if (kCopy) {
+      const bool esc = (qc >> 15) != 0;
+      if (kMode == 1) {
         off[item0 + N] = (int32_t)(dst0 + B);
-        if (esc) len = unescape_copy(dc.ab, pos + 1, raw, data + dst0 + B);
-        else
-          for (int i = 0; i < raw; ++i) data[dst0 + B + i] = dc.ab[pos + 1 + i];
+        if (esc) len = unescape_copy(dc.ab, pos + 1, raw, data + dst0 + B, limit);
+        else copy_plain(dc.ab + pos + 1, raw, data + dst0 + B, limit);
       } else if (esc) {
         bool bad = false;
-        len = raw - escape_savings(ws, dc.ab, pos, cq, &bad);
+        len = raw - escape_savings(dc.ab, pos + 1, raw, limit, &bad);
         if (bad) return false;
+      }
+      if (kMode == 2) {
+        const uint32_t lo = (uint32_t)(pos + 1) | ((uint32_t)raw << 14) | ((uint32_t)esc << 28);
+        const uint32_t hi = heap | ((dst0 + B) << 5) | ((item0 + N) << 19);
+        recs[N] = (unsigned long long)lo | ((unsigned long long)hi << 32);
       }
       B += (uint32_t)len;
       ++N;
@@ -480,6 +609,7 @@ __device__ __forceinline__ bool walk_items(const WarpShared& ws, const Doc& dc, 
       if (nc == ']') break;
       if (nc != ',') return false;
       pos = cq + 2;
+      qi += 2;
     }
   }
   *n_items = N;
@@ -488,34 +618,45 @@ __device__ __forceinline__ bool walk_items(const WarpShared& ws, const Doc& dc, 
 }
 
 // ---- one document -------------------------------------------------------------------------------------------------
-// kFill = false: validates, counts (planes_row receives the document's 26 counts); true = accepted.
+// kFill = false: validates, counts (planes_row receives the document's 26 counts) and, when the pool has room, writes
+// the document's records; returns kRouteSlow (declined), kRouteFast (accepted; pass 2 parses it again) or kRouteRecords.
 // kFill = true: planes_row holds where the document's part of every plane starts; writes its part of the table.
 template <bool kFill>
-__device__ __forceinline__ bool fast_doc(WarpShared& ws, const TablePointers& tp, const uint8_t* __restrict__ text, int64_t from,
-                                         int64_t to, int64_t s, int64_t n_docs, uint32_t* __restrict__ planes_row,
-                                         const IngestOut& out, const Pow5Table& pow5) {
+__device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp, const uint8_t* __restrict__ text, int64_t from,
+                                        int64_t to, int64_t s, int64_t n_docs, uint32_t* __restrict__ planes_row,
+                                        const IngestOut& out, const Pow5Table& pow5, const RecCtx& rc) {
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
   const int64_t n = to - from;
-  if (n < 2) return false;
+  if (n < 2) return kRouteSlow;
   Doc dc;
   {
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(text + from);
     dc.skip = (int)(a0 & 31);
     dc.ab = reinterpret_cast<const uint8_t*>(a0 - dc.skip);
   }
-  if (dc.skip + n > kFastMaxBytes) return false;
+  if (dc.skip + n > kFastMaxBytes) return kRouteSlow;
   dc.span = dc.skip + (int)n;
   dc.nwords = (dc.span + 31) >> 5;
   const uint8_t* ab = dc.ab;
 
   __syncwarp();
-  if (lane == 0) { ws.n_num = 0; ws.n_esc = 0; ws.seen_show = 0; }
+  if (lane == 0) { ws.n_num = 0; ws.n_esc = 0; ws.seen_show = 0; ws.n_arr = 0; ws.n_items = 0; }
   if (lane < kPlanes) ws.cnt[lane] = kFill ? planes_row[lane] : 0u;
   IndexTotals tot;
-  if (!build_index<!kFill>(ws, dc, &tot)) return false;
+  if (!build_index<!kFill>(ws, dc, &tot)) return kRouteSlow;
   if (!kFill)
     for (int e = lane; e < tot.entries; e += 32) ws.seen[e] = 0;
+  // records: room for a record per member now, for the numbers and the elements when they are counted.  (The last
+  // document is parsed again by pass 2: it writes the terminal offsets from the counters it ends on.)
+  bool rec_on = false;
+  unsigned long long members_at = 0;
+  if (!kFill && rc.pool && s != n_docs - 1) {
+    if (lane == 0) members_at = atomicAdd(rc.cursor, (unsigned long long)tot.members);
+    members_at = __shfl_sync(kFull, members_at, 0);
+    rec_on = members_at + (unsigned long long)tot.members <= rc.capacity;
+  }
+  unsigned long long* const slots = rc.pool + members_at;
   __syncwarp();
   const uint32_t row0 = kFill ? ws.cnt[kPlaneEntries] : 0u;
   if (kFill) {
@@ -533,157 +674,158 @@ __device__ __forceinline__ bool fast_doc(WarpShared& ws, const TablePointers& tp
   const int steps = (tot.members + 31) >> 5;
   for (int t = 0; t < steps; ++t) {
     const int k = t * 32 + lane;
-    int heap = -1;       // the heap that receives bytes from this member
+    const bool act = k < tot.members;
+    // ---- the member: every lane runs the same straight code; a lane without a member runs it on the last member and
+    // leaves no trace
+    const uint32_t rec = ws.mem[act ? k : tot.members - 1];
+    const int c = (int)(rec & kPosMask), kq = (int)((rec >> 14) & 0x7ff), e1 = (int)(rec >> 25);
+    const bool in_entry = e1 != 0;
+    const int e = in_entry ? e1 - 1 : 0;
+    const uint32_t row = row0 + (uint32_t)e;
+    const uint32_t qk = ws.qpos[kq];
+    const int ko = (int)(ws.qpos[kq - 1] & kPosMask), kc = (int)(qk & kPosMask);
+    const int klen = kc - ko - 1;
+    bool mbad = false;
+    if (!kFill) {
+      const uint8_t pk = ab[ko - 1];
+      mbad = kc != c - 1 || !(pk == '{' || pk == ',') || (qk >> 15) != 0;  // a key right before the colon, without escapes
+    }
+    int key = -1;
+    if (klen >= 1 && klen <= 16) {
+      uint64_t k0, k1;
+      load_key(ab + ko + 1, klen, ab + dc.nwords * 32, &k0, &k1);
+      key = in_entry ? match_key(tp.keys.entry, kEntryKeyMul, klen, k0, k1) : match_key(tp.keys.show, kShowKeyMul, klen, k0, k1);
+    }
+    if (!kFill && act && key >= 0) {
+      const uint32_t bit = 1u << key;
+      const uint32_t old = in_entry ? atomicOr(&ws.seen[e], bit) : atomicOr(&ws.seen_show, bit);
+      if (old & bit) mbad = true;  // a known key twice
+    }
+    // what the value is for
+    int heap = -1, tf = -1, numrole = 0, arr_heap = -1;
+    bool is_entries = false;
+    if (in_entry) {
+      if (key >= 0 && key < 14) heap = kHeapEntry0 + key;
+      numrole = key == kEkTs ? 3 : key == kEkDelaySec ? 4 : 0;
+      if (key == kEkActions) arr_heap = kHeapActions;
+    } else {
+      if (key >= 0 && key < 7) heap = key;
+      if (key == kSkCreatedAt) { tf = PIE_TF_CREATED; numrole = 1; }
+      else if (key == kSkArchivedAt) { tf = PIE_TF_ARCHIVED; numrole = 2; }
+      else if (key == kSkUpdatedAt) { tf = PIE_TF_UPDATED; numrole = 5; }
+      else if (key == kSkDeletedAt) { tf = PIE_TF_DELETED; numrole = 6; }
+      if (key == kSkCrew) arr_heap = kHeapCrew;
+      is_entries = key == kSkEntries;
+    }
+    const int v = c + 1;
+    const uint8_t ch = v < dc.span ? ab[v] : 0;
     uint32_t L = 0, N = 0;
-    int vkind = 0;       // 1 plain string, 2 string with escapes, 3 elements of an array
-    int vsrc = 0, vraw = 0, arr_at = 0;
-    uint32_t row = 0;
-    if (k < tot.members) {
-      const int c = ws.colon[k];
-      const int kc = c - 1;
-      const int ko = prev_bit(ws.q, kc);
-      const int d = depth_at(ws, c);
-      bool mbad = ko < 0 || !(d == 1 || d == 3);
+    int vkind = 0;  // 1 plain string (or null) for a heap, 2 string with escapes for a heap, 3 elements of an array
+    int vsrc = 0, vraw = 0;
+    uint32_t strings = 1;
+    uint32_t rkind = kRecNone, rlo = 0;  // pass 1: the member's record
+    if (ch == '"') {
+      // the string behind the colon is the next pair of quotes
+      const bool have = kq + 2 < tot.quotes;
+      const uint32_t qc = ws.qpos[have ? kq + 2 : kq];
+      const int cq = (int)(qc & kPosMask);
+      const bool esc = (qc >> 15) != 0;
+      if (!have || cq + 1 >= dc.span) mbad = true;
+      strings = 2;
       if (!kFill && !mbad) {
-        const uint8_t pk = ab[ko - 1];
-        if (!(pk == '{' || pk == ',')) mbad = true;          // the string before the colon is a key
-        if (kc - ko > 1 && any_bit_between(ws.bs, ko, kc)) mbad = true;  // an escape in a key: the walk's business
+        const uint8_t nc = ab[cq + 1];
+        if (nc != ',' && nc != '}') mbad = true;
       }
-      if (!mbad) {
-        const int klen = kc - ko - 1;
-        int key = -1;
-        if (klen >= 1 && klen <= 16) {
-          uint64_t k0, k1;
-          load_key(ab + ko + 1, klen, ab + dc.nwords * 32, &k0, &k1);
-          key = d == 1 ? match_show_key((uint32_t)klen, k0, k1) : match_entry_key((uint32_t)klen, k0, k1);
+      vsrc = v + 1;
+      vraw = cq - v - 1;
+      if (heap >= 0) {
+        L = (uint32_t)vraw;
+        vkind = 1;
+        if (esc && !mbad) {
+          bool ebad = false;
+          L = (uint32_t)(vraw - escape_savings(ab, vsrc, vraw, ab + dc.nwords * 32, &ebad));
+          vkind = 2;
+          if (ebad) mbad = true;
         }
-        int e = 0;
-        if (d == 3) {
-          e = entry_at(ws, c);
-          row = row0 + (uint32_t)e;
-        }
-        if (!kFill && key >= 0) {
-          const uint32_t bit = 1u << key;
-          const uint32_t old = d == 1 ? atomicOr(&ws.seen_show, bit) : atomicOr(&ws.seen[e], bit);
-          if (old & bit) mbad = true;  // a known key twice
-        }
-        // what the value is for
-        int tf = -1, numrole = 0, arr_heap = -1;
-        bool is_entries = false;
-        if (d == 1) {
-          if (key >= 0 && key < 7) heap = key;
-          else if (key == kSkCreatedAt) { tf = PIE_TF_CREATED; numrole = 1; }
-          else if (key == kSkArchivedAt) { tf = PIE_TF_ARCHIVED; numrole = 2; }
-          else if (key == kSkUpdatedAt) { tf = PIE_TF_UPDATED; numrole = 5; }
-          else if (key == kSkDeletedAt) { tf = PIE_TF_DELETED; numrole = 6; }
-          else if (key == kSkCrew) arr_heap = kHeapCrew;
-          else if (key == kSkEntries) is_entries = true;
-        } else {
-          if (key >= 0 && key < 14) heap = kHeapEntry0 + key;
-          else if (key == kEkTs) numrole = 3;
-          else if (key == kEkDelaySec) numrole = 4;
-          else if (key == kEkActions) arr_heap = kHeapActions;
-        }
-        const int v = c + 1;
-        const uint8_t ch = v < dc.span ? ab[v] : 0;
-        accounted += 1;
-        if (ch == '"') {
-          const int cq = next_bit(ws.q, v, dc.nwords);
-          if (cq < 0 || cq + 1 >= dc.span) {
-            mbad = true;
-          } else {
-            accounted += 1;
-            if (!kFill) {
-              const uint8_t nc = ab[cq + 1];
-              if (nc != ',' && nc != '}') mbad = true;
-            }
-            const int raw = cq - v - 1;
-            const bool esc = raw > 0 && any_bit_between(ws.bs, v, cq);
-            if (heap >= 0) {
-              vsrc = v + 1;
-              vraw = raw;
-              L = (uint32_t)raw;
-              vkind = 1;
-              if (esc) {
-                bool ebad = false;
-                L = (uint32_t)(raw - escape_savings(ws, ab, v, cq, &ebad));
-                vkind = 2;
-                if (ebad) mbad = true;
-              }
-            } else {
-              if (esc) mbad = true;  // nobody unescapes it here, so nobody validates it: the walk does
-              if (numrole == 4 || arr_heap == kHeapActions) mbad = true;  // delaySec / actions that are text
-              if (kFill) {
-                if (tf >= 0) {
-                  if (out.time_kind) out.time_kind[s * PIE_TF_COUNT + tf] = (uint8_t)PIE_TK_STRING;
-                  if (out.time_val[tf])
-                    out.time_val[tf][s] =
-                        np_bits_to_double(0x7ff8000000000000ull | ((uint64_t)((ab + v + 1) - out.text) & 0x7ffffffffffffull));
-                } else if (numrole == 3) {
-                  out.entry_ts[row] = jw_nan();
-                }
-              }
-            }
-          }
-        } else if (ch == '[') {
-          if (arr_heap >= 0) {
-            heap = arr_heap;
-            vkind = 3;
-            arr_at = v;
-            if (!walk_items<false>(ws, dc, v, &N, &L, nullptr, nullptr, 0, 0)) mbad = true;
-            accounted += N;
-          } else if (!is_entries) {
-            mbad = true;  // an array under any other key
-          }
-          heap = arr_heap;
-        } else if (ch == '-' || (ch >= '0' && ch <= '9')) {
-          if (heap >= 0 || arr_heap == kHeapActions) mbad = true;  // a number where text / a list belongs
-          heap = -1;
-          const uint32_t slot = atomicAdd(&ws.n_num, 1u);
-          if (slot < (uint32_t)kFastMaxNumbers) ws.num[slot] = (uint32_t)v | ((uint32_t)e << 13) | ((uint32_t)numrole << 21);
-          else mbad = true;
-        } else {
-          const char* lit = ch == 'n' ? "null" : ch == 't' ? "true" : ch == 'f' ? "false" : nullptr;
-          int ln = 0;
-          if (!lit) {
-            mbad = true;
-          } else {
-            for (; lit[ln]; ++ln)
-              if (v + ln >= dc.span || ab[v + ln] != (uint8_t)lit[ln]) mbad = true;
-            const uint8_t nc = v + ln < dc.span ? ab[v + ln] : 0;
-            if (nc != ',' && nc != '}') mbad = true;
-          }
-          if (ch != 'n' && (heap >= 0 || numrole == 4)) mbad = true;  // true / false where text / a number belongs
-          if (arr_heap == kHeapActions) mbad = true;
-          if (heap >= 0) vkind = 1;  // null: the empty text (its offset is still written)
-          if (kFill && !mbad) {
-            if (tf >= 0) {
-              if (out.time_kind)
-                out.time_kind[s * PIE_TF_COUNT + tf] = (uint8_t)(ch == 'n' ? PIE_TK_NULL : ch == 't' ? PIE_TK_TRUE : PIE_TK_FALSE);
-            } else if (numrole == 3) {
-              out.entry_ts[row] = jw_nan();
-            } else if (numrole == 4) {
-              out.delay_sec[row] = 0.0;
-              out.delay_valid[row] = 0;
-            }
+      } else {
+        if (esc) mbad = true;  // nobody unescapes it here, so nobody validates it: the walk does
+        if (numrole == 4 || arr_heap == kHeapActions) mbad = true;  // delaySec / actions that are text
+        if (tf >= 0) { rkind = kRecTimeString; rlo = (uint32_t)(v + 1); }
+        else if (numrole == 3) rkind = kRecNanTs;
+        if (kFill && act) {
+          if (tf >= 0) {
+            if (out.time_kind) out.time_kind[s * PIE_TF_COUNT + tf] = (uint8_t)PIE_TK_STRING;
+            if (out.time_val[tf])
+              out.time_val[tf][s] = np_bits_to_double(0x7ff8000000000000ull | ((uint64_t)((ab + v + 1) - out.text) & 0x7ffffffffffffull));
+          } else if (numrole == 3) {
+            out.entry_ts[row] = jw_nan();
           }
         }
       }
-      if (mbad) {
-        bad = true;
-        heap = -1;
-        vkind = 0;
-        L = N = 0;
+    } else if (ch == '[') {
+      if (arr_heap >= 0) {
+        vkind = 3;
+        if (!walk_items<0>(ws, dc, v, kq + 1, tot.quotes, &N, &L, nullptr, nullptr, 0, 0)) mbad = true;
+        strings += N;
+      } else if (!is_entries) {
+        mbad = true;  // an array under any other key
+      }
+      heap = arr_heap;
+    } else if (ch == '-' || (ch >= '0' && ch <= '9')) {
+      if (heap >= 0 || arr_heap == kHeapActions) mbad = true;  // a number where text / a list belongs
+      heap = -1;
+      if (act) {
+        const uint32_t slot = atomicAdd(&ws.n_num, 1u);
+        if (slot < (uint32_t)kFastMaxNumbers) ws.num[slot] = (uint32_t)v | ((uint32_t)e << 14) | ((uint32_t)numrole << 21);
+        else mbad = true;
+      }
+    } else {
+      // null, true, false
+      const uint32_t w4 = (uint32_t)ch | ((uint32_t)(v + 1 < dc.span ? ab[v + 1] : 0) << 8) |
+                          ((uint32_t)(v + 2 < dc.span ? ab[v + 2] : 0) << 16) | ((uint32_t)(v + 3 < dc.span ? ab[v + 3] : 0) << 24);
+      int ln = 0;
+      if (w4 == 0x6c6c756eu) ln = 4;       // "null"
+      else if (w4 == 0x65757274u) ln = 4;  // "true"
+      else if (w4 == 0x736c6166u && v + 4 < dc.span && ab[v + 4] == 'e') ln = 5;  // "false"
+      const uint8_t nc = (ln && v + ln < dc.span) ? ab[v + ln] : 0;
+      if (nc != ',' && nc != '}') mbad = true;
+      if (ch != 'n' && (heap >= 0 || numrole == 4)) mbad = true;  // true / false where text / a number belongs
+      if (arr_heap == kHeapActions) mbad = true;
+      if (heap >= 0) vkind = 1;  // null: the empty text (its offset is still written)
+      if (tf >= 0) { rkind = kRecTimeKind; rlo = (uint32_t)(ch == 'n' ? PIE_TK_NULL : ch == 't' ? PIE_TK_TRUE : PIE_TK_FALSE); }
+      else if (numrole == 3) rkind = kRecNanTs;
+      else if (numrole == 4) rkind = kRecNullDelay;
+      if (kFill && act && !mbad) {
+        if (tf >= 0) {
+          if (out.time_kind)
+            out.time_kind[s * PIE_TF_COUNT + tf] = (uint8_t)(ch == 'n' ? PIE_TK_NULL : ch == 't' ? PIE_TK_TRUE : PIE_TK_FALSE);
+        } else if (numrole == 3) {
+          out.entry_ts[row] = jw_nan();
+        } else if (numrole == 4) {
+          out.delay_sec[row] = 0.0;
+          out.delay_valid[row] = 0;
+        }
       }
     }
-    if (!kFill) {
+    if (!act) {
+      mbad = false;
+      strings = 0;
+    }
+    if (mbad || !act) {
+      heap = -1;
+      vkind = 0;
+      L = N = 0;
+    }
+    bad |= mbad;
+    accounted += strings;
+    if (!kFill && !rec_on) {
       if (heap >= 0) {
         if (L) atomicAdd(&ws.cnt[heap], L);
         if (N) atomicAdd(&ws.cnt[heap == kHeapCrew ? kPlaneCrewItems : kPlaneActionItems], N);
       }
       continue;
     }
-    // ---- fill: where this member's bytes go — the members of a heap in document order
+    // ---- where this member's bytes go — the members of a heap in document order
     bool leader;
     const uint32_t pre = group_prefix(heap >= 0 ? heap : 64 + lane, L | (N << 16), lt, &leader);
     const uint32_t preL = pre & 0xffffu, preN = pre >> 16;
@@ -698,12 +840,41 @@ __device__ __forceinline__ bool fast_doc(WarpShared& ws, const TablePointers& tp
       ws.cnt[heap] = dst + L;
       if (vkind == 3) ws.cnt[items_plane] = item0 + N;
     }
+    if (!kFill) {
+      // pass 1 with records: the counters run from 0, so dst / item0 are relative to the document's part
+      uint32_t rhi = 0;
+      if (vkind == 1 || vkind == 2) {
+        rkind = kRecText;
+        rlo = (uint32_t)vsrc | ((uint32_t)vraw << 14) | ((uint32_t)(vkind == 2) << 28);
+        if (L == 0) rlo = 0;  // null or '': nothing to copy
+        rhi = (uint32_t)heap | ((uint32_t)e << 5) | (dst << 12);
+      } else if (vkind == 3) {
+        rkind = kRecArray;
+        rlo = item0;
+        rhi = (uint32_t)heap | ((uint32_t)e << 5);
+        if (N) {  // its elements' records are written when all of the document's are counted
+          const uint32_t slot = atomicAdd(&ws.n_arr, 1u);
+          const uint32_t first = atomicAdd(&ws.n_items, N);
+          if (slot < (uint32_t)kFastMaxArrays) {
+            ws.arr[slot][0] = (uint32_t)v | ((uint32_t)(kq + 1) << 14) | ((uint32_t)(heap == kHeapActions) << 25);
+            ws.arr[slot][1] = dst | (item0 << 14);
+            ws.arr[slot][2] = first;
+          }
+        }
+      } else {
+        rhi = (uint32_t)e << 5;
+        if (rkind == kRecTimeKind || rkind == kRecTimeString) rhi = (uint32_t)tf;
+      }
+      if (act) slots[k] = (unsigned long long)rlo | ((unsigned long long)(rhi | (rkind << 29)) << 32);
+      __syncwarp();
+      continue;
+    }
     if (heap >= 0) {
       if (heap >= kHeapEntry0 && heap < kHeapActions) tp.off[heap][row] = (int32_t)dst;
       if (vkind == 3) {
         if (heap == kHeapActions) out.actions_list[row] = (int32_t)item0;
         uint32_t nn, bb;
-        walk_items<true>(ws, dc, arr_at, &nn, &bb, tp.off[heap], tp.data[heap], item0, dst);
+        walk_items<1>(ws, dc, v, kq + 1, tot.quotes, &nn, &bb, tp.off[heap], tp.data[heap], item0, dst);
       } else if (vkind == 2) {
         const uint32_t slot = atomicAdd(&ws.n_esc, 1u);
         if (slot < (uint32_t)kFastMaxEsc) {
@@ -711,11 +882,12 @@ __device__ __forceinline__ bool fast_doc(WarpShared& ws, const TablePointers& tp
           ws.esc_dst[slot] = dst;
           ws.esc_heap[slot] = (uint8_t)heap;
         } else {
-          unescape_copy(ab, vsrc, vraw, tp.data[heap] + dst);
+          unescape_copy(ab, vsrc, vraw, tp.data[heap] + dst, ab + dc.nwords * 32);
         }
       } else if (vkind == 1 && L <= (uint32_t)kInlineCopy) {
         uint8_t* dp = tp.data[heap] + dst;
-        for (uint32_t i = 0; i < L; ++i) dp[i] = ab[vsrc + i];
+        store_upto8(dp, load8(ab + vsrc, ab + dc.nwords * 32), (int)L);
+        if (L > 8) store_upto8(dp + 8, load8(ab + vsrc + 8, ab + dc.nwords * 32), (int)L - 8);
       }
     }
     // long plain values: the whole warp copies each
@@ -732,20 +904,33 @@ __device__ __forceinline__ bool fast_doc(WarpShared& ws, const TablePointers& tp
     __syncwarp();
   }
 
-  // ---- numbers: a lane each
+  // ---- numbers: a lane each, the text through a register window (DocCursor: 8 aligned bytes at a time)
   __syncwarp();
+  unsigned long long extra_at = 0;
+  if (!kFill && rec_on) {
+    if (ws.n_arr > (uint32_t)kFastMaxArrays) rec_on = false;
+    const unsigned long long units = 2ull * ws.n_num + ws.n_items;
+    if (lane == 0) extra_at = atomicAdd(rc.cursor, units);
+    extra_at = __shfl_sync(kFull, extra_at, 0);
+    if (extra_at + units > rc.capacity) rec_on = false;
+  }
   {
     const uint32_t nn = ws.n_num < (uint32_t)kFastMaxNumbers ? ws.n_num : (uint32_t)kFastMaxNumbers;
     for (uint32_t i = lane; i < nn; i += 32) {
       const uint32_t rec = ws.num[i];
-      const int pos = (int)(rec & 8191u), role = (int)(rec >> 21);
-      const uint32_t row = row0 + ((rec >> 13) & 255u);
-      MemSource src{ab, (int64_t)dc.span, (int64_t)pos};
+      const int pos = (int)(rec & kPosMask), role = (int)(rec >> 21);
+      const uint32_t row = row0 + ((rec >> 14) & 127u);
+      DocCursor src;
+      src.open(ab, pos, dc.span);
       double v = 0.0;
-      const int rc = role ? parse_json_number_from<true>(src, pow5, &v) : parse_json_number_from<false>(src, pow5, &v);
+      const int prc = role ? parse_json_number_from<true>(src, pow5, &v) : parse_json_number_from<false>(src, pow5, &v);
       if (!kFill) {
-        const uint8_t term = src.i < dc.span ? ab[src.i] : 0;
-        if (rc != kNumOk || (term != ',' && term != '}')) bad = true;
+        const int term = src.peek();
+        if (prc != kNumOk || (term != ',' && term != '}')) bad = true;
+        if (rec_on) {
+          rc.pool[extra_at + 2ull * i] = (unsigned long long)((uint32_t)role | (((rec >> 14) & 127u) << 3));
+          rc.pool[extra_at + 2ull * i + 1] = (unsigned long long)__double_as_longlong(v);
+        }
       } else if (role == 3) {
         out.entry_ts[row] = jw_is_finite(v) ? v : jw_nan();
       } else if (role == 4) {
@@ -764,7 +949,7 @@ __device__ __forceinline__ bool fast_doc(WarpShared& ws, const TablePointers& tp
     const uint32_t ne = ws.n_esc < (uint32_t)kFastMaxEsc ? ws.n_esc : (uint32_t)kFastMaxEsc;
     for (uint32_t i = lane; i < ne; i += 32) {
       const uint32_t sr = ws.esc_src[i];
-      unescape_copy(ab, (int)(sr & 0xffffu), (int)(sr >> 16), tp.data[ws.esc_heap[i]] + ws.esc_dst[i]);
+      unescape_copy(ab, (int)(sr & 0xffffu), (int)(sr >> 16), tp.data[ws.esc_heap[i]] + ws.esc_dst[i], ab + dc.nwords * 32);
     }
     if (s == n_docs - 1) {  // the terminal offsets: where the last document ended
       __syncwarp();
@@ -777,20 +962,138 @@ __device__ __forceinline__ bool fast_doc(WarpShared& ws, const TablePointers& tp
       else if (lane == 11) tp.off[kHeapActions][ws.cnt[kPlaneActionItems]] = (int32_t)ws.cnt[kHeapActions];
       else if (lane >= 12 && lane < 26) tp.off[kHeapEntry0 + lane - 12][rows] = (int32_t)ws.cnt[kHeapEntry0 + lane - 12];
     }
-    return true;
+    return kRouteFast;
   } else {
+    // ---- the elements of crew / actions: their records, a lane per array
+    if (rec_on) {
+      const uint32_t na = ws.n_arr;
+      for (uint32_t i = lane; i < na; i += 32) {
+        const uint32_t a0 = ws.arr[i][0], a1 = ws.arr[i][1];
+        uint32_t nn, bb;
+        walk_items<2>(ws, dc, (int)(a0 & kPosMask), (int)((a0 >> 14) & 0x7ff), tot.quotes, &nn, &bb, nullptr, nullptr, a1 >> 14,
+                      a1 & 0x3fffu, rc.pool + extra_at + 2ull * ws.n_num + ws.arr[i][2],
+                      (a0 >> 25) ? (uint32_t)kHeapActions : (uint32_t)kHeapCrew);
+      }
+    }
     // ---- measure: is it the shape, all of it?
     for (int e = lane; e < tot.entries; e += 32)
       if (ws.seen[e] != kAllEntryKeys) bad = true;  // an entry without one of its keys: the walk fills the gaps
 #pragma unroll
     for (int dlt = 16; dlt > 0; dlt >>= 1) accounted += __shfl_xor_sync(kFull, accounted, dlt);
-    if (accounted != (uint32_t)tot.strings) bad = true;  // a string that is neither key, value nor element
-    if (__any_sync(kFull, bad)) return false;
+    if (2 * accounted != (uint32_t)tot.quotes) bad = true;  // a string that is neither key, value nor element
+    if (__any_sync(kFull, bad)) return kRouteSlow;
     __syncwarp();
-    if (lane == 0) ws.cnt[kPlaneEntries] = (uint32_t)tot.entries;
+    if (lane == 0) {
+      ws.cnt[kPlaneEntries] = (uint32_t)tot.entries;
+      if (rec_on) rc.doc_rec[s] = DocRec{members_at, extra_at, (uint32_t)tot.members, ws.n_num, ws.n_items, 0u};
+    }
     __syncwarp();
     if (lane < kPlanes) planes_row[lane] = ws.cnt[lane];
-    return true;
+    return rec_on ? kRouteRecords : kRouteFast;
+  }
+}
+
+// ---- pass 2 of a document with records: a scatter ----------------------------------------------------------------
+__device__ __forceinline__ void fill_records(WarpShared& ws, const TablePointers& tp, const uint8_t* __restrict__ text, int64_t from,
+                                             int64_t to, int64_t s, const uint32_t* __restrict__ planes_row, const IngestOut& out,
+                                             const RecCtx& rc) {
+  const int lane = threadIdx.x & 31;
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(text + from);
+  const int skip = (int)(a0 & 31);
+  const uint8_t* ab = reinterpret_cast<const uint8_t*>(a0 - skip);
+  const uint8_t* limit = ab + (((skip + (int)(to - from)) + 31) & ~31);
+  __syncwarp();
+  if (lane < kPlanes) ws.cnt[lane] = planes_row[lane];
+  const DocRec dr = rc.doc_rec[s];
+  __syncwarp();
+  const uint32_t row0 = ws.cnt[kPlaneEntries];
+  if (lane < 7) tp.off[lane][s] = (int32_t)ws.cnt[lane];
+  else if (lane == 7) out.entry_offsets[s] = (int32_t)row0;
+  else if (lane == 8) out.crew_list[s] = (int32_t)ws.cnt[kPlaneCrewItems];
+  else if (lane < 9 + PIE_TF_COUNT) { if (out.time_val[lane - 9]) out.time_val[lane - 9][s] = jw_nan(); }
+  else if (lane == 9 + PIE_TF_COUNT) { if (out.time_kind) *reinterpret_cast<uint32_t*>(out.time_kind + s * PIE_TF_COUNT) = 0u; }
+  __syncwarp();
+  const unsigned long long* slots = rc.pool + dr.members_at;
+  const int steps = ((int)dr.members + 31) >> 5;
+  for (int t = 0; t < steps; ++t) {
+    const int k = t * 32 + lane;
+    unsigned long long r = 0;
+    if (k < (int)dr.members) r = slots[k];
+    const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+    const uint32_t kind = hi >> 29, heap = hi & 31u, row = row0 + ((hi >> 5) & 127u);
+    int src = 0;
+    uint32_t len = 0, dst = 0;
+    bool plain = false;
+    if (kind == kRecText) {
+      src = (int)(lo & kPosMask);
+      len = (lo >> 14) & kPosMask;
+      dst = ws.cnt[heap] + ((hi >> 12) & kPosMask);
+      if (heap >= (uint32_t)kHeapEntry0) tp.off[heap][row] = (int32_t)dst;
+      if ((lo >> 28) & 1u) {
+        unescape_copy(ab, src, (int)len, tp.data[heap] + dst, limit);
+      } else {
+        plain = true;
+        if (len <= (uint32_t)kInlineCopy) {
+          uint8_t* dp = tp.data[heap] + dst;
+          if (len) store_upto8(dp, load8(ab + src, limit), (int)len);
+          if (len > 8) store_upto8(dp + 8, load8(ab + src + 8, limit), (int)len - 8);
+        }
+      }
+    } else if (kind == kRecArray) {
+      if (heap == (uint32_t)kHeapActions) out.actions_list[row] = (int32_t)(ws.cnt[kPlaneActionItems] + lo);
+    } else if (kind == kRecNullDelay) {
+      out.delay_sec[row] = 0.0;
+      out.delay_valid[row] = 0;
+    } else if (kind == kRecNanTs) {
+      out.entry_ts[row] = jw_nan();
+    } else if (kind == kRecTimeKind) {
+      if (out.time_kind) out.time_kind[s * PIE_TF_COUNT + (hi & 3u)] = (uint8_t)lo;
+    } else if (kind == kRecTimeString) {
+      const uint32_t tf = hi & 3u;
+      if (out.time_kind) out.time_kind[s * PIE_TF_COUNT + tf] = (uint8_t)PIE_TK_STRING;
+      if (out.time_val[tf])
+        out.time_val[tf][s] = np_bits_to_double(0x7ff8000000000000ull | ((uint64_t)((ab + lo) - out.text) & 0x7ffffffffffffull));
+    }
+    // long plain values: the whole warp copies each
+    uint32_t longm = __ballot_sync(kFull, plain && len > (uint32_t)kInlineCopy);
+    while (longm) {
+      const int j = __ffs(longm) - 1;
+      longm &= longm - 1;
+      const int src_j = __shfl_sync(kFull, src, j);
+      const uint32_t len_j = __shfl_sync(kFull, len, j), dst_j = __shfl_sync(kFull, dst, j), heap_j = __shfl_sync(kFull, heap, j);
+      uint8_t* dp = tp.data[heap_j] + dst_j;
+      for (uint32_t i = lane; i < len_j; i += 32) dp[i] = ab[src_j + i];
+    }
+  }
+  const unsigned long long* extra = rc.pool + dr.extra_at;
+  for (uint32_t i = lane; i < dr.numbers; i += 32) {
+    const uint32_t tag = (uint32_t)extra[2ull * i];
+    const double v = __longlong_as_double((long long)extra[2ull * i + 1]);
+    const int role = (int)(tag & 7u);
+    const uint32_t row = row0 + ((tag >> 3) & 127u);
+    const bool fin = jw_is_finite(v);
+    if (role == 3) {
+      out.entry_ts[row] = fin ? v : jw_nan();
+    } else if (role == 4) {
+      out.delay_sec[row] = v;
+      out.delay_valid[row] = 1;
+    } else if (role) {
+      const int tf = role == 1 ? PIE_TF_CREATED : role == 2 ? PIE_TF_ARCHIVED : role == 5 ? PIE_TF_UPDATED : PIE_TF_DELETED;
+      if (out.time_val[tf]) out.time_val[tf][s] = fin ? v : jw_nan();
+      if (out.time_kind) out.time_kind[s * PIE_TF_COUNT + tf] = (uint8_t)(fin ? PIE_TK_NUMBER : PIE_TK_NONFINITE);
+    }
+  }
+  const unsigned long long* items = extra + 2ull * dr.numbers;
+  for (uint32_t i = lane; i < dr.items; i += 32) {
+    const unsigned long long r = items[i];
+    const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+    const uint32_t heap = hi & 31u;
+    const uint32_t dst = ws.cnt[heap] + ((hi >> 5) & kPosMask);
+    const uint32_t item = ws.cnt[heap == (uint32_t)kHeapCrew ? kPlaneCrewItems : kPlaneActionItems] + (hi >> 19);
+    tp.off[heap][item] = (int32_t)dst;
+    const int src = (int)(lo & kPosMask), raw = (int)((lo >> 14) & kPosMask);
+    if ((lo >> 28) & 1u) unescape_copy(ab, src, raw, tp.data[heap] + dst, limit);
+    else copy_plain(ab + src, raw, tp.data[heap] + dst, limit);
   }
 }
 
