@@ -323,7 +323,7 @@ int pie_debug_csv_slow_tiles(const void* scratch, int64_t n_entries, uint32_t* s
  * (JSON.stringify of _normalizeShow's result, sqlProvider.js:361-409) a warp per document and hands every other
  * document to the thread-per-document walk; results are identical either way.
  * pie_debug_ingest_warp_path: 1 / 0 switches the warp path on / off, < 0 only queries; returns the previous value
- * (off unless the environment variable PIE_INGEST_WARP_PATH=1 is set).
+ * (on unless the environment variable PIE_INGEST_WARP_PATH=0 is set).
  * pie_debug_ingest_declined: how many documents of the last pie_ingest_measure_dev on `scratch` the warp path
  * declined (synchronises `stream`). */
 int pie_debug_ingest_warp_path(int on);

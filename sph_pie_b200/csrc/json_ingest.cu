@@ -157,10 +157,26 @@ __global__ void __launch_bounds__(jf::kFastThreads) ingest_fast_kernel(const int
   __syncthreads();
   const Pow5Table pow5{g_pow5_dev};
   const int lane = threadIdx.x & 31;
+  // pass 2 draws a document ahead and asks L2 for its text and records while it works on the current one (a scatter
+  // is a chain of dependent loads: record -> text -> store)
+  int64_t ahead = -1;
+  if (kFill) {
+    unsigned long long d0 = 0;
+    if (lane == 0) d0 = atomicAdd(sc.next_fast + 1, 1ull);
+    ahead = (int64_t)__shfl_sync(0xffffffffu, d0, 0);
+    if (ahead < n_docs && sc.route[ahead] == jf::kRouteRecords) jf::prefetch_records_doc(text, doc_offsets[ahead], doc_offsets[ahead + 1], ahead, sc.rec);
+  }
   for (;;) {
     unsigned long long drawn = 0;
     if (lane == 0) drawn = atomicAdd(sc.next_fast + (kFill ? 1 : 0), 1ull);
-    const int64_t s = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
+    int64_t s = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
+    if (kFill) {
+      const int64_t next = s;
+      s = ahead;
+      ahead = next;
+      if (s >= n_docs) break;
+      if (ahead < n_docs && sc.route[ahead] == jf::kRouteRecords) jf::prefetch_records_doc(text, doc_offsets[ahead], doc_offsets[ahead + 1], ahead, sc.rec);
+    }
     if (s >= n_docs) break;
     if (kFill) {
       const uint8_t route = sc.route[s];
@@ -471,13 +487,14 @@ IngestScratch carve(void* scratch, int64_t n_docs) {
   return sc;
 }
 
-// PIE_INGEST_WARP_PATH=0 keeps every document on the thread-per-document walk (the round-1 pipeline: A/B timing)
+// PIE_INGEST_WARP_PATH=0 keeps every document on the thread-per-document walk (the round-1 pipeline: A/B timing; it is
+// the faster one only when a warp's 32 documents are copies of one another, profiles/ncu_r02_ingest_summary.md)
 std::atomic<int> g_warp_path{-1};  // -1: not decided yet (the environment decides)
 bool warp_path_enabled() {
   int v = g_warp_path.load();
   if (v < 0) {
     const char* e = std::getenv("PIE_INGEST_WARP_PATH");
-    v = (e && e[0] == '1') ? 1 : 0;  // opt-in until it beats the walk on every workload (profiles/ncu_r02_ingest_summary.md)
+    v = (e && e[0] == '0') ? 0 : 1;
     g_warp_path.store(v);
   }
   return v != 0;

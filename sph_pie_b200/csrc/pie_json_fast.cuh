@@ -30,6 +30,34 @@
 #include "pie_device.cuh"
 #include "pie_json_walk.cuh"
 
+// build-time experiment switches (scripts/_variants): which helpers are out of line, the number fast path
+// Measured on B200 (2^19 documents, pass 1): everything inline, generic number parser 9.6 ms; number fast path 10.0;
+// parse_number_at out of line 10.5 / 9.9 without the fast path; every helper out of line 11.9.  Pass 1 waits for
+// instructions (8 "no instruction" stalls per issue: > 64 KB of SASS, 28 warps in different places of it), so anything
+// that adds code or jumps far costs more than the instructions it saves.
+#ifndef PIE_JF_NOINLINE_MASK
+#define PIE_JF_NOINLINE_MASK 0
+#endif
+#ifndef PIE_JF_FASTNUM
+#define PIE_JF_FASTNUM 0
+#endif
+#define PIE_JF_INL(bit) ((PIE_JF_NOINLINE_MASK >> (bit)) & 1)
+#if PIE_JF_INL(0)
+#define PIE_JF_ESC_FN __device__ __noinline__
+#else
+#define PIE_JF_ESC_FN __device__ __forceinline__
+#endif
+#if PIE_JF_INL(1)
+#define PIE_JF_ITEMS_FN __device__ __noinline__
+#else
+#define PIE_JF_ITEMS_FN __device__ __forceinline__
+#endif
+#if PIE_JF_INL(2)
+#define PIE_JF_NUM_FN __device__ __noinline__
+#else
+#define PIE_JF_NUM_FN __device__ __forceinline__
+#endif
+
 namespace pie {
 namespace jf {
 
@@ -226,7 +254,7 @@ __device__ __forceinline__ void copy_plain(const uint8_t* src, int len, uint8_t*
 // what the escapes of the raw string ab[src .. src + raw) save: raw bytes minus unescaped bytes; *bad when an escape
 // is not one of ECMA-404's, or names a surrogate (the walk decides those).  Only called for strings stage 1 flagged.
 // Backslashes are found 8 bytes at a time.
-__device__ __forceinline__ int escape_savings(const uint8_t* ab, int src, int raw, const uint8_t* limit, bool* bad) {
+PIE_JF_ESC_FN int escape_savings(const uint8_t* ab, int src, int raw, const uint8_t* limit, bool* bad) {
   int saved = 0, i = 0;
   while (i < raw) {
     {
@@ -262,7 +290,7 @@ __device__ __forceinline__ int escape_savings(const uint8_t* ab, int src, int ra
 }
 // the unescaped bytes of ab[src .. src + raw) to dst (escapes already validated); returns how many.  Plain runs go 8
 // bytes at a time.
-__device__ __forceinline__ int unescape_copy(const uint8_t* ab, int src, int raw, uint8_t* dst, const uint8_t* limit) {
+PIE_JF_ESC_FN int unescape_copy(const uint8_t* ab, int src, int raw, uint8_t* dst, const uint8_t* limit) {
   int i = 0, o = 0;
   while (i < raw) {
     const uint64_t w = load8(ab + src + i, limit);
@@ -334,6 +362,98 @@ __device__ __noinline__ bool utf8_ok(const uint8_t* ab, uint32_t hib, int pos0, 
     done = bit + need + 1;
   }
   return true;
+}
+
+// ---- numbers ------------------------------------------------------------------------------------------------------
+// eight ASCII digits, the first in the low byte, as a number
+__device__ __forceinline__ uint32_t digits8(uint64_t x) {
+  x = (x & 0x0f0f0f0f0f0f0f0full) * 2561 >> 8;
+  x = (x & 0x00ff00ff00ff00ffull) * 6553601 >> 16;
+  return (uint32_t)((x & 0x0000ffff0000ffffull) * 42949672960001ull >> 32);
+}
+// bit 7 of every byte of x that is an ASCII digit
+__device__ __forceinline__ uint64_t digit_flags(uint64_t x) {
+  const uint64_t lo7 = x & 0x7f7f7f7f7f7f7f7full;
+  const uint64_t ge0 = lo7 + 0x5050505050505050ull;  // bit 7: >= '0'
+  const uint64_t gt9 = lo7 + 0x4646464646464646ull;  // bit 7: > '9'
+  return ge0 & ~gt9 & ~x & 0x8080808080808080ull;
+}
+// The JSON number at ab[pos ..) (the document ends at span): its value, and in *term the byte behind it (-1: none).
+// Numbers of the everyday form -?digits(.digits)? with at most 15 digits that end within 16 bytes are read 8 bytes at
+// a time and converted by ONE exact IEEE operation, as parse_json_number_from does for them (Clinger's case: the
+// digits as an integer below 2^53, over an exact power of ten); everything else goes through that parser.
+PIE_JF_NUM_FN int parse_number_at(const uint8_t* ab, int pos, int span, const uint8_t* limit, const Pow5Table& pow5,
+                                            double* value, int* term) {
+  if (PIE_JF_FASTNUM) {
+    uint64_t lo = load8(ab + pos, limit), hi = load8(ab + pos + 8, limit);
+    const int avail = span - pos;  // >= 1
+    const bool neg = (lo & 0xff) == '-';
+    int at = 0;
+    if (neg) {  // drop the sign
+      lo = (lo >> 8) | (hi << 56);
+      hi >>= 8;
+      at = 1;
+    }
+    const uint64_t d_lo = digit_flags(lo), d_hi = digit_flags(hi);
+    // length of the run of digits at the start
+    const uint64_t nd_lo = ~d_lo & 0x8080808080808080ull;
+    int n1 = nd_lo ? (__ffsll((long long)nd_lo) - 1) >> 3 : 8;
+    if (n1 == 8) {
+      const uint64_t nd_hi = ~d_hi & 0x8080808080808080ull;
+      n1 += nd_hi ? (__ffsll((long long)nd_hi) - 1) >> 3 : 8;
+    }
+    // the bytes from the first non-digit on, as a 128-bit shift
+    if (n1 >= 1 && n1 <= 15 && !((lo & 0xff) == '0' && n1 > 1)) {
+      // integer part: n1 digits (no leading zero unless it is the only digit)
+      uint64_t a = lo, b = hi;
+      uint64_t ip;
+      if (n1 <= 8) {
+        ip = digits8((a & (n1 == 8 ? ~0ull : ((1ull << (8 * n1)) - 1ull))) << (8 * (8 - n1)));
+      } else {
+        const int r = n1 - 8;
+        ip = (uint64_t)digits8(a) * (r == 1 ? 10ull : r == 2 ? 100ull : r == 3 ? 1000ull : r == 4 ? 10000ull : r == 5 ? 100000ull
+                                                         : r == 6 ? 1000000ull : 10000000ull) +
+             digits8((b & ((1ull << (8 * r)) - 1ull)) << (8 * (8 - r)));
+      }
+      // what follows the integer part
+      uint64_t rest_lo, rest_hi;
+      if (n1 < 8) { rest_lo = (a >> (8 * n1)) | (b << (64 - 8 * n1)); rest_hi = b >> (8 * n1); }
+      else if (n1 == 8) { rest_lo = b; rest_hi = 0; }
+      else { rest_lo = b >> (8 * (n1 - 8)); rest_hi = 0; }
+      int used = at + n1;
+      int nf = 0;
+      uint64_t fp = 0;
+      bool ok = true;
+      if ((rest_lo & 0xff) == '.') {
+        const uint64_t f = (rest_lo >> 8) | (rest_hi << 56);
+        const uint64_t nd = ~digit_flags(f) & 0x8080808080808080ull;
+        nf = nd ? (__ffsll((long long)nd) - 1) >> 3 : 8;
+        ok = nf >= 1 && nf <= 7 && n1 + nf <= 15 && used + 1 + nf < 16;  // the digit run must end inside what was loaded
+        if (ok) fp = digits8((f & ((1ull << (8 * nf)) - 1ull)) << (8 * (8 - nf)));
+        used += 1 + nf;
+        rest_lo = f >> (8 * nf);
+      } else {
+        ok = used < 16;
+      }
+      const uint32_t t = (uint32_t)(rest_lo & 0xff);
+      if (ok && used <= avail && t != 'e' && t != 'E' && t != '.' && !(t >= '0' && t <= '9')) {
+        static const double kPow10[8] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7};
+        const uint64_t scale = nf == 0 ? 1ull : nf == 1 ? 10ull : nf == 2 ? 100ull : nf == 3 ? 1000ull : nf == 4 ? 10000ull
+                               : nf == 5 ? 100000ull : nf == 6 ? 1000000ull : 10000000ull;
+        const uint64_t w = ip * scale + fp;
+        double d = (double)w;
+        if (nf) d = d / kPow10[nf];
+        *value = neg ? -d : d;
+        *term = used < avail ? (int)ab[pos + used] : -1;
+        return kNumOk;
+      }
+    }
+  }
+  DocCursor src;
+  src.open(ab, pos, span);
+  const int rc = parse_json_number_from<true>(src, pow5, value);
+  *term = src.peek();
+  return rc;
 }
 
 // ---- stage 1 ------------------------------------------------------------------------------------------------------
@@ -573,7 +693,7 @@ __device__ __forceinline__ uint32_t group_prefix(int key, uint32_t val, uint32_t
 // quote behind the bracket.  kMode 0: counts them and their unescaped bytes; 1: writes offsets and bytes from
 // (item0, dst0) on; 2: writes their records (heap; item0 / dst0 relative to the document).  false = not the shape.
 template <int kMode>
-__device__ __forceinline__ bool walk_items(const WarpShared& ws, const Doc& dc, int at, int qi, int n_quotes, uint32_t* n_items,
+PIE_JF_ITEMS_FN bool walk_items(const WarpShared& ws, const Doc& dc, int at, int qi, int n_quotes, uint32_t* n_items,
                                            uint32_t* n_bytes, int32_t* off, uint8_t* data, uint32_t item0, uint32_t dst0,
                                            unsigned long long* recs = nullptr, uint32_t heap = 0) {
   uint32_t N = 0, B = 0;
@@ -920,12 +1040,10 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
       const uint32_t rec = ws.num[i];
       const int pos = (int)(rec & kPosMask), role = (int)(rec >> 21);
       const uint32_t row = row0 + ((rec >> 14) & 127u);
-      DocCursor src;
-      src.open(ab, pos, dc.span);
       double v = 0.0;
-      const int prc = role ? parse_json_number_from<true>(src, pow5, &v) : parse_json_number_from<false>(src, pow5, &v);
+      int term = -1;
+      const int prc = parse_number_at(ab, pos, dc.span, ab + dc.nwords * 32, pow5, &v, &term);
       if (!kFill) {
-        const int term = src.peek();
         if (prc != kNumOk || (term != ',' && term != '}')) bad = true;
         if (rec_on) {
           rc.pool[extra_at + 2ull * i] = (unsigned long long)((uint32_t)role | (((rec >> 14) & 127u) << 3));
@@ -991,6 +1109,21 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
     if (lane < kPlanes) planes_row[lane] = ws.cnt[lane];
     return rec_on ? kRouteRecords : kRouteFast;
   }
+}
+
+// asks L2 for what pass 2 of document s will read: its text (the values are copied from it) and its records
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_records_doc(const uint8_t* __restrict__ text, int64_t from, int64_t to, int64_t s,
+                                                     const RecCtx& rc) {
+  const int lane = threadIdx.x & 31;
+  const uint8_t* a = text + (from & ~(int64_t)127);
+  for (const uint8_t* p = a + lane * 128; p < text + to; p += 32 * 128) prefetch_l2(p);
+  const DocRec dr = rc.doc_rec[s];
+  const unsigned long long* m = rc.pool + dr.members_at;
+  for (uint32_t i = lane * 16; i < dr.members; i += 32 * 16) prefetch_l2(m + i);
+  const unsigned long long* x = rc.pool + dr.extra_at;
+  const uint32_t nx = 2 * dr.numbers + dr.items;
+  for (uint32_t i = lane * 16; i < nx; i += 32 * 16) prefetch_l2(x + i);
 }
 
 // ---- pass 2 of a document with records: a scatter ----------------------------------------------------------------

@@ -64,7 +64,7 @@ uint64_t ingest_scratch_bytes(int64_t n_docs);
 cudaError_t launch_ingest_measure(const pie_json_docs& dev_docs, void* scratch, uint8_t* doc_status, int64_t* totals,
                                   int32_t* status, cudaStream_t stream);
 // debug knobs (tests, A/B timing): the warp-cooperative path on / off (on < 0 only queries; returns the previous
-// value; off unless PIE_INGEST_WARP_PATH=1 is in the environment); how many documents of the last measure on
+// value; on unless PIE_INGEST_WARP_PATH=0 is in the environment); how many documents of the last measure on
 // `scratch` the warp path declined (they took the thread-per-document walk)
 int ingest_set_warp_path(int on);
 cudaError_t ingest_read_declined(const void* scratch, int64_t n_docs, unsigned int* out, cudaStream_t stream);
