@@ -682,7 +682,7 @@ def main():
                     "ms_per_launch": payload_ms, "algorithmic_bytes": payload_bytes, "json_bytes_out": payload_total,
                     "achieved_gbs": gbs(payload_bytes, payload_ms), "frac": gbs(payload_bytes, payload_ms) / peak,
                     "entries_per_s": E / (payload_ms * 1e-3)},
-                "JSON ingest of stored documents (ingest_walk_kernel x2 + scans, not part of the step)":
+                "JSON ingest of stored documents (ingest_fast_kernel x2 + ingest_walk_kernel x2 + scans, not part of the step)":
                     dict(ingest, frac=ingest["achieved_gbs"] / peak, traffic=ingest_traffic) if ingest else None,
                 "schemaVersion 2 show payloads (payload_measure_kernel + scan + payload_write_kernel, not part of the step)":
                     dict(widened["show_payloads"], frac=widened["show_payloads"]["achieved_gbs"] / peak),
@@ -799,20 +799,35 @@ def ingest_leg(args, dev, n_shows, runs, note):
     assert bufs.status.cpu().tolist()[0] == 0
     table = ops.alloc_ingest_table(docs.n_docs, totals, dev)
     table_bytes = table.nbytes()
-    for _ in range(2):
-        ops.ingest_measure_dev(docs, bufs)
-        ops.ingest_fill_dev(docs, bufs, table)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    tm = tf = 0.0
-    for _ in range(runs):
-        ev[0].record()
-        ops.ingest_measure_dev(docs, bufs)
-        ev[1].record()
-        ops.ingest_fill_dev(docs, bufs, table)
-        ev[2].record()
-        torch.cuda.synchronize()
-        tm += ev[0].elapsed_time(ev[1]) / runs
-        tf += ev[1].elapsed_time(ev[2]) / runs
+
+    def timed(d, b, t, n_runs):
+        for _ in range(2):
+            ops.ingest_measure_dev(d, b)
+            ops.ingest_fill_dev(d, b, t)
+        m = f = 0.0
+        for _ in range(n_runs):
+            ev[0].record()
+            ops.ingest_measure_dev(d, b)
+            ev[1].record()
+            ops.ingest_fill_dev(d, b, t)
+            ev[2].record()
+            torch.cuda.synchronize()
+            m += ev[0].elapsed_time(ev[1]) / n_runs
+            f += ev[1].elapsed_time(ev[2]) / n_runs
+        return m, f
+
+    # the thread-per-document walk alone (the round-1 pipeline) beside the default (a warp per document, the walk
+    # for what it declines): same documents, same table
+    old_path = ops.set_ingest_warp_path(0)
+    wm, wf = timed(docs, bufs, table, runs)
+    ops.set_ingest_warp_path(1)
+    tm, tf = timed(docs, bufs, table, runs)
+    declined = ops.ingest_declined(bufs, docs.n_docs)
+    paths = {"warp_per_document": {"measure_ms": tm, "fill_ms": tf, "ms": tm + tf, "declined_to_the_walk": declined},
+             "thread_per_document_walk": {"measure_ms": wm, "fill_ms": wf, "ms": wm + wf},
+             "note": "the walk is at its best here: the copies of a document are neighbours in its length order, so a "
+                     "warp's 32 lanes walk identical documents; different_documents below is the other case"}
     note(f"JSON ingest on the device: {tm:.2f} + {tf:.2f} ms for {text_bytes / 1e9:.2f} GB of text")
     # parity of the timed ingest: the table the timed walks left in HBM against the C oracle's own parser
     # (oracle_ingest_measure + oracle_ingest_fill, recursive descent + strtod) on ALL the timed documents
@@ -830,6 +845,28 @@ def ingest_leg(args, dev, n_shows, runs, note):
                      "seconds": round(time.perf_counter() - t0, 2)}
     note(f"parity of the timed ingest: equal={ingest_parity['equal']} ({ingest_parity['seconds']} s)")
     del ref_table
+    # how much the documents decide: the same number of documents, 8x as many different ones
+    different = None
+    if n_shows >= 8 * sample:
+        sample2 = 8 * sample
+        docs2, n_entries2, text_bytes2, _ = synth_stored_docs(sample2, max(1, n_shows // sample2), dev, seed=8765)
+        bufs2 = ops.IngestBuffers(docs2.n_docs, dev)
+        ops.ingest_measure_dev(docs2, bufs2)
+        totals2 = bufs2.totals.cpu().tolist()
+        assert bufs2.status.cpu().tolist()[0] == 0
+        table2 = ops.alloc_ingest_table(docs2.n_docs, totals2, dev)
+        ops.set_ingest_warp_path(0)
+        wm2, wf2 = timed(docs2, bufs2, table2, max(2, runs // 2))
+        ops.set_ingest_warp_path(1)
+        tm2, tf2 = timed(docs2, bufs2, table2, max(2, runs // 2))
+        different = {"workload": f"{sample2} different documents x{max(1, n_shows // sample2)}", "documents": docs2.n_docs,
+                     "entries": n_entries2, "text_bytes": text_bytes2,
+                     "warp_per_document": {"measure_ms": tm2, "fill_ms": tf2, "ms": tm2 + tf2,
+                                           "declined_to_the_walk": ops.ingest_declined(bufs2, docs2.n_docs)},
+                     "thread_per_document_walk": {"measure_ms": wm2, "fill_ms": wf2, "ms": wm2 + wf2}}
+        note(f"JSON ingest, {sample2} different documents: warp path {tm2 + tf2:.2f} ms, walk {wm2 + wf2:.2f} ms")
+        del docs2, bufs2, table2
+    ops.set_ingest_warp_path(old_path)
     # host buffers through the C ABI
     lib = _lib.load()
     hdocs = hdocs_plain.pin()
@@ -905,6 +942,7 @@ def ingest_leg(args, dev, n_shows, runs, note):
     ms = tm + tf
     return {
         "ms_per_launch": ms, "measure_ms": tm, "fill_ms": tf, "documents": hdocs.n_docs, "entries": n_entries,
+        "paths": paths, "different_documents": different,
         "text_bytes": text_bytes, "table_bytes": table_bytes, "algorithmic_bytes": alg,
         "two_pass_bytes": 2 * text_bytes + table_bytes + 2 * 4 * 26 * hdocs.n_docs, "parity_checked": ingest_parity,
         "achieved_gbs": alg / (ms * 1e-3) / 1e9, "text_gbs": text_bytes / (ms * 1e-3) / 1e9,

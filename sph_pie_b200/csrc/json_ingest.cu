@@ -516,6 +516,11 @@ cudaError_t fast_kernel_ready(int* blocks_per_sm) {
   return cudaSuccess;
 }
 unsigned fast_blocks(int64_t n_docs, int per_sm) {
+  static const int cap_env = [] {  // experiment knob: fewer resident CTAs per SM (PIE_INGEST_FAST_CTAS)
+    const char* e = std::getenv("PIE_INGEST_FAST_CTAS");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (cap_env > 0 && cap_env < per_sm) per_sm = cap_env;
   const int64_t want = (n_docs + jf::kFastWarps - 1) / jf::kFastWarps;
   const int64_t cap = (int64_t)sm_count_or_default() * per_sm;
   return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
