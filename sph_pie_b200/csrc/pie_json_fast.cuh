@@ -72,7 +72,9 @@ constexpr int kFastMaxEntries = 127;
 constexpr int kFastMaxNumbers = 128;
 constexpr int kFastMaxEsc = 32;
 constexpr int kFastMaxArrays = 64;
-constexpr int kInlineCopy = 16;  // longer values are copied by the whole warp
+constexpr int kInlineCopy = 16;  // pass 2 without records: longer values are copied by the whole warp
+constexpr int kLaneCopy = 16;    // pass 2 with records: the same (lanes copying their own values up to 96 bytes, 8 bytes a turn,
+                                 // was measured: 10.2 ms instead of 8.3 — the longest value of a turn decides)
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kAllEntryKeys = 0x1ffffu;  // the 17 keys of an entry
 constexpr uint32_t kPosMask = 0x3fffu;
@@ -1166,11 +1168,7 @@ __device__ __forceinline__ void fill_records(WarpShared& ws, const TablePointers
         unescape_copy(ab, src, (int)len, tp.data[heap] + dst, limit);
       } else {
         plain = true;
-        if (len <= (uint32_t)kInlineCopy) {
-          uint8_t* dp = tp.data[heap] + dst;
-          if (len) store_upto8(dp, load8(ab + src, limit), (int)len);
-          if (len > 8) store_upto8(dp + 8, load8(ab + src + 8, limit), (int)len - 8);
-        }
+        if (len <= (uint32_t)kLaneCopy) copy_plain(ab + src, (int)len, tp.data[heap] + dst, limit);
       }
     } else if (kind == kRecArray) {
       if (heap == (uint32_t)kHeapActions) out.actions_list[row] = (int32_t)(ws.cnt[kPlaneActionItems] + lo);
@@ -1188,7 +1186,7 @@ __device__ __forceinline__ void fill_records(WarpShared& ws, const TablePointers
         out.time_val[tf][s] = np_bits_to_double(0x7ff8000000000000ull | ((uint64_t)((ab + lo) - out.text) & 0x7ffffffffffffull));
     }
     // long plain values: the whole warp copies each
-    uint32_t longm = __ballot_sync(kFull, plain && len > (uint32_t)kInlineCopy);
+    uint32_t longm = __ballot_sync(kFull, plain && len > (uint32_t)kLaneCopy);
     while (longm) {
       const int j = __ffs(longm) - 1;
       longm &= longm - 1;

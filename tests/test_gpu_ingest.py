@@ -77,6 +77,27 @@ def test_warp_path_takes_the_providers_documents_and_declines_the_rest(cuda):
         ops.set_ingest_warp_path(old)
 
 
+def test_record_pool_under_pressure(cuda):
+    """Pass 1 leaves records for pass 2 in a pool sized for average documents (288 x 8 bytes each): a batch of nothing
+    but the largest documents overflows it, the documents that find it full are parsed again by pass 2 — same table."""
+    old = ops.set_ingest_warp_path(1)
+    try:
+        rng = random.Random(6)
+        shows = [s for s in canonical_shows(600, 17) if len(s["entries"]) >= 18]
+        assert len(shows) > 40
+        for sh in shows:
+            sh["crew"] = ["Ann", "Bob", "Cy"]
+            for e in sh["entries"]:
+                e["actions"] = ["Swap battery", "Reboot", 'Call "lead"']
+        docs = [stored_doc(s, rng, "stringify") for s in shows]
+        docs = [d for d in docs if len(d.encode()) <= 8000]
+        assert declined_of(cuda, docs) == 0
+        gpu_check(cuda, docs, "pool under pressure", host_too=False)
+        gpu_check(cuda, docs[:1], "one document (the last document is always parsed twice)", host_too=False)
+    finally:
+        ops.set_ingest_warp_path(old)
+
+
 def test_damaged_canonical_documents(cuda, both_paths):
     """Every prefix and thousands of single-byte damages of documents of the provider's shape: whatever the warp path
     accepts must be what the oracle makes of it; the rest goes to the walk.  Strings with escapes, non-ASCII text,
