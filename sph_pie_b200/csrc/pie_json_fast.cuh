@@ -41,6 +41,13 @@
 #ifndef PIE_JF_FASTNUM
 #define PIE_JF_FASTNUM 0
 #endif
+// 1: pass 1 converts only numbers of the everyday form (-?digits(.digits)?, at most 15 digits, within 16 bytes) and declines
+// a document with any other number to the walk — no Eisel-Lemire, no cursor in the kernel, 56 registers instead of 72.
+// Measured and NOT shipped: a quarter of the bench's documents hold a 17-digit delaySec (54.976914585768995), which
+// needs the general parser, and the walk's tail on them costs more than the smaller kernel saves (26.8 + 21.0 ms).
+#ifndef PIE_JF_NUMBERS_EVERYDAY_ONLY
+#define PIE_JF_NUMBERS_EVERYDAY_ONLY 0
+#endif
 #define PIE_JF_INL(bit) ((PIE_JF_NOINLINE_MASK >> (bit)) & 1)
 #if PIE_JF_INL(0)
 #define PIE_JF_ESC_FN __device__ __noinline__
@@ -384,9 +391,12 @@ __device__ __forceinline__ uint64_t digit_flags(uint64_t x) {
 // Numbers of the everyday form -?digits(.digits)? with at most 15 digits that end within 16 bytes are read 8 bytes at
 // a time and converted by ONE exact IEEE operation, as parse_json_number_from does for them (Clinger's case: the
 // digits as an integer below 2^53, over an exact power of ten); everything else goes through that parser.
+// kGeneric = false (pass 1, PIE_JF_NUMBERS_EVERYDAY_ONLY): a number that is not of the everyday form is kNumUndecided —
+// the document is declined and the walk's parser decides it; pass 1 then carries no general number parser at all.
+template <bool kGeneric>
 PIE_JF_NUM_FN int parse_number_at(const uint8_t* ab, int pos, int span, const uint8_t* limit, const Pow5Table& pow5,
                                             double* value, int* term) {
-  if (PIE_JF_FASTNUM) {
+  if (PIE_JF_FASTNUM || !kGeneric) {
     uint64_t lo = load8(ab + pos, limit), hi = load8(ab + pos + 8, limit);
     const int avail = span - pos;  // >= 1
     const bool neg = (lo & 0xff) == '-';
@@ -450,6 +460,10 @@ PIE_JF_NUM_FN int parse_number_at(const uint8_t* ab, int pos, int span, const ui
         return kNumOk;
       }
     }
+  }
+  if (!kGeneric) {
+    *term = -1;
+    return kNumUndecided;
   }
   DocCursor src;
   src.open(ab, pos, span);
@@ -1044,7 +1058,7 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
       const uint32_t row = row0 + ((rec >> 14) & 127u);
       double v = 0.0;
       int term = -1;
-      const int prc = parse_number_at(ab, pos, dc.span, ab + dc.nwords * 32, pow5, &v, &term);
+      const int prc = parse_number_at<kFill || !PIE_JF_NUMBERS_EVERYDAY_ONLY>(ab, pos, dc.span, ab + dc.nwords * 32, pow5, &v, &term);
       if (!kFill) {
         if (prc != kNumOk || (term != ',' && term != '}')) bad = true;
         if (rec_on) {
