@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(jf::kFastThreads) ingest_fast_kernel(const int
     if (kFill) {
       const uint8_t route = sc.route[s];
       if (route == jf::kRouteRecords)
-        jf::fill_records(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, sc.planes + s * kPlanes, out, sc.rec);
+        jf::fill_records(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, sc.planes + s * kPlanes, out, sc.rec, pow5);
       else if (route == jf::kRouteFast)
         jf::fast_doc<true>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out, pow5, sc.rec);
     } else {

@@ -70,15 +70,15 @@ namespace jf {
 
 using namespace jw;
 
-constexpr int kFastWarps = 7;  // x 4 CTAs per SM: what the shared memory of a warp's lists allows
+constexpr int kFastWarps = 7;  // x 5 CTAs per SM: what the shared memory of a warp's lists (6.2 KB) and 56 registers allow
 constexpr int kFastThreads = kFastWarps * 32;
 constexpr int kFastMaxBytes = 16384;   // alignment skip + document length a warp takes (positions are 14 bits)
-constexpr int kFastMaxQuotes = 1536;   // twice the strings: ~0.18 per byte in the provider's documents, so ~8.5 KB of them
-constexpr int kFastMaxMembers = 512;
+constexpr int kFastMaxQuotes = 1472;   // twice the strings: ~0.18 per byte in the provider's documents, so ~8.5 KB of them
+constexpr int kFastMaxMembers = 480;
 constexpr int kFastMaxEntries = 127;
-constexpr int kFastMaxNumbers = 128;
+constexpr int kFastMaxNumbers = 64;
 constexpr int kFastMaxEsc = 32;
-constexpr int kFastMaxArrays = 64;
+constexpr int kFastMaxArrays = 32;
 constexpr int kInlineCopy = 16;  // pass 2 without records: longer values are copied by the whole warp
 constexpr int kLaneCopy = 16;    // pass 2 with records: the same (lanes copying their own values up to 96 bytes, 8 bytes a turn,
                                  // was measured: 10.2 ms instead of 8.3 — the longest value of a turn decides)
@@ -113,7 +113,7 @@ struct alignas(16) WarpShared {
 // pass 2 as before).  Pass 2 of such a document is a scatter: no index, no keys, no grammar.
 //   member  lo = first byte | raw length << 14 | has escapes << 28        hi = heap | entry << 5 | offset in the document's
 //           part of the heap << 12 | kind << 29
-//   number  lo = role | entry << 3, hi = 0; then the binary64
+//   number  lo = role | entry << 3 | position << 10 (pass 2 converts it from the text)
 //   element lo as a member's; hi = heap | offset << 5 | index in the document's part of the list << 19
 enum RecKind : uint32_t { kRecNone = 0, kRecText, kRecArray, kRecNullDelay, kRecNanTs, kRecTimeKind, kRecTimeString };
 constexpr int kPoolUnitsPerDoc = 288;
@@ -470,6 +470,37 @@ PIE_JF_NUM_FN int parse_number_at(const uint8_t* ab, int pos, int span, const ui
   const int rc = parse_json_number_from<true>(src, pow5, value);
   *term = src.peek();
   return rc;
+}
+
+// Pass 1 does not convert numbers, it only makes sure that pass 2 can: ECMA-404's grammar without an exponent part and
+// at most 19 digits in all.  Such a number is always decided by parse_json_number_from (no digit is dropped, and the
+// Eisel-Lemire product can only be undecided for powers of ten outside 10^-27 .. 10^55): pass 2 converts it from the
+// text, and pass 1 carries no number parser.  Anything else (1e21, 25 digits) declines the document to the walk.
+__device__ __forceinline__ bool number_shape(const uint8_t* ab, int pos, int span, int* term) {
+  int i = pos, digits = 0;
+  int c = i < span ? (int)ab[i] : -1;
+  if (c == '-') c = ++i < span ? (int)ab[i] : -1;
+  if (c < '0' || c > '9') return false;
+  if (c == '0') {
+    c = ++i < span ? (int)ab[i] : -1;
+    if (c >= '0' && c <= '9') return false;  // no leading zeros
+    digits = 1;
+  } else {
+    while (c >= '0' && c <= '9') {
+      ++digits;
+      c = ++i < span ? (int)ab[i] : -1;
+    }
+  }
+  if (c == '.') {
+    c = ++i < span ? (int)ab[i] : -1;
+    if (c < '0' || c > '9') return false;
+    while (c >= '0' && c <= '9') {
+      ++digits;
+      c = ++i < span ? (int)ab[i] : -1;
+    }
+  }
+  *term = c;
+  return digits <= 19 && c != 'e' && c != 'E';
 }
 
 // ---- stage 1 ------------------------------------------------------------------------------------------------------
@@ -1045,7 +1076,7 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
   unsigned long long extra_at = 0;
   if (!kFill && rec_on) {
     if (ws.n_arr > (uint32_t)kFastMaxArrays) rec_on = false;
-    const unsigned long long units = 2ull * ws.n_num + ws.n_items;
+    const unsigned long long units = (unsigned long long)ws.n_num + ws.n_items;
     if (lane == 0) extra_at = atomicAdd(rc.cursor, units);
     extra_at = __shfl_sync(kFull, extra_at, 0);
     if (extra_at + units > rc.capacity) rec_on = false;
@@ -1058,14 +1089,14 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
       const uint32_t row = row0 + ((rec >> 14) & 127u);
       double v = 0.0;
       int term = -1;
-      const int prc = parse_number_at<kFill || !PIE_JF_NUMBERS_EVERYDAY_ONLY>(ab, pos, dc.span, ab + dc.nwords * 32, pow5, &v, &term);
       if (!kFill) {
-        if (prc != kNumOk || (term != ',' && term != '}')) bad = true;
-        if (rec_on) {
-          rc.pool[extra_at + 2ull * i] = (unsigned long long)((uint32_t)role | (((rec >> 14) & 127u) << 3));
-          rc.pool[extra_at + 2ull * i + 1] = (unsigned long long)__double_as_longlong(v);
-        }
-      } else if (role == 3) {
+        // the shape only; the record says where the number is and what it is for
+        if (!number_shape(ab, pos, dc.span, &term) || (term != ',' && term != '}')) bad = true;
+        if (rec_on) rc.pool[extra_at + i] = (unsigned long long)((uint32_t)role | (((rec >> 14) & 127u) << 3) | ((uint32_t)pos << 10));
+        continue;
+      }
+      parse_number_at<true>(ab, pos, dc.span, ab + dc.nwords * 32, pow5, &v, &term);
+      if (role == 3) {
         out.entry_ts[row] = jw_is_finite(v) ? v : jw_nan();
       } else if (role == 4) {
         out.delay_sec[row] = v;
@@ -1105,7 +1136,7 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
         const uint32_t a0 = ws.arr[i][0], a1 = ws.arr[i][1];
         uint32_t nn, bb;
         walk_items<2>(ws, dc, (int)(a0 & kPosMask), (int)((a0 >> 14) & 0x7ff), tot.quotes, &nn, &bb, nullptr, nullptr, a1 >> 14,
-                      a1 & 0x3fffu, rc.pool + extra_at + 2ull * ws.n_num + ws.arr[i][2],
+                      a1 & 0x3fffu, rc.pool + extra_at + ws.n_num + ws.arr[i][2],
                       (a0 >> 25) ? (uint32_t)kHeapActions : (uint32_t)kHeapCrew);
       }
     }
@@ -1138,14 +1169,14 @@ __device__ __forceinline__ void prefetch_records_doc(const uint8_t* __restrict__
   const unsigned long long* m = rc.pool + dr.members_at;
   for (uint32_t i = lane * 16; i < dr.members; i += 32 * 16) prefetch_l2(m + i);
   const unsigned long long* x = rc.pool + dr.extra_at;
-  const uint32_t nx = 2 * dr.numbers + dr.items;
+  const uint32_t nx = dr.numbers + dr.items;
   for (uint32_t i = lane * 16; i < nx; i += 32 * 16) prefetch_l2(x + i);
 }
 
 // ---- pass 2 of a document with records: a scatter ----------------------------------------------------------------
 __device__ __forceinline__ void fill_records(WarpShared& ws, const TablePointers& tp, const uint8_t* __restrict__ text, int64_t from,
                                              int64_t to, int64_t s, const uint32_t* __restrict__ planes_row, const IngestOut& out,
-                                             const RecCtx& rc) {
+                                             const RecCtx& rc, const Pow5Table& pow5) {
   const int lane = threadIdx.x & 31;
   const uintptr_t a0 = reinterpret_cast<uintptr_t>(text + from);
   const int skip = (int)(a0 & 31);
@@ -1212,8 +1243,14 @@ __device__ __forceinline__ void fill_records(WarpShared& ws, const TablePointers
   }
   const unsigned long long* extra = rc.pool + dr.extra_at;
   for (uint32_t i = lane; i < dr.numbers; i += 32) {
-    const uint32_t tag = (uint32_t)extra[2ull * i];
-    const double v = __longlong_as_double((long long)extra[2ull * i + 1]);
+    // a number: converted here, from the text, by the parser the walk uses (pass 1 made sure it decides it)
+    const uint32_t tag = (uint32_t)extra[i];
+    double v = 0.0;
+    if (tag & 7u) {  // a number under a key the table does not hold needs no value
+      DocCursor src;
+      src.open(ab, (int)((tag >> 10) & kPosMask), skip + (int)(to - from));
+      parse_json_number_from<true>(src, pow5, &v);
+    }
     const int role = (int)(tag & 7u);
     const uint32_t row = row0 + ((tag >> 3) & 127u);
     const bool fin = jw_is_finite(v);
@@ -1228,7 +1265,7 @@ __device__ __forceinline__ void fill_records(WarpShared& ws, const TablePointers
       if (out.time_kind) out.time_kind[s * PIE_TF_COUNT + tf] = (uint8_t)(fin ? PIE_TK_NUMBER : PIE_TK_NONFINITE);
     }
   }
-  const unsigned long long* items = extra + 2ull * dr.numbers;
+  const unsigned long long* items = extra + dr.numbers;
   for (uint32_t i = lane; i < dr.items; i += 32) {
     const unsigned long long r = items[i];
     const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
