@@ -3,7 +3,8 @@
 --log-file gpurun_out/launches.csv ...`): per-kernel per-launch averages over the launches on the bench workload, and
 the same summed over the kernel GROUPS bench.py times as one unit (roofline.traffic must cover what roofline.kernel
 names).  Records the hash of the sources the captured library was built from.
-usage: python scripts/traffic_from_launches.py gpurun_out/launches.csv profiles/traffic_r02.json <shows>"""
+usage: python scripts/traffic_from_launches.py gpurun_out/launches.csv profiles/traffic_r02.json <shows> [trimmed.csv]
+(trimmed.csv: the list reduced to this library's kernels, at most 120 launches of each — the copy kept under profiles/)"""
 import collections
 import csv
 import json
@@ -28,7 +29,8 @@ GROUPS = {
 
 
 def kernel_name(full: str) -> str:
-    full = full.replace("pie::", "").replace("void ", "").replace("(anonymous namespace)::", "").replace("unnamed>::", "")
+    full = (full.replace("pie::", "").replace("void ", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+            .replace("unnamed>::", "").replace("(bool)", ""))
     targ = full.split("(")[0]
     name = targ.split("<")[0]
     first = targ.split("<", 1)[1] if "<" in targ else ""
@@ -40,8 +42,27 @@ def kernel_name(full: str) -> str:
     return name
 
 
+def trim(src: str, dst: str) -> None:
+    rows = list(csv.reader(open(src)))
+    hdr = next(r for r in rows if len(r) > 10)
+    ki, mi = hdr.index("Kernel Name"), hdr.index("Metric Name")
+    seen, out = collections.Counter(), []
+    for r in rows:
+        if len(r) > 10 and r is not hdr:
+            if "pie::" not in r[ki]:
+                continue
+            key = (r[ki].split("(")[0], r[mi])
+            seen[key] += 1
+            if seen[key] > 120:
+                continue
+        out.append(r)
+    csv.writer(open(dst, "w", newline=""), quoting=csv.QUOTE_ALL).writerows(out)
+
+
 def main():
     src, dst, shows = sys.argv[1], sys.argv[2], int(sys.argv[3])
+    if len(sys.argv) > 4:
+        trim(src, sys.argv[4])
     rows = [r for r in csv.reader(open(src)) if len(r) > 10]
     col = {h: i for i, h in enumerate(rows[0])}
     agg = collections.defaultdict(lambda: collections.defaultdict(list))

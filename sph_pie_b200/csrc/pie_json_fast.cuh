@@ -393,10 +393,11 @@ __device__ __forceinline__ uint64_t digit_flags(uint64_t x) {
 // digits as an integer below 2^53, over an exact power of ten); everything else goes through that parser.
 // kGeneric = false (pass 1, PIE_JF_NUMBERS_EVERYDAY_ONLY): a number that is not of the everyday form is kNumUndecided —
 // the document is declined and the walk's parser decides it; pass 1 then carries no general number parser at all.
-template <bool kGeneric>
+template <bool kGeneric, bool kFastFirst = false>
 PIE_JF_NUM_FN int parse_number_at(const uint8_t* ab, int pos, int span, const uint8_t* limit, const Pow5Table& pow5,
                                             double* value, int* term) {
-  if (PIE_JF_FASTNUM || !kGeneric) {
+  // kFastFirst: pass 2 with records, which has the room for it (pass 1 does not: profiles/ncu_r02_ingest_summary.md)
+  if (PIE_JF_FASTNUM || !kGeneric || kFastFirst) {
     uint64_t lo = load8(ab + pos, limit), hi = load8(ab + pos + 8, limit);
     const int avail = span - pos;  // >= 1
     const bool neg = (lo & 0xff) == '-';
@@ -1158,21 +1159,6 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
   }
 }
 
-// asks L2 for what pass 2 of document s will read: its text (the values are copied from it) and its records
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_records_doc(const uint8_t* __restrict__ text, int64_t from, int64_t to, int64_t s,
-                                                     const RecCtx& rc) {
-  const int lane = threadIdx.x & 31;
-  const uint8_t* a = text + (from & ~(int64_t)127);
-  for (const uint8_t* p = a + lane * 128; p < text + to; p += 32 * 128) prefetch_l2(p);
-  const DocRec dr = rc.doc_rec[s];
-  const unsigned long long* m = rc.pool + dr.members_at;
-  for (uint32_t i = lane * 16; i < dr.members; i += 32 * 16) prefetch_l2(m + i);
-  const unsigned long long* x = rc.pool + dr.extra_at;
-  const uint32_t nx = dr.numbers + dr.items;
-  for (uint32_t i = lane * 16; i < nx; i += 32 * 16) prefetch_l2(x + i);
-}
-
 // ---- pass 2 of a document with records: a scatter ----------------------------------------------------------------
 __device__ __forceinline__ void fill_records(WarpShared& ws, const TablePointers& tp, const uint8_t* __restrict__ text, int64_t from,
                                              int64_t to, int64_t s, const uint32_t* __restrict__ planes_row, const IngestOut& out,
@@ -1247,9 +1233,8 @@ __device__ __forceinline__ void fill_records(WarpShared& ws, const TablePointers
     const uint32_t tag = (uint32_t)extra[i];
     double v = 0.0;
     if (tag & 7u) {  // a number under a key the table does not hold needs no value
-      DocCursor src;
-      src.open(ab, (int)((tag >> 10) & kPosMask), skip + (int)(to - from));
-      parse_json_number_from<true>(src, pow5, &v);
+      int term;
+      parse_number_at<true, true>(ab, (int)((tag >> 10) & kPosMask), skip + (int)(to - from), limit, pow5, &v, &term);
     }
     const int role = (int)(tag & 7u);
     const uint32_t row = row0 + ((tag >> 3) & 127u);
