@@ -357,7 +357,9 @@ int pie_debug_ingest_declined(const void* scratch, int64_t n_docs, uint32_t* dec
  * Two device calls, because the caller owns the memory of the table:
  *   1. pie_ingest_measure_dev: walks every document once; totals_dev[PIE_INGEST_TOTALS] receive the bytes of the 23
  *      string heaps, n_entries and the item counts of crew / actions; status_dev[2] = {pie_status, document};
- *      `scratch` (pie_ingest_scratch_bytes(n_docs)) keeps where each document's part of every column starts.
+ *      `scratch` (pie_ingest_scratch_bytes(n_docs), ~2.5 KB per document) keeps where each document's part of every
+ *      column starts and what the first pass learnt of each document (records: where every value is and where it
+ *      goes), so that the second pass does not parse again.
  *   2. the caller reads totals/status, allocates the table (offsets: rows + 1 elements) and calls
  *      pie_ingest_fill_dev with the same docs / scratch / doc_status: the second walk writes everything.
  *      Not to be called when status[0] != 0. */
@@ -411,8 +413,9 @@ typedef struct pie_archive_table {
 uint64_t pie_ingest_scratch_bytes(int64_t n_docs);
 int pie_ingest_measure_dev(const pie_json_docs* dev_docs, void* scratch, uint8_t* doc_status, int64_t* totals_dev,
                            int32_t* status_dev, void* stream);
-/* fill_scratch: device memory of pie_ingest_fill_scratch_bytes(n_entries) bytes, 32-byte aligned (the second walk
- * writes one 96-byte row per entry there; a coalesced pass turns the rows into the entry columns).
+/* fill_scratch: device memory of pie_ingest_fill_scratch_bytes(n_entries) bytes, 32-byte aligned (used when the
+ * thread-per-document walk takes every document — pie_debug_ingest_warp_path(0): it writes one 96-byte row per entry
+ * there and a coalesced pass turns the rows into the entry columns; untouched otherwise).
  * dev_table->n_shows must be n_docs and dev_table->n_entries the measured total. */
 uint64_t pie_ingest_fill_scratch_bytes(int64_t n_entries);
 int pie_ingest_fill_dev(const pie_json_docs* dev_docs, const void* scratch, const uint8_t* doc_status,

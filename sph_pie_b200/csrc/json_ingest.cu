@@ -59,7 +59,10 @@ struct IngestScratch {
   // the warp-cooperative path (pie_json_fast.cuh)
   unsigned long long* next_fast;   // [2] the next document a warp takes in pass 1 / pass 2
   uint32_t* n_slow;                // documents on the list of the thread-per-document walk
-  uint8_t* route;                  // [n_docs] jf::kRouteFast / kRouteRecords: pass 1 accepted the document on the warp path
+  int32_t* order_big;              // [n_docs] what the roomy configuration of the warp path declined as well: the walk's list
+  uint32_t* n_slow_big;
+  unsigned long long* next_big;    // [2] the next place of `order` the roomy configuration takes in pass 1 / pass 2
+  uint8_t* route;                  // [n_docs] jf::kRouteFast / kRouteRecords / kRouteFastBig: pass 1 accepted the document on the warp path
   jf::RecCtx rec;                  // the records pass 1 leaves for pass 2 (pie_json_fast.cuh)
 };
 
@@ -133,19 +136,24 @@ __global__ void ingest_init_kernel(IngestScratch sc) {
   sc.next_fast[0] = 0;
   sc.next_fast[1] = 0;
   *sc.n_slow = 0;
+  *sc.n_slow_big = 0;
+  sc.next_big[0] = 0;
+  sc.next_big[1] = 0;
   *sc.rec.cursor = 0;
 }
 
 // The warp-cooperative path: every warp takes documents in table order (neighbours in time write neighbouring parts
-// of every heap) until none is left.  Pass 1 hands what it declines to the list of the thread-per-document walk.
-template <bool kFill>
-__global__ void __launch_bounds__(jf::kFastThreads) ingest_fast_kernel(const int64_t* __restrict__ doc_offsets,
-                                                                       const uint8_t* __restrict__ text, int64_t n_docs,
-                                                                       IngestScratch sc, uint8_t* __restrict__ doc_status,
-                                                                       IngestOut out) {
+// of every heap) until none is left.  Pass 1 hands what it declines to a list: that of the roomy configuration
+// (kFromList = false -> sc.order), which hands what it declines as well to the thread-per-document walk (sc.order_big).
+template <bool kFill, class Caps, bool kFromList>
+__global__ void __launch_bounds__(Caps::kWarps * 32) ingest_fast_kernel(const int64_t* __restrict__ doc_offsets,
+                                                                        const uint8_t* __restrict__ text, int64_t n_docs,
+                                                                        IngestScratch sc, uint8_t* __restrict__ doc_status,
+                                                                        IngestOut out) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
   jf::TablePointers& tp = *reinterpret_cast<jf::TablePointers*>(fast_smem);
-  jf::WarpShared& ws = reinterpret_cast<jf::WarpShared*>(fast_smem + ((sizeof(jf::TablePointers) + 15) & ~(size_t)15))[threadIdx.x >> 5];
+  jf::WarpShared<Caps>& ws =
+      reinterpret_cast<jf::WarpShared<Caps>*>(fast_smem + ((sizeof(jf::TablePointers) + 15) & ~(size_t)15))[threadIdx.x >> 5];
   if (kFill) {
     for (int h = threadIdx.x; h < kHeaps; h += blockDim.x) {
       tp.data[h] = out.data[h];
@@ -157,25 +165,34 @@ __global__ void __launch_bounds__(jf::kFastThreads) ingest_fast_kernel(const int
   __syncthreads();
   const Pow5Table pow5{g_pow5_dev};
   const int lane = threadIdx.x & 31;
+  const int64_t n_take = kFromList ? (int64_t)*sc.n_slow : n_docs;
+  unsigned long long* next = (kFromList ? sc.next_big : sc.next_fast) + (kFill ? 1 : 0);
   // (Pass 2 drawing a document ahead and asking L2 for its text and records was measured: the same 8.3 ms, and 4.2 GB
   // more DRAM reads per 2^20 documents — the prefetched lines are gone again before they are used.  Not shipped.)
   for (;;) {
     unsigned long long drawn = 0;
-    if (lane == 0) drawn = atomicAdd(sc.next_fast + (kFill ? 1 : 0), 1ull);
-    const int64_t s = (int64_t)__shfl_sync(0xffffffffu, drawn, 0);
-    if (s >= n_docs) break;
+    if (lane == 0) drawn = atomicAdd(next, 1ull);
+    drawn = __shfl_sync(0xffffffffu, drawn, 0);
+    if ((int64_t)drawn >= n_take) break;
+    const int64_t s = kFromList ? (int64_t)sc.order[drawn] : (int64_t)drawn;
     if (kFill) {
       const uint8_t route = sc.route[s];
-      if (route == jf::kRouteRecords)
+      if (kFromList) {  // the roomy configuration parses again what only it could take and the pool had no room for
+        if (route == jf::kRouteFastBig)
+          jf::fast_doc<true, Caps>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out, pow5, sc.rec);
+      } else if (route == jf::kRouteRecords) {
         jf::fill_records(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, sc.planes + s * kPlanes, out, sc.rec, pow5);
-      else if (route == jf::kRouteFast)
-        jf::fast_doc<true>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out, pow5, sc.rec);
+      } else if (route == jf::kRouteFast) {
+        jf::fast_doc<true, Caps>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out, pow5, sc.rec);
+      }
     } else {
-      const int route = jf::fast_doc<false>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out,
+      int route = jf::fast_doc<false, Caps>(ws, tp, text, doc_offsets[s], doc_offsets[s + 1], s, n_docs, sc.planes + s * kPlanes, out,
                                             pow5, sc.rec);
+      if (kFromList && route == jf::kRouteFast) route = jf::kRouteFastBig;
       if (lane == 0) {
         sc.route[s] = (uint8_t)route;
         if (route != jf::kRouteSlow) doc_status[s] = 0;
+        else if (kFromList) sc.order_big[atomicAdd(sc.n_slow_big, 1u)] = (int32_t)s;
         else sc.order[atomicAdd(sc.n_slow, 1u)] = (int32_t)s;
       }
     }
@@ -189,7 +206,8 @@ __global__ void __launch_bounds__(kIngestThreads, kFill ? 8 : 10) ingest_walk_ke
                                                                       IngestScratch sc, uint8_t* __restrict__ doc_status,
                                                                       IngestOut out, const uint32_t* __restrict__ list_len) {
   const Pow5Table pow5{g_pow5_dev};
-  const int32_t* __restrict__ order = sc.order;
+  // list_len: the walk takes the list of what both configurations of the warp path declined
+  const int32_t* __restrict__ order = list_len ? sc.order_big : sc.order;
   // list_len: `order` is the list of what the warp path declined (in no particular order), not all the documents
   const int64_t n_order = list_len ? (int64_t)*list_len : n_docs;
   uint32_t cnt[kPlanes];
@@ -463,7 +481,11 @@ IngestScratch carve(void* scratch, int64_t n_docs) {
   sc.next_fast = (unsigned long long*)p;
   sc.n_slow = (uint32_t*)(sc.next_fast + 2);
   sc.rec.cursor = sc.next_fast + 3;
-  p += 32;
+  sc.next_big = sc.next_fast + 4;
+  sc.n_slow_big = (uint32_t*)(sc.next_fast + 6);
+  p += 64;
+  sc.order_big = (int32_t*)p;
+  p += 4 * (uint64_t)stride;
   sc.route = p;
   p += (uint64_t)stride;  // a multiple of 32
   sc.rec.doc_rec = (jf::DocRec*)p;
@@ -485,31 +507,39 @@ bool warp_path_enabled() {
   }
   return v != 0;
 }
-constexpr size_t kFastSmemBytes = ((sizeof(jf::TablePointers) + 15) & ~(size_t)15) + sizeof(jf::WarpShared) * jf::kFastWarps;
+template <class Caps>
+constexpr size_t fast_smem_bytes() {
+  return ((sizeof(jf::TablePointers) + 15) & ~(size_t)15) + sizeof(jf::WarpShared<Caps>) * Caps::kWarps;
+}
 
-template <bool kFill>
-cudaError_t fast_kernel_ready(int* blocks_per_sm) {
+// one launch of a configuration of the warp path: as many CTAs as can be resident, fewer for small batches
+template <bool kFill, class Caps, bool kFromList>
+cudaError_t launch_fast(const pie_json_docs& docs, const IngestScratch& sc, uint8_t* doc_status, const IngestOut& out,
+                        cudaStream_t stream) {
   static int per_sm = -1;
+  constexpr size_t smem = fast_smem_bytes<Caps>();
   if (per_sm < 0) {
-    cudaError_t e = cudaFuncSetAttribute(ingest_fast_kernel<kFill>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(ingest_fast_kernel<kFill, Caps, kFromList>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ingest_fast_kernel<kFill>, jf::kFastThreads, kFastSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ingest_fast_kernel<kFill, Caps, kFromList>, Caps::kWarps * 32, smem);
     if (e != cudaSuccess) return e;
     per_sm = n > 0 ? n : 1;
   }
-  *blocks_per_sm = per_sm;
-  return cudaSuccess;
-}
-unsigned fast_blocks(int64_t n_docs, int per_sm) {
   static const int cap_env = [] {  // experiment knob: fewer resident CTAs per SM (PIE_INGEST_FAST_CTAS)
     const char* e = std::getenv("PIE_INGEST_FAST_CTAS");
     return e ? std::atoi(e) : 0;
   }();
-  if (cap_env > 0 && cap_env < per_sm) per_sm = cap_env;
-  const int64_t want = (n_docs + jf::kFastWarps - 1) / jf::kFastWarps;
-  const int64_t cap = (int64_t)sm_count_or_default() * per_sm;
-  return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+  const int ctas = cap_env > 0 && cap_env < per_sm ? cap_env : per_sm;
+  // the roomy configuration does not know how long its list is when it is launched: half a wave of it (it exits at
+  // once when the list is empty, which is the usual case)
+  const int64_t want = kFromList ? (int64_t)sm_count_or_default() * 2 : (docs.n_docs + Caps::kWarps - 1) / Caps::kWarps;
+  const int64_t cap = (int64_t)sm_count_or_default() * ctas;
+  const unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+  ingest_fast_kernel<kFill, Caps, kFromList><<<grid, Caps::kWarps * 32, smem, stream>>>(docs.offsets, docs.data, docs.n_docs, sc,
+                                                                                        doc_status, out);
+  ++g_launches;
+  return cudaGetLastError();
 }
 
 IngestOut make_out(const pie_archive_table& t) {
@@ -552,7 +582,7 @@ int ingest_set_warp_path(int on) {
 }
 cudaError_t ingest_read_declined(const void* scratch, int64_t n_docs, unsigned int* out, cudaStream_t stream) {
   IngestScratch sc = carve(const_cast<void*>(scratch), n_docs);
-  cudaError_t e = cudaMemcpyAsync(out, sc.n_slow, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
+  cudaError_t e = cudaMemcpyAsync(out, sc.n_slow_big, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);  // declined twice
   if (e != cudaSuccess) return e;
   return cudaStreamSynchronize(stream);
 }
@@ -560,7 +590,7 @@ cudaError_t ingest_read_declined(const void* scratch, int64_t n_docs, unsigned i
 uint64_t ingest_scratch_bytes(int64_t n_docs) {
   const int64_t stride = ((n_docs > 0 ? n_docs : 1) + 31) & ~(int64_t)31;
   return (uint64_t)kPlanes * stride * 4 + ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8 + 64 + 4 * (kOrderBuckets + 2) +
-         4 * (uint64_t)stride + 32 + (uint64_t)stride + (sizeof(jf::DocRec) + 8ull * jf::kPoolUnitsPerDoc) * (uint64_t)stride;
+         8 * (uint64_t)stride + 64 + (uint64_t)stride + (sizeof(jf::DocRec) + 8ull * jf::kPoolUnitsPerDoc) * (uint64_t)stride;
 }
 
 cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint8_t* doc_status, int64_t* totals,
@@ -576,15 +606,15 @@ cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint
   ++g_launches;
   if (n > 0) {
     if (warp_path_enabled()) {
-      // the warp path takes every document it can decide; what it declines goes on sc.order for the walk
-      int per_sm = 1;
-      e = fast_kernel_ready<false>(&per_sm);
+      // the warp path takes every document it can decide: first with the lists nearly every document fits, then — what
+      // that declined — with the roomy ones; what is declined twice goes on sc.order_big for the walk
+      e = launch_fast<false, jf::CapsSmall, false>(docs, sc, doc_status, IngestOut{}, stream);
       if (e != cudaSuccess) return e;
-      ingest_fast_kernel<false><<<fast_blocks(n, per_sm), jf::kFastThreads, kFastSmemBytes, stream>>>(docs.offsets, docs.data, n, sc,
-                                                                                                   doc_status, IngestOut{});
+      e = launch_fast<false, jf::CapsBig, true>(docs, sc, doc_status, IngestOut{}, stream);
+      if (e != cudaSuccess) return e;
       ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, doc_status,
-                                                                              IngestOut{}, sc.n_slow);
-      g_launches += 2;
+                                                                              IngestOut{}, sc.n_slow_big);
+      ++g_launches;
     } else {
       const unsigned doc_blocks = (unsigned)((n + 255) / 256);
       ingest_order_count_kernel<<<doc_blocks, 256, 0, stream>>>(docs.offsets, n, sc);
@@ -617,19 +647,19 @@ cudaError_t launch_ingest_fill(const pie_json_docs& docs, const void* scratch, c
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(sc.next_fast + 1, 0, 8, stream);
   if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(sc.next_big + 1, 0, 8, stream);
+  if (e != cudaSuccess) return e;
   IngestOut out = make_out(table);
   out.text = docs.data;
   if (n > 0 && warp_path_enabled()) {
     // both kernels write the table's columns directly (the walk's entry rows are for when it takes every document)
-    int per_sm = 1;
-    e = fast_kernel_ready<true>(&per_sm);
-    if (e != cudaSuccess) return e;
     out.rows = nullptr;
-    ingest_fast_kernel<true><<<fast_blocks(n, per_sm), jf::kFastThreads, kFastSmemBytes, stream>>>(docs.offsets, docs.data, n, sc,
-                                                                                                const_cast<uint8_t*>(doc_status), out);
+    e = launch_fast<true, jf::CapsSmall, false>(docs, sc, const_cast<uint8_t*>(doc_status), out, stream);
+    if (e != cudaSuccess) return e;
+    e = launch_fast<true, jf::CapsBig, true>(docs, sc, const_cast<uint8_t*>(doc_status), out, stream);
+    if (e != cudaSuccess) return e;
     ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc,
-                                                                           const_cast<uint8_t*>(doc_status), out, sc.n_slow);
-    ++g_launches;
+                                                                           const_cast<uint8_t*>(doc_status), out, sc.n_slow_big);
   } else if (n > 0) {
     out.rows = static_cast<EntryRow*>(fill_scratch);
     ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc,

@@ -22,7 +22,7 @@
 //     entry   := '{' the 17 known keys exactly once each, any order, other keys with scalar / string values '}'
 //                actions -> '[' strings ']', text keys -> string | null, delaySec -> number | null
 // recognised exactly (adjacency rules on the class masks + depth rules, see build_index / the member loop; every
-// string and every scalar is accounted for), at most 8 KB.  EVERYTHING ELSE IS DECLINED, never guessed: the document
+// string and every scalar is accounted for), at most 16 KB and 63 entries.  EVERYTHING ELSE IS DECLINED, never guessed: the document
 // goes on the list of the thread-per-document walk, which stays the complete ECMA-404 recogniser and the only place
 // that reports errors.  Declining is always safe; accepting is what the damage tests in tests/test_gpu_ingest.py hold
 // to the oracle byte by byte.
@@ -70,13 +70,25 @@ namespace jf {
 
 using namespace jw;
 
-constexpr int kFastWarps = 7;  // x 5 CTAs per SM: what the shared memory of a warp's lists (6.2 KB) and 56 registers allow
-constexpr int kFastThreads = kFastWarps * 32;
 constexpr int kFastMaxBytes = 16384;   // alignment skip + document length a warp takes (positions are 14 bits)
-constexpr int kFastMaxQuotes = 1472;   // twice the strings: ~0.18 per byte in the provider's documents, so ~8.5 KB of them
-constexpr int kFastMaxMembers = 480;
-constexpr int kFastMaxEntries = 127;
-constexpr int kFastMaxNumbers = 64;
+constexpr int kFastMaxEntries = 63;    // entry + 1 is 6 bits of a member's word
+// What a warp's lists hold.  Two configurations of the same kernels: the one nearly every document fits (6 KB of shared
+// memory a warp: 7 warps x 5 CTAs per SM), and a roomy one for the long documents the first one declines, so that a show
+// of 40 entries does not fall to the thread-per-document walk (which needs ~1 ms per KB of ONE document).
+struct CapsSmall {
+  static constexpr int kWarps = 7;
+  static constexpr int kQuotes = 1472;   // twice the strings: ~0.18 per byte in the provider's documents, so ~8.5 KB of them
+  static constexpr int kMembers = 480;
+  static constexpr int kNumbers = 64;
+  static constexpr int kArrays = 32;
+};
+struct CapsBig {
+  static constexpr int kWarps = 4;
+  static constexpr int kQuotes = 3584;   // a quote's index is 12 bits of a member's word
+  static constexpr int kMembers = 1152;
+  static constexpr int kNumbers = 128;
+  static constexpr int kArrays = 64;
+};
 constexpr int kFastMaxEsc = 32;
 constexpr int kFastMaxArrays = 32;
 constexpr int kInlineCopy = 16;  // pass 2 without records: longer values are copied by the whole warp
@@ -85,23 +97,24 @@ constexpr int kLaneCopy = 16;    // pass 2 with records: the same (lanes copying
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kAllEntryKeys = 0x1ffffu;  // the 17 keys of an entry
 constexpr uint32_t kPosMask = 0x3fffu;
-constexpr uint8_t kRouteSlow = 0, kRouteFast = 1, kRouteRecords = 2;
+constexpr uint8_t kRouteSlow = 0, kRouteFast = 1, kRouteRecords = 2, kRouteFastBig = 3;  // Big: pass 2 parses it again with CapsBig
 
 // Stage 1 leaves two lists, so that stage 2 never searches: the quotes that open or close a string in text order
 // (string i is the pair 2 i, 2 i + 1), and the members by their colons with what stage 2 would otherwise look up.
+template <class Caps>
 struct alignas(16) WarpShared {
-  uint16_t qpos[kFastMaxQuotes];   // position | (an escape starts between the quote before and this one) << 15
-  uint32_t mem[kFastMaxMembers];   // colon position | index in qpos of the key's closing quote << 14 | (entry + 1, 0 = the show) << 25
+  uint16_t qpos[Caps::kQuotes];    // position | (an escape starts between the quote before and this one) << 15
+  uint32_t mem[Caps::kMembers];    // colon position | index in qpos of the key's closing quote << 14 | (entry + 1, 0 = the show) << 26
   uint32_t cnt[kPlanes];           // measure: what the document adds to each plane; fill: the running position in it
   uint32_t seen[kFastMaxEntries + 1];
-  uint32_t num[kFastMaxNumbers];   // position | entry << 14 | role << 21
+  uint32_t num[Caps::kNumbers];    // position | entry << 14 | role << 21
   union {
     struct {                          // pass 2 without records: values with escapes, unescaped at the end of the document
       uint32_t esc_src[kFastMaxEsc];  // position of the first byte | raw length << 16
       uint32_t esc_dst[kFastMaxEsc];  // where it goes in its heap
       uint8_t esc_heap[kFastMaxEsc];
     };
-    uint32_t arr[kFastMaxArrays][3];  // pass 1 with records: the crew / actions arrays, their elements' records come last
+    uint32_t arr[Caps::kArrays][3];   // pass 1 with records: the crew / actions arrays, their elements' records come last
   };
   uint32_t n_num, n_esc, seen_show, n_arr, n_items, pad[3];
 };
@@ -528,8 +541,8 @@ struct IndexTotals {
 
 // Builds the two lists of the document in ws; false = declined.  kCheck (the measuring pass): every rule that makes
 // "accepted" mean "a document of the shape in the header" that does not need a key or a value.
-template <bool kCheck>
-__device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, IndexTotals* tot) {
+template <bool kCheck, class Caps>
+__device__ __forceinline__ bool build_index(WarpShared<Caps>& ws, const Doc& dc, IndexTotals* tot) {
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t c_esc = 0, c_instr = 0, c_tops = 0, c_bsq = 0;
@@ -646,7 +659,7 @@ __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, Index
       int idx = q0;
       for (uint32_t m = qr; m; m &= m - 1, ++idx) {
         const int bit = __ffs(m) - 1;
-        if (idx < kFastMaxQuotes) ws.qpos[idx] = (uint16_t)((uint32_t)(pos0 + bit) | (((flagged >> bit) & 1u) << 15));
+        if (idx < Caps::kQuotes) ws.qpos[idx] = (uint16_t)((uint32_t)(pos0 + bit) | (((flagged >> bit) & 1u) << 15));
       }
     }
     // the members: a colon, the index of the quote before it (the key's closing quote), the entry it is in
@@ -659,8 +672,8 @@ __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, Index
         const int e1 = d == 3 ? lb0 + __popc(lb & below) - 1 : 0;  // entry + 1 (the show's own brace is the first)
         const int kq = q0 + __popc(qr & below) - 1;
         if (!(d == 1 || d == 3) || kq < 1 || e1 > kFastMaxEntries) bad = true;  // a colon in an array, or no key before it
-        if (idx < kFastMaxMembers)
-          ws.mem[idx] = (uint32_t)(pos0 + bit) | ((uint32_t)(kq & 0x7ff) << 14) | ((uint32_t)(e1 & 0x7f) << 25);
+        if (idx < Caps::kMembers)
+          ws.mem[idx] = (uint32_t)(pos0 + bit) | ((uint32_t)(kq & 0xfff) << 14) | ((uint32_t)(e1 & 0x3f) << 26);
       }
     }
     if (kCheck) {
@@ -716,7 +729,7 @@ __device__ __forceinline__ bool build_index(WarpShared& ws, const Doc& dc, Index
   tot->members = c_co;
   tot->entries = c_lb - 1;
   tot->quotes = c_q;
-  if (c_co > kFastMaxMembers || c_lb - 1 > kFastMaxEntries || c_q > kFastMaxQuotes) bad = true;
+  if (c_co > Caps::kMembers || c_lb - 1 > kFastMaxEntries || c_q > Caps::kQuotes) bad = true;
   if (kCheck && (c_depth != 0 || c_instr != 0 || c_lb < 1)) bad = true;
   return !__any_sync(kFull, bad);
 }
@@ -740,8 +753,8 @@ __device__ __forceinline__ uint32_t group_prefix(int key, uint32_t val, uint32_t
 // The elements of a crew / actions array that opens at `at` ('['): strings only; qi = the index in qpos of the first
 // quote behind the bracket.  kMode 0: counts them and their unescaped bytes; 1: writes offsets and bytes from
 // (item0, dst0) on; 2: writes their records (heap; item0 / dst0 relative to the document).  false = not the shape.
-template <int kMode>
-PIE_JF_ITEMS_FN bool walk_items(const WarpShared& ws, const Doc& dc, int at, int qi, int n_quotes, uint32_t* n_items,
+template <int kMode, class Caps>
+PIE_JF_ITEMS_FN bool walk_items(const WarpShared<Caps>& ws, const Doc& dc, int at, int qi, int n_quotes, uint32_t* n_items,
                                            uint32_t* n_bytes, int32_t* off, uint8_t* data, uint32_t item0, uint32_t dst0,
                                            unsigned long long* recs = nullptr, uint32_t heap = 0) {
   uint32_t N = 0, B = 0;
@@ -789,8 +802,8 @@ PIE_JF_ITEMS_FN bool walk_items(const WarpShared& ws, const Doc& dc, int at, int
 // kFill = false: validates, counts (planes_row receives the document's 26 counts) and, when the pool has room, writes
 // the document's records; returns kRouteSlow (declined), kRouteFast (accepted; pass 2 parses it again) or kRouteRecords.
 // kFill = true: planes_row holds where the document's part of every plane starts; writes its part of the table.
-template <bool kFill>
-__device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp, const uint8_t* __restrict__ text, int64_t from,
+template <bool kFill, class Caps>
+__device__ __forceinline__ int fast_doc(WarpShared<Caps>& ws, const TablePointers& tp, const uint8_t* __restrict__ text, int64_t from,
                                         int64_t to, int64_t s, int64_t n_docs, uint32_t* __restrict__ planes_row,
                                         const IngestOut& out, const Pow5Table& pow5, const RecCtx& rc) {
   const int lane = threadIdx.x & 31;
@@ -812,7 +825,7 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
   if (lane == 0) { ws.n_num = 0; ws.n_esc = 0; ws.seen_show = 0; ws.n_arr = 0; ws.n_items = 0; }
   if (lane < kPlanes) ws.cnt[lane] = kFill ? planes_row[lane] : 0u;
   IndexTotals tot;
-  if (!build_index<!kFill>(ws, dc, &tot)) return kRouteSlow;
+  if (!build_index<!kFill, Caps>(ws, dc, &tot)) return kRouteSlow;
   if (!kFill)
     for (int e = lane; e < tot.entries; e += 32) ws.seen[e] = 0;
   // records: room for a record per member now, for the numbers and the elements when they are counted.  (The last
@@ -846,7 +859,7 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
     // ---- the member: every lane runs the same straight code; a lane without a member runs it on the last member and
     // leaves no trace
     const uint32_t rec = ws.mem[act ? k : tot.members - 1];
-    const int c = (int)(rec & kPosMask), kq = (int)((rec >> 14) & 0x7ff), e1 = (int)(rec >> 25);
+    const int c = (int)(rec & kPosMask), kq = (int)((rec >> 14) & 0xfff), e1 = (int)(rec >> 26);
     const bool in_entry = e1 != 0;
     const int e = in_entry ? e1 - 1 : 0;
     const uint32_t row = row0 + (uint32_t)e;
@@ -933,7 +946,7 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
     } else if (ch == '[') {
       if (arr_heap >= 0) {
         vkind = 3;
-        if (!walk_items<0>(ws, dc, v, kq + 1, tot.quotes, &N, &L, nullptr, nullptr, 0, 0)) mbad = true;
+        if (!walk_items<0, Caps>(ws, dc, v, kq + 1, tot.quotes, &N, &L, nullptr, nullptr, 0, 0)) mbad = true;
         strings += N;
       } else if (!is_entries) {
         mbad = true;  // an array under any other key
@@ -944,7 +957,7 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
       heap = -1;
       if (act) {
         const uint32_t slot = atomicAdd(&ws.n_num, 1u);
-        if (slot < (uint32_t)kFastMaxNumbers) ws.num[slot] = (uint32_t)v | ((uint32_t)e << 14) | ((uint32_t)numrole << 21);
+        if (slot < (uint32_t)Caps::kNumbers) ws.num[slot] = (uint32_t)v | ((uint32_t)e << 14) | ((uint32_t)numrole << 21);
         else mbad = true;
       }
     } else {
@@ -1023,8 +1036,8 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
         if (N) {  // its elements' records are written when all of the document's are counted
           const uint32_t slot = atomicAdd(&ws.n_arr, 1u);
           const uint32_t first = atomicAdd(&ws.n_items, N);
-          if (slot < (uint32_t)kFastMaxArrays) {
-            ws.arr[slot][0] = (uint32_t)v | ((uint32_t)(kq + 1) << 14) | ((uint32_t)(heap == kHeapActions) << 25);
+          if (slot < (uint32_t)Caps::kArrays) {
+            ws.arr[slot][0] = (uint32_t)v | ((uint32_t)(kq + 1) << 14) | ((uint32_t)(heap == kHeapActions) << 26);
             ws.arr[slot][1] = dst | (item0 << 14);
             ws.arr[slot][2] = first;
           }
@@ -1042,7 +1055,7 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
       if (vkind == 3) {
         if (heap == kHeapActions) out.actions_list[row] = (int32_t)item0;
         uint32_t nn, bb;
-        walk_items<1>(ws, dc, v, kq + 1, tot.quotes, &nn, &bb, tp.off[heap], tp.data[heap], item0, dst);
+        walk_items<1, Caps>(ws, dc, v, kq + 1, tot.quotes, &nn, &bb, tp.off[heap], tp.data[heap], item0, dst);
       } else if (vkind == 2) {
         const uint32_t slot = atomicAdd(&ws.n_esc, 1u);
         if (slot < (uint32_t)kFastMaxEsc) {
@@ -1076,14 +1089,14 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
   __syncwarp();
   unsigned long long extra_at = 0;
   if (!kFill && rec_on) {
-    if (ws.n_arr > (uint32_t)kFastMaxArrays) rec_on = false;
+    if (ws.n_arr > (uint32_t)Caps::kArrays) rec_on = false;
     const unsigned long long units = (unsigned long long)ws.n_num + ws.n_items;
     if (lane == 0) extra_at = atomicAdd(rc.cursor, units);
     extra_at = __shfl_sync(kFull, extra_at, 0);
     if (extra_at + units > rc.capacity) rec_on = false;
   }
   {
-    const uint32_t nn = ws.n_num < (uint32_t)kFastMaxNumbers ? ws.n_num : (uint32_t)kFastMaxNumbers;
+    const uint32_t nn = ws.n_num < (uint32_t)Caps::kNumbers ? ws.n_num : (uint32_t)Caps::kNumbers;
     for (uint32_t i = lane; i < nn; i += 32) {
       const uint32_t rec = ws.num[i];
       const int pos = (int)(rec & kPosMask), role = (int)(rec >> 21);
@@ -1136,9 +1149,9 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
       for (uint32_t i = lane; i < na; i += 32) {
         const uint32_t a0 = ws.arr[i][0], a1 = ws.arr[i][1];
         uint32_t nn, bb;
-        walk_items<2>(ws, dc, (int)(a0 & kPosMask), (int)((a0 >> 14) & 0x7ff), tot.quotes, &nn, &bb, nullptr, nullptr, a1 >> 14,
+        walk_items<2, Caps>(ws, dc, (int)(a0 & kPosMask), (int)((a0 >> 14) & 0xfff), tot.quotes, &nn, &bb, nullptr, nullptr, a1 >> 14,
                       a1 & 0x3fffu, rc.pool + extra_at + ws.n_num + ws.arr[i][2],
-                      (a0 >> 25) ? (uint32_t)kHeapActions : (uint32_t)kHeapCrew);
+                      (a0 >> 26) ? (uint32_t)kHeapActions : (uint32_t)kHeapCrew);
       }
     }
     // ---- measure: is it the shape, all of it?
@@ -1160,7 +1173,8 @@ __device__ __forceinline__ int fast_doc(WarpShared& ws, const TablePointers& tp,
 }
 
 // ---- pass 2 of a document with records: a scatter ----------------------------------------------------------------
-__device__ __forceinline__ void fill_records(WarpShared& ws, const TablePointers& tp, const uint8_t* __restrict__ text, int64_t from,
+template <class Caps>
+__device__ __forceinline__ void fill_records(WarpShared<Caps>& ws, const TablePointers& tp, const uint8_t* __restrict__ text, int64_t from,
                                              int64_t to, int64_t s, const uint32_t* __restrict__ planes_row, const IngestOut& out,
                                              const RecCtx& rc, const Pow5Table& pow5) {
   const int lane = threadIdx.x & 31;

@@ -43,9 +43,9 @@ def both_paths(request):
     ops.set_ingest_warp_path(old)
 
 
-def canonical_shows(n, seed):
+def canonical_shows(n, seed, max_entries=21):
     """Shows the way the provider normalises them (sqlProvider.js:361-409): every entry holds all of its 17 keys."""
-    host = synth_archive(n, seed=seed, missing_created_frac=0.1)
+    host = synth_archive(n, seed=seed, missing_created_frac=0.1, max_entries=max_entries)
     lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
     host.delay_valid[lost] = 0
     return table_to_shows(host)
@@ -73,6 +73,27 @@ def test_warp_path_takes_the_providers_documents_and_declines_the_rest(cuda):
         assert declined_of(cuda, ["", "{", "[]", "null", '{"id":1}', '{"entries":[{}]}', '{"entries":[{"id":"a"}]}']) == 7
         # shapes the warp path takes although they are not what the provider writes
         assert declined_of(cuda, ["{}", '{"id":"a"}', '{"id":null,"x":1,"y":"z","entries":[],"crew":[]}', '{"crew":["a","b"]}']) == 0
+    finally:
+        ops.set_ingest_warp_path(old)
+
+
+def test_long_documents_take_the_roomy_lists(cuda):
+    """Documents of 8.5 - 16 KB (shows of 25 - 45 entries) are declined by the lists nearly every document fits and taken
+    by the roomy configuration of the same kernels, not by the thread-per-document walk; longer ones (and shows of more
+    than 63 entries) are the walk's.  Same table whichever takes them."""
+    old = ops.set_ingest_warp_path(1)
+    try:
+        rng = random.Random(8)
+        shows = canonical_shows(160, 23, max_entries=80)
+        docs = [stored_doc(s, rng, "stringify") for s in shows]
+        sizes = [len(d.encode()) for d in docs]
+        mid = [d for d, n, sh in zip(docs, sizes, shows) if 9000 <= n <= 15500 and len(sh["entries"]) <= 63]
+        big = [d for d, n in zip(docs, sizes) if n > 17000]
+        assert len(mid) > 15 and len(big) > 15
+        assert declined_of(cuda, mid) == 0
+        assert declined_of(cuda, big) == len(big)
+        gpu_check(cuda, docs, "long documents", host_too=False)
+        gpu_check(cuda, mid[:3], "long documents only (the last one is parsed twice, by the roomy lists)", host_too=False)
     finally:
         ops.set_ingest_warp_path(old)
 
