@@ -31,6 +31,7 @@
 #include "pie_json_fast.cuh"
 
 #include <cstdlib>
+#include <mutex>
 
 namespace pie {
 
@@ -59,6 +60,9 @@ struct IngestScratch {
   // the warp-cooperative path (pie_json_fast.cuh)
   unsigned long long* next_fast;   // [2] the next document a warp takes in pass 1 / pass 2
   uint32_t* n_slow;                // documents on the list of the thread-per-document walk
+  int32_t* order_long;             // [n_docs] documents too long for the warp path: the walk takes them on a second stream
+  uint32_t* n_long;                //   WHILE the warp path takes the others (a long document is ~1 ms per KB on one lane)
+  unsigned long long* next_long;   // [2]
   int32_t* order_big;              // [n_docs] what the roomy configuration of the warp path declined as well: the walk's list
   uint32_t* n_slow_big;
   unsigned long long* next_big;    // [2] the next place of `order` the roomy configuration takes in pass 1 / pass 2
@@ -137,9 +141,22 @@ __global__ void ingest_init_kernel(IngestScratch sc) {
   sc.next_fast[1] = 0;
   *sc.n_slow = 0;
   *sc.n_slow_big = 0;
+  *sc.n_long = 0;
   sc.next_big[0] = 0;
   sc.next_big[1] = 0;
+  sc.next_long[0] = 0;
+  sc.next_long[1] = 0;
   *sc.rec.cursor = 0;
+}
+
+// Which documents are too long for the warp path is known from their lengths alone: they go on a list of their own,
+// which the walk takes on a second stream while the warp path works (every other route starts as "declined").
+__global__ void __launch_bounds__(256) ingest_route_kernel(const int64_t* __restrict__ doc_offsets, int64_t n_docs, IngestScratch sc) {
+  const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (s >= n_docs) return;
+  const bool is_long = doc_offsets[s + 1] - doc_offsets[s] + 31 > jf::kFastMaxBytes;  // whatever its alignment
+  sc.route[s] = is_long ? jf::kRouteLong : jf::kRouteSlow;
+  if (is_long) sc.order_long[atomicAdd(sc.n_long, 1u)] = (int32_t)s;
 }
 
 // The warp-cooperative path: every warp takes documents in table order (neighbours in time write neighbouring parts
@@ -175,6 +192,7 @@ __global__ void __launch_bounds__(Caps::kWarps * 32) ingest_fast_kernel(const in
     drawn = __shfl_sync(0xffffffffu, drawn, 0);
     if ((int64_t)drawn >= n_take) break;
     const int64_t s = kFromList ? (int64_t)sc.order[drawn] : (int64_t)drawn;
+    if (!kFill && !kFromList && sc.route[s] == jf::kRouteLong) continue;  // the walk has it already
     if (kFill) {
       const uint8_t route = sc.route[s];
       if (kFromList) {  // the roomy configuration parses again what only it could take and the pool had no room for
@@ -204,11 +222,12 @@ template <bool kFill>
 __global__ void __launch_bounds__(kIngestThreads, kFill ? 8 : 10) ingest_walk_kernel(const int64_t* __restrict__ doc_offsets,
                                                                       const uint8_t* __restrict__ text, int64_t n_docs,
                                                                       IngestScratch sc, uint8_t* __restrict__ doc_status,
-                                                                      IngestOut out, const uint32_t* __restrict__ list_len) {
+                                                                      IngestOut out, const int32_t* __restrict__ order,
+                                                                      const uint32_t* __restrict__ list_len,
+                                                                      unsigned long long* __restrict__ next) {
   const Pow5Table pow5{g_pow5_dev};
-  // list_len: the walk takes the list of what both configurations of the warp path declined
-  const int32_t* __restrict__ order = list_len ? sc.order_big : sc.order;
-  // list_len: `order` is the list of what the warp path declined (in no particular order), not all the documents
+  // list_len: `order` is a list of some documents (in no particular order) — what the warp path declined, or the long
+  // documents; nullptr: all the documents by length class (the walk alone)
   const int64_t n_order = list_len ? (int64_t)*list_len : n_docs;
   uint32_t cnt[kPlanes];
   DocWalker<kFill> w;
@@ -218,7 +237,7 @@ __global__ void __launch_bounds__(kIngestThreads, kFill ? 8 : 10) ingest_walk_ke
     int r = kDocRunning;
     // the warp (all its lanes are between documents here) draws 32 places of the order at once
     unsigned long long base = 0;
-    if ((threadIdx.x & 31) == 0) base = atomicAdd(sc.next_doc + (kFill ? 1 : 0), 32ull);
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(next, 32ull);
     base = __shfl_sync(0xffffffffu, base, 0);
     const int64_t drawn = (int64_t)base + (threadIdx.x & 31);
     if (!exhausted) {
@@ -483,8 +502,12 @@ IngestScratch carve(void* scratch, int64_t n_docs) {
   sc.rec.cursor = sc.next_fast + 3;
   sc.next_big = sc.next_fast + 4;
   sc.n_slow_big = (uint32_t*)(sc.next_fast + 6);
-  p += 64;
+  sc.n_long = (uint32_t*)(sc.next_fast + 7);
+  sc.next_long = sc.next_fast + 8;
+  p += 96;
   sc.order_big = (int32_t*)p;
+  p += 4 * (uint64_t)stride;
+  sc.order_long = (int32_t*)p;
   p += 4 * (uint64_t)stride;
   sc.route = p;
   p += (uint64_t)stride;  // a multiple of 32
@@ -582,15 +605,71 @@ int ingest_set_warp_path(int on) {
 }
 cudaError_t ingest_read_declined(const void* scratch, int64_t n_docs, unsigned int* out, cudaStream_t stream) {
   IngestScratch sc = carve(const_cast<void*>(scratch), n_docs);
-  cudaError_t e = cudaMemcpyAsync(out, sc.n_slow_big, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);  // declined twice
+  unsigned int twice = 0, too_long = 0;  // declined by both configurations; never offered to them
+  cudaError_t e = cudaMemcpyAsync(&twice, sc.n_slow_big, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
   if (e != cudaSuccess) return e;
-  return cudaStreamSynchronize(stream);
+  e = cudaMemcpyAsync(&too_long, sc.n_long, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(stream);
+  *out = twice + too_long;
+  return e;
 }
 
 uint64_t ingest_scratch_bytes(int64_t n_docs) {
   const int64_t stride = ((n_docs > 0 ? n_docs : 1) + 31) & ~(int64_t)31;
   return (uint64_t)kPlanes * stride * 4 + ((uint64_t)kPlanes * scan_blocks(n_docs) + 1) * 8 + 64 + 4 * (kOrderBuckets + 2) +
-         8 * (uint64_t)stride + 64 + (uint64_t)stride + (sizeof(jf::DocRec) + 8ull * jf::kPoolUnitsPerDoc) * (uint64_t)stride;
+         12 * (uint64_t)stride + 96 + (uint64_t)stride + (sizeof(jf::DocRec) + 8ull * jf::kPoolUnitsPerDoc) * (uint64_t)stride;
+}
+
+// The walk of the long documents runs beside the warp path on a stream of the library's own: fork after the routes
+// are known, join before what follows reads the planes / the table.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+};
+SideStream g_side;
+std::mutex g_side_mutex;
+
+cudaError_t side_fork(cudaStream_t main, cudaStream_t* side) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!g_side.stream || g_side.device != dev) {
+    if (g_side.stream) {
+      cudaStreamDestroy(g_side.stream);
+      cudaEventDestroy(g_side.fork);
+      cudaEventDestroy(g_side.join);
+      g_side = SideStream();
+    }
+    e = cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    g_side.device = dev;
+  }
+  e = cudaEventRecord(g_side.fork, main);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamWaitEvent(g_side.stream, g_side.fork, 0);
+  *side = g_side.stream;
+  return e;
+}
+cudaError_t side_join(cudaStream_t main) {
+  cudaError_t e = cudaEventRecord(g_side.join, g_side.stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamWaitEvent(main, g_side.join, 0);
+}
+
+void ingest_release() {  // pie_release(): the side stream and its events
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  if (g_side.stream) {
+    cudaStreamDestroy(g_side.stream);
+    cudaEventDestroy(g_side.fork);
+    cudaEventDestroy(g_side.join);
+  }
+  g_side = SideStream();
 }
 
 cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint8_t* doc_status, int64_t* totals,
@@ -606,15 +685,25 @@ cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint
   ++g_launches;
   if (n > 0) {
     if (warp_path_enabled()) {
-      // the warp path takes every document it can decide: first with the lists nearly every document fits, then — what
-      // that declined — with the roomy ones; what is declined twice goes on sc.order_big for the walk
+      // the documents too long for the warp path are known from their lengths: the walk takes them on the side stream
+      // while the warp path takes every document it can decide — first with the lists nearly every document fits, then,
+      // what that declined, with the roomy ones; what is declined twice goes on sc.order_big for a second walk
+      std::lock_guard<std::mutex> lock(g_side_mutex);
+      ingest_route_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(docs.offsets, n, sc);
+      cudaStream_t side = nullptr;
+      e = side_fork(stream, &side);
+      if (e != cudaSuccess) return e;
+      ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, side>>>(docs.offsets, docs.data, n, sc, doc_status,
+                                                                            IngestOut{}, sc.order_long, sc.n_long, sc.next_long);
       e = launch_fast<false, jf::CapsSmall, false>(docs, sc, doc_status, IngestOut{}, stream);
       if (e != cudaSuccess) return e;
       e = launch_fast<false, jf::CapsBig, true>(docs, sc, doc_status, IngestOut{}, stream);
       if (e != cudaSuccess) return e;
       ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, doc_status,
-                                                                              IngestOut{}, sc.n_slow_big);
-      ++g_launches;
+                                                                              IngestOut{}, sc.order_big, sc.n_slow_big, sc.next_doc);
+      g_launches += 3;
+      e = side_join(stream);
+      if (e != cudaSuccess) return e;
     } else {
       const unsigned doc_blocks = (unsigned)((n + 255) / 256);
       ingest_order_count_kernel<<<doc_blocks, 256, 0, stream>>>(docs.offsets, n, sc);
@@ -622,7 +711,7 @@ cudaError_t launch_ingest_measure(const pie_json_docs& docs, void* scratch, uint
       ingest_order_place_kernel<<<doc_blocks, 256, 0, stream>>>(docs.offsets, n, sc);
       g_launches += 3;
       ingest_walk_kernel<false><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, doc_status,
-                                                                              IngestOut{}, nullptr);
+                                                                              IngestOut{}, sc.order, nullptr, sc.next_doc);
       ++g_launches;
     }
     ingest_scan_sums_kernel<<<nblk, kScanThreads, 0, stream>>>(sc, n, nblk);
@@ -649,21 +738,32 @@ cudaError_t launch_ingest_fill(const pie_json_docs& docs, const void* scratch, c
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(sc.next_big + 1, 0, 8, stream);
   if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(sc.next_long + 1, 0, 8, stream);
+  if (e != cudaSuccess) return e;
   IngestOut out = make_out(table);
   out.text = docs.data;
   if (n > 0 && warp_path_enabled()) {
     // both kernels write the table's columns directly (the walk's entry rows are for when it takes every document)
     out.rows = nullptr;
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    cudaStream_t side = nullptr;
+    e = side_fork(stream, &side);
+    if (e != cudaSuccess) return e;
+    ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, side>>>(docs.offsets, docs.data, n, sc, const_cast<uint8_t*>(doc_status),
+                                                                         out, sc.order_long, sc.n_long, sc.next_long + 1);
     e = launch_fast<true, jf::CapsSmall, false>(docs, sc, const_cast<uint8_t*>(doc_status), out, stream);
     if (e != cudaSuccess) return e;
     e = launch_fast<true, jf::CapsBig, true>(docs, sc, const_cast<uint8_t*>(doc_status), out, stream);
     if (e != cudaSuccess) return e;
-    ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc,
-                                                                           const_cast<uint8_t*>(doc_status), out, sc.n_slow_big);
+    ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, const_cast<uint8_t*>(doc_status),
+                                                                           out, sc.order_big, sc.n_slow_big, sc.next_doc + 1);
+    ++g_launches;
+    e = side_join(stream);
+    if (e != cudaSuccess) return e;
   } else if (n > 0) {
     out.rows = static_cast<EntryRow*>(fill_scratch);
-    ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc,
-                                                                           const_cast<uint8_t*>(doc_status), out, nullptr);
+    ingest_walk_kernel<true><<<walk_blocks(n), kIngestThreads, 0, stream>>>(docs.offsets, docs.data, n, sc, const_cast<uint8_t*>(doc_status),
+                                                                           out, sc.order, nullptr, sc.next_doc + 1);
     if (table.n_entries > 0) {
       ingest_rows_to_columns_kernel<<<(unsigned)((table.n_entries + 255) / 256), 256, 0, stream>>>(out.rows, table.n_entries, out);
       ++g_launches;

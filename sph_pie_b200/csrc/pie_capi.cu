@@ -1634,6 +1634,7 @@ int pie_release(void) {
   free_out(g_pipe.out[1]);
   free_out(g_pipe.off[0]);
   free_out(g_pipe.off[1]);
+  pie::ingest_release();
   free_out(g_ingest_out);
   free_out(g_ingest_rows);
   free_out(g_json_csv);

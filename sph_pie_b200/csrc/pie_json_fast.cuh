@@ -97,7 +97,8 @@ constexpr int kLaneCopy = 16;    // pass 2 with records: the same (lanes copying
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kAllEntryKeys = 0x1ffffu;  // the 17 keys of an entry
 constexpr uint32_t kPosMask = 0x3fffu;
-constexpr uint8_t kRouteSlow = 0, kRouteFast = 1, kRouteRecords = 2, kRouteFastBig = 3;  // Big: pass 2 parses it again with CapsBig
+constexpr uint8_t kRouteSlow = 0, kRouteFast = 1, kRouteRecords = 2, kRouteFastBig = 3,  // Big: pass 2 parses it again with CapsBig
+                  kRouteLong = 4;  // too long for the warp path: the walk's, known before pass 1 starts
 
 // Stage 1 leaves two lists, so that stage 2 never searches: the quotes that open or close a string in text order
 // (string i is the pair 2 i, 2 i + 1), and the members by their colons with what stage 2 would otherwise look up.

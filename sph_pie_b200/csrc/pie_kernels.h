@@ -67,6 +67,7 @@ cudaError_t launch_ingest_measure(const pie_json_docs& dev_docs, void* scratch, 
 // value; on unless PIE_INGEST_WARP_PATH=0 is in the environment); how many documents of the last measure on
 // `scratch` the warp path declined (they took the thread-per-document walk)
 int ingest_set_warp_path(int on);
+void ingest_release();  // what the ingest holds beyond the caller's buffers (a stream and two events)
 cudaError_t ingest_read_declined(const void* scratch, int64_t n_docs, unsigned int* out, cudaStream_t stream);
 uint64_t ingest_fill_scratch_bytes(int64_t n_entries);
 cudaError_t launch_ingest_fill(const pie_json_docs& dev_docs, const void* scratch, const uint8_t* doc_status,
