@@ -20,7 +20,7 @@ GROUPS = {
     "export_rows_json": ["export_rows_kernel<json>"],
     # the default path: a warp per document (the walk kernels it launches beside them find an empty list on the bench's
     # documents; their large launches in the list are those of the walk timed alone)
-    "ingest": ["ingest_init_kernel", "ingest_fast_kernel<measure>", "ingest_scan_sums_kernel", "ingest_scan_blocks_kernel",
+    "ingest": ["ingest_init_kernel", "ingest_route_kernel", "ingest_fast_kernel<measure>", "ingest_scan_sums_kernel", "ingest_scan_blocks_kernel",
                "ingest_scan_apply_kernel", "ingest_fast_kernel<fill>"],
     "ingest_walk_alone": ["ingest_order_count_kernel", "ingest_order_scan_kernel", "ingest_order_place_kernel", "ingest_init_kernel",
                           "ingest_walk_kernel<measure>", "ingest_scan_sums_kernel", "ingest_scan_blocks_kernel",
