@@ -498,6 +498,9 @@ def main():
     # show_archive.data texts, repeated on the device to the bench's number of shows
     # (N = 1 only, like the CPU baseline: it is reported by rank 0 and would only add pinned memory on the others)
     ingest = ingest_leg(args, dev, S, n_payload_runs, note) if world == 1 else None
+    # N > 1: the device-resident part only (every rank ingests its own replica of the documents: the path partitions by
+    # document, no collective), max over ranks
+    ingest_multi = ingest_multi_leg(args, dev, S, n_payload_runs, world) if world > 1 else None
 
     note("payload rows, live metrics and JSON ingest timed; end-to-end leg (host buffers)")
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
@@ -684,7 +687,7 @@ def main():
                     "achieved_gbs": gbs(payload_bytes, payload_ms), "frac": gbs(payload_bytes, payload_ms) / peak,
                     "entries_per_s": E / (payload_ms * 1e-3)},
                 "JSON ingest of stored documents (ingest_fast_kernel x2 + ingest_walk_kernel x2 + scans, not part of the step)":
-                    dict(ingest, frac=ingest["achieved_gbs"] / peak, traffic=ingest_traffic) if ingest else None,
+                    dict(ingest, frac=ingest["achieved_gbs"] / peak, traffic=ingest_traffic) if ingest else ingest_multi,
                 "schemaVersion 2 show payloads (payload_measure_kernel + scan + payload_write_kernel, not part of the step)":
                     dict(widened["show_payloads"], frac=widened["show_payloads"]["achieved_gbs"] / peak),
                 "provider maintenance (get_timestamps + _archiveDailyShows + _purgeExpiredArchives decisions, not part of the step)":
@@ -780,6 +783,47 @@ def widened_leg(table, dev, S, E, runs, tz):
                         "what": "pie_get_timestamps_dev + pie_archive_due_dev + pie_archive_expired_dev, S-sized "
                                 "(no per-entry work), through the Python operators incl. their allocations and one status read-back"},
     }
+
+
+def ingest_multi_leg(args, dev, n_shows, runs, world):
+    """N > 1: pie_ingest_measure_dev + pie_ingest_fill_dev on every rank's own copy of the bench's documents (CUDA events
+    per rank, max over ranks; the aggregate is N times the documents over that time: replicas, no collective)."""
+    import torch
+    import torch.distributed as dist
+
+    from sph_pie_b200 import ops
+    from sph_pie_b200.synth import synth_stored_docs
+
+    sample = min(n_shows, 8192)
+    copies = max(1, n_shows // sample)
+    docs, n_entries, text_bytes, _ = synth_stored_docs(sample, copies, dev, seed=4321)
+    bufs = ops.IngestBuffers(docs.n_docs, dev)
+    ops.ingest_measure_dev(docs, bufs)
+    totals = bufs.totals.cpu().tolist()
+    assert bufs.status.cpu().tolist()[0] == 0
+    table = ops.alloc_ingest_table(docs.n_docs, totals, dev)
+    table_bytes = table.nbytes()
+    for _ in range(2):
+        ops.ingest_measure_dev(docs, bufs)
+        ops.ingest_fill_dev(docs, bufs, table)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev[0].record()
+    for _ in range(runs):
+        ops.ingest_measure_dev(docs, bufs)
+        ops.ingest_fill_dev(docs, bufs, table)
+    ev[1].record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]) / runs], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    del docs, bufs, table
+    return {"ms_per_launch": ms, "documents_per_rank": sample * copies, "entries_per_rank": n_entries, "ranks": world,
+            "entries_per_s": world * n_entries / (ms * 1e-3), "text_gbs": world * text_bytes / (ms * 1e-3) / 1e9,
+            "achieved_gbs": world * (text_bytes + table_bytes) / (ms * 1e-3) / 1e9,
+            "what": "device-resident texts, every rank its own replica of the bench's documents, max over ranks; the host "
+                    "legs, the parity check and the second workload are reported at N = 1"}
 
 
 def ingest_leg(args, dev, n_shows, runs, note):
