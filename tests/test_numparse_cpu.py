@@ -100,3 +100,39 @@ def test_halfway_and_boundaries(numparse):
         for m in ("1", "9.999999999999999", "1.0000000000000002", "4.4501477170144023"):
             texts.append(f"{m}e{e}")
     assert check(numparse, texts, allow_undecided=0.01) <= 80
+
+
+def test_numbers_of_the_shape_the_warp_path_defers_are_always_decided(numparse):
+    """The warp-per-document ingest (csrc/pie_json_fast.cuh, number_shape) only CHECKS in its first pass that a number has
+    no exponent part and at most 19 digits in all, and leaves the conversion to the second pass, which can no longer
+    decline a document: the parser must never answer "undecided" for such a number.  (No digit is dropped at <= 19
+    digits, and the Eisel-Lemire product is only undecided for powers of ten outside 10^-27 .. 10^55.)"""
+    rng = np.random.default_rng(29)
+    texts = []
+    for _ in range(60000):
+        digits = int(rng.integers(1, 20))
+        body = "".join(str(int(d)) for d in rng.integers(0, 10, digits))
+        cut = int(rng.integers(0, digits + 1))  # digits before the point
+        ip, fp = body[:cut], body[cut:]
+        ip = ip.lstrip("0") or "0"
+        if ip == "0" and cut > 1:
+            continue  # the stripped zeros would no longer count as digits of the text: keep the total honest
+        t = ip + ("." + fp if fp else "")
+        if rng.random() < 0.3:
+            t = "-" + t
+        texts.append(t)
+    # the worst cases for a truncated product: digit strings around powers of two and the halfway points between doubles
+    for e in range(0, 64):
+        for d in (-1, 0, 1):
+            v = 2 ** e + d
+            if 0 < v < 10 ** 19:
+                texts.append(str(v))
+                s = str(v)
+                for cut in (1, len(s) // 2, len(s) - 1):
+                    if 0 < cut < len(s):
+                        texts.append(s[:cut] + "." + s[cut:])
+    texts += ["9999999999999999999", "0.9999999999999999999"[:21], "1844674407370955161.5", "0.000000000000000001",
+              "9007199254740993", "9007199254740992.5", "4503599627370496.5", "4503599627370497.5"]
+    texts = [t for t in texts if sum(c.isdigit() for c in t) <= 19]
+    assert len(texts) > 50000
+    assert check(numparse, texts, allow_undecided=0.0) == 0
