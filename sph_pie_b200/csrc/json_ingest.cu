@@ -3,22 +3,28 @@
 // `rows.map(row => this._mapArchiveRow(row)).filter(Boolean)` (sqlProvider.js:230-234, :892-926: JSON.parse, drop
 // what is not an object) followed by the projection on the table's schema (columnar.py pack_shows) does.
 //
-// A document is ~0.4 KB per entry of sequential grammar; 2^20 of them are independent.  So: ONE THREAD WALKS ONE
-// DOCUMENT AT A TIME with a complete ECMA-404 recogniser (strings with every escape and UTF-8 validation, numbers,
-// literals, nesting checked against a 64-level kind stack) written as a resumable state machine
-// (pie_json_walk.cuh): a step is one token, or up to 8 bytes of a string found with word-wide byte tests.  The
-// kernels are persistent, and documents are handed out by LENGTH CLASS, 32 neighbours of that order to a warp at a
-// time: documents of one length are almost always of one make, and lanes that start them together walk them roughly
-// in step.  The text is read through the read-only path 8 aligned bytes at a time with the next word in flight.
+// Two passes with a scan between them, because the caller allocates the table from what pass 1 counted.  Round 2: A WARP
+// TAKES A DOCUMENT (pie_json_fast.cuh: structural index by SIMD-in-register byte classes and ballots, member-parallel
+// projection) when it is of the shape the provider writes itself, and hands every other document to the walk of round
+// 1, in which ONE THREAD WALKS ONE DOCUMENT with a complete ECMA-404 recogniser written as a resumable state machine
+// (pie_json_walk.cuh) — the only place that reports errors.  Results are identical whichever takes a document.
 //
-//   order   ingest_order_*              counting sort of the documents by length
-//   pass 1  ingest_walk_kernel<false>   per document: entries, items of crew / actions, unescaped bytes of each of the
-//                                       23 string heaps — one 104-byte row; syntax errors make the document a dropped
-//                                       row (all counts zero)
-//   scan    ingest_scan_*               exclusive prefix sums of the 26 counts over the documents, in place; totals
-//   pass 2  ingest_walk_kernel<true>    the same walk (same template) with every counter started at its prefix:
-//                                       unescaped bytes in place, one 96-byte row per entry (offsets, numbers)
-//           ingest_rows_to_columns      the entry rows into the table's entry columns, coalesced
+//   pass 1  ingest_route_kernel                 documents over 16 KB -> the walk's list at once (side stream, see below)
+//           ingest_fast_kernel<false, Small>    a warp per document: validates, counts into the document's 104-byte row of
+//                                               26 counts, leaves records for pass 2 (where every value is and where it
+//                                               goes) in a pool of the scratch area; what it declines -> list
+//           ingest_fast_kernel<false, Big>      the same with roomy lists, over that list (documents of 8.5 - 16 KB)
+//           ingest_walk_kernel<false>           what both declined (pretty-printed text, entries without a key, ...); and,
+//                                               on a stream of the library's own beside the three above, the long documents
+//   scan    ingest_scan_*                       exclusive prefix sums of the 26 counts over the documents, in place; totals
+//   pass 2  ingest_fast_kernel<true, Small>     documents with records: a scatter (no index, no keys, no grammar; numbers
+//                                               are converted here); without (pool full, the last document): parsed again
+//           ingest_fast_kernel<true, Big>       the latter for the roomy configuration's documents
+//           ingest_walk_kernel<true>            the walk's documents, the same walk with every counter started at its prefix
+//
+// With pie_debug_ingest_warp_path(0) the walk takes everything, as in round 1: documents handed out by LENGTH CLASS
+// (ingest_order_*: a counting sort; lanes that start documents of one length together walk them roughly in step), one
+// 96-byte row per entry in pass 2 and ingest_rows_to_columns to turn the rows into the entry columns.
 //
 // Restrictions that fail loudly (pie_status in the status word, first offending document): a text field that is not
 // a string / null, delaySec that is not a number / null, a string with a lone surrogate escape (pack_shows raises

@@ -8,12 +8,14 @@
 //            a byte-transposed copy of the lane's 32 bytes (so that the per-word flags merge into 32-bit position
 //            masks by shifts, without a movemask per word), escaped characters by the carry trick of simdjson's
 //            stage 1 with the carry passed between lanes, quote parity by prefix-xor + ballot, bracket depth /
-//            entry index / colon index by warp scans.  Masks (quotes, brackets, escape starts) and the list of the
-//            colons stay in shared memory.
-//   stage 2  member-parallel projection (lane = one `"key":value` member, found by its colon): key by two 64-bit
-//            compares, value by its first byte; lengths of the text values are ranked per heap in document order
-//            (match_any + shuffles), copied lane-parallel (short) or by the whole warp (long); numbers and escaped
-//            strings are queued and converted with all lanes busy at the end of the document.
+//            entry index / colon and quote counts by warp scans.  It leaves two lists in shared memory, so that stage
+//            2 never searches: the quotes in text order (each with "an escape starts between the quote before and this
+//            one"), and the members by their colons (with the key's closing quote and the entry they are in).
+//   stage 2  member-parallel projection (lane = one `"key":value` member): key by one probe of a perfect hash and a
+//            16-byte compare, value by its first byte; lengths of the text values are ranked per heap in document
+//            order (match_any + shuffles).  Pass 1 checks, counts and writes down what it learnt as records (where
+//            every value is and where it goes; of a number only that its shape is one the parser always decides);
+//            pass 2 of a document with records is a scatter that converts the numbers on its way.
 //
 // The path decides ONLY documents of the shape the provider writes (sqlProvider.js:361-409 _normalizeShow /
 // _normalizeEntry through JSON.stringify, :682 / :696):
