@@ -97,3 +97,28 @@ def test_synth_is_deterministic_and_well_formed():
         o = c.offsets
         assert o[0] == 0 and bool((o[1:] >= o[:-1]).all()) and int(o[-1]) == c.data.numel()
     assert int(a.entry_offsets[-1]) == a.n_entries
+
+
+def test_launch_list_kernel_names():
+    """scripts/traffic_from_launches.py groups an ncu launch list by kernel: the names ncu prints for kernels in an
+    unnamed namespace, with bool / class template arguments, must land in the groups bench.py reads the traffic of."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("traffic_from_launches", os.path.join(ROOT, "scripts", "traffic_from_launches.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cases = {
+        "void pie::<unnamed>::ingest_fast_kernel<(bool)0, pie::jf::CapsSmall, (bool)0>(const long *, const unsigned char *, long, pie::<unnamed>::IngestScratch, unsigned char *, pie::jw::IngestOut)": "ingest_fast_kernel<measure>",
+        "void pie::<unnamed>::ingest_fast_kernel<(bool)1, pie::jf::CapsBig, (bool)1>(const long *, const unsigned char *, long, pie::<unnamed>::IngestScratch, unsigned char *, pie::jw::IngestOut)": "ingest_fast_kernel<fill>",
+        "void pie::<unnamed>::ingest_walk_kernel<(bool)1>(const long *, const unsigned char *, long, pie::<unnamed>::IngestScratch, unsigned char *, pie::jw::IngestOut, const int *, const unsigned int *, unsigned long long *)": "ingest_walk_kernel<fill>",
+        "pie::<unnamed>::ingest_init_kernel(pie::<unnamed>::IngestScratch)": "ingest_init_kernel",
+        "pie::<unnamed>::ingest_route_kernel(const long *, long, pie::<unnamed>::IngestScratch)": "ingest_route_kernel",
+        "void pie::(anonymous namespace)::export_rows_kernel<false>(pie_archive_view, pie::RowTable)": "export_rows_kernel<csv>",
+        "void pie::<unnamed>::export_rows_kernel<(bool)1>(pie_archive_view, pie::<unnamed>::RowTable)": "export_rows_kernel<json>",
+        "pie::<unnamed>::show_stats_kernel(pie_archive_view, int *, double *, long)": "show_stats_kernel",
+    }
+    for full, want in cases.items():
+        assert mod.kernel_name(full) == want, (full, mod.kernel_name(full))
+    for group, names in mod.GROUPS.items():
+        assert len(set(names)) == len(names), group
+    assert "ingest_fast_kernel<measure>" in mod.GROUPS["ingest"] and "ingest_fast_kernel<fill>" in mod.GROUPS["ingest"]
