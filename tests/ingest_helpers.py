@@ -164,3 +164,54 @@ def stored_doc(show, rng=None, style="stringify"):
             return v
         return json.dumps(shuffle(show), ensure_ascii=False, separators=(", ", " : "))
     raise ValueError(style)
+
+
+# ---- the warp-per-document path built for the host (its lanes as fibers) -----------------------------------------
+_fast = None
+ROUTE_SLOW, ROUTE_FAST, ROUTE_RECORDS, ROUTE_FAST_BIG, ROUTE_LONG = 0, 1, 2, 3, 4
+
+
+def fast_host():
+    global _fast
+    if _fast is None:
+        src = os.path.join(HERE, "native", "fast_host.cpp")
+        so = os.path.join(HERE, "native", "libfast_host.so")
+        csrc = os.path.join(HERE, "..", "sph_pie_b200", "csrc")
+        deps = [src, os.path.join(HERE, "native", "cuda_shim", "cuda_runtime.h")]
+        deps += [os.path.join(csrc, f) for f in ("pie_json_fast.cuh", "pie_json_walk.cuh", "pie_numparse.cuh", "pie_device.cuh",
+                                                 "pow5_128_table.h")]
+        deps.append(os.path.join(HERE, "..", "include", "sph_pie_b200.h"))
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(HERE, "native", "cuda_shim"),
+                                   "-o", so, src])
+        _fast = C.CDLL(so)
+    return _fast
+
+
+def fast_host_ingest(docs, pool_units_per_doc=288):
+    """The DEVICE code of the warp-per-document ingest run on the CPU (32 lanes = 32 fibers), driven like json_ingest.cu:
+    (table | None, doc_status, (pie_status, document), routes)."""
+    lib = fast_host()
+    offs, data = docs_to_buffers(docs)
+    # the device code reads the aligned 32-byte words that hold a document: room before and behind the text
+    pad = np.zeros(len(data) + 96, dtype=np.uint8)
+    base = 64 - (pad.ctypes.data % 32) % 32
+    pad[base:base + len(data)] = data
+    text = pad[base:]
+    n = len(docs)
+    rows = np.zeros((max(n, 1), _lib.PIE_INGEST_TOTALS), dtype=np.uint32)
+    doc_status = np.zeros(max(n, 1), dtype=np.uint8)
+    routes = np.zeros(max(n, 1), dtype=np.uint8)
+    totals = np.zeros(_lib.PIE_INGEST_TOTALS, dtype=np.int64)
+    status = np.zeros(2, dtype=np.int32)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    rc = lib.fast_host_measure(p(text), p(offs), C.c_int64(n), p(rows), p(doc_status), p(totals), p(status), p(routes),
+                               C.c_int(pool_units_per_doc))
+    assert rc == 0, "the lanes of a warp disagreed on a document"
+    if status[0] != 0:
+        return None, doc_status[:n], (int(status[0]), int(status[1])), routes[:n]
+    table = empty_table(n, totals.tolist())
+    view = table.view()
+    rc = lib.fast_host_fill(p(text), p(offs), C.c_int64(n), p(rows), p(doc_status), C.byref(view))
+    assert rc == 0, f"pass 2 of the warp path failed ({rc})"
+    return table, doc_status[:n], (0, -1), routes[:n]

@@ -11,7 +11,8 @@ import torch
 
 import oracle_c
 import pie_oracle as po
-from ingest_helpers import assert_tables_equal, host_ingest, oracle_ingest, stored_doc
+from ingest_helpers import (ROUTE_FAST, ROUTE_FAST_BIG, ROUTE_LONG, ROUTE_RECORDS, ROUTE_SLOW, assert_tables_equal, fast_host_ingest,
+                            host_ingest, oracle_ingest, stored_doc)
 from sph_pie_b200 import _lib
 from sph_pie_b200.synth import synth_archive, table_to_shows
 
@@ -42,13 +43,20 @@ def hostile_show(rng, n_entries):
 
 
 def check(docs, what=""):
-    """Three implementations on the same texts: the Python oracle (json module + packer), the C oracle (recursive
-    descent + strtod, oracle/pie_oracle.c) and the kernels' walk built for the host."""
+    """Four implementations on the same texts: the Python oracle (json module + packer), the C oracle (recursive
+    descent + strtod, oracle/pie_oracle.c), the kernels' thread-per-document walk built for the host, and the kernels'
+    warp-per-document path built for the host (its 32 lanes as fibers; with the records its first pass leaves for the
+    second, and without them, when the second pass parses again)."""
     ref_table, ref_status = oracle_ingest(docs)
     table, status, err = host_ingest(docs)
     assert err == (0, -1), (what, err)
     assert np.array_equal(status, ref_status), f"{what} doc_status"
     assert_tables_equal(table, ref_table, what)
+    for pool in (288, 0):
+        ftable, fstatus, ferr, _ = fast_host_ingest(docs, pool_units_per_doc=pool)
+        assert ferr == (0, -1), (what, ferr)
+        assert np.array_equal(fstatus, ref_status), f"{what} doc_status (warp path, pool {pool})"
+        assert_tables_equal(ftable, ref_table, f"{what} warp path, pool {pool}")
     for threads in (1, 3):
         ctable, cstatus, cerr = oracle_c.ingest(docs, nthreads=threads)
         assert cerr == (0, -1), (what, cerr)
@@ -146,17 +154,83 @@ UNSUPPORTED_DOCS = [
 ]
 
 
+def test_warp_path_on_the_cpu_routes_and_damage():
+    """The device code of the warp-per-document path, run on the CPU: which documents it takes (by route), and that
+    whatever it takes of damaged documents of the provider's shape is what the oracle makes of them."""
+    from sph_pie_b200.synth import synth_archive, table_to_shows
+    import torch
+
+    def canonical(n, seed, max_entries=21):
+        host = synth_archive(n, seed=seed, missing_created_frac=0.1, max_entries=max_entries)
+        lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+        host.delay_valid[lost] = 0
+        return table_to_shows(host)
+
+    rng = random.Random(12)
+    shows = canonical(60, 31, max_entries=70)
+    docs = [stored_doc(s, rng, "stringify") for s in shows]
+    sizes = [len(d.encode()) for d in docs]
+    _, _, err, routes = fast_host_ingest(docs)
+    assert err == (0, -1)
+    for d, n, sh, r in zip(docs, sizes, shows, routes.tolist()[:-1]):  # (the last document is always parsed twice)
+        if n <= 8000:
+            assert r == ROUTE_RECORDS, (n, r)
+        elif 9500 <= n <= 15500 and len(sh["entries"]) <= 63:
+            assert r in (ROUTE_RECORDS, ROUTE_FAST_BIG), (n, r)
+        elif n > 16500:
+            assert r == ROUTE_LONG, (n, r)
+    assert routes[-1] in (ROUTE_FAST, ROUTE_FAST_BIG, ROUTE_LONG, ROUTE_SLOW)
+    check(docs, "canonical, long documents among them")
+    pretty = [stored_doc(s, rng, "pretty") for s in shows[:8]]
+    assert set(fast_host_ingest(pretty)[3].tolist()) <= {ROUTE_SLOW, ROUTE_LONG}
+    # with a pool too small for all of them, the later documents are parsed again by the second pass
+    _, _, _, routes = fast_host_ingest(docs[:20], pool_units_per_doc=60)
+    assert ROUTE_RECORDS in routes.tolist() and (ROUTE_FAST in routes.tolist() or ROUTE_FAST_BIG in routes.tolist())
+    # damage: every prefix of one document, single-character edits of several
+    small = [d for d, n in zip(docs, sizes) if n < 2500]
+    damaged = []
+    if small:
+        doc = small[0]
+        damaged += [doc[:k] for k in range(len(doc) + 1)]
+    alphabet = '"\\{}[]:,0-9.eE+tfn ux\n\t\x01a\u00e9'
+    for doc in [d for d, n in zip(docs, sizes) if n < 9000][:12]:
+        for _ in range(120):
+            k = rng.randrange(len(doc))
+            damaged.append(doc[:k] + rng.choice(alphabet) + doc[k + 1:])
+        for _ in range(20):
+            k = rng.randrange(len(doc))
+            damaged.append(doc[:k] + doc[k + 1:])
+            damaged.append(doc[:k] + rng.choice(alphabet) + doc[k:])
+    keep = []
+    for d in damaged:
+        try:
+            oracle_ingest([d])
+            keep.append(d)
+        except (TypeError, po.UnsupportedJson):
+            _, _, err, _ = fast_host_ingest([d])
+            assert err[0] in (_lib.PIE_ERR_SCHEMA, _lib.PIE_ERR_UNSUPPORTED_JSON), (d[:80], err)
+    assert len(keep) > 1500
+    ref_table, ref_status = oracle_ingest(keep)
+    table, status, err, routes = fast_host_ingest(keep)
+    assert err == (0, -1)
+    assert np.array_equal(status, ref_status)
+    assert_tables_equal(table, ref_table, "damaged canonical documents, warp path on the CPU")
+    assert (routes == ROUTE_RECORDS).sum() > 100  # damage inside a value leaves the shape alone: the warp path decides those
+
+
 def test_schema_and_unsupported_documents_fail_loudly():
     good = '{"id":"fine","entries":[{"id":"e"}]}'
     for d in SCHEMA_DOCS:
         with pytest.raises(TypeError):
             oracle_ingest([good, d])
+        assert fast_host_ingest([good, d, good, '{"id":7}'])[2] == host_ingest([good, d, good, '{"id":7}'])[2], d
         _, _, err = host_ingest([good, d, good, '{"id":7}'])
         assert err == (_lib.PIE_ERR_SCHEMA, 1), (d, err)
         assert oracle_c.ingest([good, d, good, '{"id":7}'])[2] == (_lib.PIE_ERR_SCHEMA, 1), d
     for d in UNSUPPORTED_DOCS:
         with pytest.raises(po.UnsupportedJson):
             oracle_ingest([good, good, d])
+        assert fast_host_ingest([good, good, d, '{"id":7}'])[2] == host_ingest([good, good, d, '{"id":7}'])[2], d
         _, _, err = host_ingest([good, good, d, '{"id":7}'])
         assert err == (_lib.PIE_ERR_UNSUPPORTED_JSON, 2), (d, err)
         assert oracle_c.ingest([good, good, d, '{"id":7}'])[2] == (_lib.PIE_ERR_UNSUPPORTED_JSON, 2), d
