@@ -188,16 +188,45 @@ def fast_host():
     return _fast
 
 
-def fast_host_ingest(docs, pool_units_per_doc=288):
+def _guarded_text(data: np.ndarray, nbytes: int, guard: str, shift: int):
+    """The text in pages of its own between two pages that must not be touched: guard = 'end': the aligned 32-byte word
+    that holds the last byte ends where the forbidden page starts; 'start': the one that holds the first byte starts
+    where the forbidden page ends.  shift (0..31): where in its 32-byte word that byte sits."""
+    import mmap
+
+    page = mmap.PAGESIZE
+    body = (nbytes + 64 + page - 1) // page * page
+    m = mmap.mmap(-1, body + 2 * page)
+    addr = C.addressof(C.c_char.from_buffer(m))
+    libc = C.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    assert libc.mprotect(addr, page, 0) == 0 and libc.mprotect(addr + page + body, page, 0) == 0
+    if guard == "end":
+        # the last byte sits `shift` bytes before the end of its 32-byte word, and that word ends at the forbidden page
+        end = page + body - shift
+        start = end - nbytes
+    else:
+        start = page + shift
+    view = np.frombuffer(m, dtype=np.uint8)
+    view[start:start + nbytes] = data[:nbytes]
+    return m, view[start:]
+
+
+def fast_host_ingest(docs, pool_units_per_doc=288, guard=None, shift=0):
     """The DEVICE code of the warp-per-document ingest run on the CPU (32 lanes = 32 fibers), driven like json_ingest.cu:
-    (table | None, doc_status, (pie_status, document), routes)."""
+    (table | None, doc_status, (pie_status, document), routes).  guard: see _guarded_text (a read outside the aligned
+    32-byte words that hold the documents kills the process)."""
     lib = fast_host()
     offs, data = docs_to_buffers(docs)
-    # the device code reads the aligned 32-byte words that hold a document: room before and behind the text
-    pad = np.zeros(len(data) + 96, dtype=np.uint8)
-    base = 64 - (pad.ctypes.data % 32) % 32
-    pad[base:base + len(data)] = data
-    text = pad[base:]
+    keep = None
+    if guard:
+        keep, text = _guarded_text(data, int(offs[-1]), guard, shift)
+    else:
+        # the device code reads the aligned 32-byte words that hold a document: room before and behind the text
+        pad = np.zeros(len(data) + 96, dtype=np.uint8)
+        base = 64 - (pad.ctypes.data % 32) % 32
+        pad[base:base + len(data)] = data
+        text = pad[base:]
     n = len(docs)
     rows = np.zeros((max(n, 1), _lib.PIE_INGEST_TOTALS), dtype=np.uint32)
     doc_status = np.zeros(max(n, 1), dtype=np.uint8)

@@ -3,6 +3,7 @@ tests/native/ingest_host.cpp, against the oracle: pie_oracle.map_archive_row (JS
 reference server/storage/sqlProvider.js:892-926; Python's json module is the parser) + the table packer.  Bit-exact
 tables.  The same cases run on the GPU in tests/test_gpu_ingest.py; this file needs no GPU."""
 import json
+import os
 import random
 
 import numpy as np
@@ -216,6 +217,46 @@ def test_warp_path_on_the_cpu_routes_and_damage():
     assert np.array_equal(status, ref_status)
     assert_tables_equal(table, ref_table, "damaged canonical documents, warp path on the CPU")
     assert (routes == ROUTE_RECORDS).sum() > 100  # damage inside a value leaves the shape alone: the warp path decides those
+
+
+def test_warp_path_reads_only_the_words_that_hold_the_documents():
+    """The warp path reads the text 32 aligned bytes at a time (the walk: 8).  Run on the CPU with a forbidden page right
+    behind the aligned 32-byte word that holds the last byte of the text, and right before the one that holds the first
+    byte, at several positions of that byte in its word: a read outside kills the (child) process.  A negative control
+    proves that the forbidden pages are."""
+    import subprocess
+    import sys
+
+    body = """
+import sys, random, ctypes
+sys.path[:0] = [%r, %r, %r]
+import torch
+from ingest_helpers import fast_host_ingest, oracle_ingest, assert_tables_equal, stored_doc, _guarded_text
+from sph_pie_b200.synth import synth_archive, table_to_shows
+import numpy as np
+if sys.argv[1] == "control":
+    m, text = _guarded_text(np.zeros(100, dtype=np.uint8), 100, "end", 0)
+    ctypes.string_at(text.ctypes.data + 100, 1)  # the first byte of the forbidden page
+    sys.exit(0)
+rng = random.Random(3)
+host = synth_archive(14, seed=5, missing_created_frac=0.1)
+lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+host.delay_valid[lost] = 0
+docs = [stored_doc(s, rng, "stringify") for s in table_to_shows(host)] + ['{"id":"x"}', ' {"id": "pretty"} ', '{"id":"\\u00e9"}']
+ref, ref_status = oracle_ingest(docs)
+for guard in ("end", "start"):
+    for shift in (0, 1, 7, 8, 9, 15, 16, 24, 31):
+        for pool in (288, 0):
+            table, status, err, routes = fast_host_ingest(docs, pool_units_per_doc=pool, guard=guard, shift=shift)
+            assert err == (0, -1) and np.array_equal(status, ref_status)
+            assert_tables_equal(table, ref, guard)
+print("ok")
+""" % (os.path.dirname(os.path.abspath(__file__)), os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"),
+       os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    control = subprocess.run([sys.executable, "-c", body, "control"], capture_output=True, text=True)
+    assert control.returncode < 0, "the forbidden page can be read: the guard does not guard"
+    run = subprocess.run([sys.executable, "-c", body, "run"], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.strip().endswith("ok"), (run.returncode, run.stderr[-2000:])
 
 
 def test_schema_and_unsupported_documents_fail_loudly():
