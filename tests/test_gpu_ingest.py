@@ -98,6 +98,27 @@ def test_long_documents_take_the_roomy_lists(cuda):
         ops.set_ingest_warp_path(old)
 
 
+def test_structural_variants_of_the_providers_documents(cuda, both_paths):
+    """The CPU test's documents (a key missing / twice / renamed / reordered, a value of another type, foreign nesting,
+    lists of other things than strings) on the GPU: the same table as the oracle's, and what the oracle refuses fails
+    the call with the same status whichever path takes the document."""
+    texts = cases.structural_variant_texts()
+    keep = []
+    for t in texts:
+        try:
+            oracle_ingest([t])
+            keep.append(t)
+        except (TypeError, po.UnsupportedJson):
+            pass
+    gpu_check(cuda, keep, "structural variants", host_too=False)
+    refused = [t for t in texts if t not in set(keep)][:40]
+    good = keep[0]
+    for t in refused:
+        with pytest.raises((_lib.SchemaError, _lib.UnsupportedJsonError)) as ei:
+            ops.ingest_json(ops.JsonDocs.from_texts([good, t, good]).to(cuda))
+        assert ei.value.doc == 1
+
+
 def test_record_pool_under_pressure(cuda):
     """Pass 1 leaves records for pass 2 in a pool sized for average documents (288 x 8 bytes each): a batch of nothing
     but the largest documents overflows it, the documents that find it full are parsed again by pass 2 — same table."""

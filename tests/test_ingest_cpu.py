@@ -219,6 +219,87 @@ def test_warp_path_on_the_cpu_routes_and_damage():
     assert (routes == ROUTE_RECORDS).sum() > 100  # damage inside a value leaves the shape alone: the warp path decides those
 
 
+def structural_variant_texts():
+    """Documents of the provider's shape with one structural change each (see the test below)."""
+    import copy
+
+    rng = random.Random(77)
+    host = synth_archive(30, seed=41, missing_created_frac=0.1, max_entries=6)
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
+    host.delay_valid[lost] = 0
+    shows = [s for s in table_to_shows(host) if s["entries"]]
+    other_values = [0, -1.5, 1e21, 12345678901234567890123, None, True, False, [], {}, ["a"], [1], [None], {"a": 1}, {"a": {"b": []}}, "",
+                    "text", "\u00e9\"\\", [[]], [{}], ["a", ["b"]], 1e-7, "1700000000000", "2024-01-01T00:00:00Z"]
+
+    def variants(show):
+        out = []
+        for _ in range(40):
+            sh = copy.deepcopy(show)
+            target = sh if rng.random() < 0.35 else rng.choice(sh["entries"])
+            keys = list(target)
+            what = rng.randrange(8)
+            if what == 0:
+                del target[rng.choice(keys)]
+            elif what == 1:
+                target[rng.choice(keys)] = copy.deepcopy(rng.choice(other_values))
+            elif what == 2:
+                target[rng.choice(["extra", "x", "showNumber", "Notes", "iD", "delaysec", "actions2"])] = copy.deepcopy(rng.choice(other_values))
+            elif what == 3:
+                rng.shuffle(keys)
+                for k in keys:
+                    target[k] = target.pop(k)
+            elif what == 4:
+                k = rng.choice(keys)
+                target[k + rng.choice(["", "_", "é"])[:1] or "k"] = target.pop(k)
+            elif what == 5:
+                sh["entries"] = rng.choice([[], None, {}, "x", 3, [{}], [None], [1, {}], sh["entries"] + [{}], [[]], sh["entries"] * 2])
+            elif what == 6:
+                sh["crew"] = rng.choice([None, [], ["A"], ["A", None], [1], "x", {}, [["A"]], ["A", "B", "C"] * 3])
+            else:
+                e = rng.choice(sh["entries"])
+                e["actions"] = rng.choice([None, [], ["a", None], [1], "x", {}, [["a"]], ["a"] * 7, [{"a": 1}]])
+            out.append(sh)
+        return out
+
+    texts = []
+    for show in shows[:12]:
+        for v in variants(show):
+            texts.append(po.js_json_stringify(v))
+            # a member twice: splice a copy of the text of one member behind itself
+            if rng.random() < 0.15:
+                t = texts[-1]
+                k = t.find('"status":"')
+                if k > 0:
+                    end = t.find(",", k)
+                    texts.append(t[:end + 1] + t[k:end + 1] + t[end + 1:])
+    return texts
+
+
+def test_structural_variants_of_the_providers_documents():
+    """Documents of the provider's shape with ONE structural change each — a key missing, twice, renamed, reordered; a value
+    of another type (number, null, boolean, list, object) where text / a number / a list belongs; nesting under a foreign
+    key; lists with other things than strings; empty objects and lists — through all four implementations.  This is where
+    a recogniser that decides only one shape could accept what it must not: whatever the warp path takes must be what
+    the oracle makes of it, and what the oracle refuses must fail the same way on both of the kernels' paths."""
+    texts = structural_variant_texts()
+    assert len(texts) > 450
+    keep, refused = [], 0
+    for t in texts:
+        try:
+            oracle_ingest([t])
+            keep.append(t)
+        except (TypeError, po.UnsupportedJson):
+            refused += 1
+            walk_err = host_ingest([t])[2]
+            warp_err = fast_host_ingest([t])[2]
+            assert walk_err[0] in (_lib.PIE_ERR_SCHEMA, _lib.PIE_ERR_UNSUPPORTED_JSON), (t[:120], walk_err)
+            assert warp_err == walk_err, (t[:120], warp_err, walk_err)
+    assert refused > 30 and len(keep) > 250
+    check(keep, "structural variants")
+    routes = fast_host_ingest(keep)[3]
+    assert (routes == ROUTE_RECORDS).sum() > 20 and (routes == ROUTE_SLOW).sum() > 50  # both decide their share
+
+
 def test_warp_path_reads_only_the_words_that_hold_the_documents():
     """The warp path reads the text 32 aligned bytes at a time (the walk: 8).  Run on the CPU with a forbidden page right
     behind the aligned 32-byte word that holds the last byte of the text, and right before the one that holds the first
