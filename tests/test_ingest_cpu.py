@@ -300,6 +300,64 @@ def test_structural_variants_of_the_providers_documents():
     assert (routes == ROUTE_RECORDS).sum() > 20 and (routes == ROUTE_SLOW).sum() > 50  # both decide their share
 
 
+def test_warp_path_at_the_brims_of_its_lists():
+    """Documents that fill a list of the warp path exactly, and by one more: quotes (1472 / 3584), members (480 / 1152),
+    numbers (64 / 128), lists with elements (32 / 64), entries (63), bytes (16 KB).  One over the small configuration's
+    brim is the roomy one's document, one over that the walk's — and the table is the oracle's every time."""
+    entry_keys = ["id", "ts", "unitId", "planned", "launched", "status", "primaryIssue", "subIssue", "otherDetail", "severity",
+                  "rootCause", "actions", "operator", "batteryId", "delaySec", "commandRx", "notes"]
+
+    def entry(i, actions=(), text=""):
+        e = {k: text for k in entry_keys}
+        e.update(id="e%d" % i if text is not None else None, ts=1700000000000 + i if text is not None else i, delaySec=None,
+                 actions=list(actions))
+        return e
+
+    docs, expect = [], []
+
+    def add(show, routes):
+        docs.append(po.js_json_stringify(show))
+        expect.append(routes)
+
+    both = (ROUTE_RECORDS, ROUTE_FAST, ROUTE_FAST_BIG)
+    # numbers: unknown keys with numeric values at the show's level
+    for n, routes in ((64, (ROUTE_RECORDS, ROUTE_FAST)), (65, both), (128, both), (129, (ROUTE_SLOW,))):
+        add({("n%d" % i): i for i in range(n)}, routes)
+    # strings: 2 quotes for a key, 2 for a string value
+    for strings, routes in ((736, (ROUTE_RECORDS, ROUTE_FAST)), (737, both), (1792, both), (1793, (ROUTE_SLOW,))):
+        show = {("k%d" % i): "v" for i in range(strings // 2)}
+        if strings % 2:
+            show["odd"] = 1
+        add(show, routes)
+    # members
+    for members, routes in ((480, (ROUTE_RECORDS, ROUTE_FAST)), (481, both), (1152, both), (1153, (ROUTE_SLOW,))):
+        add({("m%d" % i): None for i in range(members)}, routes)
+    # entries, and entries whose actions hold an element
+    for n, routes in ((20, (ROUTE_RECORDS, ROUTE_FAST)), (40, both), (57, both), (58, (ROUTE_SLOW,))):  # 62 quotes an entry
+        add({"id": "s", "entries": [entry(i) for i in range(n)]}, routes)
+    for n, routes in ((63, both), (64, (ROUTE_SLOW, ROUTE_LONG))):  # null texts: the entry index (or the 16 KB) is what runs out
+        add({"id": "s", "entries": [entry(i, text=None) for i in range(n)]}, routes)
+    # lists with elements: an entry is 17 members, so the members (480 / 1152) run out before the list of lists (32 / 64)
+    # can: 28 entries are the small configuration's, 29 the roomy one's, and both still leave records
+    for n, routes in ((28, (ROUTE_RECORDS,)), (29, (ROUTE_RECORDS,)), (40, (ROUTE_RECORDS,))):
+        add({"id": "s", "entries": [entry(i, ["go"], text=None) for i in range(n)]}, routes)
+    # bytes: one long text value up to the 16 KB a warp takes (less the 31 bytes its alignment may cost)
+    for n, routes in ((8000, both), (16000, both), (16300, (ROUTE_RECORDS, ROUTE_FAST, ROUTE_FAST_BIG, ROUTE_LONG)), (16500, (ROUTE_LONG,))):
+        add({"id": "s", "notes": "x" * (n - 22)}, routes)
+    docs.append('{"id":"the last document is parsed twice"}')
+    expect.append((ROUTE_FAST,))
+    got = fast_host_ingest(docs, pool_units_per_doc=4000)[3].tolist()  # (a pool that does not run out: that is another test)
+    for d, r, want in zip(docs, got, expect):
+        assert r in want, (len(d), d[:60], r, want)
+    check(docs, "brims")
+    # and each of them alone, i.e. as the last document of its batch (no records: the second pass parses it again)
+    for d in docs[:-1]:
+        ref_table, ref_status = oracle_ingest([d])
+        table, status, err, routes = fast_host_ingest([d])
+        assert err == (0, -1) and np.array_equal(status, ref_status)
+        assert_tables_equal(table, ref_table, d[:40])
+
+
 def test_warp_path_reads_only_the_words_that_hold_the_documents():
     """The warp path reads the text 32 aligned bytes at a time (the walk: 8).  Run on the CPU with a forbidden page right
     behind the aligned 32-byte word that holds the last byte of the text, and right before the one that holds the first
