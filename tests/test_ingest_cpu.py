@@ -219,12 +219,13 @@ def test_warp_path_on_the_cpu_routes_and_damage():
     assert (routes == ROUTE_RECORDS).sum() > 100  # damage inside a value leaves the shape alone: the warp path decides those
 
 
-def structural_variant_texts():
-    """Documents of the provider's shape with one structural change each (see the test below)."""
+def structural_variant_texts(seed=77, archive_seed=41):
+    """Documents of the provider's shape with one structural change each (see the test below; scripts/fuzz_ingest_cpu.py
+    runs it with other seeds)."""
     import copy
 
-    rng = random.Random(77)
-    host = synth_archive(30, seed=41, missing_created_frac=0.1, max_entries=6)
+    rng = random.Random(seed)
+    host = synth_archive(30, seed=archive_seed, missing_created_frac=0.1, max_entries=6)
     lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)
     host.delay_valid[lost] = 0
     shows = [s for s in table_to_shows(host) if s["entries"]]
