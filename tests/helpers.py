@@ -73,3 +73,21 @@ def assert_daily_match_py_oracle(shows, daily, tz):
             for k, name in ((_lib.DF_AVERAGE, "average"), (_lib.DF_MIN, "min"), (_lib.DF_MAX, "max")):
                 got = float(sf[k][m][g]) if n else None
                 assert same_value(want[name], got), (g, key, name, want[name], got)
+
+
+def build_c_consumer() -> str:
+    """tests/native/c_consumer.c — a plain C99 program over include/sph_pie_b200.h with malloc'd buffers only — built
+    with -Wall -Wextra -Werror -pedantic against the in-tree library; returns the path of the executable."""
+    import os
+    import subprocess
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    src, exe = os.path.join(here, "native", "c_consumer.c"), os.path.join(here, "native", "c_consumer")
+    lib = os.path.join(root, "sph_pie_b200", "libsphpie_b200.so")
+    deps = [src, os.path.join(root, "include", "sph_pie_b200.h"), lib]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["gcc", "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Wextra", "-Werror", "-pedantic", "-O1",
+                               "-I", os.path.join(root, "include"), "-o", exe, src, "-L", os.path.dirname(lib), "-lsphpie_b200",
+                               "-Wl,-rpath," + os.path.dirname(lib)])
+    return exe

@@ -97,3 +97,44 @@ def test_release_and_reuse(cuda):
     _lib.check(lib.pie_release())
     table, status = ops.ingest_json(docs)
     assert table.n_entries == 1 and status.tolist() == [0]
+
+
+def test_plain_c_caller_from_stored_texts(cuda, tmp_path):
+    """tests/native/c_consumer.c: a C99 program with nothing but malloc'd (pageable) buffers hands the provider's stored
+    texts (one JSON.stringify(show) per line) to pie_archive_step_json_host and writes the CSV rows, the statistics
+    planes and the dropped-row flags: byte for byte what the C oracle makes of the same shows."""
+    import json
+    import subprocess
+
+    import numpy as np
+    import oracle_c
+    from helpers import build_c_consumer
+    from sph_pie_b200.columnar import pack_shows
+    from sph_pie_b200.synth import table_to_shows
+
+    host = synth_archive(2500, seed=61, shuffle_days=True)
+    lost = host.delay_valid.bool() & ~torch.isfinite(host.delay_sec)  # JSON.stringify writes NaN / Infinity as null
+    host.delay_valid[lost] = 0
+    host.delay_sec[lost] = 0.0
+    shows = table_to_shows(host)
+    texts = [json.dumps(s, ensure_ascii=False, separators=(",", ":")) for s in shows]
+    for k, junk in ((7, "not json"), (300, ""), (1999, '"a string"'), (2400, '{"id":"cut')):  # rows the reference maps to null
+        shows[k], texts[k] = None, junk
+    assert not any("\n" in t for t in texts)
+    path = tmp_path / "docs.jsonl"
+    path.write_bytes(("\n".join(texts) + "\n").encode("utf-8"))
+    exe = build_c_consumer()
+    r = subprocess.run([exe, str(path), "-300", str(tmp_path / "out")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    ref = pack_shows(shows)
+    ref_offsets, ref_csv = oracle_c.csv_rows(ref)
+    ref_stats, ref_daily, rc, _ = oracle_c.archive_analytics(ref, tz_offset_minutes=-300)
+    assert rc == 0
+    n_docs, n_entries, csv_bytes, n_groups, dropped = (int(x) for x in r.stdout.split())
+    assert (n_docs, n_entries, csv_bytes, dropped) == (len(texts), ref.n_entries, int(ref_offsets[-1]), 4)
+    assert n_groups == ref_daily.n_groups
+    assert (tmp_path / "out.csv").read_bytes() == bytes(ref_csv.numpy())
+    status = np.frombuffer((tmp_path / "out.status").read_bytes(), dtype=np.uint8)
+    assert status.nonzero()[0].tolist() == [7, 300, 1999, 2400]
+    stats = np.frombuffer((tmp_path / "out.stats_i32").read_bytes(), dtype=np.int32).reshape(_lib.PIE_SI_COUNT, n_docs)
+    assert np.array_equal(stats, ref_stats.i32.numpy())

@@ -47,6 +47,26 @@ def test_no_gpu_means_loud_failure(built):
         computeArchiveShowStats({"entries": []})
 
 
+def test_plain_c_caller_builds_and_fails_loudly_without_a_gpu(built, tmp_path):
+    """include/sph_pie_b200.h is C99, and a C program with malloc'd buffers links and calls the library (the drop-in
+    boundary is the C ABI, not the ctypes binding); without a device it stops with the library's message, exit 3."""
+    import subprocess
+
+    from helpers import build_c_consumer
+
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c",
+                           os.path.join(ROOT, "include", "sph_pie_b200.h")])
+    exe = build_c_consumer()
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: tests/test_gpu_abi_errors.py runs the program")
+    docs = tmp_path / "docs.jsonl"
+    docs.write_text('{"id":"a","entries":[{"id":"e"}]}\n')
+    r = subprocess.run([exe, str(docs), "0", str(tmp_path / "out")], capture_output=True, text=True)
+    assert r.returncode == 3, (r.returncode, r.stderr)
+    assert "pie_init(0) = %d" % _lib.PIE_ERR_NO_DEVICE in r.stderr and "no CPU fallback" in r.stderr
+    assert not (tmp_path / "out.csv").exists()
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "sph_pie_b200")
     for dirpath, _, files in os.walk(pkg):
