@@ -625,3 +625,29 @@ def test_archive_maintenance_oracle_rules():
             {"data": '{"createdAt":"2024-01-01T00:00:00.000Z"}'}]                    # Date.parse
     assert po.purge_expired_archives_decision(rows, d(2024, 3, 1)) == [True, True, True, False, True]
     assert po.purge_expired_archives_decision(rows, d(2024, 3, 1) - 1) == [False, False, True, False, False]
+
+
+def test_add_months_against_the_calendar_of_pythons_datetime():
+    """_addMonths (sqlProvider.js:999-1009) restated with days_from_civil arithmetic, against an independent calendar:
+    Python's datetime.  setMonth(getMonth() + 2) in a fixed-offset zone is "the first of the month two months on, plus
+    (day of the month - 1) days, at the same local time of day" (MakeDay carries a day past the month's end over)."""
+    import datetime as dt
+
+    rng = random.Random(23)
+    epoch = dt.datetime(1970, 1, 1)
+    for _ in range(20000):
+        tz = rng.choice([0, -480, 330, 765, -720, 60, -210])
+        y, m = rng.randrange(1800, 2400), rng.randrange(1, 13)
+        if rng.random() < 0.5:  # the last days of a month, where the overflow happens
+            first_next = dt.datetime(y + m // 12, m % 12 + 1, 1)
+            local = first_next - dt.timedelta(days=rng.randrange(1, 5), milliseconds=rng.randrange(0, 86400000))
+        else:
+            local = dt.datetime(y, m, 1) + dt.timedelta(milliseconds=rng.randrange(0, 31 * 86400000))
+        m0 = local.month - 1 + 2
+        first = dt.datetime(local.year + m0 // 12, m0 % 12 + 1, 1)
+        want_local = first + dt.timedelta(days=local.day - 1, hours=local.hour, minutes=local.minute, seconds=local.second,
+                                          microseconds=local.microsecond)
+        to_ms = lambda t: (t - epoch) // dt.timedelta(milliseconds=1) - tz * 60000  # noqa: E731
+        t, want = float(to_ms(local)), float(to_ms(want_local))
+        assert po.add_months(t, 2, tz) == want, (local, tz, po.add_months(t, 2, tz), want)
+        assert po.is_archive_expired(t, want, tz) and not po.is_archive_expired(t, want - 1, tz)
