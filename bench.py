@@ -645,7 +645,11 @@ def main():
         if tj.get("shows") == S and grp:
             traffic = grp["dram_bytes_read"] + grp["dram_bytes_write"]
             traffic_kernels = grp["kernels"]
-            traffic_current = tj.get("csrc_sha16") == entry.csrc_sha16()
+            # current = the capture was taken on the sources THIS group's kernels are compiled from (csv_rows.cu and what it
+            # includes, same flags); another translation unit may have changed since (csrc_sha16 is the whole tree)
+            per_group = tj.get("group_src_sha16", {}).get("export_rows_csv")
+            traffic_current = (per_group == entry.group_src_sha16("export_rows_csv")) if per_group else \
+                (tj.get("csrc_sha16") == entry.csrc_sha16())
             ig = tj.get("groups", {}).get("ingest")
             ingest_traffic = ig["dram_bytes_read"] + ig["dram_bytes_write"] if ig else None
 

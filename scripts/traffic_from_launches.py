@@ -94,6 +94,7 @@ def main():
                          "--clock-control none on `python bench.py --steps 3 --warmup 3`; per-launch averages over the "
                          "launches on the bench workload (ncu times are cold-cache and serialised: shares, not absolutes)",
                "shows": shows, "csrc_sha16": entry.csrc_sha16(),
+               "group_src_sha16": {g: entry.group_src_sha16(g) for g in entry.TRAFFIC_GROUP_SOURCES},
                "kernels": dict(sorted(out.items(), key=lambda kv: -kv[1]["time_us"])), "groups": groups},
               open(dst, "w"), indent=1)
 

@@ -110,3 +110,149 @@ def test_show_payload_oracle_on_the_fixture_and_its_rules():
     p = json.loads(po.show_payload_json("e", nan_show, "t", "u", "m"))
     assert p["table"]["rows"][0][21] is None and p["entries"][1]["delaySec"] is None
     assert p["csv"]["rows"][0].split(",")[21] == "NaN" and p["csv"]["rows"][1].split(",")[21] == "Infinity"
+
+
+# ---- the DEVICE code of the show payload, run on the CPU (tests/native/payload_host.cpp) --------------------------------
+ENTRY_KEYS = ["id", "ts", "unitId", "planned", "launched", "status", "primaryIssue", "subIssue", "otherDetail", "severity",
+              "rootCause", "actions", "operator", "batteryId", "delaySec", "commandRx", "notes"]  # sqlProvider.js:386-408
+
+
+def normalised(show):
+    """The shape _normalizeShow / _normalizeEntry store (key order included)."""
+    out = dict(show)
+    out["entries"] = [{k: e.get(k, [] if k == "actions" else "" if k not in ("ts", "delaySec") else None) for k in ENTRY_KEYS}
+                      for e in show.get("entries", [])]
+    return out
+
+
+_payload_host = None
+
+
+def payload_host_bodies(shows, event, at, url, method, meta=None, use_stage=1):
+    """(bodies, shows that went through the shared-memory stage, status) of pie_show_payload.cuh run on the CPU: its 32
+    lanes as fibers, driven like show_payload.cu (measure, exclusive sum, write)."""
+    import ctypes as C
+    import subprocess
+
+    import numpy as np
+    from sph_pie_b200 import webhook
+    from sph_pie_b200.columnar import pack_shows
+
+    global _payload_host
+    if _payload_host is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        src, so = os.path.join(here, "native", "payload_host.cpp"), os.path.join(here, "native", "libpayload_host.so")
+        csrc = os.path.join(here, "..", "sph_pie_b200", "csrc")
+        deps = [src, os.path.join(here, "native", "cuda_shim", "cuda_runtime.h"), os.path.join(here, "..", "include", "sph_pie_b200.h")]
+        deps += [os.path.join(csrc, f) for f in ("pie_show_payload.cuh", "pie_device.cuh", "pie_numfmt.cuh", "ryu_tables.h")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(here, "native", "cuda_shim"),
+                                   "-o", so, src])
+        _payload_host = C.CDLL(so)
+    lib = _payload_host
+    table = pack_shows(shows)
+    head, tail = webhook.payload_frame(event, at, url, method, meta)
+    view = table.view()
+    n = table.n_shows
+    offs = np.zeros(n + 1, dtype=np.int64)
+    staged, status = C.c_int64(0), np.zeros(2, dtype=np.int32)
+    h, t = np.frombuffer(head or b"\0", dtype=np.uint8).copy(), np.frombuffer(tail or b"\0", dtype=np.uint8).copy()
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    args = (C.byref(view), p(h), C.c_int(len(head)), p(t), C.c_int(len(tail)), p(offs))
+    rc = lib.payload_host(*args, None, C.c_uint64(0), C.c_int(use_stage), C.byref(staged), p(status))
+    assert rc == 0, rc
+    if status[0]:
+        return None, staged.value, status.tolist()
+    total, guard = int(offs[-1]), 64
+    out = np.full(total + 2 * guard, 0xEE, dtype=np.uint8)
+    rc = lib.payload_host(*args, C.c_void_p(out.ctypes.data + guard), C.c_uint64(total), C.c_int(use_stage), C.byref(staged), p(status))
+    assert rc == 0, rc
+    assert (out[:guard] == 0xEE).all() and (out[guard + total:] == 0xEE).all(), "bytes written outside the documents"
+    blob, o = bytes(out[guard:guard + total]), offs.tolist()
+    return [blob[o[i]:o[i + 1]].decode("utf-8") for i in range(n)], staged.value, status.tolist()
+
+
+def _check_payload_host(shows, event="show.updated", at="2024-07-05T04:00:00.000Z", url="https://hooks.example/pie?x=1&y=\"2\"",
+                        method="POST", meta=None, staged_at_least=None):
+    want = [po.show_payload_json(event, normalised(s) if isinstance(s, dict) else {}, at, url, method,
+                                 meta if meta is not None else po.UNDEFINED) for s in shows]
+    for use_stage in (1, 0):
+        bodies, staged, status = payload_host_bodies(shows, event, at, url, method, meta, use_stage)
+        assert status == [0, -1]
+        assert staged == 0 if not use_stage else staged >= (len(shows) if staged_at_least is None else staged_at_least)
+        for i, (body, w) in enumerate(zip(bodies, want)):
+            assert body == w, (use_stage, i)
+    return want
+
+
+def test_show_payload_device_code_on_the_cpu_synthetic_archive():
+    import random
+
+    shows = [normalised(s) for s in table_to_shows(synth_archive(250, seed=3, missing_created_frac=0.1))]
+    rng = random.Random(3)
+    for s in shows:
+        s["updatedAt"] = rng.choice([None, 1704067200000.5, 0, True, False, 1e21, -0.0])
+        if rng.random() < 0.3:
+            s["deletedAt"] = rng.choice([None, 1704067200001.0, float("inf")])
+    want = _check_payload_host(shows, meta={"automation": {"source": "daily-archive", "totalShows": 250, "showIndex": 0, "showId": None}})
+    for w in want[:20]:
+        json.loads(w)
+
+
+def test_show_payload_device_code_on_the_cpu_hostile_strings_and_edge_shapes():
+    import random
+
+    rng = random.Random(7)
+    alphabet = ['"', ",", "\n", "\r", "\\", "\t", "\b", "\f", "\x00", "\x1f", "|", "é", "漢", "🚁", " ", "a", "B", "7", "'", "/", "{", "]"]
+    t = lambda: "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 40)))
+    shows = []
+    for i in range(150):
+        show = {"id": t(), "date": t(), "time": t(), "label": t(), "crew": [t() for _ in range(rng.randrange(0, 4))],
+                "leadPilot": t(), "monkeyLead": t(), "notes": t(), "createdAt": rng.choice([None, 1.5, 1e-7, 123456789012345680000.0]),
+                "entries": []}
+        for _ in range(rng.randrange(0, 5)):
+            show["entries"].append({"id": t(), "ts": rng.choice([None, 0.0, 1704067200123.0]), "unitId": t(), "planned": t(),
+                                    "launched": t(), "status": rng.choice(["Completed", "Abort", "completed", t()]),
+                                    "primaryIssue": t(), "subIssue": t(), "otherDetail": t(), "severity": t(), "rootCause": t(),
+                                    "actions": [t() for _ in range(rng.randrange(0, 3))], "operator": t(), "batteryId": t(),
+                                    "delaySec": rng.choice([None, 0.0, -0.0, 12.5, 1e21, 1e-7, float("nan"), float("-inf"), 1 / 3]),
+                                    "commandRx": t(), "notes": t()})
+        shows.append(show)
+    shows += [{"entries": []}, None, {"id": "only a show", "crew": []}]
+    _check_payload_host(shows, "ev\"ent\n", "t", "u\\", "GET")
+    # cells at the brims of the one-round paths: 28 .. 33 plain bytes, and the same with one byte that needs an escape
+    brim = []
+    for n in range(26, 36):
+        for extra in ("", '"', ",", "\\", "\n", "é"):
+            text = ("x" * n + extra)[:n] if not extra else "x" * (n - 1) + extra
+            brim.append({"id": text, "label": text, "crew": [text], "entries": [{"id": text, "notes": text, "actions": [text], "status": "Completed",
+                                                                                  "rootCause": text, "delaySec": 0.5},
+                                                                                 {"unitId": text, "actions": [text, text], "delaySec": None}]})
+    _check_payload_host(brim)
+
+
+def test_show_payload_device_code_on_the_cpu_shows_that_do_not_fit_the_stage():
+    """More entries than number slots (33), more bytes than the stage holds (6 KB), both: the same documents either way."""
+    entry = lambda i, text="": {"id": "e%d" % i, "ts": 1704067200000.0 + i, "unitId": "u", "status": "Abort", "notes": text,
+                                "actions": ["a", "b"] if i % 3 == 0 else [], "delaySec": i / 7 if i % 2 else None}
+    shows = [{"id": "33 entries", "entries": [entry(i) for i in range(33)]},
+             {"id": "32 entries", "entries": [entry(i) for i in range(32)]},
+             {"id": "long notes", "notes": "n" * 7000, "entries": [entry(0, "m" * 100)]},
+             {"id": "many and long", "entries": [entry(i, "z" * 90) for i in range(70)]},
+             {"id": "just fits?", "entries": [entry(i, "y" * 150) for i in range(14)]},
+             {"id": "small", "entries": [entry(1)]}]
+    want = _check_payload_host(shows, staged_at_least=3)
+    bodies, staged, _ = payload_host_bodies(shows, "show.updated", "2024-07-05T04:00:00.000Z", "https://hooks.example/pie?x=1&y=\"2\"", "POST")
+    assert 3 <= staged < len(shows)  # the long ones were emitted from the caller's view
+    assert bodies == want
+
+
+def test_show_payload_device_code_on_the_cpu_schema_error():
+    bodies, _, status = payload_host_bodies([{"id": "ok"}, {"id": "x", "createdAt": "2024-01-01"}], "e", "t", "u", "m")
+    assert bodies is None and status == [_lib_codes().PIE_ERR_SCHEMA, 1]
+
+
+def _lib_codes():
+    from sph_pie_b200 import _lib
+
+    return _lib
