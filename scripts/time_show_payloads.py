@@ -56,25 +56,23 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / runs
     assert status.cpu().tolist()[0] == 0 and int(tot.cpu()) == total
-    # a sample against the oracle: the first 150 shows and 150 spread over the table
-    idx = sorted(set(list(range(min(150, S))) + [int(i * (S - 1) / 149) for i in range(150)]))
-    o = first.doc_offsets.cpu().tolist()
-    host = table.to("cpu")
-    equal = True
-    for i in idx:
-        show = table_to_shows(host.slice_shows(i, i + 1))[0]
-        show["entries"] = [{k: e.get(k, [] if k == "actions" else "" if k not in ("ts", "delaySec") else None) for k in ENTRY_KEYS}
-                           for e in show.get("entries", [])]
-        body = bytes(first.data[o[i]:o[i + 1]].cpu().numpy()).decode("utf-8")
-        if body != po.show_payload_json(*args[:1], show, *args[1:]):
-            equal = False
-            print("DIFFERS at show", i, flush=True)
-            break
     in_bytes = table.nbytes()
     print(json.dumps({"shows": S, "entries": table.n_entries, "json_bytes_out": total, "ms_per_call": ms,
                       "first_call_s_incl_alloc": first_s, "algorithmic_bytes": in_bytes + total + 8 * (S + 1),
                       "achieved_gbs": (in_bytes + total + 8 * (S + 1)) / (ms * 1e-3) / 1e9,
-                      "shows_per_s": S / (ms * 1e-3), "sample_equals_oracle": equal, "sampled": len(idx)}), flush=True)
+                      "shows_per_s": S / (ms * 1e-3)}), flush=True)
+    # parity of the same kernels on a SMALL table of its own (slices of the big one share its heaps: a per-show copy to the
+    # host would move the whole heap each time — that is what ate the last GPU seconds of round 2)
+    small = synth_archive(400, seed=1, device=dev)
+    docs = ops.show_payloads(small, head, tail).documents()
+    equal = True
+    for show, body in zip(table_to_shows(small.to("cpu")), docs):
+        show["entries"] = [{k: e.get(k, [] if k == "actions" else "" if k not in ("ts", "delaySec") else None) for k in ENTRY_KEYS}
+                           for e in show.get("entries", [])]
+        if body != po.show_payload_json(args[0], show, *args[1:]):
+            equal = False
+            break
+    print(json.dumps({"sample_equals_oracle": equal, "sampled": len(docs)}), flush=True)
 
 
 if __name__ == "__main__":
