@@ -100,3 +100,18 @@ def test_summary_mirror_and_schema_error(cuda):
     with pytest.raises(_lib.SchemaError) as e:
         ops.show_payloads(table, head, tail)
     assert "show 0" in e.value.message
+
+
+def test_shows_that_do_not_fit_the_stage(cuda):
+    """The kernels stage a show in 6 KB of shared memory and keep the numbers of up to 32 entries (pie_show_payload.cuh): more
+    entries than number slots, more bytes than the stage holds, both — emitted from global memory through the caller's
+    view, the same documents.  (Also run on the CPU: tests/test_payload_oracles_cpu.py.)"""
+    entry = lambda i, text="": {"id": "e%d" % i, "ts": 1704067200000.0 + i, "unitId": "u", "status": "Abort", "notes": text,
+                                "actions": ["a", "b"] if i % 3 == 0 else [], "delaySec": i / 7 if i % 2 else None}
+    shows = [{"id": "33 entries", "entries": [entry(i) for i in range(33)]},
+             {"id": "32 entries", "entries": [entry(i) for i in range(32)]},
+             {"id": "long notes", "notes": "n" * 7000, "entries": [entry(0, "m" * 100)]},
+             {"id": "many and long", "entries": [entry(i, "z" * 90) for i in range(70)]},
+             {"id": "just fits?", "entries": [entry(i, "y" * 150) for i in range(14)]},
+             {"id": "small", "entries": [entry(1)]}]
+    check([normalised(s) for s in shows])
