@@ -651,3 +651,66 @@ def test_add_months_against_the_calendar_of_pythons_datetime():
         t, want = float(to_ms(local)), float(to_ms(want_local))
         assert po.add_months(t, 2, tz) == want, (local, tz, po.add_months(t, 2, tz), want)
         assert po.is_archive_expired(t, want, tz) and not po.is_archive_expired(t, want - 1, tz)
+
+
+def test_date_parse_and_string_to_number_against_pythons_own():
+    """The Date.parse leg of _getTimestamp (sqlProvider.js:978-982) restated for the ECMA-262 date-time format, against an
+    independent implementation — Python's datetime — on random well-formed texts: date-only forms are UTC, a date-time without
+    an offset is local time of the fixed-offset zone, Z / +-HH:mm are honoured.  And StringToNumber (Number(value), :974)
+    against float() / int() on the spellings a stored document can hold."""
+    import datetime as dt
+
+    rng = random.Random(31)
+    epoch = dt.datetime(1970, 1, 1, tzinfo=dt.timezone.utc)
+    for _ in range(20000):
+        tz = rng.choice([0, -480, 330, 765, -720, 60])
+        y, mo = rng.randrange(1, 9999), rng.randrange(1, 13)
+        d = rng.randrange(1, po.days_in_month(y, mo) + 1)
+        h, mi, sec, ms = rng.randrange(24), rng.randrange(60), rng.randrange(60), rng.randrange(1000)
+        form = rng.randrange(4)
+        date = "%04d-%02d-%02d" % (y, mo, d)
+        if form == 0:
+            text, local, off = date, dt.datetime(y, mo, d), 0
+        else:
+            clock = "%02d:%02d" % (h, mi) + (":%02d" % sec if form >= 2 else "") + (".%03d" % ms if form == 3 else "")
+            local = dt.datetime(y, mo, d, h, mi, sec if form >= 2 else 0, (ms if form == 3 else 0) * 1000)
+            zone = rng.choice(["", "Z", "+05:30", "-08:00", "+00:00", "-11:45", "+14:00"])
+            text = date + "T" + clock + zone
+            off = tz if zone == "" else 0 if zone == "Z" else (1 if zone[0] == "+" else -1) * (int(zone[1:3]) * 60 + int(zone[4:6]))
+        want = (local.replace(tzinfo=dt.timezone.utc) - epoch) // dt.timedelta(milliseconds=1) - off * 60000
+        assert po.js_date_parse(text, tz) == float(want), (text, tz)
+        assert po.get_timestamp_tz(text, tz) == float(want)
+    assert np.isnan(po.js_date_parse("2024-13-01")) and np.isnan(po.js_date_parse("2024-01-01T25:00")) and np.isnan(po.js_date_parse("2024-01-01T10:60"))
+    assert po.js_date_parse("2024-01-01T24:00") == po.js_date_parse("2024-01-02") and np.isnan(po.js_date_parse("2024-01-01T24:00:01"))
+    for bad in ("2024-1-1", "01/02/2024", "2024-01-01 10:00", "2024-01-01T10", "Jan 1 2024", "2024-02-30"):
+        with pytest.raises(NotImplementedError):
+            po.js_date_parse(bad)
+    # StringToNumber
+    for _ in range(20000):
+        k = rng.randrange(6)
+        if k == 0:
+            body = str(rng.randrange(10 ** rng.randrange(1, 25)))
+        elif k == 1:
+            body = "%s.%s" % (rng.randrange(10 ** 6), rng.randrange(10 ** rng.randrange(1, 12)))
+        elif k == 2:
+            body = repr(rng.uniform(-1, 1) * 10.0 ** rng.randrange(-300, 300)).lstrip("-")
+        elif k == 3:
+            body = rng.choice([".5", "5.", "1e3", "1E-3", "0.1e+2", "00012", "1.e2", "Infinity"])
+        elif k == 4:
+            n = rng.randrange(1 << rng.randrange(1, 70))
+            base, prefix = rng.choice([(16, "0x"), (16, "0X"), (8, "0o"), (2, "0b"), (2, "0B")])
+            body = prefix + {16: "%x", 8: "%o", 2: "{:b}"}[base].replace("{:b}", "%s") % (n if base != 2 else bin(n)[2:])
+            want = float(n)
+            pad = rng.choice(["", " ", "\t\n", " ", "﻿", "　 "])
+            assert po.js_string_to_number(pad + body + pad) == want, body
+            continue
+        else:
+            body = rng.choice(["", " ", "abc", "1 2", "1,5", "0x", "0xg", "1e", "e5", "+-1", "--1", "1_000", "١٢", "infinity", "NaN", "+0x10", "-0b1"])
+            got = po.js_string_to_number(body)
+            assert (got == 0.0) if body.strip() == "" else np.isnan(got), body
+            continue
+        sign = rng.choice(["", "+", "-"])
+        pad = rng.choice(["", " ", "\r\n", " ", " "])
+        got = po.js_string_to_number(pad + sign + body + pad)
+        want = float(sign + body.replace("Infinity", "inf"))
+        assert got == want and np.copysign(1, got) == np.copysign(1, want), (sign, body, got, want)
