@@ -781,7 +781,10 @@ def widened_leg(table, dev, S, E, runs, tz):
                           "achieved_gbs": payload_bytes / (payload_ms * 1e-3) / 1e9, "shows_per_s": S / (payload_ms * 1e-3),
                           "entries_per_s": E / (payload_ms * 1e-3),
                           "what": "one call: measure pass + scan + write pass over every column; documents of ~"
-                                  f"{total // max(S, 1)} bytes"},
+                                  f"{total // max(S, 1)} bytes",
+                          "note": "kernels rebuilt in the last session of round 2 (a warp stages its show in shared memory, "
+                                  "pie_show_payload.cuh); their first version took 2198.8 ms on 2^20 shows "
+                                  "(profiles/bench_r02_h_final.json, profiles/show_payload_r02.md)"},
         "maintenance": {"ms_per_round": maint_ms, "shows_per_s": S / (maint_ms * 1e-3), "due": int(due.sum().cpu()),
                         "expired": int(expired.sum().cpu()),
                         "what": "pie_get_timestamps_dev + pie_archive_due_dev + pie_archive_expired_dev, S-sized "
